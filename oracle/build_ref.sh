@@ -1,0 +1,39 @@
+#!/usr/bin/env bash
+# Builds oracle/_ref/libgauss_ref.so from the reference's OWN sources where they lie
+# (/root/reference/src).  Test infrastructure only.  Outputs go to oracle/_ref/ (git-ignored,
+# NOT gpurun-ignored, so the prebuilt .so travels to the GPU box).  No reference source is
+# copied into the tracked tree: the hot-path functions are extracted by line range into
+# oracle/_ref/gen/*.inc at build time.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${GAUSS_REFERENCE_DIR:-/root/reference}"
+SRC="$REF/src"
+OUT="$HERE/_ref"
+if [ ! -d "$SRC" ]; then
+  echo "build_ref: $SRC not present; keeping any prebuilt $OUT/libgauss_ref.so" >&2
+  exit 0
+fi
+mkdir -p "$OUT/gen"
+cut_lines() { sed -n "$2,$3p" "$SRC/$1" > "$OUT/gen/$4"; }
+cut_lines util.cpp 49 70 util_49_70.inc            # CalCor(vector<string>, vector<string>)
+cut_lines util.cpp 103 124 util_103_124.inc        # CalWgtCov
+cut_lines gauss.cpp 18 35 gauss_18_35.inc          # Arguments::Arguments defaults
+cut_lines dist.cpp 129 227 dist_129_227.inc        # run_dist
+cut_lines distmix.cpp 138 253 distmix_138_253.inc  # run_distmix
+cut_lines computeLD.cpp 95 116 computeLD_95_116.inc
+# guard: the extraction must start/end on the expected function boundaries
+grep -q '^double CalCor(std::vector<std::string>& x, std::vector<std::string>& y){' "$OUT/gen/util_49_70.inc"
+grep -q '^double CalWgtCov(' "$OUT/gen/util_103_124.inc"
+grep -q '^void run_dist(' "$OUT/gen/dist_129_227.inc"
+grep -q '^void run_distmix(' "$OUT/gen/distmix_138_253.inc"
+grep -q '^Arguments::Arguments(){' "$OUT/gen/gauss_18_35.inc"
+CXXFLAGS="-O2 -fPIC -ffp-contract=off -w -I$HERE/ref_shim -I$SRC -I$HERE -I$OUT"
+gcc -O2 -fPIC -ffp-contract=off -c "$HERE/gauss_oracle.c" -o "$OUT/gauss_oracle_int.o" \
+    -Dgo_make_pos_def=gor_make_pos_def -Dgo_inv_full_piv_lu=gor_inv_full_piv_lu \
+    -Dgo_cal_cor=gor_cal_cor -Dgo_cal_wgt_cov=gor_cal_wgt_cov -Dgo_run_window=gor_run_window \
+    -Dgo_compute_ld=gor_compute_ld -Dgo_last_sample_pairs=gor_last_sample_pairs \
+    -Dgo_gram_counts=gor_gram_counts -Dgo_sym_eig=gor_sym_eig -Dgo_args_default=gor_args_default
+g++ $CXXFLAGS -c "$SRC/snp.cpp" -o "$OUT/snp.o"
+g++ $CXXFLAGS -c "$HERE/ref_glue.cpp" -o "$OUT/ref_glue.o"
+g++ -shared -o "$OUT/libgauss_ref.so" "$OUT/ref_glue.o" "$OUT/snp.o" "$OUT/gauss_oracle_int.o" -lm
+echo "build_ref: wrote $OUT/libgauss_ref.so"

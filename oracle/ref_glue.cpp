@@ -1,0 +1,159 @@
+// ref_glue.cpp -- builds oracle/_ref/libgauss_ref.so (test infrastructure, NOT product code).
+//
+// Wraps the REFERENCE'S OWN hot-path code, compiled from /root/reference/src where it lies,
+// behind the same C API as oracle/gauss_oracle.c so tests can diff the two:
+//   * CalCor / CalWgtCov            src/util.cpp:49-70, 103-124   (extracted verbatim at build time)
+//   * run_dist / run_distmix        src/dist.cpp:129-227, src/distmix.cpp:138-253 (ditto)
+//   * computeLD kernel block        src/computeLD.cpp:95-116      (ditto)
+//   * Arguments::Arguments defaults src/gauss.cpp:18-35           (ditto)
+//   * class Snp                     src/snp.{h,cpp}               (compiled unmodified)
+// The extracted fragments are written by oracle/build_ref.sh into oracle/_ref/gen/*.inc
+// (git-ignored; reference sources are never copied into the repository history).
+// Eigen is not installed here, so the three Eigen algorithms the reference calls are
+// provided below from the restatements in gauss_oracle.c; everything else is the
+// reference's code path.
+#include <deque>
+#include <map>
+#include <string>
+#include <vector>
+#include <cstring>
+
+#include <RcppEigen.h>
+#include "snp.h"
+#include "gauss.h"
+#include "util.h"
+
+extern "C" {
+#include "gauss_oracle_internal.h"
+}
+
+using namespace Rcpp;
+
+// ---- Eigen-backed helpers of src/util.cpp, re-provided on the oracle's restatements ----
+void MpMatMat(Eigen::MatrixXd& result, const Eigen::Ref<const Eigen::MatrixXd>& m1,
+              const Eigen::Ref<const Eigen::MatrixXd>& m2) {  // util.cpp:262-264
+  Eigen::MatrixXd out(m1.rows(), m2.cols());
+  for (long j = 0; j < m2.cols(); j++)
+    for (long i = 0; i < m1.rows(); i++) {
+      double acc = 0.0;
+      for (long k = 0; k < m1.cols(); k++) acc += m1(i, k) * m2(k, j);
+      out(i, j) = acc;
+    }
+  result = out;
+}
+void InvMat(Eigen::MatrixXd& inverse, const Eigen::Ref<const Eigen::MatrixXd>& m1) {  // util.cpp:298-300
+  inverse.resize(m1.rows(), m1.cols());
+  gor_inv_full_piv_lu(inverse.data(), m1.data(), (int)m1.rows());
+}
+void MakePosDef(Eigen::MatrixXd& m1, double min_abs_eig) {  // util.cpp:302-318
+  gor_make_pos_def(m1.data(), (int)m1.rows(), min_abs_eig);
+}
+void LoadProgressBar(int) {}  // util.cpp:449-461 prints a text bar; silent here
+
+// ---- the reference's own code, extracted at build time -----------------------------------
+#include "gen/util_49_70.inc"
+#include "gen/util_103_124.inc"
+#include "gen/gauss_18_35.inc"
+void run_dist(std::vector<Snp*>& snp_vec, Arguments& args);
+void run_distmix(std::vector<Snp*>& snp_vec, Arguments& args);
+#include "gen/dist_129_227.inc"
+#include "gen/distmix_138_253.inc"
+
+static void ref_ld_block(std::vector<Snp*>& snp_vec_measured, Arguments& args, double* out) {
+  int num_measured = snp_vec_measured.size();
+#include "gen/computeLD_95_116.inc"
+  std::memcpy(out, Cor_Mat.data(), sizeof(double) * (size_t)num_measured * num_measured);
+}
+
+// ---- same C surface as gauss_oracle.h ------------------------------------------------------
+static __thread double g_pairs = 0.0;
+
+static std::vector<std::string> split_pops(const char* row, const int* m, int n_pops) {
+  std::vector<std::string> v;
+  const char* p = row;
+  for (int k = 0; k < n_pops; k++) {
+    v.emplace_back(p, p + m[k]);
+    p += m[k];
+  }
+  return v;
+}
+
+extern "C" {
+
+double go_last_sample_pairs(void) { return g_pairs; }
+
+double go_cal_cor(const char* x, const char* y, const int* m, int n_pops) {
+  auto vx = split_pops(x, m, n_pops), vy = split_pops(y, m, n_pops);
+  return CalCor(vx, vy);
+}
+
+double go_cal_wgt_cov(const char* x, const char* y, const int* m, int n_pops, const double* w) {
+  auto vx = split_pops(x, m, n_pops), vy = split_pops(y, m, n_pops);
+  std::vector<double> wv(w, w + n_pops);
+  return CalWgtCov(vx, vy, wv);
+}
+
+int go_run_window(const int* type, const long long* bp, double* z, double* info, const char* geno,
+                  int64_t n_snps, const int* m, int n_pops, const double* w, const go_args* a,
+                  int* n_measured, int* n_unmeasured, double* B11_out, double* B21_out) {
+  (void)B11_out; (void)B21_out;  // the reference exposes no intermediate dumps
+  int64_t N = 0;
+  for (int p = 0; p < n_pops; p++) N += m[p];
+  Arguments args;
+  args.chr = 0;
+  args.start_bp = a->start_bp;
+  args.end_bp = a->end_bp;
+  args.lambda = a->lambda;
+  args.min_abs_eig = a->min_abs_eig;
+  args.min_num_measured_snp = a->min_num_measured_snp;
+  args.min_num_unmeasured_snp = a->min_num_unmeasured_snp;
+  args.num_samples = (int)N;
+  if (w) args.pop_wgt_vec.assign(w, w + n_pops);
+  std::vector<Snp> store((size_t)n_snps);
+  std::vector<Snp*> snp_vec;
+  int nt = 0, nu = 0;
+  for (int64_t i = 0; i < n_snps; i++) {
+    Snp& s = store[(size_t)i];
+    s.SetBp(bp[i]);
+    s.SetType(type[i]);
+    s.SetZ(z[i]);
+    s.SetInfo(info[i]);
+    auto gv = split_pops(geno + i * N, m, n_pops);
+    s.SetGenotypeVec(gv);
+    snp_vec.push_back(&s);
+    if (type[i] == 1) nt++;
+    if (type[i] == 0 && bp[i] >= a->start_bp && bp[i] <= a->end_bp) nu++;
+  }
+  if (n_measured) *n_measured = nt;
+  if (n_unmeasured) *n_unmeasured = nu;
+  g_pairs = (double)N * ((double)nt * (nt - 1) / 2 + (double)nu * nt + (w ? nt + nu : 0));
+  try {
+    if (w) run_distmix(snp_vec, args);
+    else run_dist(snp_vec, args);
+  } catch (const std::runtime_error&) {
+    return GO_ERR_TOO_FEW_SNPS;
+  }
+  for (int64_t i = 0; i < n_snps; i++) {
+    z[i] = store[(size_t)i].GetZ();
+    info[i] = store[(size_t)i].GetInfo();
+  }
+  return GO_OK;
+}
+
+void go_compute_ld(const char* geno, int64_t n, const int* m, int n_pops, const double* w, double* cormat) {
+  int64_t N = 0;
+  for (int p = 0; p < n_pops; p++) N += m[p];
+  Arguments args;
+  args.pop_wgt_vec.assign(w, w + n_pops);
+  std::vector<Snp> store((size_t)n);
+  std::vector<Snp*> v;
+  for (int64_t i = 0; i < n; i++) {
+    auto gv = split_pops(geno + i * N, m, n_pops);
+    store[(size_t)i].SetGenotypeVec(gv);
+    store[(size_t)i].SetType(1);
+    v.push_back(&store[(size_t)i]);
+  }
+  g_pairs = (double)N * ((double)n * (n - 1) / 2 + n);
+  ref_ld_block(v, args, cormat);
+}
+}  // extern "C"
