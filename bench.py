@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- distmix imputed SNPs/sec on a 33KG-shaped synthetic panel (BASELINE.json configs[1]).
+
+A "step" is one pass of the window hot path over one chromosome-22-shaped batch: 36 one-Mb
+prediction windows (0.5 Mb wings), measured SNPs at the positions of the reference's bundled
+PGC2_Chr22_ilmn1M_Z.txt, ~3,700 synthetic unmeasured sites per Mb, 21 flagged populations /
+32,147 individuals with the PGC2_SCZ_ANC_Prop weights.
+
+  value  whole-job imputed SNPs/s with the packed panel resident in HBM (K0 stats + K1 Gram +
+         K2 Cholesky/solve; device-timed with CUDA events, max over ranks)
+  e2e    the same metric through the per-window C-ABI call with HOST buffers: pinned-host
+         genotype rows -> H2D -> pack -> window -> D2H of (z, info), every window, every step
+  roofline  K1 (gram_seg_i8_kernel): algorithmic int8 ops / measured launch time vs int8 peak
+  cpu_baseline / --impl reference  the reference's own CPU code path (oracle/_ref when built,
+         else the C restatement) on a bounded sample of the same workload, 1 host core (the
+         reference is single-threaded by construction)
+
+N > 1 (torchrun): every rank owns one GPU and one chromosome-shaped shard (different seed);
+windows are independent so there is no data-path collective; scaling is weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gauss_b200 import synth  # noqa: E402
+
+METRIC = "distmix imputed SNPs/sec"
+UNIT = "SNPs/s"
+SITES = os.path.join(ROOT, "tests", "golden", "pgc2_chr22_sites.npz")
+
+
+# ------------------------------------------------------------------------------------------------
+def chr22_layout():
+    d = np.load(SITES)
+    bp_m, first = np.unique(d["bp"].astype(np.int64), return_index=True)
+    z_m = d["z"][first]
+    bp, type_, windows = synth.chr22_windows(bp_m)
+    return bp, type_, windows, bp_m, z_m
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=j["hbm_gbs"], bf16_tflops=j["bf16_tflops"],
+                    bf16_tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1]))
+                mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(kind_pref: str, n_t_target: int, n_u_sample: int, seed: int = 5):
+    """Time the reference's CPU path on ONE bounded sample window of the workload and extrapolate
+    linearly in sample-pairs to the whole chromosome-shaped step."""
+    from oracle.oracle_py import Oracle
+    kind = kind_pref if Oracle.available(kind_pref) else "port"
+    orc = Oracle(kind)
+    _, sizes, w = synth.flagged_33kg_pgc2()
+    N = int(sizes.sum())
+    bp, type_, windows, bp_m, z_m = chr22_layout()
+    nts = np.array([len(x["measured"]) for x in windows])
+    wi = int(np.argmin(np.abs(nts - n_t_target)))
+    win = windows[wi]
+    n_t = len(win["measured"])
+    n_u = min(n_u_sample, len(win["unmeasured"]))
+    g = synth.make_genotypes(n_t + n_u, sizes, seed=seed)
+    t = np.concatenate([np.ones(n_t, np.int32), np.zeros(n_u, np.int32)])
+    zz = np.concatenate([z_m[:n_t], np.zeros(n_u)])
+    bpp = np.arange(n_t + n_u, dtype=np.int64)
+    t0 = time.perf_counter()
+    r = orc.run_window(t, bpp, zz, g, sizes, w, 0, 10 ** 12)
+    dt = time.perf_counter() - t0
+    assert r["rc"] == 0
+    pairs_sample = n_t * (n_t - 1) / 2 + n_u * n_t + (n_t + n_u)
+    rate = pairs_sample * N / dt                       # sample-pairs / s, 1 core
+    tot_pairs, tot_u = 0.0, 0
+    for x in windows:
+        a, b = len(x["measured"]), len(x["unmeasured"])
+        if a > 10 and b > 10:
+            tot_pairs += a * (a - 1) / 2 + b * a + (a + b)
+            tot_u += b
+    est_step_s = tot_pairs * N / rate
+    return dict(kind=kind, value=tot_u / est_step_s, seconds=dt, n_t=n_t, n_u=n_u, rate=rate,
+                sample=(f"1 window, n_t={n_t} measured (chr22 window {wi}) x {n_u} of its unmeasured SNPs, "
+                        f"N={N}, 21 pops: {dt:.1f} s on 1 core = {rate:.3g} sample-pairs/s incl. eig+LU; "
+                        f"extrapolated linearly in sample-pairs to the {tot_u}-SNP step ({est_step_s / 3600:.2f} core-hours)"))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        s = cpu_sample("reference", n_t_target=250, n_u_sample=48, seed=5 + i)
+        if i >= args.warmup:
+            vals.append(s["value"])
+        last = s
+    v = float(np.mean(vals))
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * last["seconds"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=workload_config(),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=1, kind=last["kind"], sample=last["sample"]),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return dict(workload="distmix chr22, 36 x 1 Mb windows (0.5 Mb wings), measured SNPs at PGC2_Chr22_ilmn1M_Z "
+                         "positions + 3.7k synthetic unmeasured/Mb, 33KG-shaped panel: 21 flagged pops / 32,147 "
+                         "indiv (of 29 / 32,953), PGC2_SCZ_ANC_Prop weights, lambda=0.1, PD certificate on",
+                windows=36, l2="inputs >> L2: each step streams the 4.6 GB packed panel slice",
+                parallelism="window-sharded, no collective")
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import gauss_b200 as gb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    _, sizes, w = synth.flagged_33kg_pgc2()
+    N = int(sizes.sum())
+    bp, type_, windows, bp_m, z_m = chr22_layout()
+    n_m = int((type_ == 1).sum())
+    n_all = len(bp)
+    # panel layout: [measured block | unmeasured block], each in bp order -> every window is two
+    # contiguous row ranges and TMA reads the panel directly (no gather)
+    pos_in_block = np.empty(n_all, np.int64)
+    pos_in_block[type_ == 1] = np.arange(n_m)
+    pos_in_block[type_ == 0] = n_m + np.arange(n_all - n_m)
+
+    t_off, u_off, rows_t, rows_u, z_t = [0], [0], [], [], []
+    meas_idx = np.where(type_ == 1)[0]
+    z_by_site = np.zeros(n_all)
+    z_by_site[meas_idx] = z_m
+    for x in windows:
+        rows_t.append(pos_in_block[x["measured"]])
+        rows_u.append(pos_in_block[x["unmeasured"]])
+        z_t.append(z_by_site[x["measured"]])
+        t_off.append(t_off[-1] + len(x["measured"]))
+        u_off.append(u_off[-1] + len(x["unmeasured"]))
+    rows_t, rows_u, z_t = np.concatenate(rows_t), np.concatenate(rows_u), np.concatenate(z_t)
+
+    ctx = gb.Context(local)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- synthetic panel, generated on the device, packed once (K0)
+    t0 = time.time()
+    geno = synth.make_genotypes_torch(n_all, sizes, dev, seed=20260101 + 22 + 1000 * rank)
+    order = torch.from_numpy(np.concatenate([meas_idx, np.where(type_ == 0)[0]])).to(dev)
+    geno = geno[order].contiguous()
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+    panel = gb.Panel(ctx, sizes, n_all)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    panel.append_device_ptr(geno.data_ptr(), n_all, N, is_ascii=False)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    pack_ms = ev0.elapsed_time(ev1)
+
+    batch = gb.Batch(panel, t_off, rows_t, u_off, rows_u, z_t, w)
+    work = batch.work()
+    n_imputed = int(sum(len(x["unmeasured"]) for x in windows
+                        if len(x["measured"]) > 10 and len(x["unmeasured"]) > 10))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident path: W warm-up steps, then K timed steps with per-stage events
+    for _ in range(args.warmup):
+        batch.run()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    for k in range(args.steps):
+        for s in range(4):
+            evs[k][s].record(stream)
+            batch.run_stage(s)
+        evs[k][4].record(stream)
+    e_end.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    total_ms = e_start.elapsed_time(e_end)
+    stage_ms = np.array([[evs[k][s].elapsed_time(evs[k][s + 1]) for s in range(4)] for k in range(args.steps)])
+    z, info, status = batch.fetch()
+    n_ok = int((status == 0).sum())
+
+    # ---- e2e path: per-window C-ABI calls with HOST buffers
+    host = torch.empty((n_all, N), dtype=torch.int8, pin_memory=True)
+    host.copy_(geno)
+    torch.cuda.synchronize()
+    del geno
+    wpanel = gb.Panel(ctx, sizes, int(max(len(x["measured"]) + len(x["unmeasured"]) for x in windows)))
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = d2h = 0
+
+    def e2e_step(count=False):
+        nonlocal h2d, d2h
+        done = 0
+        for x in windows:
+            a, b = len(x["measured"]), len(x["unmeasured"])
+            if a <= 10 or b <= 10:
+                continue
+            m0, u0 = int(pos_in_block[x["measured"][0]]), int(pos_in_block[x["unmeasured"][0]])
+            wpanel.clear()
+            wpanel.append_host_ptr(host.data_ptr() + m0 * N, a, N, False)   # pinned host -> H2D -> pack
+            wpanel.append_host_ptr(host.data_ptr() + u0 * N, b, N, False)
+            zz, ii, rc = wpanel.window_distmix(np.arange(a), np.arange(a, a + b), z_by_site[x["measured"]], w)
+            done += b
+            if count:
+                h2d += (a + b) * N + a * 8 + (a + b) * 8 + len(w) * 8
+                d2h += b * 16 + 8
+        return done
+
+    e2e_step()  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    e2e_done = 0
+    for k in range(e2e_steps):
+        e2e_done += e2e_step(count=(k == 0))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks
+    t_res = torch.tensor([total_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    cnt = torch.tensor([float(n_imputed), float(e2e_done)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_ms_max = float(t_res[0]), float(t_res[1])
+    value = float(cnt[0]) * args.steps / (total_ms_max / 1e3)
+    e2e_value = float(cnt[1]) / (e2e_ms_max / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        gram_ms = float(stage_ms[:, 1].mean())
+        achieved = work["gram_ops"] / (gram_ms / 1e3) / 1e12
+        int8_peak = 2.0 * pk["bf16_tflops_sustained"]
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="int8 Gram (int32 accumulate) + f64 epilogue/solve", data="synthetic",
+            config=workload_config(),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                     steps=e2e_steps, note="per-window gb_panel_append_host + gb_window_distmix, pinned host rows"),
+            gpu_launches=int(launches),
+            clocks=clocks,
+            roofline=dict(bound="tensor", kernel="gram_seg_i8_kernel", achieved=achieved, peak=int8_peak,
+                          unit="TFLOP/s", frac=achieved / int8_peak, traffic=None,
+                          note=(f"int8 TOP/s; algorithmic ops 2*N*(n_u*n_t+n_t(n_t+1)/2) summed over windows = "
+                                f"{work['gram_ops']:.4g} per launch; peak = 2 x {pk['source']} sustained bf16 "
+                                f"({pk['bf16_tflops_sustained']} TF/s) -- int8 dense is nominally 2x bf16; no "
+                                f"measured int8 figure in MEASURED_PEAKS.json")),
+            stage_ms=dict(row_stats=float(stage_ms[:, 0].mean()), gram=gram_ms,
+                          cholesky=float(stage_ms[:, 2].mean()), solve=float(stage_ms[:, 3].mean())),
+            solve=dict(flops_per_step=work["solve_flops"],
+                       tflops=work["solve_flops"] / (float(stage_ms[:, 2:].sum(1).mean()) / 1e3) / 1e12),
+            pack=dict(ms=pack_ms, gbs=2.0 * n_all * N / (pack_ms / 1e3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"]),
+            windows_ok=n_ok, imputed_per_step=n_imputed, panel_gen_s=gen_s,
+        )
+        if world == 1 and not args.no_cpu_baseline:
+            s = cpu_sample("reference", n_t_target=400, n_u_sample=96)
+            line["cpu_baseline"] = dict(value=s["value"], unit=UNIT, cores=1, kind=s["kind"], sample=s["sample"])
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gauss_b200", choices=["gauss_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

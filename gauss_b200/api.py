@@ -1,0 +1,325 @@
+"""ctypes binding of include/gauss_b200.h.  No compute happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+GB_OK = 0
+GB_ERR_BAD_ARG, GB_ERR_CUDA, GB_ERR_NO_DEVICE, GB_ERR_OOM = 1, 2, 3, 4
+GB_ERR_TOO_FEW_MEASURED, GB_ERR_TOO_FEW_UNMEASURED, GB_ERR_NOT_PD, GB_ERR_UNSUPPORTED = 5, 6, 7, 8
+
+
+class GaussB200Error(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"gauss_b200 status {status}: {msg}")
+        self.status = status
+
+
+class Params(C.Structure):
+    """struct gb_params (hidden arguments of the reference, gauss.cpp:18-35)."""
+    _fields_ = [("lambda_", C.c_double), ("min_abs_eig", C.c_double), ("min_num_measured_snp", C.c_int),
+                ("min_num_unmeasured_snp", C.c_int), ("check_pd", C.c_int), ("reserved", C.c_int)]
+
+    @staticmethod
+    def default() -> "Params":
+        p = Params()
+        load_library().gb_params_default(C.byref(p))
+        return p
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "lib", "libgauss_b200.so")
+
+
+def header_path() -> str:
+    return os.path.join(os.path.dirname(_HERE), "include", "gauss_b200.h")
+
+
+def exported_symbols() -> list[str]:
+    """Names declared GB_API in include/gauss_b200.h."""
+    txt = open(header_path()).read()
+    return sorted(set(re.findall(r"GB_API[^;(]*?\b(gb_\w+)\s*\(", txt)))
+
+
+def load_library():
+    """Load the CUDA library; fail loudly if it has not been built (no fallback exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -m gauss_b200.build` (needs nvcc). "
+                          "gauss_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(path)
+    vp, i64, i32p, dblp, i64p = C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p
+    sig = {
+        "gb_params_default": (None, [C.POINTER(Params)]),
+        "gb_version": (C.c_int, []),
+        "gb_status_string": (C.c_char_p, [C.c_int]),
+        "gb_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "gb_ctx_destroy": (None, [vp]),
+        "gb_ctx_set_stream": (C.c_int, [vp, vp]),
+        "gb_ctx_synchronize": (C.c_int, [vp]),
+        "gb_last_error": (C.c_char_p, [vp]),
+        "gb_ctx_launch_count": (i64, [vp]),
+        "gb_panel_create": (C.c_int, [vp, C.c_int, i32p, i64, C.POINTER(vp)]),
+        "gb_panel_destroy": (None, [vp]),
+        "gb_panel_clear": (C.c_int, [vp]),
+        "gb_panel_num_rows": (i64, [vp]),
+        "gb_panel_num_samples": (i64, [vp]),
+        "gb_panel_append_strings": (C.c_int, [vp, i64, vp]),
+        "gb_panel_append_host": (C.c_int, [vp, i64, vp, i64, C.c_int]),
+        "gb_panel_append_device": (C.c_int, [vp, i64, vp, i64, C.c_int]),
+        "gb_gram_counts": (C.c_int, [vp, vp, i64, i64p, i64, i64p, vp, vp, vp]),
+        "gb_window_dist": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, C.POINTER(Params), dblp, dblp]),
+        "gb_window_distmix": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, dblp, C.POINTER(Params), dblp, dblp]),
+        "gb_window_ld": (C.c_int, [vp, vp, i64, i64p, dblp, dblp]),
+        "gb_window_cor": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, C.POINTER(Params), dblp, dblp]),
+        "gb_batch_create": (C.c_int, [vp, vp, i64, i64p, i64p, i64p, i64p, dblp, dblp, C.POINTER(Params),
+                                      C.POINTER(vp)]),
+        "gb_batch_destroy": (None, [vp]),
+        "gb_batch_run": (C.c_int, [vp]),
+        "gb_batch_run_stage": (C.c_int, [vp, C.c_int]),
+        "gb_batch_fetch": (C.c_int, [vp, dblp, dblp, vp]),
+        "gb_batch_work": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "gb_run_window_strings": (C.c_int, [vp, i64, vp, vp, dblp, dblp, vp, C.c_int, vp, dblp, C.c_longlong,
+                                            C.c_longlong, C.POINTER(Params), C.POINTER(C.c_int),
+                                            C.POINTER(C.c_int)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """gb_ctx: one per GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.gb_ctx_create(device, C.byref(h))
+        if rc != GB_OK:
+            raise GaussB200Error(rc, self.lib.gb_last_error(None).decode() or
+                                 self.lib.gb_status_string(rc).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int, allow=()):
+        if rc != GB_OK and rc not in allow:
+            raise GaussB200Error(rc, self.lib.gb_last_error(self.h).decode() or
+                                 self.lib.gb_status_string(rc).decode())
+        return rc
+
+    def set_stream(self, cuda_stream: int | None):
+        self.check(self.lib.gb_ctx_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self.check(self.lib.gb_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.gb_ctx_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host-side mirror of run_dist / run_distmix (dist.cpp:129-227, distmix.cpp:138-253) ----
+    def run_window_strings(self, type_, bp, z, info, pop_strings, pop_sizes, pop_wgt, start_bp, end_bp,
+                           params: Params | None = None):
+        """pop_strings: list (per SNP) of list (per population) of bytes.  Updates z/info copies."""
+        type_ = np.ascontiguousarray(type_, np.int32)
+        bp = np.ascontiguousarray(bp, np.int64)
+        z = np.array(z, np.float64, copy=True)
+        info = np.array(info, np.float64, copy=True)
+        pop_sizes = np.ascontiguousarray(pop_sizes, np.int32)
+        n, P = len(type_), len(pop_sizes)
+        arr = (C.c_char_p * (n * P))()
+        keep = []
+        for i in range(n):
+            for k in range(P):
+                s = pop_strings[i][k] if pop_strings[i] is not None else None
+                keep.append(s)
+                arr[i * P + k] = s
+        w = None if pop_wgt is None else _f64(pop_wgt)
+        nt, nu = C.c_int(0), C.c_int(0)
+        rc = self.lib.gb_run_window_strings(self.h, n, _ptr(type_), _ptr(bp), _ptr(z), _ptr(info),
+                                            C.cast(arr, C.c_void_p), P, _ptr(pop_sizes), _ptr(w), int(start_bp),
+                                            int(end_bp), C.byref(params) if params else None, C.byref(nt),
+                                            C.byref(nu))
+        return dict(rc=rc, z=z, info=info, n_t=nt.value, n_u=nu.value)
+
+
+class Panel:
+    """gb_panel: HBM-resident packed panel (int8 rows, per-population blocks padded to 32)."""
+
+    def __init__(self, ctx: Context, pop_sizes, capacity_rows: int):
+        self.ctx = ctx
+        self.pop_sizes = np.ascontiguousarray(pop_sizes, np.int32)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.gb_panel_create(ctx.h, len(self.pop_sizes), _ptr(self.pop_sizes), int(capacity_rows),
+                                          C.byref(h)))
+        self.h = h
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.ctx.lib.gb_panel_num_rows(self.h))
+
+    @property
+    def n_samples(self) -> int:
+        return int(self.ctx.lib.gb_panel_num_samples(self.h))
+
+    def clear(self):
+        self.ctx.check(self.ctx.lib.gb_panel_clear(self.h))
+
+    def append_host(self, rows: np.ndarray, is_ascii: bool | None = None):
+        """rows: [n, n_samples] int8 dosages or uint8 ASCII chars (HOST numpy array)."""
+        rows = np.ascontiguousarray(rows)
+        if is_ascii is None:
+            is_ascii = rows.dtype == np.uint8
+        assert rows.ndim == 2 and rows.itemsize == 1
+        self.ctx.check(self.ctx.lib.gb_panel_append_host(self.h, rows.shape[0], rows.ctypes.data,
+                                                         rows.strides[0], int(bool(is_ascii))))
+
+    def append_host_ptr(self, ptr: int, n_rows: int, row_stride: int, is_ascii: bool):
+        self.ctx.check(self.ctx.lib.gb_panel_append_host(self.h, n_rows, C.c_void_p(ptr), row_stride,
+                                                         int(bool(is_ascii))))
+
+    def append_device_ptr(self, ptr: int, n_rows: int, row_stride: int, is_ascii: bool):
+        self.ctx.check(self.ctx.lib.gb_panel_append_device(self.h, n_rows, C.c_void_p(ptr), row_stride,
+                                                           int(bool(is_ascii))))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gb_panel_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parity surface ------------------------------------------------------------------
+    def gram_counts(self, rows_a, rows_b):
+        ra, rb = _i64(rows_a), _i64(rows_b)
+        P = len(self.pop_sizes)
+        sxy = np.zeros((P, len(ra), len(rb)), np.int32)
+        sx = np.zeros((P, len(ra)), np.int32)
+        sxx = np.zeros((P, len(ra)), np.int32)
+        self.ctx.check(self.ctx.lib.gb_gram_counts(self.ctx.h, self.h, len(ra), _ptr(ra), len(rb), _ptr(rb),
+                                                   _ptr(sxy), _ptr(sx), _ptr(sxx)))
+        return sxy, sx, sxx
+
+    def window_cor(self, rows_t, rows_u, pop_wgt=None, params: Params | None = None):
+        rt, ru = _i64(rows_t), _i64(rows_u)
+        w = None if pop_wgt is None else _f64(pop_wgt)
+        B11 = np.zeros((len(rt), len(rt)))
+        B21 = np.zeros((len(ru), len(rt)))
+        self.ctx.check(self.ctx.lib.gb_window_cor(self.ctx.h, self.h, len(rt), _ptr(rt), len(ru), _ptr(ru),
+                                                  _ptr(w), C.byref(params) if params else None, _ptr(B11),
+                                                  _ptr(B21)))
+        return B11, B21
+
+    # ---- one window ---------------------------------------------------------------------------
+    def window_dist(self, rows_t, rows_u, z_t, params: Params | None = None, allow=()):
+        return self._impute(rows_t, rows_u, z_t, None, params, allow)
+
+    def window_distmix(self, rows_t, rows_u, z_t, pop_wgt, params: Params | None = None, allow=()):
+        return self._impute(rows_t, rows_u, z_t, _f64(pop_wgt), params, allow)
+
+    def _impute(self, rows_t, rows_u, z_t, w, params, allow):
+        rt, ru, zt = _i64(rows_t), _i64(rows_u), _f64(z_t)
+        z = np.zeros(len(ru))
+        info = np.zeros(len(ru))
+        lib, pp = self.ctx.lib, (C.byref(params) if params else None)
+        if w is None:
+            rc = lib.gb_window_dist(self.ctx.h, self.h, len(rt), _ptr(rt), len(ru), _ptr(ru), _ptr(zt), pp,
+                                    _ptr(z), _ptr(info))
+        else:
+            rc = lib.gb_window_distmix(self.ctx.h, self.h, len(rt), _ptr(rt), len(ru), _ptr(ru), _ptr(zt),
+                                       _ptr(w), pp, _ptr(z), _ptr(info))
+        self.ctx.check(rc, allow)
+        return z, info, rc
+
+    def window_ld(self, rows, pop_wgt, allow=()):
+        r, w = _i64(rows), _f64(pop_wgt)
+        cm = np.zeros((len(r), len(r)))
+        rc = self.ctx.lib.gb_window_ld(self.ctx.h, self.h, len(r), _ptr(r), _ptr(w), _ptr(cm))
+        self.ctx.check(rc, allow)
+        return cm, rc
+
+
+class Batch:
+    """gb_batch: many windows on one resident panel."""
+
+    def __init__(self, panel: Panel, t_off, rows_t, u_off, rows_u, z_t, pop_wgt=None,
+                 params: Params | None = None):
+        self.panel, self.ctx = panel, panel.ctx
+        self.t_off, self.u_off = _i64(t_off), _i64(u_off)
+        self.rows_t, self.rows_u, self.z_t = _i64(rows_t), _i64(rows_u), _f64(z_t)
+        self.w = None if pop_wgt is None else _f64(pop_wgt)
+        self.n_windows = len(self.t_off) - 1
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.gb_batch_create(
+            self.ctx.h, panel.h, self.n_windows, _ptr(self.t_off), _ptr(self.rows_t), _ptr(self.u_off),
+            _ptr(self.rows_u), _ptr(self.z_t), _ptr(self.w), C.byref(params) if params else None, C.byref(h)))
+        self.h = h
+
+    def run(self):
+        self.ctx.check(self.ctx.lib.gb_batch_run(self.h))
+
+    def run_stage(self, stage: int):
+        self.ctx.check(self.ctx.lib.gb_batch_run_stage(self.h, stage))
+
+    def fetch(self, z=None, info=None):
+        n = int(self.u_off[-1])
+        z = np.zeros(n) if z is None else z
+        info = np.zeros(n) if info is None else info
+        status = np.zeros(self.n_windows, np.int32)
+        self.ctx.check(self.ctx.lib.gb_batch_fetch(self.h, _ptr(z), _ptr(info), _ptr(status)))
+        return z, info, status
+
+    def work(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.ctx.check(self.ctx.lib.gb_batch_work(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(gram_ops=a.value, solve_flops=b.value, panel_bytes=c.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gb_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

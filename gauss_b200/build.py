@@ -1,0 +1,66 @@
+"""Build gauss_b200/lib/libgauss_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libgauss_b200.so")
+SOURCES = ["gb_api.cu", "gb_gram.cu", "gb_pack.cu", "gb_solve.cu"]
+HEADERS = ["gb_common.cuh", "gb_ptx.cuh", os.path.join("..", "..", "include", "gauss_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fvisibility=hidden",
+]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; gauss_b200 has no prebuilt or CPU fallback")
+    return exe
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for s in SOURCES:
+        obj = os.path.join(LIB_DIR, s.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out, file=sys.stderr)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
+    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+            "-Xcompiler", "-fPIC", "-cudart", "static"]
+    subprocess.check_call(link)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,915 @@
+// gb_api.cu -- C-ABI of gauss_b200 (include/gauss_b200.h): contexts, packed panels, the window
+// batch engine and the host-side mirror of run_dist / run_distmix (dist.cpp:129-227,
+// distmix.cpp:138-253).  All compute is CUDA; there is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "gb_common.cuh"
+
+using namespace gb;
+
+struct gb_ctx : public Ctx {};
+struct gb_panel : public Panel {};
+
+static thread_local std::string g_create_err;
+
+// ---------------------------------------------------------------------------------------------
+struct gb_batch {
+  Ctx* ctx = nullptr;
+  Panel* panel = nullptr;
+  int mode = GRAM_MIX;
+  bool ld_mode = false;      // computeLD: T x T only, full symmetric output, no solve
+  bool counts_mode = false;  // raw per-population counts
+  gb_params params{};
+  int64_t n_windows = 0;
+  std::vector<int64_t> t_off, u_off;
+  int64_t n_t_total = 0, n_u_total = 0;
+  std::vector<int> plan_status;       // per window: GB_OK or a TOO_FEW_* code (window skipped)
+  std::vector<int> active;            // window ids that run
+  std::vector<SolveWin> h_wins;       // aligned with `active`
+  std::vector<GramTile> h_tiles;
+  int64_t n_gather = 0;
+  double work_gram_ops = 0, work_solve_flops = 0, work_panel_bytes = 0;
+  long long tt_elems = 0, ut_elems = 0, dinv_elems = 0, counts_elems = 0;
+  // device
+  int32_t *d_rows_t = nullptr, *d_rows_u = nullptr, *d_gather = nullptr;
+  int32_t *d_pool_t = nullptr, *d_pool_u = nullptr;
+  double *d_sd_t = nullptr, *d_sd_u = nullptr;
+  double *d_zt = nullptr, *d_y = nullptr, *d_zu = nullptr, *d_info = nullptr;
+  double *d_tt = nullptr, *d_tt_shift = nullptr, *d_ut = nullptr, *d_dinv = nullptr;
+  double *d_coef = nullptr, *d_wgt = nullptr;
+  int32_t* d_counts = nullptr;
+  int *d_status = nullptr, *d_status_pd = nullptr;
+  SolveWin* d_wins = nullptr;
+  GramTile* d_tiles = nullptr;
+  int8_t* d_scratch = nullptr;
+  CUtensorMap tmap_scratch;
+  GramParams gp{};
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(Ctx* ctx, T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  // stream-ordered pool allocation: the per-window entry points create and destroy a batch per
+  // call, and cudaMalloc/cudaFree would serialise the device every time
+  GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(p), n * sizeof(T), ctx->stream));
+  return GB_OK;
+}
+template <class T>
+int dev_upload(Ctx* ctx, T** p, const std::vector<T>& h) {
+  int rc = dev_alloc(ctx, p, h.size());
+  if (rc) return rc;
+  if (!h.empty()) GB_CUDA(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return GB_OK;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int check_device(Ctx* ctx) {
+  GB_CUDA(cudaSetDevice(ctx->device));
+  return GB_OK;
+}
+
+void free_batch_device(gb_batch* b) {
+  void* ptrs[] = {b->d_rows_t, b->d_rows_u, b->d_gather, b->d_pool_t, b->d_pool_u, b->d_sd_t, b->d_sd_u,
+                  b->d_zt, b->d_y, b->d_zu, b->d_info, b->d_tt, b->d_tt_shift, b->d_ut, b->d_dinv,
+                  b->d_coef, b->d_wgt, b->d_counts, b->d_status, b->d_status_pd, b->d_wins, b->d_tiles,
+                  b->d_scratch};
+  for (void* p : ptrs)
+    if (p) cudaFreeAsync(p, b->ctx->stream);
+}
+
+// Shared planner.  rows_u may be empty (ld_mode).  In counts_mode rows_u plays the A side and
+// rows_t the B side of one full rectangle.
+int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const int64_t* u_off,
+               const int64_t* rows_u, const double* z_t, const double* pop_wgt) {
+  Ctx* ctx = b->ctx;
+  Panel* pn = b->panel;
+  const int64_t nw = b->n_windows;
+  b->t_off.assign(t_off, t_off + nw + 1);
+  if (u_off) b->u_off.assign(u_off, u_off + nw + 1);
+  else b->u_off.assign((size_t)nw + 1, 0);
+  b->n_t_total = b->t_off[nw];
+  b->n_u_total = b->u_off[nw];
+  if (b->t_off[0] != 0 || b->u_off[0] != 0) {
+    ctx->err = "window offsets must start at 0";
+    return GB_ERR_BAD_ARG;
+  }
+  std::vector<int32_t> h_rows_t((size_t)b->n_t_total), h_rows_u((size_t)b->n_u_total);
+  for (int64_t i = 0; i < b->n_t_total; i++) {
+    if (rows_t[i] < 0 || rows_t[i] >= pn->n_rows) {
+      ctx->err = "measured row index out of range";
+      return GB_ERR_BAD_ARG;
+    }
+    h_rows_t[(size_t)i] = (int32_t)rows_t[i];
+  }
+  for (int64_t i = 0; i < b->n_u_total; i++) {
+    if (rows_u[i] < 0 || rows_u[i] >= pn->n_rows) {
+      ctx->err = "unmeasured row index out of range";
+      return GB_ERR_BAD_ARG;
+    }
+    h_rows_u[(size_t)i] = (int32_t)rows_u[i];
+  }
+
+  // ---- segments / coefficients
+  GramParams& gp = b->gp;
+  std::memset(&gp, 0, sizeof(gp));
+  std::vector<double> h_coef((size_t)pn->n_pops, 0.0), h_wgt((size_t)pn->n_pops, 0.0);
+  if (b->mode == GRAM_POOLED) {
+    gp.n_seg = 1;
+    const int last = pn->n_pops - 1;
+    const int k_used = pn->koff[last] + round_up(pn->pop_sizes[last], K_ATOM);
+    gp.seg[0] = Seg{0, k_used / K_ATOM, pn->n_samples, 0};
+    gp.n_pooled = (double)pn->n_samples;
+  } else {
+    gp.n_seg = pn->n_pops;
+    for (int p = 0; p < pn->n_pops; p++) {
+      const int m = pn->pop_sizes[p];
+      gp.seg[p] = Seg{pn->koff[p], (m + K_ATOM - 1) / K_ATOM, m, 0};
+      if (pop_wgt) {
+        const double factor = ((double)m) / (m - 1);   // util.cpp:117
+        h_wgt[(size_t)p] = pop_wgt[p];
+        h_coef[(size_t)p] = pop_wgt[p] * factor;       // wgt_val*factor, left-assoc in util.cpp:118
+        gp.coef[p] = h_coef[(size_t)p];
+        gp.wgt[p] = h_wgt[(size_t)p];
+      }
+    }
+  }
+  gp.mode = b->counts_mode ? GRAM_COUNTS : b->mode;
+  gp.mirror = b->ld_mode ? 1 : 0;
+  gp.diag = b->ld_mode ? 1.0 : 1.0 + b->params.lambda;   // computeLD.cpp:107 vs dist.cpp:172
+
+  // ---- windows
+  b->plan_status.assign((size_t)nw, GB_OK);
+  std::vector<int32_t> h_gather;
+  const double N = (double)pn->n_samples;
+  for (int64_t w = 0; w < nw; w++) {
+    const int64_t nt = b->t_off[w + 1] - b->t_off[w];
+    const int64_t nu = b->u_off[w + 1] - b->u_off[w];
+    if (nt < 0 || nu < 0) {
+      ctx->err = "window offsets must be non-decreasing";
+      return GB_ERR_BAD_ARG;
+    }
+    if (!b->counts_mode) {
+      if (nt <= b->params.min_num_measured_snp) {            // dist.cpp:146, computeLD.cpp:89
+        b->plan_status[(size_t)w] = GB_ERR_TOO_FEW_MEASURED;
+        continue;
+      }
+      if (!b->ld_mode && nu <= b->params.min_num_unmeasured_snp) {
+        b->plan_status[(size_t)w] = GB_ERR_TOO_FEW_UNMEASURED;
+        continue;
+      }
+    } else if (nt == 0 || nu == 0) {
+      continue;
+    }
+    SolveWin sw{};
+    sw.n_t = (int)nt;
+    sw.n_u = (int)nu;
+    sw.ld_t = round_up((int)nt, 8);
+    sw.ld_u = round_up((int)std::max<int64_t>(nu, 1), 8);
+    sw.off_t = b->t_off[w];
+    sw.off_u = b->u_off[w];
+    sw.off_tt = b->tt_elems;
+    sw.off_ut = b->ut_elems;
+    sw.off_dinv = b->dinv_elems;
+    long long counts_off = b->counts_elems;
+    if (b->counts_mode) {
+      b->counts_elems += (long long)nu * nt;
+    } else {
+      b->tt_elems += (long long)nt * sw.ld_t;
+      if (!b->ld_mode) b->ut_elems += (long long)nt * sw.ld_u;
+      b->dinv_elems += (long long)((nt + 63) / 64) * 64 * 64;
+    }
+    b->active.push_back((int)w);
+    b->h_wins.push_back(sw);
+
+    // operand placement: a contiguous ascending run is read straight from the panel by TMA,
+    // anything else is gathered into scratch rows first
+    auto place = [&](const int32_t* rows, int64_t n, int& src, int& row0) {
+      bool contig = true;
+      for (int64_t i = 1; i < n && contig; i++) contig = rows[i] == rows[0] + i;
+      if (contig) {
+        src = 0;
+        row0 = rows[0];
+      } else {
+        src = 1;
+        row0 = (int)h_gather.size();
+        h_gather.insert(h_gather.end(), rows, rows + n);
+      }
+    };
+    int t_src = 0, t_row0 = 0, u_src = 0, u_row0 = 0;
+    place(h_rows_t.data() + b->t_off[w], nt, t_src, t_row0);
+    if (nu > 0) place(h_rows_u.data() + b->u_off[w], nu, u_src, u_row0);
+
+    const int nbt = (int)((nt + 127) / 128), nbu = (int)((nu + 127) / 128);
+    auto push_tile = [&](bool a_is_u, int bi, int bj) {
+      GramTile t{};
+      const int64_t na = a_is_u ? nu : nt;
+      t.a_src = a_is_u ? u_src : t_src;
+      t.a_row0 = (a_is_u ? u_row0 : t_row0) + bi * 128;
+      t.a_list0 = (int)((a_is_u ? b->u_off[w] : b->t_off[w]) + bi * 128);
+      t.a_valid = (int)std::min<int64_t>(128, na - (int64_t)bi * 128);
+      t.b_src = t_src;
+      t.b_row0 = t_row0 + bj * 128;
+      t.b_list0 = (int)(b->t_off[w] + bj * 128);
+      t.b_valid = (int)std::min<int64_t>(128, nt - (int64_t)bj * 128);
+      t.a_is_u = a_is_u ? 1 : 0;
+      t.i0 = bi * 128;
+      t.j0 = bj * 128;
+      if (b->counts_mode) {
+        t.ld_out = (int)nt;
+        t.out_off = counts_off;
+      } else {
+        t.ld_out = a_is_u ? sw.ld_u : sw.ld_t;
+        t.out_off = a_is_u ? sw.off_ut : sw.off_tt;
+      }
+      b->h_tiles.push_back(t);
+    };
+    if (b->counts_mode) {
+      for (int bi = 0; bi < nbu; bi++)
+        for (int bj = 0; bj < nbt; bj++) push_tile(true, bi, bj);
+    } else {
+      for (int bi = 0; bi < nbu; bi++)
+        for (int bj = 0; bj < nbt; bj++) push_tile(true, bi, bj);
+      for (int bi = 0; bi < nbt; bi++)
+        for (int bj = 0; bj <= bi; bj++) push_tile(false, bi, bj);
+      // algorithmic work, SURVEY.md §8(d)
+      const double dnt = (double)nt, dnu = (double)nu;
+      b->work_gram_ops += 2.0 * N * (dnu * dnt + dnt * (dnt + 1) / 2);
+      b->work_panel_bytes += (dnu + dnt) * N;
+      if (!b->ld_mode) b->work_solve_flops += dnt * dnt * dnt / 3 + dnt * dnt * dnu + dnt * dnt + 4 * dnt * dnu;
+    }
+  }
+  b->n_gather = (int64_t)h_gather.size();
+
+  // ---- device buffers
+  int rc;
+  if ((rc = dev_upload(ctx, &b->d_rows_t, h_rows_t))) return rc;
+  if ((rc = dev_upload(ctx, &b->d_rows_u, h_rows_u))) return rc;
+  if ((rc = dev_upload(ctx, &b->d_gather, h_gather))) return rc;
+  if ((rc = dev_upload(ctx, &b->d_coef, h_coef))) return rc;
+  if ((rc = dev_upload(ctx, &b->d_wgt, h_wgt))) return rc;
+  if ((rc = dev_upload(ctx, &b->d_wins, b->h_wins))) return rc;
+  if ((rc = dev_upload(ctx, &b->d_tiles, b->h_tiles))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_sd_t, (size_t)b->n_t_total))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_sd_u, (size_t)b->n_u_total))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_pool_t, (size_t)b->n_t_total))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_pool_u, (size_t)b->n_u_total))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_status, (size_t)nw + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_status_pd, (size_t)nw + 1))) return rc;
+  if (b->counts_mode) {
+    if ((rc = dev_alloc(ctx, &b->d_counts, (size_t)b->counts_elems * pn->n_pops))) return rc;
+  } else {
+    if ((rc = dev_alloc(ctx, &b->d_tt, (size_t)b->tt_elems))) return rc;
+    if (!b->ld_mode) {
+      if ((rc = dev_alloc(ctx, &b->d_ut, (size_t)b->ut_elems))) return rc;
+      if ((rc = dev_alloc(ctx, &b->d_dinv, (size_t)b->dinv_elems))) return rc;
+      if (b->params.check_pd)
+        if ((rc = dev_alloc(ctx, &b->d_tt_shift, (size_t)b->tt_elems))) return rc;
+      if ((rc = dev_alloc(ctx, &b->d_zt, (size_t)b->n_t_total))) return rc;
+      if ((rc = dev_alloc(ctx, &b->d_y, (size_t)b->n_t_total))) return rc;
+      if ((rc = dev_alloc(ctx, &b->d_zu, (size_t)b->n_u_total))) return rc;
+      if ((rc = dev_alloc(ctx, &b->d_info, (size_t)b->n_u_total))) return rc;
+      if (b->n_t_total)
+        GB_CUDA(cudaMemcpyAsync(b->d_zt, z_t, sizeof(double) * (size_t)b->n_t_total, cudaMemcpyHostToDevice,
+                                ctx->stream));
+    }
+  }
+  if (b->n_gather > 0) {
+    if ((rc = dev_alloc(ctx, &b->d_scratch, (size_t)b->n_gather * pn->k_stride))) return rc;
+    if ((rc = make_row_tensor_map(ctx, &b->tmap_scratch, b->d_scratch, b->n_gather, pn->k_stride))) return rc;
+  } else {
+    b->tmap_scratch = pn->tmap;
+  }
+
+  gp.tiles = b->d_tiles;
+  gp.n_tiles = (int)b->h_tiles.size();
+  gp.sx = pn->d_sx;
+  gp.sxx = pn->d_sxx;
+  gp.stat_ld = pn->capacity;
+  gp.rows_t = b->d_rows_t;
+  gp.rows_u = b->d_rows_u;
+  gp.sd_t = b->d_sd_t;
+  gp.sd_u = b->d_sd_u;
+  gp.pool_t = b->d_pool_t;
+  gp.pool_u = b->d_pool_u;
+  gp.out_tt = b->d_tt;
+  gp.out_ut = b->d_ut;
+  gp.out_counts = b->d_counts;
+  gp.counts_seg_stride = b->counts_elems;
+  // the planning uploads read host vectors that die with this frame
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GB_OK;
+}
+
+int run_stage(gb_batch* b, int stage) {
+  Ctx* ctx = b->ctx;
+  Panel* pn = b->panel;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  switch (stage) {
+    case 0: {
+      if (b->n_gather > 0)
+        if ((rc = launch_gather_rows(ctx, pn, b->d_gather, b->n_gather, b->d_scratch))) return rc;
+      if (b->counts_mode) return GB_OK;
+      if ((rc = launch_row_prep(ctx, pn, b->d_rows_t, b->n_t_total, b->mode, b->d_coef, b->d_wgt, b->d_sd_t,
+                                b->d_pool_t)))
+        return rc;
+      return launch_row_prep(ctx, pn, b->d_rows_u, b->n_u_total, b->mode, b->d_coef, b->d_wgt, b->d_sd_u,
+                             b->d_pool_u);
+    }
+    case 1:
+      return launch_gram(ctx, pn->tmap, b->tmap_scratch, b->gp);
+    case 2: {
+      if (b->ld_mode || b->counts_mode) return GB_OK;
+      GB_CUDA(cudaMemsetAsync(b->d_status, 0, sizeof(int) * (size_t)(b->n_windows + 1), ctx->stream));
+      GB_CUDA(cudaMemsetAsync(b->d_status_pd, 0, sizeof(int) * (size_t)(b->n_windows + 1), ctx->stream));
+      if (b->params.check_pd) {
+        // certificate: Cholesky of B11 - min_abs_eig*I succeeds  <=>  lambda_min(B11) > min_abs_eig
+        if ((rc = launch_copy_shift(ctx, b->d_wins, b->h_wins, b->d_tt, b->d_tt_shift, b->params.min_abs_eig)))
+          return rc;
+        if ((rc = launch_cholesky(ctx, b->d_wins, b->h_wins, b->d_tt_shift, b->d_dinv, b->d_zt, b->d_y,
+                                  b->d_status_pd, 0.0, 0)))
+          return rc;
+      }
+      return launch_cholesky(ctx, b->d_wins, b->h_wins, b->d_tt, b->d_dinv, b->d_zt, b->d_y, b->d_status, 0.0, 1);
+    }
+    case 3:
+      if (b->ld_mode || b->counts_mode) return GB_OK;
+      return launch_trsm_finalize(ctx, b->d_wins, b->h_wins, b->d_tt, b->d_dinv, b->d_ut, b->d_y, b->d_zu,
+                                  b->d_info);
+    default:
+      ctx->err = "unknown stage";
+      return GB_ERR_BAD_ARG;
+  }
+}
+
+int create_batch_internal(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const int64_t* t_off,
+                          const int64_t* rows_t, const int64_t* u_off, const int64_t* rows_u, const double* z_t,
+                          const double* pop_wgt, const gb_params* params, bool ld_mode, bool counts_mode,
+                          gb_batch** out) {
+  if (!ctx || !panel || !out || n_windows < 0 || !t_off || (!rows_t && t_off[n_windows] > 0)) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  if (panel->ctx != ctx) {
+    ctx->err = "panel belongs to another context";
+    return GB_ERR_BAD_ARG;
+  }
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  gb_batch* b = new (std::nothrow) gb_batch();
+  if (!b) return GB_ERR_OOM;
+  b->ctx = ctx;
+  b->panel = panel;
+  b->mode = (pop_wgt || counts_mode) ? GRAM_MIX : GRAM_POOLED;
+  b->ld_mode = ld_mode;
+  b->counts_mode = counts_mode;
+  if (params) b->params = *params;
+  else gb_params_default(&b->params);
+  b->n_windows = n_windows;
+  rc = plan_batch(b, t_off, rows_t, u_off, rows_u, z_t, pop_wgt);
+  if (rc) {
+    free_batch_device(b);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return GB_OK;
+}
+
+int window_status(const gb_batch* b, const std::vector<int>& st, const std::vector<int>& st_pd, int64_t w) {
+  if (b->plan_status[(size_t)w] != GB_OK) return b->plan_status[(size_t)w];
+  if (st[(size_t)w] || st_pd[(size_t)w]) return GB_ERR_NOT_PD;
+  return GB_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+void gb_params_default(gb_params* p) {  // gauss.cpp:18-35
+  if (!p) return;
+  p->lambda = 0.1;
+  p->min_abs_eig = 1e-5;
+  p->min_num_measured_snp = 10;
+  p->min_num_unmeasured_snp = 10;
+  p->check_pd = 1;
+  p->reserved = 0;
+}
+
+int gb_version(void) { return GB_VERSION; }
+
+const char* gb_status_string(int s) {
+  switch (s) {
+    case GB_OK: return "ok";
+    case GB_ERR_BAD_ARG: return "bad argument";
+    case GB_ERR_CUDA: return "CUDA error";
+    case GB_ERR_NO_DEVICE: return "no CUDA device (gauss_b200 has no CPU fallback)";
+    case GB_ERR_OOM: return "out of memory";
+    case GB_ERR_TOO_FEW_MEASURED:
+    case GB_ERR_TOO_FEW_UNMEASURED: return "Not enough number of SNPs loaded";
+    case GB_ERR_NOT_PD: return "B11 not certified positive definite above min_abs_eig";
+    case GB_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+
+int gb_ctx_create(int device, gb_ctx** out) {
+  if (!out) return GB_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return GB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    g_create_err = "device index out of range";
+    return GB_ERR_BAD_ARG;
+  }
+  gb_ctx* ctx = new (std::nothrow) gb_ctx();
+  if (!ctx) return GB_ERR_OOM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    delete ctx;
+    return GB_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_err = "gauss_b200 kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor);
+    delete ctx;
+    return GB_ERR_UNSUPPORTED;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    delete ctx;
+    return GB_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  {  // keep freed blocks cached in the device's default pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  *out = ctx;
+  return GB_OK;
+}
+
+void gb_ctx_destroy(gb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int gb_ctx_set_stream(gb_ctx* ctx, void* s) {
+  if (!ctx) return GB_ERR_BAD_ARG;
+  ctx->stream = s ? static_cast<cudaStream_t>(s) : ctx->own_stream;
+  return GB_OK;
+}
+
+int gb_ctx_synchronize(gb_ctx* ctx) {
+  if (!ctx) return GB_ERR_BAD_ARG;
+  GB_CUDA(cudaSetDevice(ctx->device));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GB_OK;
+}
+
+const char* gb_last_error(const gb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+int64_t gb_ctx_launch_count(const gb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- panel ----------------------------------------------------------------------------------
+int gb_panel_create(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t capacity_rows, gb_panel** out) {
+  if (!ctx || !out || !pop_sizes || n_pops < 1 || capacity_rows < 1) {
+    if (ctx) ctx->err = "bad panel description";
+    return GB_ERR_BAD_ARG;
+  }
+  if (n_pops > P_MAX) {
+    ctx->err = "more than " + std::to_string(P_MAX) + " flagged populations";
+    return GB_ERR_UNSUPPORTED;
+  }
+  if (capacity_rows > (int64_t)std::numeric_limits<int32_t>::max() - 256) return GB_ERR_BAD_ARG;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  gb_panel* p = new (std::nothrow) gb_panel();
+  if (!p) return GB_ERR_OOM;
+  p->ctx = ctx;
+  p->n_pops = n_pops;
+  int k = 0;
+  for (int i = 0; i < n_pops; i++) {
+    if (pop_sizes[i] < 1) {
+      delete p;
+      ctx->err = "population size must be >= 1";
+      return GB_ERR_BAD_ARG;
+    }
+    p->pop_sizes.push_back(pop_sizes[i]);
+    p->koff.push_back(k);
+    k += round_up(pop_sizes[i], K_ATOM);
+    p->n_samples += pop_sizes[i];
+  }
+  p->k_stride = round_up(k, K_BLOCK);
+  p->capacity = capacity_rows;
+  auto fail = [&](int code) {
+    gb_panel_destroy(p);
+    return code;
+  };
+  auto pmalloc = [&](void** ptr, size_t bytes) -> int {
+    cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("cudaMalloc(panel): ") + cudaGetErrorString(e);
+      return e == cudaErrorMemoryAllocation ? GB_ERR_OOM : GB_ERR_CUDA;
+    }
+    return GB_OK;
+  };
+  if ((rc = pmalloc((void**)&p->d_rows, (size_t)capacity_rows * p->k_stride))) return fail(rc);
+  if ((rc = pmalloc((void**)&p->d_sx, sizeof(int32_t) * (size_t)capacity_rows * n_pops))) return fail(rc);
+  if ((rc = pmalloc((void**)&p->d_sxx, sizeof(int32_t) * (size_t)capacity_rows * n_pops))) return fail(rc);
+  if ((rc = pmalloc((void**)&p->d_pop_sizes, sizeof(int) * (size_t)n_pops))) return fail(rc);
+  if ((rc = pmalloc((void**)&p->d_koff, sizeof(int) * (size_t)n_pops))) return fail(rc);
+  cudaMemcpyAsync(p->d_pop_sizes, p->pop_sizes.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(p->d_koff, p->koff.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
+  if ((rc = make_row_tensor_map(ctx, &p->tmap, p->d_rows, capacity_rows, p->k_stride))) return fail(rc);
+  cudaStreamSynchronize(ctx->stream);
+  *out = p;
+  return GB_OK;
+}
+
+void gb_panel_destroy(gb_panel* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  if (p->d_rows) cudaFree(p->d_rows);
+  if (p->d_sx) cudaFree(p->d_sx);
+  if (p->d_sxx) cudaFree(p->d_sxx);
+  if (p->d_pop_sizes) cudaFree(p->d_pop_sizes);
+  if (p->d_koff) cudaFree(p->d_koff);
+  delete p;
+}
+
+int gb_panel_clear(gb_panel* p) {
+  if (!p) return GB_ERR_BAD_ARG;
+  p->n_rows = 0;
+  return GB_OK;
+}
+int64_t gb_panel_num_rows(const gb_panel* p) { return p ? p->n_rows : -1; }
+int64_t gb_panel_num_samples(const gb_panel* p) { return p ? p->n_samples : -1; }
+
+int gb_panel_append_device(gb_panel* p, int64_t n_rows, const void* dev_rows, int64_t row_stride, int is_ascii) {
+  if (!p || n_rows < 0 || (!dev_rows && n_rows > 0) || row_stride < p->n_samples) {
+    if (p) p->ctx->err = "bad append arguments";
+    return GB_ERR_BAD_ARG;
+  }
+  Ctx* ctx = p->ctx;
+  if (p->n_rows + n_rows > p->capacity) {
+    ctx->err = "panel capacity exceeded";
+    return GB_ERR_BAD_ARG;
+  }
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  if ((rc = launch_pack(ctx, p, dev_rows, row_stride, is_ascii, p->n_rows, n_rows))) return rc;
+  p->n_rows += n_rows;
+  return GB_OK;
+}
+
+int gb_panel_append_host(gb_panel* p, int64_t n_rows, const void* rows, int64_t row_stride, int is_ascii) {
+  if (!p || n_rows < 0 || (!rows && n_rows > 0) || row_stride < p->n_samples) {
+    if (p) p->ctx->err = "bad append arguments";
+    return GB_ERR_BAD_ARG;
+  }
+  if (n_rows == 0) return GB_OK;
+  Ctx* ctx = p->ctx;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  void* d = nullptr;
+  const size_t bytes = (size_t)n_rows * (size_t)row_stride;
+  GB_CUDA(cudaMallocAsync(&d, bytes, ctx->stream));
+  cudaError_t e = cudaMemcpyAsync(d, rows, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    rc = gb_panel_append_device(p, n_rows, d, row_stride, is_ascii);
+  } else {
+    ctx->err = cudaGetErrorString(e);
+    rc = GB_ERR_CUDA;
+  }
+  cudaFreeAsync(d, ctx->stream);
+  return rc;
+}
+
+int gb_panel_append_strings(gb_panel* p, int64_t n_rows, const char* const* pop_strings) {
+  if (!p || n_rows < 0 || (!pop_strings && n_rows > 0)) return GB_ERR_BAD_ARG;
+  if (n_rows == 0) return GB_OK;
+  Ctx* ctx = p->ctx;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  // concatenate the per-population strings of each SNP into one pinned staging row
+  const size_t N = (size_t)p->n_samples;
+  char* stage = nullptr;
+  GB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&stage), (size_t)n_rows * N));
+  for (int64_t r = 0; r < n_rows; r++) {
+    char* dst = stage + (size_t)r * N;
+    for (int k = 0; k < p->n_pops; k++) {
+      const char* s = pop_strings[r * p->n_pops + k];
+      if (!s) {
+        cudaFreeHost(stage);
+        ctx->err = "null genotype string";
+        return GB_ERR_BAD_ARG;
+      }
+      std::memcpy(dst, s, (size_t)p->pop_sizes[(size_t)k]);
+      dst += p->pop_sizes[(size_t)k];
+    }
+  }
+  rc = gb_panel_append_host(p, n_rows, stage, (int64_t)N, 1);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFreeHost(stage);
+  return rc;
+}
+
+// ---- batches ---------------------------------------------------------------------------------
+int gb_batch_create(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const int64_t* t_off, const int64_t* rows_t,
+                    const int64_t* u_off, const int64_t* rows_u, const double* z_t, const double* pop_wgt,
+                    const gb_params* params, gb_batch** out) {
+  if (!u_off || !z_t) {
+    if (ctx) ctx->err = "null argument";
+    return GB_ERR_BAD_ARG;
+  }
+  return create_batch_internal(ctx, panel, n_windows, t_off, rows_t, u_off, rows_u, z_t, pop_wgt, params, false,
+                               false, out);
+}
+
+void gb_batch_destroy(gb_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  free_batch_device(b);
+  delete b;
+}
+
+int gb_batch_run(gb_batch* b) {
+  if (!b) return GB_ERR_BAD_ARG;
+  for (int s = 0; s < 4; s++) {
+    int rc = run_stage(b, s);
+    if (rc) return rc;
+  }
+  return GB_OK;
+}
+
+int gb_batch_run_stage(gb_batch* b, int stage) {
+  if (!b) return GB_ERR_BAD_ARG;
+  return run_stage(b, stage);
+}
+
+int gb_batch_fetch(gb_batch* b, double* z_u, double* info_u, int* window_status_out) {
+  if (!b || b->ld_mode || b->counts_mode) return GB_ERR_BAD_ARG;
+  Ctx* ctx = b->ctx;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  std::vector<int> st((size_t)b->n_windows + 1, 0), st_pd((size_t)b->n_windows + 1, 0);
+  if (b->n_u_total) {
+    if (z_u) GB_CUDA(cudaMemcpyAsync(z_u, b->d_zu, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (info_u) GB_CUDA(cudaMemcpyAsync(info_u, b->d_info, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  // d_status is indexed by position in the active list
+  GB_CUDA(cudaMemcpyAsync(st.data(), b->d_status, sizeof(int) * (size_t)b->n_windows, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaMemcpyAsync(st_pd.data(), b->d_status_pd, sizeof(int) * (size_t)b->n_windows, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> st_w((size_t)b->n_windows, 0), st_pd_w((size_t)b->n_windows, 0);
+  for (size_t a = 0; a < b->active.size(); a++) {
+    st_w[(size_t)b->active[a]] = st[a];
+    st_pd_w[(size_t)b->active[a]] = st_pd[a];
+  }
+  int worst = GB_OK;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  for (int64_t w = 0; w < b->n_windows; w++) {
+    const int s = window_status(b, st_w, st_pd_w, w);
+    if (window_status_out) window_status_out[w] = s;
+    if (s != GB_OK && worst == GB_OK) worst = s;
+    if (b->plan_status[(size_t)w] != GB_OK)  // skipped window: no result exists
+      for (int64_t i = b->u_off[w]; i < b->u_off[w + 1]; i++) {
+        if (z_u) z_u[i] = nan;
+        if (info_u) info_u[i] = nan;
+      }
+  }
+  return window_status_out ? GB_OK : worst;
+}
+
+int gb_batch_work(const gb_batch* b, double* gram_ops, double* solve_flops, double* panel_bytes) {
+  if (!b) return GB_ERR_BAD_ARG;
+  if (gram_ops) *gram_ops = b->work_gram_ops;
+  if (solve_flops) *solve_flops = b->work_solve_flops;
+  if (panel_bytes) *panel_bytes = b->work_panel_bytes;
+  return GB_OK;
+}
+
+// ---- single windows -----------------------------------------------------------------------------
+static int window_impute(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* rows_t, int64_t n_u,
+                         const int64_t* rows_u, const double* z_t, const double* pop_wgt, const gb_params* params,
+                         double* z_u, double* info_u) {
+  if (!ctx || !panel || n_t < 0 || n_u < 0 || !z_u || !info_u || (!z_t && n_t > 0)) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  const int64_t t_off[2] = {0, n_t}, u_off[2] = {0, n_u};
+  gb_batch* b = nullptr;
+  double dummy = 0.0;
+  int rc = gb_batch_create(ctx, panel, 1, t_off, rows_t, u_off, rows_u, z_t ? z_t : &dummy, pop_wgt, params, &b);
+  if (rc) return rc;
+  if ((rc = gb_batch_run(b)) == GB_OK) rc = gb_batch_fetch(b, z_u, info_u, nullptr);
+  gb_batch_destroy(b);
+  return rc;
+}
+
+int gb_window_dist(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* rows_t, int64_t n_u,
+                   const int64_t* rows_u, const double* z_t, const gb_params* params, double* z_u, double* info_u) {
+  return window_impute(ctx, panel, n_t, rows_t, n_u, rows_u, z_t, nullptr, params, z_u, info_u);
+}
+
+int gb_window_distmix(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* rows_t, int64_t n_u,
+                      const int64_t* rows_u, const double* z_t, const double* pop_wgt, const gb_params* params,
+                      double* z_u, double* info_u) {
+  if (!pop_wgt) {
+    if (ctx) ctx->err = "distmix needs population weights";
+    return GB_ERR_BAD_ARG;
+  }
+  return window_impute(ctx, panel, n_t, rows_t, n_u, rows_u, z_t, pop_wgt, params, z_u, info_u);
+}
+
+int gb_window_ld(gb_ctx* ctx, gb_panel* panel, int64_t n, const int64_t* rows, const double* pop_wgt,
+                 double* cormat) {
+  if (!ctx || !panel || n < 0 || !cormat || !pop_wgt) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  const int64_t t_off[2] = {0, n};
+  gb_batch* b = nullptr;
+  int rc = create_batch_internal(ctx, panel, 1, t_off, rows, nullptr, nullptr, nullptr, pop_wgt, nullptr, true,
+                                 false, &b);
+  if (rc) return rc;
+  if (b->plan_status[0] != GB_OK) {
+    rc = b->plan_status[0];
+  } else {
+    rc = run_stage(b, 0);
+    if (!rc) rc = run_stage(b, 1);
+    if (!rc) {
+      const SolveWin& w = b->h_wins[0];
+      cudaError_t e = cudaMemcpy2DAsync(cormat, sizeof(double) * (size_t)n, b->d_tt + w.off_tt,
+                                        sizeof(double) * (size_t)w.ld_t, sizeof(double) * (size_t)n, (size_t)n,
+                                        cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) {
+        ctx->err = cudaGetErrorString(e);
+        rc = GB_ERR_CUDA;
+      }
+    }
+  }
+  gb_batch_destroy(b);
+  return rc;
+}
+
+int gb_window_cor(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* rows_t, int64_t n_u,
+                  const int64_t* rows_u, const double* pop_wgt, const gb_params* params, double* B11, double* B21) {
+  if (!ctx || !panel || n_t < 1 || n_u < 0) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  gb_params p;
+  if (params) p = *params;
+  else gb_params_default(&p);
+  p.min_num_measured_snp = 0;  // debug surface: no thresholds
+  p.min_num_unmeasured_snp = -1;
+  const int64_t t_off[2] = {0, n_t}, u_off[2] = {0, n_u};
+  std::vector<double> zt((size_t)n_t, 0.0);
+  gb_batch* b = nullptr;
+  int rc = gb_batch_create(ctx, panel, 1, t_off, rows_t, u_off, rows_u, zt.data(), pop_wgt, &p, &b);
+  if (rc) return rc;
+  rc = run_stage(b, 0);
+  if (!rc) rc = run_stage(b, 1);
+  if (!rc) {
+    const SolveWin& w = b->h_wins[0];
+    std::vector<double> tt((size_t)n_t * w.ld_t), ut((size_t)n_t * w.ld_u);
+    cudaError_t e = cudaMemcpyAsync(tt.data(), b->d_tt + w.off_tt, tt.size() * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && n_u > 0)
+      e = cudaMemcpyAsync(ut.data(), b->d_ut + w.off_ut, ut.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                          ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = cudaGetErrorString(e);
+      rc = GB_ERR_CUDA;
+    } else {
+      if (B11)
+        for (int64_t i = 0; i < n_t; i++)
+          for (int64_t j = 0; j <= i; j++) {
+            const double v = tt[(size_t)j * w.ld_t + i];  // column-major lower
+            B11[i * n_t + j] = v;
+            B11[j * n_t + i] = v;
+          }
+      if (B21)
+        for (int64_t u = 0; u < n_u; u++)
+          for (int64_t t = 0; t < n_t; t++) B21[u * n_t + t] = ut[(size_t)t * w.ld_u + u];
+    }
+  }
+  gb_batch_destroy(b);
+  return rc;
+}
+
+int gb_gram_counts(gb_ctx* ctx, gb_panel* panel, int64_t n_a, const int64_t* rows_a, int64_t n_b,
+                   const int64_t* rows_b, int32_t* out_sxy, int32_t* out_sx, int32_t* out_sxx) {
+  if (!ctx || !panel || n_a < 1 || n_b < 1 || !rows_a || !rows_b) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  const int64_t t_off[2] = {0, n_b}, u_off[2] = {0, n_a};
+  gb_batch* b = nullptr;
+  int rc = create_batch_internal(ctx, panel, 1, t_off, rows_b, u_off, rows_a, nullptr, nullptr, nullptr, false,
+                                 true, &b);
+  if (rc) return rc;
+  rc = run_stage(b, 0);
+  if (!rc) rc = run_stage(b, 1);
+  if (!rc) {
+    cudaError_t e = cudaSuccess;
+    if (out_sxy)
+      e = cudaMemcpyAsync(out_sxy, b->d_counts, sizeof(int32_t) * (size_t)(n_a * n_b * panel->n_pops),
+                          cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && (out_sx || out_sxx)) {
+      std::vector<int32_t> col((size_t)panel->n_rows);
+      for (int p = 0; p < panel->n_pops && e == cudaSuccess; p++) {
+        for (int which = 0; which < 2 && e == cudaSuccess; which++) {
+          int32_t* dst = which ? out_sxx : out_sx;
+          if (!dst) continue;
+          e = cudaMemcpy(col.data(), (which ? panel->d_sxx : panel->d_sx) + (size_t)p * panel->capacity,
+                         sizeof(int32_t) * (size_t)panel->n_rows, cudaMemcpyDeviceToHost);
+          for (int64_t i = 0; i < n_a; i++) dst[(size_t)p * n_a + i] = col[(size_t)rows_a[i]];
+        }
+      }
+    }
+    if (e != cudaSuccess) {
+      ctx->err = cudaGetErrorString(e);
+      rc = GB_ERR_CUDA;
+    }
+  }
+  gb_batch_destroy(b);
+  return rc;
+}
+
+// ---- host-side mirror of run_dist / run_distmix ---------------------------------------------------
+int gb_run_window_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const long long* bp, double* z,
+                          double* info, const char* const* pop_strings, int n_pops, const int* pop_sizes,
+                          const double* pop_wgt, long long start_bp, long long end_bp, const gb_params* params,
+                          int* n_measured, int* n_unmeasured) {
+  if (!ctx || n_snps < 0 || !type || !bp || !z || !info || !pop_strings || !pop_sizes) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  gb_params p;
+  if (params) p = *params;
+  else gb_params_default(&p);
+  // dist.cpp:132-141 -- type 0 inside the prediction window -> unmeasured; type 1 anywhere in the
+  // extended window -> measured; type 2 ignored
+  std::vector<int64_t> meas, unme;
+  for (int64_t i = 0; i < n_snps; i++) {
+    if (type[i] == 0 && bp[i] >= start_bp && bp[i] <= end_bp) unme.push_back(i);
+    else if (type[i] == 1) meas.push_back(i);
+  }
+  if (n_measured) *n_measured = (int)meas.size();
+  if (n_unmeasured) *n_unmeasured = (int)unme.size();
+  if ((int64_t)meas.size() <= p.min_num_measured_snp) return GB_ERR_TOO_FEW_MEASURED;      // dist.cpp:146
+  if ((int64_t)unme.size() <= p.min_num_unmeasured_snp) return GB_ERR_TOO_FEW_UNMEASURED;  // dist.cpp:147
+  const int64_t nt = (int64_t)meas.size(), nu = (int64_t)unme.size();
+  gb_panel* panel = nullptr;
+  int rc = gb_panel_create(ctx, n_pops, pop_sizes, nt + nu, &panel);
+  if (rc) return rc;
+  std::vector<const char*> strs((size_t)(nt + nu) * n_pops);
+  for (int64_t i = 0; i < nt + nu; i++) {
+    const int64_t s = i < nt ? meas[(size_t)i] : unme[(size_t)(i - nt)];
+    for (int k = 0; k < n_pops; k++) strs[(size_t)(i * n_pops + k)] = pop_strings[s * n_pops + k];
+  }
+  rc = gb_panel_append_strings(panel, nt + nu, strs.data());
+  if (!rc) {
+    std::vector<int64_t> rt((size_t)nt), ru((size_t)nu);
+    std::vector<double> zt((size_t)nt), zu((size_t)nu), iu((size_t)nu);
+    for (int64_t i = 0; i < nt; i++) rt[(size_t)i] = i, zt[(size_t)i] = z[meas[(size_t)i]];
+    for (int64_t i = 0; i < nu; i++) ru[(size_t)i] = nt + i;
+    rc = window_impute(ctx, panel, nt, rt.data(), nu, ru.data(), zt.data(), pop_wgt, &p, zu.data(), iu.data());
+    if (rc == GB_OK || rc == GB_ERR_NOT_PD)
+      for (int64_t i = 0; i < nu; i++) {  // SetZ / SetInfo, dist.cpp:200-202
+        z[unme[(size_t)i]] = zu[(size_t)i];
+        info[unme[(size_t)i]] = iu[(size_t)i];
+      }
+  }
+  gb_panel_destroy(panel);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// gb_common.cuh -- shared declarations of the gauss_b200 device library (not part of the C-ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/gauss_b200.h"
+
+namespace gb {
+
+// ------------------------------------------------------------------ geometry of the packed panel
+constexpr int K_ATOM = 32;    // int8 elements one tcgen05.mma kind::i8 consumes along K
+constexpr int K_BLOCK = 128;  // bytes of K per smem stage row == TMA box width == swizzle span
+constexpr int P_MAX = 30;     // max flagged populations (33KG, the largest panel the reference documents, has 29; 1KG 26);
+                              // bounded by the epilogue's shared-memory statistics tables
+
+// One K-segment = one population block of the packed panel (or the pooled whole row for dist()).
+struct Seg {
+  int koff;    // first K column of the segment (multiple of 32)
+  int natoms;  // number of 32-wide K atoms to multiply (ceil(m/32))
+  int m;       // individuals in the segment
+  int pad;
+};
+
+// ------------------------------------------------------------------ Gram kernel interface
+enum GramMode : int {
+  GRAM_MIX = 0,     // CalWgtCov -> correlation (distmix / computeLD)
+  GRAM_POOLED = 1,  // CalCor pooled Pearson r (dist)
+  GRAM_COUNTS = 2   // raw int32 per-segment counts (parity surface)
+};
+
+struct GramTile {      // one 128 x 128 output tile
+  int a_row0, b_row0;  // first row of the A (M side) / B (N side) operand in its TMA source
+  int a_src, b_src;    // 0: panel, 1: gathered scratch
+  int a_list0, b_list0;// index of the first A / B row in the batch row lists (stats, sd)
+  int a_valid, b_valid;// rows that exist (<= 128)
+  int a_is_u;          // 1: A rows come from the unmeasured list (B21 tile), 0: measured (B11 tile)
+  int i0, j0;          // local coordinates of the tile inside the window's output matrix
+  int ld_out;          // leading dimension of the output matrix (doubles / int32)
+  long long out_off;   // element offset of the window's output matrix in the output buffer
+};
+
+struct GramParams {
+  const GramTile* tiles;
+  int n_tiles;
+  int mode;
+  int n_seg;
+  int mirror;            // 1: also store the transposed entry (full symmetric matrix, computeLD)
+  Seg seg[P_MAX];
+  double coef[P_MAX];    // w_p * (m_p / (m_p - 1))          (util.cpp:117-118)
+  double wgt[P_MAX];     // w_p
+  double n_pooled;       // total flagged individuals (dist)
+  double diag;           // value forced on the diagonal of T x T tiles (1 + lambda, or 1.0)
+  const int32_t* sx;     // [n_pops][stat_ld] per-population sum x   (panel rows)
+  const int32_t* sxx;    // [n_pops][stat_ld] per-population sum x^2
+  long long stat_ld;
+  const int32_t* rows_t; // batch row lists -> panel rows
+  const int32_t* rows_u;
+  const double* sd_t;    // per listed row: mix: sqrt(cov_ii); pooled: sqrt(N*sxx - sx^2)
+  const double* sd_u;
+  const int32_t* pool_t; // pooled sum x per listed row (dist)
+  const int32_t* pool_u;
+  double* out_tt;        // B11 buffers (column-major, lower triangle incl. whole diagonal tiles)
+  double* out_ut;        // B21^T buffers ([n_t][ld_u], u contiguous)
+  int32_t* out_counts;   // GRAM_COUNTS: [n_seg][n_a][n_b]
+  long long counts_seg_stride;
+};
+
+// ------------------------------------------------------------------ context / panel
+struct Ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // lazily grown device scratch shared by the single-window entry points
+  void* fn_encode_tiled = nullptr;  // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
+};
+
+struct Panel {
+  Ctx* ctx = nullptr;
+  int n_pops = 0;
+  std::vector<int> pop_sizes;
+  std::vector<int> koff;       // per pop first K column (padded to 32)
+  int n_samples = 0;           // sum pop_sizes
+  int k_stride = 0;            // bytes per packed row (multiple of 128)
+  int64_t capacity = 0;
+  int64_t n_rows = 0;
+  int8_t* d_rows = nullptr;    // [capacity][k_stride]
+  int32_t* d_sx = nullptr;     // [n_pops][capacity]
+  int32_t* d_sxx = nullptr;    // [n_pops][capacity]
+  int* d_pop_sizes = nullptr;  // [n_pops]
+  int* d_koff = nullptr;       // [n_pops]
+  CUtensorMap tmap;            // {k_stride, capacity} int8, box {128, 128}, SWIZZLE_128B
+};
+
+#define GB_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+      return e__ == cudaErrorMemoryAllocation ? GB_ERR_OOM : GB_ERR_CUDA;                      \
+    }                                                                                          \
+  } while (0)
+
+// gb_pack.cu
+int launch_pack(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int is_ascii,
+                int64_t row0, int64_t n_rows);
+int launch_gather_rows(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int8_t* dst);
+int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int mode,
+                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool);
+
+// gb_gram.cu
+int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_rows, int64_t k_stride);
+int launch_gram(Ctx* ctx, const CUtensorMap& tmap_panel, const CUtensorMap& tmap_scratch,
+                const GramParams& prm);
+
+// gb_solve.cu
+struct SolveWin {        // per-window solve descriptor
+  int n_t, n_u;
+  int ld_t, ld_u;        // leading dims of B11 (column-major, lower) and B21^T (row-major n_t x ld_u)
+  long long off_tt;      // element offset of B11 / L in the TT buffer
+  long long off_ut;      // element offset of B21^T / W in the UT buffer
+  long long off_t;       // offset into per-measured arrays (z_t, y)
+  long long off_u;       // offset into per-unmeasured arrays (z_u, info_u)
+  long long off_dinv;    // element offset of this window's inverted 64x64 diagonal blocks
+};
+int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins, double* d_tt,
+                    double* d_dinv, const double* d_zt, double* d_y, int* d_status, double shift,
+                    int want_y);
+int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins,
+                         const double* d_tt, const double* d_dinv, double* d_ut, const double* d_y,
+                         double* d_zu, double* d_info);
+int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins,
+                      const double* d_src, double* d_dst, double shift);
+
+}  // namespace gb

@@ -1,0 +1,148 @@
+// gb_pack.cu -- K0: panel packing and per-row statistics (HBM-bound byte streams).
+//
+// The reference keeps genotypes as one std::string of '0'/'1'/'2' per population on every Snp
+// (snp.h:109, filled by ReadGenotype gauss.cpp:720-785) and re-derives sum x, sum x^2 for every
+// SNP pair.  Here a SNP is packed ONCE into an int8 row whose population blocks start on
+// 32-column boundaries (zero padded: zeros are neutral for sum xy, sum x, sum x^2), and the
+// per-population integer sums are computed once per SNP.
+#include "gb_common.cuh"
+
+namespace gb {
+
+namespace {
+
+// One CTA per SNP row; warp w packs populations w, w+8, ...  Each lane moves 4 consecutive
+// dosages per step: 4 byte loads (source population offsets are unaligned) and one 32-bit store.
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_ascii,
+                 int8_t* __restrict__ dst, int k_stride, long long row0, int n_pops,
+                 const int* __restrict__ pop_sizes, const int* __restrict__ koff,
+                 int32_t* __restrict__ sx, int32_t* __restrict__ sxx, long long stat_ld) {
+  const long long row = blockIdx.x;
+  const uint8_t* s = src + row * src_stride;
+  int8_t* d = dst + (row0 + row) * (long long)k_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = is_ascii ? 48 : 0;
+  // source offset of population p = sum of sizes before it
+  int src_off = 0;
+  int next_p = 0;
+  for (int p = warp; p < n_pops; p += 8) {
+    for (; next_p < p; next_p++) src_off += pop_sizes[next_p];
+    const int m = pop_sizes[p];
+    const int kp = (m + K_ATOM - 1) / K_ATOM * K_ATOM;
+    const uint8_t* sp = s + src_off;
+    uint32_t* dp = reinterpret_cast<uint32_t*>(d + koff[p]);
+    int sum = 0, sq = 0;
+    for (int j = lane * 4; j < kp; j += 128) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        int v = 0;
+        if (j + b < m) v = (int)(signed char)((int)sp[j + b] - sub);
+        sum += v;
+        sq += v * v;
+        word |= (uint32_t)(v & 0xff) << (8 * b);
+      }
+      dp[j >> 2] = word;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+      sx[(long long)p * stat_ld + row0 + row] = sum;
+      sxx[(long long)p * stat_ld + row0 + row] = sq;
+    }
+  }
+  // zero the tail between the last population block and the row stride
+  const int k_end = koff[n_pops - 1] + (pop_sizes[n_pops - 1] + K_ATOM - 1) / K_ATOM * K_ATOM;
+  for (int j = k_end + threadIdx.x * 4; j < k_stride; j += 256 * 4)
+    *reinterpret_cast<uint32_t*>(d + j) = 0u;
+}
+
+// dst[i] = panel row rows[i]; 16-byte vectors, one CTA per row.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const int8_t* __restrict__ panel, int k_stride, const int32_t* __restrict__ rows,
+                   int8_t* __restrict__ dst) {
+  const long long i = blockIdx.x;
+  const uint4* s = reinterpret_cast<const uint4*>(panel + (long long)rows[i] * k_stride);
+  uint4* d = reinterpret_cast<uint4*>(dst + i * (long long)k_stride);
+  const int n16 = k_stride >> 4;
+  for (int j = threadIdx.x; j < n16; j += 256) d[j] = s[j];
+}
+
+// Per listed row: the standard deviation the reference derives from CalWgtCov(g,g)
+// (distmix.cpp:180-187, computeLD.cpp:100-103) or the pooled denominator factor of CalCor
+// (util.cpp:67).  One thread per row, populations in panel order so the fp64 operation order
+// is the reference's.
+__global__ void row_prep_kernel(const int32_t* __restrict__ rows, long long n, int mode, int n_pops,
+                                const int* __restrict__ pop_sizes, const double* __restrict__ coef,
+                                const double* __restrict__ wgt, const int32_t* __restrict__ sx,
+                                const int32_t* __restrict__ sxx, long long stat_ld,
+                                double* __restrict__ sd, int32_t* __restrict__ pool) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long prow = rows[i];
+  if (mode == GRAM_MIX) {
+    double wsumcov = 0.0, wsum_mi_mj = 0.0, wsum_mi = 0.0;
+    for (int p = 0; p < n_pops; p++) {
+      const int m = pop_sizes[p];
+      const long long s = sx[(long long)p * stat_ld + prow];
+      const long long q = sxx[(long long)p * stat_ld + prow];
+      const double d = (double)((long long)m * q - s * s);          // m*sumxy - sumx*sumy (exact)
+      wsumcov = __dadd_rn(wsumcov, __dmul_rn(coef[p], d));          // util.cpp:118
+      const double mean = __ddiv_rn((double)s, (double)m);
+      const double wm = __dmul_rn(wgt[p], mean);
+      wsum_mi_mj = __dadd_rn(wsum_mi_mj, __dmul_rn(wm, mean));      // util.cpp:119
+      wsum_mi = __dadd_rn(wsum_mi, wm);                             // util.cpp:120-121
+    }
+    const double cov = __dsub_rn(__dadd_rn(wsumcov, wsum_mi_mj), __dmul_rn(wsum_mi, wsum_mi));
+    sd[i] = __dsqrt_rn(cov);
+  } else {
+    long long s = 0, q = 0, n_ind = 0;
+    for (int p = 0; p < n_pops; p++) {
+      s += sx[(long long)p * stat_ld + prow];
+      q += sxx[(long long)p * stat_ld + prow];
+      n_ind += pop_sizes[p];
+    }
+    pool[i] = (int32_t)s;
+    // sqrt(num_samples*sumxsq - sumx*sumx)   (util.cpp:67)
+    sd[i] = __dsqrt_rn(__dsub_rn(__dmul_rn((double)n_ind, (double)q), __dmul_rn((double)s, (double)s)));
+  }
+}
+
+}  // namespace
+
+int launch_pack(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int is_ascii,
+                int64_t row0, int64_t n_rows) {
+  if (n_rows <= 0) return GB_OK;
+  pack_rows_kernel<<<(unsigned)n_rows, 256, 0, ctx->stream>>>(
+      static_cast<const uint8_t*>(dev_src), src_stride, is_ascii, panel->d_rows, panel->k_stride, row0,
+      panel->n_pops, panel->d_pop_sizes, panel->d_koff, panel->d_sx, panel->d_sxx, panel->capacity);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+int launch_gather_rows(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int8_t* dst) {
+  if (n <= 0) return GB_OK;
+  gather_rows_kernel<<<(unsigned)n, 256, 0, ctx->stream>>>(panel->d_rows, panel->k_stride, d_rows, dst);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int mode,
+                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool) {
+  if (n <= 0) return GB_OK;
+  const int bs = 128;
+  row_prep_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, ctx->stream>>>(
+      d_rows, n, mode, panel->n_pops, panel->d_pop_sizes, d_coef, d_wgt, panel->d_sx, panel->d_sxx,
+      panel->capacity, d_sd, d_pool);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+}  // namespace gb

@@ -1,0 +1,167 @@
+/*
+ * gauss_b200.h -- C-ABI of the B200-native window hot path of GAUSS.
+ *
+ * This is the drop-in boundary.  The reference has no plugin API; the seam
+ * these entry points replace is the body of
+ *     void run_dist   (std::vector<Snp*>&, Arguments&)   reference src/dist.cpp:129-227
+ *     void run_distmix(std::vector<Snp*>&, Arguments&)   reference src/distmix.cpp:138-253
+ *     the LD block of computeLD()                         reference src/computeLD.cpp:95-116
+ * and the arithmetic they call in src/util.cpp:49-70 (CalCor), 103-124 (CalWgtCov),
+ * 262-264 (MpMatMat), 298-300 (InvMat), 302-318 (MakePosDef).  The Rcpp entry points
+ * (src/RcppExports.cpp:31-47,65-82,85-102) keep their signatures; INTEGRATION.md shows the
+ * binding a maintainer adds.
+ *
+ * Conventions: every function returns an int status (GB_OK == 0), never throws, never exits,
+ * never calls back into R.  The caller owns all host buffers; the library owns device memory
+ * behind opaque handles.  One gb_ctx drives one GPU; calls on one ctx are not thread-safe,
+ * calls on different ctxs are independent (one host thread or process per GPU).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * GB_ERR_NO_DEVICE / GB_ERR_CUDA.
+ */
+#ifndef GAUSS_B200_H
+#define GAUSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_VERSION 100
+
+#if defined(__GNUC__)
+#define GB_API __attribute__((visibility("default")))
+#else
+#define GB_API
+#endif
+
+enum gb_status {
+  GB_OK = 0,
+  GB_ERR_BAD_ARG = 1,
+  GB_ERR_CUDA = 2,
+  GB_ERR_NO_DEVICE = 3,
+  GB_ERR_OOM = 4,
+  /* "Not enough number of SNPs loaded - DIST[MIX] not performed": dist.cpp:146-151, distmix.cpp:154-160 */
+  GB_ERR_TOO_FEW_MEASURED = 5,
+  GB_ERR_TOO_FEW_UNMEASURED = 6,
+  /* B11 is not certified to satisfy lambda_min >= min_abs_eig, i.e. the reference's MakePosDef
+   * (util.cpp:302-318) would have modified it; no eigen-clip path exists on the device. */
+  GB_ERR_NOT_PD = 7,
+  GB_ERR_UNSUPPORTED = 8
+};
+
+typedef struct gb_ctx gb_ctx;     /* one per GPU */
+typedef struct gb_panel gb_panel; /* HBM-resident packed reference panel */
+typedef struct gb_batch gb_batch; /* a planned set of windows on one panel */
+
+/* Hidden arguments of the reference (struct Arguments, gauss.h:44-62; defaults gauss.cpp:18-35). */
+typedef struct gb_params {
+  double lambda;              /* 0.1   ridge added as B11 diagonal := 1 + lambda (dist.cpp:172) */
+  double min_abs_eig;         /* 1e-5  MakePosDef threshold (dist.cpp:181) */
+  int min_num_measured_snp;   /* 10    window rejected if n_t <= this */
+  int min_num_unmeasured_snp; /* 10    window rejected if n_u <= this */
+  int check_pd;               /* 1: certify lambda_min(B11) > min_abs_eig with a shifted Cholesky
+                                 (GB_ERR_NOT_PD otherwise); 0: only detect factorisation breakdown */
+  int reserved;
+} gb_params;
+
+GB_API void gb_params_default(gb_params *p);
+GB_API int gb_version(void);
+GB_API const char *gb_status_string(int status);
+
+/* ---- context ------------------------------------------------------------------------------ */
+GB_API int gb_ctx_create(int device, gb_ctx **out);
+GB_API void gb_ctx_destroy(gb_ctx *ctx);
+/* Run all work of this ctx on a caller-owned cudaStream_t (NULL restores the ctx's own stream). */
+GB_API int gb_ctx_set_stream(gb_ctx *ctx, void *cuda_stream);
+GB_API int gb_ctx_synchronize(gb_ctx *ctx);
+/* Last error text of this ctx (or of ctx creation when ctx == NULL). */
+GB_API const char *gb_last_error(const gb_ctx *ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+GB_API int64_t gb_ctx_launch_count(const gb_ctx *ctx);
+
+/* ---- panel packing (new step hanging off ReadGenotype, gauss.cpp:720-785) ------------------ */
+/* pop_sizes[p] = individuals of the p-th FLAGGED population, in panel order -- exactly the
+ * strings Snp::genotype_vec_ holds (snp.h:109).  Rows are SNPs. */
+GB_API int gb_panel_create(gb_ctx *ctx, int n_pops, const int *pop_sizes, int64_t capacity_rows,
+                    gb_panel **out);
+GB_API void gb_panel_destroy(gb_panel *panel);
+GB_API int gb_panel_clear(gb_panel *panel); /* forget all rows, keep the allocation */
+GB_API int64_t gb_panel_num_rows(const gb_panel *panel);
+GB_API int64_t gb_panel_num_samples(const gb_panel *panel);
+/* Append SNP rows given as the reference stores them: n_rows * n_pops C strings, string
+ * (r, p) holding pop_sizes[p] chars '0'/'1'/'2' (any 7-bit char c packs as c - '0', like the
+ * reference's arithmetic).  HOST memory. */
+GB_API int gb_panel_append_strings(gb_panel *panel, int64_t n_rows, const char *const *pop_strings);
+/* Same rows as one flat HOST buffer: row r at rows + r*row_stride, populations concatenated
+ * (sum(pop_sizes) bytes).  is_ascii != 0: bytes are chars; 0: bytes are int8 dosages. */
+GB_API int gb_panel_append_host(gb_panel *panel, int64_t n_rows, const void *rows, int64_t row_stride,
+                         int is_ascii);
+/* Same, but the flat buffer already lives in DEVICE memory of this ctx's GPU. */
+GB_API int gb_panel_append_device(gb_panel *panel, int64_t n_rows, const void *dev_rows,
+                           int64_t row_stride, int is_ascii);
+
+/* ---- raw integer statistics (bit-exact parity surface) -------------------------------------- */
+/* Per-population Gram counts S^p[a][b] = sum_k x_a,k * x_b,k over population p, plus (optional)
+ * per-row sums: out_sxy [n_pops][n_a][n_b], out_sx / out_sxx [n_pops][n_a] (int32, HOST). */
+GB_API int gb_gram_counts(gb_ctx *ctx, gb_panel *panel, int64_t n_a, const int64_t *rows_a, int64_t n_b,
+                   const int64_t *rows_b, int32_t *out_sxy, int32_t *out_sx, int32_t *out_sxx);
+
+/* ---- one window, host in / host out (what run_dist / run_distmix / computeLD call) ---------- */
+/* rows_t: panel rows of the measured SNPs (type 1, whole extended window, bp order);
+ * rows_u: panel rows of the unmeasured SNPs (type 0 inside [start_bp,end_bp]);
+ * z_t: their input Z-scores.  Outputs, per unmeasured SNP: z_u = normalised imputed z
+ * (dist.cpp:195-201), info_u = |b21 B11^-1 b12|. */
+GB_API int gb_window_dist(gb_ctx *ctx, gb_panel *panel, int64_t n_t, const int64_t *rows_t, int64_t n_u,
+                   const int64_t *rows_u, const double *z_t, const gb_params *params, double *z_u,
+                   double *info_u);
+/* pop_wgt: weights of the flagged populations in panel order (Arguments::pop_wgt_vec). */
+GB_API int gb_window_distmix(gb_ctx *ctx, gb_panel *panel, int64_t n_t, const int64_t *rows_t,
+                      int64_t n_u, const int64_t *rows_u, const double *z_t, const double *pop_wgt,
+                      const gb_params *params, double *z_u, double *info_u);
+/* computeLD block: cormat is n x n (symmetric; column-major == row-major), diagonal exactly 1.0. */
+GB_API int gb_window_ld(gb_ctx *ctx, gb_panel *panel, int64_t n, const int64_t *rows,
+                 const double *pop_wgt, double *cormat);
+/* Parity/debug surface: the correlation blocks the solve consumes.  pop_wgt == NULL selects the
+ * pooled Pearson r of dist().  B11 is n_t x n_t symmetric with diagonal 1+lambda; B21 is
+ * n_u x n_t row-major. */
+GB_API int gb_window_cor(gb_ctx *ctx, gb_panel *panel, int64_t n_t, const int64_t *rows_t, int64_t n_u,
+                  const int64_t *rows_u, const double *pop_wgt, const gb_params *params,
+                  double *B11, double *B21);
+
+/* ---- many windows on a resident panel (genome driver / benchmark path) ---------------------- */
+/* Window w uses rows_t[t_off[w] .. t_off[w+1]) and rows_u[u_off[w] .. u_off[w+1]); z_t is
+ * aligned with rows_t.  pop_wgt == NULL selects dist().  Planning uploads the descriptors once. */
+GB_API int gb_batch_create(gb_ctx *ctx, gb_panel *panel, int64_t n_windows, const int64_t *t_off,
+                    const int64_t *rows_t, const int64_t *u_off, const int64_t *rows_u,
+                    const double *z_t, const double *pop_wgt, const gb_params *params,
+                    gb_batch **out);
+GB_API void gb_batch_destroy(gb_batch *batch);
+/* Enqueue every kernel of the batch on the ctx stream (asynchronous). */
+GB_API int gb_batch_run(gb_batch *batch);
+/* Copy results to HOST (aligned with rows_u) and per-window status codes; synchronises. */
+GB_API int gb_batch_fetch(gb_batch *batch, double *z_u, double *info_u, int *window_status);
+/* Algorithmic work of the batch: int8 Gram ops, solve fp64 flops, panel bytes. */
+GB_API int gb_batch_work(const gb_batch *batch, double *gram_ops, double *solve_flops,
+                  double *panel_bytes);
+/* Enqueue only one stage (profiling / roofline timing): 0 = row statistics, 1 = Gram+epilogue,
+ * 2 = Cholesky, 3 = triangular solve + finalise. */
+GB_API int gb_batch_run_stage(gb_batch *batch, int stage);
+
+/* ---- host-side mirror of the reference seam --------------------------------------------------- */
+/* run_dist / run_distmix on a bp-sorted snp_vec given as parallel arrays: type (0/1/2), bp, z,
+ * info and, per SNP, n_pops genotype strings (may be NULL for type 2).  Splits measured /
+ * unmeasured exactly as dist.cpp:132-141, enforces the thresholds (dist.cpp:146), packs the
+ * strings, runs the window on the GPU and writes z/info of the imputed SNPs back in place
+ * (SetZ/SetInfo, dist.cpp:200-202).  pop_wgt == NULL -> run_dist. */
+GB_API int gb_run_window_strings(gb_ctx *ctx, int64_t n_snps, const int *type, const long long *bp,
+                          double *z, double *info, const char *const *pop_strings, int n_pops,
+                          const int *pop_sizes, const double *pop_wgt, long long start_bp,
+                          long long end_bp, const gb_params *params, int *n_measured,
+                          int *n_unmeasured);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAUSS_B200_H */

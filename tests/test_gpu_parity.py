@@ -1,0 +1,253 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle and the
+golden vectors minted from the reference's own code.  Bars (BASELINE.json north_star):
+Gram counts bit-exact; correlations, imputed Z and info within 1e-6 absolute (fp64)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import gauss_b200 as gb
+from gauss_b200 import synth
+from helpers import small_case, split_rows
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6        # the tolerance north_star states
+TIGHT = 1e-10     # what fp64 Cholesky-vs-LU actually achieves on these well-conditioned windows
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("pgc2_"))
+
+
+def make_panel(ctx, g, pop_sizes, mode="i8"):
+    p = gb.Panel(ctx, pop_sizes, len(g))
+    if mode == "i8":
+        p.append_host(g.astype(np.int8), is_ascii=False)
+    elif mode == "ascii":
+        p.append_host((g.astype(np.int16) + 48).astype(np.uint8), is_ascii=True)
+    assert p.n_rows == len(g)
+    return p
+
+
+# ------------------------------------------------------------------ integer surface: bit-exact
+@pytest.mark.parametrize("mode", ["i8", "ascii"])
+def test_gram_counts_bit_exact(gpu_ctx, oracle, mode):
+    c = small_case(seed=21, n_snps=330, pop_sizes=(61, 103, 40, 25, 2, 330, 97, 128, 31, 33))
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"], mode)
+    rows_a = np.arange(0, 200)
+    rows_b = np.arange(193, 330)           # ragged: 200 x 137, overlapping ranges
+    sxy, sx, sxx = panel.gram_counts(rows_a, rows_b)
+    o_sxy, o_sx, o_sxx = oracle.gram_counts(c["g"][rows_a], c["g"][rows_b], c["pop_sizes"])
+    np.testing.assert_array_equal(sxy, o_sxy)
+    np.testing.assert_array_equal(sx, o_sx)
+    np.testing.assert_array_equal(sxx, o_sxx)
+
+
+def test_gram_counts_gathered_rows(gpu_ctx, oracle):
+    """Non-contiguous row lists go through the gather-to-scratch path."""
+    c = small_case(seed=22, n_snps=300)
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"])
+    rng = np.random.default_rng(0)
+    rows_a = np.sort(rng.choice(300, 150, replace=False))
+    rows_b = rng.permutation(300)[:70]
+    sxy, _, _ = panel.gram_counts(rows_a, rows_b)
+    o_sxy, _, _ = oracle.gram_counts(c["g"][rows_a], c["g"][rows_b], c["pop_sizes"])
+    np.testing.assert_array_equal(sxy, o_sxy)
+
+
+def test_gram_counts_33kg_shape(gpu_ctx):
+    """Full K extent (32,147 individuals, 21 populations): exactness via numpy int64 matmul."""
+    _, sizes, _ = synth.flagged_33kg_pgc2()
+    g = synth.make_genotypes(160, sizes, seed=3)
+    panel = make_panel(gpu_ctx, g, sizes)
+    sxy, sx, sxx = panel.gram_counts(np.arange(0, 130), np.arange(30, 160))
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    for p in range(len(sizes)):
+        a = g[0:130, offs[p]:offs[p + 1]].astype(np.int32)
+        b = g[30:160, offs[p]:offs[p + 1]].astype(np.int32)
+        np.testing.assert_array_equal(sxy[p], a @ b.T)
+        np.testing.assert_array_equal(sx[p], a.sum(1))
+        np.testing.assert_array_equal(sxx[p], (a * a).sum(1))
+
+
+# ------------------------------------------------------------------ correlations
+@pytest.mark.parametrize("mix", [True, False])
+def test_correlation_blocks_match_oracle(gpu_ctx, oracle, mix):
+    c = small_case(seed=23, n_snps=420, pop_sizes=(33, 129, 500, 64, 7))
+    meas, unme = split_rows(c)
+    w = c["w"] if mix else None
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"])
+    B11, B21 = panel.window_cor(meas, unme, w)
+    r = oracle.run_window(c["type"], c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"], dump=True)
+    assert np.abs(B11 - r["B11"]).max() <= 1e-13
+    assert np.abs(B21 - r["B21"]).max() <= 1e-13
+    # the epilogue keeps the reference's fp64 operation order: entries should be bit-identical
+    assert (B21 == r["B21"]).mean() > 0.999
+    assert (B11 == r["B11"]).mean() > 0.999
+    np.testing.assert_array_equal(np.diag(B11), np.full(len(meas), 1.1))
+
+
+# ------------------------------------------------------------------ imputation
+@pytest.mark.parametrize("mix", [True, False])
+def test_window_imputation_matches_oracle(gpu_ctx, oracle, mix):
+    c = small_case(seed=24, n_snps=500, pop_sizes=(61, 103, 40, 25, 2, 330, 97), measured_frac=0.4, core=(30, 470))
+    meas, unme = split_rows(c)
+    w = c["w"] if mix else None
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"])
+    if mix:
+        z, info, rc = panel.window_distmix(meas, unme, c["z"][meas], w)
+    else:
+        z, info, rc = panel.window_dist(meas, unme, c["z"][meas])
+    assert rc == gb.GB_OK
+    r = oracle.run_window(c["type"], c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"])
+    assert r["rc"] == 0 and r["n_t"] == len(meas) and r["n_u"] == len(unme)
+    assert np.abs(z - r["z"][unme]).max() <= TOL
+    assert np.abs(info - r["info"][unme]).max() <= TOL
+    assert np.abs(z - r["z"][unme]).max() <= TIGHT
+    assert np.abs(info - r["info"][unme]).max() <= TIGHT
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_against_golden_reference_vectors(gpu_ctx, path):
+    d = np.load(path)
+    panel = make_panel(gpu_ctx, d["g"], d["pop_sizes"])
+    meas, unme = d["meas"], d["unme"]
+    z, info, _ = panel.window_distmix(meas, unme, d["z"][meas], d["w"])
+    assert np.abs(z - d["mix_z"][unme]).max() <= TOL and np.abs(info - d["mix_info"][unme]).max() <= TOL
+    z, info, _ = panel.window_dist(meas, unme, d["z"][meas])
+    assert np.abs(z - d["dist_z"][unme]).max() <= TOL and np.abs(info - d["dist_info"][unme]).max() <= TOL
+    ld, _ = panel.window_ld(meas, d["w"])
+    assert np.abs(ld - d["ld"]).max() <= TOL
+    np.testing.assert_array_equal(np.diag(ld), np.ones(len(meas)))
+    np.testing.assert_array_equal(ld, ld.T)
+
+
+def test_compute_ld_matches_oracle(gpu_ctx, oracle):
+    c = small_case(seed=25, n_snps=300, pop_sizes=(90, 40, 260))
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"])
+    rows = np.arange(17, 290)
+    ld, _ = panel.window_ld(rows, c["w"])
+    ref = oracle.compute_ld(c["g"][rows], c["pop_sizes"], c["w"])
+    assert np.abs(ld - ref).max() <= 1e-13
+    assert (ld == ref).mean() > 0.999
+
+
+def test_host_mirror_of_run_distmix_strings(gpu_ctx, oracle):
+    """gb_run_window_strings takes what run_distmix takes: bp-sorted SNPs with type, z and one
+    genotype string per population (snp.h:109)."""
+    c = small_case(seed=26, n_snps=260, pop_sizes=(50, 7, 211, 96))
+    offs = np.concatenate([[0], np.cumsum(c["pop_sizes"])])
+    chars = (c["g"].astype(np.int16) + 48).astype(np.uint8)
+    strings = [[chars[i, offs[p]:offs[p + 1]].tobytes() for p in range(len(c["pop_sizes"]))]
+               for i in range(len(chars))]
+    for w in (c["w"], None):
+        out = gpu_ctx.run_window_strings(c["type"], c["bp"], c["z"], np.ones(len(chars)), strings, c["pop_sizes"],
+                                         w, c["start_bp"], c["end_bp"])
+        r = oracle.run_window(c["type"], c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"])
+        assert out["rc"] == 0 and out["n_t"] == r["n_t"] and out["n_u"] == r["n_u"]
+        assert np.abs(out["z"] - r["z"]).max() <= TOL       # measured / out-of-window SNPs untouched
+        assert np.abs(out["info"] - r["info"]).max() <= TOL
+
+
+def test_too_few_snps_status_codes(gpu_ctx):
+    c = small_case(seed=27, n_snps=100)
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"])
+    z, info, rc = panel.window_distmix(np.arange(10), np.arange(20, 60), np.zeros(10), c["w"],
+                                       allow=(gb.api.GB_ERR_TOO_FEW_MEASURED,))
+    assert rc == gb.api.GB_ERR_TOO_FEW_MEASURED          # n_t <= 10, distmix.cpp:154
+    z, info, rc = panel.window_dist(np.arange(30), np.arange(40, 50), np.zeros(30),
+                                    allow=(gb.api.GB_ERR_TOO_FEW_UNMEASURED,))
+    assert rc == gb.api.GB_ERR_TOO_FEW_UNMEASURED        # n_u <= 10
+    _, rc = panel.window_ld(np.arange(10), c["w"], allow=(gb.api.GB_ERR_TOO_FEW_MEASURED,))
+    assert rc == gb.api.GB_ERR_TOO_FEW_MEASURED          # computeLD.cpp:89
+
+
+def test_not_positive_definite_is_reported(gpu_ctx):
+    """lambda = 0 with a duplicated measured SNP makes B11 singular: the reference's MakePosDef would
+    rewrite the matrix, so the window must be flagged instead of silently differing."""
+    c = small_case(seed=28, n_snps=120)
+    g = c["g"].copy()
+    g[5] = g[4]
+    panel = make_panel(gpu_ctx, g, c["pop_sizes"])
+    p = gb.Params.default()
+    p.lambda_ = 0.0
+    _, _, rc = panel.window_distmix(np.arange(0, 40), np.arange(40, 120), np.zeros(40), c["w"], p,
+                                    allow=(gb.api.GB_ERR_NOT_PD,))
+    assert rc == gb.api.GB_ERR_NOT_PD
+    # a monomorphic SNP has zero variance -> NaN correlations (no guard at distmix.cpp:196)
+    g2 = c["g"].copy()
+    g2[7] = 0
+    panel2 = make_panel(gpu_ctx, g2, c["pop_sizes"])
+    _, _, rc = panel2.window_distmix(np.arange(0, 40), np.arange(40, 120), np.zeros(40), c["w"],
+                                     allow=(gb.api.GB_ERR_NOT_PD,))
+    assert rc == gb.api.GB_ERR_NOT_PD
+
+
+def test_batch_equals_single_windows_and_placement_invariance(gpu_ctx, oracle):
+    """Several windows of different sizes in one batch; results must not depend on batching, on
+    the row layout (interleaved vs measured/unmeasured blocks) or on which launch computed them."""
+    c = small_case(seed=29, n_snps=900, pop_sizes=(61, 103, 40, 25, 2, 330, 97), measured_frac=0.3, core=(0, 900))
+    g, t = c["g"], c["type"]
+    panel = make_panel(gpu_ctx, g, c["pop_sizes"])
+    wins = [(0, 300), (150, 520), (400, 900), (880, 900), (300, 700)]
+    t_rows, u_rows, t_off, u_off = [], [], [0], [0]
+    for lo, hi in wins:
+        idx = np.arange(lo, hi)
+        t_rows.append(idx[t[lo:hi] == 1])
+        u_rows.append(idx[t[lo:hi] == 0])
+        t_off.append(t_off[-1] + len(t_rows[-1]))
+        u_off.append(u_off[-1] + len(u_rows[-1]))
+    rows_t, rows_u = np.concatenate(t_rows), np.concatenate(u_rows)
+    batch = gb.Batch(panel, t_off, rows_t, u_off, rows_u, c["z"][rows_t], c["w"])
+    batch.run()
+    z, info, status = batch.fetch()
+    assert status[3] in (gb.api.GB_ERR_TOO_FEW_MEASURED, gb.api.GB_ERR_TOO_FEW_UNMEASURED)
+    assert np.isnan(z[u_off[3]:u_off[4]]).all()
+    for k, (lo, hi) in enumerate(wins):
+        if k == 3:
+            continue
+        assert status[k] == gb.GB_OK
+        z1, i1, _ = panel.window_distmix(t_rows[k], u_rows[k], c["z"][t_rows[k]], c["w"])
+        np.testing.assert_array_equal(z[u_off[k]:u_off[k + 1]], z1)
+        np.testing.assert_array_equal(info[u_off[k]:u_off[k + 1]], i1)
+    # same SNPs re-packed as [measured block | unmeasured block]: contiguous TMA path, no gather
+    order = np.concatenate([np.where(t == 1)[0], np.where(t == 0)[0]])
+    inv = np.empty_like(order)
+    inv[order] = np.arange(len(order))
+    panel2 = make_panel(gpu_ctx, g[order], c["pop_sizes"])
+    k = 1
+    z2, i2, _ = panel2.window_distmix(inv[t_rows[k]], inv[u_rows[k]], c["z"][t_rows[k]], c["w"])
+    np.testing.assert_array_equal(z[u_off[k]:u_off[k + 1]], z2)
+    np.testing.assert_array_equal(info[u_off[k]:u_off[k + 1]], i2)
+    # and the oracle agrees on one of them
+    lo, hi = wins[1]
+    r = oracle.run_window(t[lo:hi], c["bp"][lo:hi], c["z"][lo:hi], g[lo:hi], c["pop_sizes"], c["w"], 0, 10**15)
+    assert np.abs(r["z"][t[lo:hi] == 0] - z[u_off[1]:u_off[2]]).max() <= TIGHT
+
+
+def test_33kg_shaped_window_matches_oracle(gpu_ctx, oracle):
+    """BASELINE config #2 shape at a size the oracle finishes in seconds: 21 flagged populations,
+    32,147 individuals, PGC2 ancestry weights (sum 1.061, not renormalised)."""
+    _, sizes, w = synth.flagged_33kg_pgc2()
+    n = 520
+    g = synth.make_genotypes(n, sizes, seed=30)
+    rng = np.random.default_rng(30)
+    t = (rng.random(n) < 0.35).astype(np.int32)
+    bp = np.arange(n, dtype=np.int64) * 300 + 1
+    zin = rng.standard_normal(n) * 1.34
+    meas, unme = np.where(t == 1)[0], np.where(t == 0)[0]
+    panel = make_panel(gpu_ctx, g, sizes)
+    z, info, rc = panel.window_distmix(meas, unme, zin[meas], w)
+    assert rc == gb.GB_OK
+    r = oracle.run_window(t, bp, zin, g, sizes, w, 0, 10**12)
+    assert np.abs(z - r["z"][unme]).max() <= TOL and np.abs(info - r["info"][unme]).max() <= TOL
+    assert np.abs(z - r["z"][unme]).max() <= 1e-9
+    # size-independent properties: info in (0, 1], flipping the sign of Z flips the imputed z
+    assert (info > 0).all() and (info <= 1.0 + 1e-12).all()
+    z_neg, info_neg, _ = panel.window_distmix(meas, unme, -zin[meas], w)
+    np.testing.assert_array_equal(z_neg, -z)
+    np.testing.assert_array_equal(info_neg, info)
+    # linearity in Z1 (dist.cpp:194): z(a + b) == z(a) + z(b) up to rounding
+    za, _, _ = panel.window_distmix(meas, unme, np.ones(len(meas)), w)
+    zb, _, _ = panel.window_distmix(meas, unme, zin[meas] + 1.0, w)
+    assert np.abs(zb - (z + za)).max() <= 1e-9
