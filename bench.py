@@ -215,7 +215,10 @@ def run_gpu(args):
     rows_t, rows_u, z_t = np.concatenate(rows_t), np.concatenate(rows_u), np.concatenate(z_t)
 
     ctx = gb.Context(local)
-    stream = torch.cuda.current_stream(dev)
+    # all library work and all timing events go on ONE explicit (non-default) torch stream
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     # ---- synthetic panel, generated on the device, packed once (K0)

@@ -32,17 +32,20 @@ struct gb_batch {
   std::vector<SolveWin> h_wins;       // aligned with `active`
   std::vector<GramTile> h_tiles;
   int64_t n_gather = 0;
+  int n_chol_wins = 0, max_nt = 0, max_nu = 0;
   double work_gram_ops = 0, work_solve_flops = 0, work_panel_bytes = 0;
   long long tt_elems = 0, ut_elems = 0, dinv_elems = 0, counts_elems = 0;
   // device
   int32_t *d_rows_t = nullptr, *d_rows_u = nullptr, *d_gather = nullptr;
   int32_t *d_pool_t = nullptr, *d_pool_u = nullptr;
-  double *d_sd_t = nullptr, *d_sd_u = nullptr;
+  double *d_sd_t = nullptr, *d_sd_u = nullptr, *d_rq_t = nullptr;
+  int* d_skip = nullptr;
+  double gneg = 0.0;  // (sum(w)-1)_+ * max(w), +inf when the analytic PD bound does not apply
   double *d_zt = nullptr, *d_y = nullptr, *d_zu = nullptr, *d_info = nullptr;
-  double *d_tt = nullptr, *d_tt_shift = nullptr, *d_ut = nullptr, *d_dinv = nullptr;
+  double *d_tt = nullptr, *d_ut = nullptr, *d_dinv = nullptr;
   double *d_coef = nullptr, *d_wgt = nullptr;
   int32_t* d_counts = nullptr;
-  int *d_status = nullptr, *d_status_pd = nullptr;
+  int* d_status = nullptr;
   SolveWin* d_wins = nullptr;
   GramTile* d_tiles = nullptr;
   int8_t* d_scratch = nullptr;
@@ -77,9 +80,9 @@ int check_device(Ctx* ctx) {
 }
 
 void free_batch_device(gb_batch* b) {
-  void* ptrs[] = {b->d_rows_t, b->d_rows_u, b->d_gather, b->d_pool_t, b->d_pool_u, b->d_sd_t, b->d_sd_u,
-                  b->d_zt, b->d_y, b->d_zu, b->d_info, b->d_tt, b->d_tt_shift, b->d_ut, b->d_dinv,
-                  b->d_coef, b->d_wgt, b->d_counts, b->d_status, b->d_status_pd, b->d_wins, b->d_tiles,
+  void* ptrs[] = {b->d_rows_t, b->d_rows_u, b->d_gather, b->d_pool_t, b->d_pool_u, b->d_sd_t, b->d_sd_u, b->d_rq_t, b->d_skip,
+                  b->d_zt, b->d_y, b->d_zu, b->d_info, b->d_tt, b->d_ut, b->d_dinv,
+                  b->d_coef, b->d_wgt, b->d_counts, b->d_status, b->d_wins, b->d_tiles,
                   b->d_scratch};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, b->ctx->stream);
@@ -141,6 +144,16 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
       }
     }
   }
+  if (b->mode == GRAM_MIX && pop_wgt) {
+    double sw = 0.0, wmax = 0.0;
+    bool applies = true;
+    for (int p = 0; p < pn->n_pops; p++) {
+      sw += pop_wgt[p];
+      wmax = std::max(wmax, pop_wgt[p]);
+      if (!(pop_wgt[p] >= 0.0) || pn->pop_sizes[p] < 2) applies = false;
+    }
+    b->gneg = applies ? std::max(0.0, sw - 1.0) * wmax : std::numeric_limits<double>::infinity();
+  }
   gp.mode = b->counts_mode ? GRAM_COUNTS : b->mode;
   gp.mirror = b->ld_mode ? 1 : 0;
   gp.diag = b->ld_mode ? 1.0 : 1.0 + b->params.lambda;   // computeLD.cpp:107 vs dist.cpp:172
@@ -178,6 +191,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     sw.off_tt = b->tt_elems;
     sw.off_ut = b->ut_elems;
     sw.off_dinv = b->dinv_elems;
+    sw.flags = 1;
     long long counts_off = b->counts_elems;
     if (b->counts_mode) {
       b->counts_elems += (long long)nu * nt;
@@ -247,6 +261,22 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     }
   }
   b->n_gather = (int64_t)h_gather.size();
+  {
+    // heaviest windows first: the solve kernels map blockIdx.y to this list, and a window's cost
+    // grows with n_t^2, so this is longest-processing-time-first scheduling of their CTAs
+    std::vector<size_t> perm(b->h_wins.size());
+    for (size_t i = 0; i < perm.size(); i++) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(),
+                     [&](size_t a, size_t c) { return b->h_wins[a].n_t > b->h_wins[c].n_t; });
+    std::vector<SolveWin> hw(perm.size());
+    std::vector<int> act(perm.size());
+    for (size_t i = 0; i < perm.size(); i++) {
+      hw[i] = b->h_wins[perm[i]];
+      act[i] = b->active[perm[i]];
+    }
+    b->h_wins.swap(hw);
+    b->active.swap(act);
+  }
 
   // ---- device buffers
   int rc;
@@ -255,23 +285,39 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   if ((rc = dev_upload(ctx, &b->d_gather, h_gather))) return rc;
   if ((rc = dev_upload(ctx, &b->d_coef, h_coef))) return rc;
   if ((rc = dev_upload(ctx, &b->d_wgt, h_wgt))) return rc;
-  if ((rc = dev_upload(ctx, &b->d_wins, b->h_wins))) return rc;
+  {
+    // the PD certificate factors B11 - min_abs_eig*I in the same launches: its windows are appended
+    // after the real ones and live in the second half of the TT buffer
+    std::vector<SolveWin> all = b->h_wins;
+    if (b->params.check_pd && !b->ld_mode && !b->counts_mode)
+      for (SolveWin sw : b->h_wins) {
+        sw.off_tt += b->tt_elems;
+        sw.flags = 0;
+        all.push_back(sw);
+      }
+    b->n_chol_wins = (int)all.size();
+    if ((rc = dev_upload(ctx, &b->d_wins, all))) return rc;
+  }
+  for (const SolveWin& sw : b->h_wins) {
+    b->max_nt = std::max(b->max_nt, sw.n_t);
+    b->max_nu = std::max(b->max_nu, sw.n_u);
+  }
   if ((rc = dev_upload(ctx, &b->d_tiles, b->h_tiles))) return rc;
   if ((rc = dev_alloc(ctx, &b->d_sd_t, (size_t)b->n_t_total))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_rq_t, (size_t)b->n_t_total))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_skip, 2 * (size_t)nw + 2))) return rc;
   if ((rc = dev_alloc(ctx, &b->d_sd_u, (size_t)b->n_u_total))) return rc;
   if ((rc = dev_alloc(ctx, &b->d_pool_t, (size_t)b->n_t_total))) return rc;
   if ((rc = dev_alloc(ctx, &b->d_pool_u, (size_t)b->n_u_total))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_status, (size_t)nw + 1))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_status_pd, (size_t)nw + 1))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_status, 2 * (size_t)nw + 2))) return rc;
   if (b->counts_mode) {
     if ((rc = dev_alloc(ctx, &b->d_counts, (size_t)b->counts_elems * pn->n_pops))) return rc;
   } else {
-    if ((rc = dev_alloc(ctx, &b->d_tt, (size_t)b->tt_elems))) return rc;
+    const bool cert = b->params.check_pd && !b->ld_mode;
+    if ((rc = dev_alloc(ctx, &b->d_tt, (size_t)b->tt_elems * (cert ? 2 : 1)))) return rc;
     if (!b->ld_mode) {
       if ((rc = dev_alloc(ctx, &b->d_ut, (size_t)b->ut_elems))) return rc;
       if ((rc = dev_alloc(ctx, &b->d_dinv, (size_t)b->dinv_elems))) return rc;
-      if (b->params.check_pd)
-        if ((rc = dev_alloc(ctx, &b->d_tt_shift, (size_t)b->tt_elems))) return rc;
       if ((rc = dev_alloc(ctx, &b->d_zt, (size_t)b->n_t_total))) return rc;
       if ((rc = dev_alloc(ctx, &b->d_y, (size_t)b->n_t_total))) return rc;
       if ((rc = dev_alloc(ctx, &b->d_zu, (size_t)b->n_u_total))) return rc;
@@ -319,31 +365,37 @@ int run_stage(gb_batch* b, int stage) {
         if ((rc = launch_gather_rows(ctx, pn, b->d_gather, b->n_gather, b->d_scratch))) return rc;
       if (b->counts_mode) return GB_OK;
       if ((rc = launch_row_prep(ctx, pn, b->d_rows_t, b->n_t_total, b->mode, b->d_coef, b->d_wgt, b->d_sd_t,
-                                b->d_pool_t)))
+                                b->d_pool_t, b->d_rq_t)))
         return rc;
       return launch_row_prep(ctx, pn, b->d_rows_u, b->n_u_total, b->mode, b->d_coef, b->d_wgt, b->d_sd_u,
-                             b->d_pool_u);
+                             b->d_pool_u, nullptr);
     }
     case 1:
       return launch_gram(ctx, pn->tmap, b->tmap_scratch, b->gp);
     case 2: {
       if (b->ld_mode || b->counts_mode) return GB_OK;
-      GB_CUDA(cudaMemsetAsync(b->d_status, 0, sizeof(int) * (size_t)(b->n_windows + 1), ctx->stream));
-      GB_CUDA(cudaMemsetAsync(b->d_status_pd, 0, sizeof(int) * (size_t)(b->n_windows + 1), ctx->stream));
+      const int nreal = (int)b->h_wins.size();
+      GB_CUDA(cudaMemsetAsync(b->d_status, 0, sizeof(int) * (2 * (size_t)b->n_windows + 2), ctx->stream));
+      const int* skip = nullptr;
       if (b->params.check_pd) {
-        // certificate: Cholesky of B11 - min_abs_eig*I succeeds  <=>  lambda_min(B11) > min_abs_eig
-        if ((rc = launch_copy_shift(ctx, b->d_wins, b->h_wins, b->d_tt, b->d_tt_shift, b->params.min_abs_eig)))
+        // certificate that MakePosDef is a no-op: the analytic lower bound on lambda_min(B11) when it
+        // applies, else a Cholesky of B11 - min_abs_eig*I (succeeds <=> lambda_min > min_abs_eig)
+        if ((rc = launch_pd_bound(ctx, b->d_wins, nreal, b->d_rq_t, b->params.lambda, b->gneg,
+                                  b->params.min_abs_eig, b->d_skip)))
           return rc;
-        if ((rc = launch_cholesky(ctx, b->d_wins, b->h_wins, b->d_tt_shift, b->d_dinv, b->d_zt, b->d_y,
-                                  b->d_status_pd, 0.0, 0)))
+        if ((rc = launch_copy_shift(ctx, b->d_wins, nreal, b->d_tt, b->d_tt + b->tt_elems, b->params.min_abs_eig,
+                                    b->d_skip)))
           return rc;
+        skip = b->d_skip;
       }
-      return launch_cholesky(ctx, b->d_wins, b->h_wins, b->d_tt, b->d_dinv, b->d_zt, b->d_y, b->d_status, 0.0, 1);
+      if ((rc = launch_cholesky(ctx, b->d_wins, b->n_chol_wins, b->max_nt, b->d_tt, b->d_dinv, b->d_status, skip)))
+        return rc;
+      return launch_solve_y(ctx, b->d_wins, nreal, b->max_nt, b->d_tt, b->d_dinv, b->d_zt, b->d_y);
     }
     case 3:
       if (b->ld_mode || b->counts_mode) return GB_OK;
-      return launch_trsm_finalize(ctx, b->d_wins, b->h_wins, b->d_tt, b->d_dinv, b->d_ut, b->d_y, b->d_zu,
-                                  b->d_info);
+      return launch_trsm_finalize(ctx, b->d_wins, (int)b->h_wins.size(), b->max_nu, b->d_tt, b->d_dinv, b->d_ut,
+                                  b->d_y, b->d_zu, b->d_info);
     default:
       ctx->err = "unknown stage";
       return GB_ERR_BAD_ARG;
@@ -674,19 +726,19 @@ int gb_batch_fetch(gb_batch* b, double* z_u, double* info_u, int* window_status_
   Ctx* ctx = b->ctx;
   int rc = check_device(ctx);
   if (rc) return rc;
-  std::vector<int> st((size_t)b->n_windows + 1, 0), st_pd((size_t)b->n_windows + 1, 0);
+  const size_t nreal = b->h_wins.size();
+  std::vector<int> st(2 * (size_t)b->n_windows + 2, 0);
   if (b->n_u_total) {
     if (z_u) GB_CUDA(cudaMemcpyAsync(z_u, b->d_zu, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
     if (info_u) GB_CUDA(cudaMemcpyAsync(info_u, b->d_info, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  // d_status is indexed by position in the active list
-  GB_CUDA(cudaMemcpyAsync(st.data(), b->d_status, sizeof(int) * (size_t)b->n_windows, cudaMemcpyDeviceToHost, ctx->stream));
-  GB_CUDA(cudaMemcpyAsync(st_pd.data(), b->d_status_pd, sizeof(int) * (size_t)b->n_windows, cudaMemcpyDeviceToHost, ctx->stream));
+  // d_status is indexed by position in the factorisation list: [real windows | certificate copies]
+  GB_CUDA(cudaMemcpyAsync(st.data(), b->d_status, sizeof(int) * st.size(), cudaMemcpyDeviceToHost, ctx->stream));
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<int> st_w((size_t)b->n_windows, 0), st_pd_w((size_t)b->n_windows, 0);
   for (size_t a = 0; a < b->active.size(); a++) {
     st_w[(size_t)b->active[a]] = st[a];
-    st_pd_w[(size_t)b->active[a]] = st_pd[a];
+    if (b->params.check_pd) st_pd_w[(size_t)b->active[a]] = st[nreal + a];
   }
   int worst = GB_OK;
   const double nan = std::numeric_limits<double>::quiet_NaN();

@@ -112,7 +112,7 @@ int launch_pack(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride,
                 int64_t row0, int64_t n_rows);
 int launch_gather_rows(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int8_t* dst);
 int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int mode,
-                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool);
+                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq);
 
 // gb_gram.cu
 int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_rows, int64_t k_stride);
@@ -128,14 +128,18 @@ struct SolveWin {        // per-window solve descriptor
   long long off_t;       // offset into per-measured arrays (z_t, y)
   long long off_u;       // offset into per-unmeasured arrays (z_u, info_u)
   long long off_dinv;    // element offset of this window's inverted 64x64 diagonal blocks
+  int flags;             // bit 0: publish inv(L_kk) (real factorisation; clear for the PD-certificate copy)
+  int pad;
 };
-int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins, double* d_tt,
-                    double* d_dinv, const double* d_zt, double* d_y, int* d_status, double shift,
-                    int want_y);
-int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins,
-                         const double* d_tt, const double* d_dinv, double* d_ut, const double* d_y,
-                         double* d_zu, double* d_info);
-int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins,
-                      const double* d_src, double* d_dst, double shift);
+int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, double* d_tt, double* d_dinv,
+                    int* d_status, const int* d_skip);
+int launch_pd_bound(Ctx* ctx, const SolveWin* d_wins, int n_real, const double* d_rq_t, double lambda,
+                    double gneg, double min_abs_eig, int* d_skip);
+int launch_solve_y(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, const double* d_tt,
+                   const double* d_dinv, const double* d_zt, double* d_y);
+int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nu, const double* d_tt,
+                         const double* d_dinv, double* d_ut, const double* d_y, double* d_zu, double* d_info);
+int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double* d_src, double* d_dst,
+                      double shift, const int* d_skip);
 
 }  // namespace gb

@@ -206,7 +206,13 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
             sdst[p * TILE + idx] = sx;
             const double mean = (double)sx / prm.seg[p].m;       // sumx/m       (util.cpp:119)
             const double wm = __dmul_rn(prm.wgt[p], mean);       // wgt*(sumx/m)
-            if (side) hB[p * TILE + idx] = mean; else gA[p * TILE + idx] = wm;
+            // CalWgtCov(x, y): wsum_mi_mj += (wgt*(sumx/m))*(sumy/m) with x the FIRST argument.
+            // B21 rows call it with x = unmeasured (our A side); B11 / LD call it with x = the
+            // smaller SNP index, which in a lower-triangle tile is our B side.  Store the weighted
+            // mean on the x side and the plain mean on the y side so the product rounds identically.
+            const bool x_side = t.a_is_u ? (side == 0) : (side == 1);
+            if (side) hB[p * TILE + idx] = x_side ? wm : mean;
+            else gA[p * TILE + idx] = x_side ? wm : mean;
             wsum = __dadd_rn(wsum, wm);                          // wsum_mi += ... (util.cpp:120-121)
           }
           (side ? bjS : aiS)[idx] = wsum;
@@ -307,7 +313,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
             double cor = __ddiv_rn(cov, __dmul_rn(sd_r, sdB[c]));
             const long long gj = t.j0 + c;
             if (diag_tile && gi == gj) cor = prm.diag;
-            if (row_ok && c < t.b_valid) {
+            if (row_ok && c < t.b_valid && !(diag_tile && gi < gj)) {  // diagonal tiles: lower part only
               out[gj * t.ld_out + gi] = cor;
               if (prm.mirror) out[gi * t.ld_out + gj] = cor;
             }
@@ -328,7 +334,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
             double cor = __ddiv_rn(numer, __dmul_rn(sd_r, sdB[c]));
             const long long gj = t.j0 + c;
             if (diag_tile && gi == gj) cor = prm.diag;
-            if (row_ok && c < t.b_valid) {
+            if (row_ok && c < t.b_valid && !(diag_tile && gi < gj)) {
               out[gj * t.ld_out + gi] = cor;
               if (prm.mirror) out[gi * t.ld_out + gj] = cor;
             }

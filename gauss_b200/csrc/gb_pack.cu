@@ -80,12 +80,13 @@ __global__ void row_prep_kernel(const int32_t* __restrict__ rows, long long n, i
                                 const int* __restrict__ pop_sizes, const double* __restrict__ coef,
                                 const double* __restrict__ wgt, const int32_t* __restrict__ sx,
                                 const int32_t* __restrict__ sxx, long long stat_ld,
-                                double* __restrict__ sd, int32_t* __restrict__ pool) {
+                                double* __restrict__ sd, int32_t* __restrict__ pool,
+                                double* __restrict__ rq) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long prow = rows[i];
   if (mode == GRAM_MIX) {
-    double wsumcov = 0.0, wsum_mi_mj = 0.0, wsum_mi = 0.0;
+    double wsumcov = 0.0, wsum_mi_mj = 0.0, wsum_mi = 0.0, musq = 0.0;
     for (int p = 0; p < n_pops; p++) {
       const int m = pop_sizes[p];
       const long long s = sx[(long long)p * stat_ld + prow];
@@ -96,9 +97,11 @@ __global__ void row_prep_kernel(const int32_t* __restrict__ rows, long long n, i
       const double wm = __dmul_rn(wgt[p], mean);
       wsum_mi_mj = __dadd_rn(wsum_mi_mj, __dmul_rn(wm, mean));      // util.cpp:119
       wsum_mi = __dadd_rn(wsum_mi, wm);                             // util.cpp:120-121
+      musq = fma(mean, mean, musq);
     }
     const double cov = __dsub_rn(__dadd_rn(wsumcov, wsum_mi_mj), __dmul_rn(wsum_mi, wsum_mi));
     sd[i] = __dsqrt_rn(cov);
+    if (rq) rq[i] = musq / cov;   // feeds the analytic PD certificate (pd_bound_kernel)
   } else {
     long long s = 0, q = 0, n_ind = 0;
     for (int p = 0; p < n_pops; p++) {
@@ -109,6 +112,7 @@ __global__ void row_prep_kernel(const int32_t* __restrict__ rows, long long n, i
     pool[i] = (int32_t)s;
     // sqrt(num_samples*sumxsq - sumx*sumx)   (util.cpp:67)
     sd[i] = __dsqrt_rn(__dsub_rn(__dmul_rn((double)n_ind, (double)q), __dmul_rn((double)s, (double)s)));
+    if (rq) rq[i] = 0.0;
   }
 }
 
@@ -134,12 +138,12 @@ int launch_gather_rows(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int6
 }
 
 int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int mode,
-                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool) {
+                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq) {
   if (n <= 0) return GB_OK;
   const int bs = 128;
   row_prep_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, ctx->stream>>>(
       d_rows, n, mode, panel->n_pops, panel->d_pop_sizes, d_coef, d_wgt, panel->d_sx, panel->d_sxx,
-      panel->capacity, d_sd, d_pool);
+      panel->capacity, d_sd, d_pool, d_rq);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

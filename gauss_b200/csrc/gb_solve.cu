@@ -5,19 +5,21 @@
 //     W = L^-1 B21^T,  y = L^-1 Z1   ->   z = W^T y,  info = |colsumsq(W)|,  z_out = z / sqrt(info)
 // which equals b21 B11^-1 Z1 and |b21 B11^-1 b12| of the reference.
 // MakePosDef is a no-op whenever lambda_min(B11) >= min_abs_eig; that is certified by a second
-// Cholesky of B11 - min_abs_eig*I (succeeds  <=>  lambda_min > min_abs_eig); otherwise the window
-// is flagged GB_ERR_NOT_PD -- there is no eigen-clip path and no CPU fallback.
+// Cholesky of B11 - min_abs_eig*I (succeeds  <=>  lambda_min > min_abs_eig), run in the SAME
+// launches as the real factorisation (the shifted copies are just extra "windows"); otherwise
+// the window is flagged GB_ERR_NOT_PD -- there is no eigen-clip path and no CPU fallback.
 //
 // Storage: B11 / L column-major n_t x ld_t (lower triangle significant); B21^T / W row-major
 // n_t x ld_u (unmeasured SNPs contiguous).  Everything is blocked by NB = 64.
 //
 // Cholesky = right-looking, two kernels per block column k, batched over all windows:
 //   chol_panel_kernel   every CTA re-factors the 64x64 diagonal block in shared memory and inverts
-//                       it; CTA ib==k publishes inv(L_kk) and y_k; CTAs ib>k form
-//                       L_ik = A_ik inv(L_kk)^T
+//                       it; CTA ib==k publishes inv(L_kk); CTAs ib>k form L_ik = A_ik inv(L_kk)^T
 //   chol_update_kernel  trailing tiles A_ij -= L_ik L_jk^T
-// Triangular solve = one CTA per (window, 128 unmeasured SNPs): forward substitution by row
-// blocks, W written in place, column sums of squares and W^T y reduced in a fixed order.
+// solve_y_kernel        y = L^-1 Z1, one CTA per window (block forward substitution)
+// trsm_finalize_kernel  one CTA per (window, 128 unmeasured SNPs): forward substitution by row
+//                       blocks with cp.async double-buffered operand chunks, W written in place,
+//                       column sums of squares and W^T y reduced in a fixed order.
 #include "gb_common.cuh"
 
 namespace gb {
@@ -30,54 +32,62 @@ constexpr int STATUS_BREAKDOWN = 1;
 __device__ __forceinline__ int win_nb(int n) { return (n + NB - 1) / NB; }
 
 // ---------------------------------------------------------------------------------------------
-// Factor the 64x64 SPD block D (lower triangle, D[c][r] = element (r, c), padded stride) in place
-// and put inv(L) into X (same layout, strictly-upper part zero).  256 threads.  Returns false on
-// a non-positive / NaN pivot (flag only; execution continues with a substituted pivot).
-constexpr int LDS_PAD = NB + 1;
+// In-place transform of a 64x64 SPD block M (lower triangle, M[c*PAD + r] = element (r, c)) into
+// inv(L), L = chol(M); L itself is never formed (nothing downstream needs it).  256 threads:
+// thread (r = tid & 63, q = tid >> 6) owns row r, columns c = q, q+4, ...
+// Step j of the right-looking factorisation and step j of the forward substitution L Y = I share
+// one pass: once column j of A has been consumed its slot holds column j of Y.
+//   rs = 1/sqrt(a_jj);  l_rj = a_rj rs
+//   row j:   Y(j,c) *= rs (c<j),  Y(j,j) = rs
+//   rows r>j: Y(r,c) -= l_rj Y(j,c) (c<j),  Y(r,j) = -l_rj rs,  A(r,c) -= l_rj l_cj (j<c<=r)
+// Two barriers per step (read phase / write phase); ~250 cycles per pivot.
+// Returns false on a non-positive / NaN pivot (flag only; a substitute pivot keeps it finite).
+constexpr int MP = NB + 2;  // even stride: double2-aligned rows for the GEMM that follows
 
-__device__ bool factor_and_invert_block(double* D, double* X) {
+__device__ bool spd_block_to_inv_chol(double* M) {
   const int tid = threadIdx.x;
-  __shared__ int s_bad;
-  if (tid == 0) s_bad = 0;
+  const int r = tid & 63;
+  const int q = tid >> 6;
+  bool bad_any = false;
   for (int j = 0; j < NB; j++) {
     __syncthreads();
-    const double piv = D[j * LDS_PAD + j];
+    const double piv = M[j * MP + j];
+    const double a_rj = M[j * MP + r];
+    double m[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int c = q + 4 * i;
+      m[i] = (c < j) ? M[c * MP + j] : M[j * MP + c];  // Y(j,c) for c<j, a_cj for c>j
+    }
+    __syncthreads();
     const bool bad = !(piv > 0.0);
-    const double dj = sqrt(bad ? 1.0 : piv);
-    __syncthreads();
-    if (tid == 0) {
-      D[j * LDS_PAD + j] = dj;
-      if (bad) s_bad = 1;
-    }
-    if (tid > j && tid < NB) D[j * LDS_PAD + tid] = D[j * LDS_PAD + tid] / dj;  // column j below diag
-    __syncthreads();
-    // trailing update: D(r, c) -= L(r, j) * L(c, j) for j < c <= r
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-      const int c = idx >> 6, r = idx & 63;
-      if (c > j && r >= c) D[c * LDS_PAD + r] = fma(-D[j * LDS_PAD + r], D[j * LDS_PAD + c], D[c * LDS_PAD + r]);
-    }
-  }
-  __syncthreads();
-  // inverse of the lower-triangular factor, one column per thread (forward substitution on e_c)
-  if (tid < NB) {
-    const int c = tid;
-    for (int r = 0; r < NB; r++) {
-      double v = 0.0;
-      if (r >= c) {
-        double acc = (r == c) ? 1.0 : 0.0;
-        for (int j = c; j < r; j++) acc = fma(-D[j * LDS_PAD + r], X[c * LDS_PAD + j], acc);
-        v = acc / D[r * LDS_PAD + r];
+    bad_any |= bad;
+    const double rs = rsqrt(bad ? 1.0 : piv);
+    if (r > j) {
+      const double l = a_rj * rs;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int c = q + 4 * i;
+        if (c == j) M[j * MP + r] = -l * rs;
+        else if (c < j || c <= r) M[c * MP + r] = fma(-l, m[i] * rs, M[c * MP + r]);
       }
-      X[c * LDS_PAD + r] = v;
+    } else if (r == j) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int c = q + 4 * i;
+        if (c < j) M[c * MP + j] = m[i] * rs;
+        else if (c == j) M[j * MP + j] = rs;
+      }
     }
   }
   __syncthreads();
-  return s_bad == 0;
+  return !bad_any;
 }
 
 __global__ void __launch_bounds__(256)
-chol_panel_kernel(const SolveWin* __restrict__ wins, double* tt, double* dinv, const double* __restrict__ zt,
-                  double* y, int* status, int k, int want_y) {
+chol_panel_kernel(const SolveWin* __restrict__ wins, double* tt, double* dinv, int* status,
+                  const int* __restrict__ skip, int k) {
+  if (skip && skip[blockIdx.y]) return;  // certificate copy whose analytic bound already holds
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t;
   const int nb = win_nb(n);
@@ -87,72 +97,73 @@ chol_panel_kernel(const SolveWin* __restrict__ wins, double* tt, double* dinv, c
   const int ld = w.ld_t;
   const int tid = threadIdx.x;
 
-  extern __shared__ double sm[];
-  double* D = sm;                      // [64][65]
-  double* X = D + NB * LDS_PAD;        // [64][65]
-  double* T = X + NB * LDS_PAD;        // [64][65]  A_ik tile, T[j][r] = A(ib*64+r, k*64+j)
+  extern __shared__ __align__(16) double sm[];
+  double* X = sm;                 // [64][MP] A_kk -> inv(L_kk)
+  double* T = X + NB * MP;        // [64][MP] A_ik tile, T[j*MP + r] = A(ib*64+r, k*64+j)
 
   const int k0 = k * NB;
+  const int i0 = ib * NB;
   // diagonal block; rows/cols past n are padded with the identity
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int c = idx >> 6, r = idx & 63;
     double v = (r == c) ? 1.0 : 0.0;
     if (k0 + r < n && k0 + c < n && r >= c) v = A[(long long)(k0 + c) * ld + k0 + r];
-    D[c * LDS_PAD + r] = v;
+    X[c * MP + r] = v;
+    if (ib != k) T[c * MP + r] = (i0 + r < n && k0 + c < n) ? A[(long long)(k0 + c) * ld + i0 + r] : 0.0;
   }
-  const bool ok = factor_and_invert_block(D, X);
+  const bool ok = spd_block_to_inv_chol(X);
 
   if (ib == k) {
     if (!ok && tid == 0) atomicOr(&status[blockIdx.y], STATUS_BREAKDOWN);
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-      const int c = idx >> 6, r = idx & 63;
-      // L_kk itself is never needed again (panel blocks, y and the solve all use inv(L_kk)), and
-      // writing it here would race with the sibling CTAs still loading A_kk.
-      dinv[w.off_dinv + (long long)k * NB * NB + c * NB + r] = X[c * LDS_PAD + r];
-    }
-    if (want_y) {
-      // y_k = inv(L_kk) (z_k - sum_{j<k} L_kj y_j)
-      double* rhs = T;  // reuse
-      if (tid < NB) {
-        const int r = k0 + tid;
-        double acc = 0.0;
-        if (r < n) {
-          acc = zt[w.off_t + r];
-          for (int c = 0; c < k0; c++) acc = fma(-A[(long long)c * ld + r], y[w.off_t + c], acc);
-        }
-        rhs[tid] = acc;
+    // L_kk is never needed again (panel blocks, y and the solve all use inv(L_kk)); A_kk is left
+    // untouched, the sibling CTAs are still reading it.
+    if (w.flags & 1)
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int c = idx >> 6, r = idx & 63;
+        dinv[w.off_dinv + (long long)k * NB * NB + c * NB + r] = X[c * MP + r];
       }
-      __syncthreads();
-      if (tid < NB) {
-        double acc = 0.0;
-        for (int j = 0; j <= tid; j++) acc = fma(X[j * LDS_PAD + tid], rhs[j], acc);
-        if (k0 + tid < n) y[w.off_t + k0 + tid] = acc;
-      }
-    }
     return;
   }
 
-  // off-diagonal panel block: L_ik = A_ik inv(L_kk)^T, i.e. L(r, c) = sum_{j<=c} A(r, j) X(c, j)
-  const int i0 = ib * NB;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int j = idx >> 6, r = idx & 63;
-    T[j * LDS_PAD + r] = (i0 + r < n && k0 + j < n) ? A[(long long)(k0 + j) * ld + i0 + r] : 0.0;
-  }
-  __syncthreads();
+  // off-diagonal panel block: L_ik = A_ik inv(L_kk)^T, i.e. L(r, c) = sum_{j<=c} A(r, j) X(c, j);
+  // 4x4 register tile per thread, rows {2a,2a+1,32+2a,32+2a+1}, columns 4b..4b+3
   {
-    const int r = tid & 63;
-    const int cq = tid >> 6;  // 0..3 -> columns cq, cq+4, ...
-    for (int c = cq; c < NB; c += 4) {
-      double acc = 0.0;
-      for (int j = 0; j <= c; j++) acc = fma(T[j * LDS_PAD + r], X[j * LDS_PAD + c], acc);
-      if (i0 + r < n && k0 + c < n) A[(long long)(k0 + c) * ld + i0 + r] = acc;
+    const int a2 = (tid & 15) * 2, cb = (tid >> 4) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+    const int jmax = cb + 3;  // X(c, j) = 0 for j > c
+    for (int j = 0; j <= jmax; j++) {
+      const double2 t01 = *reinterpret_cast<const double2*>(&T[j * MP + a2]);
+      const double2 t23 = *reinterpret_cast<const double2*>(&T[j * MP + 32 + a2]);
+      const double2 x01 = *reinterpret_cast<const double2*>(&X[j * MP + cb]);
+      const double2 x23 = *reinterpret_cast<const double2*>(&X[j * MP + cb + 2]);
+      const double tv[4] = {t01.x, t01.y, t23.x, t23.y};
+      const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = fma(tv[a], xv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int c = k0 + cb + b;
+      if (c >= n) continue;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int r = i0 + a2 + (a & 1) + (a >> 1) * 32;
+        if (r < n) A[(long long)c * ld + r] = acc[a][b];
+      }
     }
   }
 }
 
 // trailing update of step k: A_ij -= L_ik L_jk^T for k < j <= i
 __global__ void __launch_bounds__(256)
-chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, int k) {
+chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, const int* __restrict__ skip, int k) {
+  if (skip && skip[blockIdx.y]) return;
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t;
   const int nb = win_nb(n);
@@ -178,7 +189,7 @@ chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, int k) {
     Rs[kk][r] = (j0 + r < n) ? A[(long long)(k0 + kk) * ld + j0 + r] : 0.0;
   }
   __syncthreads();
-  const int tr = (tid & 15) * 4;   // rows tr..tr+3   (fastest across threads -> coalesced stores)
+  const int a2 = (tid & 15) * 2;   // rows {a2, a2+1, 32+a2, 32+a2+1}: conflict-free 16-byte smem reads
   const int tc = (tid >> 4) * 4;   // cols tc..tc+3
   double acc[4][4];
 #pragma unroll
@@ -187,8 +198,8 @@ chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, int k) {
     for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
 #pragma unroll 8
   for (int kk = 0; kk < NB; kk++) {
-    const double2 l01 = *reinterpret_cast<const double2*>(&Ls[kk][tr]);
-    const double2 l23 = *reinterpret_cast<const double2*>(&Ls[kk][tr + 2]);
+    const double2 l01 = *reinterpret_cast<const double2*>(&Ls[kk][a2]);
+    const double2 l23 = *reinterpret_cast<const double2*>(&Ls[kk][32 + a2]);
     const double2 r01 = *reinterpret_cast<const double2*>(&Rs[kk][tc]);
     const double2 r23 = *reinterpret_cast<const double2*>(&Rs[kk][tc + 2]);
     const double lv[4] = {l01.x, l01.y, l23.x, l23.y};
@@ -204,15 +215,16 @@ chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, int k) {
     if (c >= n) continue;
 #pragma unroll
     for (int a = 0; a < 4; a++) {
-      const int r = i0 + tr + a;
+      const int r = i0 + a2 + (a & 1) + (a >> 1) * 32;
       if (r < n && r >= c) A[(long long)c * ld + r] -= acc[a][b];
     }
   }
 }
 
-// dst = src with the diagonal lowered by `shift` (lower triangle only), per window
+// dst = src with the diagonal lowered by `shift`, per window (dst is the certificate copy)
 __global__ void copy_shift_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ src, double* dst,
-                                  double shift) {
+                                  double shift, const int* __restrict__ skip, int nreal) {
+  if (skip[nreal + blockIdx.y]) return;
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t, ld = w.ld_t;
   const long long total = (long long)n * ld;
@@ -225,12 +237,103 @@ __global__ void copy_shift_kernel(const SolveWin* __restrict__ wins, const doubl
   }
 }
 
+// Analytic positive-definiteness certificate (DESIGN.md "MakePosDef").  B11 = R + lambda*I with
+// R = D^-1/2 (Wn + E) D^-1/2: Wn = sum_p w_p m_p/(m_p-1) (m_p X_p X_p^T - s_p s_p^T) is a positively
+// weighted sum of centred Gram matrices, hence PSD for w_p >= 0; E = M (diag(w) - w w^T) M^T with
+// M = [mu_ip] satisfies  x^T E x >= -(sum(w)-1)_+ max(w) |M^T x|^2.  So
+//     lambda_min(B11) >= lambda - gneg * sum_i (sum_p mu_ip^2) / cov_ii - rounding slack,
+// gneg = (sum(w)-1)_+ * max(w) (0 for the pooled r of dist(): a Pearson matrix is PSD).  When that
+// bound exceeds min_abs_eig the reference's MakePosDef is provably a no-op and the shifted
+// factorisation is skipped; otherwise (lambda = 0, negative weights, NaN, ...) it runs.
+__global__ void __launch_bounds__(256)
+pd_bound_kernel(const SolveWin* __restrict__ wins, int nreal, const double* __restrict__ rq_t, double lambda,
+                double gneg, double min_abs_eig, int* skip) {
+  const SolveWin w = wins[blockIdx.x];
+  __shared__ double red[256];
+  double s = 0.0;
+  if (rq_t)
+    for (int i = threadIdx.x; i < w.n_t; i += 256) s += rq_t[w.off_t + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double lb = lambda - ((gneg > 0.0) ? gneg * red[0] : 0.0) - 1e-9 * (1.0 + w.n_t / 1000.0);
+    skip[blockIdx.x] = 0;
+    skip[nreal + blockIdx.x] = (lb > min_abs_eig) ? 1 : 0;  // NaN compares false -> exact certificate runs
+  }
+}
+
+// y = L^-1 Z1 by block forward substitution, one CTA per window:
+//   y_k = inv(L_kk) (z_k - sum_{j<k} L_kj y_j)
+__global__ void __launch_bounds__(256)
+solve_y_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt, const double* __restrict__ dinv,
+               const double* __restrict__ zt, double* y) {
+  const SolveWin w = wins[blockIdx.x];
+  const int n = w.n_t, ld = w.ld_t, nb = win_nb(n);
+  const double* L = tt + w.off_tt;
+  const int tid = threadIdx.x;
+  const int r = tid & 63, q = tid >> 6;
+  extern __shared__ double sm[];
+  double* ys = sm;                 // [nb*64] solution so far
+  double* part = ys + nb * NB;     // [4][64]
+  double* rhs = part + 4 * NB;     // [64]
+  for (int k = 0; k < nb; k++) {
+    const int k0 = k * NB;
+    double acc = 0.0;
+    if (k0 + r < n) {
+      double a4[4] = {0.0, 0.0, 0.0, 0.0};
+      int c = q;
+      for (; c + 12 < k0; c += 16) {  // four independent loads in flight per thread
+#pragma unroll
+        for (int u = 0; u < 4; u++) a4[u] = fma(L[(long long)(c + 4 * u) * ld + k0 + r], ys[c + 4 * u], a4[u]);
+      }
+      for (; c < k0; c += 4) a4[0] = fma(L[(long long)c * ld + k0 + r], ys[c], a4[0]);
+      acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    }
+    part[q * NB + r] = acc;
+    __syncthreads();
+    if (tid < NB) {
+      double v = 0.0;
+      if (k0 + r < n) v = zt[w.off_t + k0 + r] - (part[r] + part[NB + r] + part[2 * NB + r] + part[3 * NB + r]);
+      rhs[r] = v;
+    }
+    __syncthreads();
+    if (tid < NB) {
+      const double* X = dinv + w.off_dinv + (long long)k * NB * NB;  // X[c*64 + r] = inv(L_kk)(r, c)
+      double v = 0.0;
+      for (int j = 0; j <= r; j++) v = fma(X[j * NB + r], rhs[j], v);
+      ys[k0 + r] = v;
+      if (k0 + r < n) y[w.off_t + k0 + r] = v;
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Blocked forward substitution W = L^-1 B21^T for 128 unmeasured SNPs, fused with the reductions.
-constexpr int UB = 128;            // unmeasured SNPs (columns of W) per CTA
-constexpr int TR_SMEM_DOUBLES = NB * NB /*Ls*/ + NB * UB /*Ws*/ + NB * UB /*Ts*/ + 16 * UB /*red*/;
+//
+// Thread tile 8 rows x 4 columns: warp g owns rows 8g..8g+7 of the 64-row block, lane l owns
+// columns {2l, 2l+1, 64+2l, 64+2l+1}.  Operand chunks (32 k-steps of L: 16 KiB, of W: 32 KiB) are
+// double-buffered with cp.async.cg (L2 path: W rows were written by this CTA earlier).  The
+// accumulator tile and inv(L_ii) alias the chunk buffers once the k-loop of a row block is done,
+// so a CTA needs 96 KiB and two CTAs share an SM.
+constexpr int UB = 128;   // unmeasured SNPs (columns of W) per CTA
+constexpr int KC = 32;    // k-steps per staged chunk
+constexpr int TR_SMEM_BYTES = 2 * (KC * NB + KC * UB) * 8;  // 98,304
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256, 2)
 trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt,
                      const double* __restrict__ dinv, double* ut, const double* __restrict__ y,
                      double* zu, double* info) {
@@ -244,123 +347,167 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   double* W = ut + w.off_ut;
   const int ldu = w.ld_u;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, g = tid >> 5;
+  const int tr = g * 8;
 
-  extern __shared__ double sm[];
-  double* Ls = sm;                 // [64 kk][64 r]
-  double* Ws = Ls + NB * NB;       // [64 kk][128 c]
-  double* Ts = Ws + NB * UB;       // [64 r ][128 c]
-  double* red = Ts + NB * UB;      // [16][128]
+  extern __shared__ __align__(16) double sm[];
+  double* LsBuf = sm;                       // 2 x [KC][64]
+  double* WsBuf = sm + 2 * KC * NB;         // 2 x [KC][128]
+  double* Ds = LsBuf;                       // [64][64] inv(L_ii), aliases both L chunks
+  double* Ts = WsBuf;                       // [64][128] accumulator tile, aliases both W chunks
+  double* red = WsBuf;                      // [8][128] final reductions
 
-  const int tr = (tid >> 4) * 4;   // rows tr..tr+3 of the 64-row block
-  const int tc = (tid & 15) * 8;   // cols tc..tc+7 of the 128-column block
-  double p_info[8], p_z[8];
-#pragma unroll
-  for (int b = 0; b < 8; b++) p_info[b] = 0.0, p_z[b] = 0.0;
+  double p_info[4] = {0.0, 0.0, 0.0, 0.0}, p_z[4] = {0.0, 0.0, 0.0, 0.0};
+  const int ccol[2] = {2 * lane, 64 + 2 * lane};   // first column of each 2-wide strip of this thread
+  const int cvalid = ldu - u0;                     // columns that exist in the row (ldu is a multiple of 8)
 
   for (int ib = 0; ib < nb; ib++) {
     const int i0 = ib * NB;
-    double acc[4][8];
+    double acc[8][4];
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
+    for (int a = 0; a < 8; a++) {
       const int r = i0 + tr + a;
 #pragma unroll
-      for (int b = 0; b < 8; b++) {
-        const int c = u0 + tc + b;
-        acc[a][b] = (r < n && c < nu) ? W[(long long)r * ldu + c] : 0.0;
+      for (int s = 0; s < 2; s++) {
+        double2 v = make_double2(0.0, 0.0);
+        if (r < n && ccol[s] < cvalid) v = *reinterpret_cast<const double2*>(&W[(long long)r * ldu + u0 + ccol[s]]);
+        acc[a][2 * s] = v.x;
+        acc[a][2 * s + 1] = v.y;
       }
     }
-    // acc -= L(ib, jb) * W(jb) for jb < ib
-    for (int jb = 0; jb < ib; jb++) {
-      const int j0 = jb * NB;
-      __syncthreads();
-      for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int kk = idx >> 6, r = idx & 63;
-        Ls[kk * NB + r] = (i0 + r < n) ? L[(long long)(j0 + kk) * ld + i0 + r] : 0.0;
+    // acc -= L(ib, 0:i0) * W(0:i0) in chunks of KC k-steps
+    const int nchunk = ib * (NB / KC);
+    auto issue = [&](int ch, int buf) {
+      const int kbase = ch * KC;
+      double* ls = LsBuf + buf * KC * NB;
+      double* ws = WsBuf + buf * KC * UB;
+      // L chunk: KC columns x 64 rows in 16-byte pieces, 32 per column
+#pragma unroll
+      for (int it = 0; it < (KC * NB / 2) / 256; it++) {
+        const int idx = tid + it * 256;
+        const int kk = idx >> 5, r2 = (idx & 31) * 2;
+        cp_async16(ls + kk * NB + r2, L + (long long)(kbase + kk) * ld + i0 + r2, i0 + r2 < n);
       }
-      for (int idx = tid; idx < NB * UB; idx += 256) {
-        const int kk = idx >> 7, c = idx & 127;
-        Ws[kk * UB + c] = (u0 + c < nu) ? W[(long long)(j0 + kk) * ldu + u0 + c] : 0.0;
+      // W chunk: KC rows x 128 columns, 64 pieces per row
+#pragma unroll
+      for (int it = 0; it < (KC * UB / 2) / 256; it++) {
+        const int idx = tid + it * 256;
+        const int kk = idx >> 6, c2 = (idx & 63) * 2;
+        cp_async16(ws + kk * UB + c2, W + (long long)(kbase + kk) * ldu + u0 + c2, c2 < cvalid);
+      }
+      cp_async_commit();
+    };
+    __syncthreads();  // previous row block finished with the aliased buffers (Ts / Ds)
+    if (nchunk > 0) issue(0, 0);
+    for (int ch = 0; ch < nchunk; ch++) {
+      const int buf = ch & 1;
+      if (ch + 1 < nchunk) {
+        issue(ch + 1, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
-#pragma unroll 4
-      for (int kk = 0; kk < NB; kk++) {
-        const double2 l01 = *reinterpret_cast<const double2*>(&Ls[kk * NB + tr]);
-        const double2 l23 = *reinterpret_cast<const double2*>(&Ls[kk * NB + tr + 2]);
-        const double lv[4] = {l01.x, l01.y, l23.x, l23.y};
-        double wv[8];
+      const double* ls = LsBuf + buf * KC * NB;
+      const double* ws = WsBuf + buf * KC * UB;
+#pragma unroll 2
+      for (int kk = 0; kk < KC; kk++) {
+        double lv[8], wv[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const double2 t2 = *reinterpret_cast<const double2*>(&Ws[kk * UB + tc + 2 * q]);
-          wv[2 * q] = t2.x;
-          wv[2 * q + 1] = t2.y;
+          const double2 t2 = *reinterpret_cast<const double2*>(&ls[kk * NB + tr + 2 * q]);
+          lv[2 * q] = t2.x;
+          lv[2 * q + 1] = t2.y;
         }
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+        for (int s = 0; s < 2; s++) {
+          const double2 t2 = *reinterpret_cast<const double2*>(&ws[kk * UB + ccol[s]]);
+          wv[2 * s] = t2.x;
+          wv[2 * s + 1] = t2.y;
+        }
 #pragma unroll
-          for (int b = 0; b < 8; b++) acc[a][b] = fma(-lv[a], wv[b], acc[a][b]);
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) acc[a][b] = fma(-lv[a], wv[b], acc[a][b]);
       }
+      __syncthreads();  // buffer `buf` may be refilled by the next issue
     }
     // W_i = inv(L_ii) * acc
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+      for (int s = 0; s < 2; s++)
+        *reinterpret_cast<double2*>(&Ts[(tr + a) * UB + ccol[s]]) = make_double2(acc[a][2 * s], acc[a][2 * s + 1]);
+    for (int idx = tid; idx < NB * NB / 2; idx += 256)  // Ds[kk*64 + r] = inv(L_ii)(r, kk), zero above diag
+      reinterpret_cast<double2*>(Ds)[idx] =
+          reinterpret_cast<const double2*>(dinv + w.off_dinv + (long long)ib * NB * NB)[idx];
     __syncthreads();
+    double out[8][4];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < 8; a++)
 #pragma unroll
-      for (int b = 0; b < 8; b++) Ts[(tr + a) * UB + tc + b] = acc[a][b];
-    for (int idx = tid; idx < NB * NB; idx += 256)  // Ls[kk][r] = inv(L_ii)(r, kk) (zero above diag)
-      Ls[idx] = dinv[w.off_dinv + (long long)ib * NB * NB + idx];
-    __syncthreads();
-    double out[4][8];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 8; b++) out[a][b] = 0.0;
-    const int kmax = tr + 4;  // inv(L_ii)(r, kk) == 0 for kk > r
+      for (int b = 0; b < 4; b++) out[a][b] = 0.0;
+    const int kmax = tr + 8;  // inv(L_ii)(r, kk) == 0 for kk > r
+#pragma unroll 1
     for (int kk = 0; kk < kmax; kk++) {
-      const double2 l01 = *reinterpret_cast<const double2*>(&Ls[kk * NB + tr]);
-      const double2 l23 = *reinterpret_cast<const double2*>(&Ls[kk * NB + tr + 2]);
-      const double lv[4] = {l01.x, l01.y, l23.x, l23.y};
-      double tv[8];
+      double lv[8], tv[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const double2 t2 = *reinterpret_cast<const double2*>(&Ts[kk * UB + tc + 2 * q]);
-        tv[2 * q] = t2.x;
-        tv[2 * q + 1] = t2.y;
+        const double2 t2 = *reinterpret_cast<const double2*>(&Ds[kk * NB + tr + 2 * q]);
+        lv[2 * q] = t2.x;
+        lv[2 * q + 1] = t2.y;
       }
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int s = 0; s < 2; s++) {
+        const double2 t2 = *reinterpret_cast<const double2*>(&Ts[kk * UB + ccol[s]]);
+        tv[2 * s] = t2.x;
+        tv[2 * s + 1] = t2.y;
+      }
 #pragma unroll
-        for (int b = 0; b < 8; b++) out[a][b] = fma(lv[a], tv[b], out[a][b]);
+      for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) out[a][b] = fma(lv[a], tv[b], out[a][b]);
     }
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
+    for (int a = 0; a < 8; a++) {
       const int r = i0 + tr + a;
       if (r >= n) continue;
       const double yr = y[w.off_t + r];
 #pragma unroll
-      for (int b = 0; b < 8; b++) {
-        const int c = u0 + tc + b;
+      for (int s = 0; s < 2; s++) {
+        if (ccol[s] < cvalid)
+          *reinterpret_cast<double2*>(&W[(long long)r * ldu + u0 + ccol[s]]) =
+              make_double2(out[a][2 * s], out[a][2 * s + 1]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
         const double v = out[a][b];
-        if (c < nu) W[(long long)r * ldu + c] = v;
         p_info[b] = fma(v, v, p_info[b]);
         p_z[b] = fma(yr, v, p_z[b]);
       }
     }
   }
-  // column reductions over the 16 row groups, fixed order
+  // column reductions over the 8 row groups, fixed order
   __syncthreads();
 #pragma unroll
-  for (int b = 0; b < 8; b++) red[(tid >> 4) * UB + tc + b] = p_info[b];
+  for (int s = 0; s < 2; s++) {
+    red[g * UB + ccol[s]] = p_info[2 * s];
+    red[g * UB + ccol[s] + 1] = p_info[2 * s + 1];
+  }
   __syncthreads();
   double s_info = 0.0;
   if (tid < UB)
-    for (int g = 0; g < 16; g++) s_info += red[g * UB + tid];
+    for (int gg = 0; gg < 8; gg++) s_info += red[gg * UB + tid];
   __syncthreads();
 #pragma unroll
-  for (int b = 0; b < 8; b++) red[(tid >> 4) * UB + tc + b] = p_z[b];
+  for (int s = 0; s < 2; s++) {
+    red[g * UB + ccol[s]] = p_z[2 * s];
+    red[g * UB + ccol[s] + 1] = p_z[2 * s + 1];
+  }
   __syncthreads();
   if (tid < UB && u0 + tid < nu) {
     double s_z = 0.0;
-    for (int g = 0; g < 16; g++) s_z += red[g * UB + tid];
+    for (int gg = 0; gg < 8; gg++) s_z += red[gg * UB + tid];
     const double inf = fabs(s_info);                 // info = |b21 B11^-1 b12|      (dist.cpp:198)
     zu[w.off_u + u0 + tid] = s_z / sqrt(inf);        // z / sqrt(info)               (dist.cpp:200)
     info[w.off_u + u0 + tid] = inf;
@@ -369,19 +516,11 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 
 }  // namespace
 
-static int max_nt(const std::vector<SolveWin>& h) {
-  int m = 0;
-  for (const auto& w : h) m = w.n_t > m ? w.n_t : m;
-  return m;
-}
-
-int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins, double* d_tt,
-                    double* d_dinv, const double* d_zt, double* d_y, int* d_status, double /*shift*/,
-                    int want_y) {
-  const int nw = (int)h_wins.size();
-  if (nw == 0) return GB_OK;
-  const int nb_max = (max_nt(h_wins) + NB - 1) / NB;
-  const size_t smem_panel = sizeof(double) * 3 * NB * LDS_PAD;
+int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, double* d_tt, double* d_dinv,
+                    int* d_status, const int* d_skip) {
+  if (n_wins == 0) return GB_OK;
+  const int nb_max = (max_nt + NB - 1) / NB;
+  const size_t smem_panel = sizeof(double) * 2 * NB * MP;
   const size_t smem_update = sizeof(double) * 2 * NB * NB;
   static bool attr_set = false;
   if (!attr_set) {
@@ -390,12 +529,12 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin
     attr_set = true;
   }
   for (int k = 0; k < nb_max; k++) {
-    chol_panel_kernel<<<dim3(nb_max - k, nw), 256, smem_panel, ctx->stream>>>(d_wins, d_tt, d_dinv, d_zt, d_y,
-                                                                             d_status, k, want_y);
+    chol_panel_kernel<<<dim3(nb_max - k, n_wins), 256, smem_panel, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status,
+                                                                                 d_skip, k);
     ctx->launches++;
     const int tb = nb_max - k - 1;
     if (tb > 0) {
-      chol_update_kernel<<<dim3(tb * (tb + 1) / 2, nw), 256, smem_update, ctx->stream>>>(d_wins, d_tt, k);
+      chol_update_kernel<<<dim3(tb * (tb + 1) / 2, n_wins), 256, smem_update, ctx->stream>>>(d_wins, d_tt, d_skip, k);
       ctx->launches++;
     }
   }
@@ -403,32 +542,50 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin
   return GB_OK;
 }
 
-int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins,
-                         const double* d_tt, const double* d_dinv, double* d_ut, const double* d_y,
-                         double* d_zu, double* d_info) {
-  const int nw = (int)h_wins.size();
-  if (nw == 0) return GB_OK;
-  int nu_max = 0;
-  for (const auto& w : h_wins) nu_max = w.n_u > nu_max ? w.n_u : nu_max;
-  if (nu_max == 0) return GB_OK;
-  const size_t smem = sizeof(double) * TR_SMEM_DOUBLES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+int launch_solve_y(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, const double* d_tt,
+                   const double* d_dinv, const double* d_zt, double* d_y) {
+  if (n_wins == 0) return GB_OK;
+  const int nb_max = (max_nt + NB - 1) / NB;
+  const size_t smem = sizeof(double) * (size_t)(nb_max * NB + 5 * NB);
+  if (smem > 200 * 1024) {
+    ctx->err = "window has too many measured SNPs for solve_y_kernel";
+    return GB_ERR_UNSUPPORTED;
   }
-  trsm_finalize_kernel<<<dim3((nu_max + UB - 1) / UB, nw), 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut,
-                                                                                    d_y, d_zu, d_info);
+  GB_CUDA(cudaFuncSetAttribute(solve_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  solve_y_kernel<<<n_wins, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_zt, d_y);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;
 }
 
-int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, const std::vector<SolveWin>& h_wins,
-                      const double* d_src, double* d_dst, double shift) {
-  const int nw = (int)h_wins.size();
-  if (nw == 0) return GB_OK;
-  copy_shift_kernel<<<dim3(64, nw), 256, 0, ctx->stream>>>(d_wins, d_src, d_dst, shift);
+int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nu, const double* d_tt,
+                         const double* d_dinv, double* d_ut, const double* d_y, double* d_zu, double* d_info) {
+  if (n_wins == 0 || max_nu == 0) return GB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM_BYTES));
+    attr_set = true;
+  }
+  trsm_finalize_kernel<<<dim3((max_nu + UB - 1) / UB, n_wins), 256, TR_SMEM_BYTES, ctx->stream>>>(
+      d_wins, d_tt, d_dinv, d_ut, d_y, d_zu, d_info);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+int launch_pd_bound(Ctx* ctx, const SolveWin* d_wins, int n_real, const double* d_rq_t, double lambda,
+                    double gneg, double min_abs_eig, int* d_skip) {
+  if (n_real == 0) return GB_OK;
+  pd_bound_kernel<<<n_real, 256, 0, ctx->stream>>>(d_wins, n_real, d_rq_t, lambda, gneg, min_abs_eig, d_skip);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double* d_src, double* d_dst,
+                      double shift, const int* d_skip) {
+  if (n_wins == 0) return GB_OK;
+  copy_shift_kernel<<<dim3(64, n_wins), 256, 0, ctx->stream>>>(d_wins, d_src, d_dst, shift, d_skip, n_wins);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;
