@@ -60,7 +60,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled through
+    NVML every 5 ms from a host thread (the timed region of one step is ~10 ms, far below
+    nvidia-smi's own polling period); falls back to `nvidia-smi -lms` when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -69,8 +71,41 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = False
+        self.samples = []
+
+    def _nvml_loop(self, nv, h):
+        bits = dict(hw_slowdown=nv.nvmlClocksThrottleReasonHwSlowdown,
+                    hw_thermal_slowdown=nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    sw_thermal_slowdown=nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    sw_power_cap=nv.nvmlClocksThrottleReasonSwPowerCap)
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                self.samples.append((sm, [k for k, b in bits.items() if rs & b], pw))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.device
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.device])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -82,6 +117,15 @@ class ClockSampler:
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=float(np.median([x[0] for x in self.samples])), sm_max_mhz=self.max_mhz,
+                           samples=len(self.samples), power_w_max=float(max(x[2] for x in self.samples)),
+                           source="nvml, 5 ms period, timed region only")
+                out["reasons"] = sorted({r for x in self.samples for r in x[1]})
+            return out
         if not self.proc:
             return out
         self.proc.terminate()
@@ -105,7 +149,7 @@ class ClockSampler:
                     reasons.add(nm)
         os.unlink(self.path)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm), source="nvidia-smi")
         out["reasons"] = sorted(reasons)
         return out
 
@@ -297,14 +341,15 @@ def run_gpu(args):
                 d2h += b * 16 + 8
         return done
 
-    e2e_step()  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    e2e_done = 0
-    for k in range(e2e_steps):
-        e2e_done += e2e_step(count=(k == 0))
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_done, e2e_s = 0, 1.0
+    if not args.no_e2e:
+        e2e_step()  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e_done += e2e_step(count=(k == 0))
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
     # ---- max over ranks
     t_res = torch.tensor([total_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
@@ -358,6 +403,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gauss_b200", choices=["gauss_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel tuning runs: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

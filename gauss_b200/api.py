@@ -15,6 +15,9 @@ GB_ERR_BAD_ARG, GB_ERR_CUDA, GB_ERR_NO_DEVICE, GB_ERR_OOM = 1, 2, 3, 4
 GB_ERR_TOO_FEW_MEASURED, GB_ERR_TOO_FEW_UNMEASURED, GB_ERR_NOT_PD, GB_ERR_UNSUPPORTED = 5, 6, 7, 8
 
 
+PANEL_FORMATS = {"int8": 0, "e2m1": 1}   # enum gb_panel_format
+
+
 class GaussB200Error(RuntimeError):
     def __init__(self, status: int, msg: str):
         super().__init__(f"gauss_b200 status {status}: {msg}")
@@ -69,6 +72,8 @@ def load_library():
         "gb_last_error": (C.c_char_p, [vp]),
         "gb_ctx_launch_count": (i64, [vp]),
         "gb_panel_create": (C.c_int, [vp, C.c_int, i32p, i64, C.POINTER(vp)]),
+        "gb_panel_create_fmt": (C.c_int, [vp, C.c_int, i32p, i64, C.c_int, C.POINTER(vp)]),
+        "gb_panel_format_of": (C.c_int, [vp]),
         "gb_panel_destroy": (None, [vp]),
         "gb_panel_clear": (C.c_int, [vp]),
         "gb_panel_num_rows": (i64, [vp]),
@@ -181,13 +186,22 @@ class Context:
 class Panel:
     """gb_panel: HBM-resident packed panel (int8 rows, per-population blocks padded to 32)."""
 
-    def __init__(self, ctx: Context, pop_sizes, capacity_rows: int):
+    def __init__(self, ctx: Context, pop_sizes, capacity_rows: int, fmt: str | None = None):
+        """fmt: None (library default: E2M1 nibbles), "int8" or "e2m1" (enum gb_panel_format)."""
         self.ctx = ctx
         self.pop_sizes = np.ascontiguousarray(pop_sizes, np.int32)
         h = C.c_void_p()
-        ctx.check(ctx.lib.gb_panel_create(ctx.h, len(self.pop_sizes), _ptr(self.pop_sizes), int(capacity_rows),
-                                          C.byref(h)))
+        if fmt is None:
+            ctx.check(ctx.lib.gb_panel_create(ctx.h, len(self.pop_sizes), _ptr(self.pop_sizes),
+                                              int(capacity_rows), C.byref(h)))
+        else:
+            ctx.check(ctx.lib.gb_panel_create_fmt(ctx.h, len(self.pop_sizes), _ptr(self.pop_sizes),
+                                                  int(capacity_rows), PANEL_FORMATS[fmt], C.byref(h)))
         self.h = h
+
+    @property
+    def format(self) -> str:
+        return {v: k for k, v in PANEL_FORMATS.items()}[int(self.ctx.lib.gb_panel_format_of(self.h))]
 
     @property
     def n_rows(self) -> int:

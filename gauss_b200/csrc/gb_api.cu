@@ -3,6 +3,7 @@
 // distmix.cpp:138-253).  All compute is CUDA; there is no CPU fallback.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -49,7 +50,8 @@ struct gb_batch {
   SolveWin* d_wins = nullptr;
   GramTile* d_tiles = nullptr;
   int8_t* d_scratch = nullptr;
-  CUtensorMap tmap_scratch;
+  RowMaps tmaps_scratch;
+  int cm = 1, cn = 1;                 // Gram cluster shape this batch was planned for
   GramParams gp{};
 };
 
@@ -156,6 +158,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   }
   gp.mode = b->counts_mode ? GRAM_COUNTS : b->mode;
   gp.mirror = b->ld_mode ? 1 : 0;
+  gp.fkind = pn->format == GB_PANEL_E2M1 ? 6 : 0;  // kind::f8f6f4 operand format 5 (E2M1) / kind::i8
   gp.diag = b->ld_mode ? 1.0 : 1.0 + b->params.lambda;   // computeLD.cpp:107 vs dist.cpp:172
 
   // ---- windows
@@ -222,7 +225,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     if (nu > 0) place(h_rows_u.data() + b->u_off[w], nu, u_src, u_row0);
 
     const int nbt = (int)((nt + 127) / 128), nbu = (int)((nu + 127) / 128);
-    auto push_tile = [&](bool a_is_u, int bi, int bj) {
+    auto make_tile = [&](bool a_is_u, int bi, int bj) {
       GramTile t{};
       const int64_t na = a_is_u ? nu : nt;
       t.a_src = a_is_u ? u_src : t_src;
@@ -243,16 +246,40 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
         t.ld_out = a_is_u ? sw.ld_u : sw.ld_t;
         t.out_off = a_is_u ? sw.off_ut : sw.off_tt;
       }
-      b->h_tiles.push_back(t);
+      return t;
     };
-    if (b->counts_mode) {
-      for (int bi = 0; bi < nbu; bi++)
-        for (int bj = 0; bj < nbt; bj++) push_tile(true, bi, bj);
-    } else {
-      for (int bi = 0; bi < nbu; bi++)
-        for (int bj = 0; bj < nbt; bj++) push_tile(true, bi, bj);
-      for (int bi = 0; bi < nbt; bi++)
-        for (int bj = 0; bj <= bi; bj++) push_tile(false, bi, bj);
+    // Cluster tiles: the window's A blocks (measured blocks of the B11 lower triangle first, then the
+    // unmeasured blocks of B21) are taken CM at a time against CN measured B blocks.  A-chunk outer /
+    // B-group inner keeps concurrently running clusters on the same A rows (L2 reuse).  Slots with
+    // no work (ragged edges, blocks above the diagonal) keep valid operand coordinates -- their
+    // CTAs still feed the multicast -- but are marked a_valid = 0 so nothing is stored.
+    struct Blk { bool is_u; int bi; };
+    std::vector<Blk> alist;
+    if (!b->counts_mode)
+      for (int bi = 0; bi < nbt; bi++) alist.push_back(Blk{false, bi});
+    for (int bi = 0; bi < nbu; bi++) alist.push_back(Blk{true, bi});
+    const int CM = b->cm, CN = b->cn;
+    for (size_t a0 = 0; a0 < alist.size(); a0 += (size_t)CM) {
+      for (int jg = 0; jg * CN < nbt; jg++) {
+        GramTile slot[16];
+        bool any = false;
+        for (int r = 0; r < CM; r++) {
+          const bool a_ok = a0 + r < alist.size();
+          const Blk a = alist[std::min(a0 + r, alist.size() - 1)];
+          for (int c = 0; c < CN; c++) {
+            const int bj = jg * CN + c;
+            const bool b_ok = bj < nbt;
+            GramTile t = make_tile(a.is_u, a.bi, std::min(bj, nbt - 1));
+            const bool live = a_ok && b_ok && (a.is_u || bj <= a.bi);
+            if (!live) t.a_valid = 0;
+            any |= live;
+            slot[r * CN + c] = t;
+          }
+        }
+        if (any) b->h_tiles.insert(b->h_tiles.end(), slot, slot + CM * CN);
+      }
+    }
+    if (!b->counts_mode) {
       // algorithmic work, SURVEY.md §8(d)
       const double dnt = (double)nt, dnu = (double)nu;
       b->work_gram_ops += 2.0 * N * (dnu * dnt + dnt * (dnt + 1) / 2);
@@ -329,13 +356,15 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   }
   if (b->n_gather > 0) {
     if ((rc = dev_alloc(ctx, &b->d_scratch, (size_t)b->n_gather * pn->k_stride))) return rc;
-    if ((rc = make_row_tensor_map(ctx, &b->tmap_scratch, b->d_scratch, b->n_gather, pn->k_stride))) return rc;
+    if ((rc = make_row_tensor_maps(ctx, &b->tmaps_scratch, b->d_scratch, b->n_gather, pn->k_elems, pn->k_stride,
+                                   pn->format)))
+      return rc;
   } else {
-    b->tmap_scratch = pn->tmap;
+    b->tmaps_scratch = pn->tmaps;
   }
 
   gp.tiles = b->d_tiles;
-  gp.n_tiles = (int)b->h_tiles.size();
+  gp.n_tiles = (int)(b->h_tiles.size() / (size_t)(b->cm * b->cn));
   gp.sx = pn->d_sx;
   gp.sxx = pn->d_sxx;
   gp.stat_ld = pn->capacity;
@@ -349,8 +378,16 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   gp.out_ut = b->d_ut;
   gp.out_counts = b->d_counts;
   gp.counts_seg_stride = b->counts_elems;
-  // the planning uploads read host vectors that die with this frame
+  // the planning uploads read host vectors that die with this frame; the same sync makes the pack
+  // kernels' representability flag readable
+  int h_flags = 0;
+  GB_CUDA(cudaMemcpyAsync(&h_flags, pn->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_flags & 1) {
+    ctx->err = "the panel holds dosages that the E2M1 operand format cannot represent exactly; "
+               "repack it with gb_panel_create_fmt(..., GB_PANEL_INT8, ...)";
+    return GB_ERR_UNSUPPORTED;
+  }
   return GB_OK;
 }
 
@@ -371,7 +408,7 @@ int run_stage(gb_batch* b, int stage) {
                              b->d_pool_u, nullptr);
     }
     case 1:
-      return launch_gram(ctx, pn->tmap, b->tmap_scratch, b->gp);
+      return launch_gram(ctx, pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn);
     case 2: {
       if (b->ld_mode || b->counts_mode) return GB_OK;
       const int nreal = (int)b->h_wins.size();
@@ -426,6 +463,8 @@ int create_batch_internal(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const
   if (params) b->params = *params;
   else gb_params_default(&b->params);
   b->n_windows = n_windows;
+  b->cm = ctx->gram_cm;
+  b->cn = ctx->gram_cn;
   rc = plan_batch(b, t_off, rows_t, u_off, rows_u, z_t, pop_wgt);
   if (rc) {
     free_batch_device(b);
@@ -509,6 +548,22 @@ int gb_ctx_create(int device, gb_ctx** out) {
     return GB_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  if (const char* e = getenv("GB_PANEL_FORMAT")) {
+    if (!strcmp(e, "int8")) ctx->panel_format = GB_PANEL_INT8;
+    else if (!strcmp(e, "e2m1")) ctx->panel_format = GB_PANEL_E2M1;
+  }
+  if (const char* e = getenv("GB_GRAM_CLUSTER")) {  // tuning knob: "CMxCN", e.g. 2x2
+    int cm = 0, cn = 0;
+    if (sscanf(e, "%dx%d", &cm, &cn) == 2 && gram_cluster_supported(cm, cn)) {
+      ctx->gram_cm = cm;
+      ctx->gram_cn = cn;
+    } else {
+      g_create_err = std::string("GB_GRAM_CLUSTER=") + e + " is not a supported cluster shape";
+      cudaStreamDestroy(ctx->own_stream);
+      delete ctx;
+      return GB_ERR_BAD_ARG;
+    }
+  }
   {  // keep freed blocks cached in the device's default pool instead of returning them to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -545,7 +600,15 @@ int64_t gb_ctx_launch_count(const gb_ctx* ctx) { return ctx ? ctx->launches : 0;
 
 // ---- panel ----------------------------------------------------------------------------------
 int gb_panel_create(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t capacity_rows, gb_panel** out) {
-  if (!ctx || !out || !pop_sizes || n_pops < 1 || capacity_rows < 1) {
+  return gb_panel_create_fmt(ctx, n_pops, pop_sizes, capacity_rows, ctx ? ctx->panel_format : GB_PANEL_E2M1, out);
+}
+
+int gb_panel_format_of(const gb_panel* p) { return p ? p->format : -1; }
+
+int gb_panel_create_fmt(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t capacity_rows, int format,
+                        gb_panel** out) {
+  if (!ctx || !out || !pop_sizes || n_pops < 1 || capacity_rows < 1 ||
+      (format != GB_PANEL_INT8 && format != GB_PANEL_E2M1)) {
     if (ctx) ctx->err = "bad panel description";
     return GB_ERR_BAD_ARG;
   }
@@ -560,6 +623,10 @@ int gb_panel_create(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t capac
   if (!p) return GB_ERR_OOM;
   p->ctx = ctx;
   p->n_pops = n_pops;
+  p->format = format;
+  // population blocks start on a K-atom boundary (32 columns); E2M1 rows on a 128-column boundary
+  // because the nibble-expanding TMA type addresses global memory in units of 128 elements
+  p->seg_align = format == GB_PANEL_E2M1 ? K_BLOCK : K_ATOM;
   int k = 0;
   for (int i = 0; i < n_pops; i++) {
     if (pop_sizes[i] < 1) {
@@ -569,10 +636,11 @@ int gb_panel_create(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t capac
     }
     p->pop_sizes.push_back(pop_sizes[i]);
     p->koff.push_back(k);
-    k += round_up(pop_sizes[i], K_ATOM);
+    k += round_up(pop_sizes[i], p->seg_align);
     p->n_samples += pop_sizes[i];
   }
-  p->k_stride = round_up(k, K_BLOCK);
+  p->k_elems = round_up(k, K_BLOCK);
+  p->k_stride = format == GB_PANEL_E2M1 ? p->k_elems / 2 : p->k_elems;
   p->capacity = capacity_rows;
   auto fail = [&](int code) {
     gb_panel_destroy(p);
@@ -591,9 +659,12 @@ int gb_panel_create(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t capac
   if ((rc = pmalloc((void**)&p->d_sxx, sizeof(int32_t) * (size_t)capacity_rows * n_pops))) return fail(rc);
   if ((rc = pmalloc((void**)&p->d_pop_sizes, sizeof(int) * (size_t)n_pops))) return fail(rc);
   if ((rc = pmalloc((void**)&p->d_koff, sizeof(int) * (size_t)n_pops))) return fail(rc);
+  if ((rc = pmalloc((void**)&p->d_flags, sizeof(int)))) return fail(rc);
+  cudaMemsetAsync(p->d_flags, 0, sizeof(int), ctx->stream);
   cudaMemcpyAsync(p->d_pop_sizes, p->pop_sizes.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(p->d_koff, p->koff.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
-  if ((rc = make_row_tensor_map(ctx, &p->tmap, p->d_rows, capacity_rows, p->k_stride))) return fail(rc);
+  if ((rc = make_row_tensor_maps(ctx, &p->tmaps, p->d_rows, capacity_rows, p->k_elems, p->k_stride, format)))
+    return fail(rc);
   cudaStreamSynchronize(ctx->stream);
   *out = p;
   return GB_OK;
@@ -607,12 +678,15 @@ void gb_panel_destroy(gb_panel* p) {
   if (p->d_sxx) cudaFree(p->d_sxx);
   if (p->d_pop_sizes) cudaFree(p->d_pop_sizes);
   if (p->d_koff) cudaFree(p->d_koff);
+  if (p->d_flags) cudaFree(p->d_flags);
   delete p;
 }
 
 int gb_panel_clear(gb_panel* p) {
   if (!p) return GB_ERR_BAD_ARG;
   p->n_rows = 0;
+  cudaSetDevice(p->ctx->device);
+  cudaMemsetAsync(p->d_flags, 0, sizeof(int), p->ctx->stream);
   return GB_OK;
 }
 int64_t gb_panel_num_rows(const gb_panel* p) { return p ? p->n_rows : -1; }
@@ -939,28 +1013,36 @@ int gb_run_window_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const lo
   if ((int64_t)meas.size() <= p.min_num_measured_snp) return GB_ERR_TOO_FEW_MEASURED;      // dist.cpp:146
   if ((int64_t)unme.size() <= p.min_num_unmeasured_snp) return GB_ERR_TOO_FEW_UNMEASURED;  // dist.cpp:147
   const int64_t nt = (int64_t)meas.size(), nu = (int64_t)unme.size();
-  gb_panel* panel = nullptr;
-  int rc = gb_panel_create(ctx, n_pops, pop_sizes, nt + nu, &panel);
-  if (rc) return rc;
   std::vector<const char*> strs((size_t)(nt + nu) * n_pops);
   for (int64_t i = 0; i < nt + nu; i++) {
     const int64_t s = i < nt ? meas[(size_t)i] : unme[(size_t)(i - nt)];
     for (int k = 0; k < n_pops; k++) strs[(size_t)(i * n_pops + k)] = pop_strings[s * n_pops + k];
   }
-  rc = gb_panel_append_strings(panel, nt + nu, strs.data());
-  if (!rc) {
-    std::vector<int64_t> rt((size_t)nt), ru((size_t)nu);
-    std::vector<double> zt((size_t)nt), zu((size_t)nu), iu((size_t)nu);
-    for (int64_t i = 0; i < nt; i++) rt[(size_t)i] = i, zt[(size_t)i] = z[meas[(size_t)i]];
-    for (int64_t i = 0; i < nu; i++) ru[(size_t)i] = nt + i;
-    rc = window_impute(ctx, panel, nt, rt.data(), nu, ru.data(), zt.data(), pop_wgt, &p, zu.data(), iu.data());
-    if (rc == GB_OK || rc == GB_ERR_NOT_PD)
-      for (int64_t i = 0; i < nu; i++) {  // SetZ / SetInfo, dist.cpp:200-202
-        z[unme[(size_t)i]] = zu[(size_t)i];
-        info[unme[(size_t)i]] = iu[(size_t)i];
-      }
+  int rc = GB_OK;
+  gb_panel* panel = nullptr;
+  // Genotype strings of a real panel hold only '0','1','2' -> 4-bit operands.  The reference's
+  // (c - '0') arithmetic accepts any byte; strings with other characters are repacked as int8,
+  // which reproduces it for every 7-bit char.
+  for (int format = ctx->panel_format;; format = GB_PANEL_INT8) {
+    rc = gb_panel_create_fmt(ctx, n_pops, pop_sizes, nt + nu, format, &panel);
+    if (rc) return rc;
+    rc = gb_panel_append_strings(panel, nt + nu, strs.data());
+    if (!rc) {
+      std::vector<int64_t> rt((size_t)nt), ru((size_t)nu);
+      std::vector<double> zt((size_t)nt), zu((size_t)nu), iu((size_t)nu);
+      for (int64_t i = 0; i < nt; i++) rt[(size_t)i] = i, zt[(size_t)i] = z[meas[(size_t)i]];
+      for (int64_t i = 0; i < nu; i++) ru[(size_t)i] = nt + i;
+      rc = window_impute(ctx, panel, nt, rt.data(), nu, ru.data(), zt.data(), pop_wgt, &p, zu.data(), iu.data());
+      if (rc == GB_OK || rc == GB_ERR_NOT_PD)
+        for (int64_t i = 0; i < nu; i++) {  // SetZ / SetInfo, dist.cpp:200-202
+          z[unme[(size_t)i]] = zu[(size_t)i];
+          info[unme[(size_t)i]] = iu[(size_t)i];
+        }
+    }
+    gb_panel_destroy(panel);
+    panel = nullptr;
+    if (rc != GB_ERR_UNSUPPORTED || format == GB_PANEL_INT8) break;
   }
-  gb_panel_destroy(panel);
   return rc;
 }
 

@@ -44,10 +44,11 @@ struct GramTile {      // one 128 x 128 output tile
 };
 
 struct GramParams {
-  const GramTile* tiles;
-  int n_tiles;
+  const GramTile* tiles;  // cm*cn descriptors per cluster tile, in cluster-rank order (r*cn + c)
+  int n_tiles;            // number of CLUSTER tiles
   int mode;
   int n_seg;
+  int fkind;             // tensor-core operand kind: 0 = int8 (kind::i8), k > 0 = kind::f8f6f4 format k-1
   int mirror;            // 1: also store the transposed entry (full symmetric matrix, computeLD)
   Seg seg[P_MAX];
   double coef[P_MAX];    // w_p * (m_p / (m_p - 1))          (util.cpp:117-118)
@@ -79,6 +80,17 @@ struct Ctx {
   int64_t launches = 0;
   // lazily grown device scratch shared by the single-window entry points
   void* fn_encode_tiled = nullptr;  // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
+  int gram_cm = 4, gram_cn = 2;     // thread-block cluster shape of the Gram kernel (A tiles x B tiles)
+  int gram_clusters = 0;            // clusters of the last Gram launch (diagnostics)
+  int panel_format = GB_PANEL_E2M1; // format gb_panel_create uses (GB_PANEL_FORMAT=int8|e2m1 overrides)
+};
+
+// TMA descriptors of one row-major packed-row matrix {k_elems, n_rows} with boxes of 128 K columns x
+// {128, 64, 32, 16} rows: a CM x CN cluster fetches A tiles in 128/CN-row and B tiles in
+// 128/CM-row slices.
+struct RowMaps {
+  static constexpr int N = 4;
+  CUtensorMap m[N];
 };
 
 struct Panel {
@@ -87,15 +99,19 @@ struct Panel {
   std::vector<int> pop_sizes;
   std::vector<int> koff;       // per pop first K column (padded to 32)
   int n_samples = 0;           // sum pop_sizes
-  int k_stride = 0;            // bytes per packed row (multiple of 128)
+  int format = GB_PANEL_E2M1;  // operand encoding of the packed rows (gb_panel_format)
+  int seg_align = K_ATOM;      // population blocks start on multiples of this many K columns
+  int k_elems = 0;             // K columns per packed row (multiple of 128)
+  int k_stride = 0;            // bytes per packed row: k_elems (int8) or k_elems / 2 (E2M1 nibbles)
+  int* d_flags = nullptr;      // [1] bit 0: a dosage outside the format's exact set was packed
   int64_t capacity = 0;
   int64_t n_rows = 0;
-  int8_t* d_rows = nullptr;    // [capacity][k_stride]
+  int8_t* d_rows = nullptr;    // [capacity][k_stride bytes]
   int32_t* d_sx = nullptr;     // [n_pops][capacity]
   int32_t* d_sxx = nullptr;    // [n_pops][capacity]
   int* d_pop_sizes = nullptr;  // [n_pops]
   int* d_koff = nullptr;       // [n_pops]
-  CUtensorMap tmap;            // {k_stride, capacity} int8, box {128, 128}, SWIZZLE_128B
+  RowMaps tmaps;               // {k_stride, capacity} int8, SWIZZLE_128B
 };
 
 #define GB_CUDA(call)                                                                          \
@@ -115,9 +131,10 @@ int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t
                     const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq);
 
 // gb_gram.cu
-int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_rows, int64_t k_stride);
-int launch_gram(Ctx* ctx, const CUtensorMap& tmap_panel, const CUtensorMap& tmap_scratch,
-                const GramParams& prm);
+int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_rows, int64_t k_elems,
+                         int64_t k_stride_bytes, int format);
+bool gram_cluster_supported(int cm, int cn);
+int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn);
 
 // gb_solve.cu
 struct SolveWin {        // per-window solve descriptor

@@ -13,8 +13,16 @@
 // last population the low-rank mean terms, the division by the standard deviations and the
 // forced diagonal are applied and the tile is written out.
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over a static tile list):
-//   warp 0      TMA producer (one elected lane): 128-byte-swizzled [128 rows x 128 B] boxes of A and B
+// Thread-block clusters: a CM x CN cluster works on CM A tiles x CN B tiles at once (CTA rank
+// r*CN + c owns tile (r, c)).  The A tile of cluster row r is needed by its CN CTAs: each of them
+// pulls 1/CN of it from L2 and TMA-multicasts that slice to the whole row; likewise every CTA pulls
+// 1/CM of its B tile and multicasts it down its column.  A 128-byte K block therefore costs
+// 16/CN + 16/CM KiB of L2->SM traffic per CTA instead of 32 KiB (the round-1 limiter, see
+// profiles/r01_gram_ncu_full.md).  A smem stage is refilled by CM+CN-1 producers, so its "empty"
+// barrier collects one multicast tcgen05.commit arrive from every CTA of the row and the column.
+//
+// Warp roles (384 threads, 1 CTA/SM, persistent over a static list of cluster tiles):
+//   warp 0      TMA producer (one elected lane): 128-byte-swizzled row slices of the A and B tiles
 //   warp 1      MMA issuer (one elected lane)
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 64*((w-4)/4)..
@@ -57,10 +65,18 @@ __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 }
 
+// tm_a_*: box {128 B, 128/CN rows} (A-tile slices); tm_b_*: box {128 B, 128/CM rows} (B-tile slices);
+// *_panel reads the packed panel, *_scratch the gathered rows of non-contiguous windows.
+template <int CM, int CN>
 __global__ void __launch_bounds__(THREADS, 1)
-gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
-                   const __grid_constant__ CUtensorMap tm_scratch,
+gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
+                   const __grid_constant__ CUtensorMap tm_a_scratch,
+                   const __grid_constant__ CUtensorMap tm_b_panel,
+                   const __grid_constant__ CUtensorMap tm_b_scratch,
                    const __grid_constant__ GramParams prm) {
+  constexpr int CSIZE = CM * CN;
+  constexpr int SLICE_A = TILE / CN;  // rows of the A tile this CTA fetches
+  constexpr int SLICE_B = TILE / CM;  // rows of the B tile this CTA fetches
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -74,14 +90,26 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  const uint32_t crank = (CSIZE > 1) ? ptx::cluster_ctarank() : 0u;
+  const int cr = (int)crank / CN, cc = (int)crank % CN;
+  // CTAs that share this CTA's A tile (its cluster row) / B tile (its cluster column)
+  const uint16_t mask_row = (uint16_t)(((1u << CN) - 1u) << (cr * CN));
+  uint16_t mask_col = 0;
+#pragma unroll
+  for (int i = 0; i < CM; i++) mask_col |= (uint16_t)(1u << (i * CN + cc));
+  const int n_clusters = gridDim.x / CSIZE;
+  const int cluster_id = blockIdx.x / CSIZE;
+
   if (warp == 0 && ptx::elect_one()) {
-    ptx::prefetch_tmap(&tm_panel);
-    ptx::prefetch_tmap(&tm_scratch);
+    ptx::prefetch_tmap(&tm_a_panel);
+    ptx::prefetch_tmap(&tm_a_scratch);
+    ptx::prefetch_tmap(&tm_b_panel);
+    ptx::prefetch_tmap(&tm_b_scratch);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < STAGES; s++) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], CM + CN - 1);  // one arrive per CTA that receives this CTA's slices
     }
     for (int b = 0; b < ACC_BUFS; b++) {
       ptx::mbar_init(&tfull_bar[b], 1);
@@ -95,6 +123,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CSIZE > 1) ptx::cluster_sync();  // every CTA's barriers are initialised before any peer signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -110,20 +139,27 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-        const GramTile t = prm.tiles[tile];
-        const CUtensorMap* map_a = t.a_src ? &tm_scratch : &tm_panel;
-        const CUtensorMap* map_b = t.b_src ? &tm_scratch : &tm_panel;
+      const uint32_t stage_tx = prm.fkind == 6 ? STAGE_BYTES / 2 : STAGE_BYTES;
+      for (int ct = cluster_id; ct < prm.n_tiles; ct += n_clusters) {
+        const GramTile t = prm.tiles[(long long)ct * CSIZE + crank];
+        const CUtensorMap* map_a = t.a_src ? &tm_a_scratch : &tm_a_panel;
+        const CUtensorMap* map_b = t.b_src ? &tm_b_scratch : &tm_b_panel;
+        const int a_row = t.a_row0 + cc * SLICE_A;
+        const int b_row = t.b_row0 + cr * SLICE_B;
         for (int s = 0; s < n_seg; s++) {
           const int koff = prm.seg[s].koff;
           const int nblk = (prm.seg[s].natoms + 3) >> 2;
           for (int b = 0; b < nblk; b++) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + OFF_STAGES + stage * STAGE_BYTES;
-            uint8_t* sb = sa + STAGE_OPERAND_BYTES;
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-            ptx::tma_load_2d(sa, map_a, &full_bar[stage], koff + b * K_BLOCK, t.a_row0);
-            ptx::tma_load_2d(sb, map_b, &full_bar[stage], koff + b * K_BLOCK, t.b_row0);
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // every receiver has drained this stage
+            uint8_t* sa = smem + OFF_STAGES + stage * STAGE_BYTES + cc * (SLICE_A * K_BLOCK);
+            uint8_t* sb = smem + OFF_STAGES + stage * STAGE_BYTES + STAGE_OPERAND_BYTES + cr * (SLICE_B * K_BLOCK);
+            // own + peers' slices; the mbarrier counts bytes as they sit in global memory (nibble-packed
+            // E2M1 rows complete half of what they occupy in shared memory)
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+            if (CN > 1) ptx::tma_load_2d_mc(sa, map_a, &full_bar[stage], koff + b * K_BLOCK, a_row, mask_row);
+            else ptx::tma_load_2d(sa, map_a, &full_bar[stage], koff + b * K_BLOCK, a_row);
+            if (CM > 1) ptx::tma_load_2d_mc(sb, map_b, &full_bar[stage], koff + b * K_BLOCK, b_row, mask_col);
+            else ptx::tma_load_2d(sb, map_b, &full_bar[stage], koff + b * K_BLOCK, b_row);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -132,13 +168,14 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_i8(TILE, TILE);
+      const int fkind = prm.fkind;  // 0: kind::i8; else kind::f8f6f4 with operand format fkind - 1
+      const uint32_t idesc = fkind ? ptx::make_idesc_f8f6f4(fkind - 1, TILE, TILE) : ptx::make_idesc_i8(TILE, TILE);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t stage_base = ptx::smem_u32(smem + OFF_STAGES);
-      for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+      for (int ct = cluster_id; ct < prm.n_tiles; ct += n_clusters) {
         for (int s = 0; s < n_seg; s++) {
           const int natoms = prm.seg[s].natoms;
           const int nblk = (natoms + 3) >> 2;
@@ -155,10 +192,13 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
             for (int k = 0; k < na; k++) {
               const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * K_ATOM);
               const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * K_ATOM);
-              ptx::mma_i8_ss(d_tmem, da, db, idesc, accumulate);
+              if (fkind) ptx::mma_f8f6f4_ss(d_tmem, da, db, idesc, accumulate);
+              else ptx::mma_i8_ss(d_tmem, da, db, idesc, accumulate);
               accumulate = 1;
             }
-            ptx::mma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+            // frees the smem stage once these MMAs retire -- in every CTA that refills it
+            if (CSIZE > 1) ptx::mma_commit_mc(&empty_bar[stage], mask_row | mask_col);
+            else ptx::mma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(&tfull_bar[acc]);      // accumulator of segment s is complete
@@ -187,8 +227,19 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
     int acc_buf = 0;
     uint32_t acc_phase = 0;
 
-    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-      const GramTile t = prm.tiles[tile];
+    for (int ct = cluster_id; ct < prm.n_tiles; ct += n_clusters) {
+      const GramTile t = prm.tiles[(long long)ct * CSIZE + crank];
+      if (t.a_valid <= 0 || t.b_valid <= 0) {
+        // padding slot of a ragged cluster tile: the MMAs ran (peers need this CTA's slices and
+        // barrier traffic) but nothing is stored; just hand the accumulators back
+        for (int s = 0; s < n_seg; s++) {
+          ptx::mbar_wait(&tfull_bar[acc_buf], acc_phase);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc_buf]);
+          if (++acc_buf == ACC_BUFS) { acc_buf = 0; acc_phase ^= 1; }
+        }
+        continue;
+      }
       // ---- per-tile row statistics into shared memory
       epi_bar_sync();  // previous tile's readers are done
       if (mode != GRAM_COUNTS) {
@@ -240,6 +291,10 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
           uint32_t v[16];
           ptx::tmem_ld_32x32b_x16(taddr + ch * 16, v);
           ptx::tmem_ld_wait();
+          if (prm.fkind) {  // fp32 accumulator holding an exact integer
+#pragma unroll
+            for (int e = 0; e < 16; e++) v[e] = (uint32_t)__float2int_rn(__uint_as_float(v[e]));
+          }
           if (ch == 3) {
             // whole accumulator is in registers: hand the TMEM buffer back to the MMA warp
             ptx::tc_fence_before();
@@ -346,6 +401,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_panel,
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CSIZE > 1) ptx::cluster_sync();  // no peer may still signal this CTA's barriers after it exits
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -362,7 +418,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_rows, int64_t k_stride) {
+int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_rows, int64_t k_elems,
+                        int64_t k_stride_bytes, int format, int box_rows) {
   if (!ctx->fn_encode_tiled) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -374,12 +431,17 @@ int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_
     ctx->fn_encode_tiled = fn;
   }
   if (n_rows < 1) n_rows = 1;
-  cuuint64_t dims[2] = {(cuuint64_t)k_stride, (cuuint64_t)n_rows};
-  cuuint64_t strides[1] = {(cuuint64_t)k_stride};
-  cuuint32_t box[2] = {(cuuint32_t)K_BLOCK, (cuuint32_t)TILE};
+  cuuint64_t dims[2] = {(cuuint64_t)k_elems, (cuuint64_t)n_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)K_BLOCK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  // E2M1 rows are nibble-packed in HBM; the TMA unit expands every 16 nibbles (8 B) into a 16-byte
+  // shared-memory slot, which is the operand layout kind::f8f6f4 reads, so a K block of 128 dosages
+  // occupies the same 128-byte swizzled row as 128 int8 dosages but crosses L2->SM as 64 bytes.
+  const CUtensorMapDataType dt =
+      format == GB_PANEL_E2M1 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->fn_encode_tiled)(
-      out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+      out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -389,19 +451,80 @@ int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_
   return GB_OK;
 }
 
-int launch_gram(Ctx* ctx, const CUtensorMap& tmap_panel, const CUtensorMap& tmap_scratch,
-                const GramParams& prm) {
-  if (prm.n_tiles <= 0) return GB_OK;
-  static bool attr_set = false;
+int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_rows, int64_t k_elems,
+                         int64_t k_stride_bytes, int format) {
+  for (int i = 0; i < RowMaps::N; i++) {
+    int rc = make_row_tensor_map(ctx, &out->m[i], base, n_rows, k_elems, k_stride_bytes, format, TILE >> i);
+    if (rc) return rc;
+  }
+  return GB_OK;
+}
+
+namespace {
+
+template <int CM, int CN>
+int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm) {
+  constexpr int CSIZE = CM * CN;
+  auto kern = gram_seg_i8_kernel<CM, CN>;
+  static bool attr_set_dev[64] = {};   // function attributes are per device
+  static int max_clusters_dev[64] = {};
+  bool& attr_set = attr_set_dev[ctx->device & 63];
+  int& max_clusters = max_clusters_dev[ctx->device & 63];
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CSIZE;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_ALLOC;
+  cfg.stream = ctx->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(gram_seg_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    if (CSIZE > 1) {
+      // how many clusters of this size the device can hold at once (GPC boundaries cost a few SMs)
+      cfg.gridDim = dim3((unsigned)(ctx->sm_count / CSIZE * CSIZE));
+      GB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+      if (max_clusters < 1) {
+        ctx->err = "device cannot co-schedule a cluster of " + std::to_string(CSIZE) + " Gram CTAs";
+        return GB_ERR_UNSUPPORTED;
+      }
+    } else {
+      max_clusters = ctx->sm_count;
+    }
     attr_set = true;
   }
-  int grid = prm.n_tiles < ctx->sm_count ? prm.n_tiles : ctx->sm_count;
-  gram_seg_i8_kernel<<<grid, THREADS, SMEM_ALLOC, ctx->stream>>>(tmap_panel, tmap_scratch, prm);
-  GB_CUDA(cudaGetLastError());
+  const int n_clusters = prm.n_tiles < max_clusters ? prm.n_tiles : max_clusters;
+  cfg.gridDim = dim3((unsigned)(n_clusters * CSIZE));
+  const int ia = CN == 1 ? 0 : CN == 2 ? 1 : CN == 4 ? 2 : 3;  // A slices: 128/CN rows
+  const int ib = CM == 1 ? 0 : CM == 2 ? 1 : CM == 4 ? 2 : 3;  // B slices: 128/CM rows
+  GB_CUDA(cudaLaunchKernelEx(&cfg, kern, panel.m[ia], scratch.m[ia], panel.m[ib], scratch.m[ib], prm));
   ctx->launches++;
+  ctx->gram_clusters = n_clusters;
   return GB_OK;
+}
+
+}  // namespace
+
+bool gram_cluster_supported(int cm, int cn) {
+  return (cm == 1 && cn == 1) || (cm == 2 && cn == 1) || (cm == 2 && cn == 2) || (cm == 4 && cn == 1) ||
+         (cm == 4 && cn == 2) || (cm == 2 && cn == 4) || (cm == 8 && cn == 1);
+}
+
+// prm.n_tiles counts CLUSTER tiles; prm.tiles holds cm*cn descriptors per cluster tile (rank order).
+int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn) {
+  if (prm.n_tiles <= 0) return GB_OK;
+  if (cm == 1 && cn == 1) return launch_gram_t<1, 1>(ctx, panel, scratch, prm);
+  if (cm == 2 && cn == 1) return launch_gram_t<2, 1>(ctx, panel, scratch, prm);
+  if (cm == 2 && cn == 2) return launch_gram_t<2, 2>(ctx, panel, scratch, prm);
+  if (cm == 4 && cn == 1) return launch_gram_t<4, 1>(ctx, panel, scratch, prm);
+  if (cm == 4 && cn == 2) return launch_gram_t<4, 2>(ctx, panel, scratch, prm);
+  if (cm == 2 && cn == 4) return launch_gram_t<2, 4>(ctx, panel, scratch, prm);
+  if (cm == 8 && cn == 1) return launch_gram_t<8, 1>(ctx, panel, scratch, prm);
+  ctx->err = "unsupported Gram cluster shape";
+  return GB_ERR_UNSUPPORTED;
 }
 
 }  // namespace gb

@@ -2,48 +2,75 @@
 //
 // The reference keeps genotypes as one std::string of '0'/'1'/'2' per population on every Snp
 // (snp.h:109, filled by ReadGenotype gauss.cpp:720-785) and re-derives sum x, sum x^2 for every
-// SNP pair.  Here a SNP is packed ONCE into an int8 row whose population blocks start on
-// 32-column boundaries (zero padded: zeros are neutral for sum xy, sum x, sum x^2), and the
-// per-population integer sums are computed once per SNP.
+// SNP pair.  Here a SNP is packed ONCE into a row of int8 bytes or E2M1 nibbles whose population
+// blocks start on 32-column boundaries (zero padded: zeros are neutral for sum xy, sum x,
+// sum x^2), and the per-population integer sums are computed once per SNP.
 #include "gb_common.cuh"
 
 namespace gb {
 
 namespace {
 
-// One CTA per SNP row; warp w packs populations w, w+8, ...  Each lane moves 4 consecutive
-// dosages per step: 4 byte loads (source population offsets are unaligned) and one 32-bit store.
+// 4-bit E2M1 code of a dosage (sign | 2-bit exponent | 1-bit mantissa); 0xFF when not representable.
+__device__ __forceinline__ uint32_t e2m1_code(int v) {
+  const int a = v < 0 ? -v : v;
+  uint32_t c;
+  switch (a) {
+    case 0: c = 0x0; break;
+    case 1: c = 0x2; break;
+    case 2: c = 0x4; break;
+    case 3: c = 0x5; break;
+    case 4: c = 0x6; break;
+    case 6: c = 0x7; break;
+    default: return 0xFFu;
+  }
+  return (v < 0 && a) ? (c | 0x8u) : c;
+}
+
+// One CTA per SNP row; warp w packs populations w, w+8, ...  Each lane moves 8 consecutive
+// dosages per step: byte loads (source population offsets are unaligned) and one 64-bit (int8) or
+// 32-bit (E2M1 nibbles, low nibble = lower K index) store.
+template <int FORMAT>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_ascii,
-                 int8_t* __restrict__ dst, int k_stride, long long row0, int n_pops,
+                 int8_t* __restrict__ dst, int k_elems, int k_stride, long long row0, int n_pops,
                  const int* __restrict__ pop_sizes, const int* __restrict__ koff,
-                 int32_t* __restrict__ sx, int32_t* __restrict__ sxx, long long stat_ld) {
+                 int32_t* __restrict__ sx, int32_t* __restrict__ sxx, long long stat_ld, int* flags,
+                 int seg_align) {
   const long long row = blockIdx.x;
   const uint8_t* s = src + row * src_stride;
   int8_t* d = dst + (row0 + row) * (long long)k_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = is_ascii ? 48 : 0;
+  bool bad = false;
   // source offset of population p = sum of sizes before it
   int src_off = 0;
   int next_p = 0;
   for (int p = warp; p < n_pops; p += 8) {
     for (; next_p < p; next_p++) src_off += pop_sizes[next_p];
     const int m = pop_sizes[p];
-    const int kp = (m + K_ATOM - 1) / K_ATOM * K_ATOM;
+    const int kp = (m + seg_align - 1) / seg_align * seg_align;
     const uint8_t* sp = s + src_off;
-    uint32_t* dp = reinterpret_cast<uint32_t*>(d + koff[p]);
     int sum = 0, sq = 0;
-    for (int j = lane * 4; j < kp; j += 128) {
-      uint32_t word = 0;
+    for (int j = lane * 8; j < kp; j += 256) {
+      uint32_t lo = 0, hi = 0;
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
+      for (int b = 0; b < 8; b++) {
         int v = 0;
         if (j + b < m) v = (int)(signed char)((int)sp[j + b] - sub);
         sum += v;
         sq += v * v;
-        word |= (uint32_t)(v & 0xff) << (8 * b);
+        if (FORMAT == GB_PANEL_E2M1) {
+          const uint32_t c = e2m1_code(v);
+          bad |= c == 0xFFu;
+          lo |= (c & 0xFu) << (4 * b);
+        } else {
+          if (b < 4) lo |= (uint32_t)(v & 0xff) << (8 * b);
+          else hi |= (uint32_t)(v & 0xff) << (8 * (b - 4));
+        }
       }
-      dp[j >> 2] = word;
+      if (FORMAT == GB_PANEL_E2M1) *reinterpret_cast<uint32_t*>(d + ((koff[p] + j) >> 1)) = lo;
+      else *reinterpret_cast<uint2*>(d + koff[p] + j) = make_uint2(lo, hi);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -55,9 +82,11 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
       sxx[(long long)p * stat_ld + row0 + row] = sq;
     }
   }
+  if (bad) atomicOr(flags, 1);
   // zero the tail between the last population block and the row stride
-  const int k_end = koff[n_pops - 1] + (pop_sizes[n_pops - 1] + K_ATOM - 1) / K_ATOM * K_ATOM;
-  for (int j = k_end + threadIdx.x * 4; j < k_stride; j += 256 * 4)
+  const int k_end = koff[n_pops - 1] + (pop_sizes[n_pops - 1] + seg_align - 1) / seg_align * seg_align;
+  const int b_end = FORMAT == GB_PANEL_E2M1 ? k_end >> 1 : k_end;
+  for (int j = b_end + threadIdx.x * 4; j < k_stride; j += 256 * 4)
     *reinterpret_cast<uint32_t*>(d + j) = 0u;
 }
 
@@ -121,9 +150,16 @@ __global__ void row_prep_kernel(const int32_t* __restrict__ rows, long long n, i
 int launch_pack(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int is_ascii,
                 int64_t row0, int64_t n_rows) {
   if (n_rows <= 0) return GB_OK;
-  pack_rows_kernel<<<(unsigned)n_rows, 256, 0, ctx->stream>>>(
-      static_cast<const uint8_t*>(dev_src), src_stride, is_ascii, panel->d_rows, panel->k_stride, row0,
-      panel->n_pops, panel->d_pop_sizes, panel->d_koff, panel->d_sx, panel->d_sxx, panel->capacity);
+  if (panel->format == GB_PANEL_E2M1)
+    pack_rows_kernel<GB_PANEL_E2M1><<<(unsigned)n_rows, 256, 0, ctx->stream>>>(
+        static_cast<const uint8_t*>(dev_src), src_stride, is_ascii, panel->d_rows, panel->k_elems, panel->k_stride,
+        row0, panel->n_pops, panel->d_pop_sizes, panel->d_koff, panel->d_sx, panel->d_sxx, panel->capacity,
+        panel->d_flags, panel->seg_align);
+  else
+    pack_rows_kernel<GB_PANEL_INT8><<<(unsigned)n_rows, 256, 0, ctx->stream>>>(
+        static_cast<const uint8_t*>(dev_src), src_stride, is_ascii, panel->d_rows, panel->k_elems, panel->k_stride,
+        row0, panel->n_pops, panel->d_pop_sizes, panel->d_koff, panel->d_sx, panel->d_sxx, panel->capacity,
+        panel->d_flags, panel->seg_align);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

@@ -19,8 +19,11 @@ GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "go
                 if not os.path.basename(p).startswith("pgc2_"))
 
 
-def make_panel(ctx, g, pop_sizes, mode="i8"):
-    p = gb.Panel(ctx, pop_sizes, len(g))
+FORMATS = ["e2m1", "int8"]   # enum gb_panel_format: both feed the same kernel and must agree bit for bit
+
+
+def make_panel(ctx, g, pop_sizes, mode="i8", fmt=None):
+    p = gb.Panel(ctx, pop_sizes, len(g), fmt)
     if mode == "i8":
         p.append_host(g.astype(np.int8), is_ascii=False)
     elif mode == "ascii":
@@ -30,10 +33,12 @@ def make_panel(ctx, g, pop_sizes, mode="i8"):
 
 
 # ------------------------------------------------------------------ integer surface: bit-exact
+@pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("mode", ["i8", "ascii"])
-def test_gram_counts_bit_exact(gpu_ctx, oracle, mode):
+def test_gram_counts_bit_exact(gpu_ctx, oracle, mode, fmt):
     c = small_case(seed=21, n_snps=330, pop_sizes=(61, 103, 40, 25, 2, 330, 97, 128, 31, 33))
-    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"], mode)
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"], mode, fmt)
+    assert panel.format == fmt
     rows_a = np.arange(0, 200)
     rows_b = np.arange(193, 330)           # ragged: 200 x 137, overlapping ranges
     sxy, sx, sxx = panel.gram_counts(rows_a, rows_b)
@@ -55,11 +60,14 @@ def test_gram_counts_gathered_rows(gpu_ctx, oracle):
     np.testing.assert_array_equal(sxy, o_sxy)
 
 
-def test_gram_counts_33kg_shape(gpu_ctx):
-    """Full K extent (32,147 individuals, 21 populations): exactness via numpy int64 matmul."""
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_gram_counts_33kg_shape(gpu_ctx, fmt):
+    """Full K extent (32,147 individuals, 21 populations): exactness via numpy int64 matmul.  Rows of
+    all-2 / all-1 dosages drive the per-population counts to their maximum (4 x 6,360 = 25,440)."""
     _, sizes, _ = synth.flagged_33kg_pgc2()
     g = synth.make_genotypes(160, sizes, seed=3)
-    panel = make_panel(gpu_ctx, g, sizes)
+    g[31], g[32], g[33] = 2, 1, 2
+    panel = make_panel(gpu_ctx, g, sizes, fmt=fmt)
     sxy, sx, sxx = panel.gram_counts(np.arange(0, 130), np.arange(30, 160))
     offs = np.concatenate([[0], np.cumsum(sizes)])
     for p in range(len(sizes)):
@@ -71,12 +79,13 @@ def test_gram_counts_33kg_shape(gpu_ctx):
 
 
 # ------------------------------------------------------------------ correlations
+@pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("mix", [True, False])
-def test_correlation_blocks_match_oracle(gpu_ctx, oracle, mix):
+def test_correlation_blocks_match_oracle(gpu_ctx, oracle, mix, fmt):
     c = small_case(seed=23, n_snps=420, pop_sizes=(33, 129, 500, 64, 7))
     meas, unme = split_rows(c)
     w = c["w"] if mix else None
-    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"])
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"], fmt=fmt)
     B11, B21 = panel.window_cor(meas, unme, w)
     r = oracle.run_window(c["type"], c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"], dump=True)
     assert np.abs(B11 - r["B11"]).max() <= 1e-13
@@ -107,10 +116,11 @@ def test_window_imputation_matches_oracle(gpu_ctx, oracle, mix):
     assert np.abs(info - r["info"][unme]).max() <= TIGHT
 
 
+@pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-def test_against_golden_reference_vectors(gpu_ctx, path):
+def test_against_golden_reference_vectors(gpu_ctx, path, fmt):
     d = np.load(path)
-    panel = make_panel(gpu_ctx, d["g"], d["pop_sizes"])
+    panel = make_panel(gpu_ctx, d["g"], d["pop_sizes"], fmt=fmt)
     meas, unme = d["meas"], d["unme"]
     z, info, _ = panel.window_distmix(meas, unme, d["z"][meas], d["w"])
     assert np.abs(z - d["mix_z"][unme]).max() <= TOL and np.abs(info - d["mix_info"][unme]).max() <= TOL
@@ -120,6 +130,59 @@ def test_against_golden_reference_vectors(gpu_ctx, path):
     assert np.abs(ld - d["ld"]).max() <= TOL
     np.testing.assert_array_equal(np.diag(ld), np.ones(len(meas)))
     np.testing.assert_array_equal(ld, ld.T)
+
+
+def test_formats_agree_bitwise_and_pooled_counts_reach_17_bits(gpu_ctx, oracle):
+    """dist() pools all 32,147 individuals into ONE accumulation (counts up to 4 x 32,147 = 128,588):
+    the fp32 accumulator of the E2M1 path must still hold exact integers, i.e. give the very same
+    doubles as the int8 path, and both must match CalCor."""
+    _, sizes, w = synth.flagged_33kg_pgc2()
+    g = synth.make_genotypes(200, sizes, seed=31)
+    g[0], g[1] = 2, 2
+    g[1, ::7] = 1
+    g[0, 5] = 1
+    meas, unme = np.arange(0, 60), np.arange(60, 200)
+    out = {}
+    for fmt in FORMATS:
+        panel = make_panel(gpu_ctx, g, sizes, fmt=fmt)
+        out[fmt] = panel.window_cor(meas, unme, None) + panel.window_cor(meas, unme, w)
+    for a, b in zip(out["e2m1"], out["int8"]):
+        np.testing.assert_array_equal(a, b)
+    assert oracle.cal_cor(g[0], g[1], sizes) == out["int8"][0][0, 1]
+    assert abs(oracle.cal_cor(g[3], g[100], sizes) - out["e2m1"][1][40, 3]) <= 1e-15
+
+
+def test_unrepresentable_dosage_needs_int8(gpu_ctx, oracle):
+    """The reference computes (c - '0') for ANY byte.  int8 panels reproduce that; an E2M1 panel must
+    refuse (not silently round) and the string-level mirror must repack by itself."""
+    c = small_case(seed=32, n_snps=160, pop_sizes=(50, 7, 211, 96))
+    g = c["g"].copy()
+    g[3, 10], g[90, 200] = 5, 7          # '5' and '7' in the genotype strings
+    rows_t, rows_u = np.arange(0, 40), np.arange(40, 160)
+    p4 = make_panel(gpu_ctx, g, c["pop_sizes"], fmt="e2m1")
+    with pytest.raises(gb.GaussB200Error) as e:
+        p4.window_distmix(rows_t, rows_u, c["z"][rows_t], c["w"])
+    assert e.value.status == gb.api.GB_ERR_UNSUPPORTED
+    p8 = make_panel(gpu_ctx, g, c["pop_sizes"], fmt="int8")
+    sxy, sx, sxx = p8.gram_counts(np.arange(0, 100), np.arange(60, 160))
+    o = oracle.gram_counts(g[0:100], g[60:160], c["pop_sizes"])
+    for a, b in zip((sxy, sx, sxx), o):
+        np.testing.assert_array_equal(a, b)
+    # values E2M1 does hold exactly besides 0/1/2: 3, 4, 6
+    g2 = c["g"].copy()
+    g2[3, 10], g2[90, 200], g2[91, 3] = 3, 4, 6
+    sxy, _, _ = make_panel(gpu_ctx, g2, c["pop_sizes"], fmt="e2m1").gram_counts(np.arange(0, 100), np.arange(60, 160))
+    np.testing.assert_array_equal(sxy, oracle.gram_counts(g2[0:100], g2[60:160], c["pop_sizes"])[0])
+    # the host mirror of run_distmix gets strings and picks the format itself
+    offs = np.concatenate([[0], np.cumsum(c["pop_sizes"])])
+    chars = (g.astype(np.int16) + 48).astype(np.uint8)
+    strings = [[chars[i, offs[p]:offs[p + 1]].tobytes() for p in range(len(c["pop_sizes"]))] for i in range(len(g))]
+    out = gpu_ctx.run_window_strings(c["type"][:160], c["bp"][:160], c["z"][:160], np.ones(160), strings,
+                                     c["pop_sizes"], c["w"], c["start_bp"], c["end_bp"])
+    r = oracle.run_window(c["type"][:160], c["bp"][:160], c["z"][:160], g, c["pop_sizes"], c["w"],
+                          c["start_bp"], c["end_bp"])
+    assert out["rc"] == r["rc"] == 0
+    assert np.abs(out["z"] - r["z"]).max() <= TOL and np.abs(out["info"] - r["info"]).max() <= TOL
 
 
 def test_compute_ld_matches_oracle(gpu_ctx, oracle):
