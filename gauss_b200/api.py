@@ -37,7 +37,8 @@ class Params(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libgauss_b200.so")
+    # GB_LIBRARY_PATH: tuning builds of the same sources (e.g. a different pipeline depth)
+    return os.environ.get("GB_LIBRARY_PATH") or os.path.join(_HERE, "lib", "libgauss_b200.so")
 
 
 def header_path() -> str:

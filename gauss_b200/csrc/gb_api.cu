@@ -40,6 +40,8 @@ struct gb_batch {
   int32_t *d_rows_t = nullptr, *d_rows_u = nullptr, *d_gather = nullptr;
   int32_t *d_pool_t = nullptr, *d_pool_u = nullptr;
   double *d_sd_t = nullptr, *d_sd_u = nullptr, *d_rq_t = nullptr;
+  int32_t *d_st_sx_t = nullptr, *d_st_sx_u = nullptr;     // [n_pops][n_*_total] per listed row: sum x
+  double *d_st_mean_t = nullptr, *d_st_mean_u = nullptr;  // [n_pops][n_*_total] sum x / m
   int* d_skip = nullptr;
   double gneg = 0.0;  // (sum(w)-1)_+ * max(w), +inf when the analytic PD bound does not apply
   double *d_zt = nullptr, *d_y = nullptr, *d_zu = nullptr, *d_info = nullptr;
@@ -83,6 +85,7 @@ int check_device(Ctx* ctx) {
 
 void free_batch_device(gb_batch* b) {
   void* ptrs[] = {b->d_rows_t, b->d_rows_u, b->d_gather, b->d_pool_t, b->d_pool_u, b->d_sd_t, b->d_sd_u, b->d_rq_t, b->d_skip,
+                  b->d_st_sx_t, b->d_st_sx_u, b->d_st_mean_t, b->d_st_mean_u,
                   b->d_zt, b->d_y, b->d_zu, b->d_info, b->d_tt, b->d_ut, b->d_dinv,
                   b->d_coef, b->d_wgt, b->d_counts, b->d_status, b->d_wins, b->d_tiles,
                   b->d_scratch};
@@ -337,6 +340,13 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   if ((rc = dev_alloc(ctx, &b->d_pool_t, (size_t)b->n_t_total))) return rc;
   if ((rc = dev_alloc(ctx, &b->d_pool_u, (size_t)b->n_u_total))) return rc;
   if ((rc = dev_alloc(ctx, &b->d_status, 2 * (size_t)nw + 2))) return rc;
+  if (b->mode == GRAM_MIX && !b->counts_mode) {
+    const size_t P = (size_t)pn->n_pops;
+    if ((rc = dev_alloc(ctx, &b->d_st_sx_t, P * (size_t)b->n_t_total))) return rc;
+    if ((rc = dev_alloc(ctx, &b->d_st_mean_t, P * (size_t)b->n_t_total))) return rc;
+    if ((rc = dev_alloc(ctx, &b->d_st_sx_u, P * (size_t)b->n_u_total))) return rc;
+    if ((rc = dev_alloc(ctx, &b->d_st_mean_u, P * (size_t)b->n_u_total))) return rc;
+  }
   if (b->counts_mode) {
     if ((rc = dev_alloc(ctx, &b->d_counts, (size_t)b->counts_elems * pn->n_pops))) return rc;
   } else {
@@ -365,11 +375,12 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
 
   gp.tiles = b->d_tiles;
   gp.n_tiles = (int)(b->h_tiles.size() / (size_t)(b->cm * b->cn));
-  gp.sx = pn->d_sx;
-  gp.sxx = pn->d_sxx;
-  gp.stat_ld = pn->capacity;
-  gp.rows_t = b->d_rows_t;
-  gp.rows_u = b->d_rows_u;
+  gp.st_sx_t = b->d_st_sx_t;
+  gp.st_sx_u = b->d_st_sx_u;
+  gp.st_mean_t = b->d_st_mean_t;
+  gp.st_mean_u = b->d_st_mean_u;
+  gp.st_ld_t = b->n_t_total;
+  gp.st_ld_u = b->n_u_total;
   gp.sd_t = b->d_sd_t;
   gp.sd_u = b->d_sd_u;
   gp.pool_t = b->d_pool_t;
@@ -402,10 +413,10 @@ int run_stage(gb_batch* b, int stage) {
         if ((rc = launch_gather_rows(ctx, pn, b->d_gather, b->n_gather, b->d_scratch))) return rc;
       if (b->counts_mode) return GB_OK;
       if ((rc = launch_row_prep(ctx, pn, b->d_rows_t, b->n_t_total, b->mode, b->d_coef, b->d_wgt, b->d_sd_t,
-                                b->d_pool_t, b->d_rq_t)))
+                                b->d_pool_t, b->d_rq_t, b->d_st_sx_t, b->d_st_mean_t)))
         return rc;
       return launch_row_prep(ctx, pn, b->d_rows_u, b->n_u_total, b->mode, b->d_coef, b->d_wgt, b->d_sd_u,
-                             b->d_pool_u, nullptr);
+                             b->d_pool_u, nullptr, b->d_st_sx_u, b->d_st_mean_u);
     }
     case 1:
       return launch_gram(ctx, pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn);

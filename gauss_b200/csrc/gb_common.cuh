@@ -55,11 +55,12 @@ struct GramParams {
   double wgt[P_MAX];     // w_p
   double n_pooled;       // total flagged individuals (dist)
   double diag;           // value forced on the diagonal of T x T tiles (1 + lambda, or 1.0)
-  const int32_t* sx;     // [n_pops][stat_ld] per-population sum x   (panel rows)
-  const int32_t* sxx;    // [n_pops][stat_ld] per-population sum x^2
-  long long stat_ld;
-  const int32_t* rows_t; // batch row lists -> panel rows
-  const int32_t* rows_u;
+  // per listed row and population, precomputed by row_prep_kernel (list order, [n_seg][st_ld_*]):
+  const int32_t* st_sx_t;   // sum x
+  const int32_t* st_sx_u;
+  const double* st_mean_t;  // sum x / m   (util.cpp:119)
+  const double* st_mean_u;
+  long long st_ld_t, st_ld_u;
   const double* sd_t;    // per listed row: mix: sqrt(cov_ii); pooled: sqrt(N*sxx - sx^2)
   const double* sd_u;
   const int32_t* pool_t; // pooled sum x per listed row (dist)
@@ -80,7 +81,10 @@ struct Ctx {
   int64_t launches = 0;
   // lazily grown device scratch shared by the single-window entry points
   void* fn_encode_tiled = nullptr;  // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
-  int gram_cm = 4, gram_cn = 2;     // thread-block cluster shape of the Gram kernel (A tiles x B tiles)
+  // Thread-block cluster shape of the Gram kernel (A tiles x B tiles).  Measured on B200:
+  // an SM takes in about one 128-byte TMA row every ~3.5 clocks whoever requested it, so multicast
+  // does not raise the feed rate and only couples the CTAs; 1 x 1 is the fastest shape.
+  int gram_cm = 1, gram_cn = 1;
   int gram_clusters = 0;            // clusters of the last Gram launch (diagnostics)
   int panel_format = GB_PANEL_E2M1; // format gb_panel_create uses (GB_PANEL_FORMAT=int8|e2m1 overrides)
 };
@@ -128,7 +132,8 @@ int launch_pack(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride,
                 int64_t row0, int64_t n_rows);
 int launch_gather_rows(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int8_t* dst);
 int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int mode,
-                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq);
+                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq,
+                    int32_t* d_st_sx, double* d_st_mean);
 
 // gb_gram.cu
 int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_rows, int64_t k_elems,

@@ -34,7 +34,10 @@ namespace gb {
 namespace {
 
 constexpr int TILE = 128;
-constexpr int STAGES = 4;
+#ifndef GB_GRAM_STAGES
+#define GB_GRAM_STAGES 4
+#endif
+constexpr int STAGES = GB_GRAM_STAGES;
 constexpr int STAGE_OPERAND_BYTES = TILE * K_BLOCK;  // 16 KiB
 constexpr int STAGE_BYTES = 2 * STAGE_OPERAND_BYTES; // A + B
 constexpr int ACC_BUFS = 4;                          // 4 x 128 TMEM columns
@@ -60,6 +63,18 @@ constexpr int OFF_TMEM_PTR = OFF_BARS + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget exceeded");
+
+// int32 -> double through the 2^52 trick: one LOP and one exact DADD on the fp64 pipe (64 / clk / SM)
+// instead of I2F.F64, which issues at 16 / clk / SM and was the epilogue's limiter.
+__device__ __forceinline__ double int_to_double(int v) {
+  return __dsub_rn(__hiloint2double(0x43300000, v ^ 0x80000000), 4503601774854144.0);  // 2^52 + 2^31
+}
+// fp32 accumulator of kind::f8f6f4 holding an exact integer |n| < 2^22 -> int, without F2I:
+// the bit pattern of n + 1.5 * 2^23 is that of 1.5 * 2^23 (0x4B400000) plus n.
+__device__ __forceinline__ int f32_count_to_int(uint32_t bits) {
+  const float f = __uint_as_float(bits) + 12582912.0f;
+  return (int)__float_as_uint(f) - 0x4B400000;
+}
 
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -167,6 +182,9 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
+    // One thread feeds the tensor core; a 128x128x32 MMA lasts 64 clocks, so the loop around it is
+    // kept to a handful of instructions: the descriptor of K atom k is the stage descriptor + 2*k
+    // (32 bytes >> 4) in its low word, and full K blocks are issued fully unrolled.
     if (ptx::elect_one()) {
       const int fkind = prm.fkind;  // 0: kind::i8; else kind::f8f6f4 with operand format fkind - 1
       const uint32_t idesc = fkind ? ptx::make_idesc_f8f6f4(fkind - 1, TILE, TILE) : ptx::make_idesc_i8(TILE, TILE);
@@ -174,30 +192,41 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t stage_base = ptx::smem_u32(smem + OFF_STAGES);
+      const uint64_t desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + OFF_STAGES));
+      const uint16_t free_mask = mask_row | mask_col;
       for (int ct = cluster_id; ct < prm.n_tiles; ct += n_clusters) {
         for (int s = 0; s < n_seg; s++) {
-          const int natoms = prm.seg[s].natoms;
-          const int nblk = (natoms + 3) >> 2;
+          int atoms = prm.seg[s].natoms;
           ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TILE;
           uint32_t accumulate = 0;
-          for (int b = 0; b < nblk; b++) {
+          for (; atoms > 0; atoms -= 4) {
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
-            const uint32_t a_addr = stage_base + stage * STAGE_BYTES;
-            const uint32_t b_addr = a_addr + STAGE_OPERAND_BYTES;
-            const int na = min(4, natoms - b * 4);
-            for (int k = 0; k < na; k++) {
-              const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * K_ATOM);
-              const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * K_ATOM);
-              if (fkind) ptx::mma_f8f6f4_ss(d_tmem, da, db, idesc, accumulate);
-              else ptx::mma_i8_ss(d_tmem, da, db, idesc, accumulate);
-              accumulate = 1;
+            const uint64_t da = desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+            const uint64_t db = da + (STAGE_OPERAND_BYTES >> 4);
+            if (atoms >= 4) {
+              if (fkind) {
+                ptx::mma_f8f6f4_ss(d_tmem, da, db, idesc, accumulate);
+                ptx::mma_f8f6f4_ss(d_tmem, da + 2, db + 2, idesc, 1);
+                ptx::mma_f8f6f4_ss(d_tmem, da + 4, db + 4, idesc, 1);
+                ptx::mma_f8f6f4_ss(d_tmem, da + 6, db + 6, idesc, 1);
+              } else {
+                ptx::mma_i8_ss(d_tmem, da, db, idesc, accumulate);
+                ptx::mma_i8_ss(d_tmem, da + 2, db + 2, idesc, 1);
+                ptx::mma_i8_ss(d_tmem, da + 4, db + 4, idesc, 1);
+                ptx::mma_i8_ss(d_tmem, da + 6, db + 6, idesc, 1);
+              }
+            } else {
+              for (int k = 0; k < atoms; k++) {
+                if (fkind) ptx::mma_f8f6f4_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
+                else ptx::mma_i8_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
+              }
             }
+            accumulate = 1;
             // frees the smem stage once these MMAs retire -- in every CTA that refills it
-            if (CSIZE > 1) ptx::mma_commit_mc(&empty_bar[stage], mask_row | mask_col);
+            if (CSIZE > 1) ptx::mma_commit_mc(&empty_bar[stage], free_mask);
             else ptx::mma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -224,6 +253,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     double* sdA = reinterpret_cast<double*>(smem + OFF_SDA);
     double* sdB = reinterpret_cast<double*>(smem + OFF_SDB);
     const int mode = prm.mode;
+    const bool f32acc = prm.fkind != 0;
     int acc_buf = 0;
     uint32_t acc_phase = 0;
 
@@ -240,30 +270,33 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
         }
         continue;
       }
-      // ---- per-tile row statistics into shared memory
+      // ---- per-tile row statistics into shared memory: plain copies of what row_prep_kernel
+      // precomputed per listed row (sum x and sum x / m per population) -- no division here
       epi_bar_sync();  // previous tile's readers are done
       if (mode != GRAM_COUNTS) {
         const int side = etid >> 7;  // 0: A rows, 1: B rows
         const int idx = etid & 127;
         const int valid = side ? t.b_valid : t.a_valid;
-        const int li = (side ? t.b_list0 : t.a_list0) + min(idx, valid - 1);
+        const long long li = (side ? t.b_list0 : t.a_list0) + min(idx, valid - 1);
         const bool from_u = (side == 0) && t.a_is_u;
         if (mode == GRAM_MIX) {
-          const int prow = from_u ? prm.rows_u[li] : prm.rows_t[li];
+          const int32_t* st_sx = from_u ? prm.st_sx_u : prm.st_sx_t;
+          const double* st_mean = from_u ? prm.st_mean_u : prm.st_mean_t;
+          const long long ld = from_u ? prm.st_ld_u : prm.st_ld_t;
           int32_t* sdst = side ? sB : sA;
+          double* mdst = side ? hB : gA;
+          // CalWgtCov(x, y): wsum_mi_mj += (wgt*(sumx/m))*(sumy/m) with x the FIRST argument.
+          // B21 rows call it with x = unmeasured (our A side); B11 / LD call it with x = the
+          // smaller SNP index, which in a lower-triangle tile is our B side.  Store the weighted
+          // mean on the x side and the plain mean on the y side so the product rounds identically.
+          const bool x_side = t.a_is_u ? (side == 0) : (side == 1);
           double wsum = 0.0;
+#pragma unroll 4
           for (int p = 0; p < n_seg; p++) {
-            const int32_t sx = prm.sx[(long long)p * prm.stat_ld + prow];
-            sdst[p * TILE + idx] = sx;
-            const double mean = (double)sx / prm.seg[p].m;       // sumx/m       (util.cpp:119)
+            const double mean = st_mean[p * ld + li];            // sumx/m       (util.cpp:119)
+            sdst[p * TILE + idx] = st_sx[p * ld + li];
             const double wm = __dmul_rn(prm.wgt[p], mean);       // wgt*(sumx/m)
-            // CalWgtCov(x, y): wsum_mi_mj += (wgt*(sumx/m))*(sumy/m) with x the FIRST argument.
-            // B21 rows call it with x = unmeasured (our A side); B11 / LD call it with x = the
-            // smaller SNP index, which in a lower-triangle tile is our B side.  Store the weighted
-            // mean on the x side and the plain mean on the y side so the product rounds identically.
-            const bool x_side = t.a_is_u ? (side == 0) : (side == 1);
-            if (side) hB[p * TILE + idx] = x_side ? wm : mean;
-            else gA[p * TILE + idx] = x_side ? wm : mean;
+            mdst[p * TILE + idx] = x_side ? wm : mean;
             wsum = __dadd_rn(wsum, wm);                          // wsum_mi += ... (util.cpp:120-121)
           }
           (side ? bjS : aiS)[idx] = wsum;
@@ -285,22 +318,25 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
         const int m = prm.seg[s].m;
         const double coef = prm.coef[s];
         const int sAr = (mode == GRAM_MIX) ? sA[s * TILE + r] : 0;
-        // four 16-column chunks, one after the other, so only 16 staging registers are live
+        // Four 16-column chunks, software pipelined: the tcgen05.ld of chunk ch+1 is in flight
+        // while chunk ch is folded (two 16-register staging buffers).
+        uint32_t vbuf[2][16];
+        ptx::tmem_ld_32x32b_x16(taddr, vbuf[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ch++) {
-          uint32_t v[16];
-          ptx::tmem_ld_32x32b_x16(taddr + ch * 16, v);
+          uint32_t (&v)[16] = vbuf[ch & 1];
           ptx::tmem_ld_wait();
-          if (prm.fkind) {  // fp32 accumulator holding an exact integer
-#pragma unroll
-            for (int e = 0; e < 16; e++) v[e] = (uint32_t)__float2int_rn(__uint_as_float(v[e]));
-          }
-          if (ch == 3) {
+          if (ch < 3) {
+            ptx::tmem_ld_32x32b_x16(taddr + (ch + 1) * 16, vbuf[(ch + 1) & 1]);
+          } else {
             // whole accumulator is in registers: hand the TMEM buffer back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc_buf]);
           }
+          int cnt[16];
+#pragma unroll
+          for (int e = 0; e < 16; e++) cnt[e] = f32acc ? f32_count_to_int(v[e]) : (int)v[e];
           if (mode == GRAM_MIX) {
             const int4* sBv = reinterpret_cast<const int4*>(sB + s * TILE + c0 + ch * 16);
 #pragma unroll
@@ -309,21 +345,21 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
               const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
               for (int k = 0; k < 4; k++) {
-                const int d = m * (int)v[q * 4 + k] - sAr * bb[k];  // m*sumxy - sumx*sumy, exact
+                const int d = m * cnt[q * 4 + k] - sAr * bb[k];  // m*sumxy - sumx*sumy, exact
                 acc[ch * 16 + q * 4 + k] =
-                    __dadd_rn(acc[ch * 16 + q * 4 + k], __dmul_rn(coef, (double)d));
+                    __dadd_rn(acc[ch * 16 + q * 4 + k], __dmul_rn(coef, int_to_double(d)));
               }
             }
           } else if (mode == GRAM_POOLED) {
 #pragma unroll
-            for (int e = 0; e < 16; e++) acc[ch * 16 + e] = (double)(int)v[e];
+            for (int e = 0; e < 16; e++) acc[ch * 16 + e] = int_to_double(cnt[e]);
           } else {  // GRAM_COUNTS
             if (r < t.a_valid) {
               int32_t* dst = prm.out_counts + (long long)s * prm.counts_seg_stride + t.out_off +
                              (long long)(t.i0 + r) * t.ld_out + t.j0 + c0 + ch * 16;
 #pragma unroll
               for (int e = 0; e < 16; e++)
-                if (c0 + ch * 16 + e < t.b_valid) dst[e] = (int)v[e];
+                if (c0 + ch * 16 + e < t.b_valid) dst[e] = cnt[e];
             }
           }
         }
@@ -338,13 +374,17 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       double* out = (t.a_is_u ? prm.out_ut : prm.out_tt) + t.out_off;
       const long long gi = t.i0 + r;
       const bool diag_tile = (!t.a_is_u) && (t.i0 == t.j0);
-      if (mode == GRAM_MIX) {
-        const double ai = aiS[r];
+      const double pooled_n = prm.n_pooled;
+      const double pooled_sx = (mode == GRAM_POOLED) ? int_to_double(sA[r]) : 0.0;
+      const double ai = (mode == GRAM_MIX) ? aiS[r] : 0.0;
 #pragma unroll
-        for (int ch = 0; ch < EPI_COLS / 8; ch++) {
+      for (int ch = 0; ch < EPI_COLS / 8; ch++) {
+        double num8[8];
+        if (mode == GRAM_MIX) {
           double x[8];
 #pragma unroll
           for (int k = 0; k < 8; k++) x[k] = 0.0;
+#pragma unroll 3
           for (int p = 0; p < n_seg; p++) {  // wsum_mi_mj += wgt*(sumx/m)*(sumy/m)  (util.cpp:119)
             const double g = gA[p * TILE + r];
             const double2* hv = reinterpret_cast<const double2*>(hB + p * TILE + c0 + ch * 8);
@@ -355,41 +395,32 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
               x[2 * k2 + 1] = __dadd_rn(x[2 * k2 + 1], __dmul_rn(g, h2.y));
             }
           }
-          // Finish 8 entries.  Deliberately a rolled loop over a small local array: unrolling
-          // would put 8 IEEE divisions in flight on top of the 64 live accumulators and spill.
-          double num8[8];
 #pragma unroll
-          for (int k = 0; k < 8; k++) num8[k] = __dadd_rn(acc[ch * 8 + k], x[k]);  // wsumcov + wsum_mi_mj
-#pragma unroll 1
           for (int k = 0; k < 8; k++) {
-            const int c = c0 + ch * 8 + k;
-            // (wsumcov + wsum_mi_mj - wsum_mi*wsum_mj) / (stdi*stdj)   (util.cpp:123, distmix.cpp:196)
-            const double cov = __dsub_rn(num8[k], __dmul_rn(ai, bjS[c]));
-            double cor = __ddiv_rn(cov, __dmul_rn(sd_r, sdB[c]));
+            // wsumcov + wsum_mi_mj - wsum_mi*wsum_mj   (util.cpp:123)
+            num8[k] = __dsub_rn(__dadd_rn(acc[ch * 8 + k], x[k]), __dmul_rn(ai, bjS[c0 + ch * 8 + k]));
+          }
+        } else {  // pooled Pearson r: num_samples*sumxy - sumx*sumy   (util.cpp:66)
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            num8[k] = __dsub_rn(__dmul_rn(pooled_n, acc[ch * 8 + k]),
+                                __dmul_rn(pooled_sx, int_to_double(sB[c0 + ch * 8 + k])));
+        }
+        // 8 IEEE divisions, four at a time (a rolled loop would expose the whole ~30-instruction
+        // latency chain of each division; eight in flight would spill next to the 64 accumulators)
+#pragma unroll
+        for (int h4 = 0; h4 < 2; h4++) {
+          double cor4[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++)   // numerator / (stdi*stdj)   (distmix.cpp:196, util.cpp:69)
+            cor4[k] = __ddiv_rn(num8[h4 * 4 + k], __dmul_rn(sd_r, sdB[c0 + ch * 8 + h4 * 4 + k]));
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int c = c0 + ch * 8 + h4 * 4 + k;
             const long long gj = t.j0 + c;
+            double cor = cor4[k];
             if (diag_tile && gi == gj) cor = prm.diag;
             if (row_ok && c < t.b_valid && !(diag_tile && gi < gj)) {  // diagonal tiles: lower part only
-              out[gj * t.ld_out + gi] = cor;
-              if (prm.mirror) out[gi * t.ld_out + gj] = cor;
-            }
-          }
-        }
-      } else {  // pooled Pearson r (util.cpp:66-69)
-        const double n = prm.n_pooled;
-        const double sx = (double)sA[r];
-#pragma unroll
-        for (int ch = 0; ch < EPI_COLS / 8; ch++) {
-          double num8[8];
-#pragma unroll
-          for (int k = 0; k < 8; k++) num8[k] = __dmul_rn(n, acc[ch * 8 + k]);  // num_samples*sumxy
-#pragma unroll 1
-          for (int k = 0; k < 8; k++) {
-            const int c = c0 + ch * 8 + k;
-            const double numer = __dsub_rn(num8[k], __dmul_rn(sx, (double)sB[c]));
-            double cor = __ddiv_rn(numer, __dmul_rn(sd_r, sdB[c]));
-            const long long gj = t.j0 + c;
-            if (diag_tile && gi == gj) cor = prm.diag;
-            if (row_ok && c < t.b_valid && !(diag_tile && gi < gj)) {
               out[gj * t.ld_out + gi] = cor;
               if (prm.mirror) out[gi * t.ld_out + gj] = cor;
             }

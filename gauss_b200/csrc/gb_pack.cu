@@ -110,7 +110,8 @@ __global__ void row_prep_kernel(const int32_t* __restrict__ rows, long long n, i
                                 const double* __restrict__ wgt, const int32_t* __restrict__ sx,
                                 const int32_t* __restrict__ sxx, long long stat_ld,
                                 double* __restrict__ sd, int32_t* __restrict__ pool,
-                                double* __restrict__ rq) {
+                                double* __restrict__ rq, int32_t* __restrict__ st_sx,
+                                double* __restrict__ st_mean) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long prow = rows[i];
@@ -123,6 +124,8 @@ __global__ void row_prep_kernel(const int32_t* __restrict__ rows, long long n, i
       const double d = (double)((long long)m * q - s * s);          // m*sumxy - sumx*sumy (exact)
       wsumcov = __dadd_rn(wsumcov, __dmul_rn(coef[p], d));          // util.cpp:118
       const double mean = __ddiv_rn((double)s, (double)m);
+      st_sx[(long long)p * n + i] = (int32_t)s;       // list-ordered copies the Gram epilogue streams per tile
+      st_mean[(long long)p * n + i] = mean;
       const double wm = __dmul_rn(wgt[p], mean);
       wsum_mi_mj = __dadd_rn(wsum_mi_mj, __dmul_rn(wm, mean));      // util.cpp:119
       wsum_mi = __dadd_rn(wsum_mi, wm);                             // util.cpp:120-121
@@ -174,12 +177,13 @@ int launch_gather_rows(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int6
 }
 
 int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int mode,
-                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq) {
+                    const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq,
+                    int32_t* d_st_sx, double* d_st_mean) {
   if (n <= 0) return GB_OK;
   const int bs = 128;
   row_prep_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, ctx->stream>>>(
       d_rows, n, mode, panel->n_pops, panel->d_pop_sizes, d_coef, d_wgt, panel->d_sx, panel->d_sxx,
-      panel->capacity, d_sd, d_pool, d_rq);
+      panel->capacity, d_sd, d_pool, d_rq, d_st_sx, d_st_mean);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;
