@@ -319,26 +319,35 @@ def run_gpu(args):
     host.copy_(geno)
     torch.cuda.synchronize()
     del geno
-    wpanel = gb.Panel(ctx, sizes, int(max(len(x["measured"]) + len(x["unmeasured"]) for x in windows)))
+    max_rows = int(max(len(x["measured"]) + len(x["unmeasured"]) for x in windows))
+    pipe = gb.Pipe(ctx, sizes, max_rows, depth=3)
     e2e_steps = max(1, min(args.steps, 3))
     h2d = d2h = 0
+    res_z = [np.zeros(len(x["unmeasured"])) for x in windows]
+    res_i = [np.zeros(len(x["unmeasured"])) for x in windows]
 
     def e2e_step(count=False):
+        """One pass over the chromosome through the reference-facing per-window call with HOST buffers:
+        gb_pipe_submit (pinned host rows -> H2D -> pack -> Gram -> solve -> D2H) / gb_pipe_wait."""
         nonlocal h2d, d2h
         done = 0
-        for x in windows:
+        pending = []
+        for wi, x in enumerate(windows):
             a, b = len(x["measured"]), len(x["unmeasured"])
             if a <= 10 or b <= 10:
                 continue
             m0, u0 = int(pos_in_block[x["measured"][0]]), int(pos_in_block[x["unmeasured"][0]])
-            wpanel.clear()
-            wpanel.append_host_ptr(host.data_ptr() + m0 * N, a, N, False)   # pinned host -> H2D -> pack
-            wpanel.append_host_ptr(host.data_ptr() + u0 * N, b, N, False)
-            zz, ii, rc = wpanel.window_distmix(np.arange(a), np.arange(a, a + b), z_by_site[x["measured"]], w)
+            t = pipe.submit_ptr(host.data_ptr() + m0 * N, a, host.data_ptr() + u0 * N, b, N, False,
+                                z_by_site[x["measured"]], w, res_z[wi], res_i[wi])
+            pending.append(t)
+            if len(pending) >= 3:
+                assert pipe.wait(pending.pop(0)) == 0
             done += b
             if count:
                 h2d += (a + b) * N + a * 8 + (a + b) * 8 + len(w) * 8
                 d2h += b * 16 + 8
+        for t in pending:
+            assert pipe.wait(t) == 0
         return done
 
     e2e_done, e2e_s = 0, 1.0
@@ -372,7 +381,7 @@ def run_gpu(args):
             dtype="int8 Gram (int32 accumulate) + f64 epilogue/solve", data="synthetic",
             config=workload_config(),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                     steps=e2e_steps, note="per-window gb_panel_append_host + gb_window_distmix, pinned host rows"),
+                     steps=e2e_steps, note="per-window gb_pipe_submit / gb_pipe_wait (depth 3), pinned host int8 rows"),
             gpu_launches=int(launches),
             clocks=clocks,
             roofline=dict(bound="tensor", kernel="gram_seg_i8_kernel", achieved=achieved, peak=int8_peak,

@@ -94,6 +94,11 @@ def load_library():
         "gb_batch_run_stage": (C.c_int, [vp, C.c_int]),
         "gb_batch_fetch": (C.c_int, [vp, dblp, dblp, vp]),
         "gb_batch_work": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "gb_pipe_create": (C.c_int, [vp, C.c_int, i32p, i64, C.c_int, C.c_int, C.POINTER(vp)]),
+        "gb_pipe_destroy": (None, [vp]),
+        "gb_pipe_submit": (C.c_int, [vp, i64, vp, i64, vp, i64, C.c_int, dblp, dblp, C.POINTER(Params), dblp, dblp,
+                                     C.POINTER(C.c_int64)]),
+        "gb_pipe_wait": (C.c_int, [vp, i64, C.POINTER(C.c_int)]),
         "gb_run_window_strings": (C.c_int, [vp, i64, vp, vp, dblp, dblp, vp, C.c_int, vp, dblp, C.c_longlong,
                                             C.c_longlong, C.POINTER(Params), C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)]),
@@ -331,6 +336,61 @@ class Batch:
     def close(self):
         if getattr(self, "h", None):
             self.ctx.lib.gb_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pipe:
+    """gb_pipe: asynchronous per-window pipeline on host buffers (H2D of window w+1 overlaps window w)."""
+
+    def __init__(self, ctx: Context, pop_sizes, max_rows_per_window: int, depth: int = 2, fmt: str | None = None):
+        self.ctx = ctx
+        self.pop_sizes = np.ascontiguousarray(pop_sizes, np.int32)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.gb_pipe_create(ctx.h, len(self.pop_sizes), _ptr(self.pop_sizes), int(max_rows_per_window),
+                                         int(depth), -1 if fmt is None else PANEL_FORMATS[fmt], C.byref(h)))
+        self.h = h
+        self._keep = {}
+
+    def submit_ptr(self, ptr_t: int, n_t: int, ptr_u: int, n_u: int, row_stride: int, is_ascii: bool, z_t, pop_wgt,
+                   z_u: np.ndarray, info_u: np.ndarray, params: Params | None = None) -> int:
+        """Host pointers to n_t measured / n_u unmeasured rows; z_u / info_u are written by the time
+        wait(ticket) returns.  Buffers must stay alive until then (they are kept referenced here)."""
+        zt = _f64(z_t)
+        w = None if pop_wgt is None else _f64(pop_wgt)
+        t = C.c_int64(-1)
+        self.ctx.check(self.ctx.lib.gb_pipe_submit(self.h, n_t, C.c_void_p(ptr_t), n_u, C.c_void_p(ptr_u), row_stride,
+                                                   int(bool(is_ascii)), _ptr(zt), _ptr(w),
+                                                   C.byref(params) if params else None, _ptr(z_u), _ptr(info_u),
+                                                   C.byref(t)))
+        self._keep[t.value] = (zt, w, z_u, info_u)
+        return t.value
+
+    def submit(self, rows_t: np.ndarray, rows_u: np.ndarray, z_t, pop_wgt, z_u=None, info_u=None,
+               params: Params | None = None):
+        rows_t, rows_u = np.ascontiguousarray(rows_t), np.ascontiguousarray(rows_u)
+        assert rows_t.itemsize == 1 and rows_u.itemsize == 1
+        z_u = np.zeros(len(rows_u)) if z_u is None else z_u
+        info_u = np.zeros(len(rows_u)) if info_u is None else info_u
+        t = self.submit_ptr(rows_t.ctypes.data, len(rows_t), rows_u.ctypes.data, len(rows_u), rows_t.shape[1],
+                            rows_t.dtype == np.uint8, z_t, pop_wgt, z_u, info_u, params)
+        self._keep[t] = self._keep[t] + (rows_t, rows_u)
+        return t, z_u, info_u
+
+    def wait(self, ticket: int) -> int:
+        st = C.c_int(0)
+        self.ctx.check(self.ctx.lib.gb_pipe_wait(self.h, ticket, C.byref(st)))
+        self._keep.pop(ticket, None)
+        return st.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gb_pipe_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -14,6 +14,8 @@ using namespace gb;
 
 struct gb_ctx : public Ctx {};
 struct gb_panel : public Panel {};
+struct gb_pipe;
+extern "C" void gb_pipe_destroy(gb_pipe* pp);
 
 static thread_local std::string g_create_err;
 
@@ -54,6 +56,8 @@ struct gb_batch {
   int8_t* d_scratch = nullptr;
   RowMaps tmaps_scratch;
   int cm = 1, cn = 1;                 // Gram cluster shape this batch was planned for
+  bool defer_flag_check = false;      // pipelined path: the panel is still being packed at plan time
+  std::vector<int> h_status;          // fetch staging: [2*n_windows + 2 status words | panel flags]
   GramParams gp{};
 };
 
@@ -91,6 +95,12 @@ void free_batch_device(gb_batch* b) {
                   b->d_scratch};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, b->ctx->stream);
+}
+
+int unrepresentable(Ctx* ctx) {
+  ctx->err = "the panel holds dosages that the E2M1 operand format cannot represent exactly; "
+             "repack it with gb_panel_create_fmt(..., GB_PANEL_INT8, ...)";
+  return GB_ERR_UNSUPPORTED;
 }
 
 // Shared planner.  rows_u may be empty (ld_mode).  In counts_mode rows_u plays the A side and
@@ -392,13 +402,10 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   // the planning uploads read host vectors that die with this frame; the same sync makes the pack
   // kernels' representability flag readable
   int h_flags = 0;
-  GB_CUDA(cudaMemcpyAsync(&h_flags, pn->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!b->defer_flag_check)
+    GB_CUDA(cudaMemcpyAsync(&h_flags, pn->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h_flags & 1) {
-    ctx->err = "the panel holds dosages that the E2M1 operand format cannot represent exactly; "
-               "repack it with gb_panel_create_fmt(..., GB_PANEL_INT8, ...)";
-    return GB_ERR_UNSUPPORTED;
-  }
+  if (h_flags & 1) return unrepresentable(ctx);
   return GB_OK;
 }
 
@@ -453,7 +460,7 @@ int run_stage(gb_batch* b, int stage) {
 int create_batch_internal(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const int64_t* t_off,
                           const int64_t* rows_t, const int64_t* u_off, const int64_t* rows_u, const double* z_t,
                           const double* pop_wgt, const gb_params* params, bool ld_mode, bool counts_mode,
-                          gb_batch** out) {
+                          gb_batch** out, bool defer_flag_check = false) {
   if (!ctx || !panel || !out || n_windows < 0 || !t_off || (!rows_t && t_off[n_windows] > 0)) {
     if (ctx) ctx->err = "null or negative argument";
     return GB_ERR_BAD_ARG;
@@ -476,6 +483,7 @@ int create_batch_internal(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const
   b->n_windows = n_windows;
   b->cm = ctx->gram_cm;
   b->cn = ctx->gram_cn;
+  b->defer_flag_check = defer_flag_check;
   rc = plan_batch(b, t_off, rows_t, u_off, rows_u, z_t, pop_wgt);
   if (rc) {
     free_batch_device(b);
@@ -806,20 +814,25 @@ int gb_batch_run_stage(gb_batch* b, int stage) {
   return run_stage(b, stage);
 }
 
-int gb_batch_fetch(gb_batch* b, double* z_u, double* info_u, int* window_status_out) {
-  if (!b || b->ld_mode || b->counts_mode) return GB_ERR_BAD_ARG;
+// Results leave in two halves so the pipelined path can enqueue the copies at submit time and
+// interpret them after its own event wait.
+static int fetch_enqueue(gb_batch* b, double* z_u, double* info_u, int* status_staging) {
   Ctx* ctx = b->ctx;
-  int rc = check_device(ctx);
-  if (rc) return rc;
-  const size_t nreal = b->h_wins.size();
-  std::vector<int> st(2 * (size_t)b->n_windows + 2, 0);
   if (b->n_u_total) {
     if (z_u) GB_CUDA(cudaMemcpyAsync(z_u, b->d_zu, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
     if (info_u) GB_CUDA(cudaMemcpyAsync(info_u, b->d_info, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
   }
   // d_status is indexed by position in the factorisation list: [real windows | certificate copies]
-  GB_CUDA(cudaMemcpyAsync(st.data(), b->d_status, sizeof(int) * st.size(), cudaMemcpyDeviceToHost, ctx->stream));
-  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const size_t n_st = 2 * (size_t)b->n_windows + 2;
+  GB_CUDA(cudaMemcpyAsync(status_staging, b->d_status, sizeof(int) * n_st, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaMemcpyAsync(status_staging + n_st, b->panel->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  return GB_OK;
+}
+
+static int fetch_finish(gb_batch* b, const int* st, double* z_u, double* info_u, int* window_status_out) {
+  const size_t nreal = b->h_wins.size();
+  const size_t n_st = 2 * (size_t)b->n_windows + 2;
+  if (st[n_st] & 1) return unrepresentable(b->ctx);
   std::vector<int> st_w((size_t)b->n_windows, 0), st_pd_w((size_t)b->n_windows, 0);
   for (size_t a = 0; a < b->active.size(); a++) {
     st_w[(size_t)b->active[a]] = st[a];
@@ -838,6 +851,17 @@ int gb_batch_fetch(gb_batch* b, double* z_u, double* info_u, int* window_status_
       }
   }
   return window_status_out ? GB_OK : worst;
+}
+
+int gb_batch_fetch(gb_batch* b, double* z_u, double* info_u, int* window_status_out) {
+  if (!b || b->ld_mode || b->counts_mode) return GB_ERR_BAD_ARG;
+  Ctx* ctx = b->ctx;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  b->h_status.assign(2 * (size_t)b->n_windows + 3, 0);
+  if ((rc = fetch_enqueue(b, z_u, info_u, b->h_status.data()))) return rc;
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return fetch_finish(b, b->h_status.data(), z_u, info_u, window_status_out);
 }
 
 int gb_batch_work(const gb_batch* b, double* gram_ops, double* solve_flops, double* panel_bytes) {
@@ -998,6 +1022,183 @@ int gb_gram_counts(gb_ctx* ctx, gb_panel* panel, int64_t n_a, const int64_t* row
   }
   gb_batch_destroy(b);
   return rc;
+}
+
+
+// ---- pipelined single windows on HOST buffers ---------------------------------------------------
+// dist()/distmix() are called once per window with genotypes that live in host memory.  A gb_pipe
+// keeps `depth` device slots (raw staging rows + packed panel); submitting window w+1 starts its
+// host->device copy on a dedicated copy stream while window w is still packing / multiplying /
+// solving on the ctx stream, so the PCIe copy -- the longest leg of a window -- never waits for compute.
+struct gb_pipe {
+  Ctx* ctx = nullptr;
+  int depth = 0;
+  int64_t max_rows = 0;
+  int64_t n_samples = 0;
+  cudaStream_t copy_stream = nullptr;
+  struct Slot {
+    gb_panel* panel = nullptr;
+    uint8_t* d_stage = nullptr;   // [max_rows][n_samples] raw host rows
+    cudaEvent_t h2d_done = nullptr, done = nullptr;
+    gb_batch* batch = nullptr;    // in flight
+    int* h_status = nullptr;      // pinned
+    double *h_z = nullptr, *h_info = nullptr;  // pinned result staging [max_rows] (caller buffers may be pageable,
+                                               // and a device->pageable copy would block the submitting thread)
+    double *z_u = nullptr, *info_u = nullptr;  // caller's result buffers, filled at wait time
+    int64_t n_u = 0;
+    int64_t ticket = -1;
+    int early_status = GB_OK;     // window rejected at plan time (too few SNPs)
+  };
+  std::vector<Slot> slots;
+  int64_t next_ticket = 0;
+};
+
+static int pipe_retire(gb_pipe* pp, gb_pipe::Slot& sl, int* status_out) {
+  Ctx* ctx = pp->ctx;
+  int rc = sl.early_status;
+  if (sl.batch) {
+    GB_CUDA(cudaEventSynchronize(sl.done));
+    std::memcpy(sl.z_u, sl.h_z, sizeof(double) * (size_t)sl.n_u);
+    std::memcpy(sl.info_u, sl.h_info, sizeof(double) * (size_t)sl.n_u);
+    rc = fetch_finish(sl.batch, sl.h_status, sl.z_u, sl.info_u, nullptr);
+    free_batch_device(sl.batch);
+    delete sl.batch;
+    sl.batch = nullptr;
+  }
+  sl.ticket = -1;
+  sl.early_status = GB_OK;
+  if (status_out) *status_out = rc;
+  return GB_OK;
+}
+
+int gb_pipe_create(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t max_rows_per_window, int depth, int format,
+                   gb_pipe** out) {
+  if (!ctx || !out || depth < 1 || depth > 8 || max_rows_per_window < 1) {
+    if (ctx) ctx->err = "bad pipe description";
+    return GB_ERR_BAD_ARG;
+  }
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  gb_pipe* pp = new (std::nothrow) gb_pipe();
+  if (!pp) return GB_ERR_OOM;
+  pp->ctx = ctx;
+  pp->depth = depth;
+  pp->max_rows = max_rows_per_window;
+  pp->slots.resize((size_t)depth);
+  auto fail = [&](int code) {
+    gb_pipe_destroy(pp);
+    return code;
+  };
+  if (cudaStreamCreateWithFlags(&pp->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(GB_ERR_CUDA);
+  for (auto& sl : pp->slots) {
+    if ((rc = gb_panel_create_fmt(ctx, n_pops, pop_sizes, max_rows_per_window, format < 0 ? ctx->panel_format : format,
+                                  &sl.panel)))
+      return fail(rc);
+    pp->n_samples = sl.panel->n_samples;
+    if (cudaMalloc(reinterpret_cast<void**>(&sl.d_stage), (size_t)max_rows_per_window * (size_t)pp->n_samples) != cudaSuccess)
+      return fail(GB_ERR_OOM);
+    if (cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&sl.h_status), sizeof(int) * 8) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&sl.h_z), sizeof(double) * (size_t)max_rows_per_window) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&sl.h_info), sizeof(double) * (size_t)max_rows_per_window) != cudaSuccess)
+      return fail(GB_ERR_CUDA);
+  }
+  *out = pp;
+  return GB_OK;
+}
+
+void gb_pipe_destroy(gb_pipe* pp) {
+  if (!pp) return;
+  cudaSetDevice(pp->ctx->device);
+  for (auto& sl : pp->slots) {
+    if (sl.batch) {
+      cudaEventSynchronize(sl.done);
+      free_batch_device(sl.batch);
+      delete sl.batch;
+    }
+    if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.h_status) cudaFreeHost(sl.h_status);
+    if (sl.h_z) cudaFreeHost(sl.h_z);
+    if (sl.h_info) cudaFreeHost(sl.h_info);
+    if (sl.d_stage) cudaFree(sl.d_stage);
+    if (sl.panel) gb_panel_destroy(sl.panel);
+  }
+  if (pp->copy_stream) cudaStreamDestroy(pp->copy_stream);
+  delete pp;
+}
+
+int gb_pipe_submit(gb_pipe* pp, int64_t n_t, const void* host_rows_t, int64_t n_u, const void* host_rows_u,
+                   int64_t row_stride, int is_ascii, const double* z_t, const double* pop_wgt, const gb_params* params,
+                   double* z_u, double* info_u, int64_t* ticket) {
+  if (!pp || !ticket || n_t < 0 || n_u < 0 || (n_t && !host_rows_t) || (n_u && !host_rows_u) || !z_u || !info_u ||
+      (!z_t && n_t > 0) || row_stride < pp->n_samples || n_t + n_u > pp->max_rows) {
+    if (pp) pp->ctx->err = "bad pipe submit arguments";
+    return GB_ERR_BAD_ARG;
+  }
+  Ctx* ctx = pp->ctx;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  gb_pipe::Slot& sl = pp->slots[(size_t)(pp->next_ticket % pp->depth)];
+  if (sl.ticket >= 0 && (rc = pipe_retire(pp, sl, nullptr))) return rc;  // slot still owned by an un-waited ticket
+  const size_t N = (size_t)pp->n_samples;
+  // 1. raw rows -> device staging on the copy stream (pinned host memory makes this asynchronous)
+  if (n_t) GB_CUDA(cudaMemcpy2DAsync(sl.d_stage, N, host_rows_t, (size_t)row_stride, N, (size_t)n_t,
+                                     cudaMemcpyHostToDevice, pp->copy_stream));
+  if (n_u) GB_CUDA(cudaMemcpy2DAsync(sl.d_stage + (size_t)n_t * N, N, host_rows_u, (size_t)row_stride, N, (size_t)n_u,
+                                     cudaMemcpyHostToDevice, pp->copy_stream));
+  GB_CUDA(cudaEventRecord(sl.h2d_done, pp->copy_stream));
+  // 2. plan the window (host work + descriptor uploads; synchronises the ctx stream, i.e. at most
+  //    the previous window's kernels -- the copy above keeps running meanwhile)
+  gb_panel_clear(sl.panel);
+  sl.panel->n_rows = n_t + n_u;
+  std::vector<int64_t> rt((size_t)n_t), ru((size_t)n_u);
+  for (int64_t i = 0; i < n_t; i++) rt[(size_t)i] = i;
+  for (int64_t i = 0; i < n_u; i++) ru[(size_t)i] = n_t + i;
+  const int64_t t_off[2] = {0, n_t}, u_off[2] = {0, n_u};
+  double dummy = 0.0;
+  gb_batch* b = nullptr;
+  sl.z_u = z_u;
+  sl.info_u = info_u;
+  sl.n_u = n_u;
+  sl.ticket = pp->next_ticket;
+  *ticket = pp->next_ticket++;
+  rc = create_batch_internal(static_cast<gb_ctx*>(ctx), sl.panel, 1, t_off, rt.data(), u_off, ru.data(),
+                             z_t ? z_t : &dummy, pop_wgt, params, false, false, &b, /*defer_flag_check=*/true);
+  if (rc) {
+    sl.early_status = rc;
+    return GB_OK;  // reported by gb_pipe_wait, like a window the reference refuses
+  }
+  if (b->plan_status[0] != GB_OK) {
+    sl.early_status = b->plan_status[0];
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int64_t i = 0; i < n_u; i++) z_u[i] = info_u[i] = nan;
+    free_batch_device(b);
+    delete b;
+    return GB_OK;
+  }
+  sl.batch = b;
+  // 3. pack + window kernels + result copies on the ctx stream, after the rows have landed
+  GB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+  if ((rc = launch_pack(ctx, sl.panel, sl.d_stage, (int64_t)N, is_ascii, 0, n_t + n_u))) return rc;
+  for (int st = 0; st < 4; st++)
+    if ((rc = run_stage(b, st))) return rc;
+  if ((rc = fetch_enqueue(b, sl.h_z, sl.h_info, sl.h_status))) return rc;
+  GB_CUDA(cudaEventRecord(sl.done, ctx->stream));
+  return GB_OK;
+}
+
+int gb_pipe_wait(gb_pipe* pp, int64_t ticket, int* window_status) {
+  if (!pp || ticket < 0 || ticket >= pp->next_ticket) return GB_ERR_BAD_ARG;
+  int rc = check_device(pp->ctx);
+  if (rc) return rc;
+  gb_pipe::Slot& sl = pp->slots[(size_t)(ticket % pp->depth)];
+  if (sl.ticket != ticket) {  // already retired when its slot was reused
+    pp->ctx->err = "ticket was already retired (its slot has been reused): wait within `depth` submissions";
+    return GB_ERR_BAD_ARG;
+  }
+  return pipe_retire(pp, sl, window_status);
 }
 
 // ---- host-side mirror of run_dist / run_distmix ---------------------------------------------------

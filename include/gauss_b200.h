@@ -54,6 +54,7 @@ enum gb_status {
 typedef struct gb_ctx gb_ctx;     /* one per GPU */
 typedef struct gb_panel gb_panel; /* HBM-resident packed reference panel */
 typedef struct gb_batch gb_batch; /* a planned set of windows on one panel */
+typedef struct gb_pipe gb_pipe;   /* asynchronous per-window pipeline on host buffers */
 
 /* Hidden arguments of the reference (struct Arguments, gauss.h:44-62; defaults gauss.cpp:18-35). */
 typedef struct gb_params {
@@ -163,6 +164,25 @@ GB_API int gb_batch_work(const gb_batch *batch, double *gram_ops, double *solve_
 /* Enqueue only one stage (profiling / roofline timing): 0 = row statistics, 1 = Gram+epilogue,
  * 2 = Cholesky, 3 = triangular solve + finalise. */
 GB_API int gb_batch_run_stage(gb_batch *batch, int stage);
+
+/* ---- pipelined single windows, host in / host out ---------------------------------------------- */
+/* What a genome loop over dist()/distmix() calls (dist.cpp:63-75 runs one window per call): the
+ * host->device copy of window w+1 overlaps the kernels of window w.  `depth` device slots of
+ * max_rows_per_window rows each; format < 0 selects the ctx default.  Host row buffers, z_u and
+ * info_u must stay valid until the ticket is waited for, and should be page-locked (pinned) for the
+ * copies to be asynchronous.  A ticket must be waited for within `depth` further submissions.
+ * gb_pipe_wait returns the window's status (GB_OK, GB_ERR_TOO_FEW_*, GB_ERR_NOT_PD, ...) in
+ * *window_status exactly as gb_window_dist/distmix would. */
+GB_API int gb_pipe_create(gb_ctx *ctx, int n_pops, const int *pop_sizes, int64_t max_rows_per_window,
+                   int depth, int format, gb_pipe **out);
+GB_API void gb_pipe_destroy(gb_pipe *pipe);
+/* host_rows_t / host_rows_u: n_t measured and n_u unmeasured SNP rows (sum(pop_sizes) bytes each,
+ * row_stride apart; is_ascii as in gb_panel_append_host).  pop_wgt == NULL selects dist(). */
+GB_API int gb_pipe_submit(gb_pipe *pipe, int64_t n_t, const void *host_rows_t, int64_t n_u,
+                   const void *host_rows_u, int64_t row_stride, int is_ascii, const double *z_t,
+                   const double *pop_wgt, const gb_params *params, double *z_u, double *info_u,
+                   int64_t *ticket);
+GB_API int gb_pipe_wait(gb_pipe *pipe, int64_t ticket, int *window_status);
 
 /* ---- host-side mirror of the reference seam --------------------------------------------------- */
 /* run_dist / run_distmix on a bp-sorted snp_vec given as parallel arrays: type (0/1/2), bp, z,

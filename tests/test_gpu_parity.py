@@ -314,3 +314,54 @@ def test_33kg_shaped_window_matches_oracle(gpu_ctx, oracle):
     za, _, _ = panel.window_distmix(meas, unme, np.ones(len(meas)), w)
     zb, _, _ = panel.window_distmix(meas, unme, zin[meas] + 1.0, w)
     assert np.abs(zb - (z + za)).max() <= 1e-9
+
+
+def test_pipe_matches_single_window_calls(gpu_ctx, oracle):
+    """gb_pipe_submit / gb_pipe_wait: host rows in, host results out, copies overlapped with compute.
+    Results must be identical to the blocking per-window call, in any submission order, and the
+    reference's refusals must come back as the window status."""
+    c = small_case(seed=33, n_snps=900, pop_sizes=(61, 103, 40, 25, 2, 330, 97), measured_frac=0.3, core=(0, 900))
+    g, t = c["g"].astype(np.int8), c["type"]
+    panel = make_panel(gpu_ctx, g, c["pop_sizes"])
+    wins = [(0, 300), (150, 520), (400, 900), (880, 900), (300, 700), (100, 400), (0, 900)]
+    pipe = gb.Pipe(gpu_ctx, c["pop_sizes"], 900, depth=2)
+    tickets, outs = [], []
+    for lo, hi in wins:
+        idx = np.arange(lo, hi)
+        rt, ru = idx[t[lo:hi] == 1], idx[t[lo:hi] == 0]
+        tk, z, info = pipe.submit(g[rt], g[ru], c["z"][rt], c["w"])
+        tickets.append(tk)
+        outs.append((rt, ru, z, info))
+        if len(tickets) >= 2:                       # wait lags one window behind, like a genome loop
+            k = len(tickets) - 2
+            st = pipe.wait(tickets[k])
+            assert (st != 0) == (k == 3)
+    assert pipe.wait(tickets[-1]) == 0
+    for k, (rt, ru, z, info) in enumerate(outs):
+        if k == 3:
+            assert np.isnan(z).all()
+            continue
+        z1, i1, _ = panel.window_distmix(rt, ru, c["z"][rt], c["w"])
+        np.testing.assert_array_equal(z, z1)
+        np.testing.assert_array_equal(info, i1)
+    # dist() through the pipe, ASCII rows
+    lo, hi = wins[1]
+    idx = np.arange(lo, hi)
+    rt, ru = idx[t[lo:hi] == 1], idx[t[lo:hi] == 0]
+    chars = (g.astype(np.int16) + 48).astype(np.uint8)
+    tk, z, info = pipe.submit(chars[rt], chars[ru], c["z"][rt], None)
+    assert pipe.wait(tk) == 0
+    z1, i1, _ = panel.window_dist(rt, ru, c["z"][rt])
+    np.testing.assert_array_equal(z, z1)
+    # an unrepresentable dosage in an E2M1 pipe is reported at wait time
+    g2 = g.copy()
+    g2[rt[0], 3] = 5
+    tk, z, info = pipe.submit(g2[rt], g2[ru], c["z"][rt], c["w"])
+    assert pipe.wait(tk) == gb.api.GB_ERR_UNSUPPORTED
+    pipe8 = gb.Pipe(gpu_ctx, c["pop_sizes"], 900, depth=1, fmt="int8")
+    tk, z, info = pipe8.submit(g2[rt], g2[ru], c["z"][rt], c["w"])
+    assert pipe8.wait(tk) == 0
+    r = oracle.run_window(np.concatenate([np.ones(len(rt), np.int32), np.zeros(len(ru), np.int32)]),
+                          np.arange(len(rt) + len(ru), dtype=np.int64), np.concatenate([c["z"][rt], np.zeros(len(ru))]),
+                          np.concatenate([g2[rt], g2[ru]]), c["pop_sizes"], c["w"], 0, 10**12)
+    assert np.abs(z - r["z"][len(rt):]).max() <= TIGHT
