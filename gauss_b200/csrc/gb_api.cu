@@ -46,7 +46,7 @@ struct gb_batch {
   double *d_st_mean_t = nullptr, *d_st_mean_u = nullptr;  // [n_pops][n_*_total] sum x / m
   int* d_skip = nullptr;
   double gneg = 0.0;  // (sum(w)-1)_+ * max(w), +inf when the analytic PD bound does not apply
-  double *d_zt = nullptr, *d_y = nullptr, *d_zu = nullptr, *d_info = nullptr;
+  double *d_zt = nullptr, *d_zu = nullptr, *d_info = nullptr;
   double *d_tt = nullptr, *d_ut = nullptr, *d_dinv = nullptr;
   double *d_coef = nullptr, *d_wgt = nullptr;
   int32_t* d_counts = nullptr;
@@ -90,7 +90,7 @@ int check_device(Ctx* ctx) {
 void free_batch_device(gb_batch* b) {
   void* ptrs[] = {b->d_rows_t, b->d_rows_u, b->d_gather, b->d_pool_t, b->d_pool_u, b->d_sd_t, b->d_sd_u, b->d_rq_t, b->d_skip,
                   b->d_st_sx_t, b->d_st_sx_u, b->d_st_mean_t, b->d_st_mean_u,
-                  b->d_zt, b->d_y, b->d_zu, b->d_info, b->d_tt, b->d_ut, b->d_dinv,
+                  b->d_zt, b->d_zu, b->d_info, b->d_tt, b->d_ut, b->d_dinv,
                   b->d_coef, b->d_wgt, b->d_counts, b->d_status, b->d_wins, b->d_tiles,
                   b->d_scratch};
   for (void* p : ptrs)
@@ -332,6 +332,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     if (b->params.check_pd && !b->ld_mode && !b->counts_mode)
       for (SolveWin sw : b->h_wins) {
         sw.off_tt += b->tt_elems;
+        sw.off_dinv += b->dinv_elems;
         sw.flags = 0;
         all.push_back(sw);
       }
@@ -364,9 +365,8 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     if ((rc = dev_alloc(ctx, &b->d_tt, (size_t)b->tt_elems * (cert ? 2 : 1)))) return rc;
     if (!b->ld_mode) {
       if ((rc = dev_alloc(ctx, &b->d_ut, (size_t)b->ut_elems))) return rc;
-      if ((rc = dev_alloc(ctx, &b->d_dinv, (size_t)b->dinv_elems))) return rc;
+      if ((rc = dev_alloc(ctx, &b->d_dinv, (size_t)b->dinv_elems * (cert ? 2 : 1)))) return rc;
       if ((rc = dev_alloc(ctx, &b->d_zt, (size_t)b->n_t_total))) return rc;
-      if ((rc = dev_alloc(ctx, &b->d_y, (size_t)b->n_t_total))) return rc;
       if ((rc = dev_alloc(ctx, &b->d_zu, (size_t)b->n_u_total))) return rc;
       if ((rc = dev_alloc(ctx, &b->d_info, (size_t)b->n_u_total))) return rc;
       if (b->n_t_total)
@@ -443,14 +443,12 @@ int run_stage(gb_batch* b, int stage) {
           return rc;
         skip = b->d_skip;
       }
-      if ((rc = launch_cholesky(ctx, b->d_wins, b->n_chol_wins, b->max_nt, b->d_tt, b->d_dinv, b->d_status, skip)))
-        return rc;
-      return launch_solve_y(ctx, b->d_wins, nreal, b->max_nt, b->d_tt, b->d_dinv, b->d_zt, b->d_y);
+      return launch_cholesky(ctx, b->d_wins, b->n_chol_wins, b->max_nt, b->d_tt, b->d_dinv, b->d_status, skip);
     }
     case 3:
       if (b->ld_mode || b->counts_mode) return GB_OK;
-      return launch_trsm_finalize(ctx, b->d_wins, (int)b->h_wins.size(), b->max_nu, b->d_tt, b->d_dinv, b->d_ut,
-                                  b->d_y, b->d_zu, b->d_info);
+      return launch_trsm_finalize(ctx, b->d_wins, (int)b->h_wins.size(), b->max_nt, b->max_nu, b->d_tt, b->d_dinv,
+                                  b->d_ut, b->d_zt, b->d_zu, b->d_info);
     default:
       ctx->err = "unknown stage";
       return GB_ERR_BAD_ARG;

@@ -157,10 +157,8 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
                     int* d_status, const int* d_skip);
 int launch_pd_bound(Ctx* ctx, const SolveWin* d_wins, int n_real, const double* d_rq_t, double lambda,
                     double gneg, double min_abs_eig, int* d_skip);
-int launch_solve_y(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, const double* d_tt,
-                   const double* d_dinv, const double* d_zt, double* d_y);
-int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nu, const double* d_tt,
-                         const double* d_dinv, double* d_ut, const double* d_y, double* d_zu, double* d_info);
+int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,
+                         const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info);
 int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double* d_src, double* d_dst,
                       double shift, const int* d_skip);
 

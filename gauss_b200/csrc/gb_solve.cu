@@ -12,14 +12,14 @@
 // Storage: B11 / L column-major n_t x ld_t (lower triangle significant); B21^T / W row-major
 // n_t x ld_u (unmeasured SNPs contiguous).  Everything is blocked by NB = 64.
 //
-// Cholesky = right-looking, two kernels per block column k, batched over all windows:
-//   chol_panel_kernel   every CTA re-factors the 64x64 diagonal block in shared memory and inverts
-//                       it; CTA ib==k publishes inv(L_kk); CTAs ib>k form L_ik = A_ik inv(L_kk)^T
+// Cholesky = right-looking, three kernels per block column k, batched over all windows:
+//   chol_diag_kernel    one CTA per window turns the 64x64 diagonal block into inv(L_kk) and publishes it
+//   chol_panel_kernel   blocks below it: L_ik = A_ik inv(L_kk)^T
 //   chol_update_kernel  trailing tiles A_ij -= L_ik L_jk^T
-// solve_y_kernel        y = L^-1 Z1, one CTA per window (block forward substitution)
 // trsm_finalize_kernel  one CTA per (window, 128 unmeasured SNPs): forward substitution by row
 //                       blocks with cp.async double-buffered operand chunks, W written in place,
-//                       column sums of squares and W^T y reduced in a fixed order.
+//                       y = L^-1 Z1 carried along as one more right-hand-side column, column sums
+//                       of squares and W^T y reduced in a fixed order.
 #include "gb_common.cuh"
 
 namespace gb {
@@ -84,49 +84,182 @@ __device__ bool spd_block_to_inv_chol(double* M) {
   return !bad_any;
 }
 
+// Warp-synchronous 32x32 version of the same transform: lane r keeps row r of A (lower) and row r
+// of Y = inv(L) in registers; column j of L and row j of Y travel through two 32-double shared
+// buffers.  No block barrier inside, ~250 clocks per pivot.  A at Ms[(o+c)*MP + o+r]; inv(L) is
+// written (lower triangle, zeros above) to Xs at the same coordinates.
+__device__ bool invchol32_warp(const double* Ms, double* Xs, int o, double* colbuf, double* rowbuf, int lane) {
+  double a[32], y[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) {
+    a[c] = (c <= lane) ? Ms[(o + c) * MP + o + lane] : 0.0;
+    y[c] = 0.0;
+  }
+  bool bad_any = false;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const double piv = __shfl_sync(0xffffffffu, a[j], j);
+    const bool bad = !(piv > 0.0);
+    bad_any |= bad;
+    const double rs = rsqrt(bad ? 1.0 : piv);
+    const double l = a[j] * rs;                 // lanes r > j: L(r, j)
+    const bool is_j = lane == j;
+#pragma unroll
+    for (int c = 0; c < j; c++) y[c] = is_j ? y[c] * rs : y[c];   // Y(j, c) *= rs
+    if (is_j) y[j] = rs;                                          // Y(j, j) = rs
+    colbuf[lane] = l;
+    if (is_j) {
+#pragma unroll
+      for (int c = 0; c <= j; c++) rowbuf[c] = y[c];
+    }
+    __syncwarp();
+    const double lm = (lane > j) ? -l : 0.0;
+#pragma unroll
+    for (int c = j + 1; c < 32; c++) a[c] = fma(lm, colbuf[c], a[c]);   // A(r, c) -= L(r, j) L(c, j)
+#pragma unroll
+    for (int c = 0; c <= j; c++) y[c] = fma(lm, rowbuf[c], y[c]);       // Y(r, c) -= L(r, j) Y(j, c)
+    __syncwarp();
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c++) Xs[(o + c) * MP + o + lane] = (c <= lane) ? y[c] : 0.0;
+  return !bad_any;
+}
+
+// Step k, part 1: one CTA per window turns the 64x64 diagonal block into inv(L_kk) and publishes it
+// (the only form of L_kk anything downstream uses: panel blocks, y and the solve).  This is the
+// sequential critical path of the factorisation, so it runs exactly once per window and step and
+// is organised for latency: two warp-synchronous 32x32 inverse-Cholesky passes joined by three
+// small products, with A = [A11 .; A21 A22]:
+//   X11 = inv(chol(A11));  L21 = A21 X11^T;  S = A22 - L21 L21^T;  X22 = inv(chol(S));
+//   X21 = -X22 L21 X11;    inv(L_kk) = [X11 0; X21 X22]
 __global__ void __launch_bounds__(256)
-chol_panel_kernel(const SolveWin* __restrict__ wins, double* tt, double* dinv, int* status,
+chol_diag_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt, double* dinv, int* status,
+                 const int* __restrict__ skip, int k) {
+  if (skip && skip[blockIdx.x]) return;  // certificate copy whose analytic bound already holds
+  const SolveWin w = wins[blockIdx.x];
+  const int n = w.n_t;
+  if (k >= win_nb(n)) return;
+  const double* A = tt + w.off_tt;
+  const int ld = w.ld_t;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int H = 32;
+  extern __shared__ __align__(16) double sm[];
+  double* Ms = sm;                      // [64][MP] A_kk (lower), later S in its (1,1) quadrant
+  double* Xs = Ms + NB * MP;            // [64][MP] inv(L_kk)
+  double* Ls = Xs + NB * MP;            // [32][34] L21, then T = L21 X11: [j*(H+2) + r]
+  double* colbuf = Ls + H * (H + 2);    // [32]
+  double* rowbuf = colbuf + H;          // [32]
+  __shared__ int ok_s;
+  const int k0 = k * NB;
+  // rows/cols past n are padded with the identity
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int c = idx >> 6, r = idx & 63;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (k0 + r < n && k0 + c < n && r >= c) v = A[(long long)(k0 + c) * ld + k0 + r];
+    Ms[c * MP + r] = v;
+    Xs[c * MP + r] = 0.0;
+  }
+  if (tid == 0) ok_s = 1;
+  __syncthreads();
+  if (warp == 0 && !invchol32_warp(Ms, Xs, 0, colbuf, rowbuf, lane) && lane == 0) ok_s = 0;
+  __syncthreads();
+  // L21(r, c) = sum_{j<=c} A21(r, j) X11(c, j): thread -> (r = tid & 31, c = (tid >> 5) + 8 i)
+  {
+    const int r = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = (tid >> 5) + 8 * i;
+      double v = 0.0;
+      for (int j = 0; j <= c; j++) v = fma(Ms[j * MP + H + r], Xs[j * MP + c], v);
+      Ls[c * (H + 2) + r] = v;
+    }
+  }
+  __syncthreads();
+  // S(r, c) = A22(r, c) - sum_j L21(r, j) L21(c, j), lower triangle
+  {
+    const int r = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = (tid >> 5) + 8 * i;
+      if (c <= r) {
+        double v = Ms[(H + c) * MP + H + r];
+#pragma unroll 8
+        for (int j = 0; j < H; j++) v = fma(-Ls[j * (H + 2) + r], Ls[j * (H + 2) + c], v);
+        Ms[(H + c) * MP + H + r] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0 && !invchol32_warp(Ms, Xs, H, colbuf, rowbuf, lane) && lane == 0) ok_s = 0;
+  __syncthreads();
+  // T(r, c) = sum_{j>=c} L21(r, j) X11(j, c)   (kept in registers across the barrier, then stored over L21)
+  double tv[4];
+  {
+    const int r = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = (tid >> 5) + 8 * i;
+      double v = 0.0;
+      for (int j = c; j < H; j++) v = fma(Ls[j * (H + 2) + r], Xs[c * MP + j], v);
+      tv[i] = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int r = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 4; i++) Ls[((tid >> 5) + 8 * i) * (H + 2) + r] = tv[i];
+  }
+  __syncthreads();
+  // X21(r, c) = -sum_{kk<=r} X22(r, kk) T(kk, c)
+  {
+    const int r = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = (tid >> 5) + 8 * i;
+      double v = 0.0;
+      for (int kk = 0; kk <= r; kk++) v = fma(Xs[(H + kk) * MP + H + r], Ls[c * (H + 2) + kk], v);
+      Xs[c * MP + H + r] = -v;
+    }
+  }
+  __syncthreads();
+  if (!ok_s && tid == 0) atomicOr(&status[blockIdx.x], STATUS_BREAKDOWN);
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int c = idx >> 6, r = idx & 63;
+    dinv[w.off_dinv + (long long)k * NB * NB + c * NB + r] = Xs[c * MP + r];  // zero above the diagonal
+  }
+}
+
+// Step k, part 2: panel blocks below the diagonal, L_ik = A_ik inv(L_kk)^T, one CTA per block.
+__global__ void __launch_bounds__(256)
+chol_panel_kernel(const SolveWin* __restrict__ wins, double* tt, const double* __restrict__ dinv,
                   const int* __restrict__ skip, int k) {
-  if (skip && skip[blockIdx.y]) return;  // certificate copy whose analytic bound already holds
+  if (skip && skip[blockIdx.y]) return;
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t;
   const int nb = win_nb(n);
-  const int ib = k + blockIdx.x;
-  if (k >= nb || ib >= nb) return;
+  const int ib = k + 1 + blockIdx.x;
+  if (ib >= nb) return;
   double* A = tt + w.off_tt;
   const int ld = w.ld_t;
   const int tid = threadIdx.x;
 
   extern __shared__ __align__(16) double sm[];
-  double* X = sm;                 // [64][MP] A_kk -> inv(L_kk)
+  double* X = sm;                 // [64][MP] inv(L_kk), X[j*MP + c] = inv(L_kk)(c, j)
   double* T = X + NB * MP;        // [64][MP] A_ik tile, T[j*MP + r] = A(ib*64+r, k*64+j)
 
   const int k0 = k * NB;
   const int i0 = ib * NB;
-  // diagonal block; rows/cols past n are padded with the identity
+  const double* D = dinv + w.off_dinv + (long long)k * NB * NB;
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int c = idx >> 6, r = idx & 63;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (k0 + r < n && k0 + c < n && r >= c) v = A[(long long)(k0 + c) * ld + k0 + r];
-    X[c * MP + r] = v;
-    if (ib != k) T[c * MP + r] = (i0 + r < n && k0 + c < n) ? A[(long long)(k0 + c) * ld + i0 + r] : 0.0;
+    X[c * MP + r] = D[c * NB + r];
+    T[c * MP + r] = (i0 + r < n && k0 + c < n) ? A[(long long)(k0 + c) * ld + i0 + r] : 0.0;
   }
-  const bool ok = spd_block_to_inv_chol(X);
+  __syncthreads();
 
-  if (ib == k) {
-    if (!ok && tid == 0) atomicOr(&status[blockIdx.y], STATUS_BREAKDOWN);
-    // L_kk is never needed again (panel blocks, y and the solve all use inv(L_kk)); A_kk is left
-    // untouched, the sibling CTAs are still reading it.
-    if (w.flags & 1)
-      for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int c = idx >> 6, r = idx & 63;
-        dinv[w.off_dinv + (long long)k * NB * NB + c * NB + r] = X[c * MP + r];
-      }
-    return;
-  }
-
-  // off-diagonal panel block: L_ik = A_ik inv(L_kk)^T, i.e. L(r, c) = sum_{j<=c} A(r, j) X(c, j);
-  // 4x4 register tile per thread, rows {2a,2a+1,32+2a,32+2a+1}, columns 4b..4b+3
+  // L(r, c) = sum_{j<=c} A(r, j) X(c, j); 4x4 register tile per thread,
+  // rows {2a,2a+1,32+2a,32+2a+1}, columns 4b..4b+3
   {
     const int a2 = (tid & 15) * 2, cb = (tid >> 4) * 4;
     double acc[4][4];
@@ -266,52 +399,6 @@ pd_bound_kernel(const SolveWin* __restrict__ wins, int nreal, const double* __re
   }
 }
 
-// y = L^-1 Z1 by block forward substitution, one CTA per window:
-//   y_k = inv(L_kk) (z_k - sum_{j<k} L_kj y_j)
-__global__ void __launch_bounds__(256)
-solve_y_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt, const double* __restrict__ dinv,
-               const double* __restrict__ zt, double* y) {
-  const SolveWin w = wins[blockIdx.x];
-  const int n = w.n_t, ld = w.ld_t, nb = win_nb(n);
-  const double* L = tt + w.off_tt;
-  const int tid = threadIdx.x;
-  const int r = tid & 63, q = tid >> 6;
-  extern __shared__ double sm[];
-  double* ys = sm;                 // [nb*64] solution so far
-  double* part = ys + nb * NB;     // [4][64]
-  double* rhs = part + 4 * NB;     // [64]
-  for (int k = 0; k < nb; k++) {
-    const int k0 = k * NB;
-    double acc = 0.0;
-    if (k0 + r < n) {
-      double a4[4] = {0.0, 0.0, 0.0, 0.0};
-      int c = q;
-      for (; c + 12 < k0; c += 16) {  // four independent loads in flight per thread
-#pragma unroll
-        for (int u = 0; u < 4; u++) a4[u] = fma(L[(long long)(c + 4 * u) * ld + k0 + r], ys[c + 4 * u], a4[u]);
-      }
-      for (; c < k0; c += 4) a4[0] = fma(L[(long long)c * ld + k0 + r], ys[c], a4[0]);
-      acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-    }
-    part[q * NB + r] = acc;
-    __syncthreads();
-    if (tid < NB) {
-      double v = 0.0;
-      if (k0 + r < n) v = zt[w.off_t + k0 + r] - (part[r] + part[NB + r] + part[2 * NB + r] + part[3 * NB + r]);
-      rhs[r] = v;
-    }
-    __syncthreads();
-    if (tid < NB) {
-      const double* X = dinv + w.off_dinv + (long long)k * NB * NB;  // X[c*64 + r] = inv(L_kk)(r, c)
-      double v = 0.0;
-      for (int j = 0; j <= r; j++) v = fma(X[j * NB + r], rhs[j], v);
-      ys[k0 + r] = v;
-      if (k0 + r < n) y[w.off_t + k0 + r] = v;
-    }
-    __syncthreads();
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Blocked forward substitution W = L^-1 B21^T for 128 unmeasured SNPs, fused with the reductions.
 //
@@ -335,7 +422,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __global__ void __launch_bounds__(256, 2)
 trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt,
-                     const double* __restrict__ dinv, double* ut, const double* __restrict__ y,
+                     const double* __restrict__ dinv, double* ut, const double* __restrict__ zt,
                      double* zu, double* info) {
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t, nu = w.n_u;
@@ -356,6 +443,9 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   double* Ds = LsBuf;                       // [64][64] inv(L_ii), aliases both L chunks
   double* Ts = WsBuf;                       // [64][128] accumulator tile, aliases both W chunks
   double* red = WsBuf;                      // [8][128] final reductions
+  double* ys = sm + 2 * (KC * NB + KC * UB); // [nb*64] y = L^-1 Z1 solved so far (every CTA carries this extra
+  double* rys = ys + nb * NB;                // [64]     right-hand side column itself: ~1/128 more work, no
+                                             //          separate latency-bound kernel and no y round trip)
 
   double p_info[4] = {0.0, 0.0, 0.0, 0.0}, p_z[4] = {0.0, 0.0, 0.0, 0.0};
   const int ccol[2] = {2 * lane, 64 + 2 * lane};   // first column of each 2-wide strip of this thread
@@ -397,6 +487,7 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
       }
       cp_async_commit();
     };
+    double acc_y = 0.0;  // threads 0..63: sum_k L(i0 + tid, k) y_k
     __syncthreads();  // previous row block finished with the aliased buffers (Ts / Ds)
     if (nchunk > 0) issue(0, 0);
     for (int ch = 0; ch < nchunk; ch++) {
@@ -430,6 +521,11 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 #pragma unroll
           for (int b = 0; b < 4; b++) acc[a][b] = fma(-lv[a], wv[b], acc[a][b]);
       }
+      if (tid < NB) {
+        const double* yk = ys + ch * KC;
+#pragma unroll 8
+        for (int kk = 0; kk < KC; kk++) acc_y = fma(ls[kk * NB + tid], yk[kk], acc_y);
+      }
       __syncthreads();  // buffer `buf` may be refilled by the next issue
     }
     // W_i = inv(L_ii) * acc
@@ -441,7 +537,13 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
     for (int idx = tid; idx < NB * NB / 2; idx += 256)  // Ds[kk*64 + r] = inv(L_ii)(r, kk), zero above diag
       reinterpret_cast<double2*>(Ds)[idx] =
           reinterpret_cast<const double2*>(dinv + w.off_dinv + (long long)ib * NB * NB)[idx];
+    if (tid < NB) rys[tid] = (i0 + tid < n) ? zt[w.off_t + i0 + tid] - acc_y : 0.0;
     __syncthreads();
+    if (tid < NB) {  // y_i = inv(L_ii) (z_i - sum_k L_ik y_k)
+      double v = 0.0;
+      for (int j = 0; j <= tid; j++) v = fma(Ds[j * NB + tid], rys[j], v);
+      ys[i0 + tid] = v;
+    }
     double out[8][4];
 #pragma unroll
     for (int a = 0; a < 8; a++)
@@ -468,11 +570,12 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 #pragma unroll
         for (int b = 0; b < 4; b++) out[a][b] = fma(lv[a], tv[b], out[a][b]);
     }
+    __syncthreads();  // ys[i0 .. i0+63] is complete
 #pragma unroll
     for (int a = 0; a < 8; a++) {
       const int r = i0 + tr + a;
       if (r >= n) continue;
-      const double yr = y[w.off_t + r];
+      const double yr = ys[r];
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         if (ccol[s] < cvalid)
@@ -522,52 +625,41 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
   const int nb_max = (max_nt + NB - 1) / NB;
   const size_t smem_panel = sizeof(double) * 2 * NB * MP;
   const size_t smem_update = sizeof(double) * 2 * NB * NB;
-  static bool attr_set = false;
+  const size_t smem_diag = sizeof(double) * (2 * NB * MP + 32 * 34 + 64);
+  static bool attr_set_dev[64] = {};
+  bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag));
     GB_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel));
     GB_CUDA(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update));
     attr_set = true;
   }
   for (int k = 0; k < nb_max; k++) {
-    chol_panel_kernel<<<dim3(nb_max - k, n_wins), 256, smem_panel, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status,
-                                                                                 d_skip, k);
+    chol_diag_kernel<<<n_wins, 256, smem_diag, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status, d_skip, k);
     ctx->launches++;
     const int tb = nb_max - k - 1;
     if (tb > 0) {
+      chol_panel_kernel<<<dim3(tb, n_wins), 256, smem_panel, ctx->stream>>>(d_wins, d_tt, d_dinv, d_skip, k);
       chol_update_kernel<<<dim3(tb * (tb + 1) / 2, n_wins), 256, smem_update, ctx->stream>>>(d_wins, d_tt, d_skip, k);
-      ctx->launches++;
+      ctx->launches += 2;
     }
   }
   GB_CUDA(cudaGetLastError());
   return GB_OK;
 }
 
-int launch_solve_y(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, const double* d_tt,
-                   const double* d_dinv, const double* d_zt, double* d_y) {
-  if (n_wins == 0) return GB_OK;
+int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,
+                         const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info) {
+  if (n_wins == 0 || max_nu == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
-  const size_t smem = sizeof(double) * (size_t)(nb_max * NB + 5 * NB);
-  if (smem > 200 * 1024) {
-    ctx->err = "window has too many measured SNPs for solve_y_kernel";
+  const size_t smem = TR_SMEM_BYTES + sizeof(double) * (size_t)(nb_max * NB + NB);
+  if (smem > 227 * 1024) {
+    ctx->err = "window has too many measured SNPs for trsm_finalize_kernel";
     return GB_ERR_UNSUPPORTED;
   }
-  GB_CUDA(cudaFuncSetAttribute(solve_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  solve_y_kernel<<<n_wins, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_zt, d_y);
-  GB_CUDA(cudaGetLastError());
-  ctx->launches++;
-  return GB_OK;
-}
-
-int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nu, const double* d_tt,
-                         const double* d_dinv, double* d_ut, const double* d_y, double* d_zu, double* d_info) {
-  if (n_wins == 0 || max_nu == 0) return GB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM_BYTES));
-    attr_set = true;
-  }
-  trsm_finalize_kernel<<<dim3((max_nu + UB - 1) / UB, n_wins), 256, TR_SMEM_BYTES, ctx->stream>>>(
-      d_wins, d_tt, d_dinv, d_ut, d_y, d_zu, d_info);
+  GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  trsm_finalize_kernel<<<dim3((max_nu + UB - 1) / UB, n_wins), 256, smem, ctx->stream>>>(
+      d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;
