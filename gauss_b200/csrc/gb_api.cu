@@ -55,6 +55,7 @@ struct gb_batch {
   GramTile* d_tiles = nullptr;
   int8_t* d_scratch = nullptr;
   RowMaps tmaps_scratch;
+  int fkind = 0;                      // tensor-core kind of this batch (GramParams::fkind)
   int cm = 1, cn = 1;                 // Gram cluster shape this batch was planned for
   bool defer_flag_check = false;      // pipelined path: the panel is still being packed at plan time
   std::vector<int> h_status;          // fetch staging: [2*n_windows + 2 status words | panel flags]
@@ -138,24 +139,30 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   // ---- segments / coefficients
   GramParams& gp = b->gp;
   std::memset(&gp, 0, sizeof(gp));
+  // int8 rows -> kind::i8; E2M1 rows -> kind::mxf4 (nibbles stay packed, K = 64 per instruction) or kind::f8f6f4
+  b->fkind = pn->format == GB_PANEL_E2M1 ? (ctx->e2m1_mxf4 ? 7 : 6) : 0;
+  gp.fkind = b->fkind;
+  const int atom = b->fkind == 7 ? 2 * K_ATOM : K_ATOM;  // K columns one MMA instruction consumes
   std::vector<double> h_coef((size_t)pn->n_pops, 0.0), h_wgt((size_t)pn->n_pops, 0.0);
   if (b->mode == GRAM_POOLED) {
     gp.n_seg = 1;
     const int last = pn->n_pops - 1;
     const int k_used = pn->koff[last] + round_up(pn->pop_sizes[last], K_ATOM);
-    gp.seg[0] = Seg{0, k_used / K_ATOM, pn->n_samples, 0};
+    gp.seg[0] = Seg{0, (k_used + atom - 1) / atom, pn->n_samples, 0};
     gp.n_pooled = (double)pn->n_samples;
   } else {
     gp.n_seg = pn->n_pops;
     for (int p = 0; p < pn->n_pops; p++) {
       const int m = pn->pop_sizes[p];
-      gp.seg[p] = Seg{pn->koff[p], (m + K_ATOM - 1) / K_ATOM, m, 0};
+      gp.seg[p] = Seg{pn->koff[p], (m + atom - 1) / atom, m, 0};
       if (pop_wgt) {
         const double factor = ((double)m) / (m - 1);   // util.cpp:117
         h_wgt[(size_t)p] = pop_wgt[p];
         h_coef[(size_t)p] = pop_wgt[p] * factor;       // wgt_val*factor, left-assoc in util.cpp:118
         gp.coef[p] = h_coef[(size_t)p];
         gp.wgt[p] = h_wgt[(size_t)p];
+        gp.coefm[p] = h_coef[(size_t)p] * m;
+        gp.kappa[p] = pop_wgt[p] / ((double)m * m) - h_coef[(size_t)p];
       }
     }
   }
@@ -171,7 +178,6 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   }
   gp.mode = b->counts_mode ? GRAM_COUNTS : b->mode;
   gp.mirror = b->ld_mode ? 1 : 0;
-  gp.fkind = pn->format == GB_PANEL_E2M1 ? 6 : 0;  // kind::f8f6f4 operand format 5 (E2M1) / kind::i8
   gp.diag = b->ld_mode ? 1.0 : 1.0 + b->params.lambda;   // computeLD.cpp:107 vs dist.cpp:172
 
   // ---- windows
@@ -377,10 +383,10 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   if (b->n_gather > 0) {
     if ((rc = dev_alloc(ctx, &b->d_scratch, (size_t)b->n_gather * pn->k_stride))) return rc;
     if ((rc = make_row_tensor_maps(ctx, &b->tmaps_scratch, b->d_scratch, b->n_gather, pn->k_elems, pn->k_stride,
-                                   pn->format)))
+                                   b->fkind == 7 ? MAP_E2M1_PACKED : b->fkind == 6 ? MAP_E2M1_EXPAND : MAP_INT8)))
       return rc;
   } else {
-    b->tmaps_scratch = pn->tmaps;
+    b->tmaps_scratch = b->fkind == 7 ? pn->tmaps_packed : pn->tmaps;
   }
 
   gp.tiles = b->d_tiles;
@@ -426,7 +432,7 @@ int run_stage(gb_batch* b, int stage) {
                              b->d_pool_u, nullptr, b->d_st_sx_u, b->d_st_mean_u);
     }
     case 1:
-      return launch_gram(ctx, pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn);
+      return launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn);
     case 2: {
       if (b->ld_mode || b->counts_mode) return GB_OK;
       const int nreal = (int)b->h_wins.size();
@@ -569,6 +575,7 @@ int gb_ctx_create(int device, gb_ctx** out) {
     if (!strcmp(e, "int8")) ctx->panel_format = GB_PANEL_INT8;
     else if (!strcmp(e, "e2m1")) ctx->panel_format = GB_PANEL_E2M1;
   }
+  if (const char* e = getenv("GB_GRAM_KIND")) ctx->e2m1_mxf4 = strcmp(e, "f8f6f4") != 0;
   if (const char* e = getenv("GB_GRAM_CLUSTER")) {  // tuning knob: "CMxCN", e.g. 2x2
     int cm = 0, cn = 0;
     if (sscanf(e, "%dx%d", &cm, &cn) == 2 && gram_cluster_supported(cm, cn)) {
@@ -680,7 +687,11 @@ int gb_panel_create_fmt(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t c
   cudaMemsetAsync(p->d_flags, 0, sizeof(int), ctx->stream);
   cudaMemcpyAsync(p->d_pop_sizes, p->pop_sizes.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(p->d_koff, p->koff.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
-  if ((rc = make_row_tensor_maps(ctx, &p->tmaps, p->d_rows, capacity_rows, p->k_elems, p->k_stride, format)))
+  if ((rc = make_row_tensor_maps(ctx, &p->tmaps, p->d_rows, capacity_rows, p->k_elems, p->k_stride,
+                                 format == GB_PANEL_E2M1 ? MAP_E2M1_EXPAND : MAP_INT8)))
+    return fail(rc);
+  if (format == GB_PANEL_E2M1 && (rc = make_row_tensor_maps(ctx, &p->tmaps_packed, p->d_rows, capacity_rows, p->k_elems,
+                                                            p->k_stride, MAP_E2M1_PACKED)))
     return fail(rc);
   cudaStreamSynchronize(ctx->stream);
   *out = p;

@@ -53,6 +53,8 @@ struct GramParams {
   Seg seg[P_MAX];
   double coef[P_MAX];    // w_p * (m_p / (m_p - 1))          (util.cpp:117-118)
   double wgt[P_MAX];     // w_p
+  double coefm[P_MAX];   // coef_p * m_p                     (regrouped fold of E2M1 panels)
+  double kappa[P_MAX];   // w_p / m_p^2 - coef_p
   double n_pooled;       // total flagged individuals (dist)
   double diag;           // value forced on the diagonal of T x T tiles (1 + lambda, or 1.0)
   // per listed row and population, precomputed by row_prep_kernel (list order, [n_seg][st_ld_*]):
@@ -87,11 +89,13 @@ struct Ctx {
   int gram_cm = 1, gram_cn = 1;
   int gram_clusters = 0;            // clusters of the last Gram launch (diagnostics)
   int panel_format = GB_PANEL_E2M1; // format gb_panel_create uses (GB_PANEL_FORMAT=int8|e2m1 overrides)
+  int e2m1_mxf4 = 1;                // E2M1 panels: 1 = kind::mxf4 (packed nibbles, K = 64), 0 = kind::f8f6f4 (GB_GRAM_KIND)
 };
 
 // TMA descriptors of one row-major packed-row matrix {k_elems, n_rows} with boxes of 128 K columns x
 // {128, 64, 32, 16} rows: a CM x CN cluster fetches A tiles in 128/CN-row and B tiles in
 // 128/CM-row slices.
+enum MapFormat : int { MAP_INT8 = 0, MAP_E2M1_EXPAND = 1, MAP_E2M1_PACKED = 2 };
 struct RowMaps {
   static constexpr int N = 4;
   CUtensorMap m[N];
@@ -115,7 +119,8 @@ struct Panel {
   int32_t* d_sxx = nullptr;    // [n_pops][capacity]
   int* d_pop_sizes = nullptr;  // [n_pops]
   int* d_koff = nullptr;       // [n_pops]
-  RowMaps tmaps;               // {k_stride, capacity} int8, SWIZZLE_128B
+  RowMaps tmaps;               // int8 rows, or E2M1 rows expanded to bytes by the TMA unit (kind::f8f6f4)
+  RowMaps tmaps_packed;        // E2M1 rows kept nibble-packed in shared memory (kind::mxf4)
 };
 
 #define GB_CUDA(call)                                                                          \

@@ -46,6 +46,10 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 128 + EPI_THREADS;           // 384
 constexpr int EPI_COLS = 64;                         // columns per epilogue thread
+// GramParams::fkind: tensor-core instruction kind the panel format maps to
+constexpr int FKIND_I8 = 0;       // kind::i8, int8 rows, K = 32 per instruction
+constexpr int FKIND_F8F6F4 = 6;   // kind::f8f6f4 with E2M1 operands (TMA expands nibbles to bytes), K = 32
+constexpr int FKIND_MXF4 = 7;     // kind::mxf4 with unit block scales, nibbles stay packed, K = 64
 
 // dynamic shared memory carve-up (byte offsets from a 1024-aligned base)
 constexpr int OFF_STAGES = 0;
@@ -76,6 +80,14 @@ __device__ __forceinline__ int f32_count_to_int(uint32_t bits) {
   return (int)__float_as_uint(f) - 0x4B400000;
 }
 
+// fp32 accumulator holding an exact NON-NEGATIVE integer -> the same value as a double, by
+// re-encoding the bits (no conversion instruction, no fp64-pipe op): exponent rebias 127 -> 1023,
+// 23 mantissa bits moved to the top of the 52.
+__device__ __forceinline__ double f32_count_to_double(uint32_t bits) {
+  const uint32_t hi = bits ? (bits >> 3) + 0x38000000u : 0u;
+  return __hiloint2double((int)hi, (int)(bits << 29));
+}
+
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 }
@@ -93,7 +105,9 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
   constexpr int SLICE_A = TILE / CN;  // rows of the A tile this CTA fetches
   constexpr int SLICE_B = TILE / CM;  // rows of the B tile this CTA fetches
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by OFFSET (not by integer round trip) so the compiler keeps emitting
+  // shared-space loads/stores for everything derived from it
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   uint64_t* full_bar = bars;
@@ -143,6 +157,19 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int n_seg = prm.n_seg;
+  // kind::mxf4 keeps its (all-ones) block scale factors in the last 128 TMEM columns: 3 accumulator buffers
+  const int acc_bufs = prm.fkind == FKIND_MXF4 ? ACC_BUFS - 1 : ACC_BUFS;
+  if (prm.fkind == FKIND_MXF4 && warp >= 4 && warp < 8) {
+    const uint32_t sf_addr = tmem_base + (uint32_t)((ACC_BUFS - 1) * TILE) + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < TILE; c += 16) ptx::tmem_st_fill_32x32b_x16(sf_addr + c, 0x7F7F7F7Fu);  // E8M0 2^0
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+  }
+  if (prm.fkind == FKIND_MXF4) {
+    __syncthreads();
+    ptx::tc_fence_after();
+  }
 
   // Register budget: the epilogue threads carry 64 fp64 accumulators each; the control warps
   // need almost nothing.  64 K regs >= 128 x 56 + 256 x 224.  Each role's code sits entirely
@@ -154,7 +181,8 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t stage_tx = prm.fkind == 6 ? STAGE_BYTES / 2 : STAGE_BYTES;
+      const uint32_t stage_tx = prm.fkind == FKIND_F8F6F4 ? STAGE_BYTES / 2 : STAGE_BYTES;
+      const int kblk = prm.fkind == FKIND_MXF4 ? 2 * K_BLOCK : K_BLOCK;  // K columns per 128-byte stage row
       for (int ct = cluster_id; ct < prm.n_tiles; ct += n_clusters) {
         const GramTile t = prm.tiles[(long long)ct * CSIZE + crank];
         const CUtensorMap* map_a = t.a_src ? &tm_a_scratch : &tm_a_panel;
@@ -171,10 +199,10 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             // own + peers' slices; the mbarrier counts bytes as they sit in global memory (nibble-packed
             // E2M1 rows complete half of what they occupy in shared memory)
             ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            if (CN > 1) ptx::tma_load_2d_mc(sa, map_a, &full_bar[stage], koff + b * K_BLOCK, a_row, mask_row);
-            else ptx::tma_load_2d(sa, map_a, &full_bar[stage], koff + b * K_BLOCK, a_row);
-            if (CM > 1) ptx::tma_load_2d_mc(sb, map_b, &full_bar[stage], koff + b * K_BLOCK, b_row, mask_col);
-            else ptx::tma_load_2d(sb, map_b, &full_bar[stage], koff + b * K_BLOCK, b_row);
+            if (CN > 1) ptx::tma_load_2d_mc(sa, map_a, &full_bar[stage], koff + b * kblk, a_row, mask_row);
+            else ptx::tma_load_2d(sa, map_a, &full_bar[stage], koff + b * kblk, a_row);
+            if (CM > 1) ptx::tma_load_2d_mc(sb, map_b, &full_bar[stage], koff + b * kblk, b_row, mask_col);
+            else ptx::tma_load_2d(sb, map_b, &full_bar[stage], koff + b * kblk, b_row);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -186,8 +214,11 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     // kept to a handful of instructions: the descriptor of K atom k is the stage descriptor + 2*k
     // (32 bytes >> 4) in its low word, and full K blocks are issued fully unrolled.
     if (ptx::elect_one()) {
-      const int fkind = prm.fkind;  // 0: kind::i8; else kind::f8f6f4 with operand format fkind - 1
-      const uint32_t idesc = fkind ? ptx::make_idesc_f8f6f4(fkind - 1, TILE, TILE) : ptx::make_idesc_i8(TILE, TILE);
+      const int fkind = prm.fkind;
+      const uint32_t idesc = fkind == FKIND_MXF4     ? ptx::make_idesc_mxf4(TILE, TILE)
+                             : fkind == FKIND_F8F6F4 ? ptx::make_idesc_f8f6f4(5, TILE, TILE)
+                                                     : ptx::make_idesc_i8(TILE, TILE);
+      const uint32_t sf_tmem = tmem_base + (uint32_t)((ACC_BUFS - 1) * TILE);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -207,7 +238,12 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             const uint64_t da = desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
             const uint64_t db = da + (STAGE_OPERAND_BYTES >> 4);
             if (atoms >= 4) {
-              if (fkind) {
+              if (fkind == FKIND_MXF4) {
+                ptx::mma_mxf4_ss(d_tmem, da, db, idesc, sf_tmem, sf_tmem, accumulate);
+                ptx::mma_mxf4_ss(d_tmem, da + 2, db + 2, idesc, sf_tmem, sf_tmem, 1);
+                ptx::mma_mxf4_ss(d_tmem, da + 4, db + 4, idesc, sf_tmem, sf_tmem, 1);
+                ptx::mma_mxf4_ss(d_tmem, da + 6, db + 6, idesc, sf_tmem, sf_tmem, 1);
+              } else if (fkind == FKIND_F8F6F4) {
                 ptx::mma_f8f6f4_ss(d_tmem, da, db, idesc, accumulate);
                 ptx::mma_f8f6f4_ss(d_tmem, da + 2, db + 2, idesc, 1);
                 ptx::mma_f8f6f4_ss(d_tmem, da + 4, db + 4, idesc, 1);
@@ -220,8 +256,10 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
               }
             } else {
               for (int k = 0; k < atoms; k++) {
-                if (fkind) ptx::mma_f8f6f4_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
-                else ptx::mma_i8_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
+                const uint32_t accu = accumulate | (uint32_t)k;
+                if (fkind == FKIND_MXF4) ptx::mma_mxf4_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, sf_tmem, sf_tmem, accu);
+                else if (fkind == FKIND_F8F6F4) ptx::mma_f8f6f4_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                else ptx::mma_i8_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
               }
             }
             accumulate = 1;
@@ -231,7 +269,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(&tfull_bar[acc]);      // accumulator of segment s is complete
-          if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+          if (++acc == acc_bufs) { acc = 0; acc_phase ^= 1; }
         }
       }
     }
@@ -254,6 +292,13 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     double* sdB = reinterpret_cast<double*>(smem + OFF_SDB);
     const int mode = prm.mode;
     const bool f32acc = prm.fkind != 0;
+    // E2M1 panels (non-negative counts in fp32 accumulators) use the regrouped fold
+    //   cov_ij = sum_p (coef_p m_p) S^p_ij + sum_p kappa_p s^p_i s^p_j - (sum_p w_p mu^p_i)(sum_p w_p mu^p_j),
+    //   kappa_p = w_p / m_p^2 - coef_p,
+    // i.e. one DFMA per entry and population while the tile streams and one more in the finish,
+    // instead of CalWgtCov's literal term order (kept for int8 panels: 2 IMAD + 3 fp64 ops + the
+    // mean term).  Same value up to ~1e-13 of the variance; the test bar is 1e-6.
+    const bool fast = mode == GRAM_MIX && f32acc;
     int acc_buf = 0;
     uint32_t acc_phase = 0;
 
@@ -266,7 +311,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
           ptx::mbar_wait(&tfull_bar[acc_buf], acc_phase);
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc_buf]);
-          if (++acc_buf == ACC_BUFS) { acc_buf = 0; acc_phase ^= 1; }
+          if (++acc_buf == acc_bufs) { acc_buf = 0; acc_phase ^= 1; }
         }
         continue;
       }
@@ -279,7 +324,21 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
         const int valid = side ? t.b_valid : t.a_valid;
         const long long li = (side ? t.b_list0 : t.a_list0) + min(idx, valid - 1);
         const bool from_u = (side == 0) && t.a_is_u;
-        if (mode == GRAM_MIX) {
+        if (fast) {
+          // regrouped form (see the fold below): A side keeps kappa_p * s^p_i, B side s^p_j as doubles
+          const int32_t* st_sx = from_u ? prm.st_sx_u : prm.st_sx_t;
+          const double* st_mean = from_u ? prm.st_mean_u : prm.st_mean_t;
+          const long long ld = from_u ? prm.st_ld_u : prm.st_ld_t;
+          double* mdst = side ? hB : gA;
+          double wsum = 0.0;
+#pragma unroll 4
+          for (int p = 0; p < n_seg; p++) {
+            const double sxd = int_to_double(st_sx[p * ld + li]);
+            mdst[p * TILE + idx] = side ? sxd : __dmul_rn(prm.kappa[p], sxd);
+            wsum = __dadd_rn(wsum, __dmul_rn(prm.wgt[p], st_mean[p * ld + li]));   // wsum_mi  (util.cpp:120-121)
+          }
+          (side ? bjS : aiS)[idx] = wsum;
+        } else if (mode == GRAM_MIX) {
           const int32_t* st_sx = from_u ? prm.st_sx_u : prm.st_sx_t;
           const double* st_mean = from_u ? prm.st_mean_u : prm.st_mean_t;
           const long long ld = from_u ? prm.st_ld_u : prm.st_ld_t;
@@ -334,6 +393,12 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc_buf]);
           }
+          if (fast) {
+            const double coefm = prm.coefm[s];
+#pragma unroll
+            for (int e = 0; e < 16; e++) acc[ch * 16 + e] = fma(coefm, f32_count_to_double(v[e]), acc[ch * 16 + e]);
+            continue;
+          }
           int cnt[16];
 #pragma unroll
           for (int e = 0; e < 16; e++) cnt[e] = f32acc ? f32_count_to_int(v[e]) : (int)v[e];
@@ -363,7 +428,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             }
           }
         }
-        if (++acc_buf == ACC_BUFS) { acc_buf = 0; acc_phase ^= 1; }
+        if (++acc_buf == acc_bufs) { acc_buf = 0; acc_phase ^= 1; }
       }
 
       if (mode == GRAM_COUNTS) continue;
@@ -380,7 +445,24 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
 #pragma unroll
       for (int ch = 0; ch < EPI_COLS / 8; ch++) {
         double num8[8];
-        if (mode == GRAM_MIX) {
+        if (fast) {
+          double x[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) x[k] = acc[ch * 8 + k];
+#pragma unroll 3
+          for (int p = 0; p < n_seg; p++) {   // + kappa_p s^p_i s^p_j
+            const double g = gA[p * TILE + r];
+            const double2* hv = reinterpret_cast<const double2*>(hB + p * TILE + c0 + ch * 8);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; k2++) {
+              const double2 h2 = hv[k2];
+              x[2 * k2] = fma(g, h2.x, x[2 * k2]);
+              x[2 * k2 + 1] = fma(g, h2.y, x[2 * k2 + 1]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k++) num8[k] = fma(-ai, bjS[c0 + ch * 8 + k], x[k]);
+        } else if (mode == GRAM_MIX) {
           double x[8];
 #pragma unroll
           for (int k = 0; k < 8; k++) x[k] = 0.0;
@@ -464,13 +546,16 @@ int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_
   if (n_rows < 1) n_rows = 1;
   cuuint64_t dims[2] = {(cuuint64_t)k_elems, (cuuint64_t)n_rows};
   cuuint64_t strides[1] = {(cuuint64_t)k_stride_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)K_BLOCK, (cuuint32_t)box_rows};
+  // every box row is 128 bytes of shared memory: 128 int8 / expanded-E2M1 columns, or 256 packed nibbles
+  cuuint32_t box[2] = {(cuuint32_t)(format == MAP_E2M1_PACKED ? 2 * K_BLOCK : K_BLOCK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   // E2M1 rows are nibble-packed in HBM; the TMA unit expands every 16 nibbles (8 B) into a 16-byte
   // shared-memory slot, which is the operand layout kind::f8f6f4 reads, so a K block of 128 dosages
   // occupies the same 128-byte swizzled row as 128 int8 dosages but crosses L2->SM as 64 bytes.
-  const CUtensorMapDataType dt =
-      format == GB_PANEL_E2M1 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  // (kind::mxf4 reads the nibbles packed: same rows, no expansion, 256 dosages per 128-byte row.)
+  const CUtensorMapDataType dt = format == MAP_E2M1_EXPAND   ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B
+                                 : format == MAP_E2M1_PACKED ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN8B
+                                                             : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->fn_encode_tiled)(
       out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

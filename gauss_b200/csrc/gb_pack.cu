@@ -11,20 +11,19 @@ namespace gb {
 
 namespace {
 
-// 4-bit E2M1 code of a dosage (sign | 2-bit exponent | 1-bit mantissa); 0xFF when not representable.
+// 4-bit E2M1 code of a dosage (sign | 2-bit exponent | 1-bit mantissa); 0xFF when the panel format
+// does not take it: values E2M1 cannot hold exactly, and negative ones (the Gram epilogue of E2M1
+// panels relies on non-negative counts).
 __device__ __forceinline__ uint32_t e2m1_code(int v) {
-  const int a = v < 0 ? -v : v;
-  uint32_t c;
-  switch (a) {
-    case 0: c = 0x0; break;
-    case 1: c = 0x2; break;
-    case 2: c = 0x4; break;
-    case 3: c = 0x5; break;
-    case 4: c = 0x6; break;
-    case 6: c = 0x7; break;
+  switch (v) {
+    case 0: return 0x0;
+    case 1: return 0x2;
+    case 2: return 0x4;
+    case 3: return 0x5;
+    case 4: return 0x6;
+    case 6: return 0x7;
     default: return 0xFFu;
   }
-  return (v < 0 && a) ? (c | 0x8u) : c;
 }
 
 // One CTA per SNP row; warp w packs populations w, w+8, ...  Each lane moves 8 consecutive

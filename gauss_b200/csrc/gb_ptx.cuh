@@ -169,6 +169,39 @@ __device__ __forceinline__ void mma_f8f6f4_ss(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::mxf4 (block-scaled FP4): A and B are nibble-packed E2M1 in shared memory (K = 64 per
+// instruction = 32 bytes per row), every 32-element block is multiplied by an E8M0 scale read from
+// TMEM.  With all scales 2^0 the products and the fp32 sums are the same exact integers as above,
+// at twice the K per instruction and per TMA row.
+__host__ __device__ constexpr uint32_t make_idesc_mxf4(int M, int N) {
+  return (1u << 7)                        // A format E2M1 (MXF4Format)
+         | (1u << 10)                     // B format E2M1
+         | (0u << 15) | (0u << 16)        // A, B K-major
+         | ((uint32_t)(N >> 3) << 17)
+         | (1u << 23)                     // scale format UE8M0
+         | ((uint32_t)(M >> 4) << 24);    // scale-factor ids (bits 4-5, 29-30) = byte 0 of each TMEM cell
+}
+__device__ __forceinline__ void mma_mxf4_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+// registers -> TMEM, 32 lanes x 16 consecutive 32-bit columns, one value replicated (scale-factor fill)
+__device__ __forceinline__ void tmem_st_fill_32x32b_x16(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05 ops of this thread have completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -92,9 +92,8 @@ GB_API int gb_panel_create(gb_ctx *ctx, int n_pops, const int *pop_sizes, int64_
  *   GB_PANEL_INT8  one signed byte per dosage (kind::i8, int32 accumulate): exact for ANY byte the
  *                  reference's (c - '0') arithmetic can produce.
  *   GB_PANEL_E2M1  one 4-bit E2M1 float per dosage (kind::f8f6f4, fp32 accumulate): half the HBM
- *                  footprint and half the L2->SM traffic; exact for dosages in
- *                  {0, 1, 2, 3, 4, 6, -1, -2, -3, -4, -6} (every product and every per-population
- *                  sum is an integer below 2^24).  A row holding any other value makes the next
+ *                  footprint and twice the dosages per TMA row; exact for dosages in {0, 1, 2, 3, 4, 6}
+ *                  (every product and every per-population sum is an integer below 2^24).  A row holding any other value makes the next
  *                  batch/window call fail with GB_ERR_UNSUPPORTED -- repack as GB_PANEL_INT8.
  * gb_panel_create uses GB_PANEL_E2M1 (real panels hold only '0','1','2') unless the environment
  * variable GB_PANEL_FORMAT=int8 is set; gb_run_window_strings repacks as int8 by itself. */

@@ -88,11 +88,14 @@ def test_correlation_blocks_match_oracle(gpu_ctx, oracle, mix, fmt):
     panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"], fmt=fmt)
     B11, B21 = panel.window_cor(meas, unme, w)
     r = oracle.run_window(c["type"], c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"], dump=True)
-    assert np.abs(B11 - r["B11"]).max() <= 1e-13
-    assert np.abs(B21 - r["B21"]).max() <= 1e-13
-    # the epilogue keeps the reference's fp64 operation order: entries should be bit-identical
-    assert (B21 == r["B21"]).mean() > 0.999
-    assert (B11 == r["B11"]).mean() > 0.999
+    assert np.abs(B11 - r["B11"]).max() <= 1e-12
+    assert np.abs(B21 - r["B21"]).max() <= 1e-12
+    if fmt == "int8" or not mix:
+        # int8 panels (and the pooled r of dist() on any panel) keep the reference's fp64 operation
+        # order term by term: entries are bit-identical to CalWgtCov / CalCor
+        assert np.abs(B11 - r["B11"]).max() <= 1e-13 and np.abs(B21 - r["B21"]).max() <= 1e-13
+        assert (B21 == r["B21"]).mean() > 0.999
+        assert (B11 == r["B11"]).mean() > 0.999
     np.testing.assert_array_equal(np.diag(B11), np.full(len(meas), 1.1))
 
 
@@ -146,8 +149,14 @@ def test_formats_agree_bitwise_and_pooled_counts_reach_17_bits(gpu_ctx, oracle):
     for fmt in FORMATS:
         panel = make_panel(gpu_ctx, g, sizes, fmt=fmt)
         out[fmt] = panel.window_cor(meas, unme, None) + panel.window_cor(meas, unme, w)
-    for a, b in zip(out["e2m1"], out["int8"]):
+    for a, b in zip(out["e2m1"][:2], out["int8"][:2]):      # pooled r: same integers -> same doubles
         np.testing.assert_array_equal(a, b)
+    # mixture: regrouped vs literal term order.  Rows 0 and 1 are almost monomorphic at dosage 2 (allele
+    # frequency 0.99998, far outside the reference's 0.01..0.99 AF filter): sums of ~1e8 cancel down to a
+    # variance of ~1e-4, the worst case for the regrouped fold -- still 5 orders inside the 1e-6 bar.
+    for a, b in zip(out["e2m1"][2:], out["int8"][2:]):
+        assert np.abs(a - b).max() <= 1e-10
+        assert np.abs(a[2:, 2:] - b[2:, 2:]).max() <= 1e-12 if a.shape[0] == a.shape[1] else np.abs(a - b)[:, 2:].max() <= 1e-12
     assert oracle.cal_cor(g[0], g[1], sizes) == out["int8"][0][0, 1]
     assert abs(oracle.cal_cor(g[3], g[100], sizes) - out["e2m1"][1][40, 3]) <= 1e-15
 
@@ -185,14 +194,16 @@ def test_unrepresentable_dosage_needs_int8(gpu_ctx, oracle):
     assert np.abs(out["z"] - r["z"]).max() <= TOL and np.abs(out["info"] - r["info"]).max() <= TOL
 
 
-def test_compute_ld_matches_oracle(gpu_ctx, oracle):
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_compute_ld_matches_oracle(gpu_ctx, oracle, fmt):
     c = small_case(seed=25, n_snps=300, pop_sizes=(90, 40, 260))
-    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"])
+    panel = make_panel(gpu_ctx, c["g"], c["pop_sizes"], fmt=fmt)
     rows = np.arange(17, 290)
     ld, _ = panel.window_ld(rows, c["w"])
     ref = oracle.compute_ld(c["g"][rows], c["pop_sizes"], c["w"])
-    assert np.abs(ld - ref).max() <= 1e-13
-    assert (ld == ref).mean() > 0.999
+    assert np.abs(ld - ref).max() <= 1e-12
+    if fmt == "int8":
+        assert np.abs(ld - ref).max() <= 1e-13 and (ld == ref).mean() > 0.999
 
 
 def test_host_mirror_of_run_distmix_strings(gpu_ctx, oracle):
