@@ -178,6 +178,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   }
   gp.mode = b->counts_mode ? GRAM_COUNTS : b->mode;
   gp.mirror = b->ld_mode ? 1 : 0;
+  gp.raw_out = (gp.mode == GRAM_MIX && b->fkind != 0) ? 1 : 0;
   gp.diag = b->ld_mode ? 1.0 : 1.0 + b->params.lambda;   // computeLD.cpp:107 vs dist.cpp:172
 
   // ---- windows
@@ -432,7 +433,13 @@ int run_stage(gb_batch* b, int stage) {
                              b->d_pool_u, nullptr, b->d_st_sx_u, b->d_st_mean_u);
     }
     case 1:
+      if ((rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn)))
+        return rc;
+      return b->gp.raw_out ? launch_gram_finalize(ctx, b->gp, (int)b->h_tiles.size()) : GB_OK;
+    case 10:  // profiling: the tensor-core kernel alone
       return launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn);
+    case 11:  // profiling: the finish pass alone (a no-op for panels whose finish is fused)
+      return b->gp.raw_out ? launch_gram_finalize(ctx, b->gp, (int)b->h_tiles.size()) : GB_OK;
     case 2: {
       if (b->ld_mode || b->counts_mode) return GB_OK;
       const int nreal = (int)b->h_wins.size();

@@ -49,6 +49,7 @@ struct GramParams {
   int mode;
   int n_seg;
   int fkind;             // tensor-core operand kind: 0 = int8 (kind::i8), k > 0 = kind::f8f6f4 format k-1
+  int raw_out;           // 1: store the raw weighted Gram sum; gram_finalize_kernel finishes it (E2M1, mixture)
   int mirror;            // 1: also store the transposed entry (full symmetric matrix, computeLD)
   Seg seg[P_MAX];
   double coef[P_MAX];    // w_p * (m_p / (m_p - 1))          (util.cpp:117-118)
@@ -144,6 +145,7 @@ int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t
 int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_rows, int64_t k_elems,
                          int64_t k_stride_bytes, int format);
 bool gram_cluster_supported(int cm, int cn);
+int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors);
 int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn);
 
 // gb_solve.cu

@@ -34,10 +34,9 @@ namespace gb {
 namespace {
 
 constexpr int TILE = 128;
-#ifndef GB_GRAM_STAGES
-#define GB_GRAM_STAGES 4
-#endif
-constexpr int STAGES = GB_GRAM_STAGES;
+constexpr int STAGES_FUSED = 4;   // smem pipeline depth when the row-statistics tables share shared memory
+constexpr int STAGES_RAW = 6;     // ... and when they do not (E2M1 panels: finish pass in gram_finalize_kernel)
+constexpr int MAX_STAGES = STAGES_RAW;
 constexpr int STAGE_OPERAND_BYTES = TILE * K_BLOCK;  // 16 KiB
 constexpr int STAGE_BYTES = 2 * STAGE_OPERAND_BYTES; // A + B
 constexpr int ACC_BUFS = 4;                          // 4 x 128 TMEM columns
@@ -52,8 +51,12 @@ constexpr int FKIND_F8F6F4 = 6;   // kind::f8f6f4 with E2M1 operands (TMA expand
 constexpr int FKIND_MXF4 = 7;     // kind::mxf4 with unit block scales, nibbles stay packed, K = 64
 
 // dynamic shared memory carve-up (byte offsets from a 1024-aligned base)
-constexpr int OFF_STAGES = 0;
-constexpr int OFF_SA = OFF_STAGES + STAGES * STAGE_BYTES;     // int32 [P_MAX][128]
+constexpr int OFF_BARS = 0;                                   // mbarriers
+constexpr int N_BARS = 2 * MAX_STAGES + 2 * ACC_BUFS;
+constexpr int OFF_TMEM_PTR = OFF_BARS + N_BARS * 8;
+constexpr int OFF_STAGES = 1024;                              // [stages][A 16 KiB | B 16 KiB]
+// fused-finish tables sit behind STAGES_FUSED stages
+constexpr int OFF_SA = OFF_STAGES + STAGES_FUSED * STAGE_BYTES; // int32 [P_MAX][128]
 constexpr int OFF_SB = OFF_SA + P_MAX * TILE * 4;             // int32 [P_MAX][128]
 constexpr int OFF_GA = OFF_SB + P_MAX * TILE * 4;             // double [P_MAX][128]  w_p*(s^p_i/m_p)
 constexpr int OFF_HB = OFF_GA + P_MAX * TILE * 8;             // double [P_MAX][128]  s^p_j/m_p
@@ -61,12 +64,12 @@ constexpr int OFF_AI = OFF_HB + P_MAX * TILE * 8;             // double [128] su
 constexpr int OFF_BJ = OFF_AI + TILE * 8;                     // double [128] same for B rows
 constexpr int OFF_SDA = OFF_BJ + TILE * 8;                    // double [128]
 constexpr int OFF_SDB = OFF_SDA + TILE * 8;                   // double [128]
-constexpr int OFF_BARS = OFF_SDB + TILE * 8;                  // mbarriers
-constexpr int N_BARS = 2 * STAGES + 2 * ACC_BUFS;
-constexpr int OFF_TMEM_PTR = OFF_BARS + N_BARS * 8;
-constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16;
+constexpr int SMEM_BYTES_FUSED = OFF_SDB + TILE * 8;
+constexpr int SMEM_BYTES_RAW = OFF_STAGES + STAGES_RAW * STAGE_BYTES;
+constexpr int SMEM_BYTES = SMEM_BYTES_FUSED > SMEM_BYTES_RAW ? SMEM_BYTES_FUSED : SMEM_BYTES_RAW;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget exceeded");
+static_assert(OFF_TMEM_PTR + 16 <= OFF_STAGES, "barrier block overlaps the stages");
 
 // int32 -> double through the 2^52 trick: one LOP and one exact DADD on the fp64 pipe (64 / clk / SM)
 // instead of I2F.F64, which issues at 16 / clk / SM and was the epilogue's limiter.
@@ -111,9 +114,13 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint64_t* tempty_bar = bars + 2 * STAGES + ACC_BUFS;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + ACC_BUFS;
+  // E2M1 panels in mixture mode store the raw weighted Gram sum and leave the finish to
+  // gram_finalize_kernel: no statistics tables here, so two more pipeline stages fit
+  const bool raw_out = prm.raw_out != 0;
+  const int n_stages = raw_out ? STAGES_RAW : STAGES_FUSED;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
@@ -136,7 +143,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     ptx::prefetch_tmap(&tm_b_scratch);
   }
   if (warp == 1 && ptx::elect_one()) {
-    for (int s = 0; s < STAGES; s++) {
+    for (int s = 0; s < MAX_STAGES; s++) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], CM + CN - 1);  // one arrive per CTA that receives this CTA's slices
     }
@@ -203,7 +210,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             else ptx::tma_load_2d(sa, map_a, &full_bar[stage], koff + b * kblk, a_row);
             if (CM > 1) ptx::tma_load_2d_mc(sb, map_b, &full_bar[stage], koff + b * kblk, b_row, mask_col);
             else ptx::tma_load_2d(sb, map_b, &full_bar[stage], koff + b * kblk, b_row);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -266,7 +273,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             // frees the smem stage once these MMAs retire -- in every CTA that refills it
             if (CSIZE > 1) ptx::mma_commit_mc(&empty_bar[stage], free_mask);
             else ptx::mma_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(&tfull_bar[acc]);      // accumulator of segment s is complete
           if (++acc == acc_bufs) { acc = 0; acc_phase ^= 1; }
@@ -298,7 +305,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     // i.e. one DFMA per entry and population while the tile streams and one more in the finish,
     // instead of CalWgtCov's literal term order (kept for int8 panels: 2 IMAD + 3 fp64 ops + the
     // mean term).  Same value up to ~1e-13 of the variance; the test bar is 1e-6.
-    const bool fast = mode == GRAM_MIX && f32acc;
+    const bool fast = raw_out;
     int acc_buf = 0;
     uint32_t acc_phase = 0;
 
@@ -317,28 +324,14 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       }
       // ---- per-tile row statistics into shared memory: plain copies of what row_prep_kernel
       // precomputed per listed row (sum x and sum x / m per population) -- no division here
-      epi_bar_sync();  // previous tile's readers are done
-      if (mode != GRAM_COUNTS) {
+      if (!fast) epi_bar_sync();  // previous tile's readers are done
+      if (mode != GRAM_COUNTS && !fast) {
         const int side = etid >> 7;  // 0: A rows, 1: B rows
         const int idx = etid & 127;
         const int valid = side ? t.b_valid : t.a_valid;
         const long long li = (side ? t.b_list0 : t.a_list0) + min(idx, valid - 1);
         const bool from_u = (side == 0) && t.a_is_u;
-        if (fast) {
-          // regrouped form (see the fold below): A side keeps kappa_p * s^p_i, B side s^p_j as doubles
-          const int32_t* st_sx = from_u ? prm.st_sx_u : prm.st_sx_t;
-          const double* st_mean = from_u ? prm.st_mean_u : prm.st_mean_t;
-          const long long ld = from_u ? prm.st_ld_u : prm.st_ld_t;
-          double* mdst = side ? hB : gA;
-          double wsum = 0.0;
-#pragma unroll 4
-          for (int p = 0; p < n_seg; p++) {
-            const double sxd = int_to_double(st_sx[p * ld + li]);
-            mdst[p * TILE + idx] = side ? sxd : __dmul_rn(prm.kappa[p], sxd);
-            wsum = __dadd_rn(wsum, __dmul_rn(prm.wgt[p], st_mean[p * ld + li]));   // wsum_mi  (util.cpp:120-121)
-          }
-          (side ? bjS : aiS)[idx] = wsum;
-        } else if (mode == GRAM_MIX) {
+        if (mode == GRAM_MIX) {
           const int32_t* st_sx = from_u ? prm.st_sx_u : prm.st_sx_t;
           const double* st_mean = from_u ? prm.st_mean_u : prm.st_mean_t;
           const long long ld = from_u ? prm.st_ld_u : prm.st_ld_t;
@@ -364,7 +357,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
         }
         (side ? sdB : sdA)[idx] = from_u ? prm.sd_u[li] : prm.sd_t[li];
       }
-      epi_bar_sync();
+      if (!fast) epi_bar_sync();
 
       double acc[EPI_COLS];
 #pragma unroll
@@ -433,6 +426,22 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
 
       if (mode == GRAM_COUNTS) continue;
 
+      if (fast) {
+        // raw sum_p (coef_p m_p) S^p_ij; gram_finalize_kernel adds the mean terms and normalises in place
+        double* out = (t.a_is_u ? prm.out_ut : prm.out_tt) + t.out_off;
+        const long long gi = t.i0 + r;
+        const bool diag_tile = (!t.a_is_u) && (t.i0 == t.j0);
+        if (r < t.a_valid) {
+#pragma unroll
+          for (int e = 0; e < EPI_COLS; e++) {
+            const int c = c0 + e;
+            const long long gj = t.j0 + c;
+            if (c < t.b_valid && !(diag_tile && gi < gj)) out[gj * t.ld_out + gi] = acc[e];
+          }
+        }
+        continue;
+      }
+
       // ---- finish the entries and store
       const bool row_ok = r < t.a_valid;
       const double sd_r = sdA[r];
@@ -445,24 +454,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
 #pragma unroll
       for (int ch = 0; ch < EPI_COLS / 8; ch++) {
         double num8[8];
-        if (fast) {
-          double x[8];
-#pragma unroll
-          for (int k = 0; k < 8; k++) x[k] = acc[ch * 8 + k];
-#pragma unroll 3
-          for (int p = 0; p < n_seg; p++) {   // + kappa_p s^p_i s^p_j
-            const double g = gA[p * TILE + r];
-            const double2* hv = reinterpret_cast<const double2*>(hB + p * TILE + c0 + ch * 8);
-#pragma unroll
-            for (int k2 = 0; k2 < 4; k2++) {
-              const double2 h2 = hv[k2];
-              x[2 * k2] = fma(g, h2.x, x[2 * k2]);
-              x[2 * k2 + 1] = fma(g, h2.y, x[2 * k2 + 1]);
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; k++) num8[k] = fma(-ai, bjS[c0 + ch * 8 + k], x[k]);
-        } else if (mode == GRAM_MIX) {
+        if (mode == GRAM_MIX) {
           double x[8];
 #pragma unroll
           for (int k = 0; k < 8; k++) x[k] = 0.0;
@@ -518,6 +510,88 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Finish pass of the regrouped fold (E2M1 panels, mixture mode).  One CTA per 128 x 128 tile of
+// the same tile list; reads the raw sum_p (coef_p m_p) S^p_ij the Gram kernel stored and writes
+//   cor_ij = (raw + sum_p kappa_p s^p_i s^p_j - a_i b_j) / (sd_i sd_j),   a_i = sum_p w_p s^p_i / m_p,
+// in place (diagonal forced, symmetric mirror for computeLD).  A separate, fully occupied kernel
+// instead of a tail on the 8 epilogue warps of the tensor-core kernel: there it serialised with
+// the next tile's MMAs (3 TMEM buffers ahead at most) and cost 27 % of the kernel.
+__global__ void __launch_bounds__(256)
+gram_finalize_kernel(const __grid_constant__ GramParams prm) {
+  const GramTile t = prm.tiles[blockIdx.x];
+  if (t.a_valid <= 0 || t.b_valid <= 0) return;
+  extern __shared__ __align__(16) double fs[];
+  const int n_seg = prm.n_seg;
+  double* gA = fs;                        // [n_seg][128] kappa_p * s^p_i
+  double* hB = gA + n_seg * TILE;         // [n_seg][128] s^p_j
+  double* aiS = hB + n_seg * TILE;        // [128]
+  double* bjS = aiS + TILE;
+  double* sdA = bjS + TILE;
+  double* sdB = sdA + TILE;
+  const int tid = threadIdx.x;
+  {
+    const int side = tid >> 7, idx = tid & 127;
+    const int valid = side ? t.b_valid : t.a_valid;
+    const long long li = (side ? t.b_list0 : t.a_list0) + min(idx, valid - 1);
+    const bool from_u = (side == 0) && t.a_is_u;
+    const int32_t* st_sx = from_u ? prm.st_sx_u : prm.st_sx_t;
+    const double* st_mean = from_u ? prm.st_mean_u : prm.st_mean_t;
+    const long long ld = from_u ? prm.st_ld_u : prm.st_ld_t;
+    double* mdst = side ? hB : gA;
+    double wsum = 0.0;
+#pragma unroll 4
+    for (int p = 0; p < n_seg; p++) {
+      const double sxd = int_to_double(st_sx[p * ld + li]);
+      mdst[p * TILE + idx] = side ? sxd : __dmul_rn(prm.kappa[p], sxd);
+      wsum = __dadd_rn(wsum, __dmul_rn(prm.wgt[p], st_mean[p * ld + li]));   // wsum_mi  (util.cpp:120-121)
+    }
+    (side ? bjS : aiS)[idx] = wsum;
+    (side ? sdB : sdA)[idx] = from_u ? prm.sd_u[li] : prm.sd_t[li];
+  }
+  __syncthreads();
+  const int r = tid & 127;
+  const int c0 = (tid >> 7) * EPI_COLS;
+  if (r >= t.a_valid) return;
+  double* out = (t.a_is_u ? prm.out_ut : prm.out_tt) + t.out_off;
+  const long long gi = t.i0 + r;
+  const bool diag_tile = (!t.a_is_u) && (t.i0 == t.j0);
+  const double ai = aiS[r], sd_r = sdA[r];
+#pragma unroll 1
+  for (int ch = 0; ch < EPI_COLS / 8; ch++) {
+    double x[8];
+    bool ok[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = c0 + ch * 8 + k;
+      const long long gj = t.j0 + c;
+      ok[k] = c < t.b_valid && !(diag_tile && gi < gj);
+      x[k] = ok[k] ? out[gj * t.ld_out + gi] : 0.0;
+    }
+#pragma unroll 3
+    for (int p = 0; p < n_seg; p++) {   // + kappa_p s^p_i s^p_j
+      const double g = gA[p * TILE + r];
+      const double2* hv = reinterpret_cast<const double2*>(hB + p * TILE + c0 + ch * 8);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; k2++) {
+        const double2 h2 = hv[k2];
+        x[2 * k2] = fma(g, h2.x, x[2 * k2]);
+        x[2 * k2 + 1] = fma(g, h2.y, x[2 * k2 + 1]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = c0 + ch * 8 + k;
+      const long long gj = t.j0 + c;
+      double cor = __ddiv_rn(fma(-ai, bjS[c], x[k]), __dmul_rn(sd_r, sdB[c]));   // cov / (stdi*stdj)  (distmix.cpp:196)
+      if (diag_tile && gi == gj) cor = prm.diag;
+      if (ok[k]) {
+        out[gj * t.ld_out + gi] = cor;
+        if (prm.mirror) out[gi * t.ld_out + gj] = cor;
+      }
+    }
   }
 }
 
@@ -627,6 +701,21 @@ int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const 
 bool gram_cluster_supported(int cm, int cn) {
   return (cm == 1 && cn == 1) || (cm == 2 && cn == 1) || (cm == 2 && cn == 2) || (cm == 4 && cn == 1) ||
          (cm == 4 && cn == 2) || (cm == 2 && cn == 4) || (cm == 8 && cn == 1);
+}
+
+int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors) {
+  if (n_descriptors <= 0) return GB_OK;
+  const size_t smem = sizeof(double) * (size_t)(2 * prm.n_seg * TILE + 4 * TILE);
+  static bool attr_set_dev[64] = {};
+  if (!attr_set_dev[ctx->device & 63]) {
+    GB_CUDA(cudaFuncSetAttribute(gram_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(double) * (2 * P_MAX * TILE + 4 * TILE))));
+    attr_set_dev[ctx->device & 63] = true;
+  }
+  gram_finalize_kernel<<<(unsigned)n_descriptors, 256, smem, ctx->stream>>>(prm);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
 }
 
 // prm.n_tiles counts CLUSTER tiles; prm.tiles holds cm*cn descriptors per cluster tile (rank order).

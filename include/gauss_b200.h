@@ -160,8 +160,9 @@ GB_API int gb_batch_fetch(gb_batch *batch, double *z_u, double *info_u, int *win
 /* Algorithmic work of the batch: int8 Gram ops, solve fp64 flops, panel bytes. */
 GB_API int gb_batch_work(const gb_batch *batch, double *gram_ops, double *solve_flops,
                   double *panel_bytes);
-/* Enqueue only one stage (profiling / roofline timing): 0 = row statistics, 1 = Gram+epilogue,
- * 2 = Cholesky, 3 = triangular solve + finalise. */
+/* Enqueue only one stage (profiling / roofline timing): 0 = row statistics, 1 = Gram + finish pass,
+ * 2 = Cholesky, 3 = triangular solve + finalise; 10 / 11 = the two halves of stage 1 (tensor-core
+ * kernel / finish pass). */
 GB_API int gb_batch_run_stage(gb_batch *batch, int stage);
 
 /* ---- pipelined single windows, host in / host out ---------------------------------------------- */
