@@ -31,6 +31,38 @@ constexpr int STATUS_BREAKDOWN = 1;
 
 __device__ __forceinline__ int win_nb(int n) { return (n + NB - 1) / NB; }
 
+// C(8x8) += A(8x4) B(4x8) on the fp64 tensor cores: lane holds A(row = lane/4, k = lane%4),
+// B(k = lane%4, col = lane/4), C(row = lane/4, cols 2(lane%4), 2(lane%4)+1).  Same 64 FMA/clk/SM peak
+// as DFMA on B200 (tools/dmma_probe.cu) at 1/8 of the instructions and operand fetches.
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// 64 x 64 x 64 product on 8 warps: C(m, n) += sign * sum_k As[k*TS + m] * Bs[k*TS + n], k < kmax (multiple of 4).
+// Warp (wr = warp/4, wc = warp%4) owns rows 32 wr .. +31 and columns 16 wc .. +15 as 4 x 2 MMA tiles;
+// C[mt][nt][e] is element (32 wr + 8 mt + lane/4, 16 wc + 8 nt + 2 (lane%4) + e).  TS = 68 doubles
+// (8 words mod 32) keeps the fragment loads conflict-free.
+constexpr int TS = NB + 4;
+__device__ __forceinline__ void tile64_dmma(const double* As, const double* Bs, double (&C)[4][2][2], int kmax,
+                                            double sign, int lane, int warp) {
+  const int gid = lane >> 2, tig = lane & 3;
+  const int row0 = 32 * (warp >> 2) + gid, col0 = 16 * (warp & 3) + gid;
+#pragma unroll 4
+  for (int k = 0; k < kmax; k += 4) {
+    double a[4], b[2];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) a[mt] = sign * As[(k + tig) * TS + row0 + 8 * mt];
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) b[nt] = Bs[(k + tig) * TS + col0 + 8 * nt];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) dmma_m8n8k4(C[mt][nt][0], C[mt][nt][1], a[mt], b[nt]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // In-place transform of a 64x64 SPD block M (lower triangle, M[c*PAD + r] = element (r, c)) into
 // inv(L), L = chol(M); L itself is never formed (nothing downstream needs it).  256 threads:
@@ -245,50 +277,40 @@ chol_panel_kernel(const SolveWin* __restrict__ wins, double* tt, const double* _
   const int tid = threadIdx.x;
 
   extern __shared__ __align__(16) double sm[];
-  double* X = sm;                 // [64][MP] inv(L_kk), X[j*MP + c] = inv(L_kk)(c, j)
-  double* T = X + NB * MP;        // [64][MP] A_ik tile, T[j*MP + r] = A(ib*64+r, k*64+j)
+  double* X = sm;                 // [64][TS] inv(L_kk), X[j*TS + c] = inv(L_kk)(c, j)
+  double* T = X + NB * TS;        // [64][TS] A_ik tile, T[j*TS + r] = A(ib*64+r, k*64+j)
 
   const int k0 = k * NB;
   const int i0 = ib * NB;
   const double* D = dinv + w.off_dinv + (long long)k * NB * NB;
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int c = idx >> 6, r = idx & 63;
-    X[c * MP + r] = D[c * NB + r];
-    T[c * MP + r] = (i0 + r < n && k0 + c < n) ? A[(long long)(k0 + c) * ld + i0 + r] : 0.0;
+    X[c * TS + r] = D[c * NB + r];
+    T[c * TS + r] = (i0 + r < n && k0 + c < n) ? A[(long long)(k0 + c) * ld + i0 + r] : 0.0;
   }
   __syncthreads();
 
-  // L(r, c) = sum_{j<=c} A(r, j) X(c, j); 4x4 register tile per thread,
-  // rows {2a,2a+1,32+2a,32+2a+1}, columns 4b..4b+3
+  // L(r, c) = sum_{j<=c} A(r, j) X(c, j) = sum_j T[j][r] X[j][c] on the fp64 tensor cores
+  // (X[j][c] = 0 for j > c, so the k range of column quarter wc ends at 16 wc + 16)
   {
-    const int a2 = (tid & 15) * 2, cb = (tid >> 4) * 4;
-    double acc[4][4];
+    const int lane = tid & 31, warp = tid >> 5;
+    double C[4][2][2];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-      for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-    const int jmax = cb + 3;  // X(c, j) = 0 for j > c
-    for (int j = 0; j <= jmax; j++) {
-      const double2 t01 = *reinterpret_cast<const double2*>(&T[j * MP + a2]);
-      const double2 t23 = *reinterpret_cast<const double2*>(&T[j * MP + 32 + a2]);
-      const double2 x01 = *reinterpret_cast<const double2*>(&X[j * MP + cb]);
-      const double2 x23 = *reinterpret_cast<const double2*>(&X[j * MP + cb + 2]);
-      const double tv[4] = {t01.x, t01.y, t23.x, t23.y};
-      const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+      for (int nt = 0; nt < 2; nt++) C[mt][nt][0] = C[mt][nt][1] = 0.0;
+    tile64_dmma(T, X, C, 16 * ((warp & 3) + 1), 1.0, lane, warp);
+    const int gid = lane >> 2, tig = lane & 3;
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+    for (int mt = 0; mt < 4; mt++) {
+      const int r = i0 + 32 * (warp >> 2) + 8 * mt + gid;
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = fma(tv[a], xv[b], acc[a][b]);
-    }
+      for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const int c = k0 + cb + b;
-      if (c >= n) continue;
-#pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const int r = i0 + a2 + (a & 1) + (a >> 1) * 32;
-        if (r < n) A[(long long)c * ld + r] = acc[a][b];
-      }
+        for (int e = 0; e < 2; e++) {
+          const int c = k0 + 16 * (warp & 3) + 8 * nt + 2 * tig + e;
+          if (r < n && c < n) A[(long long)c * ld + r] = C[mt][nt][e];
+        }
     }
   }
 }
@@ -313,44 +335,40 @@ chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, const int* __r
   const int ld = w.ld_t;
   const int tid = threadIdx.x;
 
-  extern __shared__ double sm[];
-  double (*Ls)[NB] = reinterpret_cast<double (*)[NB]>(sm);            // Ls[kk][r] = L(i0+r, k0+kk)
-  double (*Rs)[NB] = reinterpret_cast<double (*)[NB]>(sm + NB * NB);  // Rs[kk][c] = L(j0+c, k0+kk)
+  extern __shared__ __align__(16) double sm[];
+  double* Ls = sm;            // Ls[kk*TS + r] = L(i0+r, k0+kk)
+  double* Rs = sm + NB * TS;  // Rs[kk*TS + c] = L(j0+c, k0+kk)
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int kk = idx >> 6, r = idx & 63;
-    Ls[kk][r] = (i0 + r < n) ? A[(long long)(k0 + kk) * ld + i0 + r] : 0.0;
-    Rs[kk][r] = (j0 + r < n) ? A[(long long)(k0 + kk) * ld + j0 + r] : 0.0;
+    Ls[kk * TS + r] = (i0 + r < n) ? A[(long long)(k0 + kk) * ld + i0 + r] : 0.0;
+    Rs[kk * TS + r] = (j0 + r < n) ? A[(long long)(k0 + kk) * ld + j0 + r] : 0.0;
   }
   __syncthreads();
-  const int a2 = (tid & 15) * 2;   // rows {a2, a2+1, 32+a2, 32+a2+1}: conflict-free 16-byte smem reads
-  const int tc = (tid >> 4) * 4;   // cols tc..tc+3
-  double acc[4][4];
+  const int lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  double C[4][2][2];
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int mt = 0; mt < 4; mt++) {
+    const int r = i0 + 32 * (warp >> 2) + 8 * mt + gid;
 #pragma unroll
-    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-#pragma unroll 8
-  for (int kk = 0; kk < NB; kk++) {
-    const double2 l01 = *reinterpret_cast<const double2*>(&Ls[kk][a2]);
-    const double2 l23 = *reinterpret_cast<const double2*>(&Ls[kk][32 + a2]);
-    const double2 r01 = *reinterpret_cast<const double2*>(&Rs[kk][tc]);
-    const double2 r23 = *reinterpret_cast<const double2*>(&Rs[kk][tc + 2]);
-    const double lv[4] = {l01.x, l01.y, l23.x, l23.y};
-    const double rv[4] = {r01.x, r01.y, r23.x, r23.y};
+    for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) acc[a][b] = fma(lv[a], rv[b], acc[a][b]);
+      for (int e = 0; e < 2; e++) {
+        const int c = j0 + 16 * (warp & 3) + 8 * nt + 2 * tig + e;
+        C[mt][nt][e] = (r < n && c < n && r >= c) ? A[(long long)c * ld + r] : 0.0;
+      }
   }
+  tile64_dmma(Ls, Rs, C, NB, -1.0, lane, warp);   // C -= L_ik L_jk^T
 #pragma unroll
-  for (int b = 0; b < 4; b++) {
-    const int c = j0 + tc + b;
-    if (c >= n) continue;
+  for (int mt = 0; mt < 4; mt++) {
+    const int r = i0 + 32 * (warp >> 2) + 8 * mt + gid;
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-      const int r = i0 + a2 + (a & 1) + (a >> 1) * 32;
-      if (r < n && r >= c) A[(long long)c * ld + r] -= acc[a][b];
-    }
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = j0 + 16 * (warp & 3) + 8 * nt + 2 * tig + e;
+        if (r < n && c < n && r >= c) A[(long long)c * ld + r] = C[mt][nt][e];
+      }
   }
 }
 
@@ -402,14 +420,21 @@ pd_bound_kernel(const SolveWin* __restrict__ wins, int nreal, const double* __re
 // ---------------------------------------------------------------------------------------------
 // Blocked forward substitution W = L^-1 B21^T for 128 unmeasured SNPs, fused with the reductions.
 //
-// Thread tile 8 rows x 4 columns: warp g owns rows 8g..8g+7 of the 64-row block, lane l owns
-// columns {2l, 2l+1, 64+2l, 64+2l+1}.  Operand chunks (32 k-steps of L: 16 KiB, of W: 32 KiB) are
-// double-buffered with cp.async.cg (L2 path: W rows were written by this CTA earlier).  The
-// accumulator tile and inv(L_ii) alias the chunk buffers once the k-loop of a row block is done,
-// so a CTA needs 96 KiB and two CTAs share an SM.
+// The two products of every 64-row block -- acc = B_i - sum_k L_ik W_k and W_i = inv(L_ii) acc --
+// run on the fp64 tensor cores (mma.sync m8n8k4 .f64: same 64 FMA/clk/SM peak as DFMA on B200, but
+// 256 FMAs per warp instruction with 2 operand registers, so the kernel is no longer bound by
+// instruction issue and shared-memory operand fetch; measured tools/dmma_probe.cu).  8 warps =
+// 2 row halves x 4 column quarters, 32 x 32 per warp = 4 x 4 MMA tiles, C fragment (row = lane / 4,
+// columns 2 (lane % 4) + {0, 1}).  Operand chunks (32 k-steps of L and of W) are double-buffered
+// with cp.async.cg; their shared-memory row strides (68 and 132 doubles = 8 words mod 32) make the
+// A / B fragment loads conflict-free.  inv(L_ii) and the accumulator tile alias the chunk buffers
+// once the k-loop of a row block is done; two CTAs share an SM.
 constexpr int UB = 128;   // unmeasured SNPs (columns of W) per CTA
 constexpr int KC = 32;    // k-steps per staged chunk
-constexpr int TR_SMEM_BYTES = 2 * (KC * NB + KC * UB) * 8;  // 98,304
+constexpr int LSS = NB + 4;   // row stride of staged L / inv(L_ii)   [k][row]
+constexpr int WSS = UB + 4;   // row stride of staged W / accumulator [k][col]
+constexpr int TR_SMEM_BYTES = 2 * (KC * LSS + KC * WSS) * 8;  // 102,400
+static_assert(2 * KC * LSS >= NB * LSS && 2 * KC * WSS >= NB * WSS, "aliased tiles must fit the chunk buffers");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -434,60 +459,66 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   double* W = ut + w.off_ut;
   const int ldu = w.ld_u;
   const int tid = threadIdx.x;
-  const int lane = tid & 31, g = tid >> 5;
-  const int tr = g * 8;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wr = warp >> 2, wc = warp & 3;       // row half / column quarter of this warp
+  const int row0 = 32 * wr + gid;                // + 8 mt: rows of this thread's A / C fragments
+  const int col0 = 32 * wc;                      // + 8 nt (+ gid for B fragments, + 2 tig for C)
 
   extern __shared__ __align__(16) double sm[];
-  double* LsBuf = sm;                       // 2 x [KC][64]
-  double* WsBuf = sm + 2 * KC * NB;         // 2 x [KC][128]
-  double* Ds = LsBuf;                       // [64][64] inv(L_ii), aliases both L chunks
-  double* Ts = WsBuf;                       // [64][128] accumulator tile, aliases both W chunks
-  double* red = WsBuf;                      // [8][128] final reductions
-  double* ys = sm + 2 * (KC * NB + KC * UB); // [nb*64] y = L^-1 Z1 solved so far (every CTA carries this extra
-  double* rys = ys + nb * NB;                // [64]     right-hand side column itself: ~1/128 more work, no
-                                             //          separate latency-bound kernel and no y round trip)
-
-  double p_info[4] = {0.0, 0.0, 0.0, 0.0}, p_z[4] = {0.0, 0.0, 0.0, 0.0};
-  const int ccol[2] = {2 * lane, 64 + 2 * lane};   // first column of each 2-wide strip of this thread
-  const int cvalid = ldu - u0;                     // columns that exist in the row (ldu is a multiple of 8)
+  double* LsBuf = sm;                        // 2 x [KC][LSS]
+  double* WsBuf = sm + 2 * KC * LSS;         // 2 x [KC][WSS]
+  double* Ds = LsBuf;                        // [64][LSS] inv(L_ii)(r, kk) at [kk][r], aliases both L chunks
+  double* Ts = WsBuf;                        // [64][WSS] accumulator tile, aliases both W chunks
+  double* red = WsBuf;                       // [2][2][UB] final reductions
+  double* ys = sm + 2 * (KC * LSS + KC * WSS);  // [nb*64] y = L^-1 Z1 solved so far (every CTA carries this extra
+  double* rys = ys + nb * NB;                   // [64]     right-hand side column itself: ~1/128 more work, no
+                                                //          separate latency-bound kernel and no y round trip)
+  double* ypart = rys + NB;                     // [4][64]  partial dot products of the y column (4 threads per row)
+  const int yr_ = tid & 63, yq = tid >> 6;
+  double p_info[4][2], p_z[4][2];            // per owned column (nt, e): partial sums over this thread's rows
+#pragma unroll
+  for (int nt = 0; nt < 4; nt++) p_info[nt][0] = p_info[nt][1] = p_z[nt][0] = p_z[nt][1] = 0.0;
+  const int cvalid = ldu - u0;               // columns that exist in the row (ldu is a multiple of 8)
 
   for (int ib = 0; ib < nb; ib++) {
     const int i0 = ib * NB;
-    double acc[8][4];
+    double C[4][4][2];
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const int r = i0 + tr + a;
+    for (int mt = 0; mt < 4; mt++) {
+      const int r = i0 + row0 + 8 * mt;
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
+      for (int nt = 0; nt < 4; nt++) {
+        const int c = col0 + 8 * nt + 2 * tig;
         double2 v = make_double2(0.0, 0.0);
-        if (r < n && ccol[s] < cvalid) v = *reinterpret_cast<const double2*>(&W[(long long)r * ldu + u0 + ccol[s]]);
-        acc[a][2 * s] = v.x;
-        acc[a][2 * s + 1] = v.y;
+        if (r < n && c < cvalid) v = *reinterpret_cast<const double2*>(&W[(long long)r * ldu + u0 + c]);
+        C[mt][nt][0] = v.x;
+        C[mt][nt][1] = v.y;
       }
     }
-    // acc -= L(ib, 0:i0) * W(0:i0) in chunks of KC k-steps
+    // C -= L(ib, 0:i0) * W(0:i0) in chunks of KC k-steps
     const int nchunk = ib * (NB / KC);
     auto issue = [&](int ch, int buf) {
       const int kbase = ch * KC;
-      double* ls = LsBuf + buf * KC * NB;
-      double* ws = WsBuf + buf * KC * UB;
+      double* ls = LsBuf + buf * KC * LSS;
+      double* ws = WsBuf + buf * KC * WSS;
       // L chunk: KC columns x 64 rows in 16-byte pieces, 32 per column
 #pragma unroll
       for (int it = 0; it < (KC * NB / 2) / 256; it++) {
         const int idx = tid + it * 256;
         const int kk = idx >> 5, r2 = (idx & 31) * 2;
-        cp_async16(ls + kk * NB + r2, L + (long long)(kbase + kk) * ld + i0 + r2, i0 + r2 < n);
+        cp_async16(ls + kk * LSS + r2, L + (long long)(kbase + kk) * ld + i0 + r2, i0 + r2 < n);
       }
       // W chunk: KC rows x 128 columns, 64 pieces per row
 #pragma unroll
       for (int it = 0; it < (KC * UB / 2) / 256; it++) {
         const int idx = tid + it * 256;
         const int kk = idx >> 6, c2 = (idx & 63) * 2;
-        cp_async16(ws + kk * UB + c2, W + (long long)(kbase + kk) * ldu + u0 + c2, c2 < cvalid);
+        cp_async16(ws + kk * WSS + c2, W + (long long)(kbase + kk) * ldu + u0 + c2, c2 < cvalid);
       }
       cp_async_commit();
     };
-    double acc_y = 0.0;  // threads 0..63: sum_k L(i0 + tid, k) y_k
+    double acc_y = 0.0;  // thread (row yr_, quarter yq): sum over k = yq mod 4 of L(i0 + yr_, k) y_k
     __syncthreads();  // previous row block finished with the aliased buffers (Ts / Ds)
     if (nchunk > 0) issue(0, 0);
     for (int ch = 0; ch < nchunk; ch++) {
@@ -499,118 +530,116 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
         cp_async_wait<0>();
       }
       __syncthreads();
-      const double* ls = LsBuf + buf * KC * NB;
-      const double* ws = WsBuf + buf * KC * UB;
+      const double* ls = LsBuf + buf * KC * LSS;
+      const double* ws = WsBuf + buf * KC * WSS;
 #pragma unroll 2
-      for (int kk = 0; kk < KC; kk++) {
-        double lv[8], wv[4];
+      for (int ks = 0; ks < KC / 4; ks++) {
+        double a[4], b[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const double2 t2 = *reinterpret_cast<const double2*>(&ls[kk * NB + tr + 2 * q]);
-          lv[2 * q] = t2.x;
-          lv[2 * q + 1] = t2.y;
-        }
+        for (int mt = 0; mt < 4; mt++) a[mt] = -ls[(4 * ks + tig) * LSS + row0 + 8 * mt];
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
-          const double2 t2 = *reinterpret_cast<const double2*>(&ws[kk * UB + ccol[s]]);
-          wv[2 * s] = t2.x;
-          wv[2 * s + 1] = t2.y;
-        }
+        for (int nt = 0; nt < 4; nt++) b[nt] = ws[(4 * ks + tig) * WSS + col0 + 8 * nt + gid];
 #pragma unroll
-        for (int a = 0; a < 8; a++)
+        for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-          for (int b = 0; b < 4; b++) acc[a][b] = fma(-lv[a], wv[b], acc[a][b]);
+          for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(C[mt][nt][0], C[mt][nt][1], a[mt], b[nt]);
       }
-      if (tid < NB) {
+      {
         const double* yk = ys + ch * KC;
-#pragma unroll 8
-        for (int kk = 0; kk < KC; kk++) acc_y = fma(ls[kk * NB + tid], yk[kk], acc_y);
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) acc_y = fma(ls[(kk + yq) * LSS + yr_], yk[kk + yq], acc_y);
       }
       __syncthreads();  // buffer `buf` may be refilled by the next issue
     }
-    // W_i = inv(L_ii) * acc
+    // W_i = inv(L_ii) * C
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+    for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-      for (int s = 0; s < 2; s++)
-        *reinterpret_cast<double2*>(&Ts[(tr + a) * UB + ccol[s]]) = make_double2(acc[a][2 * s], acc[a][2 * s + 1]);
-    for (int idx = tid; idx < NB * NB / 2; idx += 256)  // Ds[kk*64 + r] = inv(L_ii)(r, kk), zero above diag
-      reinterpret_cast<double2*>(Ds)[idx] =
+      for (int nt = 0; nt < 4; nt++)
+        *reinterpret_cast<double2*>(&Ts[(row0 + 8 * mt) * WSS + col0 + 8 * nt + 2 * tig]) =
+            make_double2(C[mt][nt][0], C[mt][nt][1]);
+    for (int idx = tid; idx < NB * NB / 2; idx += 256) {  // Ds[kk*LSS + r] = inv(L_ii)(r, kk), zero above diag
+      const int kk = idx >> 5, r2 = (idx & 31) * 2;
+      *reinterpret_cast<double2*>(&Ds[kk * LSS + r2]) =
           reinterpret_cast<const double2*>(dinv + w.off_dinv + (long long)ib * NB * NB)[idx];
-    if (tid < NB) rys[tid] = (i0 + tid < n) ? zt[w.off_t + i0 + tid] - acc_y : 0.0;
+    }
+    ypart[yq * NB + yr_] = acc_y;
     __syncthreads();
-    if (tid < NB) {  // y_i = inv(L_ii) (z_i - sum_k L_ik y_k)
+    if (tid < NB)
+      rys[tid] = (i0 + tid < n)
+                     ? zt[w.off_t + i0 + tid] - ((ypart[tid] + ypart[NB + tid]) + (ypart[2 * NB + tid] + ypart[3 * NB + tid]))
+                     : 0.0;
+    __syncthreads();
+    {  // y_i = inv(L_ii) (z_i - sum_k L_ik y_k): 4 threads per row, combined after the tile product below
       double v = 0.0;
-      for (int j = 0; j <= tid; j++) v = fma(Ds[j * NB + tid], rys[j], v);
-      ys[i0 + tid] = v;
+      for (int j = yq; j <= yr_; j += 4) v = fma(Ds[j * LSS + yr_], rys[j], v);
+      ypart[yq * NB + yr_] = v;
     }
-    double out[8][4];
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+    for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-      for (int b = 0; b < 4; b++) out[a][b] = 0.0;
-    const int kmax = tr + 8;  // inv(L_ii)(r, kk) == 0 for kk > r
-#pragma unroll 1
-    for (int kk = 0; kk < kmax; kk++) {
-      double lv[8], tv[4];
+      for (int nt = 0; nt < 4; nt++) C[mt][nt][0] = C[mt][nt][1] = 0.0;
+    const int ksmax = 8 * (wr + 1);  // inv(L_ii)(r, kk) == 0 for kk > r, and this warp's rows end at 32 wr + 31
+#pragma unroll 2
+    for (int ks = 0; ks < ksmax; ks++) {
+      double a[4], b[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const double2 t2 = *reinterpret_cast<const double2*>(&Ds[kk * NB + tr + 2 * q]);
-        lv[2 * q] = t2.x;
-        lv[2 * q + 1] = t2.y;
-      }
+      for (int mt = 0; mt < 4; mt++) a[mt] = Ds[(4 * ks + tig) * LSS + row0 + 8 * mt];
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const double2 t2 = *reinterpret_cast<const double2*>(&Ts[kk * UB + ccol[s]]);
-        tv[2 * s] = t2.x;
-        tv[2 * s + 1] = t2.y;
-      }
+      for (int nt = 0; nt < 4; nt++) b[nt] = Ts[(4 * ks + tig) * WSS + col0 + 8 * nt + gid];
 #pragma unroll
-      for (int a = 0; a < 8; a++)
+      for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) out[a][b] = fma(lv[a], tv[b], out[a][b]);
+        for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(C[mt][nt][0], C[mt][nt][1], a[mt], b[nt]);
     }
+    __syncthreads();
+    if (tid < NB) ys[i0 + tid] = (ypart[tid] + ypart[NB + tid]) + (ypart[2 * NB + tid] + ypart[3 * NB + tid]);
     __syncthreads();  // ys[i0 .. i0+63] is complete
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const int r = i0 + tr + a;
+    for (int mt = 0; mt < 4; mt++) {
+      const int r = i0 + row0 + 8 * mt;
       if (r >= n) continue;
       const double yr = ys[r];
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        if (ccol[s] < cvalid)
-          *reinterpret_cast<double2*>(&W[(long long)r * ldu + u0 + ccol[s]]) =
-              make_double2(out[a][2 * s], out[a][2 * s + 1]);
-      }
+      for (int nt = 0; nt < 4; nt++) {
+        const int c = col0 + 8 * nt + 2 * tig;
+        if (c < cvalid)
+          *reinterpret_cast<double2*>(&W[(long long)r * ldu + u0 + c]) = make_double2(C[mt][nt][0], C[mt][nt][1]);
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const double v = out[a][b];
-        p_info[b] = fma(v, v, p_info[b]);
-        p_z[b] = fma(yr, v, p_z[b]);
+        for (int e = 0; e < 2; e++) {
+          const double v = C[mt][nt][e];
+          p_info[nt][e] = fma(v, v, p_info[nt][e]);
+          p_z[nt][e] = fma(yr, v, p_z[nt][e]);
+        }
       }
     }
   }
-  // column reductions over the 8 row groups, fixed order
-  __syncthreads();
+  // column reductions in a fixed order: over the 8 row groups of a warp (shuffles), then over the
+  // two row-half warps through shared memory
 #pragma unroll
-  for (int s = 0; s < 2; s++) {
-    red[g * UB + ccol[s]] = p_info[2 * s];
-    red[g * UB + ccol[s] + 1] = p_info[2 * s + 1];
-  }
-  __syncthreads();
-  double s_info = 0.0;
-  if (tid < UB)
-    for (int gg = 0; gg < 8; gg++) s_info += red[gg * UB + tid];
-  __syncthreads();
+  for (int nt = 0; nt < 4; nt++)
 #pragma unroll
-  for (int s = 0; s < 2; s++) {
-    red[g * UB + ccol[s]] = p_z[2 * s];
-    red[g * UB + ccol[s] + 1] = p_z[2 * s + 1];
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        p_info[nt][e] += __shfl_xor_sync(0xffffffffu, p_info[nt][e], o);
+        p_z[nt][e] += __shfl_xor_sync(0xffffffffu, p_z[nt][e], o);
+      }
+  __syncthreads();
+  if (gid == 0) {
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = col0 + 8 * nt + 2 * tig + e;
+        red[(0 * 2 + wr) * UB + c] = p_info[nt][e];
+        red[(1 * 2 + wr) * UB + c] = p_z[nt][e];
+      }
   }
   __syncthreads();
   if (tid < UB && u0 + tid < nu) {
-    double s_z = 0.0;
-    for (int gg = 0; gg < 8; gg++) s_z += red[gg * UB + tid];
+    const double s_info = red[0 * UB + tid] + red[1 * UB + tid];
+    const double s_z = red[2 * UB + tid] + red[3 * UB + tid];
     const double inf = fabs(s_info);                 // info = |b21 B11^-1 b12|      (dist.cpp:198)
     zu[w.off_u + u0 + tid] = s_z / sqrt(inf);        // z / sqrt(info)               (dist.cpp:200)
     info[w.off_u + u0 + tid] = inf;
@@ -623,8 +652,8 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
                     int* d_status, const int* d_skip) {
   if (n_wins == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
-  const size_t smem_panel = sizeof(double) * 2 * NB * MP;
-  const size_t smem_update = sizeof(double) * 2 * NB * NB;
+  const size_t smem_panel = sizeof(double) * 2 * NB * TS;
+  const size_t smem_update = sizeof(double) * 2 * NB * TS;
   const size_t smem_diag = sizeof(double) * (2 * NB * MP + 32 * 34 + 64);
   static bool attr_set_dev[64] = {};
   bool& attr_set = attr_set_dev[ctx->device & 63];
@@ -652,7 +681,7 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
                          const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info) {
   if (n_wins == 0 || max_nu == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
-  const size_t smem = TR_SMEM_BYTES + sizeof(double) * (size_t)(nb_max * NB + NB);
+  const size_t smem = TR_SMEM_BYTES + sizeof(double) * (size_t)(nb_max * NB + 5 * NB);
   if (smem > 227 * 1024) {
     ctx->err = "window has too many measured SNPs for trsm_finalize_kernel";
     return GB_ERR_UNSUPPORTED;
