@@ -63,73 +63,27 @@ __device__ __forceinline__ void tile64_dmma(const double* As, const double* Bs, 
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// In-place transform of a 64x64 SPD block M (lower triangle, M[c*PAD + r] = element (r, c)) into
-// inv(L), L = chol(M); L itself is never formed (nothing downstream needs it).  256 threads:
-// thread (r = tid & 63, q = tid >> 6) owns row r, columns c = q, q+4, ...
-// Step j of the right-looking factorisation and step j of the forward substitution L Y = I share
-// one pass: once column j of A has been consumed its slot holds column j of Y.
-//   rs = 1/sqrt(a_jj);  l_rj = a_rj rs
-//   row j:   Y(j,c) *= rs (c<j),  Y(j,j) = rs
-//   rows r>j: Y(r,c) -= l_rj Y(j,c) (c<j),  Y(r,j) = -l_rj rs,  A(r,c) -= l_rj l_cj (j<c<=r)
-// Two barriers per step (read phase / write phase); ~250 cycles per pivot.
-// Returns false on a non-positive / NaN pivot (flag only; a substitute pivot keeps it finite).
-constexpr int MP = NB + 2;  // even stride: double2-aligned rows for the GEMM that follows
+constexpr int MP = NB + 2;  // column stride of the 64 x 64 shared-memory blocks of the factorisation
 
-__device__ bool spd_block_to_inv_chol(double* M) {
-  const int tid = threadIdx.x;
-  const int r = tid & 63;
-  const int q = tid >> 6;
-  bool bad_any = false;
-  for (int j = 0; j < NB; j++) {
-    __syncthreads();
-    const double piv = M[j * MP + j];
-    const double a_rj = M[j * MP + r];
-    double m[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const int c = q + 4 * i;
-      m[i] = (c < j) ? M[c * MP + j] : M[j * MP + c];  // Y(j,c) for c<j, a_cj for c>j
-    }
-    __syncthreads();
-    const bool bad = !(piv > 0.0);
-    bad_any |= bad;
-    const double rs = rsqrt(bad ? 1.0 : piv);
-    if (r > j) {
-      const double l = a_rj * rs;
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const int c = q + 4 * i;
-        if (c == j) M[j * MP + r] = -l * rs;
-        else if (c < j || c <= r) M[c * MP + r] = fma(-l, m[i] * rs, M[c * MP + r]);
-      }
-    } else if (r == j) {
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const int c = q + 4 * i;
-        if (c < j) M[c * MP + j] = m[i] * rs;
-        else if (c == j) M[j * MP + j] = rs;
-      }
-    }
-  }
-  __syncthreads();
-  return !bad_any;
-}
-
-// Warp-synchronous 32x32 version of the same transform: lane r keeps row r of A (lower) and row r
-// of Y = inv(L) in registers; column j of L and row j of Y travel through two 32-double shared
+// Warp-synchronous B x B version of the same transform (B = 16): lane r < B keeps row r of A (lower)
+// and row r of Y = inv(L) in registers; column j of L and row j of Y travel through two small shared
 // buffers.  No block barrier inside, ~250 clocks per pivot.  A at Ms[(o+c)*MP + o+r]; inv(L) is
-// written (lower triangle, zeros above) to Xs at the same coordinates.
-__device__ bool invchol32_warp(const double* Ms, double* Xs, int o, double* colbuf, double* rowbuf, int lane) {
-  double a[32], y[32];
+// written (lower triangle, zeros above) to Xs at the same coordinates.  Kept out of line: the fully
+// unrolled pivot loop is straight-line code (a 32 x 32 version was 140 KB and bound by instruction
+// fetch); one 16 x 16 copy is called four times per diagonal block.
+template <int B>
+__device__ __noinline__ bool invchol_warp(const double* Ms, double* Xs, int o, double* colbuf, double* rowbuf,
+                                          int lane) {
+  double a[B], y[B];
+  const bool act = lane < B;
 #pragma unroll
-  for (int c = 0; c < 32; c++) {
-    a[c] = (c <= lane) ? Ms[(o + c) * MP + o + lane] : 0.0;
+  for (int c = 0; c < B; c++) {
+    a[c] = (act && c <= lane) ? Ms[(o + c) * MP + o + lane] : 0.0;
     y[c] = 0.0;
   }
   bool bad_any = false;
 #pragma unroll
-  for (int j = 0; j < 32; j++) {
+  for (int j = 0; j < B; j++) {
     const double piv = __shfl_sync(0xffffffffu, a[j], j);
     const bool bad = !(piv > 0.0);
     bad_any |= bad;
@@ -139,31 +93,33 @@ __device__ bool invchol32_warp(const double* Ms, double* Xs, int o, double* colb
 #pragma unroll
     for (int c = 0; c < j; c++) y[c] = is_j ? y[c] * rs : y[c];   // Y(j, c) *= rs
     if (is_j) y[j] = rs;                                          // Y(j, j) = rs
-    colbuf[lane] = l;
+    if (act) colbuf[lane] = l;
     if (is_j) {
 #pragma unroll
       for (int c = 0; c <= j; c++) rowbuf[c] = y[c];
     }
     __syncwarp();
-    const double lm = (lane > j) ? -l : 0.0;
+    const double lm = (act && lane > j) ? -l : 0.0;
 #pragma unroll
-    for (int c = j + 1; c < 32; c++) a[c] = fma(lm, colbuf[c], a[c]);   // A(r, c) -= L(r, j) L(c, j)
+    for (int c = j + 1; c < B; c++) a[c] = fma(lm, colbuf[c], a[c]);   // A(r, c) -= L(r, j) L(c, j)
 #pragma unroll
-    for (int c = 0; c <= j; c++) y[c] = fma(lm, rowbuf[c], y[c]);       // Y(r, c) -= L(r, j) Y(j, c)
+    for (int c = 0; c <= j; c++) y[c] = fma(lm, rowbuf[c], y[c]);      // Y(r, c) -= L(r, j) Y(j, c)
     __syncwarp();
   }
+  if (act) {
 #pragma unroll
-  for (int c = 0; c < 32; c++) Xs[(o + c) * MP + o + lane] = (c <= lane) ? y[c] : 0.0;
+    for (int c = 0; c < B; c++) Xs[(o + c) * MP + o + lane] = (c <= lane) ? y[c] : 0.0;
+  }
   return !bad_any;
 }
 
 // Step k, part 1: one CTA per window turns the 64x64 diagonal block into inv(L_kk) and publishes it
 // (the only form of L_kk anything downstream uses: panel blocks, y and the solve).  This is the
 // sequential critical path of the factorisation, so it runs exactly once per window and step and
-// is organised for latency: two warp-synchronous 32x32 inverse-Cholesky passes joined by three
-// small products, with A = [A11 .; A21 A22]:
-//   X11 = inv(chol(A11));  L21 = A21 X11^T;  S = A22 - L21 L21^T;  X22 = inv(chol(S));
-//   X21 = -X22 L21 X11;    inv(L_kk) = [X11 0; X21 X22]
+// is organised for latency: a right-looking factorisation over 4 x 4 blocks of 16 inside shared
+// memory -- warp 0 inverts the 16 x 16 diagonal block in registers, all 8 warps form the panel blocks
+// L_ik = A_ik inv(L_kk)^T and the trailing update -- followed by the block forward substitution
+//   X_ij = -X_ii sum_{q=j..i-1} L_iq X_qj   (i > j),   X = inv(L_kk).
 __global__ void __launch_bounds__(256)
 chol_diag_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt, double* dinv, int* status,
                  const int* __restrict__ skip, int k) {
@@ -174,13 +130,13 @@ chol_diag_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ t
   const double* A = tt + w.off_tt;
   const int ld = w.ld_t;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int H = 32;
+  constexpr int B = 16, NBLK = NB / B;
   extern __shared__ __align__(16) double sm[];
-  double* Ms = sm;                      // [64][MP] A_kk (lower), later S in its (1,1) quadrant
+  double* Ms = sm;                      // [64][MP] A_kk (lower); off-diagonal blocks become L
   double* Xs = Ms + NB * MP;            // [64][MP] inv(L_kk)
-  double* Ls = Xs + NB * MP;            // [32][34] L21, then T = L21 X11: [j*(H+2) + r]
-  double* colbuf = Ls + H * (H + 2);    // [32]
-  double* rowbuf = colbuf + H;          // [32]
+  double* Tb = Xs + NB * MP;            // [3][16][17] block temporaries of the substitution
+  double* colbuf = Tb + 3 * B * (B + 1);
+  double* rowbuf = colbuf + B;
   __shared__ int ok_s;
   const int k0 = k * NB;
   // rows/cols past n are padded with the identity
@@ -193,68 +149,63 @@ chol_diag_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ t
   }
   if (tid == 0) ok_s = 1;
   __syncthreads();
-  if (warp == 0 && !invchol32_warp(Ms, Xs, 0, colbuf, rowbuf, lane) && lane == 0) ok_s = 0;
-  __syncthreads();
-  // L21(r, c) = sum_{j<=c} A21(r, j) X11(c, j): thread -> (r = tid & 31, c = (tid >> 5) + 8 i)
-  {
-    const int r = tid & 31;
+  const int er = tid & 15, ec = (tid >> 4) & 15;   // element (er, ec) of a 16 x 16 block; one block per 256 threads
+  for (int kb = 0; kb < NBLK; kb++) {
+    const int ko = kb * B;
+    if (warp == 0 && !invchol_warp<B>(Ms, Xs, ko, colbuf, rowbuf, lane) && lane == 0) ok_s = 0;
+    __syncthreads();
+    // panel: L_ik(r, c) = sum_{j<=c} A_ik(r, j) X_kk(c, j), blocks i = kb+1 .. 3 (one element per thread and block)
+    double pv[NBLK - 1];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int c = (tid >> 5) + 8 * i;
+    for (int bi = 0; bi < NBLK - 1; bi++) {
+      const int io = (kb + 1 + bi) * B;
       double v = 0.0;
-      for (int j = 0; j <= c; j++) v = fma(Ms[j * MP + H + r], Xs[j * MP + c], v);
-      Ls[c * (H + 2) + r] = v;
+      if (kb + 1 + bi < NBLK)
+        for (int j = 0; j <= ec; j++) v = fma(Ms[(ko + j) * MP + io + er], Xs[(ko + j) * MP + ko + ec], v);
+      pv[bi] = v;
     }
-  }
-  __syncthreads();
-  // S(r, c) = A22(r, c) - sum_j L21(r, j) L21(c, j), lower triangle
-  {
-    const int r = tid & 31;
+    __syncthreads();   // every A_ik entry has been read before it is overwritten by L_ik
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int c = (tid >> 5) + 8 * i;
-      if (c <= r) {
-        double v = Ms[(H + c) * MP + H + r];
-#pragma unroll 8
-        for (int j = 0; j < H; j++) v = fma(-Ls[j * (H + 2) + r], Ls[j * (H + 2) + c], v);
-        Ms[(H + c) * MP + H + r] = v;
+    for (int bi = 0; bi < NBLK - 1; bi++)
+      if (kb + 1 + bi < NBLK) Ms[(ko + ec) * MP + (kb + 1 + bi) * B + er] = pv[bi];
+    __syncthreads();
+    // trailing update: A_ij(r, c) -= sum_q L_ik(r, q) L_jk(c, q), kb < j <= i
+    for (int i = kb + 1; i < NBLK; i++)
+      for (int j = kb + 1; j <= i; j++) {
+        double v = Ms[(j * B + ec) * MP + i * B + er];
+#pragma unroll
+        for (int q = 0; q < B; q++) v = fma(-Ms[(ko + q) * MP + i * B + er], Ms[(ko + q) * MP + j * B + ec], v);
+        Ms[(j * B + ec) * MP + i * B + er] = v;
       }
-    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (warp == 0 && !invchol32_warp(Ms, Xs, H, colbuf, rowbuf, lane) && lane == 0) ok_s = 0;
-  __syncthreads();
-  // T(r, c) = sum_{j>=c} L21(r, j) X11(j, c)   (kept in registers across the barrier, then stored over L21)
-  double tv[4];
-  {
-    const int r = tid & 31;
+  // block forward substitution for the off-diagonal blocks of X = inv(L), by block distance d = i - j
+  for (int d = 1; d < NBLK; d++) {
+    double tv[NBLK - 1];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int c = (tid >> 5) + 8 * i;
+    for (int bj = 0; bj < NBLK - 1; bj++) {      // T_ij(r, c) = sum_{q=j..i-1} sum_t L_iq(r, t) X_qj(t, c)
       double v = 0.0;
-      for (int j = c; j < H; j++) v = fma(Ls[j * (H + 2) + r], Xs[c * MP + j], v);
-      tv[i] = v;
+      if (bj + d < NBLK) {
+        const int i = bj + d;
+        for (int q = bj; q < i; q++)
+          for (int t = 0; t < B; t++) v = fma(Ms[(q * B + t) * MP + i * B + er], Xs[(bj * B + ec) * MP + q * B + t], v);
+      }
+      tv[bj] = v;
     }
-  }
-  __syncthreads();
-  {
-    const int r = tid & 31;
 #pragma unroll
-    for (int i = 0; i < 4; i++) Ls[((tid >> 5) + 8 * i) * (H + 2) + r] = tv[i];
-  }
-  __syncthreads();
-  // X21(r, c) = -sum_{kk<=r} X22(r, kk) T(kk, c)
-  {
-    const int r = tid & 31;
+    for (int bj = 0; bj < NBLK - 1; bj++)
+      if (bj + d < NBLK) Tb[bj * B * (B + 1) + ec * (B + 1) + er] = tv[bj];
+    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int c = (tid >> 5) + 8 * i;
-      double v = 0.0;
-      for (int kk = 0; kk <= r; kk++) v = fma(Xs[(H + kk) * MP + H + r], Ls[c * (H + 2) + kk], v);
-      Xs[c * MP + H + r] = -v;
-    }
+    for (int bj = 0; bj < NBLK - 1; bj++)        // X_ij(r, c) = -sum_{q<=r} X_ii(r, q) T_ij(q, c)
+      if (bj + d < NBLK) {
+        const int i = bj + d;
+        double v = 0.0;
+        for (int q = 0; q <= er; q++) v = fma(Xs[(i * B + q) * MP + i * B + er], Tb[bj * B * (B + 1) + ec * (B + 1) + q], v);
+        Xs[(bj * B + ec) * MP + i * B + er] = -v;
+      }
+    __syncthreads();
   }
-  __syncthreads();
   if (!ok_s && tid == 0) atomicOr(&status[blockIdx.x], STATUS_BREAKDOWN);
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int c = idx >> 6, r = idx & 63;
@@ -654,7 +605,7 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
   const int nb_max = (max_nt + NB - 1) / NB;
   const size_t smem_panel = sizeof(double) * 2 * NB * TS;
   const size_t smem_update = sizeof(double) * 2 * NB * TS;
-  const size_t smem_diag = sizeof(double) * (2 * NB * MP + 32 * 34 + 64);
+  const size_t smem_diag = sizeof(double) * (2 * NB * MP + 3 * 16 * 17 + 32);
   static bool attr_set_dev[64] = {};
   bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) {
