@@ -422,9 +422,11 @@ def run_gpu(args):
             clocks=clocks,
             roofline=dict(bound="tensor", kernel="gram_seg_i8_kernel", achieved=achieved, peak=tensor_peak,
                           unit="TFLOP/s", frac=achieved / tensor_peak,
-                          traffic=dict(dram_bytes_per_launch=3.676e9, algorithmic_bytes_per_launch=work["panel_bytes"] / 2 + 1.06e9,
-                                       source="profiles/r01_final_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                              "one ncu --set full capture of this workload; not re-measured by bench.py)"),
+                          traffic=3.676e9,
+                          traffic_note=("DRAM bytes per launch of this kernel on this workload (dram__bytes_read.sum + "
+                                        "dram__bytes_write.sum = 2.82 + 0.86 GB, profiles/r01_final_ncu_full.md; one ncu "
+                                        "--set full capture, not re-measured here) vs algorithmic "
+                                        f"{(work['panel_bytes'] / 2 + 1.06e9) / 1e9:.2f} GB (panel nibbles + fp64 output)"),
                           note=(f"Gram multiply-add TOP/s of the dominant kernel alone (CUDA events); algorithmic ops "
                                 f"2*N*(n_u*n_t+n_t(n_t+1)/2) summed over windows = {work['gram_ops']:.4g} per launch; "
                                 f"peak = {rate:g} x {pk['source']} sustained bf16 ({pk['bf16_tflops_sustained']} TF/s): "
