@@ -1,31 +1,29 @@
-// gb_gram.cu -- K1: segmented int8 Gram on tcgen05 tensor cores with a fused fp64 epilogue.
+// gb_gram.cu -- K1: segmented Gram on tcgen05 tensor cores with a fused fp64 fold.
 //
 // Replaces the reference's SNP-pair loops (dist.cpp:171-179,187-191; distmix.cpp:190-200,209-217;
 // computeLD.cpp:106-116) and the per-pair string walks CalCor / CalWgtCov (util.cpp:49-70,103-124).
 //
 // For a 128 x 128 tile of SNP pairs (A rows x B rows of the packed panel) the kernel streams K
-// (individuals) population by population.  Per population p ("segment") a chain of
-// tcgen05.mma.kind::i8 instructions accumulates the exact int32 counts S^p = sum_k x_ik x_jk in
-// TMEM; the epilogue warps pull the finished accumulator into registers and fold it into one
-// fp64 accumulator per matrix entry in the reference's operation order:
-//     wsumcov += (w_p * m_p/(m_p-1)) * (m_p*S^p - s^p_i*s^p_j)            (util.cpp:117-118)
-// while the tensor core already works on population p+1 (4 TMEM accumulator buffers).  After the
-// last population the low-rank mean terms, the division by the standard deviations and the
-// forced diagonal are applied and the tile is written out.
+// (individuals) population by population.  Per population p ("segment") a chain of tcgen05.mma
+// instructions (kind::i8 for int8 panels, kind::mxf4 with unit block scales for E2M1 panels)
+// accumulates the exact counts S^p = sum_k x_ik x_jk in TMEM; the epilogue warps pull the finished
+// accumulator into registers and fold it into one fp64 accumulator per matrix entry while the tensor
+// core already works on population p+1 (3-4 TMEM accumulator buffers).
 //
-// Thread-block clusters: a CM x CN cluster works on CM A tiles x CN B tiles at once (CTA rank
-// r*CN + c owns tile (r, c)).  The A tile of cluster row r is needed by its CN CTAs: each of them
-// pulls 1/CN of it from L2 and TMA-multicasts that slice to the whole row; likewise every CTA pulls
-// 1/CM of its B tile and multicasts it down its column.  A 128-byte K block therefore costs
-// 16/CN + 16/CM KiB of L2->SM traffic per CTA instead of 32 KiB (the round-1 limiter, see
-// profiles/r01_gram_ncu_full.md).  A smem stage is refilled by CM+CN-1 producers, so its "empty"
-// barrier collects one multicast tcgen05.commit arrive from every CTA of the row and the column.
-//
-// Warp roles (384 threads, 1 CTA/SM, persistent over a static list of cluster tiles):
-//   warp 0      TMA producer (one elected lane): 128-byte-swizzled row slices of the A and B tiles
+// Warp roles (384 threads, 1 CTA/SM, persistent over a static tile list):
+//   warp 0      TMA producer (one elected lane): 128-byte-swizzled [128 rows x 128 B] boxes of A and B
 //   warp 1      MMA issuer (one elected lane)
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 64*((w-4)/4)..
+//
+// The MMA issue loop is the kernel's pacemaker: tools/mma_probe.cu shows that the tensor pipe runs a
+// 128x128 MMA in 64 clocks only while tcgen05.mma instructions follow each other back to back --
+// anything the issuing thread does between them (barrier polls, constant loads, descriptor
+// arithmetic, branches on the operand kind) is NOT hidden behind the previous MMA.  The loop is
+// therefore templated on the operand kind, reads its per-segment table from shared memory, keeps the
+// descriptor as a running sum and polls the NEXT stage's barrier before issuing the current MMAs.
+// (Thread-block clusters with TMA multicast were built and measured in round 1 -- 2x1 ... 4x2, 8x1 --
+// and were slower than plain CTAs; see DESIGN.md section 7.  They are gone from the code.)
 #include "gb_common.cuh"
 #include "gb_ptx.cuh"
 
@@ -54,6 +52,8 @@ constexpr int FKIND_MXF4 = 7;     // kind::mxf4 with unit block scales, nibbles 
 constexpr int OFF_BARS = 0;                                   // mbarriers
 constexpr int N_BARS = 2 * MAX_STAGES + 2 * ACC_BUFS;
 constexpr int OFF_TMEM_PTR = OFF_BARS + N_BARS * 8;
+constexpr int OFF_SEGTAB = 256;                               // int2 [P_MAX] {first K column, K atoms} per segment
+constexpr int OFF_COEFM = OFF_SEGTAB + P_MAX * 8;             // double [P_MAX] coef_p * m_p
 constexpr int OFF_STAGES = 1024;                              // [stages][A 16 KiB | B 16 KiB]
 // fused-finish tables sit behind STAGES_FUSED stages
 constexpr int OFF_SA = OFF_STAGES + STAGES_FUSED * STAGE_BYTES; // int32 [P_MAX][128]
@@ -69,7 +69,8 @@ constexpr int SMEM_BYTES_RAW = OFF_STAGES + STAGES_RAW * STAGE_BYTES;
 constexpr int SMEM_BYTES = SMEM_BYTES_FUSED > SMEM_BYTES_RAW ? SMEM_BYTES_FUSED : SMEM_BYTES_RAW;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget exceeded");
-static_assert(OFF_TMEM_PTR + 16 <= OFF_STAGES, "barrier block overlaps the stages");
+static_assert(OFF_TMEM_PTR + 16 <= OFF_SEGTAB, "barrier block overlaps the segment table");
+static_assert(OFF_COEFM + P_MAX * 8 <= OFF_STAGES, "segment tables overlap the stages");
 
 // int32 -> double through the 2^52 trick: one LOP and one exact DADD on the fp64 pipe (64 / clk / SM)
 // instead of I2F.F64, which issues at 16 / clk / SM and was the epilogue's limiter.
@@ -83,30 +84,40 @@ __device__ __forceinline__ int f32_count_to_int(uint32_t bits) {
   return (int)__float_as_uint(f) - 0x4B400000;
 }
 
-// fp32 accumulator holding an exact NON-NEGATIVE integer -> the same value as a double, by
-// re-encoding the bits (no conversion instruction, no fp64-pipe op): exponent rebias 127 -> 1023,
-// 23 mantissa bits moved to the top of the 52.
+// fp32 accumulator holding an exact NON-NEGATIVE integer n < 2^21 -> the same value as a double, by
+// re-encoding the bits (one LEA.HI; no conversion instruction, no fp64-pipe op): exponent rebias
+// 127 -> 1023 in the high word.  An integer below 2^21 has its three lowest fp32 mantissa bits clear, so
+// the low word of the double is always zero (per-population counts are <= 4 * 6,360, pooled ones
+// 4 * 32,147).  n = 0 (bits 0) maps to 2^-127 instead of 0: absorbed by any nonzero sum, and flushed to
+// zero at the store when every count of the entry was zero.
 __device__ __forceinline__ double f32_count_to_double(uint32_t bits) {
-  const uint32_t hi = bits ? (bits >> 3) + 0x38000000u : 0u;
-  return __hiloint2double((int)hi, (int)(bits << 29));
+  return __hiloint2double((int)((bits >> 3) + 0x38000000u), 0);
 }
+constexpr double RAW_FLUSH = 1e-30;   // |raw| below this can only be a sum of the 2^-127 stand-ins
 
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 }
 
-// tm_a_*: box {128 B, 128/CN rows} (A-tile slices); tm_b_*: box {128 B, 128/CM rows} (B-tile slices);
-// *_panel reads the packed panel, *_scratch the gathered rows of non-contiguous windows.
-template <int CM, int CN>
+template <int FKIND>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t sf_tmem, uint32_t accumulate) {
+  if (FKIND == FKIND_MXF4)
+    ptx::mma_mxf4_ss(d_tmem, da, db, ptx::make_idesc_mxf4(TILE, TILE), sf_tmem, sf_tmem, accumulate);
+  else if (FKIND == FKIND_F8F6F4)
+    ptx::mma_f8f6f4_ss(d_tmem, da, db, ptx::make_idesc_f8f6f4(5, TILE, TILE), accumulate);
+  else
+    ptx::mma_i8_ss(d_tmem, da, db, ptx::make_idesc_i8(TILE, TILE), accumulate);
+}
+
+// tm_*_panel reads the packed panel, tm_*_scratch the gathered rows of non-contiguous windows
+// (boxes of {128 B, 128 rows}).
+template <int FKIND>
 __global__ void __launch_bounds__(THREADS, 1)
-gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
-                   const __grid_constant__ CUtensorMap tm_a_scratch,
-                   const __grid_constant__ CUtensorMap tm_b_panel,
-                   const __grid_constant__ CUtensorMap tm_b_scratch,
-                   const __grid_constant__ GramParams prm) {
-  constexpr int CSIZE = CM * CN;
-  constexpr int SLICE_A = TILE / CN;  // rows of the A tile this CTA fetches
-  constexpr int SLICE_B = TILE / CM;  // rows of the B tile this CTA fetches
+gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
+                const __grid_constant__ CUtensorMap tm_a_scratch,
+                const __grid_constant__ CUtensorMap tm_b_panel,
+                const __grid_constant__ CUtensorMap tm_b_scratch,
+                const __grid_constant__ GramParams prm) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSET (not by integer round trip) so the compiler keeps emitting
   // shared-space loads/stores for everything derived from it
@@ -122,20 +133,18 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
   const bool raw_out = prm.raw_out != 0;
   const int n_stages = raw_out ? STAGES_RAW : STAGES_FUSED;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
+  int2* segtab = reinterpret_cast<int2*>(smem + OFF_SEGTAB);
+  double* coefm_s = reinterpret_cast<double*>(smem + OFF_COEFM);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int n_seg = prm.n_seg;
+  const int n_ctas = gridDim.x;
 
-  const uint32_t crank = (CSIZE > 1) ? ptx::cluster_ctarank() : 0u;
-  const int cr = (int)crank / CN, cc = (int)crank % CN;
-  // CTAs that share this CTA's A tile (its cluster row) / B tile (its cluster column)
-  const uint16_t mask_row = (uint16_t)(((1u << CN) - 1u) << (cr * CN));
-  uint16_t mask_col = 0;
-#pragma unroll
-  for (int i = 0; i < CM; i++) mask_col |= (uint16_t)(1u << (i * CN + cc));
-  const int n_clusters = gridDim.x / CSIZE;
-  const int cluster_id = blockIdx.x / CSIZE;
-
+  if (threadIdx.x < n_seg) {
+    segtab[threadIdx.x] = make_int2(prm.seg[threadIdx.x].koff, prm.seg[threadIdx.x].natoms);
+    coefm_s[threadIdx.x] = prm.coefm[threadIdx.x];
+  }
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tm_a_panel);
     ptx::prefetch_tmap(&tm_a_scratch);
@@ -145,7 +154,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < MAX_STAGES; s++) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], CM + CN - 1);  // one arrive per CTA that receives this CTA's slices
+      ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < ACC_BUFS; b++) {
       ptx::mbar_init(&tfull_bar[b], 1);
@@ -159,21 +168,19 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CSIZE > 1) ptx::cluster_sync();  // every CTA's barriers are initialised before any peer signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int n_seg = prm.n_seg;
   // kind::mxf4 keeps its (all-ones) block scale factors in the last 128 TMEM columns: 3 accumulator buffers
-  const int acc_bufs = prm.fkind == FKIND_MXF4 ? ACC_BUFS - 1 : ACC_BUFS;
-  if (prm.fkind == FKIND_MXF4 && warp >= 4 && warp < 8) {
-    const uint32_t sf_addr = tmem_base + (uint32_t)((ACC_BUFS - 1) * TILE) + ((uint32_t)((warp & 3) * 32) << 16);
+  constexpr int acc_bufs = FKIND == FKIND_MXF4 ? ACC_BUFS - 1 : ACC_BUFS;
+  if (FKIND == FKIND_MXF4) {
+    if (warp >= 4 && warp < 8) {
+      const uint32_t sf_addr = tmem_base + (uint32_t)((ACC_BUFS - 1) * TILE) + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
-    for (int c = 0; c < TILE; c += 16) ptx::tmem_st_fill_32x32b_x16(sf_addr + c, 0x7F7F7F7Fu);  // E8M0 2^0
-    ptx::tmem_st_wait();
-    ptx::tc_fence_before();
-  }
-  if (prm.fkind == FKIND_MXF4) {
+      for (int c = 0; c < TILE; c += 16) ptx::tmem_st_fill_32x32b_x16(sf_addr + c, 0x7F7F7F7Fu);  // E8M0 2^0
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+    }
     __syncthreads();
     ptx::tc_fence_after();
   }
@@ -188,28 +195,24 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t stage_tx = prm.fkind == FKIND_F8F6F4 ? STAGE_BYTES / 2 : STAGE_BYTES;
-      const int kblk = prm.fkind == FKIND_MXF4 ? 2 * K_BLOCK : K_BLOCK;  // K columns per 128-byte stage row
-      for (int ct = cluster_id; ct < prm.n_tiles; ct += n_clusters) {
-        const GramTile t = prm.tiles[(long long)ct * CSIZE + crank];
-        const CUtensorMap* map_a = t.a_src ? &tm_a_scratch : &tm_a_panel;
-        const CUtensorMap* map_b = t.b_src ? &tm_b_scratch : &tm_b_panel;
-        const int a_row = t.a_row0 + cc * SLICE_A;
-        const int b_row = t.b_row0 + cr * SLICE_B;
+      // the mbarrier counts bytes as they sit in global memory (nibble-packed E2M1 rows expanded by the
+      // TMA unit complete half of what they occupy in shared memory)
+      constexpr uint32_t stage_tx = FKIND == FKIND_F8F6F4 ? STAGE_BYTES / 2 : STAGE_BYTES;
+      constexpr int kblk = FKIND == FKIND_MXF4 ? 2 * K_BLOCK : K_BLOCK;  // K columns per 128-byte stage row
+      for (int ct = blockIdx.x; ct < prm.n_tiles; ct += n_ctas) {
+        const int2 rows = *reinterpret_cast<const int2*>(&prm.tiles[ct].a_row0);   // a_row0, b_row0
+        const int2 srcs = *reinterpret_cast<const int2*>(&prm.tiles[ct].a_src);    // a_src, b_src
+        const CUtensorMap* map_a = srcs.x ? &tm_a_scratch : &tm_a_panel;
+        const CUtensorMap* map_b = srcs.y ? &tm_b_scratch : &tm_b_panel;
         for (int s = 0; s < n_seg; s++) {
-          const int koff = prm.seg[s].koff;
-          const int nblk = (prm.seg[s].natoms + 3) >> 2;
-          for (int b = 0; b < nblk; b++) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // every receiver has drained this stage
-            uint8_t* sa = smem + OFF_STAGES + stage * STAGE_BYTES + cc * (SLICE_A * K_BLOCK);
-            uint8_t* sb = smem + OFF_STAGES + stage * STAGE_BYTES + STAGE_OPERAND_BYTES + cr * (SLICE_B * K_BLOCK);
-            // own + peers' slices; the mbarrier counts bytes as they sit in global memory (nibble-packed
-            // E2M1 rows complete half of what they occupy in shared memory)
+          const int2 sg = segtab[s];
+          const int kend = sg.x + ((sg.y + 3) >> 2) * kblk;
+          for (int kcol = sg.x; kcol < kend; kcol += kblk) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // the MMAs that read this stage have retired
+            uint8_t* sa = smem + OFF_STAGES + stage * STAGE_BYTES;
             ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            if (CN > 1) ptx::tma_load_2d_mc(sa, map_a, &full_bar[stage], koff + b * kblk, a_row, mask_row);
-            else ptx::tma_load_2d(sa, map_a, &full_bar[stage], koff + b * kblk, a_row);
-            if (CM > 1) ptx::tma_load_2d_mc(sb, map_b, &full_bar[stage], koff + b * kblk, b_row, mask_col);
-            else ptx::tma_load_2d(sb, map_b, &full_bar[stage], koff + b * kblk, b_row);
+            ptx::tma_load_2d(sa, map_a, &full_bar[stage], kcol, rows.x);
+            ptx::tma_load_2d(sa + STAGE_OPERAND_BYTES, map_b, &full_bar[stage], kcol, rows.y);
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -217,63 +220,49 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    // One thread feeds the tensor core; a 128x128x32 MMA lasts 64 clocks, so the loop around it is
-    // kept to a handful of instructions: the descriptor of K atom k is the stage descriptor + 2*k
-    // (32 bytes >> 4) in its low word, and full K blocks are issued fully unrolled.
+    // One thread feeds the tensor core.  Per K block (4 instructions, 256 clocks of tensor work):
+    // one non-blocking poll of the NEXT stage's barrier, four tcgen05.mma, one commit.  The smem
+    // descriptor of K atom k is the stage descriptor + 2*k (32 bytes >> 4) in its low word.
     if (ptx::elect_one()) {
-      const int fkind = prm.fkind;
-      const uint32_t idesc = fkind == FKIND_MXF4     ? ptx::make_idesc_mxf4(TILE, TILE)
-                             : fkind == FKIND_F8F6F4 ? ptx::make_idesc_f8f6f4(5, TILE, TILE)
-                                                     : ptx::make_idesc_i8(TILE, TILE);
       const uint32_t sf_tmem = tmem_base + (uint32_t)((ACC_BUFS - 1) * TILE);
-      int stage = 0;
+      const uint64_t desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + OFF_STAGES));
+      const uint64_t desc_end = desc0 + (uint64_t)(n_stages * (STAGE_BYTES >> 4));
+      uint64_t da = desc0;
+      uint64_t* fullp = full_bar;             // barrier of the current stage
+      uint64_t* const full_end = full_bar + n_stages;
       uint32_t phase = 0;
+      bool ready = false;                     // the current stage's barrier was already seen complete
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint64_t desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + OFF_STAGES));
-      const uint16_t free_mask = mask_row | mask_col;
-      for (int ct = cluster_id; ct < prm.n_tiles; ct += n_clusters) {
+      for (int ct = blockIdx.x; ct < prm.n_tiles; ct += n_ctas) {
         for (int s = 0; s < n_seg; s++) {
-          int atoms = prm.seg[s].natoms;
+          int atoms = segtab[s].y;
           ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TILE;
           uint32_t accumulate = 0;
           for (; atoms > 0; atoms -= 4) {
-            ptx::mbar_wait(&full_bar[stage], phase);
+            if (!ready) ptx::mbar_wait(fullp, phase);
             ptx::tc_fence_after();
-            const uint64_t da = desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+            uint64_t* nextp = fullp + 1;
+            uint32_t next_phase = phase;
+            if (nextp == full_end) { nextp = full_bar; next_phase ^= 1; }
+            ready = ptx::mbar_test_wait(nextp, next_phase);   // result is needed only after the MMAs below
             const uint64_t db = da + (STAGE_OPERAND_BYTES >> 4);
             if (atoms >= 4) {
-              if (fkind == FKIND_MXF4) {
-                ptx::mma_mxf4_ss(d_tmem, da, db, idesc, sf_tmem, sf_tmem, accumulate);
-                ptx::mma_mxf4_ss(d_tmem, da + 2, db + 2, idesc, sf_tmem, sf_tmem, 1);
-                ptx::mma_mxf4_ss(d_tmem, da + 4, db + 4, idesc, sf_tmem, sf_tmem, 1);
-                ptx::mma_mxf4_ss(d_tmem, da + 6, db + 6, idesc, sf_tmem, sf_tmem, 1);
-              } else if (fkind == FKIND_F8F6F4) {
-                ptx::mma_f8f6f4_ss(d_tmem, da, db, idesc, accumulate);
-                ptx::mma_f8f6f4_ss(d_tmem, da + 2, db + 2, idesc, 1);
-                ptx::mma_f8f6f4_ss(d_tmem, da + 4, db + 4, idesc, 1);
-                ptx::mma_f8f6f4_ss(d_tmem, da + 6, db + 6, idesc, 1);
-              } else {
-                ptx::mma_i8_ss(d_tmem, da, db, idesc, accumulate);
-                ptx::mma_i8_ss(d_tmem, da + 2, db + 2, idesc, 1);
-                ptx::mma_i8_ss(d_tmem, da + 4, db + 4, idesc, 1);
-                ptx::mma_i8_ss(d_tmem, da + 6, db + 6, idesc, 1);
-              }
+              mma_ss<FKIND>(d_tmem, da, db, sf_tmem, accumulate);
+              mma_ss<FKIND>(d_tmem, da + 2, db + 2, sf_tmem, 1);
+              mma_ss<FKIND>(d_tmem, da + 4, db + 4, sf_tmem, 1);
+              mma_ss<FKIND>(d_tmem, da + 6, db + 6, sf_tmem, 1);
             } else {
-              for (int k = 0; k < atoms; k++) {
-                const uint32_t accu = accumulate | (uint32_t)k;
-                if (fkind == FKIND_MXF4) ptx::mma_mxf4_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, sf_tmem, sf_tmem, accu);
-                else if (fkind == FKIND_F8F6F4) ptx::mma_f8f6f4_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
-                else ptx::mma_i8_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
-              }
+              for (int k = 0; k < atoms; k++) mma_ss<FKIND>(d_tmem, da + 2 * k, db + 2 * k, sf_tmem, accumulate | (uint32_t)k);
             }
             accumulate = 1;
-            // frees the smem stage once these MMAs retire -- in every CTA that refills it
-            if (CSIZE > 1) ptx::mma_commit_mc(&empty_bar[stage], free_mask);
-            else ptx::mma_commit(&empty_bar[stage]);
-            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            ptx::mma_commit(fullp + MAX_STAGES);   // empty_bar[stage]: frees the smem stage once these MMAs retire
+            fullp = nextp;
+            phase = next_phase;
+            da += (uint64_t)(STAGE_BYTES >> 4);
+            if (da == desc_end) da = desc0;
           }
           ptx::mma_commit(&tfull_bar[acc]);      // accumulator of segment s is complete
           if (++acc == acc_bufs) { acc = 0; acc_phase ^= 1; }
@@ -298,7 +287,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     double* sdA = reinterpret_cast<double*>(smem + OFF_SDA);
     double* sdB = reinterpret_cast<double*>(smem + OFF_SDB);
     const int mode = prm.mode;
-    const bool f32acc = prm.fkind != 0;
+    constexpr bool f32acc = FKIND != FKIND_I8;
     // E2M1 panels (non-negative counts in fp32 accumulators) use the regrouped fold
     //   cov_ij = sum_p (coef_p m_p) S^p_ij + sum_p kappa_p s^p_i s^p_j - (sum_p w_p mu^p_i)(sum_p w_p mu^p_j),
     //   kappa_p = w_p / m_p^2 - coef_p,
@@ -309,8 +298,8 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     int acc_buf = 0;
     uint32_t acc_phase = 0;
 
-    for (int ct = cluster_id; ct < prm.n_tiles; ct += n_clusters) {
-      const GramTile t = prm.tiles[(long long)ct * CSIZE + crank];
+    for (int ct = blockIdx.x; ct < prm.n_tiles; ct += n_ctas) {
+      const GramTile t = prm.tiles[ct];
       if (t.a_valid <= 0 || t.b_valid <= 0) {
         // padding slot of a ragged cluster tile: the MMAs ran (peers need this CTA's slices and
         // barrier traffic) but nothing is stored; just hand the accumulators back
@@ -387,7 +376,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc_buf]);
           }
           if (fast) {
-            const double coefm = prm.coefm[s];
+            const double coefm = coefm_s[s];
 #pragma unroll
             for (int e = 0; e < 16; e++) acc[ch * 16 + e] = fma(coefm, f32_count_to_double(v[e]), acc[ch * 16 + e]);
             continue;
@@ -436,7 +425,7 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
           for (int e = 0; e < EPI_COLS; e++) {
             const int c = c0 + e;
             const long long gj = t.j0 + c;
-            if (c < t.b_valid && !(diag_tile && gi < gj)) out[gj * t.ld_out + gi] = acc[e];
+            if (c < t.b_valid && !(diag_tile && gi < gj)) out[gj * t.ld_out + gi] = fabs(acc[e]) < RAW_FLUSH ? 0.0 : acc[e];
           }
         }
         continue;
@@ -506,7 +495,6 @@ gram_seg_i8_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (CSIZE > 1) ptx::cluster_sync();  // no peer may still signal this CTA's barriers after it exits
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -652,56 +640,29 @@ int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_row
 
 namespace {
 
-template <int CM, int CN>
+template <int FKIND>
 int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm) {
-  constexpr int CSIZE = CM * CN;
-  auto kern = gram_seg_i8_kernel<CM, CN>;
+  auto kern = gram_seg_kernel<FKIND>;
   static bool attr_set_dev[64] = {};   // function attributes are per device
-  static int max_clusters_dev[64] = {};
   bool& attr_set = attr_set_dev[ctx->device & 63];
-  int& max_clusters = max_clusters_dev[ctx->device & 63];
-  cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CSIZE;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SMEM_ALLOC;
-  cfg.stream = ctx->stream;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   if (!attr_set) {
     GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-    if (CSIZE > 1) {
-      // how many clusters of this size the device can hold at once (GPC boundaries cost a few SMs)
-      cfg.gridDim = dim3((unsigned)(ctx->sm_count / CSIZE * CSIZE));
-      GB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-      if (max_clusters < 1) {
-        ctx->err = "device cannot co-schedule a cluster of " + std::to_string(CSIZE) + " Gram CTAs";
-        return GB_ERR_UNSUPPORTED;
-      }
-    } else {
-      max_clusters = ctx->sm_count;
-    }
     attr_set = true;
   }
-  const int n_clusters = prm.n_tiles < max_clusters ? prm.n_tiles : max_clusters;
-  cfg.gridDim = dim3((unsigned)(n_clusters * CSIZE));
-  const int ia = CN == 1 ? 0 : CN == 2 ? 1 : CN == 4 ? 2 : 3;  // A slices: 128/CN rows
-  const int ib = CM == 1 ? 0 : CM == 2 ? 1 : CM == 4 ? 2 : 3;  // B slices: 128/CM rows
-  GB_CUDA(cudaLaunchKernelEx(&cfg, kern, panel.m[ia], scratch.m[ia], panel.m[ib], scratch.m[ib], prm));
+  // persistent: one CTA per SM (229 KB of shared memory each), tiles dealt round-robin
+  const int n_ctas = prm.n_tiles < ctx->sm_count ? prm.n_tiles : ctx->sm_count;
+  kern<<<(unsigned)n_ctas, THREADS, SMEM_ALLOC, ctx->stream>>>(panel.m[0], scratch.m[0], panel.m[0], scratch.m[0], prm);
+  GB_CUDA(cudaGetLastError());
   ctx->launches++;
-  ctx->gram_clusters = n_clusters;
+  ctx->gram_clusters = n_ctas;
   return GB_OK;
 }
 
 }  // namespace
 
-bool gram_cluster_supported(int cm, int cn) {
-  return (cm == 1 && cn == 1) || (cm == 2 && cn == 1) || (cm == 2 && cn == 2) || (cm == 4 && cn == 1) ||
-         (cm == 4 && cn == 2) || (cm == 2 && cn == 4) || (cm == 8 && cn == 1);
-}
+// Round 1 built and measured CM x CN thread-block clusters with TMA multicast (2x1 ... 4x2, 8x1); all were
+// slower than independent CTAs and the code is gone: only 1 x 1 is accepted.
+bool gram_cluster_supported(int cm, int cn) { return cm == 1 && cn == 1; }
 
 int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors) {
   if (n_descriptors <= 0) return GB_OK;
@@ -718,18 +679,23 @@ int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors) {
   return GB_OK;
 }
 
-// prm.n_tiles counts CLUSTER tiles; prm.tiles holds cm*cn descriptors per cluster tile (rank order).
 int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn) {
   if (prm.n_tiles <= 0) return GB_OK;
-  if (cm == 1 && cn == 1) return launch_gram_t<1, 1>(ctx, panel, scratch, prm);
-  if (cm == 2 && cn == 1) return launch_gram_t<2, 1>(ctx, panel, scratch, prm);
-  if (cm == 2 && cn == 2) return launch_gram_t<2, 2>(ctx, panel, scratch, prm);
-  if (cm == 4 && cn == 1) return launch_gram_t<4, 1>(ctx, panel, scratch, prm);
-  if (cm == 4 && cn == 2) return launch_gram_t<4, 2>(ctx, panel, scratch, prm);
-  if (cm == 2 && cn == 4) return launch_gram_t<2, 4>(ctx, panel, scratch, prm);
-  if (cm == 8 && cn == 1) return launch_gram_t<8, 1>(ctx, panel, scratch, prm);
-  ctx->err = "unsupported Gram cluster shape";
-  return GB_ERR_UNSUPPORTED;
+  if (cm != 1 || cn != 1) {
+    ctx->err = "unsupported Gram cluster shape";
+    return GB_ERR_UNSUPPORTED;
+  }
+  if (prm.n_seg > P_MAX) {
+    ctx->err = "too many population segments for the Gram kernel";
+    return GB_ERR_UNSUPPORTED;
+  }
+  switch (prm.fkind) {
+    case FKIND_I8: return launch_gram_t<FKIND_I8>(ctx, panel, scratch, prm);
+    case FKIND_F8F6F4: return launch_gram_t<FKIND_F8F6F4>(ctx, panel, scratch, prm);
+    case FKIND_MXF4: return launch_gram_t<FKIND_MXF4>(ctx, panel, scratch, prm);
+  }
+  ctx->err = "unknown Gram operand kind";
+  return GB_ERR_BAD_ARG;
 }
 
 }  // namespace gb
