@@ -94,6 +94,11 @@ def load_library():
         "gb_batch_run_stage": (C.c_int, [vp, C.c_int]),
         "gb_batch_fetch": (C.c_int, [vp, dblp, dblp, vp]),
         "gb_batch_work": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "gb_pack2_row_bytes": (i64, [C.c_int, i32p]),
+        "gb_pack2_rows_host": (C.c_int, [C.c_int, i32p, i64, vp, i64, C.c_int, vp, i64]),
+        "gb_panel_append_pack2_host": (C.c_int, [vp, i64, vp, i64]),
+        "gb_chrom_run_pack2": (C.c_int, [vp, vp, i64, vp, i64, i64, i64p, i64p, i64p, i64p, dblp, dblp,
+                                         C.POINTER(Params), C.c_int, dblp, dblp, vp]),
         "gb_pipe_create": (C.c_int, [vp, C.c_int, i32p, i64, C.c_int, C.c_int, C.POINTER(vp)]),
         "gb_pipe_destroy": (None, [vp]),
         "gb_pipe_submit": (C.c_int, [vp, i64, vp, i64, vp, i64, C.c_int, dblp, dblp, C.POINTER(Params), dblp, dblp,
@@ -121,6 +126,32 @@ def _i64(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def pack2_row_bytes(pop_sizes) -> int:
+    """Bytes per SNP row of the 2-bit host format (gb_pack2_row_bytes)."""
+    ps = np.ascontiguousarray(pop_sizes, np.int32)
+    return int(load_library().gb_pack2_row_bytes(len(ps), _ptr(ps)))
+
+
+def pack2_rows_host(pop_sizes, rows: np.ndarray, is_ascii: bool | None = None, out: np.ndarray | None = None):
+    """HOST-side packer: [n, n_samples] int8 dosages / uint8 chars -> [n, pack2_row_bytes] uint8 (CPU threads)."""
+    lib = load_library()
+    ps = np.ascontiguousarray(pop_sizes, np.int32)
+    assert rows.ndim == 2 and rows.itemsize == 1 and (rows.size == 0 or rows.strides[1] == 1)
+    if is_ascii is None:
+        is_ascii = rows.dtype == np.uint8
+    rb = pack2_row_bytes(ps)
+    if out is None:
+        out = np.empty((rows.shape[0], rb), np.uint8)
+    assert out.shape == (rows.shape[0], rb) and (out.size == 0 or out.strides[1] == 1)
+    if rows.shape[0] == 0:
+        return out
+    rc = lib.gb_pack2_rows_host(len(ps), _ptr(ps), rows.shape[0], rows.ctypes.data, rows.strides[0],
+                                int(bool(is_ascii)), out.ctypes.data, out.strides[0])
+    if rc != GB_OK:
+        raise GaussB200Error(rc, lib.gb_status_string(rc).decode())
+    return out
 
 
 class Context:
@@ -228,6 +259,28 @@ class Panel:
         assert rows.ndim == 2 and rows.itemsize == 1
         self.ctx.check(self.ctx.lib.gb_panel_append_host(self.h, rows.shape[0], rows.ctypes.data,
                                                          rows.strides[0], int(bool(is_ascii))))
+
+    def append_pack2_host(self, rows2: np.ndarray):
+        """rows2: [n, pack2_row_bytes] uint8 rows of the 2-bit host format (E2M1 panels only)."""
+        assert rows2.ndim == 2 and rows2.dtype == np.uint8 and rows2.strides[1] == 1
+        self.ctx.check(self.ctx.lib.gb_panel_append_pack2_host(self.h, rows2.shape[0], rows2.ctypes.data,
+                                                               rows2.strides[0]))
+
+    def chrom_run_pack2(self, rows2_ptr: int, n_rows: int, row_stride: int, t_off, rows_t, u_off, rows_u, z_t,
+                        pop_wgt=None, params: Params | None = None, n_groups: int = 4, z=None, info=None):
+        """gb_chrom_run_pack2: one chromosome from pack2 HOST rows to HOST results (clears this panel)."""
+        t_off, u_off, rt, ru, zt = _i64(t_off), _i64(u_off), _i64(rows_t), _i64(rows_u), _f64(z_t)
+        w = None if pop_wgt is None else _f64(pop_wgt)
+        nw = len(t_off) - 1
+        n = int(u_off[-1])
+        z = np.zeros(n) if z is None else z
+        info = np.zeros(n) if info is None else info
+        status = np.zeros(nw, np.int32)
+        self.ctx.check(self.ctx.lib.gb_chrom_run_pack2(
+            self.ctx.h, self.h, int(n_rows), C.c_void_p(rows2_ptr), int(row_stride), nw, _ptr(t_off), _ptr(rt),
+            _ptr(u_off), _ptr(ru), _ptr(zt), _ptr(w), C.byref(params) if params else None, int(n_groups), _ptr(z),
+            _ptr(info), _ptr(status)))
+        return z, info, status
 
     def append_host_ptr(self, ptr: int, n_rows: int, row_stride: int, is_ascii: bool):
         self.ctx.check(self.ctx.lib.gb_panel_append_host(self.h, n_rows, C.c_void_p(ptr), row_stride,

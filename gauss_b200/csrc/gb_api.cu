@@ -9,6 +9,8 @@
 #include <new>
 
 #include "gb_common.cuh"
+#include <atomic>
+#include <thread>
 
 using namespace gb;
 
@@ -610,6 +612,7 @@ void gb_ctx_destroy(gb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
@@ -1038,6 +1041,253 @@ int gb_gram_counts(gb_ctx* ctx, gb_panel* panel, int64_t n_a, const int64_t* row
   }
   gb_batch_destroy(b);
   return rc;
+}
+
+
+// ---- 2-bit host panel format ("pack2") --------------------------------------------------------------
+// A dosage in {0,1,2} needs two bits; a char/int8 host row spends eight, and PCIe (~50 GB/s) is the
+// longest leg of any host-buffer path.  pack2 rows hold 4 dosages per byte at the column positions of the
+// E2M1 device row (population blocks on 128-dosage boundaries, zero padded), so the device side is a pure
+// bit expansion (expand2_rows_kernel).  This is the format a cached packed panel would be stored in.
+static int pack2_k_elems(int n_pops, const int* pop_sizes) {
+  long long k = 0;
+  for (int i = 0; i < n_pops; i++) {
+    if (pop_sizes[i] < 1) return -1;
+    k += round_up(pop_sizes[i], K_BLOCK);
+  }
+  return k > (1ll << 30) ? -1 : round_up((int)k, K_BLOCK);
+}
+
+int64_t gb_pack2_row_bytes(int n_pops, const int* pop_sizes) {
+  if (n_pops < 1 || !pop_sizes) return -1;
+  const int k = pack2_k_elems(n_pops, pop_sizes);
+  return k < 0 ? -1 : k / 4;
+}
+
+int gb_pack2_rows_host(int n_pops, const int* pop_sizes, int64_t n_rows, const void* rows, int64_t row_stride,
+                       int is_ascii, void* out, int64_t out_stride) {
+  if (n_pops < 1 || !pop_sizes || n_rows < 0 || (n_rows && (!rows || !out))) return GB_ERR_BAD_ARG;
+  const int64_t rb = gb_pack2_row_bytes(n_pops, pop_sizes);
+  int64_t n_samples = 0;
+  for (int i = 0; i < n_pops; i++) n_samples += pop_sizes[i];
+  if (rb < 0 || out_stride < rb || row_stride < n_samples) return GB_ERR_BAD_ARG;
+  const int sub = is_ascii ? 48 : 0;
+  std::atomic<int> bad{0};
+  auto work = [&](int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1; r++) {
+      const uint8_t* src = static_cast<const uint8_t*>(rows) + r * row_stride;
+      uint8_t* dst = static_cast<uint8_t*>(out) + r * out_stride;
+      std::memset(dst, 0, (size_t)rb);
+      int64_t col = 0;
+      for (int p = 0; p < n_pops; p++) {
+        const int m = pop_sizes[p];
+        uint8_t* d = dst + col / 4;
+        int j = 0;
+        for (; j + 4 <= m; j += 4) {
+          const unsigned a = (unsigned)(uint8_t)(src[j] - sub), b = (unsigned)(uint8_t)(src[j + 1] - sub),
+                         c = (unsigned)(uint8_t)(src[j + 2] - sub), e = (unsigned)(uint8_t)(src[j + 3] - sub);
+          if ((a | b | c | e) > 3u || a == 3u || b == 3u || c == 3u || e == 3u) bad.store(1, std::memory_order_relaxed);
+          d[j >> 2] = (uint8_t)((a & 3u) | ((b & 3u) << 2) | ((c & 3u) << 4) | ((e & 3u) << 6));
+        }
+        for (; j < m; j++) {
+          const unsigned a = (unsigned)(uint8_t)(src[j] - sub);
+          if (a > 2u) bad.store(1, std::memory_order_relaxed);
+          d[j >> 2] |= (uint8_t)((a & 3u) << (2 * (j & 3)));
+        }
+        src += m;
+        col += round_up(m, K_BLOCK);
+      }
+    }
+  };
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(hw ? hw : 1, n_rows / 256));
+  if (nth <= 1) {
+    work(0, n_rows);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; t++) th.emplace_back(work, n_rows * t / nth, n_rows * (t + 1) / nth);
+    for (auto& t : th) t.join();
+  }
+  return bad.load() ? GB_ERR_UNSUPPORTED : GB_OK;
+}
+
+int gb_panel_append_pack2_host(gb_panel* p, int64_t n_rows, const void* rows2, int64_t row_stride) {
+  if (!p || n_rows < 0 || (!rows2 && n_rows > 0)) {
+    if (p) p->ctx->err = "bad append arguments";
+    return GB_ERR_BAD_ARG;
+  }
+  Ctx* ctx = p->ctx;
+  if (p->format != GB_PANEL_E2M1 || row_stride < p->k_elems / 4) {
+    ctx->err = "pack2 rows need an E2M1 panel and a row stride of at least gb_pack2_row_bytes()";
+    return GB_ERR_BAD_ARG;
+  }
+  if (p->n_rows + n_rows > p->capacity) {
+    ctx->err = "panel capacity exceeded";
+    return GB_ERR_BAD_ARG;
+  }
+  if (n_rows == 0) return GB_OK;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  void* d = nullptr;
+  const size_t bytes = (size_t)n_rows * (size_t)row_stride;
+  GB_CUDA(cudaMallocAsync(&d, bytes, ctx->stream));
+  cudaError_t e = cudaMemcpyAsync(d, rows2, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    rc = launch_expand2(ctx, p, d, row_stride, p->n_rows, n_rows);
+    if (!rc) p->n_rows += n_rows;
+  } else {
+    ctx->err = cudaGetErrorString(e);
+    rc = GB_ERR_CUDA;
+  }
+  cudaFreeAsync(d, ctx->stream);
+  return rc;
+}
+
+// ---- chromosome driver on pack2 HOST rows -----------------------------------------------------------
+// One call = one chromosome (or any bp-sorted run of windows) of dist()/distmix(): the pack2 rows are copied
+// to the GPU in n_groups contiguous chunks on a copy stream; the windows are cut into n_groups contiguous,
+// cost-balanced batches, and batch g starts as soon as the rows its windows touch have landed and been
+// expanded -- so all but the last batch's kernels hide behind the PCIe copy.  Results and statuses are
+// written to HOST buffers before the call returns.
+int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void* host_rows2, int64_t row_stride,
+                       int64_t n_windows, const int64_t* t_off, const int64_t* rows_t, const int64_t* u_off,
+                       const int64_t* rows_u, const double* z_t, const double* pop_wgt, const gb_params* params,
+                       int n_groups, double* z_u, double* info_u, int* window_status) {
+  if (!ctx || !panel || n_rows < 0 || n_windows < 0 || !t_off || !u_off || (n_rows && !host_rows2) || !z_u || !info_u ||
+      n_groups < 1) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  if (panel->ctx != ctx || panel->format != GB_PANEL_E2M1 || row_stride < panel->k_elems / 4 || n_rows > panel->capacity) {
+    ctx->err = "chromosome driver needs an E2M1 panel of this context with capacity >= n_rows";
+    return GB_ERR_BAD_ARG;
+  }
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  if (!ctx->copy_stream) GB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (n_groups > n_windows) n_groups = (int)std::max<int64_t>(1, n_windows);
+  gb_panel_clear(panel);
+  panel->n_rows = n_rows;   // the batches are planned against the full row range before the rows arrive
+
+  // contiguous groups of ~equal cost (Gram ~ n_u n_t + n_t^2/2 samples, solve ~ n_t^2 n_u + n_t^3/3)
+  std::vector<double> cost((size_t)n_windows);
+  double total = 0;
+  const double N = (double)panel->n_samples;
+  for (int64_t w = 0; w < n_windows; w++) {
+    const double nt = (double)(t_off[w + 1] - t_off[w]), nu = (double)(u_off[w + 1] - u_off[w]);
+    cost[(size_t)w] = N * (nu * nt + nt * nt / 2) / 16 + 100.0 * (nt * nt * nu + nt * nt * nt / 3) + 1.0;
+    total += cost[(size_t)w];
+  }
+  std::vector<int64_t> g_lo((size_t)n_groups + 1, n_windows);
+  g_lo[0] = 0;
+  {
+    double acc = 0;
+    int g = 1;
+    for (int64_t w = 0; w < n_windows && g < n_groups; w++) {
+      acc += cost[(size_t)w];
+      if (acc >= total * g / n_groups) g_lo[(size_t)g++] = w + 1;
+    }
+  }
+  for (int g = 1; g <= n_groups; g++) g_lo[(size_t)g] = std::max(g_lo[(size_t)g], g_lo[(size_t)g - 1]);
+
+  std::vector<gb_batch*> batches((size_t)n_groups, nullptr);
+  std::vector<int64_t> need((size_t)n_groups, 0);
+  std::vector<cudaEvent_t> landed((size_t)n_groups, nullptr);
+  uint8_t* d_stage = nullptr;
+  int* h_status = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto b : batches)
+      if (b) {
+        free_batch_device(b);
+        delete b;
+      }
+    for (auto e : landed)
+      if (e) cudaEventDestroy(e);
+    if (d_stage) cudaFreeAsync(d_stage, ctx->stream);
+    if (h_status) cudaFreeHost(h_status);
+  };
+  auto fail = [&](int code) {
+    cleanup();
+    return code;
+  };
+  // plan every group first (host work + small uploads), then let copies and kernels stream
+  int64_t need_run = 0;
+  for (int g = 0; g < n_groups; g++) {
+    const int64_t w0 = g_lo[(size_t)g], w1 = g_lo[(size_t)g + 1], nw = w1 - w0;
+    std::vector<int64_t> to((size_t)nw + 1), uo((size_t)nw + 1);
+    for (int64_t i = 0; i <= nw; i++) {
+      to[(size_t)i] = t_off[w0 + i] - t_off[w0];
+      uo[(size_t)i] = u_off[w0 + i] - u_off[w0];
+    }
+    for (int64_t i = t_off[w0]; i < t_off[w1]; i++) need_run = std::max(need_run, rows_t[i] + 1);
+    for (int64_t i = u_off[w0]; i < u_off[w1]; i++) need_run = std::max(need_run, rows_u[i] + 1);
+    need[(size_t)g] = g == n_groups - 1 ? n_rows : std::min(need_run, n_rows);
+    double dummy = 0.0;
+    rc = create_batch_internal(ctx, panel, nw, to.data(), rows_t ? rows_t + t_off[w0] : nullptr, uo.data(),
+                               rows_u ? rows_u + u_off[w0] : nullptr, z_t ? z_t + t_off[w0] : &dummy, pop_wgt, params,
+                               false, false, &batches[(size_t)g], /*defer_flag_check=*/true);
+    if (rc) return fail(rc);
+    if (cudaEventCreateWithFlags(&landed[(size_t)g], cudaEventDisableTiming) != cudaSuccess) return fail(GB_ERR_CUDA);
+  }
+  size_t st_total = 0;
+  for (int g = 0; g < n_groups; g++) st_total += 2 * (size_t)(g_lo[(size_t)g + 1] - g_lo[(size_t)g]) + 3;
+  if (cudaMallocHost(reinterpret_cast<void**>(&h_status), sizeof(int) * st_total) != cudaSuccess) return fail(GB_ERR_CUDA);
+  if (n_rows) {
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_stage), (size_t)n_rows * (size_t)row_stride, ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("cudaMallocAsync(pack2 staging): ") + cudaGetErrorString(e);
+      d_stage = nullptr;
+      return fail(e == cudaErrorMemoryAllocation ? GB_ERR_OOM : GB_ERR_CUDA);
+    }
+    // the copy stream may not touch the staging buffer before the allocation is ordered
+    cudaEvent_t alloc_done;
+    if (cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming) != cudaSuccess) return fail(GB_ERR_CUDA);
+    cudaEventRecord(alloc_done, ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);
+    cudaEventDestroy(alloc_done);
+  }
+  int64_t have = 0;
+  size_t st_off = 0;
+  std::vector<size_t> st_offs((size_t)n_groups);
+  for (int g = 0; g < n_groups; g++) {
+    const int64_t lo = have, hi = need[(size_t)g];
+    if (hi > lo) {
+      cudaError_t e = cudaMemcpyAsync(d_stage + (size_t)lo * (size_t)row_stride,
+                                      static_cast<const uint8_t*>(host_rows2) + (size_t)lo * (size_t)row_stride,
+                                      (size_t)(hi - lo) * (size_t)row_stride, cudaMemcpyHostToDevice, ctx->copy_stream);
+      if (e != cudaSuccess) {
+        ctx->err = cudaGetErrorString(e);
+        return fail(GB_ERR_CUDA);
+      }
+      have = hi;
+    }
+    cudaEventRecord(landed[(size_t)g], ctx->copy_stream);
+    cudaStreamWaitEvent(ctx->stream, landed[(size_t)g], 0);
+    if (hi > lo && (rc = launch_expand2(ctx, panel, d_stage + (size_t)lo * (size_t)row_stride, row_stride, lo, hi - lo)))
+      return fail(rc);
+    gb_batch* b = batches[(size_t)g];
+    if ((rc = gb_batch_run(b))) return fail(rc);
+    const int64_t w0 = g_lo[(size_t)g];
+    st_offs[(size_t)g] = st_off;
+    if ((rc = fetch_enqueue(b, z_u + u_off[w0], info_u + u_off[w0], h_status + st_off))) return fail(rc);
+    st_off += 2 * (size_t)b->n_windows + 3;
+  }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = "chromosome driver: stream synchronisation failed";
+    return fail(GB_ERR_CUDA);
+  }
+  int worst = GB_OK;
+  for (int g = 0; g < n_groups; g++) {
+    const int64_t w0 = g_lo[(size_t)g];
+    gb_batch* b = batches[(size_t)g];
+    rc = fetch_finish(b, h_status + st_offs[(size_t)g], z_u + u_off[w0], info_u + u_off[w0],
+                      window_status ? window_status + w0 : nullptr);
+    if (rc != GB_OK && worst == GB_OK) worst = rc;
+  }
+  cleanup();
+  return worst;
 }
 
 

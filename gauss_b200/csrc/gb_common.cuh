@@ -51,6 +51,7 @@ struct GramParams {
   int fkind;             // tensor-core operand kind: 0 = int8 (kind::i8), k > 0 = kind::f8f6f4 format k-1
   int raw_out;           // 1: store the raw weighted Gram sum; gram_finalize_kernel finishes it (E2M1, mixture)
   int mirror;            // 1: also store the transposed entry (full symmetric matrix, computeLD)
+  long long* dbg;        // diagnostics only (GB_GRAM_TRACE): per-CTA stall counters, 8 per CTA; nullptr in production
   Seg seg[P_MAX];
   double coef[P_MAX];    // w_p * (m_p / (m_p - 1))          (util.cpp:117-118)
   double wgt[P_MAX];     // w_p
@@ -80,6 +81,7 @@ struct Ctx {
   int sm_count = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // lazily created: host->device copies of the chromosome driver
   std::string err;
   int64_t launches = 0;
   // lazily grown device scratch shared by the single-window entry points
@@ -136,6 +138,7 @@ struct Panel {
 // gb_pack.cu
 int launch_pack(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int is_ascii,
                 int64_t row0, int64_t n_rows);
+int launch_expand2(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int64_t row0, int64_t n_rows);
 int launch_gather_rows(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int8_t* dst);
 int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int mode,
                     const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq,

@@ -234,15 +234,32 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       bool ready = false;                     // the current stage's barrier was already seen complete
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long* const dbg = prm.dbg;
+      long long w_tempty = 0, w_full = 0, n_tempty_miss = 0, n_full_miss = 0;
+      const long long t_begin = dbg ? clock64() : 0;
       for (int ct = blockIdx.x; ct < prm.n_tiles; ct += n_ctas) {
         for (int s = 0; s < n_seg; s++) {
           int atoms = segtab[s].y;
+          if (dbg && !ptx::mbar_test_wait(&tempty_bar[acc], acc_phase ^ 1)) {
+            const long long c0 = clock64();
+            ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            w_tempty += clock64() - c0;
+            n_tempty_miss++;
+          }
           ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TILE;
           uint32_t accumulate = 0;
           for (; atoms > 0; atoms -= 4) {
-            if (!ready) ptx::mbar_wait(fullp, phase);
+            if (!ready) {
+              if (dbg && !ptx::mbar_test_wait(fullp, phase)) {
+                const long long c0 = clock64();
+                ptx::mbar_wait(fullp, phase);
+                w_full += clock64() - c0;
+                n_full_miss++;
+              }
+              ptx::mbar_wait(fullp, phase);
+            }
             ptx::tc_fence_after();
             uint64_t* nextp = fullp + 1;
             uint32_t next_phase = phase;
@@ -267,6 +284,13 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
           ptx::mma_commit(&tfull_bar[acc]);      // accumulator of segment s is complete
           if (++acc == acc_bufs) { acc = 0; acc_phase ^= 1; }
         }
+      }
+      if (dbg) {
+        dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+        dbg[blockIdx.x * 8 + 1] = w_tempty;
+        dbg[blockIdx.x * 8 + 2] = n_tempty_miss;
+        dbg[blockIdx.x * 8 + 3] = w_full;
+        dbg[blockIdx.x * 8 + 4] = n_full_miss;
       }
     }
   }
@@ -651,6 +675,20 @@ int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const 
   }
   // persistent: one CTA per SM (229 KB of shared memory each), tiles dealt round-robin
   const int n_ctas = prm.n_tiles < ctx->sm_count ? prm.n_tiles : ctx->sm_count;
+  if (getenv("GB_GRAM_TRACE")) {   // diagnostics: where the MMA thread waits (per launch, to stderr)
+    static long long* dbg = nullptr;
+    if (!dbg) GB_CUDA(cudaMallocManaged(&dbg, 1024 * 8 * sizeof(long long)));
+    GramParams p2 = prm;
+    p2.dbg = dbg;
+    kern<<<(unsigned)n_ctas, THREADS, SMEM_ALLOC, ctx->stream>>>(panel.m[0], scratch.m[0], panel.m[0], scratch.m[0], p2);
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double sum[8] = {};
+    for (int i = 0; i < n_ctas; i++) for (int k = 0; k < 8; k++) sum[k] += (double)dbg[i * 8 + k] / n_ctas;
+    fprintf(stderr, "[gram trace] CTAs %d tiles %d segs %d | mma thread total %.0f clk | tempty misses %.0f (%.0f clk) | full misses %.0f (%.0f clk)\n",
+            n_ctas, prm.n_tiles, prm.n_seg, sum[0], sum[2], sum[1], sum[4], sum[3]);
+    ctx->launches++;
+    return GB_OK;
+  }
   kern<<<(unsigned)n_ctas, THREADS, SMEM_ALLOC, ctx->stream>>>(panel.m[0], scratch.m[0], panel.m[0], scratch.m[0], prm);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;

@@ -89,6 +89,57 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
     *reinterpret_cast<uint32_t*>(d + j) = 0u;
 }
 
+
+// 2-bit host rows ("pack2": 4 dosages per byte, low bits = lower K index, the same column positions as the
+// E2M1 panel row) -> E2M1 nibbles plus per-population sum x, sum x^2.  One CTA per row; warp w expands
+// populations w, w+8, ...; a lane turns one 32-bit word (16 dosages) into one 64-bit word of nibbles.
+// Code c in {0,1,2} is dosage c and E2M1 nibble c << 1; code 3 is not a dosage the format holds (flagged).
+// PCIe carries a quarter of the bytes a char/int8 row needs.
+__global__ void __launch_bounds__(256)
+expand2_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int8_t* __restrict__ dst, int k_stride,
+                    long long row0, int n_pops, const int* __restrict__ pop_sizes, const int* __restrict__ koff,
+                    int32_t* __restrict__ sx, int32_t* __restrict__ sxx, long long stat_ld, int* flags, int seg_align) {
+  const long long row = blockIdx.x;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src + row * src_stride);
+  uint2* d = reinterpret_cast<uint2*>(dst + (row0 + row) * (long long)k_stride);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t bad = 0;
+  for (int p = warp; p < n_pops; p += 8) {
+    const int w0 = koff[p] >> 4;                                               // first 16-dosage word of the block
+    const int nw = ((pop_sizes[p] + seg_align - 1) / seg_align * seg_align) >> 4;
+    int ones = 0, twos = 0;
+    for (int j = lane; j < nw; j += 32) {
+      const uint32_t w = s[w0 + j];
+      const uint32_t b0 = w & 0x55555555u, b1 = (w >> 1) & 0x55555555u;
+      bad |= b0 & b1;
+      ones += __popc(b0);
+      twos += __popc(b1);
+      uint32_t h[2] = {w & 0xFFFFu, w >> 16};
+#pragma unroll
+      for (int q = 0; q < 2; q++) {   // spread eight 2-bit codes over eight nibbles, then code -> code << 1
+        uint32_t t = (h[q] | (h[q] << 8)) & 0x00FF00FFu;
+        t = (t | (t << 4)) & 0x0F0F0F0Fu;
+        t = (t | (t << 2)) & 0x33333333u;
+        h[q] = t << 1;
+      }
+      d[w0 + j] = make_uint2(h[0], h[1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ones += __shfl_xor_sync(0xffffffffu, ones, o);
+      twos += __shfl_xor_sync(0xffffffffu, twos, o);
+    }
+    if (lane == 0) {
+      sx[(long long)p * stat_ld + row0 + row] = ones + 2 * twos;
+      sxx[(long long)p * stat_ld + row0 + row] = ones + 4 * twos;
+    }
+  }
+  if (bad) atomicOr(flags, 1);
+  const int k_end = koff[n_pops - 1] + (pop_sizes[n_pops - 1] + seg_align - 1) / seg_align * seg_align;
+  for (int j = (k_end >> 1) + threadIdx.x * 4; j < k_stride; j += 256 * 4)
+    *reinterpret_cast<uint32_t*>(dst + (row0 + row) * (long long)k_stride + j) = 0u;
+}
+
 // dst[i] = panel row rows[i]; 16-byte vectors, one CTA per row.
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const int8_t* __restrict__ panel, int k_stride, const int32_t* __restrict__ rows,
@@ -162,6 +213,16 @@ int launch_pack(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride,
         static_cast<const uint8_t*>(dev_src), src_stride, is_ascii, panel->d_rows, panel->k_elems, panel->k_stride,
         row0, panel->n_pops, panel->d_pop_sizes, panel->d_koff, panel->d_sx, panel->d_sxx, panel->capacity,
         panel->d_flags, panel->seg_align);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+int launch_expand2(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int64_t row0, int64_t n_rows) {
+  if (n_rows <= 0) return GB_OK;
+  expand2_rows_kernel<<<(unsigned)n_rows, 256, 0, ctx->stream>>>(
+      static_cast<const uint8_t*>(dev_src), src_stride, panel->d_rows, panel->k_stride, row0, panel->n_pops,
+      panel->d_pop_sizes, panel->d_koff, panel->d_sx, panel->d_sxx, panel->capacity, panel->d_flags, panel->seg_align);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

@@ -165,6 +165,30 @@ GB_API int gb_batch_work(const gb_batch *batch, double *gram_ops, double *solve_
  * kernel / finish pass). */
 GB_API int gb_batch_run_stage(gb_batch *batch, int stage);
 
+/* ---- 2-bit host rows ("pack2") and the chromosome driver ---------------------------------------- */
+/* The packed-panel step the north star hangs off ReadGenotype (gauss.cpp:720-785): a dosage in {0,1,2} is
+ * stored in two bits, 4 per byte (low bits = lower individual), population blocks on 128-dosage boundaries
+ * and zero padded -- the column positions of the E2M1 device row, so the GPU side is a pure bit expansion
+ * and PCIe carries a quarter of the bytes of a char row.  This is also the layout a cached on-disk packed
+ * panel would use. */
+GB_API int64_t gb_pack2_row_bytes(int n_pops, const int *pop_sizes);
+/* HOST-side packer (CPU threads; formatting only, no statistics): rows as in gb_panel_append_host ->
+ * pack2 rows at out + r*out_stride.  GB_ERR_UNSUPPORTED if a dosage outside {0,1,2} is met (keep such a
+ * panel as char/int8 rows). */
+GB_API int gb_pack2_rows_host(int n_pops, const int *pop_sizes, int64_t n_rows, const void *rows,
+                       int64_t row_stride, int is_ascii, void *out, int64_t out_stride);
+/* Append pack2 rows (HOST memory) to a GB_PANEL_E2M1 panel: copy + expand2_rows_kernel. */
+GB_API int gb_panel_append_pack2_host(gb_panel *panel, int64_t n_rows, const void *rows2, int64_t row_stride);
+/* One chromosome (any bp-sorted run of windows) of dist()/distmix() from pack2 HOST rows to HOST results:
+ * `panel` (E2M1, capacity >= n_rows) is cleared and refilled; the rows travel in n_groups chunks on a copy
+ * stream while the windows -- cut into n_groups contiguous cost-balanced batches -- run as soon as the rows
+ * they touch have landed.  Arguments as gb_batch_create; window_status (optional) receives one status per
+ * window; returns the first non-OK window status otherwise.  Synchronous. */
+GB_API int gb_chrom_run_pack2(gb_ctx *ctx, gb_panel *panel, int64_t n_rows, const void *host_rows2,
+                       int64_t row_stride, int64_t n_windows, const int64_t *t_off, const int64_t *rows_t,
+                       const int64_t *u_off, const int64_t *rows_u, const double *z_t, const double *pop_wgt,
+                       const gb_params *params, int n_groups, double *z_u, double *info_u, int *window_status);
+
 /* ---- pipelined single windows, host in / host out ---------------------------------------------- */
 /* What a genome loop over dist()/distmix() calls (dist.cpp:63-75 runs one window per call): the
  * host->device copy of window w+1 overlaps the kernels of window w.  `depth` device slots of
