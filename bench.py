@@ -10,7 +10,7 @@ PGC2_Chr22_ilmn1M_Z.txt, ~3,700 synthetic unmeasured sites per Mb, 21 flagged po
          K2 Cholesky/solve; device-timed with CUDA events, max over ranks)
   e2e    the same metric through the per-window C-ABI call with HOST buffers: pinned-host
          genotype rows -> H2D -> pack -> window -> D2H of (z, info), every window, every step
-  roofline  K1 (gram_seg_i8_kernel): algorithmic int8 ops / measured launch time vs int8 peak
+  roofline  K1 (gram_seg_kernel): algorithmic int8 ops / measured launch time vs int8 peak
   cpu_baseline / --impl reference  the reference's own CPU code path (oracle/_ref when built,
          else the C restatement) on a bounded sample of the same workload, 1 host core (the
          reference is single-threaded by construction)
@@ -320,27 +320,34 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident path: W warm-up steps, then K timed steps with per-stage events
+    # ---- resident path: W warm-up steps, then K timed steps of the product call (gb_batch_run: the factorisation
+    # overlaps the B21 part of the Gram kernel on a side stream; both join before the solve, so events on the
+    # launching stream bracket all of it)
     for _ in range(args.warmup):
         batch.run()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ctx.launch_count
-    STAGES = [0, 10, 11, 2, 3]   # row statistics | Gram tensor-core kernel | Gram finish pass | Cholesky | solve
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(STAGES) + 1)] for _ in range(args.steps)]
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(stream)
     for k in range(args.steps):
-        for i, s in enumerate(STAGES):
-            evs[k][i].record(stream)
-            batch.run_stage(s)
-        evs[k][len(STAGES)].record(stream)
+        batch.run()
     e_end.record(stream)
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     total_ms = e_start.elapsed_time(e_end)
+    # ---- the same K steps stage by stage (serialised, every kernel on all SMs): per-stage times and the
+    # dominant kernel's own launch duration for the roofline
+    STAGES = [0, 10, 11, 2, 3]   # row statistics | Gram tensor-core kernel | Gram finish pass | Cholesky | solve
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(STAGES) + 1)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        for i, s in enumerate(STAGES):
+            evs[k][i].record(stream)
+            batch.run_stage(s)
+        evs[k][len(STAGES)].record(stream)
+    torch.cuda.synchronize()
     stage_ms = np.array([[evs[k][s].elapsed_time(evs[k][s + 1]) for s in range(len(STAGES))]
                          for k in range(args.steps)])
     z, info, status = batch.fetch()
@@ -465,7 +472,7 @@ def run_gpu(args):
                                      "the seam run_distmix sees today (one window per call, 8 bits per dosage over PCIe)"),
             gpu_launches=int(launches),
             clocks=clocks,
-            roofline=dict(bound="tensor", kernel="gram_seg_i8_kernel", achieved=achieved, peak=tensor_peak,
+            roofline=dict(bound="tensor", kernel="gram_seg_kernel", achieved=achieved, peak=tensor_peak,
                           unit="TFLOP/s", frac=achieved / tensor_peak,
                           traffic=3.676e9,
                           traffic_note=("DRAM bytes per launch of this kernel on this workload (dram__bytes_read.sum + "
@@ -478,6 +485,7 @@ def run_gpu(args):
                                 f"the kernel's MMA kind for {fmt} panels nominally runs at {rate:g} x the bf16 rate and "
                                 f"MEASURED_PEAKS.json has no entry for it; against the int8 rate (2 x bf16) the same "
                                 f"number is {achieved / (2.0 * pk['bf16_tflops_sustained']):.3f}")),
+            stage_ms_serial=float(stage_ms.sum(1).mean()),
             stage_ms=dict(row_stats=float(stage_ms[:, 0].mean()), gram=gram_ms,
                           gram_finish=float(stage_ms[:, 2].mean()), cholesky=float(stage_ms[:, 3].mean()),
                           solve=float(stage_ms[:, 4].mean())),

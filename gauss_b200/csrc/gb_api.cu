@@ -35,7 +35,9 @@ struct gb_batch {
   std::vector<int> plan_status;       // per window: GB_OK or a TOO_FEW_* code (window skipped)
   std::vector<int> active;            // window ids that run
   std::vector<SolveWin> h_wins;       // aligned with `active`
-  std::vector<GramTile> h_tiles;
+  std::vector<GramTile> h_tiles;      // [B11 tiles of all windows | B21 tiles of all windows]
+  int n_tiles_tt = 0;                 // length of the B11 part
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // factorisation runs beside the B21 part (gb_batch_run)
   int64_t n_gather = 0;
   int n_chol_wins = 0, max_nt = 0, max_nu = 0;
   double work_gram_ops = 0, work_solve_flops = 0, work_panel_bytes = 0;
@@ -98,6 +100,9 @@ void free_batch_device(gb_batch* b) {
                   b->d_scratch};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, b->ctx->stream);
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_join) cudaEventDestroy(b->ev_join);
+  b->ev_fork = b->ev_join = nullptr;
 }
 
 int unrepresentable(Ctx* ctx) {
@@ -186,6 +191,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   // ---- windows
   b->plan_status.assign((size_t)nw, GB_OK);
   std::vector<int32_t> h_gather;
+  std::vector<GramTile> h_tiles_tt, h_tiles_ut;
   const double N = (double)pn->n_samples;
   for (int64_t w = 0; w < nw; w++) {
     const int64_t nt = b->t_off[w + 1] - b->t_off[w];
@@ -270,37 +276,14 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
       }
       return t;
     };
-    // Cluster tiles: the window's A blocks (measured blocks of the B11 lower triangle first, then the
-    // unmeasured blocks of B21) are taken CM at a time against CN measured B blocks.  A-chunk outer /
-    // B-group inner keeps concurrently running clusters on the same A rows (L2 reuse).  Slots with
-    // no work (ragged edges, blocks above the diagonal) keep valid operand coordinates -- their
-    // CTAs still feed the multicast -- but are marked a_valid = 0 so nothing is stored.
-    struct Blk { bool is_u; int bi; };
-    std::vector<Blk> alist;
+    // Tiles: the B11 lower-triangle tiles of every window go to the FRONT part of the list (h_tiles_tt), the
+    // B21 tiles behind them, so the factorisation can start once the front part is done (gb_batch_run).
+    // Within a window: A block outer / B block inner keeps concurrently running CTAs on the same A rows.
     if (!b->counts_mode)
-      for (int bi = 0; bi < nbt; bi++) alist.push_back(Blk{false, bi});
-    for (int bi = 0; bi < nbu; bi++) alist.push_back(Blk{true, bi});
-    const int CM = b->cm, CN = b->cn;
-    for (size_t a0 = 0; a0 < alist.size(); a0 += (size_t)CM) {
-      for (int jg = 0; jg * CN < nbt; jg++) {
-        GramTile slot[16];
-        bool any = false;
-        for (int r = 0; r < CM; r++) {
-          const bool a_ok = a0 + r < alist.size();
-          const Blk a = alist[std::min(a0 + r, alist.size() - 1)];
-          for (int c = 0; c < CN; c++) {
-            const int bj = jg * CN + c;
-            const bool b_ok = bj < nbt;
-            GramTile t = make_tile(a.is_u, a.bi, std::min(bj, nbt - 1));
-            const bool live = a_ok && b_ok && (a.is_u || bj <= a.bi);
-            if (!live) t.a_valid = 0;
-            any |= live;
-            slot[r * CN + c] = t;
-          }
-        }
-        if (any) b->h_tiles.insert(b->h_tiles.end(), slot, slot + CM * CN);
-      }
-    }
+      for (int bi = 0; bi < nbt; bi++)
+        for (int bj = 0; bj <= bi; bj++) h_tiles_tt.push_back(make_tile(false, bi, bj));
+    for (int bi = 0; bi < nbu; bi++)
+      for (int bj = 0; bj < nbt; bj++) h_tiles_ut.push_back(make_tile(true, bi, bj));
     if (!b->counts_mode) {
       // algorithmic work, SURVEY.md §8(d)
       const double dnt = (double)nt, dnu = (double)nu;
@@ -310,6 +293,9 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     }
   }
   b->n_gather = (int64_t)h_gather.size();
+  b->n_tiles_tt = (int)h_tiles_tt.size();
+  b->h_tiles = std::move(h_tiles_tt);
+  b->h_tiles.insert(b->h_tiles.end(), h_tiles_ut.begin(), h_tiles_ut.end());
   {
     // heaviest windows first: the solve kernels map blockIdx.y to this list, and a window's cost
     // grows with n_t^2, so this is longest-processing-time-first scheduling of their CTAs
@@ -393,7 +379,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   }
 
   gp.tiles = b->d_tiles;
-  gp.n_tiles = (int)(b->h_tiles.size() / (size_t)(b->cm * b->cn));
+  gp.n_tiles = (int)b->h_tiles.size();
   gp.st_sx_t = b->d_st_sx_t;
   gp.st_sx_u = b->d_st_sx_u;
   gp.st_mean_t = b->d_st_mean_t;
@@ -435,11 +421,11 @@ int run_stage(gb_batch* b, int stage) {
                              b->d_pool_u, nullptr, b->d_st_sx_u, b->d_st_mean_u);
     }
     case 1:
-      if ((rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn)))
+      if ((rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn, 0)))
         return rc;
       return b->gp.raw_out ? launch_gram_finalize(ctx, b->gp, (int)b->h_tiles.size()) : GB_OK;
     case 10:  // profiling: the tensor-core kernel alone
-      return launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn);
+      return launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn, 0);
     case 11:  // profiling: the finish pass alone (a no-op for panels whose finish is fused)
       return b->gp.raw_out ? launch_gram_finalize(ctx, b->gp, (int)b->h_tiles.size()) : GB_OK;
     case 2: {
@@ -584,6 +570,7 @@ int gb_ctx_create(int device, gb_ctx** out) {
     if (!strcmp(e, "int8")) ctx->panel_format = GB_PANEL_INT8;
     else if (!strcmp(e, "e2m1")) ctx->panel_format = GB_PANEL_E2M1;
   }
+  if (const char* e = getenv("GB_CHOL_SMS")) ctx->chol_sms = atoi(e);   // tuning knob; 0 = no overlap
   if (const char* e = getenv("GB_GRAM_KIND")) ctx->e2m1_mxf4 = strcmp(e, "f8f6f4") != 0;
   if (const char* e = getenv("GB_GRAM_CLUSTER")) {  // tuning knob: "CMxCN", e.g. 2x2
     int cm = 0, cn = 0;
@@ -613,6 +600,7 @@ void gb_ctx_destroy(gb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   delete ctx;
 }
 
@@ -819,13 +807,59 @@ void gb_batch_destroy(gb_batch* b) {
   delete b;
 }
 
+// Gram kernel + finish pass over tiles [first, first + count) of the batch's list, on at most max_ctas SMs
+// (0 = all of them).
+static int run_gram_range(gb_batch* b, int first, int count, int max_ctas) {
+  if (count <= 0) return GB_OK;
+  Ctx* ctx = b->ctx;
+  Panel* pn = b->panel;
+  GramParams gp = b->gp;
+  gp.tiles = b->gp.tiles + first;
+  gp.n_tiles = count;
+  int rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, gp, b->cm, b->cn, max_ctas);
+  if (rc) return rc;
+  return gp.raw_out ? launch_gram_finalize(ctx, gp, count) : GB_OK;
+}
+
+// Whole pipeline of the batch.  The Cholesky chain of stage 2 is a latency-bound sequence of small launches
+// (three per 64-column block step) that needs B11 only, and B11 is a tenth of the Gram work: the B11 tiles run
+// first on every SM, then the factorisation runs on a side stream next to the B21 tiles, which leave
+// `chol_sms` SMs free for it (the Gram kernel is persistent with one CTA per SM).  Both join before the solve.
 int gb_batch_run(gb_batch* b) {
   if (!b) return GB_ERR_BAD_ARG;
-  for (int s = 0; s < 4; s++) {
-    int rc = run_stage(b, s);
-    if (rc) return rc;
+  Ctx* ctx = b->ctx;
+  const int n_all = (int)b->h_tiles.size(), n_tt = b->n_tiles_tt;
+  const bool overlap = !b->ld_mode && !b->counts_mode && ctx->chol_sms > 0 && n_tt > 0 && n_all - n_tt >= ctx->sm_count &&
+                       ctx->sm_count > 2 * ctx->chol_sms;
+  if (!overlap) {
+    for (int s = 0; s < 4; s++) {
+      int rc = run_stage(b, s);
+      if (rc) return rc;
+    }
+    return GB_OK;
   }
-  return GB_OK;
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  if (!ctx->side_stream) GB_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  if (!b->ev_fork) {
+    GB_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    GB_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+  }
+  if ((rc = run_stage(b, 0))) return rc;
+  if ((rc = run_gram_range(b, 0, n_tt, 0))) return rc;
+  GB_CUDA(cudaEventRecord(b->ev_fork, ctx->stream));
+  GB_CUDA(cudaStreamWaitEvent(ctx->side_stream, b->ev_fork, 0));
+  // B21 tiles first in launch order, so their persistent CTAs own their SMs before the factorisation's
+  // many small CTAs arrive
+  if ((rc = run_gram_range(b, n_tt, n_all - n_tt, ctx->sm_count - ctx->chol_sms))) return rc;
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->side_stream;
+  rc = run_stage(b, 2);
+  ctx->stream = main_stream;
+  if (rc) return rc;
+  GB_CUDA(cudaEventRecord(b->ev_join, ctx->side_stream));
+  GB_CUDA(cudaStreamWaitEvent(ctx->stream, b->ev_join, 0));
+  return run_stage(b, 3);
 }
 
 int gb_batch_run_stage(gb_batch* b, int stage) {

@@ -81,6 +81,8 @@ struct Ctx {
   int sm_count = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;   // lazily created: the factorisation beside the B21 Gram tiles (gb_batch_run)
+  int chol_sms = 48;                    // SMs the B21 Gram launch leaves to it (GB_CHOL_SMS; 0 = run the stages one after another)
   cudaStream_t copy_stream = nullptr;   // lazily created: host->device copies of the chromosome driver
   std::string err;
   int64_t launches = 0;
@@ -149,7 +151,8 @@ int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_row
                          int64_t k_stride_bytes, int format);
 bool gram_cluster_supported(int cm, int cn);
 int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors);
-int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn);
+int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn,
+                int max_ctas);
 
 // gb_solve.cu
 struct SolveWin {        // per-window solve descriptor

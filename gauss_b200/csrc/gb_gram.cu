@@ -665,7 +665,7 @@ int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_row
 namespace {
 
 template <int FKIND>
-int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm) {
+int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int max_ctas) {
   auto kern = gram_seg_kernel<FKIND>;
   static bool attr_set_dev[64] = {};   // function attributes are per device
   bool& attr_set = attr_set_dev[ctx->device & 63];
@@ -674,7 +674,8 @@ int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const 
     attr_set = true;
   }
   // persistent: one CTA per SM (229 KB of shared memory each), tiles dealt round-robin
-  const int n_ctas = prm.n_tiles < ctx->sm_count ? prm.n_tiles : ctx->sm_count;
+  const int cap = max_ctas > 0 && max_ctas < ctx->sm_count ? max_ctas : ctx->sm_count;
+  const int n_ctas = prm.n_tiles < cap ? prm.n_tiles : cap;
   if (getenv("GB_GRAM_TRACE")) {   // diagnostics: where the MMA thread waits (per launch, to stderr)
     static long long* dbg = nullptr;
     if (!dbg) GB_CUDA(cudaMallocManaged(&dbg, 1024 * 8 * sizeof(long long)));
@@ -717,7 +718,8 @@ int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors) {
   return GB_OK;
 }
 
-int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn) {
+int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn,
+                int max_ctas) {
   if (prm.n_tiles <= 0) return GB_OK;
   if (cm != 1 || cn != 1) {
     ctx->err = "unsupported Gram cluster shape";
@@ -728,9 +730,9 @@ int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const Gr
     return GB_ERR_UNSUPPORTED;
   }
   switch (prm.fkind) {
-    case FKIND_I8: return launch_gram_t<FKIND_I8>(ctx, panel, scratch, prm);
-    case FKIND_F8F6F4: return launch_gram_t<FKIND_F8F6F4>(ctx, panel, scratch, prm);
-    case FKIND_MXF4: return launch_gram_t<FKIND_MXF4>(ctx, panel, scratch, prm);
+    case FKIND_I8: return launch_gram_t<FKIND_I8>(ctx, panel, scratch, prm, max_ctas);
+    case FKIND_F8F6F4: return launch_gram_t<FKIND_F8F6F4>(ctx, panel, scratch, prm, max_ctas);
+    case FKIND_MXF4: return launch_gram_t<FKIND_MXF4>(ctx, panel, scratch, prm, max_ctas);
   }
   ctx->err = "unknown Gram operand kind";
   return GB_ERR_BAD_ARG;
