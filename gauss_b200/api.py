@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 import re
 
@@ -87,6 +88,8 @@ def load_library():
         "gb_window_distmix": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, dblp, C.POINTER(Params), dblp, dblp]),
         "gb_window_ld": (C.c_int, [vp, vp, i64, i64p, dblp, dblp]),
         "gb_window_cor": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, C.POINTER(Params), dblp, dblp]),
+        "gb_window_qcat": (C.c_int, [vp, vp, i64, i64p, dblp, i64, i64, i64, i64p, dblp, C.POINTER(Params), C.c_double,
+                                     C.POINTER(C.c_int), dblp, dblp, dblp, dblp]),
         "gb_batch_create": (C.c_int, [vp, vp, i64, i64p, i64p, i64p, i64p, dblp, dblp, C.POINTER(Params),
                                       C.POINTER(vp)]),
         "gb_batch_destroy": (None, [vp]),
@@ -166,6 +169,7 @@ class Context:
                                  self.lib.gb_status_string(rc).decode())
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()   # panels / batches / pipes: destroyed before the context they point into
 
     def check(self, rc: int, allow=()):
         if rc != GB_OK and rc not in allow:
@@ -185,6 +189,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(getattr(self, "_children", ())):
+                child.close()
             self.lib.gb_ctx_destroy(self.h)
             self.h = None
 
@@ -235,6 +241,7 @@ class Panel:
             ctx.check(ctx.lib.gb_panel_create_fmt(ctx.h, len(self.pop_sizes), _ptr(self.pop_sizes),
                                                   int(capacity_rows), PANEL_FORMATS[fmt], C.byref(h)))
         self.h = h
+        self.ctx._children.add(self)
 
     @property
     def format(self) -> str:
@@ -292,7 +299,8 @@ class Panel:
 
     def close(self):
         if getattr(self, "h", None):
-            self.ctx.lib.gb_panel_destroy(self.h)
+            if getattr(self.ctx, "h", None):     # a closed context has already taken its children with it
+                self.ctx.lib.gb_panel_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -343,6 +351,20 @@ class Panel:
         self.ctx.check(rc, allow)
         return z, info, rc
 
+    def window_qcat(self, rows_t, z_t, core_first, n_core, rows_u, pop_wgt=None, params: Params | None = None,
+                    eig_cutoff: float = 0.01, allow=()):
+        """gb_window_qcat: qcat (pop_wgt None) / qcatmix.  -> dict(rc, num_eig, t_m, chisq_m, t_u, chisq_u)."""
+        rt, ru, zt = _i64(rows_t), _i64(rows_u), _f64(z_t)
+        w = None if pop_wgt is None else _f64(pop_wgt)
+        t_m, c_m = np.zeros(n_core), np.zeros(n_core)
+        t_u, c_u = np.zeros(len(ru)), np.zeros(len(ru))
+        ne = C.c_int(0)
+        rc = self.ctx.lib.gb_window_qcat(self.ctx.h, self.h, len(rt), _ptr(rt), _ptr(zt), int(core_first), int(n_core),
+                                         len(ru), _ptr(ru), _ptr(w), C.byref(params) if params else None,
+                                         float(eig_cutoff), C.byref(ne), _ptr(t_m), _ptr(c_m), _ptr(t_u), _ptr(c_u))
+        self.ctx.check(rc, allow)
+        return dict(rc=rc, num_eig=ne.value, t_m=t_m, chisq_m=c_m, t_u=t_u, chisq_u=c_u)
+
     def window_ld(self, rows, pop_wgt, allow=()):
         r, w = _i64(rows), _f64(pop_wgt)
         cm = np.zeros((len(r), len(r)))
@@ -366,6 +388,7 @@ class Batch:
             self.ctx.h, panel.h, self.n_windows, _ptr(self.t_off), _ptr(self.rows_t), _ptr(self.u_off),
             _ptr(self.rows_u), _ptr(self.z_t), _ptr(self.w), C.byref(params) if params else None, C.byref(h)))
         self.h = h
+        self.ctx._children.add(self)
 
     def run(self):
         self.ctx.check(self.ctx.lib.gb_batch_run(self.h))
@@ -388,7 +411,8 @@ class Batch:
 
     def close(self):
         if getattr(self, "h", None):
-            self.ctx.lib.gb_batch_destroy(self.h)
+            if getattr(self.ctx, "h", None):     # a closed context has already taken its children with it
+                self.ctx.lib.gb_batch_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -408,6 +432,7 @@ class Pipe:
         ctx.check(ctx.lib.gb_pipe_create(ctx.h, len(self.pop_sizes), _ptr(self.pop_sizes), int(max_rows_per_window),
                                          int(depth), -1 if fmt is None else PANEL_FORMATS[fmt], C.byref(h)))
         self.h = h
+        self.ctx._children.add(self)
         self._keep = {}
 
     def submit_ptr(self, ptr_t: int, n_t: int, ptr_u: int, n_u: int, row_stride: int, is_ascii: bool, z_t, pop_wgt,
@@ -443,7 +468,8 @@ class Pipe:
 
     def close(self):
         if getattr(self, "h", None):
-            self.ctx.lib.gb_pipe_destroy(self.h)
+            if getattr(self.ctx, "h", None):     # a closed context has already taken its children with it
+                self.ctx.lib.gb_pipe_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -37,6 +37,7 @@ struct gb_batch {
   std::vector<SolveWin> h_wins;       // aligned with `active`
   std::vector<GramTile> h_tiles;      // [B11 tiles of all windows | B21 tiles of all windows]
   int n_tiles_tt = 0;                 // length of the B11 part
+  double* d_y = nullptr;              // qcat only: y = L^-1 Z1 written by the solve kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // factorisation runs beside the B21 part (gb_batch_run)
   int64_t n_gather = 0;
   int n_chol_wins = 0, max_nt = 0, max_nu = 0;
@@ -97,7 +98,7 @@ void free_batch_device(gb_batch* b) {
                   b->d_st_sx_t, b->d_st_sx_u, b->d_st_mean_t, b->d_st_mean_u,
                   b->d_zt, b->d_zu, b->d_info, b->d_tt, b->d_ut, b->d_dinv,
                   b->d_coef, b->d_wgt, b->d_counts, b->d_status, b->d_wins, b->d_tiles,
-                  b->d_scratch};
+                  b->d_scratch, b->d_y};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, b->ctx->stream);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
@@ -449,7 +450,7 @@ int run_stage(gb_batch* b, int stage) {
     case 3:
       if (b->ld_mode || b->counts_mode) return GB_OK;
       return launch_trsm_finalize(ctx, b->d_wins, (int)b->h_wins.size(), b->max_nt, b->max_nu, b->d_tt, b->d_dinv,
-                                  b->d_ut, b->d_zt, b->d_zu, b->d_info);
+                                  b->d_ut, b->d_zt, b->d_zu, b->d_info, b->d_y);
     default:
       ctx->err = "unknown stage";
       return GB_ERR_BAD_ARG;
@@ -1324,6 +1325,82 @@ int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void*
   return worst;
 }
 
+
+// ---- qcat() / qcatmix() window -------------------------------------------
+// Same B11 / B21 as dist() / distmix(); the tail is y = L^-1 Z1, w_s = L^-1 b_s and a Pearson correlation per
+// tested SNP s (qcat.cpp:203-250).  The tested MEASURED SNPs (rows_t[core_first .. core_first + n_core)) are
+// appended to the unmeasured list as extra right-hand-side columns -- their b_s is a row of B11 -- and the one
+// entry where such a column meets itself is patched to the forced diagonal 1 + lambda.  CountPC (util.cpp:355-388)
+// returns n_t unless an eigenvalue of B11 lies below eig_cutoff; like MakePosDef in dist() that is certified, not
+// computed: analytic bound or a Cholesky of B11 - eig_cutoff*I.  GB_ERR_NOT_PD = not certified (no eigen-count path).
+int gb_window_qcat(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* rows_t, const double* z_t,
+                   int64_t core_first, int64_t n_core, int64_t n_u, const int64_t* rows_u, const double* pop_wgt,
+                   const gb_params* params, double eig_cutoff, int* num_eig, double* t_m, double* chisq_m,
+                   double* t_u, double* chisq_u) {
+  if (!ctx || !panel || n_t < 0 || n_u < 0 || n_core < 0 || core_first < 0 || core_first + n_core > n_t ||
+      (n_t && (!rows_t || !z_t)) || (n_u && (!rows_u || !t_u || !chisq_u)) || (n_core && (!t_m || !chisq_m))) {
+    if (ctx) ctx->err = "null or inconsistent argument";
+    return GB_ERR_BAD_ARG;
+  }
+  gb_params p;
+  if (params) p = *params;
+  else gb_params_default(&p);
+  p.check_pd = 1;
+  p.min_abs_eig = eig_cutoff;         // the certificate threshold plays CountPC's cut-off
+  p.min_num_unmeasured_snp = -1;      // run_qcat only checks the measured count (qcat.cpp:157)
+  const int64_t n_test = n_u + n_core;
+  std::vector<int64_t> ru((size_t)n_test);
+  for (int64_t i = 0; i < n_u; i++) ru[(size_t)i] = rows_u[i];
+  for (int64_t i = 0; i < n_core; i++) ru[(size_t)(n_u + i)] = rows_t[core_first + i];
+  const int64_t t_off[2] = {0, n_t}, u_off[2] = {0, n_test};
+  double dummy = 0.0;
+  gb_batch* b = nullptr;
+  int rc = create_batch_internal(ctx, panel, 1, t_off, rows_t, u_off, ru.data(), z_t ? z_t : &dummy, pop_wgt, &p, false,
+                                 false, &b);
+  if (rc) return rc;
+  auto done = [&](int code) {
+    cudaStreamSynchronize(ctx->stream);
+    free_batch_device(b);
+    delete b;
+    return code;
+  };
+  if (b->plan_status[0] != GB_OK) return done(b->plan_status[0]);
+  double *d_qt = nullptr, *d_qc = nullptr;
+  const size_t nb_test = sizeof(double) * (size_t)std::max<int64_t>(n_test, 1);
+  if (cudaMallocAsync(reinterpret_cast<void**>(&b->d_y), sizeof(double) * (size_t)std::max<int64_t>(n_t, 1), ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(reinterpret_cast<void**>(&d_qt), nb_test, ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(reinterpret_cast<void**>(&d_qc), nb_test, ctx->stream) != cudaSuccess) {
+    ctx->err = "cudaMallocAsync(qcat) failed";
+    return done(GB_ERR_OOM);
+  }
+  auto done2 = [&](int code) {
+    cudaFreeAsync(d_qt, ctx->stream);
+    cudaFreeAsync(d_qc, ctx->stream);
+    return done(code);
+  };
+  if ((rc = run_stage(b, 0)) || (rc = run_stage(b, 1))) return done2(rc);
+  if ((rc = launch_qcat_patch(ctx, b->d_wins, b->d_ut, (int)n_u, (int)core_first, (int)n_core, 1.0 + p.lambda))) return done2(rc);
+  if ((rc = run_stage(b, 2)) || (rc = run_stage(b, 3))) return done2(rc);
+  if ((rc = launch_qcat_finalize(ctx, b->d_wins, b->d_ut, b->d_y, (int)n_test, (int)n_t, d_qt, d_qc))) return done2(rc);
+  std::vector<double> h_t((size_t)n_test), h_c((size_t)n_test);
+  if (n_test) {
+    cudaMemcpyAsync(h_t.data(), d_qt, sizeof(double) * (size_t)n_test, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(h_c.data(), d_qc, sizeof(double) * (size_t)n_test, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  rc = gb_batch_fetch(b, nullptr, nullptr, nullptr);   // synchronises; window status (breakdown / not certified / format)
+  if (rc == GB_OK) {
+    for (int64_t i = 0; i < n_u; i++) {
+      t_u[i] = h_t[(size_t)i];
+      chisq_u[i] = h_c[(size_t)i];
+    }
+    for (int64_t i = 0; i < n_core; i++) {
+      t_m[i] = h_t[(size_t)(n_u + i)];
+      chisq_m[i] = h_c[(size_t)(n_u + i)];
+    }
+    if (num_eig) *num_eig = (int)n_t;
+  }
+  return done2(rc);
+}
 
 // ---- pipelined single windows on HOST buffers ---------------------------------------------------
 // dist()/distmix() are called once per window with genotypes that live in host memory.  A gb_pipe

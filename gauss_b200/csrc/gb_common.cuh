@@ -171,7 +171,11 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
 int launch_pd_bound(Ctx* ctx, const SolveWin* d_wins, int n_real, const double* d_rq_t, double lambda,
                     double gneg, double min_abs_eig, int* d_skip);
 int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,
-                         const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info);
+                         const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info,
+                         double* d_y_out);
+int launch_qcat_patch(Ctx* ctx, const SolveWin* d_wins, double* d_ut, int n_u, int core_first, int n_core, double diag);
+int launch_qcat_finalize(Ctx* ctx, const SolveWin* d_wins, const double* d_ut, const double* d_y, int n_tested,
+                         int num_eig, double* d_qt, double* d_qchisq);
 int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double* d_src, double* d_dst,
                       double shift, const int* d_skip);
 

@@ -399,7 +399,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __global__ void __launch_bounds__(256, 2)
 trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt,
                      const double* __restrict__ dinv, double* ut, const double* __restrict__ zt,
-                     double* zu, double* info) {
+                     double* zu, double* info, double* y_out) {
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t, nu = w.n_u;
   const int u0 = blockIdx.x * UB;
@@ -588,6 +588,8 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
       }
   }
   __syncthreads();
+  if (y_out && blockIdx.x == 0)   // qcat: y = L^-1 Z1 is an output too (every CTA carries the same column)
+    for (int i = tid; i < n; i += 256) y_out[w.off_t + i] = ys[i];
   if (tid < UB && u0 + tid < nu) {
     const double s_info = red[0 * UB + tid] + red[1 * UB + tid];
     const double s_z = red[2 * UB + tid] + red[3 * UB + tid];
@@ -595,6 +597,47 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
     zu[w.off_u + u0 + tid] = s_z / sqrt(inf);        // z / sqrt(info)               (dist.cpp:200)
     info[w.off_u + u0 + tid] = inf;
   }
+}
+
+// qcat: the tested measured SNPs ride along as extra right-hand-side columns; their correlation row is a row
+// of B11, whose own entry is the forced diagonal 1 + lambda (qcat.cpp:186), not the computed self-correlation.
+__global__ void qcat_patch_kernel(const SolveWin* __restrict__ wins, double* ut, int n_u, int core_first, int n_core,
+                                  double diag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_core) return;
+  const SolveWin w = wins[0];
+  ut[w.off_ut + (long long)(core_first + c) * w.ld_u + n_u + c] = diag;
+}
+
+// qcat: per tested SNP u, Pearson correlation (util.cpp:193-202, two passes like Eigen's mean-then-centre) of
+// y = L^-1 Z1 and W(:, u) = L^-1 b_u over the measured SNPs; qcat_t = sqrt(num_eig - 3) r, qcat_chisq =
+// (num_eig - 3) r^2 (qcat.cpp:224-229).  One thread per column: W rows are read coalesced.
+__global__ void __launch_bounds__(128)
+qcat_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ ut, const double* __restrict__ y,
+                     int num_eig, double* __restrict__ qt, double* __restrict__ qchisq) {
+  const SolveWin w = wins[0];
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= w.n_u) return;
+  const int n = w.n_t;
+  const double* W = ut + w.off_ut + u;
+  const double* yy = y + w.off_t;
+  double sy = 0.0, sw = 0.0;
+  for (int k = 0; k < n; k++) {
+    sy += yy[k];
+    sw += W[(long long)k * w.ld_u];
+  }
+  const double my = sy / n, mw = sw / n;
+  double sxx = 0.0, syy = 0.0, sxy = 0.0;
+  for (int k = 0; k < n; k++) {
+    const double dy = yy[k] - my, dw = W[(long long)k * w.ld_u] - mw;
+    sxx = fma(dy, dy, sxx);
+    syy = fma(dw, dw, syy);
+    sxy = fma(dy, dw, sxy);
+  }
+  const double r = sxy / sqrt(sxx * syy);
+  const double dof = (double)(num_eig - 3);
+  qt[u] = sqrt(dof) * r;
+  qchisq[u] = dof * r * r;
 }
 
 }  // namespace
@@ -629,7 +672,8 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
 }
 
 int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,
-                         const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info) {
+                         const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info,
+                         double* d_y_out) {
   if (n_wins == 0 || max_nu == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
   const size_t smem = TR_SMEM_BYTES + sizeof(double) * (size_t)(nb_max * NB + 5 * NB);
@@ -639,7 +683,24 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
   }
   GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   trsm_finalize_kernel<<<dim3((max_nu + UB - 1) / UB, n_wins), 256, smem, ctx->stream>>>(
-      d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info);
+      d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+int launch_qcat_patch(Ctx* ctx, const SolveWin* d_wins, double* d_ut, int n_u, int core_first, int n_core, double diag) {
+  if (n_core <= 0) return GB_OK;
+  qcat_patch_kernel<<<(unsigned)((n_core + 127) / 128), 128, 0, ctx->stream>>>(d_wins, d_ut, n_u, core_first, n_core, diag);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+int launch_qcat_finalize(Ctx* ctx, const SolveWin* d_wins, const double* d_ut, const double* d_y, int n_tested,
+                         int num_eig, double* d_qt, double* d_qchisq) {
+  if (n_tested <= 0) return GB_OK;
+  qcat_finalize_kernel<<<(unsigned)((n_tested + 127) / 128), 128, 0, ctx->stream>>>(d_wins, d_ut, d_y, num_eig, d_qt, d_qchisq);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

@@ -145,6 +145,18 @@ GB_API int gb_window_cor(gb_ctx *ctx, gb_panel *panel, int64_t n_t, const int64_
                   const int64_t *rows_u, const double *pop_wgt, const gb_params *params,
                   double *B11, double *B21);
 
+/* ---- qcat() / qcatmix() window (run_qcat qcat.cpp:133-238, run_qcatmix qcatmix.cpp:140-269) ------------ */
+/* Tests every SNP of the prediction window: measured SNPs rows_t[core_first .. core_first + n_core) (the
+ * reference's [num_measured_headwing, + num_measured_pred) range of the extended window) and the unmeasured
+ * SNPs rows_u.  pop_wgt == NULL -> qcat (pooled CalCor), else qcatmix (CalWgtCov).  Outputs: qcat_t and
+ * qcat_chisq per tested SNP (SetQcatT / SetQcatChisq) and *num_eig (SetQcatM; CountPC util.cpp:355-388).
+ * GB_ERR_TOO_FEW_MEASURED as qcat.cpp:157; GB_ERR_NOT_PD when no eigenvalue bound above eig_cutoff (default
+ * 0.01, gauss.cpp:22) could be certified. */
+GB_API int gb_window_qcat(gb_ctx *ctx, gb_panel *panel, int64_t n_t, const int64_t *rows_t, const double *z_t,
+                   int64_t core_first, int64_t n_core, int64_t n_u, const int64_t *rows_u,
+                   const double *pop_wgt, const gb_params *params, double eig_cutoff, int *num_eig,
+                   double *t_m, double *chisq_m, double *t_u, double *chisq_u);
+
 /* ---- many windows on a resident panel (genome driver / benchmark path) ---------------------- */
 /* Window w uses rows_t[t_off[w] .. t_off[w+1]) and rows_u[u_off[w] .. u_off[w+1]); z_t is
  * aligned with rows_t.  pop_wgt == NULL selects dist().  Planning uploads the descriptors once. */

@@ -509,6 +509,126 @@ int go_run_window(const int *type, const long long *bp, double *z, double *info,
   return GO_OK;
 }
 
+/* ---- src/qcat.cpp:133-238 (w == NULL) / src/qcatmix.cpp:140-269 ------------------------------
+ * Tests every SNP of the prediction window: L = chol(B11), LInvZ1 = L^-1 Z1, and for a SNP with
+ * correlation row b (a row of B11 for measured SNPs, of B21 for unmeasured ones) r = Pearson
+ * correlation of LInvZ1 and L^-1 b over the measured SNPs, qcat_t = sqrt(num_eig - 3) r,
+ * qcat_chisq = (num_eig - 3) r^2, num_eig = CountPC(B11, eig_cutoff) (util.cpp:355-388).
+ * Outputs are indexed like snp_vec; untouched entries keep their input value. */
+static double vec_cor(const double *x, const double *y, int n) { /* util.cpp:193-202 */
+  double mx = 0.0, my = 0.0;
+  for (int i = 0; i < n; i++) mx += x[i];
+  for (int i = 0; i < n; i++) my += y[i];
+  mx /= n;
+  my /= n;
+  double sxx = 0.0, syy = 0.0, sxy = 0.0;
+  for (int i = 0; i < n; i++) sxx += (x[i] - mx) * (x[i] - mx);
+  for (int i = 0; i < n; i++) syy += (y[i] - my) * (y[i] - my);
+  for (int i = 0; i < n; i++) sxy += (x[i] - mx) * (y[i] - my);
+  return sxy / sqrt(sxx * syy);
+}
+
+int go_count_pc(const double *A, int n, double eig_cutoff) { /* util.cpp:355-388 */
+  double *ev = (double *)malloc(sizeof(double) * (size_t)n);
+  int num = n;
+  if (go_sym_eig(A, n, ev, NULL) != 0) {
+    free(ev);
+    return num;
+  }
+  if (ev[0] < eig_cutoff)
+    for (int i = 0; i < n; i++)
+      if (ev[i] < eig_cutoff) num--;
+  free(ev);
+  return num;
+}
+
+int go_run_qcat(const int *type, const long long *bp, const double *z, const char *geno, int64_t n_snps,
+                const int *m, int n_pops, const double *w, const go_args *args, double eig_cutoff,
+                double *qcat_m, double *qcat_t, double *qcat_chisq) {
+  int64_t N = 0;
+  for (int p = 0; p < n_pops; p++) N += m[p];
+  int64_t *meas = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_snps + 1));
+  int64_t *unme = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_snps + 1));
+  int nt = 0, nu = 0, headwing = 0, npred = 0;
+  for (int64_t i = 0; i < n_snps; i++) { /* qcat.cpp:139-152 */
+    if (type[i] == 0 && bp[i] >= args->start_bp && bp[i] <= args->end_bp) {
+      unme[nu++] = i;
+    } else if (type[i] == 1) {
+      meas[nt++] = i;
+      if (bp[i] < args->start_bp) headwing++;
+      else if (bp[i] >= args->start_bp && bp[i] <= args->end_bp) npred++;
+    }
+  }
+  if (nt <= args->min_num_measured_snp) { /* qcat.cpp:157 */
+    free(meas);
+    free(unme);
+    return GO_ERR_TOO_FEW_SNPS;
+  }
+  size_t ntt = (size_t)nt * nt;
+  double *B11 = (double *)calloc(ntt, sizeof(double));
+  double *L = (double *)calloc(ntt, sizeof(double));
+  double *LInv = (double *)malloc(sizeof(double) * ntt);
+  double *y = (double *)malloc(sizeof(double) * (size_t)nt);
+  double *b = (double *)malloc(sizeof(double) * (size_t)nt);
+  double *lb = (double *)malloc(sizeof(double) * (size_t)nt);
+  double *sd = NULL;
+  if (w) { /* qcatmix.cpp:196-205 */
+    sd = (double *)malloc(sizeof(double) * (size_t)(nt + nu));
+    for (int i = 0; i < nt; i++) sd[i] = sqrt(go_cal_wgt_cov(geno + meas[i] * N, geno + meas[i] * N, m, n_pops, w));
+    for (int i = 0; i < nu; i++) sd[nt + i] = sqrt(go_cal_wgt_cov(geno + unme[i] * N, geno + unme[i] * N, m, n_pops, w));
+  }
+  for (int i = 0; i < nt; i++) { /* qcat.cpp:185-193, qcatmix.cpp:208-219 */
+    B11[(size_t)i * nt + i] = 1.0 + args->lambda;
+    for (int j = i + 1; j < nt; j++) {
+      double v = w ? go_cal_wgt_cov(geno + meas[i] * N, geno + meas[j] * N, m, n_pops, w) / (sd[i] * sd[j])
+                   : go_cal_cor(geno + meas[i] * N, geno + meas[j] * N, m, n_pops);
+      B11[(size_t)j * nt + i] = v;
+      B11[(size_t)i * nt + j] = v;
+    }
+  }
+  const int num_eig = go_count_pc(B11, nt, eig_cutoff); /* qcat.cpp:203 */
+  /* CholeskyMat (util.cpp:271-274, Eigen::LLT): lower factor, column by column */
+  for (int j = 0; j < nt; j++) {
+    double d = B11[(size_t)j * nt + j];
+    for (int k = 0; k < j; k++) d -= L[(size_t)k * nt + j] * L[(size_t)k * nt + j];
+    d = sqrt(d);
+    L[(size_t)j * nt + j] = d;
+    for (int i = j + 1; i < nt; i++) {
+      double v = B11[(size_t)j * nt + i];
+      for (int k = 0; k < j; k++) v -= L[(size_t)k * nt + i] * L[(size_t)k * nt + j];
+      L[(size_t)j * nt + i] = v / d;
+    }
+  }
+  go_inv_full_piv_lu(LInv, L, nt); /* qcat.cpp:207 */
+  for (int i = 0; i < nt; i++) {   /* LInvZ1 = LInv * Z1, qcat.cpp:208 */
+    double acc = 0.0;
+    for (int k = 0; k < nt; k++) acc += LInv[(size_t)k * nt + i] * z[meas[k]];
+    y[i] = acc;
+  }
+  for (int t = 0; t < npred + nu; t++) { /* qcat.cpp:221-250 */
+    const int is_m = t < npred;
+    const int64_t snp = is_m ? meas[headwing + t] : unme[t - npred];
+    if (is_m) {
+      for (int j = 0; j < nt; j++) b[j] = B11[(size_t)j * nt + headwing + t];
+    } else {
+      for (int j = 0; j < nt; j++)
+        b[j] = w ? go_cal_wgt_cov(geno + snp * N, geno + meas[j] * N, m, n_pops, w) / (sd[nt + (t - npred)] * sd[j])
+                 : go_cal_cor(geno + snp * N, geno + meas[j] * N, m, n_pops);
+    }
+    for (int i = 0; i < nt; i++) {
+      double acc = 0.0;
+      for (int k = 0; k < nt; k++) acc += LInv[(size_t)k * nt + i] * b[k];
+      lb[i] = acc;
+    }
+    const double r = vec_cor(y, lb, nt);
+    qcat_m[snp] = num_eig;
+    qcat_t[snp] = sqrt((double)(num_eig - 3)) * r;
+    qcat_chisq[snp] = (num_eig - 3) * r * r;
+  }
+  free(meas); free(unme); free(B11); free(L); free(LInv); free(y); free(b); free(lb); free(sd);
+  return GO_OK;
+}
+
 /* ---- src/computeLD.cpp:95-116 ---------------------------------------------- */
 void go_compute_ld(const char *geno, int64_t n, const int *m, int n_pops, const double *w,
                    double *cormat) {

@@ -65,6 +65,14 @@ int go_run_window(const int *type, const long long *bp, double *z, double *info,
                   const double *w, const go_args *args, int *n_measured, int *n_unmeasured,
                   double *B11_out, double *B21_out);
 
+/* run_qcat (src/qcat.cpp:133-238, w == NULL) / run_qcatmix (src/qcatmix.cpp:140-269): the QCAT test of every SNP
+ * of the prediction window.  qcat_m / qcat_t / qcat_chisq are indexed like snp_vec (SetQcatM / SetQcatT /
+ * SetQcatChisq); entries of SNPs that are not tested are left untouched.  CountPC: util.cpp:355-388. */
+int go_count_pc(const double *A, int n, double eig_cutoff);
+int go_run_qcat(const int *type, const long long *bp, const double *z, const char *geno, int64_t n_snps,
+                const int *m, int n_pops, const double *w, const go_args *args, double eig_cutoff,
+                double *qcat_m, double *qcat_t, double *qcat_chisq);
+
 /* computeLD kernel (src/computeLD.cpp:95-116): correlation among n SNPs,
  * diagonal exactly 1.0, col-major n x n. */
 void go_compute_ld(const char *geno, int64_t n, const int *m, int n_pops, const double *w,

@@ -83,6 +83,8 @@ class Oracle:
             lib.go_sym_eig.argtypes = [_c_f64p, C.c_int, _c_f64p, C.c_void_p]
             lib.go_make_pos_def.restype = C.c_int
             lib.go_make_pos_def.argtypes = [_c_f64p, C.c_int, C.c_double]
+            lib.go_count_pc.restype = C.c_int
+            lib.go_count_pc.argtypes = [_c_f64p, C.c_int, C.c_double]
             lib.go_inv_full_piv_lu.restype = None
             lib.go_inv_full_piv_lu.argtypes = [_c_f64p, _c_f64p, C.c_int]
         elif kind == "reference":
@@ -150,6 +152,27 @@ class Oracle:
         if dump:
             out["B11"], out["B21"] = B11, B21
         return out
+
+    def run_qcat(self, type_, bp, z, geno, m, w=None, start_bp=0, end_bp=0, lam=0.1, eig_cutoff=0.01,
+                 min_measured=10):
+        """run_qcat (w=None) / run_qcatmix.  Returns dict(rc, m, t, chisq) indexed like the SNP list (NaN = untested)."""
+        assert self.kind == "port"
+        type_ = np.ascontiguousarray(type_, np.int32)
+        bp = np.ascontiguousarray(bp, np.int64)
+        zz = np.ascontiguousarray(z, np.float64)
+        g = _chars(geno)
+        m = np.ascontiguousarray(m, np.int32)
+        a = GoArgs(int(start_bp), int(end_bp), lam, 1e-5, min_measured, 10)
+        wp = None
+        if w is not None:
+            w = np.ascontiguousarray(w, np.float64)
+            wp = w.ctypes.data
+        qm, qt, qc = (np.full(len(zz), np.nan) for _ in range(3))
+        self.lib.go_run_qcat.restype = C.c_int
+        self.lib.go_run_qcat.argtypes = [_c_i32p, _c_i64p, _c_f64p, _c_u8p, C.c_int64, _c_i32p, C.c_int, C.c_void_p,
+                                         C.POINTER(GoArgs), C.c_double, _c_f64p, _c_f64p, _c_f64p]
+        rc = self.lib.go_run_qcat(type_, bp, zz, g, g.shape[0], m, len(m), wp, C.byref(a), eig_cutoff, qm, qt, qc)
+        return dict(rc=rc, m=qm, t=qt, chisq=qc)
 
     def compute_ld(self, geno, m, w):
         g = _chars(geno)
