@@ -88,6 +88,7 @@ def load_library():
         "gb_window_distmix": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, dblp, C.POINTER(Params), dblp, dblp]),
         "gb_window_ld": (C.c_int, [vp, vp, i64, i64p, dblp, dblp]),
         "gb_window_cor": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, C.POINTER(Params), dblp, dblp]),
+        "gb_zmix_pair_cor": (C.c_int, [vp, vp, i64, i64p, dblp, dblp]),
         "gb_window_qcat": (C.c_int, [vp, vp, i64, i64p, dblp, i64, i64, i64, i64p, dblp, C.POINTER(Params), C.c_double,
                                      C.POINTER(C.c_int), dblp, dblp, dblp, dblp]),
         "gb_batch_create": (C.c_int, [vp, vp, i64, i64p, i64p, i64p, i64p, dblp, dblp, C.POINTER(Params),
@@ -350,6 +351,14 @@ class Panel:
                                        _ptr(w), pp, _ptr(z), _ptr(info))
         self.ctx.check(rc, allow)
         return z, info, rc
+
+    def zmix_pair_cor(self, rows, z):
+        """gb_zmix_pair_cor: prep_zmix5's pair matrix [n(n-1)/2, 1 + P] (column 0 = z_i z_j)."""
+        r, zz = _i64(rows), _f64(z)
+        n, P = len(r), len(self.pop_sizes)
+        out = np.zeros((1 + P, n * (n - 1) // 2))
+        self.ctx.check(self.ctx.lib.gb_zmix_pair_cor(self.ctx.h, self.h, n, _ptr(r), _ptr(zz), _ptr(out)))
+        return out.T
 
     def window_qcat(self, rows_t, z_t, core_first, n_core, rows_u, pop_wgt=None, params: Params | None = None,
                     eig_cutoff: float = 0.01, allow=()):

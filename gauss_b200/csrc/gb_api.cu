@@ -1079,6 +1079,45 @@ int gb_gram_counts(gb_ctx* ctx, gb_panel* panel, int64_t n_a, const int64_t* row
 }
 
 
+// ---- prep_zmix5 pair correlations -------------------------------------------
+// zmix.cpp:151-170 walks every SNP pair and calls CalCor(std::string&, std::string&) once per population.  Here the
+// Gram kernel's GRAM_COUNTS mode gives the exact per-population counts of all pairs in one launch and
+// zmix_pair_kernel turns them into the reference's output matrix.
+int gb_zmix_pair_cor(gb_ctx* ctx, gb_panel* panel, int64_t n, const int64_t* rows, const double* z, double* out) {
+  if (!ctx || !panel || n < 2 || !rows || !z || !out || n > 46340) {
+    if (ctx) ctx->err = "null argument or n outside [2, 46340]";
+    return GB_ERR_BAD_ARG;
+  }
+  const int64_t t_off[2] = {0, n}, u_off[2] = {0, n};
+  gb_batch* b = nullptr;
+  int rc = create_batch_internal(ctx, panel, 1, t_off, rows, u_off, rows, nullptr, nullptr, nullptr, false, true, &b);
+  if (rc) return rc;
+  const size_t n_out = (size_t)(n * (n - 1) / 2) * (size_t)(1 + panel->n_pops);
+  double *d_out = nullptr, *d_z = nullptr;
+  auto done = [&](int code) {
+    if (d_out) cudaFreeAsync(d_out, ctx->stream);
+    if (d_z) cudaFreeAsync(d_z, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    gb_batch_destroy(b);
+    return code;
+  };
+  if (cudaMallocAsync(reinterpret_cast<void**>(&d_out), sizeof(double) * n_out, ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(reinterpret_cast<void**>(&d_z), sizeof(double) * (size_t)n, ctx->stream) != cudaSuccess) {
+    ctx->err = "cudaMallocAsync(zmix pair matrix) failed";
+    cudaGetLastError();
+    return done(GB_ERR_OOM);
+  }
+  if (cudaMemcpyAsync(d_z, z, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return done(GB_ERR_CUDA);
+  if ((rc = run_stage(b, 0)) || (rc = run_stage(b, 1))) return done(rc);
+  if ((rc = launch_zmix_pairs(ctx, panel, b->d_counts, (int)n, b->d_rows_t, d_z, d_out))) return done(rc);
+  if (cudaMemcpyAsync(out, d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = "zmix pair matrix copy failed";
+    return done(GB_ERR_CUDA);
+  }
+  return done(GB_OK);
+}
+
 // ---- 2-bit host panel format ("pack2") --------------------------------------------------------------
 // A dosage in {0,1,2} needs two bits; a char/int8 host row spends eight, and PCIe (~50 GB/s) is the
 // longest leg of any host-buffer path.  pack2 rows hold 4 dosages per byte at the column positions of the

@@ -151,6 +151,8 @@ int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_row
                          int64_t k_stride_bytes, int format);
 bool gram_cluster_supported(int cm, int cn);
 int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors);
+int launch_zmix_pairs(Ctx* ctx, const Panel* panel, const int32_t* d_counts, int n, const int32_t* d_rows,
+                      const double* d_z, double* d_out);
 int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn,
                 int max_ctas);
 

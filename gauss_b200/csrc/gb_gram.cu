@@ -607,6 +607,35 @@ gram_finalize_kernel(const __grid_constant__ GramParams prm) {
   }
 }
 
+// prep_zmix5's pair loop (zmix.cpp:151-170): per SNP pair i < j and population p the Pearson r of
+// CalCor(std::string&, std::string&) (util.cpp:153-169) from the exact per-population counts the Gram kernel
+// wrote in GRAM_COUNTS mode, in the reference's operation order (n*sumxy - sumx*sumy over
+// sqrt(n*sumxsq - sumx^2) * sqrt(n*sumysq - sumy^2); every sum is an exact integer held in a double).
+// Output column-major [n(n-1)/2][1 + P] like the reference's NumericMatrix: column 0 = z_i z_j.
+// Thread (i, j): consecutive j are consecutive output rows, so every column is written coalesced.
+__global__ void __launch_bounds__(256)
+zmix_pair_kernel(const int32_t* __restrict__ counts, int n, int n_pops, const int* __restrict__ pop_sizes,
+                 const int32_t* __restrict__ rows, const int32_t* __restrict__ sx, const int32_t* __restrict__ sxx,
+                 long long stat_ld, const double* __restrict__ z, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= n || j <= i) return;
+  const long long total = (long long)n * (n - 1) / 2;
+  const long long row = (long long)i * n - (long long)i * (i + 1) / 2 + (j - i - 1);
+  out[row] = __dmul_rn(z[i], z[j]);
+  const long long ri = rows[i], rj = rows[j];
+  for (int p = 0; p < n_pops; p++) {
+    const double m = (double)pop_sizes[p];
+    const double sumxy = (double)counts[((long long)p * n + i) * n + j];
+    const double sumx = (double)sx[p * stat_ld + ri], sumy = (double)sx[p * stat_ld + rj];
+    const double sumxsq = (double)sxx[p * stat_ld + ri], sumysq = (double)sxx[p * stat_ld + rj];
+    const double numer = __dsub_rn(__dmul_rn(m, sumxy), __dmul_rn(sumx, sumy));
+    const double denor = __dmul_rn(__dsqrt_rn(__dsub_rn(__dmul_rn(m, sumxsq), __dmul_rn(sumx, sumx))),
+                                   __dsqrt_rn(__dsub_rn(__dmul_rn(m, sumysq), __dmul_rn(sumy, sumy))));
+    out[(long long)(p + 1) * total + row] = __ddiv_rn(numer, denor);
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -702,6 +731,16 @@ int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const 
 // Round 1 built and measured CM x CN thread-block clusters with TMA multicast (2x1 ... 4x2, 8x1); all were
 // slower than independent CTAs and the code is gone: only 1 x 1 is accepted.
 bool gram_cluster_supported(int cm, int cn) { return cm == 1 && cn == 1; }
+
+int launch_zmix_pairs(Ctx* ctx, const Panel* panel, const int32_t* d_counts, int n, const int32_t* d_rows,
+                      const double* d_z, double* d_out) {
+  if (n < 2) return GB_OK;
+  zmix_pair_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)(n - 1)), 256, 0, ctx->stream>>>(
+      d_counts, n, panel->n_pops, panel->d_pop_sizes, d_rows, panel->d_sx, panel->d_sxx, panel->capacity, d_z, d_out);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
 
 int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors) {
   if (n_descriptors <= 0) return GB_OK;

@@ -145,6 +145,14 @@ GB_API int gb_window_cor(gb_ctx *ctx, gb_panel *panel, int64_t n_t, const int64_
                   const int64_t *rows_u, const double *pop_wgt, const gb_params *params,
                   double *B11, double *B21);
 
+/* ---- prep_zmix5 pair loop (zmix.cpp:151-170) ------------------------------------------------------ */
+/* For every pair i < j of the n listed SNPs (row-major over i, then j) one row of `out`, COLUMN-major
+ * [n(n-1)/2][1 + n_pops] like the reference's NumericMatrix: column 0 = z[i]*z[j], column 1 + p = the Pearson r of
+ * population p (CalCor(std::string&, std::string&), util.cpp:153-169; NaN where a SNP is monomorphic in p, as
+ * in the reference).  Every population of the panel is used (prep_zmix5 flags all, zmix.cpp:142-144). */
+GB_API int gb_zmix_pair_cor(gb_ctx *ctx, gb_panel *panel, int64_t n, const int64_t *rows, const double *z,
+                     double *out);
+
 /* ---- qcat() / qcatmix() window (run_qcat qcat.cpp:133-238, run_qcatmix qcatmix.cpp:140-269) ------------ */
 /* Tests every SNP of the prediction window: measured SNPs rows_t[core_first .. core_first + n_core) (the
  * reference's [num_measured_headwing, + num_measured_pred) range of the extended window) and the unmeasured

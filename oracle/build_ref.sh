@@ -17,6 +17,7 @@ mkdir -p "$OUT/gen"
 cut_lines() { sed -n "$2,$3p" "$SRC/$1" > "$OUT/gen/$4"; }
 cut_lines util.cpp 49 70 util_49_70.inc            # CalCor(vector<string>, vector<string>)
 cut_lines util.cpp 103 124 util_103_124.inc        # CalWgtCov
+cut_lines util.cpp 153 169 util_153_169.inc        # CalCor(std::string&, std::string&)  (zmix)
 cut_lines gauss.cpp 18 35 gauss_18_35.inc          # Arguments::Arguments defaults
 cut_lines dist.cpp 129 227 dist_129_227.inc        # run_dist
 cut_lines distmix.cpp 138 253 distmix_138_253.inc  # run_distmix
@@ -24,6 +25,7 @@ cut_lines computeLD.cpp 95 116 computeLD_95_116.inc
 # guard: the extraction must start/end on the expected function boundaries
 grep -q '^double CalCor(std::vector<std::string>& x, std::vector<std::string>& y){' "$OUT/gen/util_49_70.inc"
 grep -q '^double CalWgtCov(' "$OUT/gen/util_103_124.inc"
+grep -q '^double CalCor(std::string& x, std::string& y){' "$OUT/gen/util_153_169.inc"
 grep -q '^void run_dist(' "$OUT/gen/dist_129_227.inc"
 grep -q '^void run_distmix(' "$OUT/gen/distmix_138_253.inc"
 grep -q '^Arguments::Arguments(){' "$OUT/gen/gauss_18_35.inc"
@@ -32,7 +34,8 @@ gcc -O2 -fPIC -ffp-contract=off -c "$HERE/gauss_oracle.c" -o "$OUT/gauss_oracle_
     -Dgo_make_pos_def=gor_make_pos_def -Dgo_inv_full_piv_lu=gor_inv_full_piv_lu \
     -Dgo_cal_cor=gor_cal_cor -Dgo_cal_wgt_cov=gor_cal_wgt_cov -Dgo_run_window=gor_run_window \
     -Dgo_compute_ld=gor_compute_ld -Dgo_last_sample_pairs=gor_last_sample_pairs \
-    -Dgo_gram_counts=gor_gram_counts -Dgo_sym_eig=gor_sym_eig -Dgo_args_default=gor_args_default
+    -Dgo_gram_counts=gor_gram_counts -Dgo_zmix_pairs=gor_zmix_pairs -Dgo_cal_cor_pop=gor_cal_cor_pop \
+    -Dgo_run_qcat=gor_run_qcat -Dgo_count_pc=gor_count_pc -Dgo_sym_eig=gor_sym_eig -Dgo_args_default=gor_args_default
 g++ $CXXFLAGS -c "$SRC/snp.cpp" -o "$OUT/snp.o"
 g++ $CXXFLAGS -c "$HERE/ref_glue.cpp" -o "$OUT/ref_glue.o"
 g++ -shared -o "$OUT/libgauss_ref.so" "$OUT/ref_glue.o" "$OUT/snp.o" "$OUT/gauss_oracle_int.o" -lm

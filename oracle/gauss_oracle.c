@@ -629,6 +629,44 @@ int go_run_qcat(const int *type, const long long *bp, const double *z, const cha
   return GO_OK;
 }
 
+/* ---- src/util.cpp:153-169 : CalCor(std::string&, std::string&), one population ---------------- */
+double go_cal_cor_pop(const char *x, const char *y, int n) {
+  double xi = 0, yi = 0, sumx = 0, sumy = 0, sumxsq = 0, sumysq = 0, sumxy = 0;
+  for (int i = 0; i < n; i++) {
+    xi = (double)(x[i] - '0');
+    yi = (double)(y[i] - '0');
+    sumx += xi;
+    sumy += yi;
+    sumxsq += xi * xi;
+    sumysq += yi * yi;
+    sumxy += xi * yi;
+  }
+  double numer = n * sumxy - sumx * sumy;
+  double denor = sqrt((n)*sumxsq - sumx * sumx) * sqrt((n)*sumysq - sumy * sumy);
+  return numer / denor;
+}
+
+/* ---- src/zmix.cpp:151-170 : the pair loop of prep_zmix5 -----------------------------------------
+ * One output row per SNP pair i < j (row-major over i, then j): column 0 = z_i z_j, column 1 + k =
+ * per-population Pearson r of population k.  out is COLUMN-major [n(n-1)/2][1 + n_pops] like the
+ * Rcpp::NumericMatrix the reference fills. */
+void go_zmix_pairs(const char *geno, int64_t n, const int *m, int n_pops, const double *z, double *out) {
+  int64_t N = 0;
+  for (int p = 0; p < n_pops; p++) N += m[p];
+  const int64_t total = n * (n - 1) / 2;
+  int64_t row = 0;
+  for (int64_t i = 0; i < n; i++)
+    for (int64_t j = i + 1; j < n; j++) {
+      out[row] = z[i] * z[j];
+      int64_t off = 0;
+      for (int k = 0; k < n_pops; k++) {
+        out[(int64_t)(k + 1) * total + row] = go_cal_cor_pop(geno + i * N + off, geno + j * N + off, m[k]);
+        off += m[k];
+      }
+      row++;
+    }
+}
+
 /* ---- src/computeLD.cpp:95-116 ---------------------------------------------- */
 void go_compute_ld(const char *geno, int64_t n, const int *m, int n_pops, const double *w,
                    double *cormat) {

@@ -73,6 +73,11 @@ int go_run_qcat(const int *type, const long long *bp, const double *z, const cha
                 const int *m, int n_pops, const double *w, const go_args *args, double eig_cutoff,
                 double *qcat_m, double *qcat_t, double *qcat_chisq);
 
+/* per-population Pearson r (src/util.cpp:153-169) and the pair loop of prep_zmix5 (src/zmix.cpp:151-170):
+ * out is column-major [n(n-1)/2][1 + n_pops], column 0 = z_i z_j, pairs i < j in row-major order. */
+double go_cal_cor_pop(const char *x, const char *y, int n);
+void go_zmix_pairs(const char *geno, int64_t n, const int *m, int n_pops, const double *z, double *out);
+
 /* computeLD kernel (src/computeLD.cpp:95-116): correlation among n SNPs,
  * diagonal exactly 1.0, col-major n x n. */
 void go_compute_ld(const char *geno, int64_t n, const int *m, int n_pops, const double *w,

@@ -63,6 +63,8 @@ def _bind(lib):
     lib.go_compute_ld.restype = None
     lib.go_compute_ld.argtypes = [_c_u8p, C.c_int64, _c_i32p, C.c_int, _c_f64p, _c_f64p]
     lib.go_last_sample_pairs.restype = C.c_double
+    lib.go_zmix_pairs.restype = None
+    lib.go_zmix_pairs.argtypes = [_c_u8p, C.c_int64, _c_i32p, C.c_int, _c_f64p, _c_f64p]
     return lib
 
 
@@ -173,6 +175,16 @@ class Oracle:
                                          C.POINTER(GoArgs), C.c_double, _c_f64p, _c_f64p, _c_f64p]
         rc = self.lib.go_run_qcat(type_, bp, zz, g, g.shape[0], m, len(m), wp, C.byref(a), eig_cutoff, qm, qt, qc)
         return dict(rc=rc, m=qm, t=qt, chisq=qc)
+
+    def zmix_pairs(self, geno, m, z):
+        """prep_zmix5 pair loop -> [n(n-1)/2, 1 + P] (column 0 = z_i z_j, then one Pearson r per population)."""
+        g = _chars(geno)
+        m = np.ascontiguousarray(m, np.int32)
+        z = np.ascontiguousarray(z, np.float64)
+        n = g.shape[0]
+        out = np.zeros((1 + len(m), n * (n - 1) // 2), np.float64)   # column-major [pairs][1+P]
+        self.lib.go_zmix_pairs(g, n, m, len(m), z, out)
+        return out.T
 
     def compute_ld(self, geno, m, w):
         g = _chars(geno)

@@ -53,6 +53,7 @@ void LoadProgressBar(int) {}  // util.cpp:449-461 prints a text bar; silent here
 // ---- the reference's own code, extracted at build time -----------------------------------
 #include "gen/util_49_70.inc"
 #include "gen/util_103_124.inc"
+#include "gen/util_153_169.inc"   // CalCor(std::string&, std::string&)
 #include "gen/gauss_18_35.inc"
 void run_dist(std::vector<Snp*>& snp_vec, Arguments& args);
 void run_distmix(std::vector<Snp*>& snp_vec, Arguments& args);
@@ -81,6 +82,22 @@ static std::vector<std::string> split_pops(const char* row, const int* m, int n_
 extern "C" {
 
 double go_last_sample_pairs(void) { return g_pairs; }
+
+// the pair loop of prep_zmix5 (zmix.cpp:151-170) around the reference's own CalCor(std::string&, std::string&)
+void go_zmix_pairs(const char* geno, int64_t n, const int* m, int n_pops, const double* z, double* out) {
+  int64_t N = 0;
+  for (int p = 0; p < n_pops; p++) N += m[p];
+  std::vector<std::vector<std::string>> g;
+  for (int64_t i = 0; i < n; i++) g.push_back(split_pops(geno + i * N, m, n_pops));
+  const int64_t total = n * (n - 1) / 2;
+  int64_t row = 0;
+  for (int64_t i = 0; i < n; i++)
+    for (int64_t j = i + 1; j < n; j++) {
+      out[row] = z[i] * z[j];
+      for (int k = 0; k < n_pops; k++) out[(int64_t)(k + 1) * total + row] = CalCor(g[i][k], g[j][k]);
+      row++;
+    }
+}
 
 double go_cal_cor(const char* x, const char* y, const int* m, int n_pops) {
   auto vx = split_pops(x, m, n_pops), vy = split_pops(y, m, n_pops);
