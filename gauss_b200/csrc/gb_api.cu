@@ -571,6 +571,7 @@ int gb_ctx_create(int device, gb_ctx** out) {
     if (!strcmp(e, "int8")) ctx->panel_format = GB_PANEL_INT8;
     else if (!strcmp(e, "e2m1")) ctx->panel_format = GB_PANEL_E2M1;
   }
+  if (const char* e = getenv("GB_SEG_ORDER")) ctx->seg_order = atoi(e);   // tuning knob: 0 panel order, 1 descending, 2 alternating
   if (const char* e = getenv("GB_CHOL_SMS")) ctx->chol_sms = atoi(e);   // tuning knob; 0 = no overlap
   if (const char* e = getenv("GB_GRAM_KIND")) ctx->e2m1_mxf4 = strcmp(e, "f8f6f4") != 0;
   if (const char* e = getenv("GB_GRAM_CLUSTER")) {  // tuning knob: "CMxCN", e.g. 2x2

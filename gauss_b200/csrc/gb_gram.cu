@@ -24,6 +24,8 @@
 // descriptor as a running sum and polls the NEXT stage's barrier before issuing the current MMAs.
 // (Thread-block clusters with TMA multicast were built and measured in round 1 -- 2x1 ... 4x2, 8x1 --
 // and were slower than plain CTAs; see DESIGN.md section 7.  They are gone from the code.)
+#include <algorithm>
+
 #include "gb_common.cuh"
 #include "gb_ptx.cuh"
 
@@ -237,18 +239,24 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       long long* const dbg = prm.dbg;
       long long w_tempty = 0, w_full = 0, n_tempty_miss = 0, n_full_miss = 0;
       const long long t_begin = dbg ? clock64() : 0;
+      bool acc_ready = false;                 // the next accumulator buffer was already seen handed back
       for (int ct = blockIdx.x; ct < prm.n_tiles; ct += n_ctas) {
         for (int s = 0; s < n_seg; s++) {
           int atoms = segtab[s].y;
-          if (dbg && !ptx::mbar_test_wait(&tempty_bar[acc], acc_phase ^ 1)) {
-            const long long c0 = clock64();
+          if (!acc_ready) {
+            if (dbg && !ptx::mbar_test_wait(&tempty_bar[acc], acc_phase ^ 1)) {
+              const long long c0 = clock64();
+              ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+              w_tempty += clock64() - c0;
+              n_tempty_miss++;
+            }
             ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-            w_tempty += clock64() - c0;
-            n_tempty_miss++;
           }
-          ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TILE;
+          int next_acc = acc + 1;
+          uint32_t next_acc_phase = acc_phase;
+          if (next_acc == acc_bufs) { next_acc = 0; next_acc_phase ^= 1; }
           uint32_t accumulate = 0;
           for (; atoms > 0; atoms -= 4) {
             if (!ready) {
@@ -264,7 +272,10 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             uint64_t* nextp = fullp + 1;
             uint32_t next_phase = phase;
             if (nextp == full_end) { nextp = full_bar; next_phase ^= 1; }
-            ready = ptx::mbar_test_wait(nextp, next_phase);   // result is needed only after the MMAs below
+            // polls whose results are needed only after the MMAs below: the next stage, and -- in the last K block
+            // of a segment -- the accumulator buffer the next segment will write
+            ready = ptx::mbar_test_wait(nextp, next_phase);
+            if (atoms <= 4) acc_ready = ptx::mbar_test_wait(&tempty_bar[next_acc], next_acc_phase ^ 1);
             const uint64_t db = da + (STAGE_OPERAND_BYTES >> 4);
             if (atoms >= 4) {
               mma_ss<FKIND>(d_tmem, da, db, sf_tmem, accumulate);
@@ -282,7 +293,8 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
             if (da == desc_end) da = desc0;
           }
           ptx::mma_commit(&tfull_bar[acc]);      // accumulator of segment s is complete
-          if (++acc == acc_bufs) { acc = 0; acc_phase ^= 1; }
+          acc = next_acc;
+          acc_phase = next_acc_phase;
         }
       }
       if (dbg) {
@@ -767,6 +779,30 @@ int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const Gr
   if (prm.n_seg > P_MAX) {
     ctx->err = "too many population segments for the Gram kernel";
     return GB_ERR_UNSUPPORTED;
+  }
+  if (prm.raw_out && ctx->seg_order != 0 && prm.n_seg > 2) {
+    // The regrouped fold is a plain sum over populations, so its order is free (the int8 fold keeps the
+    // reference's).  Largest population first: its long MMA chain covers the epilogue's store phase of the
+    // previous tile; then big and small ones alternate so the epilogue catches up behind every long chain.
+    GramParams q = prm;
+    int idx[P_MAX];
+    for (int i = 0; i < prm.n_seg; i++) idx[i] = i;
+    std::sort(idx, idx + prm.n_seg, [&](int a, int b) { return prm.seg[a].natoms > prm.seg[b].natoms; });
+    int order[P_MAX];
+    if (ctx->seg_order == 1) {
+      for (int i = 0; i < prm.n_seg; i++) order[i] = idx[i];
+    } else {
+      int lo = 0, hi = prm.n_seg - 1;
+      for (int i = 0; i < prm.n_seg; i++) order[i] = (i & 1) ? idx[hi--] : idx[lo++];
+    }
+    for (int i = 0; i < prm.n_seg; i++) {
+      q.seg[i] = prm.seg[order[i]];
+      q.coefm[i] = prm.coefm[order[i]];
+    }
+    switch (prm.fkind) {
+      case FKIND_F8F6F4: return launch_gram_t<FKIND_F8F6F4>(ctx, panel, scratch, q, max_ctas);
+      case FKIND_MXF4: return launch_gram_t<FKIND_MXF4>(ctx, panel, scratch, q, max_ctas);
+    }
   }
   switch (prm.fkind) {
     case FKIND_I8: return launch_gram_t<FKIND_I8>(ctx, panel, scratch, prm, max_ctas);
