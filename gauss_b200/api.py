@@ -88,6 +88,7 @@ def load_library():
         "gb_window_distmix": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, dblp, C.POINTER(Params), dblp, dblp]),
         "gb_window_ld": (C.c_int, [vp, vp, i64, i64p, dblp, dblp]),
         "gb_window_cor": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, C.POINTER(Params), dblp, dblp]),
+        "gb_genes_ld": (C.c_int, [vp, vp, i64, i64p, i64p, dblp, C.c_double, dblp]),
         "gb_zmix_pair_cor": (C.c_int, [vp, vp, i64, i64p, dblp, dblp]),
         "gb_window_qcat": (C.c_int, [vp, vp, i64, i64p, dblp, i64, i64, i64, i64p, dblp, C.POINTER(Params), C.c_double,
                                      C.POINTER(C.c_int), dblp, dblp, dblp, dblp]),
@@ -351,6 +352,17 @@ class Panel:
                                        _ptr(w), pp, _ptr(z), _ptr(info))
         self.ctx.check(rc, allow)
         return z, info, rc
+
+    def genes_ld(self, g_off, rows, pop_wgt=None, diag: float = 1.1):
+        """gb_genes_ld: list of per-gene correlation matrices (CorG of jepeg / jepegmix)."""
+        go, r = _i64(g_off), _i64(rows)
+        w = None if pop_wgt is None else _f64(pop_wgt)
+        sizes = np.diff(go)
+        out = np.zeros(int((sizes * sizes).sum()))
+        self.ctx.check(self.ctx.lib.gb_genes_ld(self.ctx.h, self.h, len(go) - 1, _ptr(go), _ptr(r), _ptr(w), float(diag),
+                                                _ptr(out)))
+        offs = np.concatenate([[0], np.cumsum(sizes * sizes)])
+        return [out[offs[g]:offs[g + 1]].reshape(sizes[g], sizes[g]) for g in range(len(sizes))]
 
     def zmix_pair_cor(self, rows, z):
         """gb_zmix_pair_cor: prep_zmix5's pair matrix [n(n-1)/2, 1 + P] (column 0 = z_i z_j)."""

@@ -27,6 +27,7 @@ struct gb_batch {
   Panel* panel = nullptr;
   int mode = GRAM_MIX;
   bool ld_mode = false;      // computeLD: T x T only, full symmetric output, no solve
+  double ld_diag = 1.0;      // value forced on the diagonal in ld_mode (computeLD.cpp:107: 1.0; gene.cpp:578: 1 + lambda)
   bool counts_mode = false;  // raw per-population counts
   gb_params params{};
   int64_t n_windows = 0;
@@ -187,7 +188,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   gp.mode = b->counts_mode ? GRAM_COUNTS : b->mode;
   gp.mirror = b->ld_mode ? 1 : 0;
   gp.raw_out = (gp.mode == GRAM_MIX && b->fkind != 0) ? 1 : 0;
-  gp.diag = b->ld_mode ? 1.0 : 1.0 + b->params.lambda;   // computeLD.cpp:107 vs dist.cpp:172
+  gp.diag = b->ld_mode ? b->ld_diag : 1.0 + b->params.lambda;   // computeLD.cpp:107 vs dist.cpp:172
 
   // ---- windows
   b->plan_status.assign((size_t)nw, GB_OK);
@@ -460,7 +461,7 @@ int run_stage(gb_batch* b, int stage) {
 int create_batch_internal(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const int64_t* t_off,
                           const int64_t* rows_t, const int64_t* u_off, const int64_t* rows_u, const double* z_t,
                           const double* pop_wgt, const gb_params* params, bool ld_mode, bool counts_mode,
-                          gb_batch** out, bool defer_flag_check = false) {
+                          gb_batch** out, bool defer_flag_check = false, double ld_diag = 1.0) {
   if (!ctx || !panel || !out || n_windows < 0 || !t_off || (!rows_t && t_off[n_windows] > 0)) {
     if (ctx) ctx->err = "null or negative argument";
     return GB_ERR_BAD_ARG;
@@ -477,6 +478,7 @@ int create_batch_internal(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const
   b->panel = panel;
   b->mode = (pop_wgt || counts_mode) ? GRAM_MIX : GRAM_POOLED;
   b->ld_mode = ld_mode;
+  b->ld_diag = ld_diag;
   b->counts_mode = counts_mode;
   if (params) b->params = *params;
   else gb_params_default(&b->params);
@@ -985,6 +987,53 @@ int gb_window_ld(gb_ctx* ctx, gb_panel* panel, int64_t n, const int64_t* rows, c
       if (e != cudaSuccess) {
         ctx->err = cudaGetErrorString(e);
         rc = GB_ERR_CUDA;
+      }
+    }
+  }
+  gb_batch_destroy(b);
+  return rc;
+}
+
+// ---- per-gene LD blocks (BASELINE config 5: jepeg / jepegmix, gene.cpp:300-316 and 569-587) ---------------
+// CorG of every gene in ONE batch: gene g owns rows[g_off[g] .. g_off[g+1]) and gets its n_g x n_g correlation
+// matrix (symmetric, so column-major == row-major) with `diag` forced on the diagonal (1 + lambda in
+// Gene::CalJepegPval / CalJepegmixPval, 1.0 in computeLD).  pop_wgt == NULL -> pooled CalCor (jepeg), else the
+// CalWgtCov correlation (jepegmix).  Blocks are written back to back in gene order.  The <= 6 x 6 category
+// algebra and the p-values that follow stay in the Rcpp caller.
+int gb_genes_ld(gb_ctx* ctx, gb_panel* panel, int64_t n_genes, const int64_t* g_off, const int64_t* rows,
+                const double* pop_wgt, double diag, double* out) {
+  if (!ctx || !panel || n_genes < 0 || !g_off || (!rows && g_off[n_genes] > 0) || !out) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  if (n_genes == 0) return GB_OK;
+  gb_params p;
+  gb_params_default(&p);
+  p.min_num_measured_snp = 0;   // a gene may hold a single SNP
+  gb_batch* b = nullptr;
+  int rc = create_batch_internal(ctx, panel, n_genes, g_off, rows, nullptr, nullptr, nullptr, pop_wgt, &p, true, false, &b,
+                                 false, diag);
+  if (rc) return rc;
+  rc = run_stage(b, 0);
+  if (!rc) rc = run_stage(b, 1);
+  if (!rc) {
+    std::vector<double> tt((size_t)std::max<long long>(b->tt_elems, 1));
+    cudaError_t e = cudaMemcpyAsync(tt.data(), b->d_tt, sizeof(double) * (size_t)b->tt_elems, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->err = cudaGetErrorString(e);
+      rc = GB_ERR_CUDA;
+    } else {
+      std::vector<int64_t> out_off((size_t)n_genes + 1, 0);
+      for (int64_t g = 0; g < n_genes; g++) {
+        const int64_t n = g_off[g + 1] - g_off[g];
+        out_off[(size_t)g + 1] = out_off[(size_t)g] + n * n;
+      }
+      for (size_t a = 0; a < b->h_wins.size(); a++) {   // h_wins is sorted by size; active[] maps back to the gene
+        const SolveWin& w = b->h_wins[a];
+        double* dst = out + out_off[(size_t)b->active[a]];
+        for (int c = 0; c < w.n_t; c++)
+          std::memcpy(dst + (size_t)c * w.n_t, tt.data() + w.off_tt + (size_t)c * w.ld_t, sizeof(double) * (size_t)w.n_t);
       }
     }
   }

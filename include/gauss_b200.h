@@ -138,6 +138,12 @@ GB_API int gb_window_distmix(gb_ctx *ctx, gb_panel *panel, int64_t n_t, const in
 /* computeLD block: cormat is n x n (symmetric; column-major == row-major), diagonal exactly 1.0. */
 GB_API int gb_window_ld(gb_ctx *ctx, gb_panel *panel, int64_t n, const int64_t *rows,
                  const double *pop_wgt, double *cormat);
+/* Per-gene LD blocks of jepeg() / jepegmix() (CorG, gene.cpp:300-316 and 569-587) for many genes in one batch:
+ * gene g owns rows[g_off[g] .. g_off[g+1]) (>= 1 SNP); its n_g x n_g correlation matrix, `diag` forced on the
+ * diagonal (1 + lambda there, 1.0 in computeLD), is written at out + sum_{h<g} n_h^2.  pop_wgt == NULL selects the
+ * pooled CalCor of jepeg(). */
+GB_API int gb_genes_ld(gb_ctx *ctx, gb_panel *panel, int64_t n_genes, const int64_t *g_off, const int64_t *rows,
+                const double *pop_wgt, double diag, double *out);
 /* Parity/debug surface: the correlation blocks the solve consumes.  pop_wgt == NULL selects the
  * pooled Pearson r of dist().  B11 is n_t x n_t symmetric with diagonal 1+lambda; B21 is
  * n_u x n_t row-major. */
