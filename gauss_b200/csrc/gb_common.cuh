@@ -83,7 +83,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side_stream = nullptr;   // lazily created: the factorisation beside the B21 Gram tiles (gb_batch_run)
   int seg_order = 2;                    // processing order of the populations in the regrouped Gram fold (GB_SEG_ORDER)
-  int chol_sms = 48;                    // SMs the B21 Gram launch leaves to it (GB_CHOL_SMS; 0 = run the stages one after another)
+  int chol_sms = 64;                    // SMs the B21 Gram launch leaves to it (GB_CHOL_SMS; 0 = run the stages one after another)
   cudaStream_t copy_stream = nullptr;   // lazily created: host->device copies of the chromosome driver
   std::string err;
   int64_t launches = 0;

@@ -120,18 +120,14 @@ __device__ __noinline__ bool invchol_warp(const double* Ms, double* Xs, int o, d
 // memory -- warp 0 inverts the 16 x 16 diagonal block in registers, all 8 warps form the panel blocks
 // L_ik = A_ik inv(L_kk)^T and the trailing update -- followed by the block forward substitution
 //   X_ij = -X_ii sum_{q=j..i-1} L_iq X_qj   (i > j),   X = inv(L_kk).
-__global__ void __launch_bounds__(256)
-chol_diag_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt, double* dinv, int* status,
-                 const int* __restrict__ skip, int k) {
-  if (skip && skip[blockIdx.x]) return;  // certificate copy whose analytic bound already holds
-  const SolveWin w = wins[blockIdx.x];
+__device__ __forceinline__ void chol_diag_body(const SolveWin& w, int win, const double* __restrict__ tt, double* dinv,
+                                               int* status, int k, double* sm) {
   const int n = w.n_t;
   if (k >= win_nb(n)) return;
   const double* A = tt + w.off_tt;
   const int ld = w.ld_t;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int B = 16, NBLK = NB / B;
-  extern __shared__ __align__(16) double sm[];
   double* Ms = sm;                      // [64][MP] A_kk (lower); off-diagonal blocks become L
   double* Xs = Ms + NB * MP;            // [64][MP] inv(L_kk)
   double* Tb = Xs + NB * MP;            // [3][16][17] block temporaries of the substitution
@@ -206,11 +202,20 @@ chol_diag_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ t
       }
     __syncthreads();
   }
-  if (!ok_s && tid == 0) atomicOr(&status[blockIdx.x], STATUS_BREAKDOWN);
+  if (!ok_s && tid == 0) atomicOr(&status[win], STATUS_BREAKDOWN);
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int c = idx >> 6, r = idx & 63;
     dinv[w.off_dinv + (long long)k * NB * NB + c * NB + r] = Xs[c * MP + r];  // zero above the diagonal
   }
+}
+
+__global__ void __launch_bounds__(256)
+chol_diag_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt, double* dinv, int* status,
+                 const int* __restrict__ skip, int k) {
+  if (skip && skip[blockIdx.x]) return;  // certificate copy whose analytic bound already holds
+  extern __shared__ __align__(16) double sm[];
+  const SolveWin w = wins[blockIdx.x];
+  chol_diag_body(w, blockIdx.x, tt, dinv, status, k, sm);
 }
 
 // Step k, part 2: panel blocks below the diagonal, L_ik = A_ik inv(L_kk)^T, one CTA per block.
@@ -268,7 +273,8 @@ chol_panel_kernel(const SolveWin* __restrict__ wins, double* tt, const double* _
 
 // trailing update of step k: A_ij -= L_ik L_jk^T for k < j <= i
 __global__ void __launch_bounds__(256)
-chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, const int* __restrict__ skip, int k) {
+chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, double* dinv, int* status,
+                   const int* __restrict__ skip, int k) {
   if (skip && skip[blockIdx.y]) return;
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t;
@@ -320,6 +326,13 @@ chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, const int* __r
         const int c = j0 + 16 * (warp & 3) + 8 * nt + 2 * tig + e;
         if (r < n && c < n && r >= c) A[(long long)c * ld + r] = C[mt][nt][e];
       }
+  }
+  // Look-ahead: the CTA that has just finished the next diagonal tile (k+1, k+1) factors and inverts it right away,
+  // while the other CTAs of this launch are still updating the rest of the trailing matrix.  The 64 x 64
+  // factorisation is the sequential part of a block step; as a separate launch it sat on the critical path.
+  if (t == 0) {
+    __syncthreads();   // the tile is complete in global memory (visible to this CTA) and the operand buffers are free
+    chol_diag_body(w, blockIdx.y, tt, dinv, status, k + 1, sm);
   }
 }
 
@@ -647,8 +660,8 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
   if (n_wins == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
   const size_t smem_panel = sizeof(double) * 2 * NB * TS;
-  const size_t smem_update = sizeof(double) * 2 * NB * TS;
   const size_t smem_diag = sizeof(double) * (2 * NB * MP + 3 * 16 * 17 + 32);
+  const size_t smem_update = std::max(sizeof(double) * 2 * NB * TS, smem_diag);   // the update CTA of tile (k+1, k+1) also factors it
   static bool attr_set_dev[64] = {};
   bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) {
@@ -657,15 +670,39 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
     GB_CUDA(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update));
     attr_set = true;
   }
-  for (int k = 0; k < nb_max; k++) {
-    chol_diag_kernel<<<n_wins, 256, smem_diag, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status, d_skip, k);
-    ctx->launches++;
+  // diagonal block 0 by its own launch; every later one is factored inside the update launch that completes it
+  const bool trace = getenv("GB_CHOL_TRACE") != nullptr;   // diagnostics: event-timed kernels, printed per call
+  std::vector<cudaEvent_t> ev;
+  auto mark = [&]() {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, ctx->stream);
+    ev.push_back(e);
+  };
+  mark();
+  chol_diag_kernel<<<n_wins, 256, smem_diag, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status, d_skip, 0);
+  ctx->launches++;
+  mark();
+  for (int k = 0; k + 1 < nb_max; k++) {
     const int tb = nb_max - k - 1;
-    if (tb > 0) {
-      chol_panel_kernel<<<dim3(tb, n_wins), 256, smem_panel, ctx->stream>>>(d_wins, d_tt, d_dinv, d_skip, k);
-      chol_update_kernel<<<dim3(tb * (tb + 1) / 2, n_wins), 256, smem_update, ctx->stream>>>(d_wins, d_tt, d_skip, k);
-      ctx->launches += 2;
+    chol_panel_kernel<<<dim3(tb, n_wins), 256, smem_panel, ctx->stream>>>(d_wins, d_tt, d_dinv, d_skip, k);
+    mark();
+    chol_update_kernel<<<dim3(tb * (tb + 1) / 2, n_wins), 256, smem_update, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status,
+                                                                                         d_skip, k);
+    mark();
+    ctx->launches += 2;
+  }
+  if (trace) {
+    cudaStreamSynchronize(ctx->stream);
+    fprintf(stderr, "[chol trace] diag0 ");
+    for (size_t i = 0; i + 1 < ev.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      fprintf(stderr, "%s%.1f", i == 0 ? "" : (i % 2 ? " | P " : " U "), ms * 1e3);
     }
+    fprintf(stderr, " (us)\n");
+    for (auto e : ev) cudaEventDestroy(e);
   }
   GB_CUDA(cudaGetLastError());
   return GB_OK;
