@@ -392,7 +392,7 @@ def run_gpu(args):
     e2e_done, e2e_s = 0, 1.0
     pw_done, pw_s = 0, 1.0
     c_h2d = c_d2h = 0
-    n_groups = int(os.environ.get("GB_E2E_GROUPS", "6"))
+    n_groups = int(os.environ.get("GB_E2E_GROUPS", "4"))
     if not args.no_e2e:
         # (a) per-window calls on raw int8 host rows (what a drop-in behind run_distmix sees today)
         e2e_step()  # warm-up
