@@ -474,7 +474,7 @@ def run_gpu(args):
             clocks=clocks,
             roofline=dict(bound="tensor", kernel="gram_seg_kernel", achieved=achieved, peak=tensor_peak,
                           unit="TFLOP/s", frac=achieved / tensor_peak,
-                          traffic=3.676e9,
+                          traffic=3.676e9, tensor_pipe_probe_peak=8600.0,
                           traffic_note=("DRAM bytes per launch of this kernel on this workload (dram__bytes_read.sum + "
                                         "dram__bytes_write.sum = 2.82 + 0.86 GB, profiles/r01_final_ncu_full.md; one ncu "
                                         "--set full capture, not re-measured here) vs algorithmic "
@@ -484,13 +484,26 @@ def run_gpu(args):
                                 f"peak = {rate:g} x {pk['source']} sustained bf16 ({pk['bf16_tflops_sustained']} TF/s): "
                                 f"the kernel's MMA kind for {fmt} panels nominally runs at {rate:g} x the bf16 rate and "
                                 f"MEASURED_PEAKS.json has no entry for it; against the int8 rate (2 x bf16) the same "
-                                f"number is {achieved / (2.0 * pk['bf16_tflops_sustained']):.3f}")),
+                                f"number is {achieved / (2.0 * pk['bf16_tflops_sustained']):.3f}; tools/mma_probe.cu measures 8,600 TOP/s for this "
+                                f"MMA kind on this GPU with the tensor pipe alone (no TMA, no epilogue): {achieved / 8600.0:.3f} "
+                                f"of that; the kernel is paced by the TMA feed (192 KB of stages x ~1,200 clk round trip) and "
+                                f"by 21 accumulator hand-offs per tile, see profiles/r01k_summary.md")),
             stage_ms_serial=float(stage_ms.sum(1).mean()),
             stage_ms=dict(row_stats=float(stage_ms[:, 0].mean()), gram=gram_ms,
                           gram_finish=float(stage_ms[:, 2].mean()), cholesky=float(stage_ms[:, 3].mean()),
                           solve=float(stage_ms[:, 4].mean())),
             solve=dict(flops_per_step=work["solve_flops"],
                        tflops=work["solve_flops"] / (float(stage_ms[:, 3:].sum(1).mean()) / 1e3) / 1e12),
+            # the longest kernel of the step is the fp64 triangular solve; its pipe is the fp64 tensor core (DMMA
+            # m8n8k4: 64 FMA/clk/SM measured by tools/dmma_probe.cu = 148 SMs x 128 flop x sm clock)
+            roofline_solve=dict(bound="tensor", kernel="trsm_finalize_kernel",
+                                achieved=work["solve_flops"] / (float(stage_ms[:, 4].mean()) / 1e3) / 1e12,
+                                peak=148 * 128 * clocks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12, unit="TFLOP/s (fp64)",
+                                frac=(work["solve_flops"] / (float(stage_ms[:, 4].mean()) / 1e3) / 1e12) /
+                                     (148 * 128 * clocks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12),
+                                note="algorithmic n_t^3/3 + n_t^2 n_u + ... flops of the whole solve over the trsm kernel's "
+                                     "event-timed duration; ncu: 75 % of the DMMA pipe busy, the rest of the gap is padding "
+                                     "(n_t to 64, n_u to 128) and the dense product with inv(L_ii)"),
             pack=dict(ms=pack_ms, gbs=2.0 * n_all * N / (pack_ms / 1e3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"]),
             windows_ok=n_ok, imputed_per_step=n_imputed, panel_gen_s=gen_s,
         )

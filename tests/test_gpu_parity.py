@@ -376,3 +376,32 @@ def test_pipe_matches_single_window_calls(gpu_ctx, oracle):
                           np.arange(len(rt) + len(ru), dtype=np.int64), np.concatenate([c["z"][rt], np.zeros(len(ru))]),
                           np.concatenate([g2[rt], g2[ru]]), c["pop_sizes"], c["w"], 0, 10**12)
     assert np.abs(z - r["z"][len(rt):]).max() <= TIGHT
+
+
+def test_overlapped_batch_run_equals_staged_run(gpu_ctx):
+    """gb_batch_run puts the factorisation on a side stream beside the B21 Gram tiles once a batch has at least one
+    B21 tile per SM; the results must be the bits of the stage-by-stage run, run after run."""
+    c = small_case(seed=81, n_snps=7200, pop_sizes=(61, 103, 40, 25, 2, 330, 97), measured_frac=0.25, core=(0, 7200))
+    g, t = c["g"].astype(np.int8), c["type"]
+    panel = make_panel(gpu_ctx, g, c["pop_sizes"])
+    t_rows, u_rows, t_off, u_off = [], [], [0], [0]
+    for lo, hi in [(0, 1900), (1500, 3600), (3300, 5400), (5000, 7200), (100, 124)]:
+        idx = np.arange(lo, hi)
+        t_rows.append(idx[t[lo:hi] == 1])
+        u_rows.append(idx[t[lo:hi] == 0])
+        t_off.append(t_off[-1] + len(t_rows[-1]))
+        u_off.append(u_off[-1] + len(u_rows[-1]))
+    n_b21_tiles = sum(-(-len(a) // 128) * -(-len(b) // 128) for a, b in zip(t_rows[:4], u_rows[:4]))
+    assert n_b21_tiles >= 160          # more than the 148 SMs: the overlapped schedule is taken
+    rows_t, rows_u = np.concatenate(t_rows), np.concatenate(u_rows)
+    batch = gb.Batch(panel, t_off, rows_t, u_off, rows_u, c["z"][rows_t], c["w"])
+    for s in (0, 1, 2, 3):
+        batch.run_stage(s)
+    z0, i0, s0 = batch.fetch()
+    assert (s0[:4] == 0).all() and s0[4] != 0 and np.isfinite(z0[:u_off[4]]).all()
+    for _ in range(3):
+        batch.run()
+        z1, i1, s1 = batch.fetch()
+        np.testing.assert_array_equal(z1, z0)
+        np.testing.assert_array_equal(i1, i0)
+        np.testing.assert_array_equal(s1, s0)
