@@ -143,7 +143,9 @@ def pack2_rows_host(pop_sizes, rows: np.ndarray, is_ascii: bool | None = None, o
     """HOST-side packer: [n, n_samples] int8 dosages / uint8 chars -> [n, pack2_row_bytes] uint8 (CPU threads)."""
     lib = load_library()
     ps = np.ascontiguousarray(pop_sizes, np.int32)
-    assert rows.ndim == 2 and rows.itemsize == 1 and (rows.size == 0 or rows.strides[1] == 1)
+    assert rows.ndim == 2 and rows.itemsize == 1
+    if rows.size and rows.strides[1] != 1:
+        rows = np.ascontiguousarray(rows)
     if is_ascii is None:
         is_ascii = rows.dtype == np.uint8
     rb = pack2_row_bytes(ps)

@@ -1,0 +1,179 @@
+"""On-disk packed panel (`.gbpack`): the cached form of the reference's BGZF text panel.
+
+The reference re-inflates and re-parses `*_geno.gz` for every call (ReadGenotype, gauss.cpp:720-785: one text line per
+SNP with one '0'/'1'/'2' string per population followed by one allele frequency per population, gauss.cpp:572-585).
+`convert_reference_panel` does that once and stores every SNP as a pack2 row over ALL populations -- 2 bits per dosage,
+each population block on a 128-dosage (32-byte) boundary -- so a later call memory-maps the file, picks the byte ranges
+of the populations its `pop_flag_vec` selects (init_pop_flag_vec, gauss.cpp:1019-1066) and hands rows that are already
+in the layout `gb_panel_append_pack2_host` / `gb_chrom_run_pack2` take.  Host-side I/O only: no statistics are computed
+here.  `flip_rows` is the packed-row form of FlipGenotypeVec (util.cpp), which ReadGenotype has switched off
+(gauss.cpp:767-776: the alleles of the Z file are matched to the panel instead); it is kept for callers that flip.
+
+File layout: b"GBPACK2\\n", uint64 little-endian header length, JSON header (version, pops, sizes, super_pops, n_rows,
+row_bytes), zero padding to a 4096-byte boundary, then n_rows * row_bytes bytes.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+
+import numpy as np
+
+from . import api
+
+MAGIC = b"GBPACK2\n"
+ALIGN = 4096
+
+
+def read_pop_desc(path: str):
+    """Population description file (gauss.cpp:970-985): one header line, then `pop n_subjects super_pop [...]`."""
+    pops, sizes, sups = [], [], []
+    with open(path) as f:
+        next(f)
+        for line in f:
+            tok = line.split()
+            if len(tok) >= 3:
+                pops.append(tok[0].upper())
+                sizes.append(int(tok[1]))
+                sups.append(tok[2].upper())
+    return pops, np.array(sizes, np.int32), sups
+
+
+def _block_bytes(sizes) -> np.ndarray:
+    return (np.asarray(sizes, np.int64) + 127) // 128 * 32
+
+
+def convert_reference_panel(geno_gz: str, pop_desc: str, out_path: str, chunk_rows: int = 4096) -> dict:
+    """Reference data file (BGZF is a sequence of gzip members, so `gzip` reads it) -> `.gbpack`.  Returns the header."""
+    pops, sizes, sups = read_pop_desc(pop_desc)
+    P, N = len(pops), int(sizes.sum())
+    row_bytes = api.pack2_row_bytes(sizes)
+    header = dict(version=1, pops=pops, sizes=[int(x) for x in sizes], super_pops=sups, n_rows=0, row_bytes=row_bytes)
+
+    def header_blob(h):
+        js = json.dumps(h).encode()
+        blob = MAGIC + np.uint64(len(js)).tobytes() + js
+        return blob + b"\0" * (-len(blob) % ALIGN)
+
+    # the header's length must not change when n_rows is filled in: reserve digits
+    header["n_rows"] = 10 ** 15
+    data_off = len(header_blob(header))
+    n_rows = 0
+    buf = np.empty((chunk_rows, N), np.uint8)
+    with gzip.open(geno_gz, "rb") as f, open(out_path, "wb") as out:
+        out.write(b"\0" * data_off)
+        fill = 0
+
+        def flush():
+            nonlocal fill
+            if fill:
+                out.write(api.pack2_rows_host(sizes, buf[:fill], is_ascii=True).tobytes())
+                fill = 0
+
+        for line in f:
+            tok = line.split()
+            if not tok:
+                continue
+            if len(tok) < P:
+                raise ValueError(f"line {n_rows + 1}: {len(tok)} fields, expected at least {P} genotype strings")
+            off = 0
+            for k in range(P):
+                s = tok[k]
+                if len(s) != sizes[k]:
+                    raise ValueError(f"line {n_rows + 1}: population {pops[k]} has {len(s)} genotypes, expected {sizes[k]}")
+                buf[fill, off:off + len(s)] = np.frombuffer(s, np.uint8)
+                off += len(s)
+            fill += 1
+            n_rows += 1
+            if fill == chunk_rows:
+                flush()
+        flush()
+        header["n_rows"] = n_rows
+        blob = header_blob(header)
+        blob = blob + b"\0" * (data_off - len(blob))
+        assert len(blob) == data_off
+        out.seek(0)
+        out.write(blob)
+    return header
+
+
+class PackFile:
+    """Memory-mapped `.gbpack`."""
+
+    def __init__(self, path: str):
+        with open(path, "rb") as f:
+            if f.read(len(MAGIC)) != MAGIC:
+                raise ValueError(f"{path} is not a GBPACK2 file")
+            hlen = int(np.frombuffer(f.read(8), np.uint64)[0])
+            self.header = json.loads(f.read(hlen))
+        self.pops = self.header["pops"]
+        self.super_pops = self.header["super_pops"]
+        self.sizes = np.array(self.header["sizes"], np.int32)
+        self.n_rows, self.row_bytes = int(self.header["n_rows"]), int(self.header["row_bytes"])
+        data_off = -(-(len(MAGIC) + 8 + hlen) // ALIGN) * ALIGN
+        if os.path.getsize(path) != data_off + self.n_rows * self.row_bytes:
+            raise ValueError(f"{path}: size does not match its header")
+        self.rows = np.memmap(path, np.uint8, "r", offset=data_off, shape=(self.n_rows, self.row_bytes))
+        self._boff = np.concatenate([[0], np.cumsum(_block_bytes(self.sizes))])
+
+    def flags_for(self, study_pop: str | None = None, weights: dict | None = None) -> np.ndarray:
+        """pop_flag_vec as the reference builds it: by population or super-population name (init_pop_flag_vec,
+        gauss.cpp:1019-1066) or by the populations a weight table names (init_pop_flag_wgt_vec, gauss.cpp:1093-1117)."""
+        if weights is not None:
+            names = {k.upper() for k in weights}
+            return np.array([p in names for p in self.pops])
+        sp = study_pop.upper()
+        return np.array([p == sp or s == sp for p, s in zip(self.pops, self.super_pops)])
+
+    def select(self, row_idx, flags, out: np.ndarray | None = None):
+        """pack2 rows of the listed SNPs restricted to the flagged populations -> (rows2, flagged sizes).
+
+        A population block is a whole number of 32-byte units in both layouts, so this is a byte-range gather."""
+        flags = np.asarray(flags, bool)
+        idx = np.asarray(row_idx, np.int64)
+        sizes = self.sizes[flags]
+        rb = api.pack2_row_bytes(sizes)
+        if out is None:
+            out = np.empty((len(idx), rb), np.uint8)
+        assert out.shape == (len(idx), rb)
+        src = self.rows[idx] if len(idx) else np.empty((0, self.row_bytes), np.uint8)
+        o = 0
+        for k in np.where(flags)[0]:
+            n = int(self._boff[k + 1] - self._boff[k])
+            out[:, o:o + n] = src[:, self._boff[k]:self._boff[k + 1]]
+            o += n
+        out[:, o:] = 0
+        return out, sizes
+
+
+_FLIP = np.zeros(256, np.uint8)
+for _b in range(256):
+    _v = 0
+    for _q in range(4):
+        _c = (_b >> (2 * _q)) & 3
+        _v |= ((2 - _c) & 3 if _c < 3 else 3) << (2 * _q)
+    _FLIP[_b] = _v
+
+
+def flip_rows(rows2: np.ndarray, sizes, which) -> None:
+    """In place: dosage x -> 2 - x for the rows in `which` (FlipGenotypeVec, util.cpp; disabled in the reference's
+    ReadGenotype, gauss.cpp:767-776).  Padding stays zero."""
+    which = np.asarray(which)
+    if which.dtype != bool:
+        m = np.zeros(rows2.shape[0], bool)
+        m[which] = True
+        which = m
+    if not which.any():
+        return
+    sub = _FLIP[rows2[which]]
+    boff = np.concatenate([[0], np.cumsum(_block_bytes(sizes))])
+    for k, m in enumerate(np.asarray(sizes, np.int64)):
+        full, rem = divmod(int(m), 4)
+        start = int(boff[k]) + full
+        if rem:
+            sub[:, start] &= (1 << (2 * rem)) - 1      # dosages past the population's size in its last byte
+            start += 1
+        sub[:, start:int(boff[k + 1])] = 0               # padding bytes of the block
+    sub[:, int(boff[-1]):] = 0
+    rows2[which] = sub
