@@ -392,6 +392,7 @@ def run_gpu(args):
     e2e_done, e2e_s = 0, 1.0
     pw_done, pw_s = 0, 1.0
     c_h2d = c_d2h = 0
+    host_fmt, row2, host_pack_s = os.environ.get("GB_E2E_HOST_FORMAT", "pack5"), 0, 0.0
     n_groups = int(os.environ.get("GB_E2E_GROUPS", "4"))
     if not args.no_e2e:
         # (a) per-window calls on raw int8 host rows (what a drop-in behind run_distmix sees today)
@@ -405,18 +406,21 @@ def run_gpu(args):
         # (b) chromosome driver on the 2-bit host panel (packed ONCE on the host, outside the timed region, like a
         # cached packed panel file): H2D of the pack2 rows in chunks on a copy stream, expansion, the window batches
         # as their rows land, D2H of z / info -- all inside the timed region, results checked against the resident run
-        row2 = gb.api.pack2_row_bytes(sizes)
+        host_fmt = os.environ.get("GB_E2E_HOST_FORMAT", "pack5")      # pack5: 1.6 bits per dosage, pack2: 2 bits
+        row2 = gb.api.pack5_row_bytes(sizes) if host_fmt == "pack5" else gb.api.pack2_row_bytes(sizes)
         host2 = torch.empty((n_all, row2), dtype=torch.uint8, pin_memory=True)
         t0 = time.perf_counter()
-        gb.api.pack2_rows_host(sizes, host.numpy(), is_ascii=False, out=host2.numpy())
+        (gb.api.pack5_rows_host if host_fmt == "pack5" else gb.api.pack2_rows_host)(
+            sizes, host.numpy(), is_ascii=False, out=host2.numpy())
         host_pack_s = time.perf_counter() - t0
         panel2 = gb.Panel(ctx, sizes, n_all, "e2m1")
         z_pin = torch.empty(int(u_off[-1]), dtype=torch.float64, pin_memory=True)
         i_pin = torch.empty(int(u_off[-1]), dtype=torch.float64, pin_memory=True)
 
         def chrom_step():
-            _, _, st = panel2.chrom_run_pack2(host2.data_ptr(), n_all, row2, t_off, rows_t, u_off, rows_u, z_t, w,
-                                              n_groups=n_groups, z=z_pin.numpy(), info=i_pin.numpy())
+            run = panel2.chrom_run_pack5 if host_fmt == "pack5" else panel2.chrom_run_pack2
+            _, _, st = run(host2.data_ptr(), n_all, row2, t_off, rows_t, u_off, rows_u, z_t, w,
+                           n_groups=n_groups, z=z_pin.numpy(), info=i_pin.numpy())
             return st
 
         st = chrom_step()  # warm-up (first call also sizes the staging allocation)
@@ -462,10 +466,12 @@ def run_gpu(args):
             config=workload_config(),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(c_h2d), d2h_bytes_per_step=int(c_d2h),
                      steps=e2e_steps, ms_per_step=e2e_ms_max / e2e_steps,
-                     note=f"gb_chrom_run_pack2 (C-ABI chromosome driver): pinned HOST 2-bit panel rows -> H2D in {n_groups} "
+                     host_format=host_fmt, host_row_bytes=int(row2), host_pack_s=host_pack_s,
+                     note=f"gb_chrom_run_{host_fmt} (C-ABI chromosome driver): pinned HOST packed panel rows "
+                          f"({row2} B per SNP; pack5 = 5 dosages per byte, pack2 = 4) -> H2D in {n_groups} "
                           "chunks on a copy stream -> expand -> window batches as their rows land -> D2H of z/info; "
-                          "wall clock around the blocking calls; results asserted equal to the resident run; the 2-bit "
-                          "rows are packed once on the host outside the timed region (cached packed panel)"),
+                          "wall clock around the blocking calls; results asserted equal to the resident run; the packed "
+                          "rows are made once on the host outside the timed region (cached packed panel)"),
             e2e_per_window=dict(value=pw_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                                 steps=e2e_steps,
                                 note="per-window gb_pipe_submit / gb_pipe_wait (depth 3) on pinned host int8 rows: "

@@ -104,6 +104,11 @@ def load_library():
         "gb_panel_append_pack2_host": (C.c_int, [vp, i64, vp, i64]),
         "gb_chrom_run_pack2": (C.c_int, [vp, vp, i64, vp, i64, i64, i64p, i64p, i64p, i64p, dblp, dblp,
                                          C.POINTER(Params), C.c_int, dblp, dblp, vp]),
+        "gb_pack5_row_bytes": (i64, [C.c_int, i32p]),
+        "gb_pack5_rows_host": (C.c_int, [C.c_int, i32p, i64, vp, i64, C.c_int, vp, i64]),
+        "gb_panel_append_pack5_host": (C.c_int, [vp, i64, vp, i64]),
+        "gb_chrom_run_pack5": (C.c_int, [vp, vp, i64, vp, i64, i64, i64p, i64p, i64p, i64p, dblp, dblp,
+                                         C.POINTER(Params), C.c_int, dblp, dblp, vp]),
         "gb_pipe_create": (C.c_int, [vp, C.c_int, i32p, i64, C.c_int, C.c_int, C.POINTER(vp)]),
         "gb_pipe_destroy": (None, [vp]),
         "gb_pipe_submit": (C.c_int, [vp, i64, vp, i64, vp, i64, C.c_int, dblp, dblp, C.POINTER(Params), dblp, dblp,
@@ -139,7 +144,19 @@ def pack2_row_bytes(pop_sizes) -> int:
     return int(load_library().gb_pack2_row_bytes(len(ps), _ptr(ps)))
 
 
-def pack2_rows_host(pop_sizes, rows: np.ndarray, is_ascii: bool | None = None, out: np.ndarray | None = None):
+def pack5_row_bytes(pop_sizes) -> int:
+    """Bytes per SNP row of the ternary host format, five dosages per byte (gb_pack5_row_bytes)."""
+    ps = np.ascontiguousarray(pop_sizes, np.int32)
+    return int(load_library().gb_pack5_row_bytes(len(ps), _ptr(ps)))
+
+
+def pack5_rows_host(pop_sizes, rows: np.ndarray, is_ascii: bool | None = None, out: np.ndarray | None = None):
+    """HOST-side packer of the ternary format (gb_pack5_rows_host); same contract as pack2_rows_host."""
+    return pack2_rows_host(pop_sizes, rows, is_ascii, out, _fmt=5)
+
+
+def pack2_rows_host(pop_sizes, rows: np.ndarray, is_ascii: bool | None = None, out: np.ndarray | None = None,
+                    _fmt: int = 2):
     """HOST-side packer: [n, n_samples] int8 dosages / uint8 chars -> [n, pack2_row_bytes] uint8 (CPU threads)."""
     lib = load_library()
     ps = np.ascontiguousarray(pop_sizes, np.int32)
@@ -148,13 +165,14 @@ def pack2_rows_host(pop_sizes, rows: np.ndarray, is_ascii: bool | None = None, o
         rows = np.ascontiguousarray(rows)
     if is_ascii is None:
         is_ascii = rows.dtype == np.uint8
-    rb = pack2_row_bytes(ps)
+    rb = pack5_row_bytes(ps) if _fmt == 5 else pack2_row_bytes(ps)
     if out is None:
         out = np.empty((rows.shape[0], rb), np.uint8)
     assert out.shape == (rows.shape[0], rb) and (out.size == 0 or out.strides[1] == 1)
     if rows.shape[0] == 0:
         return out
-    rc = lib.gb_pack2_rows_host(len(ps), _ptr(ps), rows.shape[0], rows.ctypes.data, rows.strides[0],
+    fn = lib.gb_pack5_rows_host if _fmt == 5 else lib.gb_pack2_rows_host
+    rc = fn(len(ps), _ptr(ps), rows.shape[0], rows.ctypes.data, rows.strides[0],
                                 int(bool(is_ascii)), out.ctypes.data, out.strides[0])
     if rc != GB_OK:
         raise GaussB200Error(rc, lib.gb_status_string(rc).decode())
@@ -277,8 +295,20 @@ class Panel:
         self.ctx.check(self.ctx.lib.gb_panel_append_pack2_host(self.h, rows2.shape[0], rows2.ctypes.data,
                                                                rows2.strides[0]))
 
-    def chrom_run_pack2(self, rows2_ptr: int, n_rows: int, row_stride: int, t_off, rows_t, u_off, rows_u, z_t,
+    def append_pack5_host(self, rows5: np.ndarray):
+        """rows5: [n, pack5_row_bytes] uint8 rows of the ternary host format (E2M1 panels only)."""
+        assert rows5.ndim == 2 and rows5.dtype == np.uint8 and rows5.strides[1] == 1
+        self.ctx.check(self.ctx.lib.gb_panel_append_pack5_host(self.h, rows5.shape[0], rows5.ctypes.data,
+                                                               rows5.strides[0]))
+
+    def chrom_run_pack5(self, rows5_ptr: int, n_rows: int, row_stride: int, t_off, rows_t, u_off, rows_u, z_t,
                         pop_wgt=None, params: Params | None = None, n_groups: int = 4, z=None, info=None):
+        """gb_chrom_run_pack5: as chrom_run_pack2 on ternary host rows."""
+        return self.chrom_run_pack2(rows5_ptr, n_rows, row_stride, t_off, rows_t, u_off, rows_u, z_t, pop_wgt, params,
+                                    n_groups, z, info, _fmt=5)
+
+    def chrom_run_pack2(self, rows2_ptr: int, n_rows: int, row_stride: int, t_off, rows_t, u_off, rows_u, z_t,
+                        pop_wgt=None, params: Params | None = None, n_groups: int = 4, z=None, info=None, _fmt: int = 2):
         """gb_chrom_run_pack2: one chromosome from pack2 HOST rows to HOST results (clears this panel)."""
         t_off, u_off, rt, ru, zt = _i64(t_off), _i64(u_off), _i64(rows_t), _i64(rows_u), _f64(z_t)
         w = None if pop_wgt is None else _f64(pop_wgt)
@@ -287,7 +317,8 @@ class Panel:
         z = np.zeros(n) if z is None else z
         info = np.zeros(n) if info is None else info
         status = np.zeros(nw, np.int32)
-        self.ctx.check(self.ctx.lib.gb_chrom_run_pack2(
+        fn = self.ctx.lib.gb_chrom_run_pack5 if _fmt == 5 else self.ctx.lib.gb_chrom_run_pack2
+        self.ctx.check(fn(
             self.ctx.h, self.h, int(n_rows), C.c_void_p(rows2_ptr), int(row_stride), nw, _ptr(t_off), _ptr(rt),
             _ptr(u_off), _ptr(ru), _ptr(zt), _ptr(w), C.byref(params) if params else None, int(n_groups), _ptr(z),
             _ptr(info), _ptr(status)))

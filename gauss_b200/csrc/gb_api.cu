@@ -10,6 +10,7 @@
 
 #include "gb_common.cuh"
 #include <atomic>
+#include <chrono>
 #include <thread>
 
 using namespace gb;
@@ -605,6 +606,8 @@ void gb_ctx_destroy(gb_ctx* ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  for (int i = 0; i < 2; i++)
+    if (ctx->chrom_streams[i]) cudaStreamDestroy(ctx->chrom_streams[i]);
   delete ctx;
 }
 
@@ -623,6 +626,20 @@ int gb_ctx_synchronize(gb_ctx* ctx) {
 
 const char* gb_last_error(const gb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 int64_t gb_ctx_launch_count(const gb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// pack5 host rows (five base-3 digits per byte): population p starts at byte boff[p], blocks padded to 4 bytes, the row
+// to 16.  Returns the row size in bytes (-1: bad sizes).
+static int pack5_layout(int n_pops, const int* pop_sizes, std::vector<int>* boff) {
+  long long b = 0;
+  if (boff) boff->clear();
+  for (int i = 0; i < n_pops; i++) {
+    if (pop_sizes[i] < 1) return -1;
+    if (boff) boff->push_back((int)b);
+    b += ((pop_sizes[i] + 4) / 5 + 3) / 4 * 4;
+    if (b > (1ll << 30)) return -1;
+  }
+  return (int)((b + 15) / 16 * 16);
+}
 
 // ---- panel ----------------------------------------------------------------------------------
 int gb_panel_create(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t capacity_rows, gb_panel** out) {
@@ -685,10 +702,14 @@ int gb_panel_create_fmt(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t c
   if ((rc = pmalloc((void**)&p->d_sxx, sizeof(int32_t) * (size_t)capacity_rows * n_pops))) return fail(rc);
   if ((rc = pmalloc((void**)&p->d_pop_sizes, sizeof(int) * (size_t)n_pops))) return fail(rc);
   if ((rc = pmalloc((void**)&p->d_koff, sizeof(int) * (size_t)n_pops))) return fail(rc);
+  if ((rc = pmalloc((void**)&p->d_boff5, sizeof(int) * (size_t)n_pops))) return fail(rc);
+  std::vector<int> boff5;
+  p->pack5_row_bytes = pack5_layout(n_pops, pop_sizes, &boff5);
   if ((rc = pmalloc((void**)&p->d_flags, sizeof(int)))) return fail(rc);
   cudaMemsetAsync(p->d_flags, 0, sizeof(int), ctx->stream);
   cudaMemcpyAsync(p->d_pop_sizes, p->pop_sizes.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(p->d_koff, p->koff.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(p->d_boff5, boff5.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
   if ((rc = make_row_tensor_maps(ctx, &p->tmaps, p->d_rows, capacity_rows, p->k_elems, p->k_stride,
                                  format == GB_PANEL_E2M1 ? MAP_E2M1_EXPAND : MAP_INT8)))
     return fail(rc);
@@ -708,6 +729,7 @@ void gb_panel_destroy(gb_panel* p) {
   if (p->d_sxx) cudaFree(p->d_sxx);
   if (p->d_pop_sizes) cudaFree(p->d_pop_sizes);
   if (p->d_koff) cudaFree(p->d_koff);
+  if (p->d_boff5) cudaFree(p->d_boff5);
   if (p->d_flags) cudaFree(p->d_flags);
   delete p;
 }
@@ -1235,14 +1257,69 @@ int gb_pack2_rows_host(int n_pops, const int* pop_sizes, int64_t n_rows, const v
   return bad.load() ? GB_ERR_UNSUPPORTED : GB_OK;
 }
 
-int gb_panel_append_pack2_host(gb_panel* p, int64_t n_rows, const void* rows2, int64_t row_stride) {
-  if (!p || n_rows < 0 || (!rows2 && n_rows > 0)) {
+// ---- ternary host rows ("pack5") ---------------------------------------------------------------------
+int64_t gb_pack5_row_bytes(int n_pops, const int* pop_sizes) {
+  if (n_pops < 1 || !pop_sizes) return -1;
+  return pack5_layout(n_pops, pop_sizes, nullptr);
+}
+
+int gb_pack5_rows_host(int n_pops, const int* pop_sizes, int64_t n_rows, const void* rows, int64_t row_stride,
+                       int is_ascii, void* out, int64_t out_stride) {
+  if (n_pops < 1 || !pop_sizes || n_rows < 0 || (n_rows && (!rows || !out))) return GB_ERR_BAD_ARG;
+  std::vector<int> boff;
+  const int rb = pack5_layout(n_pops, pop_sizes, &boff);
+  int64_t n_samples = 0;
+  for (int i = 0; i < n_pops; i++) n_samples += pop_sizes[i];
+  if (rb < 0 || out_stride < rb || row_stride < n_samples) return GB_ERR_BAD_ARG;
+  const int sub = is_ascii ? 48 : 0;
+  std::atomic<int> bad{0};
+  auto work = [&](int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1; r++) {
+      const uint8_t* src = static_cast<const uint8_t*>(rows) + r * row_stride;
+      uint8_t* dst = static_cast<uint8_t*>(out) + r * out_stride;
+      std::memset(dst, 0, (size_t)rb);
+      for (int p = 0; p < n_pops; p++) {
+        const int m = pop_sizes[p];
+        uint8_t* d = dst + boff[(size_t)p];
+        int j = 0;
+        for (; j + 5 <= m; j += 5) {
+          const unsigned a = (uint8_t)(src[j] - sub), b = (uint8_t)(src[j + 1] - sub), c = (uint8_t)(src[j + 2] - sub),
+                         e = (uint8_t)(src[j + 3] - sub), f = (uint8_t)(src[j + 4] - sub);
+          if (a > 2u || b > 2u || c > 2u || e > 2u || f > 2u) bad.store(1, std::memory_order_relaxed);
+          d[j / 5] = (uint8_t)(a + 3u * b + 9u * c + 27u * e + 81u * f);
+        }
+        unsigned v = 0, mul = 1;
+        for (int k = j; k < m; k++, mul *= 3) {
+          const unsigned a = (uint8_t)(src[k] - sub);
+          if (a > 2u) bad.store(1, std::memory_order_relaxed);
+          v += mul * (a % 3u);
+        }
+        if (j < m) d[j / 5] = (uint8_t)v;
+        src += m;
+      }
+    }
+  };
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(hw ? hw : 1, n_rows / 256));
+  if (nth <= 1) {
+    work(0, n_rows);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; t++) th.emplace_back(work, n_rows * t / nth, n_rows * (t + 1) / nth);
+    for (auto& t : th) t.join();
+  }
+  return bad.load() ? GB_ERR_UNSUPPORTED : GB_OK;
+}
+
+static int append_packed_host(gb_panel* p, int64_t n_rows, const void* rows_p, int64_t row_stride, int host_format) {
+  if (!p || n_rows < 0 || (!rows_p && n_rows > 0)) {
     if (p) p->ctx->err = "bad append arguments";
     return GB_ERR_BAD_ARG;
   }
   Ctx* ctx = p->ctx;
-  if (p->format != GB_PANEL_E2M1 || row_stride < p->k_elems / 4) {
-    ctx->err = "pack2 rows need an E2M1 panel and a row stride of at least gb_pack2_row_bytes()";
+  const int64_t need = host_format == 5 ? p->pack5_row_bytes : p->k_elems / 4;
+  if (p->format != GB_PANEL_E2M1 || row_stride < need) {
+    ctx->err = "packed host rows need an E2M1 panel and a row stride of at least gb_pack2/5_row_bytes()";
     return GB_ERR_BAD_ARG;
   }
   if (p->n_rows + n_rows > p->capacity) {
@@ -1255,9 +1332,10 @@ int gb_panel_append_pack2_host(gb_panel* p, int64_t n_rows, const void* rows2, i
   void* d = nullptr;
   const size_t bytes = (size_t)n_rows * (size_t)row_stride;
   GB_CUDA(cudaMallocAsync(&d, bytes, ctx->stream));
-  cudaError_t e = cudaMemcpyAsync(d, rows2, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  cudaError_t e = cudaMemcpyAsync(d, rows_p, bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
-    rc = launch_expand2(ctx, p, d, row_stride, p->n_rows, n_rows);
+    rc = host_format == 5 ? launch_expand5(ctx, p, d, row_stride, p->n_rows, n_rows)
+                          : launch_expand2(ctx, p, d, row_stride, p->n_rows, n_rows);
     if (!rc) p->n_rows += n_rows;
   } else {
     ctx->err = cudaGetErrorString(e);
@@ -1267,28 +1345,39 @@ int gb_panel_append_pack2_host(gb_panel* p, int64_t n_rows, const void* rows2, i
   return rc;
 }
 
+int gb_panel_append_pack5_host(gb_panel* p, int64_t n_rows, const void* rows5, int64_t row_stride) {
+  return append_packed_host(p, n_rows, rows5, row_stride, 5);
+}
+
+int gb_panel_append_pack2_host(gb_panel* p, int64_t n_rows, const void* rows2, int64_t row_stride) {
+  return append_packed_host(p, n_rows, rows2, row_stride, 2);
+}
+
 // ---- chromosome driver on pack2 HOST rows -----------------------------------------------------------
 // One call = one chromosome (or any bp-sorted run of windows) of dist()/distmix(): the pack2 rows are copied
 // to the GPU in n_groups contiguous chunks on a copy stream; the windows are cut into n_groups contiguous,
 // cost-balanced batches, and batch g starts as soon as the rows its windows touch have landed and been
 // expanded -- so all but the last batch's kernels hide behind the PCIe copy.  Results and statuses are
 // written to HOST buffers before the call returns.
-int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void* host_rows2, int64_t row_stride,
-                       int64_t n_windows, const int64_t* t_off, const int64_t* rows_t, const int64_t* u_off,
-                       const int64_t* rows_u, const double* z_t, const double* pop_wgt, const gb_params* params,
-                       int n_groups, double* z_u, double* info_u, int* window_status) {
+static int chrom_run_packed(gb_ctx* ctx, gb_panel* panel, int host_format, int64_t n_rows, const void* host_rows2,
+                            int64_t row_stride, int64_t n_windows, const int64_t* t_off, const int64_t* rows_t,
+                            const int64_t* u_off, const int64_t* rows_u, const double* z_t, const double* pop_wgt,
+                            const gb_params* params, int n_groups, double* z_u, double* info_u, int* window_status) {
   if (!ctx || !panel || n_rows < 0 || n_windows < 0 || !t_off || !u_off || (n_rows && !host_rows2) || !z_u || !info_u ||
       n_groups < 1) {
     if (ctx) ctx->err = "null or negative argument";
     return GB_ERR_BAD_ARG;
   }
-  if (panel->ctx != ctx || panel->format != GB_PANEL_E2M1 || row_stride < panel->k_elems / 4 || n_rows > panel->capacity) {
+  if (panel->ctx != ctx || panel->format != GB_PANEL_E2M1 || n_rows > panel->capacity ||
+      row_stride < (host_format == 5 ? panel->pack5_row_bytes : panel->k_elems / 4)) {
     ctx->err = "chromosome driver needs an E2M1 panel of this context with capacity >= n_rows";
     return GB_ERR_BAD_ARG;
   }
   int rc = check_device(ctx);
   if (rc) return rc;
   if (!ctx->copy_stream) GB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++)
+    if (!ctx->chrom_streams[i]) GB_CUDA(cudaStreamCreateWithFlags(&ctx->chrom_streams[i], cudaStreamNonBlocking));
   if (n_groups > n_windows) n_groups = (int)std::max<int64_t>(1, n_windows);
   gb_panel_clear(panel);
   panel->n_rows = n_rows;   // the batches are planned against the full row range before the rows arrive
@@ -1309,6 +1398,9 @@ int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void*
     int g = 1;
     for (int64_t w = 0; w < n_windows && g < n_groups; w++) {
       acc += cost[(size_t)w];
+      // even cost shares: tapering the groups so that the last batch is the smallest, or giving it one or two
+      // windows only, was measured and does not help (a batch's latency is set by its Cholesky chain and its
+      // single wave of solve CTAs, not by its size)
       if (acc >= total * g / n_groups) g_lo[(size_t)g++] = w + 1;
     }
   }
@@ -1321,6 +1413,8 @@ int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void*
   int* h_status = nullptr;
   auto cleanup = [&]() {
     cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->chrom_streams[0]);
+    cudaStreamSynchronize(ctx->chrom_streams[1]);
     cudaStreamSynchronize(ctx->stream);
     for (auto b : batches)
       if (b) {
@@ -1337,6 +1431,10 @@ int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void*
     return code;
   };
   // plan every group first (host work + small uploads: 0.65 ms for 6 groups), then let copies and kernels stream
+  const bool trace = getenv("GB_CHROM_TRACE") != nullptr;   // diagnostics: when each chunk landed / each batch finished
+  std::vector<cudaEvent_t> done_ev;
+  cudaEvent_t ev_t0 = nullptr;
+  const auto host_t0 = std::chrono::steady_clock::now();
   int64_t need_run = 0;
   for (int g = 0; g < n_groups; g++) {
     const int64_t w0 = g_lo[(size_t)g], w1 = g_lo[(size_t)g + 1], nw = w1 - w0;
@@ -1353,7 +1451,8 @@ int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void*
                                rows_u ? rows_u + u_off[w0] : nullptr, z_t ? z_t + t_off[w0] : &dummy, pop_wgt, params,
                                false, false, &batches[(size_t)g], /*defer_flag_check=*/true);
     if (rc) return fail(rc);
-    if (cudaEventCreateWithFlags(&landed[(size_t)g], cudaEventDisableTiming) != cudaSuccess) return fail(GB_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&landed[(size_t)g], trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess)
+      return fail(GB_ERR_CUDA);
   }
   size_t st_total = 0;
   for (int g = 0; g < n_groups; g++) st_total += 2 * (size_t)(g_lo[(size_t)g + 1] - g_lo[(size_t)g]) + 3;
@@ -1372,6 +1471,11 @@ int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void*
     cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);
     cudaEventDestroy(alloc_done);
   }
+  if (trace) {
+    cudaEventCreate(&ev_t0);
+    cudaEventRecord(ev_t0, ctx->copy_stream);
+  }
+  const double plan_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
   int64_t have = 0;
   size_t st_off = 0;
   std::vector<size_t> st_offs((size_t)n_groups);
@@ -1389,18 +1493,51 @@ int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void*
     }
     cudaEventRecord(landed[(size_t)g], ctx->copy_stream);
     cudaStreamWaitEvent(ctx->stream, landed[(size_t)g], 0);
-    if (hi > lo && (rc = launch_expand2(ctx, panel, d_stage + (size_t)lo * (size_t)row_stride, row_stride, lo, hi - lo)))
-      return fail(rc);
+    if (hi > lo) {
+      const uint8_t* chunk = d_stage + (size_t)lo * (size_t)row_stride;
+      rc = host_format == 5 ? launch_expand5(ctx, panel, chunk, row_stride, lo, hi - lo)
+                            : launch_expand2(ctx, panel, chunk, row_stride, lo, hi - lo);
+      if (rc) return fail(rc);
+    }
+    // The batches alternate between two compute streams: a quarter-chromosome batch cannot fill the GPU by itself
+    // (its Cholesky chain is latency-bound, its solve is a single wave of CTAs), so the next batch's Gram kernel
+    // runs beside them.  Expansion stays on the context stream; `landed[g]` is re-recorded there as "rows expanded".
+    cudaEventRecord(landed[(size_t)g], ctx->stream);
+    cudaStream_t cs = ctx->chrom_streams[g & 1];
+    cudaStreamWaitEvent(cs, landed[(size_t)g], 0);
     gb_batch* b = batches[(size_t)g];
-    if ((rc = gb_batch_run(b))) return fail(rc);
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = cs;
+    rc = gb_batch_run(b);
     const int64_t w0 = g_lo[(size_t)g];
     st_offs[(size_t)g] = st_off;
-    if ((rc = fetch_enqueue(b, z_u + u_off[w0], info_u + u_off[w0], h_status + st_off))) return fail(rc);
+    if (!rc) rc = fetch_enqueue(b, z_u + u_off[w0], info_u + u_off[w0], h_status + st_off);
+    ctx->stream = main_stream;
+    if (rc) return fail(rc);
     st_off += 2 * (size_t)b->n_windows + 3;
+    if (trace) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, cs);
+      done_ev.push_back(e);
+    }
   }
-  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+  if (cudaStreamSynchronize(ctx->chrom_streams[0]) != cudaSuccess || cudaStreamSynchronize(ctx->chrom_streams[1]) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
     ctx->err = "chromosome driver: stream synchronisation failed";
     return fail(GB_ERR_CUDA);
+  }
+  if (trace) {
+    fprintf(stderr, "[chrom trace] plan %.2f ms |", plan_ms);
+    for (int g = 0; g < n_groups; g++) {
+      float a = 0, c = 0;
+      cudaEventElapsedTime(&a, ev_t0, landed[(size_t)g]);
+      cudaEventElapsedTime(&c, ev_t0, done_ev[(size_t)g]);
+      fprintf(stderr, " group %d: rows expanded %.2f ms, batch done %.2f ms |", g, a, c);
+    }
+    fprintf(stderr, " total host %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+    for (auto e : done_ev) cudaEventDestroy(e);
+    cudaEventDestroy(ev_t0);
   }
   int worst = GB_OK;
   for (int g = 0; g < n_groups; g++) {
@@ -1489,6 +1626,22 @@ int gb_window_qcat(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* row
     if (num_eig) *num_eig = (int)n_t;
   }
   return done2(rc);
+}
+
+int gb_chrom_run_pack2(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void* host_rows2, int64_t row_stride,
+                       int64_t n_windows, const int64_t* t_off, const int64_t* rows_t, const int64_t* u_off,
+                       const int64_t* rows_u, const double* z_t, const double* pop_wgt, const gb_params* params,
+                       int n_groups, double* z_u, double* info_u, int* window_status) {
+  return chrom_run_packed(ctx, panel, 2, n_rows, host_rows2, row_stride, n_windows, t_off, rows_t, u_off, rows_u, z_t,
+                          pop_wgt, params, n_groups, z_u, info_u, window_status);
+}
+
+int gb_chrom_run_pack5(gb_ctx* ctx, gb_panel* panel, int64_t n_rows, const void* host_rows5, int64_t row_stride,
+                       int64_t n_windows, const int64_t* t_off, const int64_t* rows_t, const int64_t* u_off,
+                       const int64_t* rows_u, const double* z_t, const double* pop_wgt, const gb_params* params,
+                       int n_groups, double* z_u, double* info_u, int* window_status) {
+  return chrom_run_packed(ctx, panel, 5, n_rows, host_rows5, row_stride, n_windows, t_off, rows_t, u_off, rows_u, z_t,
+                          pop_wgt, params, n_groups, z_u, info_u, window_status);
 }
 
 // ---- pipelined single windows on HOST buffers ---------------------------------------------------

@@ -84,6 +84,7 @@ struct Ctx {
   cudaStream_t side_stream = nullptr;   // lazily created: the factorisation beside the B21 Gram tiles (gb_batch_run)
   int seg_order = 2;                    // processing order of the populations in the regrouped Gram fold (GB_SEG_ORDER)
   int chol_sms = 64;                    // SMs the B21 Gram launch leaves to it (GB_CHOL_SMS; 0 = run the stages one after another)
+  cudaStream_t chrom_streams[2] = {nullptr, nullptr};   // lazily created: alternating batches of the chromosome driver
   cudaStream_t copy_stream = nullptr;   // lazily created: host->device copies of the chromosome driver
   std::string err;
   int64_t launches = 0;
@@ -125,6 +126,8 @@ struct Panel {
   int32_t* d_sxx = nullptr;    // [n_pops][capacity]
   int* d_pop_sizes = nullptr;  // [n_pops]
   int* d_koff = nullptr;       // [n_pops]
+  int* d_boff5 = nullptr;      // [n_pops] byte offset of each population block in a pack5 host row
+  int pack5_row_bytes = 0;
   RowMaps tmaps;               // int8 rows, or E2M1 rows expanded to bytes by the TMA unit (kind::f8f6f4)
   RowMaps tmaps_packed;        // E2M1 rows kept nibble-packed in shared memory (kind::mxf4)
 };
@@ -142,6 +145,7 @@ struct Panel {
 int launch_pack(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int is_ascii,
                 int64_t row0, int64_t n_rows);
 int launch_expand2(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int64_t row0, int64_t n_rows);
+int launch_expand5(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int64_t row0, int64_t n_rows);
 int launch_gather_rows(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int8_t* dst);
 int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t n, int mode,
                     const double* d_coef, const double* d_wgt, double* d_sd, int32_t* d_pool, double* d_rq,

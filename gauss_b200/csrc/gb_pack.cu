@@ -140,6 +140,98 @@ expand2_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int8_
     *reinterpret_cast<uint32_t*>(dst + (row0 + row) * (long long)k_stride + j) = 0u;
 }
 
+// Ternary host rows ("pack5": five dosages per byte, byte = d0 + 3 d1 + 9 d2 + 27 d3 + 81 d4, 1.6 bits per dosage;
+// population p starts at byte boff5[p], blocks padded to 4 bytes) -> E2M1 nibbles plus per-population sum x,
+// sum x^2.  A dosage in {0,1,2} has log2(3) = 1.58 bits of information, so this is within 1 % of the densest
+// fixed-width code and takes another fifth off what crosses PCIe after pack2.  One CTA per row, warp w takes
+// populations w, w+8, ...: a lane decodes one 32-bit word (4 bytes = 20 dosages) through two 256-entry tables into
+// five 32-bit shared-memory stores of one dosage per byte (lane stride 5 words: conflict-free), then the block is
+// re-packed eight dosages per 32-bit global store, coalesced.  Bytes 243..255 are not codes (flagged).
+__global__ void __launch_bounds__(256)
+expand5_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int8_t* __restrict__ dst, int k_elems,
+                    int k_stride, long long row0, int n_pops, const int* __restrict__ pop_sizes,
+                    const int* __restrict__ koff, const int* __restrict__ boff5, int32_t* __restrict__ sx,
+                    int32_t* __restrict__ sxx, long long stat_ld, int* flags, int seg_align) {
+  extern __shared__ __align__(16) uint8_t dos[];   // population p at koff[p] + 32 p (32 bytes of slack behind each block)
+  __shared__ uint32_t lut_a[256];                  // digits 0..3, one per byte
+  __shared__ uint32_t lut_b[256];                  // digit 4 | #ones << 8 | #twos << 12 | invalid << 31
+  const long long row = blockIdx.x;
+  const uint8_t* s = src + row * src_stride;
+  const int tid = threadIdx.x;
+  {
+    uint32_t va = 0, vb = 0x80000000u;
+    if (tid < 243) {
+      int b = tid, ones = 0, twos = 0, dg[5];
+#pragma unroll
+      for (int q = 0; q < 5; q++) { dg[q] = b % 3; b /= 3; ones += dg[q] == 1; twos += dg[q] == 2; }
+      va = (uint32_t)dg[0] | ((uint32_t)dg[1] << 8) | ((uint32_t)dg[2] << 16) | ((uint32_t)dg[3] << 24);
+      vb = (uint32_t)dg[4] | ((uint32_t)ones << 8) | ((uint32_t)twos << 12);
+    }
+    lut_a[tid] = va;
+    lut_b[tid] = vb;
+  }
+  const int smem_bytes = k_elems + 32 * n_pops;
+  for (int j = tid * 16; j < smem_bytes; j += 256 * 16) *reinterpret_cast<uint4*>(dos + j) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  uint32_t bad = 0;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int p = warp; p < n_pops; p += 8) {
+    const int m = pop_sizes[p];
+    const int nwords = ((m + 4) / 5 + 3) >> 2;
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(s + boff5[p]);
+    uint32_t* dp = reinterpret_cast<uint32_t*>(dos + koff[p] + 32 * p);
+    int ones = 0, twos = 0;
+    for (int j = lane; j < nwords; j += 32) {
+      const uint32_t w = sp[j];
+      const uint32_t a0 = lut_a[w & 255], a1 = lut_a[(w >> 8) & 255], a2 = lut_a[(w >> 16) & 255], a3 = lut_a[w >> 24];
+      const uint32_t b0 = lut_b[w & 255], b1 = lut_b[(w >> 8) & 255], b2 = lut_b[(w >> 16) & 255], b3 = lut_b[w >> 24];
+      bad |= (b0 | b1 | b2 | b3) & 0x80000000u;
+      ones += ((b0 >> 8) & 7) + ((b1 >> 8) & 7) + ((b2 >> 8) & 7) + ((b3 >> 8) & 7);
+      twos += ((b0 >> 12) & 7) + ((b1 >> 12) & 7) + ((b2 >> 12) & 7) + ((b3 >> 12) & 7);
+      uint32_t* o = dp + 5 * j;              // 20 dosages, one per byte; the slack takes what runs past the block
+      o[0] = a0;
+      o[1] = (b0 & 3u) | (a1 << 8);
+      o[2] = (a1 >> 24) | ((b1 & 3u) << 8) | (a2 << 16);
+      o[3] = (a2 >> 16) | ((b2 & 3u) << 16) | (a3 << 24);
+      o[4] = (a3 >> 8) | ((b3 & 3u) << 24);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ones += __shfl_xor_sync(0xffffffffu, ones, o);
+      twos += __shfl_xor_sync(0xffffffffu, twos, o);
+    }
+    __syncwarp();
+    // digits past the population's size must be zero (the host packer writes them so)
+    const int kp = (m + seg_align - 1) / seg_align * seg_align;
+    const uint8_t* dpb = dos + koff[p] + 32 * p;
+    for (int c = m + lane; c < nwords * 20; c += 32) bad |= dpb[c];
+    // re-pack: eight dosages -> eight nibbles (E2M1 code = dosage << 1), columns m .. kp stay zero
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + (row0 + row) * (long long)k_stride) + (koff[p] >> 3);
+    for (int j = lane; j < (kp >> 3); j += 32) {
+      uint2 v = *reinterpret_cast<const uint2*>(dpb + 8 * j);
+      if (8 * j + 8 > m) {                   // the word that straddles the population's end
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (8 * j + q >= m) v.x &= ~(0xFFu << (8 * q));
+          if (8 * j + 4 + q >= m) v.y &= ~(0xFFu << (8 * q));
+        }
+      }
+      uint32_t out = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        out |= ((v.x >> (8 * q)) & 3u) << (4 * q + 1);
+        out |= ((v.y >> (8 * q)) & 3u) << (4 * (q + 4) + 1);
+      }
+      d[j] = out;
+    }
+    if (lane == 0) {
+      sx[(long long)p * stat_ld + row0 + row] = ones + 2 * twos;
+      sxx[(long long)p * stat_ld + row0 + row] = ones + 4 * twos;
+    }
+  }
+  if (bad) atomicOr(flags, 1);
+}
+
 // dst[i] = panel row rows[i]; 16-byte vectors, one CTA per row.
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const int8_t* __restrict__ panel, int k_stride, const int32_t* __restrict__ rows,
@@ -223,6 +315,27 @@ int launch_expand2(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stri
   expand2_rows_kernel<<<(unsigned)n_rows, 256, 0, ctx->stream>>>(
       static_cast<const uint8_t*>(dev_src), src_stride, panel->d_rows, panel->k_stride, row0, panel->n_pops,
       panel->d_pop_sizes, panel->d_koff, panel->d_sx, panel->d_sxx, panel->capacity, panel->d_flags, panel->seg_align);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+int launch_expand5(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stride, int64_t row0, int64_t n_rows) {
+  if (n_rows <= 0) return GB_OK;
+  if (src_stride % 4 != 0 || (reinterpret_cast<uintptr_t>(dev_src) & 3)) {
+    ctx->err = "pack5 rows must be 4-byte aligned (use gb_pack5_row_bytes() as the row stride)";
+    return GB_ERR_BAD_ARG;
+  }
+  const size_t smem = ((size_t)panel->k_elems + 32 * (size_t)panel->n_pops + 15) / 16 * 16;
+  if (smem > 200 * 1024) {
+    ctx->err = "panel row too long for expand5_rows_kernel";
+    return GB_ERR_UNSUPPORTED;
+  }
+  GB_CUDA(cudaFuncSetAttribute(expand5_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  expand5_rows_kernel<<<(unsigned)n_rows, 256, smem, ctx->stream>>>(
+      static_cast<const uint8_t*>(dev_src), src_stride, panel->d_rows, panel->k_elems, panel->k_stride, row0, panel->n_pops,
+      panel->d_pop_sizes, panel->d_koff, panel->d_boff5, panel->d_sx, panel->d_sxx, panel->capacity, panel->d_flags,
+      panel->seg_align);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

@@ -215,6 +215,19 @@ GB_API int gb_chrom_run_pack2(gb_ctx *ctx, gb_panel *panel, int64_t n_rows, cons
                        const int64_t *u_off, const int64_t *rows_u, const double *z_t, const double *pop_wgt,
                        const gb_params *params, int n_groups, double *z_u, double *info_u, int *window_status);
 
+/* ---- ternary host rows ("pack5") --------------------------------------------------------------------- */
+/* Five dosages per byte (byte = d0 + 3 d1 + 9 d2 + 27 d3 + 81 d4): 1.6 bits per dosage against an information content of
+ * log2(3) = 1.58, i.e. another fifth off the PCIe bytes of pack2.  Population p starts at a 4-byte boundary; the row is
+ * padded to 16 bytes (gb_pack5_row_bytes).  Same contract as the pack2 functions above. */
+GB_API int64_t gb_pack5_row_bytes(int n_pops, const int *pop_sizes);
+GB_API int gb_pack5_rows_host(int n_pops, const int *pop_sizes, int64_t n_rows, const void *rows,
+                       int64_t row_stride, int is_ascii, void *out, int64_t out_stride);
+GB_API int gb_panel_append_pack5_host(gb_panel *panel, int64_t n_rows, const void *rows5, int64_t row_stride);
+GB_API int gb_chrom_run_pack5(gb_ctx *ctx, gb_panel *panel, int64_t n_rows, const void *host_rows5,
+                       int64_t row_stride, int64_t n_windows, const int64_t *t_off, const int64_t *rows_t,
+                       const int64_t *u_off, const int64_t *rows_u, const double *z_t, const double *pop_wgt,
+                       const gb_params *params, int n_groups, double *z_u, double *info_u, int *window_status);
+
 /* ---- pipelined single windows, host in / host out ---------------------------------------------- */
 /* What a genome loop over dist()/distmix() calls (dist.cpp:63-75 runs one window per call): the
  * host->device copy of window w+1 overlaps the kernels of window w.  `depth` device slots of

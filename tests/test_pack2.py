@@ -49,6 +49,80 @@ def test_host_packer_refuses_other_dosages():
     assert api.pack2_row_bytes(np.array([0, 3], np.int32)) == -1
 
 
+def numpy_unpack5(pop_sizes, rows5):
+    boff = [0]
+    for m in pop_sizes:
+        boff.append(boff[-1] + ((int(m) + 4) // 5 + 3) // 4 * 4)
+    out = []
+    for k, m in enumerate(pop_sizes):
+        blk = rows5[:, boff[k]:boff[k] + (int(m) + 4) // 5].astype(np.int64)
+        out.append(np.stack([(blk // 3 ** q) % 3 for q in range(5)], axis=2).reshape(len(rows5), -1)[:, :int(m)])
+    return np.concatenate(out, axis=1).astype(np.int8), boff[-1]
+
+
+@pytest.mark.parametrize("pop_sizes", [(5, 130, 7), (128,), (1, 1, 1), (61, 103, 40, 25, 2, 330, 97)])
+def test_ternary_host_packer_layout(pop_sizes):
+    ps = np.array(pop_sizes, np.int32)
+    rng = np.random.default_rng(len(pop_sizes) + 5)
+    g = rng.integers(0, 3, (700, int(ps.sum()))).astype(np.int8)
+    rows5 = api.pack5_rows_host(ps, g)
+    dec, used = numpy_unpack5(ps, rows5)
+    np.testing.assert_array_equal(dec, g)
+    assert rows5.shape[1] == api.pack5_row_bytes(ps) == (used + 15) // 16 * 16
+    assert (rows5 <= 242).all() and (rows5[:, used:] == 0).all()
+    np.testing.assert_array_equal(api.pack5_rows_host(ps, (g + 48).astype(np.uint8), is_ascii=True), rows5)
+    np.testing.assert_array_equal(api.pack5_rows_host(ps, g[:3]), rows5[:3])
+    for bad in (3, -1):
+        g2 = g[:4].copy()
+        g2[1, -1] = bad
+        with pytest.raises(gb.GaussB200Error):
+            api.pack5_rows_host(ps, g2)
+
+
+@pytest.mark.gpu
+def test_pack5_panel_and_chrom_driver(gpu_ctx):
+    c = small_case(seed=45, n_snps=900, pop_sizes=(61, 103, 40, 25, 2, 330, 97), measured_frac=0.3, core=(0, 900))
+    g, t = c["g"].astype(np.int8), c["type"]
+    rows5 = api.pack5_rows_host(c["pop_sizes"], g)
+    ref = gb.Panel(gpu_ctx, c["pop_sizes"], len(g), "int8")
+    ref.append_host(g, is_ascii=False)
+    p5 = gb.Panel(gpu_ctx, c["pop_sizes"], len(g), "e2m1")
+    p5.append_pack5_host(rows5[:333])
+    p5.append_pack5_host(rows5[333:])
+    a, b = np.arange(0, 600), np.arange(300, 900)
+    for x, y in zip(ref.gram_counts(a, b), p5.gram_counts(a, b)):
+        np.testing.assert_array_equal(x, y)
+    wins = [(0, 300), (150, 520), (400, 900)]
+    t_rows, u_rows, t_off, u_off = [], [], [0], [0]
+    for lo, hi in wins:
+        idx = np.arange(lo, hi)
+        t_rows.append(idx[t[lo:hi] == 1])
+        u_rows.append(idx[t[lo:hi] == 0])
+        t_off.append(t_off[-1] + len(t_rows[-1]))
+        u_off.append(u_off[-1] + len(u_rows[-1]))
+    rows_t, rows_u = np.concatenate(t_rows), np.concatenate(u_rows)
+    batch = gb.Batch(p5, t_off, rows_t, u_off, rows_u, c["z"][rows_t], c["w"])
+    batch.run()
+    z0, i0, s0 = batch.fetch()
+    work = gb.Panel(gpu_ctx, c["pop_sizes"], len(g), "e2m1")
+    for n_groups in (1, 3):
+        z, info, st = work.chrom_run_pack5(rows5.ctypes.data, len(g), rows5.strides[0], t_off, rows_t, u_off, rows_u,
+                                           c["z"][rows_t], c["w"], n_groups=n_groups)
+        np.testing.assert_array_equal(st, s0)
+        np.testing.assert_array_equal(z, z0)
+        np.testing.assert_array_equal(info, i0)
+    # a byte that is not a code (243..255), and a digit past a population's size, are refused
+    for r, col, val in ((10, 0, 250), (20, 12, 242)):       # population 0 has 61 dosages: its 13th byte holds one digit
+        bad = rows5.copy()
+        bad[r, col] = val
+        pb = gb.Panel(gpu_ctx, c["pop_sizes"], len(g), "e2m1")
+        pb.append_pack5_host(bad)
+        _, _, rc = pb.window_distmix(t_rows[0], u_rows[0], c["z"][t_rows[0]], c["w"], allow=(api.GB_ERR_UNSUPPORTED,))
+        assert rc == api.GB_ERR_UNSUPPORTED
+    with pytest.raises(gb.GaussB200Error):
+        ref.append_pack5_host(rows5[:1])
+
+
 @pytest.mark.gpu
 def test_pack2_panel_equals_int8_panel(gpu_ctx):
     c = small_case(seed=41, n_snps=400, pop_sizes=(61, 103, 40, 25, 2, 330, 97))
