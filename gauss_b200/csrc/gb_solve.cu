@@ -393,12 +393,11 @@ pd_bound_kernel(const SolveWin* __restrict__ wins, int nreal, const double* __re
 // with cp.async.cg; their shared-memory row strides (68 and 132 doubles = 8 words mod 32) make the
 // A / B fragment loads conflict-free.  inv(L_ii) and the accumulator tile alias the chunk buffers
 // once the k-loop of a row block is done; two CTAs share an SM.
-constexpr int UB = 128;   // unmeasured SNPs (columns of W) per CTA
+constexpr int UB = 128;   // unmeasured SNPs (columns of W) per CTA; a 64-column variant serves launches of about one wave
 constexpr int KC = 32;    // k-steps per staged chunk
 constexpr int LSS = NB + 4;   // row stride of staged L / inv(L_ii)   [k][row]
-constexpr int WSS = UB + 4;   // row stride of staged W / accumulator [k][col]
-constexpr int TR_SMEM_BYTES = 2 * (KC * LSS + KC * WSS) * 8;  // 102,400
-static_assert(2 * KC * LSS >= NB * LSS && 2 * KC * WSS >= NB * WSS, "aliased tiles must fit the chunk buffers");
+constexpr int tr_smem_bytes(int ub) { return 2 * (KC * LSS + KC * (ub + 4)) * 8; }   // 102,400 for 128 columns
+static_assert(2 * KC >= NB, "aliased tiles must fit the chunk buffers");
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -409,13 +408,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int UB_>
 __global__ void __launch_bounds__(256, 2)
 trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt,
                      const double* __restrict__ dinv, double* ut, const double* __restrict__ zt,
                      double* zu, double* info, double* y_out) {
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t, nu = w.n_u;
-  const int u0 = blockIdx.x * UB;
+  constexpr int NTW = UB_ / 32;      // 8-column MMA tiles per warp
+  constexpr int WSS = UB_ + 4;       // row stride of staged W / accumulator [k][col]
+  const int u0 = blockIdx.x * UB_;
   if (u0 >= nu) return;
   const int nb = win_nb(n);
   const double* L = tt + w.off_tt;
@@ -427,32 +429,32 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   const int gid = lane >> 2, tig = lane & 3;
   const int wr = warp >> 2, wc = warp & 3;       // row half / column quarter of this warp
   const int row0 = 32 * wr + gid;                // + 8 mt: rows of this thread's A / C fragments
-  const int col0 = 32 * wc;                      // + 8 nt (+ gid for B fragments, + 2 tig for C)
+  const int col0 = 8 * NTW * wc;                      // + 8 nt (+ gid for B fragments, + 2 tig for C)
 
   extern __shared__ __align__(16) double sm[];
   double* LsBuf = sm;                        // 2 x [KC][LSS]
   double* WsBuf = sm + 2 * KC * LSS;         // 2 x [KC][WSS]
   double* Ds = LsBuf;                        // [64][LSS] inv(L_ii)(r, kk) at [kk][r], aliases both L chunks
   double* Ts = WsBuf;                        // [64][WSS] accumulator tile, aliases both W chunks
-  double* red = WsBuf;                       // [2][2][UB] final reductions
+  double* red = WsBuf;                       // [2][2][UB_] final reductions
   double* ys = sm + 2 * (KC * LSS + KC * WSS);  // [nb*64] y = L^-1 Z1 solved so far (every CTA carries this extra
   double* rys = ys + nb * NB;                   // [64]     right-hand side column itself: ~1/128 more work, no
                                                 //          separate latency-bound kernel and no y round trip)
   double* ypart = rys + NB;                     // [4][64]  partial dot products of the y column (4 threads per row)
   const int yr_ = tid & 63, yq = tid >> 6;
-  double p_info[4][2], p_z[4][2];            // per owned column (nt, e): partial sums over this thread's rows
+  double p_info[NTW][2], p_z[NTW][2];            // per owned column (nt, e): partial sums over this thread's rows
 #pragma unroll
-  for (int nt = 0; nt < 4; nt++) p_info[nt][0] = p_info[nt][1] = p_z[nt][0] = p_z[nt][1] = 0.0;
+  for (int nt = 0; nt < NTW; nt++) p_info[nt][0] = p_info[nt][1] = p_z[nt][0] = p_z[nt][1] = 0.0;
   const int cvalid = ldu - u0;               // columns that exist in the row (ldu is a multiple of 8)
 
   for (int ib = 0; ib < nb; ib++) {
     const int i0 = ib * NB;
-    double C[4][4][2];
+    double C[4][NTW][2];
 #pragma unroll
     for (int mt = 0; mt < 4; mt++) {
       const int r = i0 + row0 + 8 * mt;
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) {
+      for (int nt = 0; nt < NTW; nt++) {
         const int c = col0 + 8 * nt + 2 * tig;
         double2 v = make_double2(0.0, 0.0);
         if (r < n && c < cvalid) v = *reinterpret_cast<const double2*>(&W[(long long)r * ldu + u0 + c]);
@@ -475,9 +477,9 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
       }
       // W chunk: KC rows x 128 columns, 64 pieces per row
 #pragma unroll
-      for (int it = 0; it < (KC * UB / 2) / 256; it++) {
+      for (int it = 0; it < (KC * UB_ / 2) / 256; it++) {
         const int idx = tid + it * 256;
-        const int kk = idx >> 6, c2 = (idx & 63) * 2;
+        const int kk = idx / (UB_ / 2), c2 = (idx % (UB_ / 2)) * 2;
         cp_async16(ws + kk * WSS + c2, W + (long long)(kbase + kk) * ldu + u0 + c2, c2 < cvalid);
       }
       cp_async_commit();
@@ -502,11 +504,11 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) a[mt] = -ls[(4 * ks + tig) * LSS + row0 + 8 * mt];
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) b[nt] = ws[(4 * ks + tig) * WSS + col0 + 8 * nt + gid];
+        for (int nt = 0; nt < NTW; nt++) b[nt] = ws[(4 * ks + tig) * WSS + col0 + 8 * nt + gid];
 #pragma unroll
         for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-          for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(C[mt][nt][0], C[mt][nt][1], a[mt], b[nt]);
+          for (int nt = 0; nt < NTW; nt++) dmma_m8n8k4(C[mt][nt][0], C[mt][nt][1], a[mt], b[nt]);
       }
       {
         const double* yk = ys + ch * KC;
@@ -519,7 +521,7 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 #pragma unroll
     for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++)
+      for (int nt = 0; nt < NTW; nt++)
         *reinterpret_cast<double2*>(&Ts[(row0 + 8 * mt) * WSS + col0 + 8 * nt + 2 * tig]) =
             make_double2(C[mt][nt][0], C[mt][nt][1]);
     for (int idx = tid; idx < NB * NB / 2; idx += 256) {  // Ds[kk*LSS + r] = inv(L_ii)(r, kk), zero above diag
@@ -542,7 +544,7 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 #pragma unroll
     for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) C[mt][nt][0] = C[mt][nt][1] = 0.0;
+      for (int nt = 0; nt < NTW; nt++) C[mt][nt][0] = C[mt][nt][1] = 0.0;
     const int ksmax = 8 * (wr + 1);  // inv(L_ii)(r, kk) == 0 for kk > r, and this warp's rows end at 32 wr + 31
 #pragma unroll 2
     for (int ks = 0; ks < ksmax; ks++) {
@@ -550,11 +552,11 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 #pragma unroll
       for (int mt = 0; mt < 4; mt++) a[mt] = Ds[(4 * ks + tig) * LSS + row0 + 8 * mt];
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) b[nt] = Ts[(4 * ks + tig) * WSS + col0 + 8 * nt + gid];
+      for (int nt = 0; nt < NTW; nt++) b[nt] = Ts[(4 * ks + tig) * WSS + col0 + 8 * nt + gid];
 #pragma unroll
       for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) dmma_m8n8k4(C[mt][nt][0], C[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < NTW; nt++) dmma_m8n8k4(C[mt][nt][0], C[mt][nt][1], a[mt], b[nt]);
     }
     __syncthreads();
     if (tid < NB) ys[i0 + tid] = (ypart[tid] + ypart[NB + tid]) + (ypart[2 * NB + tid] + ypart[3 * NB + tid]);
@@ -565,7 +567,7 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
       if (r >= n) continue;
       const double yr = ys[r];
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) {
+      for (int nt = 0; nt < NTW; nt++) {
         const int c = col0 + 8 * nt + 2 * tig;
         if (c < cvalid)
           *reinterpret_cast<double2*>(&W[(long long)r * ldu + u0 + c]) = make_double2(C[mt][nt][0], C[mt][nt][1]);
@@ -581,7 +583,7 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   // column reductions in a fixed order: over the 8 row groups of a warp (shuffles), then over the
   // two row-half warps through shared memory
 #pragma unroll
-  for (int nt = 0; nt < 4; nt++)
+  for (int nt = 0; nt < NTW; nt++)
 #pragma unroll
     for (int e = 0; e < 2; e++)
 #pragma unroll
@@ -592,20 +594,20 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   __syncthreads();
   if (gid == 0) {
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++)
+    for (int nt = 0; nt < NTW; nt++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int c = col0 + 8 * nt + 2 * tig + e;
-        red[(0 * 2 + wr) * UB + c] = p_info[nt][e];
-        red[(1 * 2 + wr) * UB + c] = p_z[nt][e];
+        red[(0 * 2 + wr) * UB_ + c] = p_info[nt][e];
+        red[(1 * 2 + wr) * UB_ + c] = p_z[nt][e];
       }
   }
   __syncthreads();
   if (y_out && blockIdx.x == 0)   // qcat: y = L^-1 Z1 is an output too (every CTA carries the same column)
     for (int i = tid; i < n; i += 256) y_out[w.off_t + i] = ys[i];
-  if (tid < UB && u0 + tid < nu) {
-    const double s_info = red[0 * UB + tid] + red[1 * UB + tid];
-    const double s_z = red[2 * UB + tid] + red[3 * UB + tid];
+  if (tid < UB_ && u0 + tid < nu) {
+    const double s_info = red[0 * UB_ + tid] + red[1 * UB_ + tid];
+    const double s_z = red[2 * UB_ + tid] + red[3 * UB_ + tid];
     const double inf = fabs(s_info);                 // info = |b21 B11^-1 b12|      (dist.cpp:198)
     zu[w.off_u + u0 + tid] = s_z / sqrt(inf);        // z / sqrt(info)               (dist.cpp:200)
     info[w.off_u + u0 + tid] = inf;
@@ -713,14 +715,24 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
                          double* d_y_out) {
   if (n_wins == 0 || max_nu == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
-  const size_t smem = TR_SMEM_BYTES + sizeof(double) * (size_t)(nb_max * NB + 5 * NB);
+  // 128 columns per CTA when the launch has waves to spare, 64 when it is about one wave (a single window, the
+  // chromosome driver's quarter batches): the longest CTA then sets the kernel's duration, and it is half as long
+  const long long ctas128 = (long long)((max_nu + UB - 1) / UB) * n_wins;
+  const bool narrow = ctas128 < 3LL * ctx->sm_count;     // 2 CTAs per SM: below 1.5 waves
+  const int ub = narrow ? 64 : UB;
+  const size_t smem = tr_smem_bytes(ub) + sizeof(double) * (size_t)(nb_max * NB + 5 * NB);
   if (smem > 227 * 1024) {
     ctx->err = "window has too many measured SNPs for trsm_finalize_kernel";
     return GB_ERR_UNSUPPORTED;
   }
-  GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  trsm_finalize_kernel<<<dim3((max_nu + UB - 1) / UB, n_wins), 256, smem, ctx->stream>>>(
-      d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
+  const dim3 grid((unsigned)((max_nu + ub - 1) / ub), (unsigned)n_wins);
+  if (narrow) {
+    GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trsm_finalize_kernel<64><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
+  } else {
+    GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trsm_finalize_kernel<128><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
+  }
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;
