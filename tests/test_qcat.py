@@ -109,3 +109,26 @@ def test_qcat_edge_cases(gpu_ctx, oracle):
     assert r["rc"] == api.GB_ERR_NOT_PD
     with pytest.raises(gb.GaussB200Error):
         panel.window_qcat(meas, z[meas], len(meas) - 2, 5, unme, None)     # core range runs past the measured list
+
+
+@pytest.mark.gpu
+def test_qcatmix_33kg_shape(gpu_ctx, oracle):
+    """qcatmix on the BASELINE config-2 panel shape: 21 flagged populations, 32,147 individuals, PGC2 weights."""
+    _, sizes, w = synth.flagged_33kg_pgc2()
+    n = 420
+    g = synth.make_genotypes(n, sizes, seed=53)
+    rng = np.random.default_rng(53)
+    t = (rng.random(n) < 0.35).astype(np.int32)
+    bp = np.arange(n, dtype=np.int64) * 300 + 1
+    z = rng.standard_normal(n) * 1.34
+    c = dict(type=t, bp=bp, start_bp=int(bp[100]), end_bp=int(bp[330]))
+    meas, unme, headwing, n_core = split(c)
+    panel = gb.Panel(gpu_ctx, sizes, n)
+    panel.append_host(g, is_ascii=False)
+    out = panel.window_qcat(meas, z[meas], headwing, n_core, unme, w)
+    ref = oracle.run_qcat(t, bp, z, g, sizes, w, c["start_bp"], c["end_bp"])
+    core_m = meas[headwing:headwing + n_core]
+    assert out["num_eig"] == len(meas) == int(ref["m"][core_m[0]])
+    assert np.abs(out["t_u"] - ref["t"][unme]).max() <= 1e-8
+    assert np.abs(out["t_m"] - ref["t"][core_m]).max() <= 1e-8
+    assert np.abs(out["chisq_u"] - ref["chisq"][unme]).max() <= 1e-8
