@@ -153,6 +153,19 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   b->fkind = pn->format == GB_PANEL_E2M1 ? (ctx->e2m1_mxf4 ? 7 : 6) : 0;
   gp.fkind = b->fkind;
   const int atom = b->fkind == 7 ? 2 * K_ATOM : K_ATOM;  // K columns one MMA instruction consumes
+  if (b->fkind != 0) {
+    // E2M1 panels count in fp32: a segment's largest possible sum (dosage 6 on both sides, 36 per individual) must stay
+    // below 2^21 for the one-instruction count -> fp64 re-encoding of the mixture fold and below 2^22 for the magic-add
+    // count -> int32 of the pooled / counts paths (both far inside fp32's exact-integer range)
+    const long long seg_max = b->mode == GRAM_POOLED ? (long long)pn->n_samples
+                                                     : (long long)*std::max_element(pn->pop_sizes.begin(), pn->pop_sizes.end());
+    const long long limit = (b->mode == GRAM_MIX && !b->counts_mode) ? (1ll << 21) : (1ll << 22);
+    if (36 * seg_max >= limit) {
+      ctx->err = "a population block of " + std::to_string(seg_max) + " individuals is too large for the exact fp32 counts of an "
+                 "E2M1 panel; use GB_PANEL_INT8";
+      return GB_ERR_UNSUPPORTED;
+    }
+  }
   std::vector<double> h_coef((size_t)pn->n_pops, 0.0), h_wgt((size_t)pn->n_pops, 0.0);
   if (b->mode == GRAM_POOLED) {
     gp.n_seg = 1;

@@ -405,3 +405,28 @@ def test_overlapped_batch_run_equals_staged_run(gpu_ctx):
         np.testing.assert_array_equal(z1, z0)
         np.testing.assert_array_equal(i1, i0)
         np.testing.assert_array_equal(s1, s0)
+
+
+def test_e2m1_count_range_guard(gpu_ctx, oracle):
+    """E2M1 panels count in fp32 and re-encode the counts with one shift-add, exact below 2^21: a population block that
+    could exceed it (36 per individual with the largest dosage the format holds) is refused, int8 takes it."""
+    sizes = np.array([60000, 50], np.int32)
+    g = synth.make_genotypes(40, sizes, seed=83).astype(np.int8)
+    w = np.array([0.7, 0.3])
+    t = np.array([1, 0] * 20, np.int32)
+    meas, unme = np.where(t == 1)[0], np.where(t == 0)[0]
+    z = np.linspace(-2, 2, 40)
+    p4 = gb.Panel(gpu_ctx, sizes, 40, "e2m1")
+    p4.append_host(g, is_ascii=False)
+    _, _, rc = p4.window_distmix(meas, unme, z[meas], w, allow=(gb.api.GB_ERR_UNSUPPORTED,))
+    assert rc == gb.api.GB_ERR_UNSUPPORTED
+    zp, ip, rc = p4.window_dist(meas, unme, z[meas])        # pooled: 36 * 60,050 is still below 2^22
+    assert rc == gb.GB_OK
+    p8 = gb.Panel(gpu_ctx, sizes, 40, "int8")
+    p8.append_host(g, is_ascii=False)
+    z8, i8, rc = p8.window_distmix(meas, unme, z[meas], w)
+    assert rc == gb.GB_OK
+    r = oracle.run_window(t, np.arange(40, dtype=np.int64), z, g, sizes, w, 0, 10**9)
+    assert np.abs(z8 - r["z"][unme]).max() <= TOL and np.abs(i8 - r["info"][unme]).max() <= TOL
+    rp = oracle.run_window(t, np.arange(40, dtype=np.int64), z, g, sizes, None, 0, 10**9)
+    assert np.abs(zp - rp["z"][unme]).max() <= TOL
