@@ -393,7 +393,7 @@ def run_gpu(args):
     pw_done, pw_s = 0, 1.0
     c_h2d = c_d2h = 0
     host_fmt, row2, host_pack_s = os.environ.get("GB_E2E_HOST_FORMAT", "pack5"), 0, 0.0
-    n_groups = int(os.environ.get("GB_E2E_GROUPS", "4"))
+    n_groups = int(os.environ.get("GB_E2E_GROUPS", "6"))
     if not args.no_e2e:
         # (a) per-window calls on raw int8 host rows (what a drop-in behind run_distmix sees today)
         e2e_step()  # warm-up

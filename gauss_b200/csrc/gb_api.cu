@@ -619,8 +619,10 @@ void gb_ctx_destroy(gb_ctx* ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 2; i++) {
     if (ctx->chrom_streams[i]) cudaStreamDestroy(ctx->chrom_streams[i]);
+    if (ctx->chrom_sides[i]) cudaStreamDestroy(ctx->chrom_sides[i]);
+  }
   delete ctx;
 }
 
@@ -1389,8 +1391,10 @@ static int chrom_run_packed(gb_ctx* ctx, gb_panel* panel, int host_format, int64
   int rc = check_device(ctx);
   if (rc) return rc;
   if (!ctx->copy_stream) GB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 2; i++) {
     if (!ctx->chrom_streams[i]) GB_CUDA(cudaStreamCreateWithFlags(&ctx->chrom_streams[i], cudaStreamNonBlocking));
+    if (!ctx->chrom_sides[i]) GB_CUDA(cudaStreamCreateWithFlags(&ctx->chrom_sides[i], cudaStreamNonBlocking));
+  }
   if (n_groups > n_windows) n_groups = (int)std::max<int64_t>(1, n_windows);
   gb_panel_clear(panel);
   panel->n_rows = n_rows;   // the batches are planned against the full row range before the rows arrive
@@ -1519,13 +1523,15 @@ static int chrom_run_packed(gb_ctx* ctx, gb_panel* panel, int host_format, int64
     cudaStream_t cs = ctx->chrom_streams[g & 1];
     cudaStreamWaitEvent(cs, landed[(size_t)g], 0);
     gb_batch* b = batches[(size_t)g];
-    cudaStream_t main_stream = ctx->stream;
+    cudaStream_t main_stream = ctx->stream, main_side = ctx->side_stream;
     ctx->stream = cs;
+    ctx->side_stream = ctx->chrom_sides[g & 1];   // each compute stream forks its factorisation onto its own side stream
     rc = gb_batch_run(b);
     const int64_t w0 = g_lo[(size_t)g];
     st_offs[(size_t)g] = st_off;
     if (!rc) rc = fetch_enqueue(b, z_u + u_off[w0], info_u + u_off[w0], h_status + st_off);
     ctx->stream = main_stream;
+    ctx->side_stream = main_side;
     if (rc) return fail(rc);
     st_off += 2 * (size_t)b->n_windows + 3;
     if (trace) {

@@ -84,6 +84,7 @@ struct Ctx {
   cudaStream_t side_stream = nullptr;   // lazily created: the factorisation beside the B21 Gram tiles (gb_batch_run)
   int seg_order = 2;                    // processing order of the populations in the regrouped Gram fold (GB_SEG_ORDER)
   int chol_sms = 64;                    // SMs the B21 Gram launch leaves to it (GB_CHOL_SMS; 0 = run the stages one after another)
+  cudaStream_t chrom_sides[2] = {nullptr, nullptr};     // ... and the side stream each of them forks its factorisation onto
   cudaStream_t chrom_streams[2] = {nullptr, nullptr};   // lazily created: alternating batches of the chromosome driver
   cudaStream_t copy_stream = nullptr;   // lazily created: host->device copies of the chromosome driver
   std::string err;
