@@ -28,6 +28,39 @@ __global__ void probe(double* out, int iters, double seed, long long* cyc) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
+// Are the fp64 tensor pipe (DMMA) and the fp64 FMA pipe (DFMA) the same execution resource?  Half of the warps of a
+// CTA run DMMAs, the other half independent DFMAs; if the two pipes were separate the combined rate would approach the
+// sum of the two alone.
+template <int MIX>   // 0: all warps DMMA, 1: all warps DFMA, 2: even warps DMMA / odd warps DFMA
+__global__ void mix_probe(double* out, int iters, double seed, long long* cyc) {
+  const int warp = threadIdx.x >> 5;
+  const bool do_mma = MIX == 0 || (MIX == 2 && (warp & 1) == 0);
+  double c[16][2];
+  for (int i = 0; i < 16; i++) { c[i][0] = seed + i; c[i][1] = seed - i; }
+  const double a = seed * 0.5 + threadIdx.x, b = 1.0 + 1e-9 * threadIdx.x;
+  __syncthreads();
+  long long t0 = clock64();
+  if (do_mma) {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) dmma884(c[i][0], c[i][1], a, b);          // 16 x 256 FMA per warp
+    }
+  } else {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int i = 0; i < 16; i++) { c[i][0] = fma(c[i][0], b, a); c[i][1] = fma(c[i][1], b, a); }   // 128 x 32 FMA per warp
+    }
+  }
+  long long t1 = clock64();
+  double s = 0;
+  for (int i = 0; i < 16; i++) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = clock64() - t0;
+}
+
 int main() {
   double* out; long long* cyc;
   cudaMalloc(&out, 148 * 1024 * 8); cudaMallocManaged(&cyc, 8);
@@ -42,6 +75,20 @@ int main() {
       // FMAs per warp per iteration: mode0: 16 x m8n8k4 (256) ; mode1: 8 x m16n8k8 (1024)
       double fma = (double)(threads / 32) * iters * (mode == 0 ? 16 * 256.0 : 8 * 1024.0);
       printf("threads/SM %4d  %-10s  %8.1f fp64 FMA / clk / SM  (%lld cycles)\n", threads, mode ? "m16n8k8" : "m8n8k4", fma / (double)*cyc, *cyc);
+    }
+  }
+  for (int threads : {256, 512}) {
+    for (int mix = 0; mix < 3; mix++) {
+      for (int rep = 0; rep < 2; rep++) {
+        if (mix == 0) mix_probe<0><<<148, threads>>>(out, iters, 1.5, cyc);
+        if (mix == 1) mix_probe<1><<<148, threads>>>(out, iters, 1.5, cyc);
+        if (mix == 2) mix_probe<2><<<148, threads>>>(out, iters, 1.5, cyc);
+        cudaDeviceSynchronize();
+      }
+      const double warps = threads / 32;
+      const double fma = mix == 2 ? warps / 2 * iters * 4096.0 * 2 : warps * iters * 4096.0;   // both kinds do 4096 FMA per warp-iteration
+      printf("threads/SM %4d  %-28s %8.1f fp64 FMA / clk / SM  (%lld cycles)\n", threads,
+             mix == 0 ? "DMMA m8n8k4 only" : mix == 1 ? "DFMA only" : "half DMMA + half DFMA warps", fma / (double)*cyc, *cyc);
     }
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
