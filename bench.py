@@ -250,6 +250,25 @@ def workload_config():
                 parallelism="window-sharded, no collective")
 
 
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Multi-rank runs: keep this process (its pinned host buffers are first-touched here, the host packer's threads
+    inherit the mask) on the CPUs NVML reports as local to its GPU, so eight ranks do not pull their panel rows across
+    the socket interconnect.  Host-side plumbing only; failures are reported, never fatal."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "nvml reports no local cpus inside this process's mask"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to {len(cpus)} cpus local to GPU {index}"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__}: {e})"
+
+
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
@@ -260,6 +279,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else "not bound (1 rank)"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -511,7 +531,7 @@ def run_gpu(args):
                                      "event-timed duration; ncu: 75 % of the DMMA pipe busy, the rest of the gap is padding "
                                      "(n_t to 64, n_u to 128) and the dense product with inv(L_ii)"),
             pack=dict(ms=pack_ms, gbs=2.0 * n_all * N / (pack_ms / 1e3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"]),
-            windows_ok=n_ok, imputed_per_step=n_imputed, panel_gen_s=gen_s,
+            windows_ok=n_ok, imputed_per_step=n_imputed, panel_gen_s=gen_s, host_affinity=numa_note,
         )
         if world == 1 and not args.no_cpu_baseline:
             s = cpu_sample("reference", n_t_target=400, n_u_sample=96)
