@@ -39,6 +39,7 @@ struct gb_batch {
   std::vector<SolveWin> h_wins;       // aligned with `active`
   std::vector<GramTile> h_tiles;      // [B11 tiles of all windows | B21 tiles of all windows]
   int n_tiles_tt = 0;                 // length of the B11 part
+  int* d_tile_counter = nullptr;      // tile ids of the B21 Gram range, drawn by the main launch and the helper launch
   double* d_y = nullptr;              // qcat only: y = L^-1 Z1 written by the solve kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // factorisation runs beside the B21 part (gb_batch_run)
   int64_t n_gather = 0;
@@ -100,7 +101,7 @@ void free_batch_device(gb_batch* b) {
                   b->d_st_sx_t, b->d_st_sx_u, b->d_st_mean_t, b->d_st_mean_u,
                   b->d_zt, b->d_zu, b->d_info, b->d_tt, b->d_ut, b->d_dinv,
                   b->d_coef, b->d_wgt, b->d_counts, b->d_status, b->d_wins, b->d_tiles,
-                  b->d_scratch, b->d_y};
+                  b->d_scratch, b->d_y, b->d_tile_counter};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, b->ctx->stream);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
@@ -362,6 +363,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   if ((rc = dev_alloc(ctx, &b->d_pool_t, (size_t)b->n_t_total))) return rc;
   if ((rc = dev_alloc(ctx, &b->d_pool_u, (size_t)b->n_u_total))) return rc;
   if ((rc = dev_alloc(ctx, &b->d_status, 2 * (size_t)nw + 2))) return rc;
+  if ((rc = dev_alloc(ctx, &b->d_tile_counter, 1))) return rc;
   if (b->mode == GRAM_MIX && !b->counts_mode) {
     const size_t P = (size_t)pn->n_pops;
     if ((rc = dev_alloc(ctx, &b->d_st_sx_t, P * (size_t)b->n_t_total))) return rc;
@@ -850,15 +852,19 @@ void gb_batch_destroy(gb_batch* b) {
 
 // Gram kernel + finish pass over tiles [first, first + count) of the batch's list, on at most max_ctas SMs
 // (0 = all of them).
-static int run_gram_range(gb_batch* b, int first, int count, int max_ctas) {
+static int run_gram_range(gb_batch* b, int first, int count, int max_ctas, int* tile_counter = nullptr,
+                          bool with_kernel = true, bool with_finish = true) {
   if (count <= 0) return GB_OK;
   Ctx* ctx = b->ctx;
   Panel* pn = b->panel;
   GramParams gp = b->gp;
   gp.tiles = b->gp.tiles + first;
   gp.n_tiles = count;
-  int rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, gp, b->cm, b->cn, max_ctas);
-  if (rc) return rc;
+  gp.tile_counter = tile_counter;
+  int rc = GB_OK;
+  if (with_kernel)
+    rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, gp, b->cm, b->cn, max_ctas);
+  if (rc || !with_finish) return rc;
   return gp.raw_out ? launch_gram_finalize(ctx, gp, count) : GB_OK;
 }
 
@@ -888,18 +894,23 @@ int gb_batch_run(gb_batch* b) {
   }
   if ((rc = run_stage(b, 0))) return rc;
   if ((rc = run_gram_range(b, 0, n_tt, 0))) return rc;
-  GB_CUDA(cudaEventRecord(b->ev_fork, ctx->stream));
+  // B21 tiles: the main launch owns sm_count - chol_sms SMs (launched first, so its persistent CTAs are placed before
+  // the factorisation's many small CTAs arrive) and draws tile ids from a counter; when the factorisation is done, a
+  // helper launch of the same kernel takes the SMs it leaves and draws from the same counter, so nothing idles while
+  // the main launch finishes.  The finish pass follows the join.
+  GB_CUDA(cudaMemsetAsync(b->d_tile_counter, 0, sizeof(int), ctx->stream));
+  GB_CUDA(cudaEventRecord(b->ev_fork, ctx->stream));      // B11 is final and the counter is zero: the side stream may start
   GB_CUDA(cudaStreamWaitEvent(ctx->side_stream, b->ev_fork, 0));
-  // B21 tiles first in launch order, so their persistent CTAs own their SMs before the factorisation's
-  // many small CTAs arrive
-  if ((rc = run_gram_range(b, n_tt, n_all - n_tt, ctx->sm_count - ctx->chol_sms))) return rc;
+  if ((rc = run_gram_range(b, n_tt, n_all - n_tt, ctx->sm_count - ctx->chol_sms, b->d_tile_counter, true, false))) return rc;
   cudaStream_t main_stream = ctx->stream;
   ctx->stream = ctx->side_stream;
   rc = run_stage(b, 2);
+  if (!rc) rc = run_gram_range(b, n_tt, n_all - n_tt, ctx->chol_sms, b->d_tile_counter, true, false);
   ctx->stream = main_stream;
   if (rc) return rc;
   GB_CUDA(cudaEventRecord(b->ev_join, ctx->side_stream));
   GB_CUDA(cudaStreamWaitEvent(ctx->stream, b->ev_join, 0));
+  if ((rc = run_gram_range(b, n_tt, n_all - n_tt, 0, nullptr, false, true))) return rc;
   return run_stage(b, 3);
 }
 

@@ -45,7 +45,8 @@ struct GramTile {      // one 128 x 128 output tile
 
 struct GramParams {
   const GramTile* tiles;  // cm*cn descriptors per cluster tile, in cluster-rank order (r*cn + c)
-  int n_tiles;            // number of CLUSTER tiles
+  int n_tiles;            // number of tiles
+  int* tile_counter;      // nullptr: tiles dealt round-robin; else a zeroed device counter several launches draw tile ids from
   int mode;
   int n_seg;
   int fkind;             // tensor-core operand kind: 0 = int8 (kind::i8), k > 0 = kind::f8f6f4 format k-1

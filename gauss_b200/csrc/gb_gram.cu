@@ -11,7 +11,9 @@
 // core already works on population p+1 (3-4 TMEM accumulator buffers).
 //
 // Warp roles (384 threads, 1 CTA/SM, persistent over a static tile list):
-//   warp 0      TMA producer (one elected lane): 128-byte-swizzled [128 rows x 128 B] boxes of A and B
+//   warp 0      TMA producer (one elected lane): 128-byte-swizzled [128 rows x 128 B] boxes of A and B; it also picks
+//               the next tile (round-robin, or from a device counter shared with other launches) and publishes the
+//               id to the other roles through a 16-slot shared-memory ring
 //   warp 1      MMA issuer (one elected lane)
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 64*((w-4)/4)..
@@ -56,6 +58,9 @@ constexpr int N_BARS = 2 * MAX_STAGES + 2 * ACC_BUFS;
 constexpr int OFF_TMEM_PTR = OFF_BARS + N_BARS * 8;
 constexpr int OFF_SEGTAB = 256;                               // int2 [P_MAX] {first K column, K atoms} per segment
 constexpr int OFF_COEFM = OFF_SEGTAB + P_MAX * 8;             // double [P_MAX] coef_p * m_p
+constexpr int TILE_RING = 16;                                 // tile ids in flight between the producer and the epilogue
+constexpr int OFF_TILE_BAR = OFF_COEFM + P_MAX * 8;           // uint64 [TILE_RING] mbarriers
+constexpr int OFF_TILE_ID = OFF_TILE_BAR + TILE_RING * 8;     // int [TILE_RING]
 constexpr int OFF_STAGES = 1024;                              // [stages][A 16 KiB | B 16 KiB]
 // fused-finish tables sit behind STAGES_FUSED stages
 constexpr int OFF_SA = OFF_STAGES + STAGES_FUSED * STAGE_BYTES; // int32 [P_MAX][128]
@@ -72,7 +77,7 @@ constexpr int SMEM_BYTES = SMEM_BYTES_FUSED > SMEM_BYTES_RAW ? SMEM_BYTES_FUSED 
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget exceeded");
 static_assert(OFF_TMEM_PTR + 16 <= OFF_SEGTAB, "barrier block overlaps the segment table");
-static_assert(OFF_COEFM + P_MAX * 8 <= OFF_STAGES, "segment tables overlap the stages");
+static_assert(OFF_TILE_ID + TILE_RING * 4 <= OFF_STAGES, "header tables overlap the stages");
 
 // int32 -> double through the 2^52 trick: one LOP and one exact DADD on the fp64 pipe (64 / clk / SM)
 // instead of I2F.F64, which issues at 16 / clk / SM and was the epilogue's limiter.
@@ -137,6 +142,11 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
   int2* segtab = reinterpret_cast<int2*>(smem + OFF_SEGTAB);
   double* coefm_s = reinterpret_cast<double*>(smem + OFF_COEFM);
+  // The producer decides which tile comes next -- round-robin, or from a global counter when several launches share one
+  // tile range (prm.tile_counter) -- and hands the id to the MMA thread and the epilogue warps through this ring.  It
+  // can be at most MAX_STAGES tiles ahead of the MMA thread and that at most ACC_BUFS tiles ahead of the epilogue.
+  uint64_t* tile_bar = reinterpret_cast<uint64_t*>(smem + OFF_TILE_BAR);
+  volatile int* tile_id = reinterpret_cast<volatile int*>(smem + OFF_TILE_ID);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,6 +172,7 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       ptx::mbar_init(&tfull_bar[b], 1);
       ptx::mbar_init(&tempty_bar[b], EPI_WARPS);
     }
+    for (int i = 0; i < TILE_RING; i++) ptx::mbar_init(&tile_bar[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -201,7 +212,19 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       // TMA unit complete half of what they occupy in shared memory)
       constexpr uint32_t stage_tx = FKIND == FKIND_F8F6F4 ? STAGE_BYTES / 2 : STAGE_BYTES;
       constexpr int kblk = FKIND == FKIND_MXF4 ? 2 * K_BLOCK : K_BLOCK;  // K columns per 128-byte stage row
-      for (int ct = blockIdx.x; ct < prm.n_tiles; ct += n_ctas) {
+      int next_static = blockIdx.x;
+      for (uint32_t seq = 0;; seq++) {
+        int ct;
+        if (prm.tile_counter) {
+          ct = atomicAdd(prm.tile_counter, 1);
+        } else {
+          ct = next_static;
+          next_static += n_ctas;
+        }
+        if (ct >= prm.n_tiles) ct = -1;
+        tile_id[seq & (TILE_RING - 1)] = ct;
+        ptx::mbar_arrive(&tile_bar[seq & (TILE_RING - 1)]);   // release: the id is visible to whoever sees the phase flip
+        if (ct < 0) break;
         const int2 rows = *reinterpret_cast<const int2*>(&prm.tiles[ct].a_row0);   // a_row0, b_row0
         const int2 srcs = *reinterpret_cast<const int2*>(&prm.tiles[ct].a_src);    // a_src, b_src
         const CUtensorMap* map_a = srcs.x ? &tm_a_scratch : &tm_a_panel;
@@ -240,7 +263,9 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       long long w_tempty = 0, w_full = 0, n_tempty_miss = 0, n_full_miss = 0;
       const long long t_begin = dbg ? clock64() : 0;
       bool acc_ready = false;                 // the next accumulator buffer was already seen handed back
-      for (int ct = blockIdx.x; ct < prm.n_tiles; ct += n_ctas) {
+      for (uint32_t seq = 0;; seq++) {
+        ptx::mbar_wait(&tile_bar[seq & (TILE_RING - 1)], (seq / TILE_RING) & 1);
+        if (tile_id[seq & (TILE_RING - 1)] < 0) break;
         for (int s = 0; s < n_seg; s++) {
           int atoms = segtab[s].y;
           if (!acc_ready) {
@@ -334,7 +359,10 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
     int acc_buf = 0;
     uint32_t acc_phase = 0;
 
-    for (int ct = blockIdx.x; ct < prm.n_tiles; ct += n_ctas) {
+    for (uint32_t seq = 0;; seq++) {
+      ptx::mbar_wait(&tile_bar[seq & (TILE_RING - 1)], (seq / TILE_RING) & 1);
+      const int ct = tile_id[seq & (TILE_RING - 1)];
+      if (ct < 0) break;
       const GramTile t = prm.tiles[ct];
       if (t.a_valid <= 0 || t.b_valid <= 0) {
         // padding slot of a ragged cluster tile: the MMAs ran (peers need this CTA's slices and
