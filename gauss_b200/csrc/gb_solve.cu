@@ -66,8 +66,9 @@ __device__ __forceinline__ void tile64_dmma(const double* As, const double* Bs, 
 constexpr int MP = NB + 2;  // column stride of the 64 x 64 shared-memory blocks of the factorisation
 
 // Warp-synchronous B x B version of the same transform (B = 16): lane r < B keeps row r of A (lower)
-// and row r of Y = inv(L) in registers; column j of L and row j of Y travel through two small shared
-// buffers.  No block barrier inside, ~250 clocks per pivot.  A at Ms[(o+c)*MP + o+r]; inv(L) is
+// and row r of Y = inv(L) in registers; column j of L and row j of Y travel by register shuffles (the
+// shared-memory round trips they used to take, with a __syncwarp each, were on the critical path of the 64
+// sequential pivots of a diagonal block: ncu put ~520 clocks on a pivot).  No block barrier inside.  A at Ms[(o+c)*MP + o+r]; inv(L) is
 // written (lower triangle, zeros above) to Xs at the same coordinates.  Kept out of line: the fully
 // unrolled pivot loop is straight-line code (a 32 x 32 version was 140 KB and bound by instruction
 // fetch); one 16 x 16 copy is called four times per diagonal block.
@@ -82,6 +83,8 @@ __device__ __noinline__ bool invchol_warp(const double* Ms, double* Xs, int o, d
     y[c] = 0.0;
   }
   bool bad_any = false;
+  (void)colbuf;
+  (void)rowbuf;
 #pragma unroll
   for (int j = 0; j < B; j++) {
     const double piv = __shfl_sync(0xffffffffu, a[j], j);
@@ -93,18 +96,13 @@ __device__ __noinline__ bool invchol_warp(const double* Ms, double* Xs, int o, d
 #pragma unroll
     for (int c = 0; c < j; c++) y[c] = is_j ? y[c] * rs : y[c];   // Y(j, c) *= rs
     if (is_j) y[j] = rs;                                          // Y(j, j) = rs
-    if (act) colbuf[lane] = l;
-    if (is_j) {
-#pragma unroll
-      for (int c = 0; c <= j; c++) rowbuf[c] = y[c];
-    }
-    __syncwarp();
+    // column j of L and row j of Y travel by register shuffles (no shared-memory round trip, no __syncwarp on the
+    // critical path of the 64 sequential pivots of a diagonal block)
     const double lm = (act && lane > j) ? -l : 0.0;
 #pragma unroll
-    for (int c = j + 1; c < B; c++) a[c] = fma(lm, colbuf[c], a[c]);   // A(r, c) -= L(r, j) L(c, j)
+    for (int c = j + 1; c < B; c++) a[c] = fma(lm, __shfl_sync(0xffffffffu, l, c), a[c]);       // A(r, c) -= L(r, j) L(c, j)
 #pragma unroll
-    for (int c = 0; c <= j; c++) y[c] = fma(lm, rowbuf[c], y[c]);      // Y(r, c) -= L(r, j) Y(j, c)
-    __syncwarp();
+    for (int c = 0; c <= j; c++) y[c] = fma(lm, __shfl_sync(0xffffffffu, y[c], j), y[c]);       // Y(r, c) -= L(r, j) Y(j, c)
   }
   if (act) {
 #pragma unroll
