@@ -354,6 +354,7 @@ def run_gpu(args):
     for k in range(args.steps):
         batch.run()
     e_end.record(stream)
+    torch.cuda.synchronize()      # the sampler must cover the device's timed region, not just the host's enqueue of it
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
