@@ -1603,7 +1603,13 @@ int gb_window_qcat(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* row
   else gb_params_default(&p);
   p.check_pd = 1;
   p.min_abs_eig = eig_cutoff;         // the certificate threshold plays CountPC's cut-off
-  p.min_num_unmeasured_snp = -1;      // run_qcat only checks the measured count (qcat.cpp:157)
+  // run_qcat only checks the measured count (qcat.cpp:157); run_qcatmix also refuses a window with too few unmeasured
+  // SNPs (qcatmix.cpp:168-169)
+  if (pop_wgt && n_u <= p.min_num_unmeasured_snp) {
+    ctx->err = "too few unmeasured SNPs in the window";
+    return GB_ERR_TOO_FEW_UNMEASURED;
+  }
+  p.min_num_unmeasured_snp = -1;
   const int64_t n_test = n_u + n_core;
   std::vector<int64_t> ru((size_t)n_test);
   for (int64_t i = 0; i < n_u; i++) ru[(size_t)i] = rows_u[i];

@@ -164,8 +164,8 @@ GB_API int gb_zmix_pair_cor(gb_ctx *ctx, gb_panel *panel, int64_t n, const int64
  * reference's [num_measured_headwing, + num_measured_pred) range of the extended window) and the unmeasured
  * SNPs rows_u.  pop_wgt == NULL -> qcat (pooled CalCor), else qcatmix (CalWgtCov).  Outputs: qcat_t and
  * qcat_chisq per tested SNP (SetQcatT / SetQcatChisq) and *num_eig (SetQcatM; CountPC util.cpp:355-388).
- * GB_ERR_TOO_FEW_MEASURED as qcat.cpp:157; GB_ERR_NOT_PD when no eigenvalue bound above eig_cutoff (default
- * 0.01, gauss.cpp:22) could be certified. */
+ * GB_ERR_TOO_FEW_MEASURED as qcat.cpp:157; qcatmix additionally GB_ERR_TOO_FEW_UNMEASURED (qcatmix.cpp:168-169);
+ * GB_ERR_NOT_PD when no eigenvalue bound above eig_cutoff (default 0.01, gauss.cpp:22) could be certified. */
 GB_API int gb_window_qcat(gb_ctx *ctx, gb_panel *panel, int64_t n_t, const int64_t *rows_t, const double *z_t,
                    int64_t core_first, int64_t n_core, int64_t n_u, const int64_t *rows_u,
                    const double *pop_wgt, const gb_params *params, double eig_cutoff, int *num_eig,

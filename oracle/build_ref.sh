@@ -22,12 +22,16 @@ cut_lines gauss.cpp 18 35 gauss_18_35.inc          # Arguments::Arguments defaul
 cut_lines dist.cpp 129 227 dist_129_227.inc        # run_dist
 cut_lines distmix.cpp 138 253 distmix_138_253.inc  # run_distmix
 cut_lines computeLD.cpp 95 116 computeLD_95_116.inc
+cut_lines qcat.cpp 134 262 qcat_134_262.inc          # run_qcat
+cut_lines qcatmix.cpp 145 286 qcatmix_145_286.inc    # run_qcatmix
 # guard: the extraction must start/end on the expected function boundaries
 grep -q '^double CalCor(std::vector<std::string>& x, std::vector<std::string>& y){' "$OUT/gen/util_49_70.inc"
 grep -q '^double CalWgtCov(' "$OUT/gen/util_103_124.inc"
 grep -q '^double CalCor(std::string& x, std::string& y){' "$OUT/gen/util_153_169.inc"
 grep -q '^void run_dist(' "$OUT/gen/dist_129_227.inc"
 grep -q '^void run_distmix(' "$OUT/gen/distmix_138_253.inc"
+grep -q '^void run_qcat(' "$OUT/gen/qcat_134_262.inc"
+grep -q '^void run_qcatmix(' "$OUT/gen/qcatmix_145_286.inc"
 grep -q '^Arguments::Arguments(){' "$OUT/gen/gauss_18_35.inc"
 CXXFLAGS="-O2 -fPIC -ffp-contract=off -w -I$HERE/ref_shim -I$SRC -I$HERE -I$OUT"
 gcc -O2 -fPIC -ffp-contract=off -c "$HERE/gauss_oracle.c" -o "$OUT/gauss_oracle_int.o" \

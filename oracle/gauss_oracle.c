@@ -559,7 +559,8 @@ int go_run_qcat(const int *type, const long long *bp, const double *z, const cha
       else if (bp[i] >= args->start_bp && bp[i] <= args->end_bp) npred++;
     }
   }
-  if (nt <= args->min_num_measured_snp) { /* qcat.cpp:157 */
+  /* run_qcat checks the measured count only (qcat.cpp:157); run_qcatmix also the unmeasured one (qcatmix.cpp:168-169) */
+  if (nt <= args->min_num_measured_snp || (w && nu <= args->min_num_unmeasured_snp)) {
     free(meas);
     free(unme);
     return GO_ERR_TOO_FEW_SNPS;

@@ -5,4 +5,5 @@
 #include "gauss_oracle.h"
 int gor_make_pos_def(double *A, int n, double min_abs_eig);
 void gor_inv_full_piv_lu(double *inv, const double *A, int n);
+int gor_count_pc(const double *A, int n, double eig_cutoff);
 #endif

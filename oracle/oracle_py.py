@@ -158,7 +158,6 @@ class Oracle:
     def run_qcat(self, type_, bp, z, geno, m, w=None, start_bp=0, end_bp=0, lam=0.1, eig_cutoff=0.01,
                  min_measured=10):
         """run_qcat (w=None) / run_qcatmix.  Returns dict(rc, m, t, chisq) indexed like the SNP list (NaN = untested)."""
-        assert self.kind == "port"
         type_ = np.ascontiguousarray(type_, np.int32)
         bp = np.ascontiguousarray(bp, np.int64)
         zz = np.ascontiguousarray(z, np.float64)

@@ -48,6 +48,46 @@ void InvMat(Eigen::MatrixXd& inverse, const Eigen::Ref<const Eigen::MatrixXd>& m
 void MakePosDef(Eigen::MatrixXd& m1, double min_abs_eig) {  // util.cpp:302-318
   gor_make_pos_def(m1.data(), (int)m1.rows(), min_abs_eig);
 }
+void CholeskyMat(Eigen::MatrixXd& result, const Eigen::Ref<const Eigen::MatrixXd>& m) {  // util.cpp:271-274 (Eigen::LLT)
+  const long n = m.rows();
+  result = Eigen::MatrixXd::Zero(n, n);
+  for (long j = 0; j < n; j++) {
+    double d = m(j, j);
+    for (long k = 0; k < j; k++) d -= result(j, k) * result(j, k);
+    d = std::sqrt(d);
+    result(j, j) = d;
+    for (long i = j + 1; i < n; i++) {
+      double v = m(i, j);
+      for (long k = 0; k < j; k++) v -= result(i, k) * result(j, k);
+      result(i, j) = v / d;
+    }
+  }
+}
+int CountPC(const Eigen::Ref<const Eigen::MatrixXd>& m1, double eig_cutoff) {  // util.cpp:355-388
+  return gor_count_pc(m1.data(), (int)m1.rows(), eig_cutoff);
+}
+double CalCor(const Eigen::Ref<const Eigen::VectorXd>& x, const Eigen::Ref<const Eigen::VectorXd>& y) {  // util.cpp:193-202
+  const long n = x.size();
+  double mx = 0.0, my = 0.0;
+  for (long i = 0; i < n; i++) mx += x(i);
+  for (long i = 0; i < n; i++) my += y(i);
+  mx /= n;
+  my /= n;
+  double sxx = 0.0, syy = 0.0, sxy = 0.0;
+  for (long i = 0; i < n; i++) sxx += (x(i) - mx) * (x(i) - mx);
+  for (long i = 0; i < n; i++) syy += (y(i) - my) * (y(i) - my);
+  for (long i = 0; i < n; i++) sxy += (x(i) - mx) * (y(i) - my);
+  return sxy / std::sqrt(sxx * syy);
+}
+double CalVar(const Eigen::Ref<const Eigen::VectorXd>& x) {  // util.cpp:214-219
+  const long n = x.size();
+  double mx = 0.0;
+  for (long i = 0; i < n; i++) mx += x(i);
+  mx /= n;
+  double s = 0.0;
+  for (long i = 0; i < n; i++) s += (x(i) - mx) * (x(i) - mx);
+  return s / (double)(n - 1);
+}
 void LoadProgressBar(int) {}  // util.cpp:449-461 prints a text bar; silent here
 
 // ---- the reference's own code, extracted at build time -----------------------------------
@@ -59,6 +99,10 @@ void run_dist(std::vector<Snp*>& snp_vec, Arguments& args);
 void run_distmix(std::vector<Snp*>& snp_vec, Arguments& args);
 #include "gen/dist_129_227.inc"
 #include "gen/distmix_138_253.inc"
+void run_qcat(std::vector<Snp*>& snp_vec, Arguments& args);
+void run_qcatmix(std::vector<Snp*>& snp_vec, Arguments& args);
+#include "gen/qcat_134_262.inc"
+#include "gen/qcatmix_145_286.inc"
 
 static void ref_ld_block(std::vector<Snp*>& snp_vec_measured, Arguments& args, double* out) {
   int num_measured = snp_vec_measured.size();
@@ -82,6 +126,49 @@ static std::vector<std::string> split_pops(const char* row, const int* m, int n_
 extern "C" {
 
 double go_last_sample_pairs(void) { return g_pairs; }
+
+// run_qcat / run_qcatmix: the reference's own bodies around the restated Eigen algorithms above
+int go_run_qcat(const int* type, const long long* bp, const double* z, const char* geno, int64_t n_snps, const int* m,
+                int n_pops, const double* w, const go_args* a, double eig_cutoff, double* qcat_m, double* qcat_t,
+                double* qcat_chisq) {
+  int64_t N = 0;
+  for (int p = 0; p < n_pops; p++) N += m[p];
+  Arguments args;
+  args.chr = 0;
+  args.start_bp = a->start_bp;
+  args.end_bp = a->end_bp;
+  args.lambda = a->lambda;
+  args.eig_cutoff = eig_cutoff;
+  args.min_num_measured_snp = a->min_num_measured_snp;
+  args.min_num_unmeasured_snp = a->min_num_unmeasured_snp;
+  args.num_samples = (int)N;
+  if (w) args.pop_wgt_vec.assign(w, w + n_pops);
+  std::vector<Snp> store((size_t)n_snps);
+  std::vector<Snp*> snp_vec;
+  for (int64_t i = 0; i < n_snps; i++) {
+    Snp& s = store[(size_t)i];
+    s.SetBp(bp[i]);
+    s.SetType(type[i]);
+    s.SetZ(z[i]);
+    s.SetQcatM(-1);
+    auto gv = split_pops(geno + i * N, m, n_pops);
+    s.SetGenotypeVec(gv);
+    snp_vec.push_back(&s);
+  }
+  try {
+    if (w) run_qcatmix(snp_vec, args);
+    else run_qcat(snp_vec, args);
+  } catch (const std::runtime_error&) {
+    return GO_ERR_TOO_FEW_SNPS;
+  }
+  for (int64_t i = 0; i < n_snps; i++) {
+    if (store[(size_t)i].GetQcatM() < 0) continue;   // not tested
+    qcat_m[i] = store[(size_t)i].GetQcatM();
+    qcat_t[i] = store[(size_t)i].GetQcatT();
+    qcat_chisq[i] = store[(size_t)i].GetQcatChisq();
+  }
+  return GO_OK;
+}
 
 // the pair loop of prep_zmix5 (zmix.cpp:151-170) around the reference's own CalCor(std::string&, std::string&)
 void go_zmix_pairs(const char* geno, int64_t n, const int* m, int n_pops, const double* z, double* out) {

@@ -1,8 +1,9 @@
 """qcat() / qcatmix() window (reference qcat.cpp:133-238, qcatmix.cpp:140-269).
 
-The reference ships no vectors for it and its compiled-here `_ref` build does not include run_qcat, so the C
-restatement (oracle/gauss_oracle.c go_run_qcat) is pinned against an independent numpy computation here (CPU test)
-and the CUDA path against the restatement (GPU tests).  Tolerance: 1e-6 absolute on qcat_t / qcat_chisq (asserted
+The reference ships no vectors for it.  The C restatement (oracle/gauss_oracle.c go_run_qcat) is pinned twice on the CPU:
+bit for bit against the reference's OWN run_qcat / run_qcatmix bodies compiled by oracle/build_ref.sh (with the restated
+Eigen algorithms, like run_dist), and against an independent numpy computation; the CUDA path is checked against the
+restatement (GPU tests).  Tolerance: 1e-6 absolute on qcat_t / qcat_chisq (asserted
 tighter where it holds); num_eig is an integer and must match exactly."""
 import numpy as np
 import pytest
@@ -57,6 +58,26 @@ def test_oracle_qcat_against_numpy(oracle):
     assert few["rc"] != 0
 
 
+@pytest.mark.parametrize("mix", [False, True])
+def test_port_matches_compiled_reference(oracle, ref_oracle, mix):
+    c = small_case(seed=7 + mix, n_snps=280, measured_frac=0.35, core=(60, 210))
+    w = c["w"] if mix else None
+    a = oracle.run_qcat(c["type"], c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"])
+    b = ref_oracle.run_qcat(c["type"], c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"])
+    assert a["rc"] == b["rc"] == 0
+    for k in ("m", "t", "chisq"):
+        np.testing.assert_array_equal(a[k], b[k])          # same tested set (NaN elsewhere), same bits
+    assert np.isfinite(a["t"]).sum() > 100
+    # the two entry points differ in what they refuse: run_qcat only looks at the measured count (qcat.cpp:157),
+    # run_qcatmix also at the unmeasured one (qcatmix.cpp:168-169)
+    t2 = c["type"].copy()
+    core = (c["bp"] >= c["start_bp"]) & (c["bp"] <= c["end_bp"])
+    t2[(t2 == 0) & core] = 2                                    # no unmeasured SNP left in the prediction window
+    a2 = oracle.run_qcat(t2, c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"])
+    b2 = ref_oracle.run_qcat(t2, c["bp"], c["z"], c["g"], c["pop_sizes"], w, c["start_bp"], c["end_bp"])
+    assert a2["rc"] == b2["rc"] and (a2["rc"] != 0) == mix
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mix", [False, True])
 @pytest.mark.parametrize("fmt", ["e2m1", "int8"])
@@ -101,6 +122,10 @@ def test_qcat_edge_cases(gpu_ctx, oracle):
     only_m = panel.window_qcat(meas, z[meas], headwing, n_core, np.zeros(0, np.int64), None)
     full = panel.window_qcat(meas, z[meas], headwing, n_core, unme, None)
     np.testing.assert_array_equal(only_m["t_m"], full["t_m"])
+    # ... but qcatmix has one (qcatmix.cpp:168-169)
+    r = panel.window_qcat(meas, z[meas], headwing, n_core, unme[:10], c["w"], allow=(api.GB_ERR_TOO_FEW_UNMEASURED,))
+    assert r["rc"] == api.GB_ERR_TOO_FEW_UNMEASURED
+    assert panel.window_qcat(meas, z[meas], headwing, n_core, unme[:10], None)["rc"] == 0
     # nothing measured in the prediction window
     none_m = panel.window_qcat(meas, z[meas], headwing, 0, unme, None)
     np.testing.assert_array_equal(none_m["t_u"], full["t_u"])
