@@ -23,6 +23,8 @@ cut_lines dist.cpp 129 227 dist_129_227.inc        # run_dist
 cut_lines distmix.cpp 138 253 distmix_138_253.inc  # run_distmix
 cut_lines computeLD.cpp 95 116 computeLD_95_116.inc
 cut_lines qcat.cpp 134 262 qcat_134_262.inc          # run_qcat
+cut_lines gene.cpp 569 586 gene_569_586.inc          # CorG of Gene::CalJepegmixPval (mixture)
+cut_lines gene.cpp 305 315 gene_305_314.inc          # CorG of Gene::CalJepegPval (pooled CalCor)
 cut_lines qcatmix.cpp 145 286 qcatmix_145_286.inc    # run_qcatmix
 # guard: the extraction must start/end on the expected function boundaries
 grep -q '^double CalCor(std::vector<std::string>& x, std::vector<std::string>& y){' "$OUT/gen/util_49_70.inc"
@@ -31,6 +33,8 @@ grep -q '^double CalCor(std::string& x, std::string& y){' "$OUT/gen/util_153_169
 grep -q '^void run_dist(' "$OUT/gen/dist_129_227.inc"
 grep -q '^void run_distmix(' "$OUT/gen/distmix_138_253.inc"
 grep -q '^void run_qcat(' "$OUT/gen/qcat_134_262.inc"
+grep -q 'Eigen::VectorXd SNP_STD_VEC' "$OUT/gen/gene_569_586.inc"
+grep -q 'CorG(i, i) = 1.0 + lambda_;' "$OUT/gen/gene_305_314.inc"
 grep -q '^void run_qcatmix(' "$OUT/gen/qcatmix_145_286.inc"
 grep -q '^Arguments::Arguments(){' "$OUT/gen/gauss_18_35.inc"
 CXXFLAGS="-O2 -fPIC -ffp-contract=off -w -I$HERE/ref_shim -I$SRC -I$HERE -I$OUT"

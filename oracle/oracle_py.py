@@ -185,6 +185,23 @@ class Oracle:
         self.lib.go_zmix_pairs(g, n, m, len(m), z, out)
         return out.T
 
+    def gene_corg(self, geno, m, w=None, lam=0.1):
+        """CorG of one gene exactly as Gene::CalJepegmixPval (w given) / Gene::CalJepegPval (w None) build it
+        (gene.cpp:569-586 / 305-315); reference build only -- the port's equivalent is compute_ld / cal_cor + diagonal."""
+        assert self.kind == "reference"
+        g = _chars(geno)
+        m = np.ascontiguousarray(m, np.int32)
+        n = g.shape[0]
+        out = np.zeros((n, n), np.float64)
+        wp = None
+        if w is not None:
+            w = np.ascontiguousarray(w, np.float64)
+            wp = w.ctypes.data
+        self.lib.go_gene_corg.restype = None
+        self.lib.go_gene_corg.argtypes = [_c_u8p, C.c_int64, _c_i32p, C.c_int, C.c_void_p, C.c_double, _c_f64p]
+        self.lib.go_gene_corg(g, n, m, len(m), wp, lam, out)
+        return out
+
     def compute_ld(self, geno, m, w):
         g = _chars(geno)
         m = np.ascontiguousarray(m, np.int32)

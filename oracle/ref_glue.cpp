@@ -110,6 +110,18 @@ static void ref_ld_block(std::vector<Snp*>& snp_vec_measured, Arguments& args, d
   std::memcpy(out, Cor_Mat.data(), sizeof(double) * (size_t)num_measured * num_measured);
 }
 
+// CorG of one gene as Gene::CalJepegmixPval (gene.cpp:569-586) / Gene::CalJepegPval (gene.cpp:305-314) build it
+static void ref_gene_corg(std::vector<Snp*>& gene_snp_vec, std::vector<double>& pop_wgt_vec_, double lambda_, bool mix,
+                          double* out) {
+  Eigen::MatrixXd CorG = Eigen::MatrixXd::Zero(gene_snp_vec.size(), gene_snp_vec.size());
+  if (mix) {
+#include "gen/gene_569_586.inc"
+  } else {
+#include "gen/gene_305_314.inc"
+  }
+  std::memcpy(out, CorG.data(), sizeof(double) * gene_snp_vec.size() * gene_snp_vec.size());
+}
+
 // ---- same C surface as gauss_oracle.h ------------------------------------------------------
 static __thread double g_pairs = 0.0;
 
@@ -126,6 +138,22 @@ static std::vector<std::string> split_pops(const char* row, const int* m, int n_
 extern "C" {
 
 double go_last_sample_pairs(void) { return g_pairs; }
+
+// CorG block of one gene (n SNP rows), column-major n x n; w == NULL -> jepeg (pooled CalCor)
+void go_gene_corg(const char* geno, int64_t n, const int* m, int n_pops, const double* w, double lambda, double* out) {
+  int64_t N = 0;
+  for (int p = 0; p < n_pops; p++) N += m[p];
+  std::vector<Snp> store((size_t)n);
+  std::vector<Snp*> vec;
+  for (int64_t i = 0; i < n; i++) {
+    auto gv = split_pops(geno + i * N, m, n_pops);
+    store[(size_t)i].SetGenotypeVec(gv);
+    vec.push_back(&store[(size_t)i]);
+  }
+  std::vector<double> wv;
+  if (w) wv.assign(w, w + n_pops);
+  ref_gene_corg(vec, wv, lambda, w != nullptr, out);
+}
 
 // run_qcat / run_qcatmix: the reference's own bodies around the restated Eigen algorithms above
 int go_run_qcat(const int* type, const long long* bp, const double* z, const char* geno, int64_t n_snps, const int* m,

@@ -8,6 +8,23 @@ from gauss_b200 import synth
 from helpers import small_case
 
 
+def test_port_corg_equals_the_references_own_block(oracle, ref_oracle):
+    """What the GPU test below compares against (computeLD restatement with the diagonal forced to 1 + lambda, and the
+    pooled CalCor) is bit for bit the CorG block Gene::CalJepegmixPval / CalJepegPval build (gene.cpp:569-586, 305-315),
+    compiled from the reference by oracle/build_ref.sh."""
+    c = small_case(seed=72, n_snps=40)
+    for n in (1, 2, 9):
+        want = ref_oracle.gene_corg(c["g"][:n], c["pop_sizes"], c["w"], lam=0.1)
+        got = oracle.compute_ld(c["g"][:n], c["pop_sizes"], c["w"])
+        np.fill_diagonal(got, 1.0 + 0.1)
+        np.testing.assert_array_equal(got, want)
+        wantp = ref_oracle.gene_corg(c["g"][:n], c["pop_sizes"], None, lam=0.1)
+        for i in range(n):
+            assert wantp[i, i] == 1.0 + 0.1
+            for j in range(i + 1, n):
+                assert wantp[i, j] == wantp[j, i] == oracle.cal_cor(c["g"][i], c["g"][j], c["pop_sizes"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["e2m1", "int8"])
 def test_genes_ld_matches_oracle(gpu_ctx, oracle, fmt):
