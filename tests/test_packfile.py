@@ -30,6 +30,34 @@ def write_reference_panel(tmp_path, g, pops, sizes, sups):
     return str(path), str(desc)
 
 
+def write_bgzf(path, data: bytes, block: int = 3000):
+    """A BGZF file as bgzf.c writes it: gzip members with the 'BC' extra field, plus the empty EOF block."""
+    import struct
+    import zlib
+    with open(path, "wb") as f:
+        chunks = [data[i:i + block] for i in range(0, len(data), block)] + [b""]
+        for c in chunks:
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            payload = co.compress(c) + co.flush()
+            bsize = 12 + 6 + len(payload) + 8 - 1
+            f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize))
+            f.write(payload + struct.pack("<II", zlib.crc32(c), len(c)))
+
+
+def test_bgzf_panel_is_inflated_block_parallel(tmp_path):
+    g = synth.make_genotypes(120, SIZES, seed=93).astype(np.int8)
+    geno, desc = write_reference_panel(tmp_path, g, POPS, SIZES, SUPS)
+    text = gzip.open(geno, "rb").read()
+    bg = str(tmp_path / "panel_bgzf_geno.gz")
+    write_bgzf(bg, text)
+    assert gzip.open(bg, "rb").read() == text                        # a BGZF file is also a valid gzip file
+    assert b"".join(packfile.iter_panel_lines(bg, threads=4, batch=7)) == text
+    assert b"".join(packfile.iter_panel_lines(geno)) == text          # plain gzip: sequential fallback
+    out = str(tmp_path / "p.gbpack")
+    packfile.convert_reference_panel(bg, desc, out)
+    np.testing.assert_array_equal(np.asarray(packfile.PackFile(out).rows), api.pack2_rows_host(SIZES, g))
+
+
 POPS = ["CEU", "GBR", "YRI", "JPT", "CHB", "MXL"]
 SUPS = ["EUR", "EUR", "AFR", "ASN", "ASN", "AMR"]
 SIZES = np.array([61, 130, 7, 128, 33, 2], np.int32)
