@@ -114,6 +114,9 @@ def load_library():
         "gb_pipe_submit": (C.c_int, [vp, i64, vp, i64, vp, i64, C.c_int, dblp, dblp, C.POINTER(Params), dblp, dblp,
                                      C.POINTER(C.c_int64)]),
         "gb_pipe_wait": (C.c_int, [vp, i64, C.POINTER(C.c_int)]),
+        "gb_run_qcat_strings": (C.c_int, [vp, i64, vp, vp, dblp, vp, C.c_int, vp, dblp, C.c_longlong, C.c_longlong,
+                                          C.POINTER(Params), C.c_double, dblp, dblp, dblp, C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int)]),
         "gb_run_window_strings": (C.c_int, [vp, i64, vp, vp, dblp, dblp, vp, C.c_int, vp, dblp, C.c_longlong,
                                             C.c_longlong, C.POINTER(Params), C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)]),
@@ -246,6 +249,36 @@ class Context:
                                             int(end_bp), C.byref(params) if params else None, C.byref(nt),
                                             C.byref(nu))
         return dict(rc=rc, z=z, info=info, n_t=nt.value, n_u=nu.value)
+
+
+def _string_table(pop_strings, n, P):
+    arr = (C.c_char_p * (n * P))()
+    keep = []
+    for i in range(n):
+        for k in range(P):
+            s = pop_strings[i][k] if pop_strings[i] is not None else None
+            keep.append(s)
+            arr[i * P + k] = s
+    return arr, keep
+
+
+def run_qcat_strings(ctx: "Context", type_, bp, z, pop_strings, pop_sizes, pop_wgt, start_bp, end_bp,
+                     params: Params | None = None, eig_cutoff: float = 0.01):
+    """gb_run_qcat_strings: host mirror of run_qcat / run_qcatmix.  -> dict(rc, m, t, chisq) (NaN = untested)."""
+    type_ = np.ascontiguousarray(type_, np.int32)
+    bp = np.ascontiguousarray(bp, np.int64)
+    z = _f64(z)
+    pop_sizes = np.ascontiguousarray(pop_sizes, np.int32)
+    n, P = len(type_), len(pop_sizes)
+    arr, keep = _string_table(pop_strings, n, P)
+    w = None if pop_wgt is None else _f64(pop_wgt)
+    qm, qt, qc = (np.full(n, np.nan) for _ in range(3))
+    nt, nu = C.c_int(0), C.c_int(0)
+    rc = ctx.lib.gb_run_qcat_strings(ctx.h, n, _ptr(type_), _ptr(bp), _ptr(z), C.cast(arr, C.c_void_p), P,
+                                     _ptr(pop_sizes), _ptr(w), int(start_bp), int(end_bp),
+                                     C.byref(params) if params else None, float(eig_cutoff), _ptr(qm), _ptr(qt),
+                                     _ptr(qc), C.byref(nt), C.byref(nu))
+    return dict(rc=rc, m=qm, t=qt, chisq=qc, n_t=nt.value, n_u=nu.value)
 
 
 class Panel:

@@ -1914,3 +1914,69 @@ int gb_run_window_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const lo
 }
 
 }  // extern "C"
+
+// ---- host-side mirror of run_qcat / run_qcatmix (qcat.cpp:134-262, qcatmix.cpp:145-286) -----------------
+int gb_run_qcat_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const long long* bp, const double* z,
+                        const char* const* pop_strings, int n_pops, const int* pop_sizes, const double* pop_wgt,
+                        long long start_bp, long long end_bp, const gb_params* params, double eig_cutoff, double* qcat_m,
+                        double* qcat_t, double* qcat_chisq, int* n_measured, int* n_unmeasured) {
+  if (!ctx || n_snps < 0 || !type || !bp || !z || !pop_strings || !pop_sizes || !qcat_m || !qcat_t || !qcat_chisq) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  gb_params p;
+  if (params) p = *params;
+  else gb_params_default(&p);
+  // qcat.cpp:139-152 -- type 0 inside the prediction window is tested as unmeasured; every type 1 SNP of the extended
+  // window is measured, those before start_bp are the head wing, those inside the window are tested as measured
+  std::vector<int64_t> meas, unme;
+  int64_t headwing = 0, n_pred = 0;
+  for (int64_t i = 0; i < n_snps; i++) {
+    if (type[i] == 0 && bp[i] >= start_bp && bp[i] <= end_bp) {
+      unme.push_back(i);
+    } else if (type[i] == 1) {
+      meas.push_back(i);
+      if (bp[i] < start_bp) headwing++;
+      else if (bp[i] <= end_bp) n_pred++;
+    }
+  }
+  if (n_measured) *n_measured = (int)meas.size();
+  if (n_unmeasured) *n_unmeasured = (int)unme.size();
+  if ((int64_t)meas.size() <= p.min_num_measured_snp) return GB_ERR_TOO_FEW_MEASURED;                      // qcat.cpp:157
+  if (pop_wgt && (int64_t)unme.size() <= p.min_num_unmeasured_snp) return GB_ERR_TOO_FEW_UNMEASURED;      // qcatmix.cpp:168
+  const int64_t nt = (int64_t)meas.size(), nu = (int64_t)unme.size();
+  std::vector<const char*> strs((size_t)(nt + nu) * n_pops);
+  for (int64_t i = 0; i < nt + nu; i++) {
+    const int64_t s = i < nt ? meas[(size_t)i] : unme[(size_t)(i - nt)];
+    for (int k = 0; k < n_pops; k++) strs[(size_t)(i * n_pops + k)] = pop_strings[s * n_pops + k];
+  }
+  int rc = GB_OK;
+  for (int format = ctx->panel_format;; format = GB_PANEL_INT8) {   // strings with other characters are repacked as int8
+    gb_panel* panel = nullptr;
+    rc = gb_panel_create_fmt(ctx, n_pops, pop_sizes, nt + nu, format, &panel);
+    if (rc) return rc;
+    rc = gb_panel_append_strings(panel, nt + nu, strs.data());
+    if (!rc) {
+      std::vector<int64_t> rt((size_t)nt), ru((size_t)nu);
+      std::vector<double> zt((size_t)nt), tm((size_t)n_pred), cm((size_t)n_pred), tu((size_t)nu), cu((size_t)nu);
+      for (int64_t i = 0; i < nt; i++) rt[(size_t)i] = i, zt[(size_t)i] = z[meas[(size_t)i]];
+      for (int64_t i = 0; i < nu; i++) ru[(size_t)i] = nt + i;
+      int num_eig = 0;
+      rc = gb_window_qcat(ctx, panel, nt, rt.data(), zt.data(), headwing, n_pred, nu, ru.data(), pop_wgt, &p, eig_cutoff,
+                          &num_eig, tm.data(), cm.data(), tu.data(), cu.data());
+      if (rc == GB_OK) {   // SetQcatM / SetQcatT / SetQcatChisq, qcat.cpp:230-232, 247-249
+        for (int64_t i = 0; i < n_pred; i++) {
+          const int64_t s = meas[(size_t)(headwing + i)];
+          qcat_m[s] = num_eig, qcat_t[s] = tm[(size_t)i], qcat_chisq[s] = cm[(size_t)i];
+        }
+        for (int64_t i = 0; i < nu; i++) {
+          const int64_t s = unme[(size_t)i];
+          qcat_m[s] = num_eig, qcat_t[s] = tu[(size_t)i], qcat_chisq[s] = cu[(size_t)i];
+        }
+      }
+    }
+    gb_panel_destroy(panel);
+    if (rc != GB_ERR_UNSUPPORTED || format == GB_PANEL_INT8) break;
+  }
+  return rc;
+}

@@ -259,6 +259,16 @@ GB_API int gb_run_window_strings(gb_ctx *ctx, int64_t n_snps, const int *type, c
                           long long end_bp, const gb_params *params, int *n_measured,
                           int *n_unmeasured);
 
+/* run_qcat / run_qcatmix (qcat.cpp:134-262, qcatmix.cpp:145-286) on the same parallel arrays: splits the SNPs as
+ * qcat.cpp:139-152 (head wing, tested measured, tested unmeasured), packs the strings, runs gb_window_qcat and writes
+ * qcat_m / qcat_t / qcat_chisq of the tested SNPs in place (SetQcatM / SetQcatT / SetQcatChisq); other entries are left
+ * untouched.  pop_wgt == NULL -> run_qcat. */
+GB_API int gb_run_qcat_strings(gb_ctx *ctx, int64_t n_snps, const int *type, const long long *bp, const double *z,
+                        const char *const *pop_strings, int n_pops, const int *pop_sizes,
+                        const double *pop_wgt, long long start_bp, long long end_bp, const gb_params *params,
+                        double eig_cutoff, double *qcat_m, double *qcat_t, double *qcat_chisq, int *n_measured,
+                        int *n_unmeasured);
+
 #ifdef __cplusplus
 }
 #endif

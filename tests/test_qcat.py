@@ -157,3 +157,30 @@ def test_qcatmix_33kg_shape(gpu_ctx, oracle):
     assert np.abs(out["t_u"] - ref["t"][unme]).max() <= 1e-8
     assert np.abs(out["t_m"] - ref["t"][core_m]).max() <= 1e-8
     assert np.abs(out["chisq_u"] - ref["chisq"][unme]).max() <= 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mix", [False, True])
+def test_host_mirror_of_run_qcat_strings(gpu_ctx, oracle, mix):
+    """gb_run_qcat_strings receives exactly what run_qcat / run_qcatmix receive (bp-sorted SNPs with type, z and one
+    genotype string per flagged population) and must leave what they leave on the Snp objects."""
+    c = small_case(seed=55 + mix, n_snps=360, measured_frac=0.33, core=(90, 280))
+    g, t, bp, z = c["g"], c["type"].copy(), c["bp"], c["z"]
+    t[::17] = 2                                             # SNPs absent from the panel are ignored (type 2)
+    w = c["w"] if mix else None
+    offs = np.concatenate([[0], np.cumsum(c["pop_sizes"])])
+    chars = (g.astype(np.int16) + 48).astype(np.uint8)
+    strings = [[chars[i, offs[k]:offs[k + 1]].tobytes() for k in range(len(c["pop_sizes"]))] if t[i] != 2 else None
+               for i in range(len(g))]
+    strings = [s if s is not None else [b""] * len(c["pop_sizes"]) for s in strings]
+    out = api.run_qcat_strings(gpu_ctx, t, bp, z, strings, c["pop_sizes"], w, c["start_bp"], c["end_bp"])
+    ref = oracle.run_qcat(t, bp, z, g, c["pop_sizes"], w, c["start_bp"], c["end_bp"])
+    assert out["rc"] == 0 and ref["rc"] == 0
+    np.testing.assert_array_equal(np.isnan(out["t"]), np.isnan(ref["t"]))          # the same SNPs are tested
+    tested = ~np.isnan(ref["t"])
+    assert tested.sum() > 100
+    np.testing.assert_array_equal(out["m"][tested], ref["m"][tested])
+    assert np.abs(out["t"][tested] - ref["t"][tested]).max() <= 1e-8
+    assert np.abs(out["chisq"][tested] - ref["chisq"][tested]).max() <= 1e-8
+    few = api.run_qcat_strings(gpu_ctx, t[:25], bp[:25], z[:25], strings[:25], c["pop_sizes"], w, 0, 10**12)
+    assert few["rc"] == api.GB_ERR_TOO_FEW_MEASURED
