@@ -5,8 +5,8 @@ The product is the C-ABI shared library ``gauss_b200/lib/libgauss_b200.so`` (see
 There is no CPU fallback: importing works anywhere, every compute call needs a B200.
 """
 from .api import (  # noqa: F401
-    GB_OK, GaussB200Error, Context, Panel, Batch, Pipe, Params, load_library, library_path, exported_symbols,
+    GB_OK, GaussB200Error, Context, Panel, Batch, Pipe, Genome, Params, load_library, library_path, exported_symbols,
 )
 
-__all__ = ["GB_OK", "GaussB200Error", "Context", "Panel", "Batch", "Pipe", "Params", "load_library",
+__all__ = ["GB_OK", "GaussB200Error", "Context", "Panel", "Batch", "Pipe", "Genome", "Params", "load_library",
            "library_path", "exported_symbols"]

@@ -114,6 +114,23 @@ def load_library():
         "gb_pipe_submit": (C.c_int, [vp, i64, vp, i64, vp, i64, C.c_int, dblp, dblp, C.POINTER(Params), dblp, dblp,
                                      C.POINTER(C.c_int64)]),
         "gb_pipe_wait": (C.c_int, [vp, i64, C.POINTER(C.c_int)]),
+        "gb_genome_create": (C.c_int, [C.c_int, i32p, C.c_int, i32p, dblp, C.POINTER(Params), C.POINTER(vp)]),
+        "gb_genome_destroy": (None, [vp]),
+        "gb_genome_last_error": (C.c_char_p, [vp]),
+        "gb_genome_add_chromosome": (C.c_int, [vp, i64, vp, i64, i64, i64p, i64p, i64p, i64p, dblp, i64p]),
+        "gb_genome_plan": (C.c_int, [vp, C.c_int, C.c_int]),
+        "gb_genome_num_chromosomes": (C.c_int, [vp]),
+        "gb_genome_shard_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int),
+                                           C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "gb_genome_upload": (C.c_int, [vp, C.c_int]),
+        "gb_genome_fill_synthetic": (C.c_int, [vp, C.c_uint64, C.c_int]),
+        "gb_genome_submit": (C.c_int, [vp, vp, vp, vp]),
+        "gb_genome_wait": (C.c_int, [vp, dblp, dblp]),
+        "gb_genome_run": (C.c_int, [vp, vp, vp, vp, dblp]),
+        "gb_genome_launch_count": (i64, [vp]),
+        "gb_partition_windows": (C.c_int, [i64, i64p, i64p, i64, C.POINTER(Params), C.c_int, i64p, dblp]),
+        "gb_synth_pack5_rows": (C.c_int, [vp, C.c_uint64, C.c_int, i64, i64p, i64, C.c_int, i32p, vp, i64, C.c_int]),
         "gb_run_qcat_strings": (C.c_int, [vp, i64, vp, vp, dblp, vp, C.c_int, vp, dblp, C.c_longlong, C.c_longlong,
                                           C.POINTER(Params), C.c_double, dblp, dblp, dblp, C.POINTER(C.c_int),
                                           C.POINTER(C.c_int)]),
@@ -557,6 +574,151 @@ class Pipe:
         if getattr(self, "h", None):
             if getattr(self.ctx, "h", None):     # a closed context has already taken its children with it
                 self.ctx.lib.gb_pipe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def partition_windows(n_t, n_u, n_samples: int, n_parts: int, params: Params | None = None):
+    """gb_partition_windows: the cost-balanced contiguous cuts gb_genome_plan uses (pure host code).
+    -> (cuts [n_parts + 1], cost per window)."""
+    lib = load_library()
+    nt, nu = _i64(n_t), _i64(n_u)
+    cuts = np.zeros(n_parts + 1, np.int64)
+    cost = np.zeros(len(nt))
+    rc = lib.gb_partition_windows(len(nt), _ptr(nt), _ptr(nu), int(n_samples), C.byref(params) if params else None,
+                                  int(n_parts), _ptr(cuts), _ptr(cost))
+    if rc != GB_OK:
+        raise GaussB200Error(rc, lib.gb_status_string(rc).decode())
+    return cuts, cost
+
+
+def unpack5_rows(rows5: np.ndarray, pop_sizes) -> np.ndarray:
+    """Ternary host rows -> [n, sum(pop_sizes)] int8 dosages (numpy; formatting only: the inverse of
+    pack5_rows_host, for callers that need the dosages of a packed or synthetic panel back)."""
+    ps = np.ascontiguousarray(pop_sizes, np.int64)
+    rows5 = np.ascontiguousarray(rows5, np.uint8)
+    n = rows5.shape[0]
+    out = np.empty((n, int(ps.sum())), np.int8)
+    pw = 3 ** np.arange(5)
+    boff = 0
+    col = 0
+    for m in ps:
+        nb = (int(m) + 4) // 5
+        blk = rows5[:, boff:boff + nb].astype(np.int64)
+        dig = ((blk[:, :, None] // pw[None, None, :]) % 3).reshape(n, nb * 5)[:, :int(m)]
+        out[:, col:col + int(m)] = dig.astype(np.int8)
+        col += int(m)
+        boff += (nb + 3) // 4 * 4
+    return out
+
+
+def synth_pack5_rows(ctx: "Context", seed: int, chrom: int, pop_sizes, n_rows: int, sites=None, first_site: int = 0):
+    """gb_synth_pack5_rows into a HOST array [n_rows, pack5_row_bytes] (the device generator of the bench panels)."""
+    ps = np.ascontiguousarray(pop_sizes, np.int32)
+    rb = pack5_row_bytes(ps)
+    out = np.zeros((n_rows, rb), np.uint8)
+    st = None if sites is None else _i64(sites)
+    ctx.check(ctx.lib.gb_synth_pack5_rows(ctx.h, int(seed), int(chrom), int(n_rows), _ptr(st), int(first_site), len(ps),
+                                          _ptr(ps), out.ctypes.data, rb, 0))
+    return out
+
+
+class Genome:
+    """gb_genome: genome-wide dist()/distmix() from one process on n_gpus GPUs (one host thread per GPU inside the
+    library).  chromosomes are added as dicts / keyword arguments, then plan() -> upload() or fill_synthetic() -> run()."""
+
+    def __init__(self, n_gpus: int, pop_sizes, pop_wgt=None, params: Params | None = None, devices=None):
+        self.lib = load_library()
+        self.pop_sizes = np.ascontiguousarray(pop_sizes, np.int32)
+        self.w = None if pop_wgt is None else _f64(pop_wgt)
+        dv = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        rc = self.lib.gb_genome_create(int(n_gpus), _ptr(dv), len(self.pop_sizes), _ptr(self.pop_sizes), _ptr(self.w),
+                                       C.byref(params) if params else None, C.byref(h))
+        if rc != GB_OK:
+            raise GaussB200Error(rc, self.lib.gb_last_error(None).decode() or self.lib.gb_status_string(rc).decode())
+        self.h = h
+        self.n_gpus = int(n_gpus)
+        self.chroms = []        # (n_u_total, n_windows) per chromosome
+        self._keep = []
+
+    def check(self, rc: int, allow=()):
+        if rc != GB_OK and rc not in allow:
+            raise GaussB200Error(rc, self.lib.gb_genome_last_error(self.h).decode() or
+                                 self.lib.gb_status_string(rc).decode())
+        return rc
+
+    def add_chromosome(self, n_rows: int, t_off, rows_t, u_off, rows_u, z_t, rows5_ptr: int | None = None,
+                       row_stride: int = 0, sites=None):
+        t_off, u_off, rt, ru, zt = _i64(t_off), _i64(u_off), _i64(rows_t), _i64(rows_u), _f64(z_t)
+        st = None if sites is None else _i64(sites)
+        self.check(self.lib.gb_genome_add_chromosome(
+            self.h, int(n_rows), C.c_void_p(rows5_ptr) if rows5_ptr else None, int(row_stride), len(t_off) - 1,
+            _ptr(t_off), _ptr(rt), _ptr(u_off), _ptr(ru), _ptr(zt), _ptr(st)))
+        self.chroms.append((int(u_off[-1]), len(t_off) - 1))
+        return len(self.chroms) - 1
+
+    def plan(self, n_parts: int | None = None, first_part: int = 0):
+        self.check(self.lib.gb_genome_plan(self.h, int(n_parts or self.n_gpus), int(first_part)))
+
+    def shard_info(self, gpu: int) -> dict:
+        a, b, c, d, e = (C.c_int64() for _ in range(5))
+        f = C.c_int()
+        g, hh = C.c_double(), C.c_double()
+        self.check(self.lib.gb_genome_shard_info(self.h, gpu, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e),
+                                                 C.byref(f), C.byref(g), C.byref(hh)))
+        return dict(first_window=a.value, n_windows=b.value, resident_rows=c.value, n_batches=d.value,
+                    n_imputed=e.value, e2m1_resident=bool(f.value), gram_ops=g.value, solve_flops=hh.value)
+
+    def upload(self, wait: bool = True):
+        self.check(self.lib.gb_genome_upload(self.h, int(bool(wait))))
+
+    def fill_synthetic(self, seed: int, wait: bool = True):
+        self.check(self.lib.gb_genome_fill_synthetic(self.h, int(seed), int(bool(wait))))
+
+    def _out_tables(self, z, info, status):
+        nc = len(self.chroms)
+        z = [np.zeros(n) for n, _ in self.chroms] if z is None else z
+        info = [np.zeros(n) for n, _ in self.chroms] if info is None else info
+        status = [np.zeros(nw, np.int32) for _, nw in self.chroms] if status is None else status
+        tabs = []
+        for arrs in (z, info, status):
+            t = (C.c_void_p * nc)()
+            for i, a in enumerate(arrs):
+                t[i] = a.ctypes.data if a is not None and a.size else None
+            tabs.append(t)
+        self._keep = [z, info, status, tabs]
+        return z, info, status, tabs
+
+    def submit(self, z=None, info=None, status=None):
+        z, info, status, tabs = self._out_tables(z, info, status)
+        self.check(self.lib.gb_genome_submit(self.h, tabs[0], tabs[1], tabs[2]))
+        return z, info, status
+
+    def wait(self):
+        ms = np.zeros(self.n_gpus)
+        up = np.zeros(self.n_gpus)
+        self.check(self.lib.gb_genome_wait(self.h, _ptr(ms), _ptr(up)))
+        return ms, up
+
+    def run(self, z=None, info=None, status=None):
+        """-> (z, info, status) lists per chromosome and the device-timed ms per GPU."""
+        z, info, status = self.submit(z, info, status)
+        ms, _ = self.wait()
+        return z, info, status, ms
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.gb_genome_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gb_genome_destroy(self.h)
             self.h = None
 
     def __del__(self):

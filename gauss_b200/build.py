@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgauss_b200.so")
-SOURCES = ["gb_api.cu", "gb_gram.cu", "gb_pack.cu", "gb_solve.cu"]
-HEADERS = ["gb_common.cuh", "gb_ptx.cuh", os.path.join("..", "..", "include", "gauss_b200.h")]
+SOURCES = ["gb_api.cu", "gb_gram.cu", "gb_pack.cu", "gb_solve.cu", "gb_genome.cu", "gb_synth.cu"]
+HEADERS = ["gb_common.cuh", "gb_ptx.cuh", "gb_batch.cuh", os.path.join("..", "..", "include", "gauss_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

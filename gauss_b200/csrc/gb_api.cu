@@ -7,6 +7,7 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <type_traits>
 
 #include "gb_common.cuh"
 #include <atomic>
@@ -15,98 +16,51 @@
 
 using namespace gb;
 
-struct gb_ctx : public Ctx {};
-struct gb_panel : public Panel {};
-struct gb_pipe;
+#include "gb_batch.cuh"
+
 extern "C" void gb_pipe_destroy(gb_pipe* pp);
 
 static thread_local std::string g_create_err;
 
-// ---------------------------------------------------------------------------------------------
-struct gb_batch {
-  Ctx* ctx = nullptr;
-  Panel* panel = nullptr;
-  int mode = GRAM_MIX;
-  bool ld_mode = false;      // computeLD: T x T only, full symmetric output, no solve
-  double ld_diag = 1.0;      // value forced on the diagonal in ld_mode (computeLD.cpp:107: 1.0; gene.cpp:578: 1 + lambda)
-  bool counts_mode = false;  // raw per-population counts
-  gb_params params{};
-  int64_t n_windows = 0;
-  std::vector<int64_t> t_off, u_off;
-  int64_t n_t_total = 0, n_u_total = 0;
-  std::vector<int> plan_status;       // per window: GB_OK or a TOO_FEW_* code (window skipped)
-  std::vector<int> active;            // window ids that run
-  std::vector<SolveWin> h_wins;       // aligned with `active`
-  std::vector<GramTile> h_tiles;      // [B11 tiles of all windows | B21 tiles of all windows]
-  int n_tiles_tt = 0;                 // length of the B11 part
-  int* d_tile_counter = nullptr;      // tile ids of the B21 Gram range, drawn by the main launch and the helper launch
-  double* d_y = nullptr;              // qcat only: y = L^-1 Z1 written by the solve kernel
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // factorisation runs beside the B21 part (gb_batch_run)
-  int64_t n_gather = 0;
-  int n_chol_wins = 0, max_nt = 0, max_nu = 0;
-  double work_gram_ops = 0, work_solve_flops = 0, work_panel_bytes = 0;
-  long long tt_elems = 0, ut_elems = 0, dinv_elems = 0, counts_elems = 0;
-  // device
-  int32_t *d_rows_t = nullptr, *d_rows_u = nullptr, *d_gather = nullptr;
-  int32_t *d_pool_t = nullptr, *d_pool_u = nullptr;
-  double *d_sd_t = nullptr, *d_sd_u = nullptr, *d_rq_t = nullptr;
-  int32_t *d_st_sx_t = nullptr, *d_st_sx_u = nullptr;     // [n_pops][n_*_total] per listed row: sum x
-  double *d_st_mean_t = nullptr, *d_st_mean_u = nullptr;  // [n_pops][n_*_total] sum x / m
-  int* d_skip = nullptr;
-  double gneg = 0.0;  // (sum(w)-1)_+ * max(w), +inf when the analytic PD bound does not apply
-  double *d_zt = nullptr, *d_zu = nullptr, *d_info = nullptr;
-  double *d_tt = nullptr, *d_ut = nullptr, *d_dinv = nullptr;
-  double *d_coef = nullptr, *d_wgt = nullptr;
-  int32_t* d_counts = nullptr;
-  int* d_status = nullptr;
-  SolveWin* d_wins = nullptr;
-  GramTile* d_tiles = nullptr;
-  int8_t* d_scratch = nullptr;
-  RowMaps tmaps_scratch;
-  int fkind = 0;                      // tensor-core kind of this batch (GramParams::fkind)
-  int cm = 1, cn = 1;                 // Gram cluster shape this batch was planned for
-  bool defer_flag_check = false;      // pipelined path: the panel is still being packed at plan time
-  std::vector<int> h_status;          // fetch staging: [2*n_windows + 2 status words | panel flags]
-  GramParams gp{};
-};
+namespace gb {
 
 namespace {
 
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Persistent buffers (descriptors, row lists, z_t): stream-ordered pool memory owned by the batch -- the per-window
+// entry points create and destroy a batch per call, and cudaMalloc/cudaFree would serialise the device every time.
 template <class T>
-int dev_alloc(Ctx* ctx, T** p, size_t n) {
+int dev_alloc(gb_batch* b, T** p, size_t n) {
+  Ctx* ctx = b->ctx;
   *p = nullptr;
   if (n == 0) n = 1;
-  // stream-ordered pool allocation: the per-window entry points create and destroy a batch per
-  // call, and cudaMalloc/cudaFree would serialise the device every time
   GB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(p), n * sizeof(T), ctx->stream));
+  b->owned.push_back(*p);
+  return GB_OK;
+}
+// Transient buffers (rewritten by every run): from the shared arena when the batch has one.
+template <class T>
+int dev_alloc_transient(gb_batch* b, T** p, size_t n) {
+  if (!b->arena.base) return dev_alloc(b, p, n);
+  if (n == 0) n = 1;
+  const size_t bytes = align256(n * sizeof(T));
+  if (b->arena_used + bytes > b->arena.cap) {
+    b->ctx->err = "batch arena too small";
+    return GB_ERR_OOM;
+  }
+  *p = reinterpret_cast<T*>(b->arena.base + b->arena_used);
+  b->arena_used += bytes;
   return GB_OK;
 }
 template <class T>
-int dev_upload(Ctx* ctx, T** p, const std::vector<T>& h) {
-  int rc = dev_alloc(ctx, p, h.size());
+int dev_upload(gb_batch* b, T** p, const std::vector<T>& h) {
+  Ctx* ctx = b->ctx;
+  int rc = dev_alloc(b, p, h.size());
   if (rc) return rc;
   if (!h.empty()) GB_CUDA(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
   return GB_OK;
-}
-
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-int check_device(Ctx* ctx) {
-  GB_CUDA(cudaSetDevice(ctx->device));
-  return GB_OK;
-}
-
-void free_batch_device(gb_batch* b) {
-  void* ptrs[] = {b->d_rows_t, b->d_rows_u, b->d_gather, b->d_pool_t, b->d_pool_u, b->d_sd_t, b->d_sd_u, b->d_rq_t, b->d_skip,
-                  b->d_st_sx_t, b->d_st_sx_u, b->d_st_mean_t, b->d_st_mean_u,
-                  b->d_zt, b->d_zu, b->d_info, b->d_tt, b->d_ut, b->d_dinv,
-                  b->d_coef, b->d_wgt, b->d_counts, b->d_status, b->d_wins, b->d_tiles,
-                  b->d_scratch, b->d_y, b->d_tile_counter};
-  for (void* p : ptrs)
-    if (p) cudaFreeAsync(p, b->ctx->stream);
-  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
-  if (b->ev_join) cudaEventDestroy(b->ev_join);
-  b->ev_fork = b->ev_join = nullptr;
 }
 
 int unrepresentable(Ctx* ctx) {
@@ -115,10 +69,21 @@ int unrepresentable(Ctx* ctx) {
   return GB_ERR_UNSUPPORTED;
 }
 
-// Shared planner.  rows_u may be empty (ld_mode).  In counts_mode rows_u plays the A side and
+}  // namespace
+
+void batch_free_device(gb_batch* b) {
+  for (void* p : b->owned)
+    if (p) cudaFreeAsync(p, b->ctx->stream);
+  b->owned.clear();
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_join) cudaEventDestroy(b->ev_join);
+  b->ev_fork = b->ev_join = nullptr;
+}
+
+// Shared planner, phase 1 (host only).  rows_u may be empty (ld_mode).  In counts_mode rows_u plays the A side and
 // rows_t the B side of one full rectangle.
-int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const int64_t* u_off,
-               const int64_t* rows_u, const double* z_t, const double* pop_wgt) {
+int batch_plan_host(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const int64_t* u_off,
+                    const int64_t* rows_u, const double* z_t, const double* pop_wgt) {
   Ctx* ctx = b->ctx;
   Panel* pn = b->panel;
   const int64_t nw = b->n_windows;
@@ -131,7 +96,10 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     ctx->err = "window offsets must start at 0";
     return GB_ERR_BAD_ARG;
   }
-  std::vector<int32_t> h_rows_t((size_t)b->n_t_total), h_rows_u((size_t)b->n_u_total);
+  std::vector<int32_t>& h_rows_t = b->h_rows_t;
+  std::vector<int32_t>& h_rows_u = b->h_rows_u;
+  h_rows_t.resize((size_t)b->n_t_total);
+  h_rows_u.resize((size_t)b->n_u_total);
   for (int64_t i = 0; i < b->n_t_total; i++) {
     if (rows_t[i] < 0 || rows_t[i] >= pn->n_rows) {
       ctx->err = "measured row index out of range";
@@ -146,6 +114,7 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     }
     h_rows_u[(size_t)i] = (int32_t)rows_u[i];
   }
+  if (z_t && !b->ld_mode && !b->counts_mode) b->h_zt.assign(z_t, z_t + b->n_t_total);
 
   // ---- segments / coefficients
   GramParams& gp = b->gp;
@@ -154,20 +123,29 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   b->fkind = pn->format == GB_PANEL_E2M1 ? (ctx->e2m1_mxf4 ? 7 : 6) : 0;
   gp.fkind = b->fkind;
   const int atom = b->fkind == 7 ? 2 * K_ATOM : K_ATOM;  // K columns one MMA instruction consumes
-  if (b->fkind != 0) {
-    // E2M1 panels count in fp32: a segment's largest possible sum (dosage 6 on both sides, 36 per individual) must stay
-    // below 2^21 for the one-instruction count -> fp64 re-encoding of the mixture fold and below 2^22 for the magic-add
-    // count -> int32 of the pooled / counts paths (both far inside fp32's exact-integer range)
-    const long long seg_max = b->mode == GRAM_POOLED ? (long long)pn->n_samples
-                                                     : (long long)*std::max_element(pn->pop_sizes.begin(), pn->pop_sizes.end());
-    const long long limit = (b->mode == GRAM_MIX && !b->counts_mode) ? (1ll << 21) : (1ll << 22);
-    if (36 * seg_max >= limit) {
-      ctx->err = "a population block of " + std::to_string(seg_max) + " individuals is too large for the exact fp32 counts of an "
-                 "E2M1 panel; use GB_PANEL_INT8";
+  {
+    const long long pop_max = (long long)*std::max_element(pn->pop_sizes.begin(), pn->pop_sizes.end());
+    const long long seg_max = b->mode == GRAM_POOLED ? (long long)pn->n_samples : pop_max;
+    if (b->fkind != 0) {
+      // E2M1 panels count in fp32: a segment's largest possible sum (dosage 6 on both sides, 36 per individual) must stay
+      // below 2^21 for the one-instruction count -> fp64 re-encoding of the mixture fold and below 2^22 for the magic-add
+      // count -> int32 of the pooled / counts paths (both far inside fp32's exact-integer range)
+      const long long limit = (b->mode == GRAM_MIX && !b->counts_mode) ? (1ll << 21) : (1ll << 22);
+      if (36 * seg_max >= limit) {
+        ctx->err = "a population block of " + std::to_string(seg_max) + " individuals is too large for the exact fp32 counts of an "
+                   "E2M1 panel (limit " + std::to_string((limit - 1) / 36) + "); an int8 panel (GB_PANEL_INT8) takes blocks of up to 133,143 individuals";
+        return GB_ERR_UNSUPPORTED;
+      }
+    } else if (127ll * 127ll * seg_max > 2147483647ll) {
+      // int8 panels count in int32: |sum x_i x_j| <= 127^2 * m must fit (the fold itself runs in 64-bit / fp64)
+      ctx->err = "a population block of " + std::to_string(seg_max) + " individuals overflows the int32 counts of an int8 panel "
+                 "(limit 133,143)";
       return GB_ERR_UNSUPPORTED;
     }
   }
-  std::vector<double> h_coef((size_t)pn->n_pops, 0.0), h_wgt((size_t)pn->n_pops, 0.0);
+  b->h_coef.assign((size_t)pn->n_pops, 0.0);
+  b->h_wgt.assign((size_t)pn->n_pops, 0.0);
+  std::vector<double>&h_coef = b->h_coef, &h_wgt = b->h_wgt;
   if (b->mode == GRAM_POOLED) {
     gp.n_seg = 1;
     const int last = pn->n_pops - 1;
@@ -201,13 +179,19 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     b->gneg = applies ? std::max(0.0, sw - 1.0) * wmax : std::numeric_limits<double>::infinity();
   }
   gp.mode = b->counts_mode ? GRAM_COUNTS : b->mode;
+  {
+    // int8 mixture fold: d = m*sumxy - sumx*sumy is formed in int32 when it provably fits and in exact fp64 otherwise
+    // (any byte the reference's (c - '0') can see: |d| <= 127^2 m^2; refined in phase 2 when the panel holds only 0/1/2)
+    const long long m = (long long)*std::max_element(pn->pop_sizes.begin(), pn->pop_sizes.end());
+    gp.wide_fold = (b->fkind == 0 && 16129ll * m * m > 2147483647ll) ? 1 : 0;
+  }
   gp.mirror = b->ld_mode ? 1 : 0;
   gp.raw_out = (gp.mode == GRAM_MIX && b->fkind != 0) ? 1 : 0;
   gp.diag = b->ld_mode ? b->ld_diag : 1.0 + b->params.lambda;   // computeLD.cpp:107 vs dist.cpp:172
 
   // ---- windows
   b->plan_status.assign((size_t)nw, GB_OK);
-  std::vector<int32_t> h_gather;
+  std::vector<int32_t>& h_gather = b->h_gather;
   std::vector<GramTile> h_tiles_tt, h_tiles_ut;
   const double N = (double)pn->n_samples;
   for (int64_t w = 0; w < nw; w++) {
@@ -329,18 +313,75 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
     b->h_wins.swap(hw);
     b->active.swap(act);
   }
+  for (const SolveWin& sw : b->h_wins) {
+    b->max_nt = std::max(b->max_nt, sw.n_t);
+    b->max_nu = std::max(b->max_nu, sw.n_u);
+  }
+  return GB_OK;
+}
 
-  // ---- device buffers
+// The transient buffers of phase 2, in allocation order: (bytes, which).  One table serves both the arena sizing and
+// the allocation itself so the two cannot drift apart.
+namespace {
+struct TransientSizes {
+  size_t sd_u, pool_u, st_sx_t, st_mean_t, st_sx_u, st_mean_u, counts, tt, ut, dinv, zu, info, scratch, clip;
+};
+TransientSizes transient_sizes(const gb_batch* b) {
+  const Panel* pn = b->panel;
+  TransientSizes s{};
+  const size_t P = (size_t)pn->n_pops;
+  s.sd_u = sizeof(double) * (size_t)b->n_u_total;
+  s.pool_u = sizeof(int32_t) * (size_t)b->n_u_total;
+  if (b->mode == GRAM_MIX && !b->counts_mode) {
+    s.st_sx_t = sizeof(int32_t) * P * (size_t)b->n_t_total;
+    s.st_mean_t = sizeof(double) * P * (size_t)b->n_t_total;
+    s.st_sx_u = sizeof(int32_t) * P * (size_t)b->n_u_total;
+    s.st_mean_u = sizeof(double) * P * (size_t)b->n_u_total;
+  }
+  if (b->counts_mode) {
+    s.counts = sizeof(int32_t) * (size_t)b->counts_elems * P;
+  } else {
+    const bool cert = b->params.check_pd && !b->ld_mode;
+    s.tt = sizeof(double) * (size_t)b->tt_elems * (cert ? 2 : 1);
+    if (!b->ld_mode) {
+      s.ut = sizeof(double) * (size_t)b->ut_elems;
+      s.dinv = sizeof(double) * (size_t)b->dinv_elems * (cert ? 2 : 1);
+      s.zu = sizeof(double) * (size_t)b->n_u_total;
+      s.info = sizeof(double) * (size_t)b->n_u_total;
+    }
+  }
+  s.scratch = (size_t)b->n_gather * (size_t)pn->k_stride;
+  return s;
+}
+}  // namespace
+
+size_t batch_arena_bytes(const gb_batch* b) {
+  const TransientSizes s = transient_sizes(b);
+  const size_t all[] = {s.sd_u, s.pool_u, s.st_sx_t, s.st_mean_t, s.st_sx_u, s.st_mean_u, s.counts,
+                        s.tt, s.ut, s.dinv, s.zu, s.info, s.scratch};
+  size_t total = 0;
+  for (size_t v : all) total += align256(v ? v : 1);
+  return total + 4096;
+}
+
+int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
+  Ctx* ctx = b->ctx;
+  Panel* pn = b->panel;
+  const int64_t nw = b->n_windows;
+  b->arena = arena;
+  b->arena_used = 0;
+  GramParams& gp = b->gp;
   int rc;
-  if ((rc = dev_upload(ctx, &b->d_rows_t, h_rows_t))) return rc;
-  if ((rc = dev_upload(ctx, &b->d_rows_u, h_rows_u))) return rc;
-  if ((rc = dev_upload(ctx, &b->d_gather, h_gather))) return rc;
-  if ((rc = dev_upload(ctx, &b->d_coef, h_coef))) return rc;
-  if ((rc = dev_upload(ctx, &b->d_wgt, h_wgt))) return rc;
+  if ((rc = dev_upload(b, &b->d_rows_t, b->h_rows_t))) return rc;
+  if ((rc = dev_upload(b, &b->d_rows_u, b->h_rows_u))) return rc;
+  if ((rc = dev_upload(b, &b->d_gather, b->h_gather))) return rc;
+  if ((rc = dev_upload(b, &b->d_coef, b->h_coef))) return rc;
+  if ((rc = dev_upload(b, &b->d_wgt, b->h_wgt))) return rc;
   {
     // the PD certificate factors B11 - min_abs_eig*I in the same launches: its windows are appended
     // after the real ones and live in the second half of the TT buffer
-    std::vector<SolveWin> all = b->h_wins;
+    std::vector<SolveWin>& all = b->h_wins_all;   // a member: the upload may still be in flight when this returns
+    all = b->h_wins;
     if (b->params.check_pd && !b->ld_mode && !b->counts_mode)
       for (SolveWin sw : b->h_wins) {
         sw.off_tt += b->tt_elems;
@@ -349,46 +390,44 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
         all.push_back(sw);
       }
     b->n_chol_wins = (int)all.size();
-    if ((rc = dev_upload(ctx, &b->d_wins, all))) return rc;
+    if ((rc = dev_upload(b, &b->d_wins, all))) return rc;
   }
-  for (const SolveWin& sw : b->h_wins) {
-    b->max_nt = std::max(b->max_nt, sw.n_t);
-    b->max_nu = std::max(b->max_nu, sw.n_u);
-  }
-  if ((rc = dev_upload(ctx, &b->d_tiles, b->h_tiles))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_sd_t, (size_t)b->n_t_total))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_rq_t, (size_t)b->n_t_total))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_skip, 2 * (size_t)nw + 2))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_sd_u, (size_t)b->n_u_total))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_pool_t, (size_t)b->n_t_total))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_pool_u, (size_t)b->n_u_total))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_status, 2 * (size_t)nw + 2))) return rc;
-  if ((rc = dev_alloc(ctx, &b->d_tile_counter, 1))) return rc;
-  if (b->mode == GRAM_MIX && !b->counts_mode) {
-    const size_t P = (size_t)pn->n_pops;
-    if ((rc = dev_alloc(ctx, &b->d_st_sx_t, P * (size_t)b->n_t_total))) return rc;
-    if ((rc = dev_alloc(ctx, &b->d_st_mean_t, P * (size_t)b->n_t_total))) return rc;
-    if ((rc = dev_alloc(ctx, &b->d_st_sx_u, P * (size_t)b->n_u_total))) return rc;
-    if ((rc = dev_alloc(ctx, &b->d_st_mean_u, P * (size_t)b->n_u_total))) return rc;
+  if ((rc = dev_upload(b, &b->d_tiles, b->h_tiles))) return rc;
+  if ((rc = dev_alloc(b, &b->d_sd_t, (size_t)b->n_t_total))) return rc;
+  if ((rc = dev_alloc(b, &b->d_rq_t, (size_t)b->n_t_total))) return rc;
+  if ((rc = dev_alloc(b, &b->d_skip, 2 * (size_t)nw + 2))) return rc;
+  if ((rc = dev_alloc(b, &b->d_pool_t, (size_t)b->n_t_total))) return rc;
+  if ((rc = dev_alloc(b, &b->d_status, 2 * (size_t)nw + 2))) return rc;
+  if ((rc = dev_alloc(b, &b->d_tile_counter, 1))) return rc;
+  const TransientSizes s = transient_sizes(b);
+  uint8_t* raw = nullptr;
+  auto take = [&](auto** p, size_t bytes) -> int {
+    int r = dev_alloc_transient(b, &raw, bytes);
+    *p = reinterpret_cast<std::remove_reference_t<decltype(**p)>*>(raw);
+    return r;
+  };
+  if ((rc = take(&b->d_sd_u, s.sd_u))) return rc;
+  if ((rc = take(&b->d_pool_u, s.pool_u))) return rc;
+  if (s.st_sx_t || s.st_sx_u) {
+    if ((rc = take(&b->d_st_sx_t, s.st_sx_t))) return rc;
+    if ((rc = take(&b->d_st_mean_t, s.st_mean_t))) return rc;
+    if ((rc = take(&b->d_st_sx_u, s.st_sx_u))) return rc;
+    if ((rc = take(&b->d_st_mean_u, s.st_mean_u))) return rc;
   }
   if (b->counts_mode) {
-    if ((rc = dev_alloc(ctx, &b->d_counts, (size_t)b->counts_elems * pn->n_pops))) return rc;
+    if ((rc = take(&b->d_counts, s.counts))) return rc;
   } else {
-    const bool cert = b->params.check_pd && !b->ld_mode;
-    if ((rc = dev_alloc(ctx, &b->d_tt, (size_t)b->tt_elems * (cert ? 2 : 1)))) return rc;
+    if ((rc = take(&b->d_tt, s.tt))) return rc;
     if (!b->ld_mode) {
-      if ((rc = dev_alloc(ctx, &b->d_ut, (size_t)b->ut_elems))) return rc;
-      if ((rc = dev_alloc(ctx, &b->d_dinv, (size_t)b->dinv_elems * (cert ? 2 : 1)))) return rc;
-      if ((rc = dev_alloc(ctx, &b->d_zt, (size_t)b->n_t_total))) return rc;
-      if ((rc = dev_alloc(ctx, &b->d_zu, (size_t)b->n_u_total))) return rc;
-      if ((rc = dev_alloc(ctx, &b->d_info, (size_t)b->n_u_total))) return rc;
-      if (b->n_t_total)
-        GB_CUDA(cudaMemcpyAsync(b->d_zt, z_t, sizeof(double) * (size_t)b->n_t_total, cudaMemcpyHostToDevice,
-                                ctx->stream));
+      if ((rc = take(&b->d_ut, s.ut))) return rc;
+      if ((rc = take(&b->d_dinv, s.dinv))) return rc;
+      if ((rc = dev_upload(b, &b->d_zt, b->h_zt))) return rc;
+      if ((rc = take(&b->d_zu, s.zu))) return rc;
+      if ((rc = take(&b->d_info, s.info))) return rc;
     }
   }
   if (b->n_gather > 0) {
-    if ((rc = dev_alloc(ctx, &b->d_scratch, (size_t)b->n_gather * pn->k_stride))) return rc;
+    if ((rc = take(&b->d_scratch, s.scratch))) return rc;
     if ((rc = make_row_tensor_maps(ctx, &b->tmaps_scratch, b->d_scratch, b->n_gather, pn->k_elems, pn->k_stride,
                                    b->fkind == 7 ? MAP_E2M1_PACKED : b->fkind == 6 ? MAP_E2M1_EXPAND : MAP_INT8)))
       return rc;
@@ -412,13 +451,108 @@ int plan_batch(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, const i
   gp.out_ut = b->d_ut;
   gp.out_counts = b->d_counts;
   gp.counts_seg_stride = b->counts_elems;
-  // the planning uploads read host vectors that die with this frame; the same sync makes the pack
-  // kernels' representability flag readable
+  if (!sync) return GB_OK;
+  // the same sync makes the pack kernels' representability flag readable
   int h_flags = 0;
   if (!b->defer_flag_check)
     GB_CUDA(cudaMemcpyAsync(&h_flags, pn->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (h_flags & 1) return unrepresentable(ctx);
+  if (b->fkind == 0 && !(h_flags & 2) && !b->defer_flag_check) {
+    // every packed byte is a dosage in {0, 1, 2}: |m*sumxy - sumx*sumy| <= 4 m^2
+    const long long m = (long long)*std::max_element(pn->pop_sizes.begin(), pn->pop_sizes.end());
+    gp.wide_fold = 4 * m * m > 2147483647ll ? 1 : 0;
+  }
+  return GB_OK;
+}
+
+// pack5 host rows (five base-3 digits per byte): population p starts at byte boff[p], blocks padded to 4 bytes, the row
+// to 16.  Returns the row size in bytes (-1: bad sizes).
+int pack5_layout(int n_pops, const int* pop_sizes, std::vector<int>* boff) {
+  long long b = 0;
+  if (boff) boff->clear();
+  for (int i = 0; i < n_pops; i++) {
+    if (pop_sizes[i] < 1) return -1;
+    if (boff) boff->push_back((int)b);
+    b += ((pop_sizes[i] + 4) / 5 + 3) / 4 * 4;
+    if (b > (1ll << 30)) return -1;
+  }
+  return (int)((b + 15) / 16 * 16);
+}
+
+
+// Results leave in two halves so the pipelined path can enqueue the copies at submit time and
+// interpret them after its own event wait.
+int batch_fetch_enqueue(gb_batch* b, double* z_u, double* info_u, int* status_staging) {
+  Ctx* ctx = b->ctx;
+  if (b->n_u_total) {
+    if (z_u) GB_CUDA(cudaMemcpyAsync(z_u, b->d_zu, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (info_u) GB_CUDA(cudaMemcpyAsync(info_u, b->d_info, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  // d_status is indexed by position in the factorisation list: [real windows | certificate copies]
+  const size_t n_st = 2 * (size_t)b->n_windows + 2;
+  GB_CUDA(cudaMemcpyAsync(status_staging, b->d_status, sizeof(int) * n_st, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaMemcpyAsync(status_staging + n_st, b->panel->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  return GB_OK;
+}
+
+int batch_fetch_finish(gb_batch* b, const int* st, double* z_u, double* info_u, int* window_status_out) {
+  const size_t nreal = b->h_wins.size();
+  const size_t n_st = 2 * (size_t)b->n_windows + 2;
+  if (st[n_st] & 1) return unrepresentable(b->ctx);
+  std::vector<int> st_w((size_t)b->n_windows, 0), st_pd_w((size_t)b->n_windows, 0);
+  for (size_t a = 0; a < b->active.size(); a++) {
+    st_w[(size_t)b->active[a]] = st[a];
+    if (b->params.check_pd) st_pd_w[(size_t)b->active[a]] = st[nreal + a];
+  }
+  int worst = GB_OK;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  for (int64_t w = 0; w < b->n_windows; w++) {
+    int s = b->plan_status[(size_t)w];
+    bool no_result = s != GB_OK;                      // skipped window: no result exists
+    if (s == GB_OK && st_w[(size_t)w]) {              // the factorisation of B11 itself broke down: what the solve wrote is garbage
+      s = GB_ERR_BREAKDOWN;
+      no_result = true;
+    } else if (s == GB_OK && st_pd_w[(size_t)w]) {
+      s = GB_ERR_NOT_PD;                              // results exist (computed without the clip), not certified
+    }
+    if (window_status_out) window_status_out[w] = s;
+    if (s != GB_OK && worst == GB_OK) worst = s;
+    if (no_result)
+      for (int64_t i = b->u_off[w]; i < b->u_off[w + 1]; i++) {
+        if (z_u) z_u[i] = nan;
+        if (info_u) info_u[i] = nan;
+      }
+  }
+  return window_status_out ? GB_OK : worst;
+}
+
+
+gb_batch* batch_new(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const double* pop_wgt, const gb_params* params,
+                    bool ld_mode, bool counts_mode, bool defer_flag_check, double ld_diag) {
+  gb_batch* b = new (std::nothrow) gb_batch();
+  if (!b) return nullptr;
+  b->ctx = ctx;
+  b->panel = panel;
+  b->mode = (pop_wgt || counts_mode) ? GRAM_MIX : GRAM_POOLED;
+  b->ld_mode = ld_mode;
+  b->ld_diag = ld_diag;
+  b->counts_mode = counts_mode;
+  if (params) b->params = *params;
+  else gb_params_default(&b->params);
+  b->n_windows = n_windows;
+  b->cm = ctx->gram_cm;
+  b->cn = ctx->gram_cn;
+  b->defer_flag_check = defer_flag_check;
+  return b;
+}
+
+}  // namespace gb
+
+namespace {
+
+int check_device(Ctx* ctx) {
+  GB_CUDA(cudaSetDevice(ctx->device));
   return GB_OK;
 }
 
@@ -488,33 +622,16 @@ int create_batch_internal(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const
   }
   int rc = check_device(ctx);
   if (rc) return rc;
-  gb_batch* b = new (std::nothrow) gb_batch();
+  gb_batch* b = gb::batch_new(ctx, panel, n_windows, pop_wgt, params, ld_mode, counts_mode, defer_flag_check, ld_diag);
   if (!b) return GB_ERR_OOM;
-  b->ctx = ctx;
-  b->panel = panel;
-  b->mode = (pop_wgt || counts_mode) ? GRAM_MIX : GRAM_POOLED;
-  b->ld_mode = ld_mode;
-  b->ld_diag = ld_diag;
-  b->counts_mode = counts_mode;
-  if (params) b->params = *params;
-  else gb_params_default(&b->params);
-  b->n_windows = n_windows;
-  b->cm = ctx->gram_cm;
-  b->cn = ctx->gram_cn;
-  b->defer_flag_check = defer_flag_check;
-  rc = plan_batch(b, t_off, rows_t, u_off, rows_u, z_t, pop_wgt);
+  rc = gb::batch_plan_host(b, t_off, rows_t, u_off, rows_u, z_t, pop_wgt);
+  if (!rc) rc = gb::batch_plan_device(b, gb::Arena{}, /*sync=*/true);
   if (rc) {
-    free_batch_device(b);
+    batch_free_device(b);
     delete b;
     return rc;
   }
   *out = b;
-  return GB_OK;
-}
-
-int window_status(const gb_batch* b, const std::vector<int>& st, const std::vector<int>& st_pd, int64_t w) {
-  if (b->plan_status[(size_t)w] != GB_OK) return b->plan_status[(size_t)w];
-  if (st[(size_t)w] || st_pd[(size_t)w]) return GB_ERR_NOT_PD;
   return GB_OK;
 }
 
@@ -546,6 +663,7 @@ const char* gb_status_string(int s) {
     case GB_ERR_TOO_FEW_UNMEASURED: return "Not enough number of SNPs loaded";
     case GB_ERR_NOT_PD: return "B11 not certified positive definite above min_abs_eig";
     case GB_ERR_UNSUPPORTED: return "unsupported configuration";
+    case GB_ERR_BREAKDOWN: return "Cholesky of B11 broke down (not positive definite): no result";
     default: return "unknown status";
   }
 }
@@ -644,20 +762,6 @@ int gb_ctx_synchronize(gb_ctx* ctx) {
 const char* gb_last_error(const gb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 int64_t gb_ctx_launch_count(const gb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-// pack5 host rows (five base-3 digits per byte): population p starts at byte boff[p], blocks padded to 4 bytes, the row
-// to 16.  Returns the row size in bytes (-1: bad sizes).
-static int pack5_layout(int n_pops, const int* pop_sizes, std::vector<int>* boff) {
-  long long b = 0;
-  if (boff) boff->clear();
-  for (int i = 0; i < n_pops; i++) {
-    if (pop_sizes[i] < 1) return -1;
-    if (boff) boff->push_back((int)b);
-    b += ((pop_sizes[i] + 4) / 5 + 3) / 4 * 4;
-    if (b > (1ll << 30)) return -1;
-  }
-  return (int)((b + 15) / 16 * 16);
-}
-
 // ---- panel ----------------------------------------------------------------------------------
 int gb_panel_create(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t capacity_rows, gb_panel** out) {
   return gb_panel_create_fmt(ctx, n_pops, pop_sizes, capacity_rows, ctx ? ctx->panel_format : GB_PANEL_E2M1, out);
@@ -721,7 +825,7 @@ int gb_panel_create_fmt(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t c
   if ((rc = pmalloc((void**)&p->d_koff, sizeof(int) * (size_t)n_pops))) return fail(rc);
   if ((rc = pmalloc((void**)&p->d_boff5, sizeof(int) * (size_t)n_pops))) return fail(rc);
   std::vector<int> boff5;
-  p->pack5_row_bytes = pack5_layout(n_pops, pop_sizes, &boff5);
+  p->pack5_row_bytes = gb::pack5_layout(n_pops, pop_sizes, &boff5);
   if ((rc = pmalloc((void**)&p->d_flags, sizeof(int)))) return fail(rc);
   cudaMemsetAsync(p->d_flags, 0, sizeof(int), ctx->stream);
   cudaMemcpyAsync(p->d_pop_sizes, p->pop_sizes.data(), sizeof(int) * (size_t)n_pops, cudaMemcpyHostToDevice, ctx->stream);
@@ -820,7 +924,17 @@ int gb_panel_append_strings(gb_panel* p, int64_t n_rows, const char* const* pop_
         ctx->err = "null genotype string";
         return GB_ERR_BAD_ARG;
       }
-      std::memcpy(dst, s, (size_t)p->pop_sizes[(size_t)k]);
+      // the string must hold exactly the population's individuals: a shorter one would be over-read here, and the
+      // reference's CalCor walks x[i].length() characters (util.cpp:55), so a longer one cannot be reproduced by
+      // truncating it
+      const size_t m = (size_t)p->pop_sizes[(size_t)k];
+      if (strnlen(s, m + 1) != m) {
+        cudaFreeHost(stage);
+        ctx->err = "genotype string of SNP " + std::to_string(r) + ", population " + std::to_string(k) + " does not hold " +
+                   std::to_string(m) + " characters";
+        return GB_ERR_BAD_ARG;
+      }
+      std::memcpy(dst, s, m);
       dst += p->pop_sizes[(size_t)k];
     }
   }
@@ -846,7 +960,7 @@ void gb_batch_destroy(gb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
-  free_batch_device(b);
+  batch_free_device(b);
   delete b;
 }
 
@@ -919,54 +1033,15 @@ int gb_batch_run_stage(gb_batch* b, int stage) {
   return run_stage(b, stage);
 }
 
-// Results leave in two halves so the pipelined path can enqueue the copies at submit time and
-// interpret them after its own event wait.
-static int fetch_enqueue(gb_batch* b, double* z_u, double* info_u, int* status_staging) {
-  Ctx* ctx = b->ctx;
-  if (b->n_u_total) {
-    if (z_u) GB_CUDA(cudaMemcpyAsync(z_u, b->d_zu, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
-    if (info_u) GB_CUDA(cudaMemcpyAsync(info_u, b->d_info, sizeof(double) * (size_t)b->n_u_total, cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  // d_status is indexed by position in the factorisation list: [real windows | certificate copies]
-  const size_t n_st = 2 * (size_t)b->n_windows + 2;
-  GB_CUDA(cudaMemcpyAsync(status_staging, b->d_status, sizeof(int) * n_st, cudaMemcpyDeviceToHost, ctx->stream));
-  GB_CUDA(cudaMemcpyAsync(status_staging + n_st, b->panel->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  return GB_OK;
-}
-
-static int fetch_finish(gb_batch* b, const int* st, double* z_u, double* info_u, int* window_status_out) {
-  const size_t nreal = b->h_wins.size();
-  const size_t n_st = 2 * (size_t)b->n_windows + 2;
-  if (st[n_st] & 1) return unrepresentable(b->ctx);
-  std::vector<int> st_w((size_t)b->n_windows, 0), st_pd_w((size_t)b->n_windows, 0);
-  for (size_t a = 0; a < b->active.size(); a++) {
-    st_w[(size_t)b->active[a]] = st[a];
-    if (b->params.check_pd) st_pd_w[(size_t)b->active[a]] = st[nreal + a];
-  }
-  int worst = GB_OK;
-  const double nan = std::numeric_limits<double>::quiet_NaN();
-  for (int64_t w = 0; w < b->n_windows; w++) {
-    const int s = window_status(b, st_w, st_pd_w, w);
-    if (window_status_out) window_status_out[w] = s;
-    if (s != GB_OK && worst == GB_OK) worst = s;
-    if (b->plan_status[(size_t)w] != GB_OK)  // skipped window: no result exists
-      for (int64_t i = b->u_off[w]; i < b->u_off[w + 1]; i++) {
-        if (z_u) z_u[i] = nan;
-        if (info_u) info_u[i] = nan;
-      }
-  }
-  return window_status_out ? GB_OK : worst;
-}
-
 int gb_batch_fetch(gb_batch* b, double* z_u, double* info_u, int* window_status_out) {
   if (!b || b->ld_mode || b->counts_mode) return GB_ERR_BAD_ARG;
   Ctx* ctx = b->ctx;
   int rc = check_device(ctx);
   if (rc) return rc;
   b->h_status.assign(2 * (size_t)b->n_windows + 3, 0);
-  if ((rc = fetch_enqueue(b, z_u, info_u, b->h_status.data()))) return rc;
+  if ((rc = gb::batch_fetch_enqueue(b, z_u, info_u, b->h_status.data()))) return rc;
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return fetch_finish(b, b->h_status.data(), z_u, info_u, window_status_out);
+  return gb::batch_fetch_finish(b, b->h_status.data(), z_u, info_u, window_status_out);
 }
 
 int gb_batch_work(const gb_batch* b, double* gram_ops, double* solve_flops, double* panel_bytes) {
@@ -1286,14 +1361,14 @@ int gb_pack2_rows_host(int n_pops, const int* pop_sizes, int64_t n_rows, const v
 // ---- ternary host rows ("pack5") ---------------------------------------------------------------------
 int64_t gb_pack5_row_bytes(int n_pops, const int* pop_sizes) {
   if (n_pops < 1 || !pop_sizes) return -1;
-  return pack5_layout(n_pops, pop_sizes, nullptr);
+  return gb::pack5_layout(n_pops, pop_sizes, nullptr);
 }
 
 int gb_pack5_rows_host(int n_pops, const int* pop_sizes, int64_t n_rows, const void* rows, int64_t row_stride,
                        int is_ascii, void* out, int64_t out_stride) {
   if (n_pops < 1 || !pop_sizes || n_rows < 0 || (n_rows && (!rows || !out))) return GB_ERR_BAD_ARG;
   std::vector<int> boff;
-  const int rb = pack5_layout(n_pops, pop_sizes, &boff);
+  const int rb = gb::pack5_layout(n_pops, pop_sizes, &boff);
   int64_t n_samples = 0;
   for (int i = 0; i < n_pops; i++) n_samples += pop_sizes[i];
   if (rb < 0 || out_stride < rb || row_stride < n_samples) return GB_ERR_BAD_ARG;
@@ -1446,7 +1521,7 @@ static int chrom_run_packed(gb_ctx* ctx, gb_panel* panel, int host_format, int64
     cudaStreamSynchronize(ctx->stream);
     for (auto b : batches)
       if (b) {
-        free_batch_device(b);
+        batch_free_device(b);
         delete b;
       }
     for (auto e : landed)
@@ -1540,7 +1615,7 @@ static int chrom_run_packed(gb_ctx* ctx, gb_panel* panel, int host_format, int64
     rc = gb_batch_run(b);
     const int64_t w0 = g_lo[(size_t)g];
     st_offs[(size_t)g] = st_off;
-    if (!rc) rc = fetch_enqueue(b, z_u + u_off[w0], info_u + u_off[w0], h_status + st_off);
+    if (!rc) rc = gb::batch_fetch_enqueue(b, z_u + u_off[w0], info_u + u_off[w0], h_status + st_off);
     ctx->stream = main_stream;
     ctx->side_stream = main_side;
     if (rc) return fail(rc);
@@ -1573,7 +1648,7 @@ static int chrom_run_packed(gb_ctx* ctx, gb_panel* panel, int host_format, int64
   for (int g = 0; g < n_groups; g++) {
     const int64_t w0 = g_lo[(size_t)g];
     gb_batch* b = batches[(size_t)g];
-    rc = fetch_finish(b, h_status + st_offs[(size_t)g], z_u + u_off[w0], info_u + u_off[w0],
+    rc = gb::batch_fetch_finish(b, h_status + st_offs[(size_t)g], z_u + u_off[w0], info_u + u_off[w0],
                       window_status ? window_status + w0 : nullptr);
     if (rc != GB_OK && worst == GB_OK) worst = rc;
   }
@@ -1622,7 +1697,7 @@ int gb_window_qcat(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* row
   if (rc) return rc;
   auto done = [&](int code) {
     cudaStreamSynchronize(ctx->stream);
-    free_batch_device(b);
+    batch_free_device(b);
     delete b;
     return code;
   };
@@ -1715,8 +1790,8 @@ static int pipe_retire(gb_pipe* pp, gb_pipe::Slot& sl, int* status_out) {
     GB_CUDA(cudaEventSynchronize(sl.done));
     std::memcpy(sl.z_u, sl.h_z, sizeof(double) * (size_t)sl.n_u);
     std::memcpy(sl.info_u, sl.h_info, sizeof(double) * (size_t)sl.n_u);
-    rc = fetch_finish(sl.batch, sl.h_status, sl.z_u, sl.info_u, nullptr);
-    free_batch_device(sl.batch);
+    rc = gb::batch_fetch_finish(sl.batch, sl.h_status, sl.z_u, sl.info_u, nullptr);
+    batch_free_device(sl.batch);
     delete sl.batch;
     sl.batch = nullptr;
   }
@@ -1769,7 +1844,7 @@ void gb_pipe_destroy(gb_pipe* pp) {
   for (auto& sl : pp->slots) {
     if (sl.batch) {
       cudaEventSynchronize(sl.done);
-      free_batch_device(sl.batch);
+      batch_free_device(sl.batch);
       delete sl.batch;
     }
     if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
@@ -1823,24 +1898,45 @@ int gb_pipe_submit(gb_pipe* pp, int64_t n_t, const void* host_rows_t, int64_t n_
                              z_t ? z_t : &dummy, pop_wgt, params, false, false, &b, /*defer_flag_check=*/true);
   if (rc) {
     sl.early_status = rc;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int64_t i = 0; i < n_u; i++) z_u[i] = info_u[i] = nan;
     return GB_OK;  // reported by gb_pipe_wait, like a window the reference refuses
   }
   if (b->plan_status[0] != GB_OK) {
     sl.early_status = b->plan_status[0];
     const double nan = std::numeric_limits<double>::quiet_NaN();
     for (int64_t i = 0; i < n_u; i++) z_u[i] = info_u[i] = nan;
-    free_batch_device(b);
+    batch_free_device(b);
     delete b;
     return GB_OK;
   }
   sl.batch = b;
   // 3. pack + window kernels + result copies on the ctx stream, after the rows have landed
-  GB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
-  if ((rc = launch_pack(ctx, sl.panel, sl.d_stage, (int64_t)N, is_ascii, 0, n_t + n_u))) return rc;
-  for (int st = 0; st < 4; st++)
-    if ((rc = run_stage(b, st))) return rc;
-  if ((rc = fetch_enqueue(b, sl.h_z, sl.h_info, sl.h_status))) return rc;
-  GB_CUDA(cudaEventRecord(sl.done, ctx->stream));
+  cudaError_t ce = cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0);
+  if (ce != cudaSuccess) {
+    ctx->err = cudaGetErrorString(ce);
+    rc = GB_ERR_CUDA;
+  }
+  if (!rc) rc = launch_pack(ctx, sl.panel, sl.d_stage, (int64_t)N, is_ascii, 0, n_t + n_u);
+  for (int st = 0; st < 4 && !rc; st++) rc = run_stage(b, st);
+  if (!rc) rc = gb::batch_fetch_enqueue(b, sl.h_z, sl.h_info, sl.h_status);
+  if (!rc && (ce = cudaEventRecord(sl.done, ctx->stream)) != cudaSuccess) {
+    ctx->err = cudaGetErrorString(ce);
+    rc = GB_ERR_CUDA;
+  }
+  if (rc) {
+    // something failed after kernels may have been enqueued: nothing may still touch the batch's buffers when they
+    // are freed, and gb_pipe_wait must not wait on an event that was never recorded
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(pp->copy_stream);
+    batch_free_device(b);
+    delete b;
+    sl.batch = nullptr;
+    sl.early_status = rc;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int64_t i = 0; i < n_u; i++) z_u[i] = info_u[i] = nan;
+    return GB_OK;   // reported by gb_pipe_wait
+  }
   return GB_OK;
 }
 

@@ -52,6 +52,7 @@ struct GramParams {
   int fkind;             // tensor-core operand kind: 0 = int8 (kind::i8), k > 0 = kind::f8f6f4 format k-1
   int raw_out;           // 1: store the raw weighted Gram sum; gram_finalize_kernel finishes it (E2M1, mixture)
   int mirror;            // 1: also store the transposed entry (full symmetric matrix, computeLD)
+  int wide_fold;         // int8 mixture fold: 1 = m*sumxy - sumx*sumy may not fit int32, form it exactly in fp64
   long long* dbg;        // diagnostics only (GB_GRAM_TRACE): per-CTA stall counters, 8 per CTA; nullptr in production
   Seg seg[P_MAX];
   double coef[P_MAX];    // w_p * (m_p / (m_p - 1))          (util.cpp:117-118)
@@ -120,7 +121,7 @@ struct Panel {
   int seg_align = K_ATOM;      // population blocks start on multiples of this many K columns
   int k_elems = 0;             // K columns per packed row (multiple of 128)
   int k_stride = 0;            // bytes per packed row: k_elems (int8) or k_elems / 2 (E2M1 nibbles)
-  int* d_flags = nullptr;      // [1] bit 0: a dosage outside the format's exact set was packed
+  int* d_flags = nullptr;      // [1] bit 0: a dosage outside the format's exact set was packed; bit 1: a byte outside {0,1,2}
   int64_t capacity = 0;
   int64_t n_rows = 0;
   int8_t* d_rows = nullptr;    // [capacity][k_stride bytes]

@@ -450,15 +450,31 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
           for (int e = 0; e < 16; e++) cnt[e] = f32acc ? f32_count_to_int(v[e]) : (int)v[e];
           if (mode == GRAM_MIX) {
             const int4* sBv = reinterpret_cast<const int4*>(sB + s * TILE + c0 + ch * 16);
+            if (prm.wide_fold) {
+              // population blocks large enough that m*sumxy - sumx*sumy can leave int32 (m > 23,170 for dosages,
+              // m > 364 for arbitrary bytes): both products are exact in fp64 (< 2^49) and so is their fused difference
+              const double dm = int_to_double(m), dsA = int_to_double(sAr);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const int4 b4 = sBv[q];
-              const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
+              for (int q = 0; q < 4; q++) {
+                const int4 b4 = sBv[q];
+                const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const int d = m * cnt[q * 4 + k] - sAr * bb[k];  // m*sumxy - sumx*sumy, exact
-                acc[ch * 16 + q * 4 + k] =
-                    __dadd_rn(acc[ch * 16 + q * 4 + k], __dmul_rn(coef, int_to_double(d)));
+                for (int k = 0; k < 4; k++) {
+                  const double d = __fma_rn(dm, int_to_double(cnt[q * 4 + k]), -__dmul_rn(dsA, int_to_double(bb[k])));
+                  acc[ch * 16 + q * 4 + k] = __dadd_rn(acc[ch * 16 + q * 4 + k], __dmul_rn(coef, d));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const int4 b4 = sBv[q];
+                const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const int d = m * cnt[q * 4 + k] - sAr * bb[k];  // m*sumxy - sumx*sumy, exact (plan-time guard: fits int32)
+                  acc[ch * 16 + q * 4 + k] =
+                      __dadd_rn(acc[ch * 16 + q * 4 + k], __dmul_rn(coef, int_to_double(d)));
+                }
               }
             }
           } else if (mode == GRAM_POOLED) {

@@ -41,7 +41,7 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
   int8_t* d = dst + (row0 + row) * (long long)k_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = is_ascii ? 48 : 0;
-  bool bad = false;
+  bool bad = false, big = false;
   // source offset of population p = sum of sizes before it
   int src_off = 0;
   int next_p = 0;
@@ -59,6 +59,7 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
         if (j + b < m) v = (int)(signed char)((int)sp[j + b] - sub);
         sum += v;
         sq += v * v;
+        big |= (unsigned)v > 2u;
         if (FORMAT == GB_PANEL_E2M1) {
           const uint32_t c = e2m1_code(v);
           bad |= c == 0xFFu;
@@ -82,6 +83,7 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
     }
   }
   if (bad) atomicOr(flags, 1);
+  if (big) atomicOr(flags, 2);   // a byte outside {0, 1, 2}: the int8 fold may not assume |d| <= 4 m^2
   // zero the tail between the last population block and the row stride
   const int k_end = koff[n_pops - 1] + (pop_sizes[n_pops - 1] + seg_align - 1) / seg_align * seg_align;
   const int b_end = FORMAT == GB_PANEL_E2M1 ? k_end >> 1 : k_end;

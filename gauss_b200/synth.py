@@ -143,3 +143,58 @@ def chr22_windows(bp_measured: np.ndarray, unmeasured_per_mb: float = 3700.0, co
         windows.append(dict(start_bp=start, end_bp=end, measured=meas, unmeasured=unme))
         start += core
     return bp, type_, windows
+
+
+HG19_MB = [249, 243, 198, 191, 181, 171, 159, 146, 141, 136, 135, 134, 115, 107, 103, 90, 81, 78, 59, 63, 48, 51]
+
+
+def genome_layout(chrom_mb=HG19_MB, measured_per_mb: float = 417.0, unmeasured_per_mb: float = 3470.0,
+                  core: int = 1_000_000, wing: int = 500_000, seed: int = 4, density_sd: float = 0.35,
+                  z_sd: float = 1.34):
+    """Site tables and window lists of a genome-wide distmix run (BASELINE.json config 4: 22 chromosomes, ~1.2 M measured /
+    ~10 M target SNPs, 1 Mb windows with 0.5 Mb wings -> ~2,900 windows, n_t ~ 830, n_u ~ 3,470 per window).
+
+    Measured SNPs follow an inhomogeneous density (log-normal factor per Mb, like the 60x spread of window cost along
+    the bundled chr22 file); unmeasured sites are uniform.  Per chromosome the panel rows are laid out as
+    [measured block | unmeasured block], each in bp order -- the order a feeder that knows the input Z file uploads them
+    in -- so every window is two contiguous row ranges.  `sites[r]` is the bp-order rank of row r (the LD chain of the
+    synthetic generator runs along it).  Windows are in the reference's sense (dist.cpp:132-141): measured = type 1 in
+    [start - wing, end + wing], unmeasured = type 0 in [start, end]."""
+    rng = np.random.default_rng(seed)
+    chroms = []
+    for ci, mb in enumerate(chrom_mb):
+        L = int(mb * core)
+        n_mb = max(1, int(np.ceil(L / core)))
+        fac = np.exp(rng.normal(0.0, density_sd, n_mb))
+        fac *= n_mb / fac.sum()
+        cnt = rng.poisson(measured_per_mb * core / 1e6 * fac)
+        def sorted_unique(a):                      # (np.unique's hash path is ~20x slower on 10^6 int64 keys)
+            a = np.sort(a)
+            return a[np.concatenate([[True], a[1:] != a[:-1]])] if len(a) else a
+
+        bp_m = sorted_unique(np.concatenate([rng.integers(i * core, min((i + 1) * core, L), size=c)
+                                             for i, c in enumerate(cnt)] + [np.zeros(0, np.int64)]))
+        n_u = int(unmeasured_per_mb * mb)
+        bp_u = sorted_unique(rng.integers(0, L, size=int(n_u * 1.02) + 8))
+        if len(bp_m):
+            pos = np.minimum(np.searchsorted(bp_m, bp_u), len(bp_m) - 1)
+            bp_u = bp_u[bp_m[pos] != bp_u]
+        if len(bp_u) > n_u:
+            bp_u = np.sort(rng.choice(bp_u, n_u, replace=False))
+        n_m, n_u = len(bp_m), len(bp_u)
+        # bp-order rank of every row: rank among the union of both sorted lists
+        sites = np.concatenate([np.arange(n_m) + np.searchsorted(bp_u, bp_m),
+                                np.arange(n_u) + np.searchsorted(bp_m, bp_u)]).astype(np.int64)
+        starts = np.arange(0, L, core, dtype=np.int64)
+        t_lo = np.searchsorted(bp_m, starts - wing, "left")
+        t_hi = np.searchsorted(bp_m, starts + core - 1 + wing, "right")
+        u_lo = np.searchsorted(bp_u, starts, "left")
+        u_hi = np.searchsorted(bp_u, starts + core - 1, "right")
+        t_off = np.concatenate([[0], np.cumsum(t_hi - t_lo)]).astype(np.int64)
+        u_off = np.concatenate([[0], np.cumsum(u_hi - u_lo)]).astype(np.int64)
+        rows_t = np.concatenate([np.arange(a, b) for a, b in zip(t_lo, t_hi)] + [np.zeros(0, np.int64)]).astype(np.int64)
+        rows_u = (n_m + np.concatenate([np.arange(a, b) for a, b in zip(u_lo, u_hi)] + [np.zeros(0, np.int64)])).astype(np.int64)
+        z_m = rng.standard_normal(n_m) * z_sd
+        chroms.append(dict(chrom=ci + 1, n_rows=n_m + n_u, n_measured=n_m, sites=sites, t_off=t_off, rows_t=rows_t,
+                           u_off=u_off, rows_u=rows_u, z_t=z_m[rows_t], start_bp=starts, bp_m=bp_m, bp_u=bp_u))
+    return chroms

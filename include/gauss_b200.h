@@ -48,7 +48,11 @@ enum gb_status {
   /* B11 is not certified to satisfy lambda_min >= min_abs_eig, i.e. the reference's MakePosDef
    * (util.cpp:302-318) would have modified it; no eigen-clip path exists on the device. */
   GB_ERR_NOT_PD = 7,
-  GB_ERR_UNSUPPORTED = 8
+  GB_ERR_UNSUPPORTED = 8,
+  /* The Cholesky factorisation of B11 itself met a non-positive pivot (lambda = 0 with duplicated SNPs, negative
+   * weights, NaN correlations of a monomorphic SNP ...): no result exists for the window and its z / info are NaN.
+   * The reference's MakePosDef would have clipped the spectrum instead (util.cpp:302-318). */
+  GB_ERR_BREAKDOWN = 9
 };
 
 typedef struct gb_ctx gb_ctx;     /* one per GPU */
@@ -227,6 +231,71 @@ GB_API int gb_chrom_run_pack5(gb_ctx *ctx, gb_panel *panel, int64_t n_rows, cons
                        int64_t row_stride, int64_t n_windows, const int64_t *t_off, const int64_t *rows_t,
                        const int64_t *u_off, const int64_t *rows_u, const double *z_t, const double *pop_wgt,
                        const gb_params *params, int n_groups, double *z_u, double *info_u, int *window_status);
+
+/* ---- genome-wide run from ONE process on 1..8 GPUs (BASELINE config 4) --------- */
+/* The reference's unit of work is one dist()/distmix() call per window, each rebuilding all of its state
+ * (dist.cpp:63-75); a genome run is a user-level R loop over ~2,900 such calls (the gb_init / gb_windows_submit /
+ * gb_windows_wait triple SURVEY.md section 8b sketches).  A gb_genome takes the whole window list at once: it is cut into
+ * contiguous, cost-balanced shards, one per GPU; every GPU gets its own host thread, context and streams, keeps the
+ * panel rows its windows touch (plus the wings of its boundary windows) resident in HBM -- uploaded ONCE -- and writes
+ * the (z, info) of its windows straight into the caller's per-chromosome arrays.  No collective is used: none is needed.
+ * An R caller behind .Call (RcppExports.cpp:85-102) drives all GPUs of the box through these blocking / submit-wait
+ * calls; nothing here calls back into R.
+ *
+ *   gb_genome_create          devices == NULL -> GPUs 0 .. n_gpus-1; pop_wgt == NULL -> dist(), else distmix()
+ *   gb_genome_add_chromosome  one bp-sorted run of windows over one row space: arguments as gb_chrom_run_pack5 (host_rows5 =
+ *                             ternary HOST rows, may be NULL when the rows will be generated by gb_genome_fill_synthetic;
+ *                             `sites` = optional site index of every row for that generator).  The window lists are
+ *                             copied; the host rows are NOT (they must stay valid until the upload has finished).
+ *   gb_genome_plan            partitions ALL windows (chromosome order) into n_parts runs of ~equal cost and plans parts
+ *                             first_part .. first_part + n_gpus - 1 on this genome's GPUs (n_parts > n_gpus: the other parts
+ *                             belong to other processes, e.g. one rank per GPU under torchrun; every rank computes the
+ *                             same cuts).  Batches of ~48 windows, workspaces, residency mode (ternary rows, or E2M1 operand
+ *                             rows when the shard fits) are decided here.
+ *   gb_genome_upload          host -> device copy of every GPU's row ranges (wait == 0: asynchronous; a run submitted next
+ *                             starts each batch as soon as the rows it touches have landed)
+ *   gb_genome_submit / _wait  all batches of all GPUs; z_u[c] / info_u[c] / window_status[c] are the arrays of chromosome c
+ *                             (aligned with its rows_u / windows; entries may be NULL).  gpu_ms / upload_ms (optional,
+ *                             [n_gpus]) receive the device-timed duration of the run / of the upload per GPU.
+ *                             With window_status == NULL the first non-OK window status is returned. */
+typedef struct gb_genome gb_genome;
+GB_API int gb_genome_create(int n_gpus, const int *devices, int n_pops, const int *pop_sizes, const double *pop_wgt,
+                     const gb_params *params, gb_genome **out);
+GB_API void gb_genome_destroy(gb_genome *g);
+GB_API const char *gb_genome_last_error(const gb_genome *g);
+GB_API int gb_genome_add_chromosome(gb_genome *g, int64_t n_rows, const void *host_rows5, int64_t row_stride,
+                             int64_t n_windows, const int64_t *t_off, const int64_t *rows_t, const int64_t *u_off,
+                             const int64_t *rows_u, const double *z_t, const int64_t *sites);
+GB_API int gb_genome_plan(gb_genome *g, int n_parts, int first_part);
+GB_API int gb_genome_num_chromosomes(const gb_genome *g);
+/* What GPU `gpu` of this genome was given (any pointer may be NULL). */
+GB_API int gb_genome_shard_info(const gb_genome *g, int gpu, int64_t *first_window, int64_t *n_windows,
+                         int64_t *resident_rows, int64_t *n_batches, int64_t *n_imputed, int *e2m1_resident,
+                         double *gram_ops, double *solve_flops);
+GB_API int gb_genome_upload(gb_genome *g, int wait);
+GB_API int gb_genome_submit(gb_genome *g, double *const *z_u, double *const *info_u, int *const *window_status);
+GB_API int gb_genome_wait(gb_genome *g, double *gpu_ms, double *upload_ms);
+GB_API int gb_genome_run(gb_genome *g, double *const *z_u, double *const *info_u, int *const *window_status,
+                  double *gpu_ms);
+GB_API int64_t gb_genome_launch_count(const gb_genome *g);
+/* The partition gb_genome_plan uses, for callers that place the parts themselves: window w costs
+ * N (n_u n_t + n_t^2 / 2) Gram multiply-adds + 80 (n_t^2 n_u + n_t^3 / 3) (the measured ratio of the two rates on B200);
+ * windows the reference refuses (dist.cpp:146) cost nothing.  cuts has n_parts + 1 entries; cost_out (optional) n_windows.
+ * Pure host code. */
+GB_API int gb_partition_windows(int64_t n_windows, const int64_t *n_t, const int64_t *n_u, int64_t n_samples,
+                         const gb_params *params, int n_parts, int64_t *cuts, double *cost_out);
+
+/* ---- synthetic panel rows, generated on the device (benchmark / test DATA, not a reference path) --------- */
+/* The 33KG panel is not distributable (docs/articles/ref_33KG.md:7) and BASELINE config 4 is ~10 M SNPs x 32,953
+ * individuals, so SURVEY.md section 7 asks for on-device generation.  Rows come out in the ternary host format
+ * (gb_pack5_row_bytes); a dosage is a pure function of (seed, chrom, site, population, individual), so every shard
+ * regenerates the rows any other would.  site of row r = sites[r], or first_site + r when sites == NULL.
+ * out: HOST memory (out_is_device == 0) or DEVICE memory of ctx's GPU. */
+GB_API int gb_synth_pack5_rows(gb_ctx *ctx, uint64_t seed, int chrom, int64_t n_rows, const int64_t *sites,
+                        int64_t first_site, int n_pops, const int *pop_sizes, void *out, int64_t out_stride,
+                        int out_is_device);
+/* Fill every GPU's resident rows with that generator instead of uploading them (chromosome index = `chrom`). */
+GB_API int gb_genome_fill_synthetic(gb_genome *g, uint64_t seed, int wait);
 
 /* ---- pipelined single windows, host in / host out ---------------------------------------------- */
 /* What a genome loop over dist()/distmix() calls (dist.cpp:63-75 runs one window per call): the
