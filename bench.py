@@ -1,22 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- distmix imputed SNPs/sec on a 33KG-shaped synthetic panel (BASELINE.json configs[1]).
+"""bench.py -- distmix imputed SNPs/sec on a 33KG-shaped synthetic panel (BASELINE.json metric).
 
-A "step" is one pass of the window hot path over one chromosome-22-shaped batch: 36 one-Mb
-prediction windows (0.5 Mb wings), measured SNPs at the positions of the reference's bundled
-PGC2_Chr22_ilmn1M_Z.txt, ~3,700 synthetic unmeasured sites per Mb, 21 flagged populations /
-32,147 individuals with the PGC2_SCZ_ANC_Prop weights.
+Workloads (`--workload`):
+  genome  (default) BASELINE config 4: genome-wide distmix, 22 chromosomes, ~2,900 one-Mb windows (0.5 Mb wings),
+          ~1.2 M measured / ~10 M target SNPs, 21 flagged populations / 32,147 individuals, PGC2 weights.  The SAME
+          job at every N (strong scaling): the window list is cut into N contiguous cost-balanced shards
+          (gb_genome_plan / gb_partition_windows), each GPU keeps its rows resident and the results are gathered on
+          the host.  One process per GPU under torchrun (each rank drives a one-GPU gb_genome with its part of the
+          partition); `--single-process` drives all N GPUs from ONE process through the same C-ABI (one host thread
+          per GPU inside the library).
+  chr22   BASELINE config 2 (the round-1 line): one chromosome-22-shaped batch, 36 windows at the bundled PGC2 positions.
+  ld5000  BASELINE config 3: computeLD of a dense 5,000-SNP block (Gram + mixture epilogue only).
+  dist1kg BASELINE config 1: dist() on chr22 against a 1KG-shaped panel (EUR, 503 individuals; and all 2,504).
 
-  value  whole-job imputed SNPs/s with the packed panel resident in HBM (K0 stats + K1 Gram +
-         K2 Cholesky/solve; device-timed with CUDA events, max over ranks)
-  e2e    the same metric through the per-window C-ABI call with HOST buffers: pinned-host
-         genotype rows -> H2D -> pack -> window -> D2H of (z, info), every window, every step
-  roofline  K1 (gram_seg_kernel): algorithmic int8 ops / measured launch time vs int8 peak
-  cpu_baseline / --impl reference  the reference's own CPU code path (oracle/_ref when built,
-         else the C restatement) on a bounded sample of the same workload, 1 host core (the
-         reference is single-threaded by construction)
-
-N > 1 (torchrun): every rank owns one GPU and one chromosome-shaped shard (different seed);
-windows are independent so there is no data-path collective; scaling is weak.
+  value     whole-job imputed SNPs/s with the panel rows resident in HBM; device-timed (CUDA events inside the library,
+            around everything the step enqueues incl. the D2H of z / info), max over ranks
+  e2e       the same job from pinned HOST rows (ternary packed panel): host -> device upload of every GPU's rows inside
+            the timed region, batches starting as their rows land, results written to host arrays; wall clock
+  roofline  the longest kernel of the step (trsm_finalize_kernel) against the fp64 tensor-core rate measured on this box
+            at bench time (gb_probe_peak); roofline_gram / roofline_chol / roofline_expand5 beside it
+  cpu_baseline / --impl reference   the reference's own CPU code (oracle/_ref) on a bounded sample, see cpu_model()
 """
 from __future__ import annotations
 
@@ -39,9 +42,10 @@ from gauss_b200 import synth  # noqa: E402
 METRIC = "distmix imputed SNPs/sec"
 UNIT = "SNPs/s"
 SITES = os.path.join(ROOT, "tests", "golden", "pgc2_chr22_sites.npz")
+SEED = 20260101
 
 
-# ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------ workloads
 def chr22_layout():
     d = np.load(SITES)
     bp_m, first = np.unique(d["bp"].astype(np.int64), return_index=True)
@@ -50,19 +54,45 @@ def chr22_layout():
     return bp, type_, windows, bp_m, z_m
 
 
+def genome_chroms(args):
+    mb = synth.HG19_MB if args.genome_mb == "all" else [int(x) for x in args.genome_mb.split(",")]
+    return synth.genome_layout(mb)
+
+
+def genome_config(chroms, world, mode):
+    nw = sum(len(c["t_off"]) - 1 for c in chroms)
+    n_m = sum(c["n_measured"] for c in chroms)
+    n_u = sum(c["n_rows"] - c["n_measured"] for c in chroms)
+    mb = sum(len(c["start_bp"]) for c in chroms)
+    return dict(workload=f"genome-wide distmix (BASELINE config 4): {len(chroms)} chromosomes / {mb} Mb (hg19 lengths), {nw} x 1 Mb "
+                         f"windows with 0.5 Mb wings, {n_m / 1e6:.2f} M measured + {n_u / 1e6:.2f} M target SNPs (synthetic sites, "
+                         "log-normal measured density), 33KG-shaped panel: 21 flagged pops / 32,147 indiv (of 29 / 32,953), "
+                         "PGC2_SCZ_ANC_Prop weights, lambda=0.1, PD certificate on",
+                windows=nw,
+                l2="inputs >> L2 (126 MB): every step streams the resident panel rows (65 GB as ternary rows at N=1)",
+                parallelism=f"{world} contiguous cost-balanced window shard(s), rows resident per GPU, host gather, no collective ({mode})")
+
+
+def chr22_config():
+    return dict(workload="distmix chr22 (BASELINE config 2), 36 x 1 Mb windows (0.5 Mb wings), measured SNPs at PGC2_Chr22_ilmn1M_Z "
+                         "positions + 3.7k synthetic unmeasured/Mb, 33KG-shaped panel: 21 flagged pops / 32,147 "
+                         "indiv (of 29 / 32,953), PGC2_SCZ_ANC_Prop weights, lambda=0.1, PD certificate on",
+                windows=36, l2="inputs >> L2 (126 MB): each step streams the packed panel slice (2.3 GB as E2M1 nibbles)",
+                parallelism="one chromosome-shaped batch per GPU, no collective")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         j = json.load(open(p))
         return dict(hbm_gbs=j["hbm_gbs"], bf16_tflops=j["bf16_tflops"],
-                    bf16_tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
-    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+                    bf16_tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="B200_PROFILING.md fallback")
 
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled through
-    NVML every 5 ms from a host thread (the timed region of one step is ~10 ms, far below
-    nvidia-smi's own polling period); falls back to `nvidia-smi -lms` when pynvml is unavailable."""
+    NVML every 5 ms from a host thread; falls back to `nvidia-smi -lms` when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -94,7 +124,6 @@ class ClockSampler:
         try:
             import pynvml as nv
             nv.nvmlInit()
-            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
             vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
             idx = self.device
             if vis and all(x.strip().isdigit() for x in vis.split(",")):
@@ -154,106 +183,152 @@ class ClockSampler:
         return out
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_sample(kind_pref: str, n_t_target: int, n_u_sample: int, seed: int = 5):
-    """Time the reference's CPU path on ONE bounded sample window of the workload and extrapolate
-    linearly in sample-pairs to the whole chromosome-shaped step."""
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def window_sizes(workload: str, args):
+    """(n_t, n_u) of every window the reference would accept (dist.cpp:146) and the flagged population sizes / weights."""
+    _, sizes, w = synth.flagged_33kg_pgc2()
+    if workload == "genome":
+        ch = genome_chroms(args)
+        nt = np.concatenate([np.diff(c["t_off"]) for c in ch])
+        nu = np.concatenate([np.diff(c["u_off"]) for c in ch])
+    else:
+        _, _, windows, _, _ = chr22_layout()
+        nt = np.array([len(x["measured"]) for x in windows])
+        nu = np.array([len(x["unmeasured"]) for x in windows])
+    ok = (nt > 10) & (nu > 10)
+    return nt[ok], nu[ok], sizes, w
+
+
+def _eig_lu_seconds(n: int) -> float:
+    """MakePosDef (symmetric eigensolver) + InvMat (full-pivot LU inverse) of an n x n correlation matrix: the O(n^3)
+    part of a window (util.cpp:298-318).  Eigen is absent here, so this times the restated algorithms the checker
+    uses (Householder + implicit QL; Gaussian elimination with complete pivoting)."""
     from oracle.oracle_py import Oracle
-    kind = kind_pref if Oracle.available(kind_pref) else "port"
+    o = Oracle("port")
+    rng = np.random.default_rng(n)
+    A = np.corrcoef(rng.standard_normal((n, 2 * n)))
+    A[np.diag_indices(n)] = 1.1
+    A = np.ascontiguousarray(A)
+    inv = np.zeros_like(A)
+    t0 = time.perf_counter()
+    o.lib.go_make_pos_def(A, n, 1e-5)
+    o.lib.go_inv_full_piv_lu(inv, A, n)
+    return time.perf_counter() - t0
+
+
+def _pair_rate_worker(arg):
+    """One bounded sample window through the reference's own run_distmix (oracle/_ref): n_t measured x n_u unmeasured
+    SNPs at the full 32,147 individuals.  Returns (sample-pairs, seconds, kind)."""
+    seed, n_t, n_u = arg
+    from oracle.oracle_py import Oracle
+    kind = "reference" if Oracle.available("reference") else "port"
     orc = Oracle(kind)
     _, sizes, w = synth.flagged_33kg_pgc2()
-    N = int(sizes.sum())
-    bp, type_, windows, bp_m, z_m = chr22_layout()
-    nts = np.array([len(x["measured"]) for x in windows])
-    wi = int(np.argmin(np.abs(nts - n_t_target)))
-    win = windows[wi]
-    n_t = len(win["measured"])
-    n_u = min(n_u_sample, len(win["unmeasured"]))
     g = synth.make_genotypes(n_t + n_u, sizes, seed=seed)
     t = np.concatenate([np.ones(n_t, np.int32), np.zeros(n_u, np.int32)])
-    zz = np.concatenate([z_m[:n_t], np.zeros(n_u)])
+    zz = np.concatenate([np.random.default_rng(seed).standard_normal(n_t), np.zeros(n_u)])
     bpp = np.arange(n_t + n_u, dtype=np.int64)
     t0 = time.perf_counter()
     r = orc.run_window(t, bpp, zz, g, sizes, w, 0, 10 ** 12)
     dt = time.perf_counter() - t0
     assert r["rc"] == 0
-    pairs_sample = n_t * (n_t - 1) / 2 + n_u * n_t + (n_t + n_u)
-    rate = pairs_sample * N / dt                       # sample-pairs / s, 1 core
-    tot_pairs, tot_u = 0.0, 0
-    for x in windows:
-        a, b = len(x["measured"]), len(x["unmeasured"])
-        if a > 10 and b > 10:
-            tot_pairs += a * (a - 1) / 2 + b * a + (a + b)
-            tot_u += b
-    est_step_s = tot_pairs * N / rate
-    return dict(kind=kind, value=tot_u / est_step_s, seconds=dt, n_t=n_t, n_u=n_u, rate=rate,
-                sample=(f"1 window, n_t={n_t} measured (chr22 window {wi}) x {n_u} of its unmeasured SNPs, "
-                        f"N={N}, 21 pops: {dt:.1f} s on 1 core = {rate:.3g} sample-pairs/s incl. eig+LU; "
-                        f"extrapolated linearly in sample-pairs to the {tot_u}-SNP step ({est_step_s / 3600:.2f} core-hours)"))
+    pairs = (n_t * (n_t - 1) / 2 + n_u * n_t + (n_t + n_u)) * float(sizes.sum())
+    return pairs, dt, kind, n_t
 
 
-def _ref_worker(seed):
-    s = cpu_sample("reference", n_t_target=250, n_u_sample=48, seed=seed)
-    return s["n_t"], s["n_u"], s["seconds"], s["kind"]
+def cpu_model(workload, args, pair_samples, eig_times):
+    """CPU time of the whole step on ONE core, assembled from measurements of the reference's own code:
+       t(window) = sample-pairs(window) / pair rate  +  eig+LU(n_t)
+    pair rate: sample windows through run_distmix at the full N (the correlation loops are linear in sample-pairs,
+    SURVEY.md section 8d); eig+LU: timed at the workload's min / mean / (capped) max n_t, interpolated in between and
+    cubic beyond.  pair_samples: (sample-pairs, seconds, kind, n_t) per sample window."""
+    nt, nu, sizes, _ = window_sizes(workload, args)
+    N = float(sizes.sum())
+    ns = np.array(sorted(eig_times))
+    ts = np.array([eig_times[k] for k in ns])
+    coef = float(np.mean(ts / ns.astype(float) ** 3))          # s per n^3
+
+    def eig(n):
+        if n <= ns[0]:
+            return float(ts[0] * (n / ns[0]) ** 3)
+        return float(np.interp(n, ns, ts)) if n <= ns[-1] else float(ts[-1] * (n / ns[-1]) ** 3)
+
+    # the sample windows' own eig+LU share is taken out of their time before the pair rate is formed
+    rate = sum(s[0] for s in pair_samples) / sum(max(s[1] - eig(s[3]), 1e-3) for s in pair_samples)
+    pairs = (nt * (nt - 1) / 2 + nu * nt + (nt + nu)) * N
+    t_pairs = float(pairs.sum() / rate)
+    t_eig = float(sum(eig(int(n)) for n in nt))
+    return dict(core_seconds=t_pairs + t_eig, pair_seconds=t_pairs, eig_lu_seconds=t_eig, pair_rate=rate,
+                eig_lu_ns_per_n3=coef * 1e9, n_imputed=int(nu.sum()), nt_min=int(nt.min()), nt_mean=float(nt.mean()),
+                nt_max=int(nt.max()), eig_points={int(k): float(v) for k, v in eig_times.items()})
+
+
+def eig_points(nt, cap=1200):
+    return sorted({int(nt.min()), int(round(nt.mean())), int(min(nt.max(), cap))})
+
+
+def cpu_baseline_one_core(workload, args):
+    nt, _, _, _ = window_sizes(workload, args)
+    n_s = int(min(max(nt.min(), 200), 320))
+    samples = [_pair_rate_worker((5, n_s, 96))]
+    eig = {n: _eig_lu_seconds(n) for n in eig_points(nt)}
+    m = cpu_model(workload, args, samples, eig)
+    return dict(value=m["n_imputed"] / m["core_seconds"], unit=UNIT, cores=1, kind=samples[0][2],
+                sample=(f"run_distmix of oracle/_ref on 1 window (n_t={n_s} x 96 unmeasured SNPs, N=32147, 21 pops: {samples[0][1]:.1f} s "
+                        f"-> {m['pair_rate']:.3g} sample-pairs/s) + eig+LU timed at n_t={list(m['eig_points'])} "
+                        f"({', '.join(f'{v:.2f} s' for v in m['eig_points'].values())}; cubic beyond the largest); step = "
+                        f"{m['pair_seconds'] / 3600:.1f} core-hours of correlation loops + {m['eig_lu_seconds'] / 3600:.2f} of "
+                        f"eig+LU over windows with n_t {m['nt_min']}/{m['nt_mean']:.0f}/{m['nt_max']} (min/mean/max)"))
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU code path (oracle/_ref = its CalWgtCov / run_distmix compiled
-    from /root/reference/src; the C port only if that library is absent) on the box's host cores.  The
-    reference is single-threaded, so "all the host threads it can use" = one window per core, the way a
-    user would fan an R loop out over processes.  Each step = one bounded sample window per core."""
+    """Reference arm: the reference's own CPU code path (oracle/_ref = its CalWgtCov / run_distmix compiled from
+    /root/reference/src; the C port only if that library is absent) on ALL host cores of the box.  The reference is
+    single-threaded, so "all the host threads it can use" = one window per core, the way a user fans the R loop out.
+    A step = one bounded sample window per core (pair-loop rate at the full N); the O(n_t^3) eig + LU part is timed
+    once, in the warm-up, at the workload's min / mean / (capped) max n_t and added per window (cpu_model)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    _, sizes, _ = synth.flagged_33kg_pgc2()
-    N = int(sizes.sum())
-    bp, type_, windows, bp_m, z_m = chr22_layout()
-    tot_pairs, tot_u = 0.0, 0
-    for x in windows:
-        a, b = len(x["measured"]), len(x["unmeasured"])
-        if a > 10 and b > 10:
-            tot_pairs += a * (a - 1) / 2 + b * a + (a + b)
-            tot_u += b
-    vals, last_ms, kind, desc = [], 0.0, "port", ""
+    workload = "genome" if args.workload in ("auto", "genome") else "chr22"
+    nt, nu, sizes, _ = window_sizes(workload, args)
+    n_s = int(min(max(nt.min(), 200), 320))
+    vals, last_ms, kind, model = [], 0.0, "port", None
     with mp.get_context("spawn").Pool(cores) as pool:
+        eig_async = pool.map_async(_eig_lu_seconds, eig_points(nt))
+        eig = None
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_ref_worker, [5 + i * cores + k for k in range(cores)])
+            res = pool.map(_pair_rate_worker, [(5 + i * cores + k, n_s, 48) for k in range(cores)])
             wall = time.perf_counter() - t0
-            # every worker times only its run_distmix call (not data generation); they overlap in time,
-            # so the node rate is the sum of the per-core rates
-            rate = sum((nt * (nt - 1) / 2 + nu * nt + (nt + nu)) * N / sec for nt, nu, sec, _ in res)
+            if eig is None:
+                eig = dict(zip(eig_points(nt), eig_async.get()))
+            # the workers overlap in time: per-core time = the model's core-seconds / cores
+            m = cpu_model(workload, args, res, eig)
             if i >= args.warmup:
-                vals.append(tot_u / (tot_pairs * N / rate))
-            last_ms, kind = wall * 1e3, res[0][3]
-            desc = (f"{cores} windows at once, one per core (n_t={res[0][0]}, {res[0][1]} unmeasured SNPs each, N={N}, "
-                    f"21 pops): {max(r[2] for r in res):.1f} s each = {rate:.3g} sample-pairs/s over all cores incl. eig+LU; "
-                    f"extrapolated linearly in "
-                    f"sample-pairs to the {tot_u}-SNP step")
+                vals.append(m["n_imputed"] / (m["core_seconds"] / cores))
+            last_ms, kind, model = wall * 1e3, res[0][2], m
     v = float(np.mean(vals))
+    step_ms = model["core_seconds"] / cores * 1e3
+    desc = (f"{cores} windows at once, one per core (n_t={n_s}, 48 unmeasured SNPs each, N=32147, 21 pops) through oracle/_ref's "
+            f"run_distmix: {model['pair_rate']:.3g} sample-pairs/s per core; eig+LU timed at n_t={list(model['eig_points'])} "
+            f"({', '.join(f'{t:.2f} s' for t in model['eig_points'].values())}); step = {model['pair_seconds'] / 3600:.1f} core-hours "
+            f"of correlation loops + {model['eig_lu_seconds'] / 3600:.2f} of eig+LU (windows n_t {model['nt_min']}/"
+            f"{model['nt_mean']:.0f}/{model['nt_max']}), divided over {cores} cores")
+    cfg = genome_config(genome_chroms(args), args.gpus, "reference") if workload == "genome" else chr22_config()
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=last_ms, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f64", data="synthetic", impl="reference",
-                config=workload_config(),
+                ms_per_step=step_ms, sample_ms_per_step=last_ms, higher_is_better=True,
+                scaling="strong" if workload == "genome" else "weak", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference", config=cfg,
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind=kind, sample=desc),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
-def workload_config():
-    return dict(workload="distmix chr22, 36 x 1 Mb windows (0.5 Mb wings), measured SNPs at PGC2_Chr22_ilmn1M_Z "
-                         "positions + 3.7k synthetic unmeasured/Mb, 33KG-shaped panel: 21 flagged pops / 32,147 "
-                         "indiv (of 29 / 32,953), PGC2_SCZ_ANC_Prop weights, lambda=0.1, PD certificate on",
-                windows=36, l2="inputs >> L2 (126 MB): each step streams the packed panel slice (2.3 GB as E2M1 nibbles)",
-                parallelism="window-sharded, no collective")
-
-
 def bind_to_gpu_numa_node(index: int) -> str:
-    """Multi-rank runs: keep this process (its pinned host buffers are first-touched here, the host packer's threads
-    inherit the mask) on the CPUs NVML reports as local to its GPU, so eight ranks do not pull their panel rows across
-    the socket interconnect.  Host-side plumbing only; failures are reported, never fatal."""
+    """Multi-rank runs: keep this process on the CPUs NVML reports as local to its GPU.  Host-side plumbing only."""
     try:
         import pynvml as nv
         nv.nvmlInit()
@@ -269,277 +344,634 @@ def bind_to_gpu_numa_node(index: int) -> str:
         return f"not bound ({type(e).__name__}: {e})"
 
 
-# ------------------------------------------------------------------------------------------------
-def run_gpu(args):
-    import torch
-    import gauss_b200 as gb
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Env:
+    """Rank / device / timing plumbing shared by the workloads."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa_note = bind_to_gpu_numa_node(local) if world > 1 else "not bound (1 rank)"
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa_node(self.local) if self.world > 1 else "not bound (1 rank)"
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
 
-    _, sizes, w = synth.flagged_33kg_pgc2()
-    N = int(sizes.sum())
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op):
+        t = self.torch.tensor(list(vals), device=self.dev, dtype=self.torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(x) for x in t]
+
+
+def u64_checksum(arrs):
+    """Order-independent exact checksum of float64 results: sum of the bit patterns mod 2^64 (placement of windows on
+    GPUs / ranks / batches cannot change it unless a result changes)."""
+    s = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for a in arrs:
+            s = s + np.ascontiguousarray(a).view(np.uint64).sum(dtype=np.uint64)
+    return int(s)
+
+
+def measure_probes(ctx):
+    pk = peaks()
+    out = dict(source="gb_probe_peak on this GPU at bench time (tensor pipe alone: one thread per SM issuing back-to-back "
+                      "tcgen05.mma 128x128 from shared memory, no TMA, no epilogue; fp64: mma.sync m8n8k4 from registers, "
+                      "16 warps per SM; copy: 1 GiB device copy, read + write bytes)")
+    for k in ("i8", "mxf4", "fp64", "copy"):
+        try:
+            out[k] = ctx.probe_peak(k)
+        except Exception as e:  # noqa: BLE001
+            out[k] = None
+            out[k + "_error"] = str(e)
+    out["units"] = dict(i8="TOP/s", mxf4="TOP/s", fp64="TFLOP/s", copy="GB/s")
+    out["measured_peaks_json"] = pk
+    try:
+        json.dump(out, open(os.path.join(ROOT, "MEASURED_PEAKS_TENSOR.json"), "w"), indent=1)
+    except OSError:
+        pass
+    return out
+
+
+# NCU figures of the kernels below (one `ncu --set full` capture each, profiles/, not re-measured here): tensor-pipe
+# utilisation and DRAM bytes per launch on the chr22-shaped batch
+NCU = dict(
+    gram=dict(tensor_pipe_pct=None, dram_bytes=3.676e9, file="profiles/r01_final_ncu_full.md"),
+    trsm=dict(dram_bytes=5.96e9, file="profiles/r01_final_ncu_full.md"),
+)
+_ncu_path = os.path.join(ROOT, "profiles", "r02_ncu_figures.json")
+if os.path.exists(_ncu_path):
+    try:
+        for _k, _v in json.load(open(_ncu_path)).items():
+            NCU.setdefault(_k, {}).update(_v)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def chr22_batch_inputs(sizes):
     bp, type_, windows, bp_m, z_m = chr22_layout()
     n_m = int((type_ == 1).sum())
     n_all = len(bp)
     # panel layout: [measured block | unmeasured block], each in bp order -> every window is two
     # contiguous row ranges and TMA reads the panel directly (no gather)
-    pos_in_block = np.empty(n_all, np.int64)
-    pos_in_block[type_ == 1] = np.arange(n_m)
-    pos_in_block[type_ == 0] = n_m + np.arange(n_all - n_m)
-
-    t_off, u_off, rows_t, rows_u, z_t = [0], [0], [], [], []
+    pos = np.empty(n_all, np.int64)
+    pos[type_ == 1] = np.arange(n_m)
+    pos[type_ == 0] = n_m + np.arange(n_all - n_m)
     meas_idx = np.where(type_ == 1)[0]
     z_by_site = np.zeros(n_all)
     z_by_site[meas_idx] = z_m
+    t_off, u_off, rows_t, rows_u, z_t = [0], [0], [], [], []
     for x in windows:
-        rows_t.append(pos_in_block[x["measured"]])
-        rows_u.append(pos_in_block[x["unmeasured"]])
+        rows_t.append(pos[x["measured"]])
+        rows_u.append(pos[x["unmeasured"]])
         z_t.append(z_by_site[x["measured"]])
         t_off.append(t_off[-1] + len(x["measured"]))
         u_off.append(u_off[-1] + len(x["unmeasured"]))
-    rows_t, rows_u, z_t = np.concatenate(rows_t), np.concatenate(rows_u), np.concatenate(z_t)
+    sites = np.concatenate([meas_idx, np.where(type_ == 0)[0]]).astype(np.int64)     # bp-order rank of every row
+    return dict(n_all=n_all, n_m=n_m, windows=windows, pos=pos, z_by_site=z_by_site, sites=sites,
+                t_off=np.array(t_off), u_off=np.array(u_off), rows_t=np.concatenate(rows_t),
+                rows_u=np.concatenate(rows_u), z_t=np.concatenate(z_t))
 
-    ctx = gb.Context(local)
-    # all library work and all timing events go on ONE explicit (non-default) torch stream
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ctx.set_stream(stream.cuda_stream)
 
-    # ---- synthetic panel, generated on the device, packed once (K0)
+def stage_times(env, batch, stream, steps, stages):
+    torch = env.torch
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(steps)]
+    for k in range(steps):
+        for i, s in enumerate(stages):
+            evs[k][i].record(stream)
+            batch.run_stage(s)
+        evs[k][len(stages)].record(stream)
+    torch.cuda.synchronize()
+    return np.array([[evs[k][s].elapsed_time(evs[k][s + 1]) for s in range(len(stages))] for k in range(steps)])
+
+
+def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, tag="chr22"):
+    """One chromosome-22-shaped batch resident in HBM: value, per-stage times, rooflines, host-buffer legs."""
+    import gauss_b200 as gb
+    from gauss_b200 import api
+    torch = env.torch
+    dev = env.dev
+    N = int(sizes.sum())
+    L = chr22_batch_inputs(sizes)
+    n_all = L["n_all"]
+    out = {}
+    # ---- synthetic panel generated on the device as ternary rows, expanded once (K0c)
+    row5 = api.pack5_row_bytes(sizes)
     t0 = time.time()
-    geno = synth.make_genotypes_torch(n_all, sizes, dev, seed=20260101 + 22 + 1000 * rank)
-    order = torch.from_numpy(np.concatenate([meas_idx, np.where(type_ == 0)[0]])).to(dev)
-    geno = geno[order].contiguous()
+    d_rows5 = torch.empty((n_all, row5), dtype=torch.uint8, device=dev)
+    api.synth_pack5_rows_device(ctx, SEED + 22 + 1000 * env.rank, 21, sizes, n_all, d_rows5.data_ptr(), row5, sites=L["sites"])
     torch.cuda.synchronize()
     gen_s = time.time() - t0
-    panel = gb.Panel(ctx, sizes, n_all)
+    panel = gb.Panel(ctx, sizes, n_all, "e2m1")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    panel.append_device_ptr(geno.data_ptr(), n_all, N, is_ascii=False)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    pack_ms = ev0.elapsed_time(ev1)
-
-    batch = gb.Batch(panel, t_off, rows_t, u_off, rows_u, z_t, w)
-    work = batch.work()
-    n_imputed = int(sum(len(x["unmeasured"]) for x in windows
-                        if len(x["measured"]) > 10 and len(x["unmeasured"]) > 10))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    exp_ms = []
+    for _ in range(3):
+        panel.clear()
+        ev0.record(stream)
+        panel.append_pack5_device_ptr(d_rows5.data_ptr(), n_all, row5)
+        ev1.record(stream)
         torch.cuda.synchronize()
+        exp_ms.append(ev0.elapsed_time(ev1))
+    k_stride = ((sizes + 127) // 128 * 128).sum() // 2
+    exp_bytes = n_all * (row5 + k_stride + 8 * len(sizes))
+    pk = peaks()
+    out["roofline_expand5"] = dict(bound="hbm", kernel="expand5_rows_kernel", achieved=exp_bytes / (min(exp_ms) / 1e3) / 1e9,
+                                   peak=pk["hbm_gbs"], unit="GB/s", frac=exp_bytes / (min(exp_ms) / 1e3) / 1e9 / pk["hbm_gbs"],
+                                   traffic=NCU.get("expand5", {}).get("dram_bytes"), ms=min(exp_ms), rows=n_all,
+                                   note=f"ternary resident rows ({row5} B) -> E2M1 operand rows ({int(k_stride)} B) + per-population "
+                                        f"sum x / sum x^2: algorithmic bytes {exp_bytes / 1e9:.2f} GB per launch; peak = {pk['source']} hbm_gbs "
+                                        f"(copy probe on this box: {probes.get('copy')})")
+    if fmt == "int8":
+        # the int8 arm: same rows as one signed byte per dosage (kind::i8, int32 accumulate)
+        host5 = torch.empty((n_all, row5), dtype=torch.uint8)
+        host5.copy_(d_rows5)
+        g8 = torch.from_numpy(api.unpack5_rows(host5.numpy(), sizes))
+        panel = gb.Panel(ctx, sizes, n_all, "int8")
+        panel.append_host(g8.numpy(), is_ascii=False)
+        del g8, host5
+    batch = gb.Batch(panel, L["t_off"], L["rows_t"], L["u_off"], L["rows_u"], L["z_t"], w)
+    work = batch.work()
+    windows = L["windows"]
+    n_imputed = int(sum(len(x["unmeasured"]) for x in windows if len(x["measured"]) > 10 and len(x["unmeasured"]) > 10))
+    n_u_all = int(L["u_off"][-1])
+    z_pin = torch.empty(n_u_all, dtype=torch.float64, pin_memory=True)
+    i_pin = torch.empty(n_u_all, dtype=torch.float64, pin_memory=True)
 
-    # ---- resident path: W warm-up steps, then K timed steps of the product call (gb_batch_run: the factorisation
-    # overlaps the B21 part of the Gram kernel on a side stream; both join before the solve, so events on the
-    # launching stream bracket all of it)
-    for _ in range(args.warmup):
+    def step():
         batch.run()
-    barrier()
-    sampler = ClockSampler(local)
+        return batch.fetch(z_pin.numpy(), i_pin.numpy())     # D2H of z / info / statuses: part of the resident step (SURVEY 8d i)
+
+    for _ in range(args.warmup):
+        step()
+    env.barrier()
+    sampler = ClockSampler(env.local)
     sampler.start()
     launches0 = ctx.launch_count
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(stream)
-    for k in range(args.steps):
-        batch.run()
+    for _ in range(args.steps):
+        z, info, status = step()
     e_end.record(stream)
-    torch.cuda.synchronize()      # the sampler must cover the device's timed region, not just the host's enqueue of it
-    barrier()
+    torch.cuda.synchronize()
+    env.barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     total_ms = e_start.elapsed_time(e_end)
-    # ---- the same K steps stage by stage (serialised, every kernel on all SMs): per-stage times and the
-    # dominant kernel's own launch duration for the roofline
-    STAGES = [0, 10, 11, 2, 3]   # row statistics | Gram tensor-core kernel | Gram finish pass | Cholesky | solve
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(STAGES) + 1)] for _ in range(args.steps)]
-    for k in range(args.steps):
-        for i, s in enumerate(STAGES):
-            evs[k][i].record(stream)
-            batch.run_stage(s)
-        evs[k][len(STAGES)].record(stream)
-    torch.cuda.synchronize()
-    stage_ms = np.array([[evs[k][s].elapsed_time(evs[k][s + 1]) for s in range(len(STAGES))]
-                         for k in range(args.steps)])
-    z, info, status = batch.fetch()
+    z, info = z.copy(), info.copy()
     n_ok = int((status == 0).sum())
+    # ---- the same K steps stage by stage (serialised, every kernel on all SMs)
+    STAGES = [0, 10, 11, 2, 3]   # row statistics | Gram tensor-core kernel | Gram finish pass | Cholesky | solve
+    st = stage_times(env, batch, stream, args.steps, STAGES)
+    gram_ms, fin_ms, chol_ms, trsm_ms = (float(st[:, i].mean()) for i in (1, 2, 3, 4))
+    nts = np.array([len(x["measured"]) for x in windows], float)
+    nus = np.array([len(x["unmeasured"]) for x in windows], float)
+    okw = (nts > 10) & (nus > 10)
+    trsm_flops = float((nts ** 2 * nus + nts ** 2 + 4 * nts * nus)[okw].sum())
+    chol_flops = float((nts ** 3 / 3)[okw].sum())
+    mhz = clocks.get("sm_max_mhz") or 1965.0
+    fp64_peak = probes.get("fp64") or 148 * 128 * mhz * 1e6 / 1e12
+    fp64_src = "gb_probe_peak fp64 (mma.sync m8n8k4, measured on this box now)" if probes.get("fp64") else "148 SM x 128 flop x SM clock"
+    out.update(
+        value=n_imputed * args.steps / (total_ms / 1e3), ms_per_step=total_ms / args.steps, launches=int(launches), clocks=clocks,
+        n_imputed=n_imputed, windows_ok=n_ok, panel_gen_s=gen_s, work=work, z=z, info=info, status=status,
+        stage_ms_serial=float(st.sum(1).mean()),
+        stage_ms=dict(row_stats=float(st[:, 0].mean()), gram=gram_ms, gram_finish=fin_ms, cholesky=chol_ms, solve=trsm_ms),
+        roofline=dict(bound="tensor", kernel="trsm_finalize_kernel", achieved=trsm_flops / (trsm_ms / 1e3) / 1e12, peak=fp64_peak,
+                      unit="TFLOP/s", frac=trsm_flops / (trsm_ms / 1e3) / 1e12 / fp64_peak,
+                      traffic=NCU["trsm"].get("dram_bytes"), ms=trsm_ms, share_of_step=trsm_ms / float(st.sum(1).mean()),
+                      note=(f"longest kernel of the step ({tag} batch, event-timed alone); algorithmic flops sum(n_t^2 n_u + n_t^2 + "
+                            f"4 n_t n_u) = {trsm_flops:.4g} per launch (no Cholesky term); pipe = fp64 tensor core (DMMA m8n8k4); peak = "
+                            f"{fp64_src}; traffic = dram bytes per launch from {NCU['trsm'].get('file')} vs {8 * float((nts * nts + nts * nus)[okw].sum()) / 1e9:.2f} GB algorithmic")),
+        roofline_chol=dict(bound="tensor", kernel="chol_diag/panel/update chain", achieved=chol_flops / (chol_ms / 1e3) / 1e12,
+                           peak=fp64_peak, unit="TFLOP/s", frac=chol_flops / (chol_ms / 1e3) / 1e12 / fp64_peak, ms=chol_ms,
+                           note=f"sum n_t^3 / 3 = {chol_flops:.4g} flops over the whole factorisation chain (latency-bound dependent launches)"),
+    )
+    is_fp4 = panel.format == "e2m1"
+    gram_peak = probes.get("mxf4" if is_fp4 else "i8")
+    rate = 4.0 if is_fp4 else 2.0
+    ach = work["gram_ops"] / (gram_ms / 1e3) / 1e12
+    rg = dict(bound="tensor", kernel="gram_seg_kernel<%s>" % ("kind::mxf4" if is_fp4 else "kind::i8"), achieved=ach,
+              peak=gram_peak or rate * pk["bf16_tflops"], unit="TOP/s",
+              frac=ach / (gram_peak or rate * pk["bf16_tflops"]), ms=gram_ms,
+              frac_vs_bf16_burst_x=ach / (rate * pk["bf16_tflops"]), frac_vs_bf16_sustained_x=ach / (rate * pk["bf16_tflops_sustained"]),
+              frac_vs_int8_spec_4500=ach / 4500.0, ncu_tensor_pipe_pct=NCU["gram"].get("tensor_pipe_pct"), ncu_file=NCU["gram"].get("file"),
+              traffic=NCU["gram"].get("dram_bytes"),
+              note=(f"algorithmic ops 2 N (n_u n_t + n_t (n_t + 1) / 2) summed over windows = {work['gram_ops']:.4g} per launch; peak = "
+                    f"{'tensor-pipe probe of this instruction kind measured on this box now (gb_probe_peak)' if gram_peak else str(rate) + ' x burst bf16 of MEASURED_PEAKS.json (probe failed)'}; "
+                    f"frac_vs_bf16_*_x = against {rate:g} x the bf16 figures of {pk['source']}"))
+    out["roofline_gram"] = rg
+    out["solve"] = dict(flops_per_step=work["solve_flops"], tflops=work["solve_flops"] / ((chol_ms + trsm_ms) / 1e3) / 1e12)
+    out["dtype"] = ("e2m1 x e2m1 -> f32 (exact integer counts, tcgen05 kind::mxf4)" if is_fp4 else "int8 x int8 -> int32 (tcgen05 kind::i8)") + " + f64 fold/solve"
+    if not with_e2e:
+        batch.close()
+        panel.close()
+        return out
 
-    # ---- e2e path: per-window C-ABI calls with HOST buffers
-    host = torch.empty((n_all, N), dtype=torch.int8, pin_memory=True)
-    host.copy_(geno)
+    # ---- host-buffer legs (N = 1 only) ------------------------------------------------------------------------
+    host5 = torch.empty((n_all, row5), dtype=torch.uint8, pin_memory=True)
+    host5.copy_(d_rows5)
     torch.cuda.synchronize()
-    del geno
+    del d_rows5
+    n_groups = int(os.environ.get("GB_E2E_GROUPS", "6"))
+    panel2 = gb.Panel(ctx, sizes, n_all, "e2m1")
+    ok_u = np.concatenate([np.full(L["u_off"][i + 1] - L["u_off"][i], status[i] == 0) for i in range(len(windows))])
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def chrom_step(rows_ptr):
+        _, _, s2 = panel2.chrom_run_pack5(rows_ptr, n_all, row5, L["t_off"], L["rows_t"], L["u_off"], L["rows_u"], L["z_t"], w,
+                                          n_groups=n_groups, z=z_pin.numpy(), info=i_pin.numpy())
+        return s2
+
+    s2 = chrom_step(host5.data_ptr())
+    eq_chrom = bool(int((s2 == 0).sum()) == n_ok and np.array_equal(z_pin.numpy()[ok_u], z[ok_u]) and
+                    np.array_equal(i_pin.numpy()[ok_u], info[ok_u]))
+    chrom_step(host5.data_ptr())
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        chrom_step(host5.data_ptr())
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    c_h2d = n_all * row5 + (len(L["rows_t"]) + len(L["rows_u"])) * 4 + len(L["z_t"]) * 8 + len(w) * 8
+    c_d2h = n_u_all * 16 + (2 * len(windows) + 3 * n_groups) * 4
+    out["e2e"] = dict(value=n_imputed / e2e_s, unit=UNIT, h2d_bytes_per_step=int(c_h2d), d2h_bytes_per_step=int(c_d2h),
+                      steps=e2e_steps, ms_per_step=e2e_s * 1e3, host_row_bytes=int(row5), equal_to_resident_run=eq_chrom,
+                      note=f"gb_chrom_run_pack5 (C-ABI chromosome driver): pinned HOST ternary panel rows ({row5} B per SNP) -> H2D in "
+                           f"{n_groups} chunks on a copy stream -> expand -> window batches as their rows land -> D2H of z/info; wall clock "
+                           "around the blocking call; results compared bit for bit with the resident run (equal_to_resident_run); the packed rows are a cached packed panel")
+    # cold: the host pack (int8 rows -> ternary rows, CPU threads) inside the timed region
+    g8 = api.unpack5_rows(host5.numpy(), sizes)
+    cold5 = torch.empty((n_all, row5), dtype=torch.uint8, pin_memory=True)
+    t0 = time.perf_counter()
+    api.pack5_rows_host(sizes, g8, is_ascii=False, out=cold5.numpy())
+    pack_s = time.perf_counter() - t0
+    chrom_step(cold5.data_ptr())
+    cold_s = time.perf_counter() - t0
+    out["e2e_cold"] = dict(value=n_imputed / cold_s, unit=UNIT, ms_per_step=cold_s * 1e3, host_pack_ms=pack_s * 1e3,
+                           h2d_bytes_per_step=int(c_h2d), d2h_bytes_per_step=int(c_d2h), steps=1,
+                           note=f"same call with the host-side pack INSIDE the timed region: gb_pack5_rows_host (int8 dosages -> ternary rows, "
+                                f"{os.cpu_count()} CPU threads, {n_all * N / pack_s / 1e9:.2f} GB/s of dosage bytes) + gb_chrom_run_pack5")
+    del cold5
+    # per-window calls on pinned int8 host rows (the seam run_distmix has today)
+    host8 = torch.empty((n_all, N), dtype=torch.int8, pin_memory=True)
+    host8.numpy()[:] = g8
     max_rows = int(max(len(x["measured"]) + len(x["unmeasured"]) for x in windows))
     pipe = gb.Pipe(ctx, sizes, max_rows, depth=3)
-    e2e_steps = max(1, min(args.steps, 3))
-    h2d = d2h = 0
     res_z = [np.zeros(len(x["unmeasured"])) for x in windows]
     res_i = [np.zeros(len(x["unmeasured"])) for x in windows]
+    cnt = dict(h2d=0, d2h=0)
 
-    def e2e_step(count=False):
-        """One pass over the chromosome through the reference-facing per-window call with HOST buffers:
-        gb_pipe_submit (pinned host rows -> H2D -> pack -> Gram -> solve -> D2H) / gb_pipe_wait."""
-        nonlocal h2d, d2h
-        done = 0
+    def pw_step(count=False):
         pending = []
         for wi, x in enumerate(windows):
             a, b = len(x["measured"]), len(x["unmeasured"])
             if a <= 10 or b <= 10:
                 continue
-            m0, u0 = int(pos_in_block[x["measured"][0]]), int(pos_in_block[x["unmeasured"][0]])
-            t = pipe.submit_ptr(host.data_ptr() + m0 * N, a, host.data_ptr() + u0 * N, b, N, False,
-                                z_by_site[x["measured"]], w, res_z[wi], res_i[wi])
-            pending.append(t)
+            m0, u0 = int(L["pos"][x["measured"][0]]), int(L["pos"][x["unmeasured"][0]])
+            pending.append(pipe.submit_ptr(host8.data_ptr() + m0 * N, a, host8.data_ptr() + u0 * N, b, N, False,
+                                           L["z_by_site"][x["measured"]], w, res_z[wi], res_i[wi]))
             if len(pending) >= 3:
                 assert pipe.wait(pending.pop(0)) == 0
-            done += b
             if count:
-                h2d += (a + b) * N + a * 8 + (a + b) * 8 + len(w) * 8
-                d2h += b * 16 + 8
+                cnt["h2d"] += (a + b) * N + a * 8 + (a + b) * 8 + len(w) * 8
+                cnt["d2h"] += b * 16 + 8
         for t in pending:
             assert pipe.wait(t) == 0
-        return done
 
-    e2e_done, e2e_s = 0, 1.0
-    pw_done, pw_s = 0, 1.0
-    c_h2d = c_d2h = 0
-    host_fmt, row2, host_pack_s = os.environ.get("GB_E2E_HOST_FORMAT", "pack5"), 0, 0.0
-    n_groups = int(os.environ.get("GB_E2E_GROUPS", "6"))
+    pw_step()
+    t0 = time.perf_counter()
+    pw_step(count=True)
+    pw_s = time.perf_counter() - t0
+    out["e2e_per_window"] = dict(value=n_imputed / pw_s, unit=UNIT, h2d_bytes_per_step=int(cnt["h2d"]), d2h_bytes_per_step=int(cnt["d2h"]),
+                                 steps=1, ms_per_step=pw_s * 1e3,
+                                 note="per-window gb_pipe_submit / gb_pipe_wait (depth 3) on pinned host int8 rows: one window per call, "
+                                      "8 bits per dosage over PCIe")
+    pipe.close()
+    del host8
+    # the literal seam: gb_run_window_strings on '0'/'1'/'2' strings, one blocking call per window
+    if not args.no_strings:
+        P = len(sizes)
+        offs = np.concatenate([[0], np.cumsum(sizes + 1)])[:-1]            # every population string is NUL-terminated
+        chars = np.zeros((n_all, int((sizes + 1).sum())), np.uint8)
+        col = 0
+        for p_, m in enumerate(sizes):
+            chars[:, offs[p_]:offs[p_] + m] = g8[:, col:col + m] + 48
+            col += m
+        base = chars.ctypes.data
+        st_s, st_done, st_ok = 0.0, 0, True
+        import ctypes as C
+        for wi, x in enumerate(windows):
+            a, b = len(x["measured"]), len(x["unmeasured"])
+            if a <= 10 or b <= 10:
+                continue
+            rows = np.concatenate([L["pos"][x["measured"]], L["pos"][x["unmeasured"]]])
+            ptrs = (base + rows[:, None] * chars.strides[0] + offs[None, :]).astype(np.uint64).ravel()
+            type_ = np.concatenate([np.ones(a, np.int32), np.zeros(b, np.int32)])
+            bpw = np.arange(a + b, dtype=np.int64)
+            zz = np.concatenate([L["z_by_site"][x["measured"]], np.zeros(b)])
+            inf = np.ones(a + b)
+            nt_, nu_ = C.c_int(0), C.c_int(0)
+            wv = np.ascontiguousarray(w, np.float64)
+            t0 = time.perf_counter()
+            rc = ctx.lib.gb_run_window_strings(ctx.h, a + b, type_.ctypes.data, bpw.ctypes.data, zz.ctypes.data, inf.ctypes.data,
+                                               ptrs.ctypes.data, P, sizes.ctypes.data, wv.ctypes.data, 0, 10 ** 12, None,
+                                               C.byref(nt_), C.byref(nu_))
+            st_s += time.perf_counter() - t0
+            lo = int(L["u_off"][wi])
+            st_ok = st_ok and rc == 0 and nt_.value == a and nu_.value == b and np.array_equal(zz[a:], z[lo:lo + b])
+            st_done += b
+        out["e2e_strings"] = dict(value=st_done / st_s, unit=UNIT, steps=1, ms_per_step=st_s * 1e3, equal_to_resident_run=bool(st_ok),
+                                  h2d_bytes_per_step=int(cnt["h2d"]), d2h_bytes_per_step=int(cnt["d2h"]),
+                                  note="gb_run_window_strings, one blocking call per window on NUL-terminated '0'/'1'/'2' strings per population "
+                                       "(what Snp::genotype_vec_ holds, snp.h:109): host concatenation + pinned staging + H2D + pack + window "
+                                       "+ D2H inside the timed region; results compared bit for bit with the resident batch")
+        del chars
+    batch.close()
+    panel.close()
+    panel2.close()
+    return out
+
+
+def bench_genome(env, args, sizes, w):
+    from gauss_b200 import api
+    torch = env.torch
+    single = args.single_process and env.world == 1
+    n_local = args.gpus if single else 1
+    devices = list(range(n_local)) if single else [env.local]
+    n_parts = n_local * env.world
+    t0 = time.time()
+    chroms = genome_chroms(args)
+    layout_s = time.time() - t0
+    g = api.Genome(n_local, sizes, w, devices=devices)
+    for c in chroms:
+        g.add_chromosome(c["n_rows"], c["t_off"], c["rows_t"], c["u_off"], c["rows_u"], c["z_t"], sites=c["sites"])
+    t0 = time.time()
+    g.plan(n_parts, env.rank * n_local)
+    plan_s = time.time() - t0
+    t0 = time.time()
+    g.fill_synthetic(SEED)
+    fill_s = time.time() - t0
+    infos = [g.shard_info(i) for i in range(n_local)]
+    n_imp_local = sum(x["n_imputed"] for x in infos)
+    z = [np.zeros(int(c["u_off"][-1])) for c in chroms]
+    info = [np.zeros(int(c["u_off"][-1])) for c in chroms]
+    status = [np.full(len(c["t_off"]) - 1, -1, np.int32) for c in chroms]
+    for _ in range(args.warmup):
+        g.run(z, info, status)
+    env.barrier()
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    l0 = g.launch_count
+    dev_ms, t0 = 0.0, time.perf_counter()
+    per_gpu = np.zeros(n_local)
+    for _ in range(args.steps):
+        _, _, _, ms = g.run(z, info, status)
+        dev_ms += float(ms.max())
+        per_gpu += ms
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    env.barrier()
+    clocks = sampler.stop()
+    launches = g.launch_count - l0
+    dev_ms_max, wall_ms_max = env.reduce([dev_ms, wall_ms], "MAX")
+    n_imp, launches_all, gram_ops, solve_flops = env.reduce(
+        [n_imp_local, launches, sum(x["gram_ops"] for x in infos), sum(x["solve_flops"] for x in infos)], "SUM")
+    # what this process computed: its windows only (status >= 0)
+    mine_z, mine_i, bad = [], [], 0
+    for c, zz, ii, st in zip(chroms, z, info, status):
+        for wdx in np.where(st >= 0)[0]:
+            a, b = c["u_off"][wdx], c["u_off"][wdx + 1]
+            if st[wdx] == 0:
+                mine_z.append(zz[a:b])
+                mine_i.append(ii[a:b])
+            elif st[wdx] not in (5, 6):
+                bad += 1
+    cks = [u64_checksum(mine_z) , u64_checksum(mine_i)]
+    if env.dist is not None:
+        t = torch.tensor([cks[0] & 0xFFFFFFFF, cks[0] >> 32, cks[1] & 0xFFFFFFFF, cks[1] >> 32, bad], device=env.dev, dtype=torch.int64)
+        env.dist.all_reduce(t)
+        lo0, hi0, lo1, hi1, bad = (int(x) for x in t)
+        cks = [((hi0 << 32) + lo0) & (2 ** 64 - 1), ((hi1 << 32) + lo1) & (2 ** 64 - 1)]
+    out = dict(value=n_imp * args.steps / (dev_ms_max / 1e3), ms_per_step=dev_ms_max / args.steps,
+               wall_ms_per_step=wall_ms_max / args.steps, launches=int(launches_all), clocks=clocks, n_imputed=int(n_imp),
+               genome=dict(layout_s=layout_s, plan_s=plan_s, fill_synthetic_s=fill_s, shards=infos if env.world == 1 else None,
+                           rank0_shard=infos[0], device_ms_per_gpu=(per_gpu / args.steps).tolist(),
+                           gram_tops=gram_ops * args.steps / (dev_ms_max / 1e3) / 1e12,
+                           solve_tflops=solve_flops * args.steps / (dev_ms_max / 1e3) / 1e12,
+                           windows_not_ok=int(bad), result_checksum_u64=dict(z=cks[0], info=cks[1]),
+                           note="result_checksum_u64 = sum of the float64 bit patterns of every OK window's z / info mod 2^64: independent of "
+                                "how windows are placed on GPUs, so it must be the same number at every N",
+                           host_gather="each GPU thread copies its windows' results from pinned staging into the caller's per-chromosome "
+                                       "arrays (inside wall_ms_per_step; the D2H itself is inside the device-timed ms_per_step)"))
+    # ---- e2e: the same job from pinned HOST rows, upload inside the timed region
     if not args.no_e2e:
-        # (a) per-window calls on raw int8 host rows (what a drop-in behind run_distmix sees today)
-        e2e_step()  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
-            pw_done += e2e_step(count=(k == 0))
-        barrier()
-        pw_s = time.perf_counter() - t0
-        # (b) chromosome driver on the 2-bit host panel (packed ONCE on the host, outside the timed region, like a
-        # cached packed panel file): H2D of the pack2 rows in chunks on a copy stream, expansion, the window batches
-        # as their rows land, D2H of z / info -- all inside the timed region, results checked against the resident run
-        host_fmt = os.environ.get("GB_E2E_HOST_FORMAT", "pack5")      # pack5: 1.6 bits per dosage, pack2: 2 bits
-        row2 = gb.api.pack5_row_bytes(sizes) if host_fmt == "pack5" else gb.api.pack2_row_bytes(sizes)
-        host2 = torch.empty((n_all, row2), dtype=torch.uint8, pin_memory=True)
-        t0 = time.perf_counter()
-        (gb.api.pack5_rows_host if host_fmt == "pack5" else gb.api.pack2_rows_host)(
-            sizes, host.numpy(), is_ascii=False, out=host2.numpy())
-        host_pack_s = time.perf_counter() - t0
-        panel2 = gb.Panel(ctx, sizes, n_all, "e2m1")
-        z_pin = torch.empty(int(u_off[-1]), dtype=torch.float64, pin_memory=True)
-        i_pin = torch.empty(int(u_off[-1]), dtype=torch.float64, pin_memory=True)
+        avail = 0
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                avail = int(ln.split()[1]) * 1024
+        row5 = api.pack5_row_bytes(sizes)
+        need = sum(x["resident_rows"] for x in infos) * row5
+        if need > 0.45 * avail / max(1, (env.world if not single else 1)):
+            out["e2e"] = dict(value=None, unit=UNIT, h2d_bytes_per_step=int(need), d2h_bytes_per_step=int(n_imp_local * 16),
+                              note=f"skipped: {need / 1e9:.0f} GB of pinned host rows would not fit this box's {avail / 1e9:.0f} GB of free RAM")
+        else:
+            ctx0 = api.Context(devices[0])
+            bufs = []
+            t0 = time.time()
+            for gi in range(n_local):
+                for ci, c in enumerate(chroms):
+                    for lo, hi in g.resident_ranges(gi, ci):
+                        buf = torch.empty((hi - lo, row5), dtype=torch.uint8, pin_memory=True)
+                        for r0 in range(lo, hi, 262144):
+                            r1 = min(hi, r0 + 262144)
+                            api.synth_pack5_rows(ctx0, SEED, ci, sizes, r1 - r0, sites=c["sites"][r0:r1], out=buf.numpy()[r0 - lo:r1 - lo])
+                        g.set_host_rows(ci, lo, hi - lo, buf.data_ptr(), row5)
+                        bufs.append(buf)
+            host_fill_s = time.time() - t0
+            ctx0.close()
+            z2 = [np.zeros_like(a) for a in z]
+            i2 = [np.zeros_like(a) for a in info]
+            e2e_steps = max(1, min(args.steps, 2))
+            g.upload(wait=False)
+            g.run(z2, i2, status)      # warm-up, also the equality check below
+            eq_up = all(np.array_equal(a, b, equal_nan=True) for a, b in zip(z + info, z2 + i2))
+            env.barrier()
+            up_ms = np.zeros(n_local)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                g.upload(wait=False)
+                g.submit(z2, i2, status)
+                _, up = g.wait()
+                up_ms += up
+            e2e_s = time.perf_counter() - t0
+            env.barrier()
+            e2e_s_max, = env.reduce([e2e_s], "MAX")
+            h2d, = env.reduce([need + sum(len(c["rows_t"]) * 12 + len(c["rows_u"]) * 4 for c in chroms) // max(1, n_parts)], "SUM")
+            out["e2e"] = dict(value=n_imp * e2e_steps / e2e_s_max, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(n_imp * 16),
+                              steps=e2e_steps, ms_per_step=e2e_s_max / e2e_steps * 1e3, upload_ms_per_gpu=(up_ms / e2e_steps).tolist(),
+                              host_rows_fill_s=host_fill_s, equal_to_resident_run=bool(eq_up),
+                              note=f"gb_genome_upload (asynchronous) + gb_genome_submit / gb_genome_wait: every step copies each GPU's ternary panel "
+                                   f"rows ({row5} B per SNP, pinned HOST memory) to the device again, batches start as their rows land, "
+                                   "z / info are written to host arrays; wall clock, max over ranks; results compared bit for bit with the "
+                                   "resident run.  One-shot cost of a genome job; a panel that stays resident across traits pays it once")
+            del bufs
+    g.close()
+    return out, chroms
 
-        def chrom_step():
-            run = panel2.chrom_run_pack5 if host_fmt == "pack5" else panel2.chrom_run_pack2
-            _, _, st = run(host2.data_ptr(), n_all, row2, t_off, rows_t, u_off, rows_u, z_t, w,
-                           n_groups=n_groups, z=z_pin.numpy(), info=i_pin.numpy())
-            return st
 
-        st = chrom_step()  # warm-up (first call also sizes the staging allocation)
-        assert int((st == 0).sum()) == n_ok
-        ok_u = np.concatenate([np.full(u_off[i + 1] - u_off[i], status[i] == 0) for i in range(len(windows))])
-        assert np.array_equal(z_pin.numpy()[ok_u], z[ok_u]) and np.array_equal(i_pin.numpy()[ok_u], info[ok_u]), \
-            "chromosome driver disagrees with the resident batch"
-        chrom_step()
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
-            chrom_step()
-            e2e_done += n_imputed
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        c_h2d = n_all * row2 + (len(rows_t) + len(rows_u)) * 4 + len(z_t) * 8 + len(w) * 8
-        c_d2h = int(u_off[-1]) * 16 + (2 * len(windows) + 3 * n_groups) * 4
+def run_gpu(args):
+    import gauss_b200 as gb
+    env = Env(args)
+    torch = env.torch
+    _, sizes, w = synth.flagged_33kg_pgc2()
+    workload = "genome" if args.workload == "auto" else args.workload
+    ctx = gb.Context(env.local)
+    stream = torch.cuda.Stream(env.dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+    probes = measure_probes(ctx) if env.rank == 0 else {}
+    line = dict(metric=METRIC, unit=UNIT, n_gpus=args.gpus if (args.single_process and env.world == 1) else env.world,
+                steps=args.steps, warmup=args.warmup, higher_is_better=True, vs_baseline=None, data="synthetic")
 
-    # ---- max over ranks
-    t_res = torch.tensor([total_ms, e2e_s * 1e3, pw_s * 1e3], device=dev, dtype=torch.float64)
-    cnt = torch.tensor([float(n_imputed), float(e2e_done), float(pw_done)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_ms_max = float(t_res[0]), float(t_res[1])
-    value = float(cnt[0]) * args.steps / (total_ms_max / 1e3)
-    e2e_value = float(cnt[1]) / (e2e_ms_max / 1e3)
-    pw_value = float(cnt[2]) / (float(t_res[2]) / 1e3)
-
-    if rank == 0:
-        pk = peaks()
-        gram_ms = float(stage_ms[:, 1].mean())
-        achieved = work["gram_ops"] / (gram_ms / 1e3) / 1e12
-        fmt = panel.format
-        # E2M1 panels run kind::mxf4 (FP4, nominally 4 x the bf16 rate), int8 panels kind::i8 (2 x)
-        rate = 4.0 if fmt == "e2m1" else 2.0
-        tensor_peak = rate * pk["bf16_tflops_sustained"]
-        line = dict(
-            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-            ms_per_step=total_ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype=("e2m1 x e2m1 -> f32 (exact integer counts, tcgen05 kind::mxf4)" if fmt == "e2m1"
-                   else "int8 x int8 -> int32 (tcgen05 kind::i8)") + " + f64 fold/solve", data="synthetic",
-            config=workload_config(),
-            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(c_h2d), d2h_bytes_per_step=int(c_d2h),
-                     steps=e2e_steps, ms_per_step=e2e_ms_max / e2e_steps,
-                     host_format=host_fmt, host_row_bytes=int(row2), host_pack_s=host_pack_s,
-                     note=f"gb_chrom_run_{host_fmt} (C-ABI chromosome driver): pinned HOST packed panel rows "
-                          f"({row2} B per SNP; pack5 = 5 dosages per byte, pack2 = 4) -> H2D in {n_groups} "
-                          "chunks on a copy stream -> expand -> window batches as their rows land -> D2H of z/info; "
-                          "wall clock around the blocking calls; results asserted equal to the resident run; the packed "
-                          "rows are made once on the host outside the timed region (cached packed panel)"),
-            e2e_per_window=dict(value=pw_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                                steps=e2e_steps,
-                                note="per-window gb_pipe_submit / gb_pipe_wait (depth 3) on pinned host int8 rows: "
-                                     "the seam run_distmix sees today (one window per call, 8 bits per dosage over PCIe)"),
-            gpu_launches=int(launches),
-            clocks=clocks,
-            roofline=dict(bound="tensor", kernel="gram_seg_kernel", achieved=achieved, peak=tensor_peak,
-                          unit="TFLOP/s", frac=achieved / tensor_peak,
-                          traffic=3.676e9, tensor_pipe_probe_peak=8600.0,
-                          traffic_note=("DRAM bytes per launch of this kernel on this workload (dram__bytes_read.sum + "
-                                        "dram__bytes_write.sum = 2.82 + 0.86 GB, profiles/r01_final_ncu_full.md; one ncu "
-                                        "--set full capture, not re-measured here) vs algorithmic "
-                                        f"{(work['panel_bytes'] / 2 + 1.06e9) / 1e9:.2f} GB (panel nibbles + fp64 output)"),
-                          note=(f"Gram multiply-add TOP/s of the dominant kernel alone (CUDA events); algorithmic ops "
-                                f"2*N*(n_u*n_t+n_t(n_t+1)/2) summed over windows = {work['gram_ops']:.4g} per launch; "
-                                f"peak = {rate:g} x {pk['source']} sustained bf16 ({pk['bf16_tflops_sustained']} TF/s): "
-                                f"the kernel's MMA kind for {fmt} panels nominally runs at {rate:g} x the bf16 rate and "
-                                f"MEASURED_PEAKS.json has no entry for it; against the int8 rate (2 x bf16) the same "
-                                f"number is {achieved / (2.0 * pk['bf16_tflops_sustained']):.3f}; tools/mma_probe.cu measures 8,600 TOP/s for this "
-                                f"MMA kind on this GPU with the tensor pipe alone (no TMA, no epilogue): {achieved / 8600.0:.3f} "
-                                f"of that; the kernel is paced by the TMA feed (192 KB of stages x ~1,200 clk round trip) and "
-                                f"by 21 accumulator hand-offs per tile, see profiles/r01k_summary.md")),
-            stage_ms_serial=float(stage_ms.sum(1).mean()),
-            stage_ms=dict(row_stats=float(stage_ms[:, 0].mean()), gram=gram_ms,
-                          gram_finish=float(stage_ms[:, 2].mean()), cholesky=float(stage_ms[:, 3].mean()),
-                          solve=float(stage_ms[:, 4].mean())),
-            solve=dict(flops_per_step=work["solve_flops"],
-                       tflops=work["solve_flops"] / (float(stage_ms[:, 3:].sum(1).mean()) / 1e3) / 1e12),
-            # the longest kernel of the step is the fp64 triangular solve; its pipe is the fp64 tensor core (DMMA
-            # m8n8k4: 64 FMA/clk/SM measured by tools/dmma_probe.cu = 148 SMs x 128 flop x sm clock)
-            roofline_solve=dict(bound="tensor", kernel="trsm_finalize_kernel",
-                                achieved=work["solve_flops"] / (float(stage_ms[:, 4].mean()) / 1e3) / 1e12,
-                                peak=148 * 128 * clocks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12, unit="TFLOP/s (fp64)",
-                                frac=(work["solve_flops"] / (float(stage_ms[:, 4].mean()) / 1e3) / 1e12) /
-                                     (148 * 128 * clocks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12),
-                                note="algorithmic n_t^3/3 + n_t^2 n_u + ... flops of the whole solve over the trsm kernel's "
-                                     "event-timed duration; ncu: 75 % of the DMMA pipe busy, the rest of the gap is padding "
-                                     "(n_t to 64, n_u to 128) and the dense product with inv(L_ii)"),
-            pack=dict(ms=pack_ms, gbs=2.0 * n_all * N / (pack_ms / 1e3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"]),
-            windows_ok=n_ok, imputed_per_step=n_imputed, panel_gen_s=gen_s, host_affinity=numa_note,
-        )
-        if world == 1 and not args.no_cpu_baseline:
-            s = cpu_sample("reference", n_t_target=400, n_u_sample=96)
-            line["cpu_baseline"] = dict(value=s["value"], unit=UNIT, cores=1, kind=s["kind"], sample=s["sample"])
+    if workload == "genome":
+        try:
+            gout, chroms = bench_genome(env, args, sizes, w)
+        except Exception as e:  # noqa: BLE001
+            if env.world > 1:
+                raise
+            print(f"[bench] genome workload failed ({type(e).__name__}: {e}); falling back to the chr22 workload", file=sys.stderr)
+            workload = "chr22"
+    if workload == "genome":
+        mode = "one process, one host thread per GPU" if (args.single_process and env.world == 1) else "one process per GPU"
+        line.update(value=gout["value"], ms_per_step=gout["ms_per_step"], wall_ms_per_step=gout["wall_ms_per_step"], scaling="strong",
+                    config=genome_config(chroms, line["n_gpus"], mode), gpu_launches=gout["launches"], clocks=gout["clocks"],
+                    imputed_per_step=gout["n_imputed"], genome=gout["genome"], host_affinity=env.numa)
+        if "e2e" in gout:
+            line["e2e"] = gout["e2e"]
+        if env.rank == 0:
+            # kernel-level numbers on one chromosome-22-shaped batch (the round-1 step): per-stage times and rooflines;
+            # at N = 1 also its host-buffer legs and the int8 arm
+            full = env.world == 1 and not args.quick
+            c22 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=full and not args.no_e2e)
+            line["dtype"] = c22["dtype"]
+            for k in ("roofline", "roofline_gram", "roofline_chol", "roofline_expand5", "stage_ms", "stage_ms_serial", "solve"):
+                line[k] = c22[k]
+            line["chr22"] = dict(value=c22["value"], ms_per_step=c22["ms_per_step"], imputed_per_step=c22["n_imputed"],
+                                 gpu_launches=c22["launches"], config=chr22_config(),
+                                 **{k: c22[k] for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings") if k in c22})
+            if full:
+                i8 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=False, fmt="int8", tag="chr22 int8")
+                dz = float(np.nanmax(np.abs(i8["z"] - c22["z"])))
+                line["int8"] = dict(value=i8["value"], ms_per_step=i8["ms_per_step"], dtype=i8["dtype"], stage_ms=i8["stage_ms"],
+                                    roofline_gram=i8["roofline_gram"], max_abs_dz_vs_e2m1=dz,
+                                    note="the same chr22 step on a GB_PANEL_INT8 panel (kind::i8, int32 accumulate): the layout the north star names")
+    elif workload == "chr22":
+        c22 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=not args.no_e2e)
+        tot_ms, = env.reduce([c22["ms_per_step"]], "MAX")
+        n_all, = env.reduce([c22["n_imputed"]], "SUM")
+        line.update(value=n_all / (tot_ms / 1e3), ms_per_step=tot_ms, scaling="weak", dtype=c22["dtype"], config=chr22_config(),
+                    gpu_launches=c22["launches"], clocks=c22["clocks"], imputed_per_step=c22["n_imputed"], host_affinity=env.numa)
+        for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings", "roofline", "roofline_gram", "roofline_chol", "roofline_expand5",
+                  "stage_ms", "stage_ms_serial", "solve"):
+            if k in c22:
+                line[k] = c22[k]
+    elif workload in ("ld5000", "dist1kg"):
+        line.update(bench_small(env, args, ctx, stream, probes, workload))
+    line["probes"] = probes
+    if env.rank == 0:
+        if env.world == 1 and not args.no_cpu_baseline and workload in ("genome", "chr22"):
+            line["cpu_baseline"] = cpu_baseline_one_core(workload, args)
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if env.dist is not None:
+        env.dist.destroy_process_group()
+
+
+def bench_small(env, args, ctx, stream, probes, workload):
+    """BASELINE config 3 (computeLD, 5,000 SNPs, 33KG-shaped) and config 1 (dist() chr22, 1KG-shaped panel)."""
+    import gauss_b200 as gb
+    from gauss_b200 import api
+    torch = env.torch
+    pk = peaks()
+    if workload == "ld5000":
+        _, sizes, w = synth.flagged_33kg_pgc2()
+        n = 5000
+        row5 = api.pack5_row_bytes(sizes)
+        d5 = torch.empty((n, row5), dtype=torch.uint8, device=env.dev)
+        api.synth_pack5_rows_device(ctx, SEED, 0, sizes, n, d5.data_ptr(), row5)
+        panel = gb.Panel(ctx, sizes, n, "e2m1")
+        panel.append_pack5_device_ptr(d5.data_ptr(), n, row5)
+        batch = gb.Batch(panel, [0, n], np.arange(n), None, None, None, w, ld_diag=1.0)
+        for _ in range(args.warmup):
+            batch.run_stage(0), batch.run_stage(1)
+        st = stage_times(env, batch, stream, args.steps, [0, 10, 11])
+        N = float(sizes.sum())
+        ops = 2.0 * N * n * (n + 1) / 2
+        gram_ms, fin_ms = float(st[:, 1].mean()), float(st[:, 2].mean())
+        tot = float(st.sum(1).mean())
+        ach = ops / (gram_ms / 1e3) / 1e12
+        peak = probes.get("mxf4") or 4 * pk["bf16_tflops"]
+        # host-in / host-out call
+        rows5 = torch.empty((n, row5), dtype=torch.uint8, pin_memory=True)
+        rows5.copy_(d5)
+        t0 = time.perf_counter()
+        p2 = gb.Panel(ctx, sizes, n, "e2m1")
+        p2.append_pack5_host(rows5.numpy())
+        cm, rc = p2.window_ld(np.arange(n), w)
+        e2e_s = time.perf_counter() - t0
+        assert rc == 0 and np.array_equal(np.diag(cm), np.ones(n))
+        return dict(metric="computeLD SNP pairs/sec", unit="pairs/s", value=n * (n - 1) / 2 / (tot / 1e3), ms_per_step=tot, scaling="weak",
+                    dtype="e2m1 x e2m1 -> f32 (exact integer counts, tcgen05 kind::mxf4) + f64 mixture epilogue",
+                    config=dict(workload="computeLD (BASELINE config 3): dense 5,000-SNP block, 33KG-shaped panel 21 pops / 32,147 indiv, "
+                                         "PGC2 weights; Gram + mixture epilogue only", windows=1, l2="operands 84 MB + 200 MB output > L2"),
+                    stage_ms=dict(row_stats=float(st[:, 0].mean()), gram=gram_ms, gram_finish=fin_ms),
+                    roofline=dict(bound="tensor", kernel="gram_seg_kernel<kind::mxf4>", achieved=ach, peak=peak, unit="TOP/s", frac=ach / peak,
+                                  traffic=None, note=f"algorithmic ops 2 N n (n + 1) / 2 = {ops:.4g} (symmetric half); peak = tensor-pipe probe"),
+                    e2e=dict(value=n * (n - 1) / 2 / e2e_s, unit="pairs/s", h2d_bytes_per_step=int(n * row5), d2h_bytes_per_step=int(n * n * 8),
+                             note="gb_panel_append_pack5_host + gb_window_ld: ternary host rows in, 5,000 x 5,000 fp64 matrix out (pageable host memory)"),
+                    gpu_launches=3 * args.steps, clocks={})
+    # dist1kg
+    res = {}
+    for name, sz in (("EUR", synth.flagged_1kg("EUR")), ("ALL", np.array([n for _, n, _ in synth.POPS_1KG], np.int32))):
+        L = chr22_batch_inputs(sz)
+        row5 = api.pack5_row_bytes(sz)
+        d5 = torch.empty((L["n_all"], row5), dtype=torch.uint8, device=env.dev)
+        api.synth_pack5_rows_device(ctx, SEED, 21, sz, L["n_all"], d5.data_ptr(), row5, sites=L["sites"])
+        panel = gb.Panel(ctx, sz, L["n_all"], "e2m1")
+        panel.append_pack5_device_ptr(d5.data_ptr(), L["n_all"], row5)
+        batch = gb.Batch(panel, L["t_off"], L["rows_t"], L["u_off"], L["rows_u"], L["z_t"], None)
+        for _ in range(args.warmup):
+            batch.run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            batch.run()
+            z, info, status = batch.fetch()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        n_imp = int(sum(len(x["unmeasured"]) for x in L["windows"] if len(x["measured"]) > 10 and len(x["unmeasured"]) > 10))
+        st = stage_times(env, batch, stream, args.steps, [0, 10, 11, 2, 3])
+        res[name] = dict(individuals=int(sz.sum()), pops=len(sz), value=n_imp / (ms / 1e3), ms_per_step=ms, windows_ok=int((status == 0).sum()),
+                         stage_ms=dict(zip(["row_stats", "gram", "gram_finish", "cholesky", "solve"], [float(x) for x in st.mean(0)])),
+                         gram_tops=batch.work()["gram_ops"] / (float(st[:, 1].mean()) / 1e3) / 1e12)
+        batch.close(), panel.close()
+    return dict(metric="dist imputed SNPs/sec", unit=UNIT, value=res["EUR"]["value"], ms_per_step=res["EUR"]["ms_per_step"], scaling="weak",
+                dtype="e2m1 x e2m1 -> f32 (exact integer counts, pooled segment) + f64 CalCor epilogue / solve",
+                config=dict(workload="dist() chr22 (BASELINE config 1): 36 x 1 Mb windows at the bundled PGC2 positions, 1KG-shaped panel, "
+                                     "study_pop=EUR (503 indiv / 5 pops); `all2504` = every population flagged", windows=36,
+                            l2="panel slice 36 MB (EUR) fits L2"),
+                all2504=res["ALL"], eur=res["EUR"], gpu_launches=0, clocks={})
 
 
 def main():
@@ -548,8 +980,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gauss_b200", choices=["gauss_b200", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "genome", "chr22", "ld5000", "dist1kg"])
+    ap.add_argument("--genome-mb", default="all", help="comma-separated chromosome lengths in Mb (tuning runs); all = hg19")
+    ap.add_argument("--single-process", action="store_true", help="drive all --gpus GPUs from this one process (gb_genome)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="kernel tuning runs: skip the host-buffer leg")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel tuning runs: skip the host-buffer legs")
+    ap.add_argument("--no-strings", action="store_true", help="skip the gb_run_window_strings leg")
+    ap.add_argument("--quick", action="store_true", help="genome workload: skip the chr22 host-buffer legs and the int8 arm")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,6 +94,7 @@ def load_library():
                                      C.POINTER(C.c_int), dblp, dblp, dblp, dblp]),
         "gb_batch_create": (C.c_int, [vp, vp, i64, i64p, i64p, i64p, i64p, dblp, dblp, C.POINTER(Params),
                                       C.POINTER(vp)]),
+        "gb_batch_create_ld": (C.c_int, [vp, vp, i64, i64p, i64p, dblp, C.c_double, C.POINTER(vp)]),
         "gb_batch_destroy": (None, [vp]),
         "gb_batch_run": (C.c_int, [vp]),
         "gb_batch_run_stage": (C.c_int, [vp, C.c_int]),
@@ -107,6 +108,7 @@ def load_library():
         "gb_pack5_row_bytes": (i64, [C.c_int, i32p]),
         "gb_pack5_rows_host": (C.c_int, [C.c_int, i32p, i64, vp, i64, C.c_int, vp, i64]),
         "gb_panel_append_pack5_host": (C.c_int, [vp, i64, vp, i64]),
+        "gb_panel_append_pack5_device": (C.c_int, [vp, i64, vp, i64]),
         "gb_chrom_run_pack5": (C.c_int, [vp, vp, i64, vp, i64, i64, i64p, i64p, i64p, i64p, dblp, dblp,
                                          C.POINTER(Params), C.c_int, dblp, dblp, vp]),
         "gb_pipe_create": (C.c_int, [vp, C.c_int, i32p, i64, C.c_int, C.c_int, C.POINTER(vp)]),
@@ -124,6 +126,8 @@ def load_library():
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int),
                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "gb_genome_upload": (C.c_int, [vp, C.c_int]),
+        "gb_genome_resident_ranges": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, i64p, i64p, C.POINTER(C.c_int)]),
+        "gb_genome_set_host_rows": (C.c_int, [vp, C.c_int, i64, i64, vp, i64]),
         "gb_genome_fill_synthetic": (C.c_int, [vp, C.c_uint64, C.c_int]),
         "gb_genome_submit": (C.c_int, [vp, vp, vp, vp]),
         "gb_genome_wait": (C.c_int, [vp, dblp, dblp]),
@@ -131,6 +135,7 @@ def load_library():
         "gb_genome_launch_count": (i64, [vp]),
         "gb_partition_windows": (C.c_int, [i64, i64p, i64p, i64, C.POINTER(Params), C.c_int, i64p, dblp]),
         "gb_synth_pack5_rows": (C.c_int, [vp, C.c_uint64, C.c_int, i64, i64p, i64, C.c_int, i32p, vp, i64, C.c_int]),
+        "gb_probe_peak": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
         "gb_run_qcat_strings": (C.c_int, [vp, i64, vp, vp, dblp, vp, C.c_int, vp, dblp, C.c_longlong, C.c_longlong,
                                           C.POINTER(Params), C.c_double, dblp, dblp, dblp, C.POINTER(C.c_int),
                                           C.POINTER(C.c_int)]),
@@ -228,6 +233,12 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.gb_ctx_launch_count(self.h))
+
+    def probe_peak(self, which: str, reps: int = 3) -> float:
+        """gb_probe_peak: "i8" / "mxf4" (TOP/s), "fp64" (TFLOP/s), "copy" (GB/s) measured on this GPU now."""
+        v = C.c_double()
+        self.check(self.lib.gb_probe_peak(self.h, {"i8": 0, "mxf4": 1, "fp64": 2, "copy": 3}[which], reps, C.byref(v)))
+        return v.value
 
     def close(self):
         if getattr(self, "h", None):
@@ -350,6 +361,9 @@ class Panel:
         assert rows5.ndim == 2 and rows5.dtype == np.uint8 and rows5.strides[1] == 1
         self.ctx.check(self.ctx.lib.gb_panel_append_pack5_host(self.h, rows5.shape[0], rows5.ctypes.data,
                                                                rows5.strides[0]))
+
+    def append_pack5_device_ptr(self, ptr: int, n_rows: int, row_stride: int):
+        self.ctx.check(self.ctx.lib.gb_panel_append_pack5_device(self.h, int(n_rows), C.c_void_p(ptr), int(row_stride)))
 
     def chrom_run_pack5(self, rows5_ptr: int, n_rows: int, row_stride: int, t_off, rows_t, u_off, rows_u, z_t,
                         pop_wgt=None, params: Params | None = None, n_groups: int = 4, z=None, info=None):
@@ -481,13 +495,23 @@ class Batch:
     """gb_batch: many windows on one resident panel."""
 
     def __init__(self, panel: Panel, t_off, rows_t, u_off, rows_u, z_t, pop_wgt=None,
-                 params: Params | None = None):
+                 params: Params | None = None, ld_diag: float | None = None):
+        """ld_diag given -> computeLD blocks (gb_batch_create_ld): u_off / rows_u / z_t are ignored."""
         self.panel, self.ctx = panel, panel.ctx
-        self.t_off, self.u_off = _i64(t_off), _i64(u_off)
-        self.rows_t, self.rows_u, self.z_t = _i64(rows_t), _i64(rows_u), _f64(z_t)
+        self.t_off = _i64(t_off)
+        self.rows_t = _i64(rows_t)
         self.w = None if pop_wgt is None else _f64(pop_wgt)
         self.n_windows = len(self.t_off) - 1
         h = C.c_void_p()
+        if ld_diag is not None:
+            self.u_off = np.zeros(self.n_windows + 1, np.int64)
+            self.ctx.check(self.ctx.lib.gb_batch_create_ld(self.ctx.h, panel.h, self.n_windows, _ptr(self.t_off),
+                                                           _ptr(self.rows_t), _ptr(self.w), float(ld_diag), C.byref(h)))
+            self.h = h
+            self.ctx._children.add(self)
+            return
+        self.u_off = _i64(u_off)
+        self.rows_u, self.z_t = _i64(rows_u), _f64(z_t)
         self.ctx.check(self.ctx.lib.gb_batch_create(
             self.ctx.h, panel.h, self.n_windows, _ptr(self.t_off), _ptr(self.rows_t), _ptr(self.u_off),
             _ptr(self.rows_u), _ptr(self.z_t), _ptr(self.w), C.byref(params) if params else None, C.byref(h)))
@@ -617,15 +641,27 @@ def unpack5_rows(rows5: np.ndarray, pop_sizes) -> np.ndarray:
     return out
 
 
-def synth_pack5_rows(ctx: "Context", seed: int, chrom: int, pop_sizes, n_rows: int, sites=None, first_site: int = 0):
+def synth_pack5_rows(ctx: "Context", seed: int, chrom: int, pop_sizes, n_rows: int, sites=None, first_site: int = 0,
+                     out: np.ndarray | None = None):
     """gb_synth_pack5_rows into a HOST array [n_rows, pack5_row_bytes] (the device generator of the bench panels)."""
     ps = np.ascontiguousarray(pop_sizes, np.int32)
     rb = pack5_row_bytes(ps)
-    out = np.zeros((n_rows, rb), np.uint8)
+    if out is None:
+        out = np.zeros((n_rows, rb), np.uint8)
+    assert out.shape == (n_rows, rb) and out.dtype == np.uint8 and (out.size == 0 or out.strides == (rb, 1))
     st = None if sites is None else _i64(sites)
     ctx.check(ctx.lib.gb_synth_pack5_rows(ctx.h, int(seed), int(chrom), int(n_rows), _ptr(st), int(first_site), len(ps),
                                           _ptr(ps), out.ctypes.data, rb, 0))
     return out
+
+
+def synth_pack5_rows_device(ctx: "Context", seed: int, chrom: int, pop_sizes, n_rows: int, dev_ptr: int, row_stride: int,
+                            sites=None, first_site: int = 0):
+    """gb_synth_pack5_rows straight into DEVICE memory (dev_ptr: n_rows * row_stride bytes on ctx's GPU)."""
+    ps = np.ascontiguousarray(pop_sizes, np.int32)
+    st = None if sites is None else _i64(sites)
+    ctx.check(ctx.lib.gb_synth_pack5_rows(ctx.h, int(seed), int(chrom), int(n_rows), _ptr(st), int(first_site), len(ps),
+                                          _ptr(ps), C.c_void_p(dev_ptr), int(row_stride), 1))
 
 
 class Genome:
@@ -677,6 +713,16 @@ class Genome:
 
     def upload(self, wait: bool = True):
         self.check(self.lib.gb_genome_upload(self.h, int(bool(wait))))
+
+    def resident_ranges(self, gpu: int, chrom: int):
+        """[(lo, hi)] panel rows of `chrom` GPU `gpu` keeps resident (what a feeder has to supply)."""
+        lo, hi = np.zeros(64, np.int64), np.zeros(64, np.int64)
+        n = C.c_int()
+        self.check(self.lib.gb_genome_resident_ranges(self.h, gpu, chrom, 64, _ptr(lo), _ptr(hi), C.byref(n)))
+        return [(int(lo[i]), int(hi[i])) for i in range(min(n.value, 64))]
+
+    def set_host_rows(self, chrom: int, row_lo: int, n_rows: int, ptr: int, row_stride: int):
+        self.check(self.lib.gb_genome_set_host_rows(self.h, chrom, int(row_lo), int(n_rows), C.c_void_p(ptr), int(row_stride)))
 
     def fill_synthetic(self, seed: int, wait: bool = True):
         self.check(self.lib.gb_genome_fill_synthetic(self.h, int(seed), int(bool(wait))))

@@ -956,6 +956,16 @@ int gb_batch_create(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const int64
                                false, out);
 }
 
+// computeLD() blocks as a resident batch (one n x n correlation matrix per "window", diagonal forced to `diag`,
+// computeLD.cpp:95-116): lets a caller run / time the Gram + epilogue stages alone (BASELINE config 3).
+int gb_batch_create_ld(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const int64_t* t_off, const int64_t* rows_t,
+                       const double* pop_wgt, double diag, gb_batch** out) {
+  gb_params p;
+  gb_params_default(&p);
+  return create_batch_internal(ctx, panel, n_windows, t_off, rows_t, nullptr, nullptr, nullptr, pop_wgt, &p, true, false, out,
+                               false, diag);
+}
+
 void gb_batch_destroy(gb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
@@ -1448,6 +1458,24 @@ static int append_packed_host(gb_panel* p, int64_t n_rows, const void* rows_p, i
 
 int gb_panel_append_pack5_host(gb_panel* p, int64_t n_rows, const void* rows5, int64_t row_stride) {
   return append_packed_host(p, n_rows, rows5, row_stride, 5);
+}
+
+// Same rows already in DEVICE memory (a resident ternary panel, gb_synth_pack5_rows): the expansion kernel alone.
+int gb_panel_append_pack5_device(gb_panel* p, int64_t n_rows, const void* dev_rows5, int64_t row_stride) {
+  if (!p || n_rows < 0 || (!dev_rows5 && n_rows > 0)) {
+    if (p) p->ctx->err = "bad append arguments";
+    return GB_ERR_BAD_ARG;
+  }
+  Ctx* ctx = p->ctx;
+  if (p->format != GB_PANEL_E2M1 || row_stride < p->pack5_row_bytes || p->n_rows + n_rows > p->capacity) {
+    ctx->err = "pack5 rows need an E2M1 panel with room for them and a row stride of at least gb_pack5_row_bytes()";
+    return GB_ERR_BAD_ARG;
+  }
+  int rc = check_device(ctx);
+  if (rc) return rc;
+  if ((rc = launch_expand5(ctx, p, dev_rows5, row_stride, p->n_rows, n_rows))) return rc;
+  p->n_rows += n_rows;
+  return GB_OK;
 }
 
 int gb_panel_append_pack2_host(gb_panel* p, int64_t n_rows, const void* rows2, int64_t row_stride) {

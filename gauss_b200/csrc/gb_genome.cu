@@ -83,10 +83,15 @@ struct RowRange {
   int64_t issued = 0;         // rows [lo, issued) have been uploaded / generated (upload cursor)
 };
 
+struct HostPiece {            // ternary HOST rows [lo, hi) of a chromosome
+  int64_t lo = 0, hi = 0;
+  const uint8_t* ptr = nullptr;
+  int64_t stride = 0;
+};
+
 struct Chrom {
   int64_t n_rows = 0;
-  const uint8_t* host_rows5 = nullptr;
-  int64_t row_stride = 0;
+  std::vector<HostPiece> pieces;
   int64_t n_windows = 0;
   std::vector<int64_t> t_off, u_off, rows_t, rows_u, sites;
   std::vector<double> z_t;
@@ -447,6 +452,35 @@ int shard_plan(gb_genome* g, Shard* sh) {
   return GB_OK;
 }
 
+// Rows [a, b) of a chromosome from the caller's HOST pieces to `dst` (device, row5 bytes apart) on the copy stream.
+int copy_host_rows(gb_genome* g, Shard* sh, const Chrom& ch, int64_t a, int64_t b, uint8_t* dst) {
+  while (a < b) {
+    const HostPiece* pc = nullptr;
+    for (const HostPiece& x : ch.pieces)
+      if (a >= x.lo && a < x.hi) {
+        pc = &x;
+        break;
+      }
+    if (!pc) {
+      sh->ctx->err = "no host rows were given for panel row " + std::to_string(a);
+      return GB_ERR_BAD_ARG;
+    }
+    const int64_t n = std::min(b, pc->hi) - a;
+    const uint8_t* src = pc->ptr + (size_t)(a - pc->lo) * (size_t)pc->stride;
+    cudaError_t e = pc->stride == g->row5
+                        ? cudaMemcpyAsync(dst, src, (size_t)n * (size_t)g->row5, cudaMemcpyHostToDevice, sh->copy)
+                        : cudaMemcpy2DAsync(dst, (size_t)g->row5, src, (size_t)pc->stride, (size_t)g->row5, (size_t)n,
+                                            cudaMemcpyHostToDevice, sh->copy);
+    if (e != cudaSuccess) {
+      sh->ctx->err = std::string("host -> device copy of panel rows: ") + cudaGetErrorString(e);
+      return GB_ERR_CUDA;
+    }
+    dst += (size_t)n * (size_t)g->row5;
+    a += n;
+  }
+  return GB_OK;
+}
+
 // ---- rows: upload from the host, or synthetic fill, segment by segment --------------------------------------------
 // Issues, on the copy stream, whatever is still missing of the rows segment s touches and records s.landed behind it.
 // E2M1 residency: the ternary rows pass through two staging chunks and are expanded into the resident panel.
@@ -468,13 +502,8 @@ int shard_rows_for_segment(gb_genome* g, Shard* sh, Segment& s, bool synthetic) 
         if (synthetic) {
           rc = launch_synth_pack5(ctx, dst, g->row5, b - a, ch.sites.empty() ? nullptr : sh->d_sites + pos, a, g->n_pops,
                                   sh->panels[0]->d_pop_sizes, sh->panels[0]->d_boff5, g->row5, g->synth_seed, s.chrom);
-        } else if (ch.row_stride == g->row5) {
-          if (cudaMemcpyAsync(dst, ch.host_rows5 + (size_t)a * (size_t)ch.row_stride, (size_t)(b - a) * (size_t)g->row5,
-                              cudaMemcpyHostToDevice, sh->copy) != cudaSuccess) rc = GB_ERR_CUDA;
-        } else if (cudaMemcpy2DAsync(dst, (size_t)g->row5, ch.host_rows5 + (size_t)a * (size_t)ch.row_stride,
-                                     (size_t)ch.row_stride, (size_t)g->row5, (size_t)(b - a), cudaMemcpyHostToDevice,
-                                     sh->copy) != cudaSuccess) {
-          rc = GB_ERR_CUDA;
+        } else {
+          rc = copy_host_rows(g, sh, ch, a, b, dst);
         }
       } else {
         for (int64_t r0 = a; r0 < b && !rc; r0 += sh->chunk_rows) {
@@ -485,10 +514,8 @@ int shard_rows_for_segment(gb_genome* g, Shard* sh, Segment& s, bool synthetic) 
           if (synthetic) {
             rc = launch_synth_pack5(ctx, stg, g->row5, n, ch.sites.empty() ? nullptr : sh->d_sites + res.res + (r0 - res.lo), r0,
                                     g->n_pops, sh->panels[0]->d_pop_sizes, sh->panels[0]->d_boff5, g->row5, g->synth_seed, s.chrom);
-          } else if (cudaMemcpy2DAsync(stg, (size_t)g->row5, ch.host_rows5 + (size_t)r0 * (size_t)ch.row_stride,
-                                       (size_t)ch.row_stride, (size_t)g->row5, (size_t)n, cudaMemcpyHostToDevice,
-                                       sh->copy) != cudaSuccess) {
-            rc = GB_ERR_CUDA;
+          } else {
+            rc = copy_host_rows(g, sh, ch, r0, r0 + n, stg);
           }
           if (!rc) rc = launch_expand5(ctx, sh->panels[0], stg, g->row5, res.res + (r0 - res.lo), n);
         }
@@ -748,8 +775,7 @@ int gb_genome_add_chromosome(gb_genome* g, int64_t n_rows, const void* host_rows
   }
   Chrom c;
   c.n_rows = n_rows;
-  c.host_rows5 = static_cast<const uint8_t*>(host_rows5);
-  c.row_stride = row_stride;
+  if (host_rows5 && n_rows > 0) c.pieces.push_back(HostPiece{0, n_rows, static_cast<const uint8_t*>(host_rows5), row_stride});
   c.n_windows = n_windows;
   c.t_off.assign(t_off, t_off + n_windows + 1);
   c.u_off.assign(u_off, u_off + n_windows + 1);
@@ -848,14 +874,34 @@ static int rows_cmd(gb_genome* g, int cmd, int wait) {
   return GB_OK;
 }
 
-int gb_genome_upload(gb_genome* g, int wait) {
-  if (g)
-    for (const Chrom& c : g->chroms)
-      if (!c.host_rows5 && c.n_rows > 0) {
-        g->err = "a chromosome was added without host rows";
-        return GB_ERR_BAD_ARG;
-      }
-  return rows_cmd(g, CMD_UPLOAD, wait);
+int gb_genome_upload(gb_genome* g, int wait) { return rows_cmd(g, CMD_UPLOAD, wait); }
+
+int gb_genome_set_host_rows(gb_genome* g, int chrom, int64_t row_lo, int64_t n_rows, const void* host_rows5, int64_t row_stride) {
+  if (!g || chrom < 0 || chrom >= (int)g->chroms.size() || row_lo < 0 || n_rows < 0 || !host_rows5 || row_stride < g->row5 ||
+      row_lo + n_rows > g->chroms[(size_t)chrom].n_rows) {
+    if (g) g->err = "bad host row piece";
+    return GB_ERR_BAD_ARG;
+  }
+  int rc0 = wait_all(g);
+  if (rc0) return rc0;
+  Chrom& c = g->chroms[(size_t)chrom];
+  // a new piece replaces whatever it overlaps
+  c.pieces.erase(std::remove_if(c.pieces.begin(), c.pieces.end(),
+                                [&](const HostPiece& x) { return x.lo < row_lo + n_rows && row_lo < x.hi; }),
+                 c.pieces.end());
+  if (n_rows > 0) c.pieces.push_back(HostPiece{row_lo, row_lo + n_rows, static_cast<const uint8_t*>(host_rows5), row_stride});
+  return GB_OK;
+}
+
+int gb_genome_resident_ranges(const gb_genome* g, int gpu, int chrom, int max_ranges, int64_t* lo, int64_t* hi, int* n_ranges) {
+  if (!g || !g->planned || gpu < 0 || gpu >= g->n_gpus || chrom < 0 || chrom >= (int)g->chroms.size() || !n_ranges) return GB_ERR_BAD_ARG;
+  const std::vector<RowRange>& v = g->shards[(size_t)gpu]->resident[(size_t)chrom];
+  *n_ranges = (int)v.size();
+  for (int i = 0; i < (int)v.size() && i < max_ranges; i++) {
+    if (lo) lo[i] = v[(size_t)i].lo;
+    if (hi) hi[i] = v[(size_t)i].hi;
+  }
+  return GB_OK;
 }
 
 int gb_genome_fill_synthetic(gb_genome* g, uint64_t seed, int wait) {

@@ -145,91 +145,125 @@ expand2_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int8_
 // Ternary host rows ("pack5": five dosages per byte, byte = d0 + 3 d1 + 9 d2 + 27 d3 + 81 d4, 1.6 bits per dosage;
 // population p starts at byte boff5[p], blocks padded to 4 bytes) -> E2M1 nibbles plus per-population sum x,
 // sum x^2.  A dosage in {0,1,2} has log2(3) = 1.58 bits of information, so this is within 1 % of the densest
-// fixed-width code and takes another fifth off what crosses PCIe after pack2.  One CTA per row, warp w takes
-// populations w, w+8, ...: a lane decodes one 32-bit word (4 bytes = 20 dosages) through two 256-entry tables into
-// five 32-bit shared-memory stores of one dosage per byte (lane stride 5 words: conflict-free), then the block is
-// re-packed eight dosages per 32-bit global store, coalesced.  Bytes 243..255 are not codes (flagged).
+// fixed-width code and takes another fifth off what crosses PCIe after pack2.  It is also the format panel rows are
+// kept RESIDENT in when a whole genome sits on one GPU (gb_genome), so this kernel runs once per batch of windows
+// and has to stream: 6.5 KB in and 16.7 KB out per row of the 33KG shape.
+//
+// Work item = 8 input words (32 bytes = 160 dosages) of one population -> 20 output words (80 bytes = 5 x 16 B,
+// 16-byte aligned because population blocks start on 128-dosage boundaries), all in registers: one shared-memory
+// table lookup per byte (five nibbles = 20 bits, the number of ones and twos, an invalid flag) and static shifts.
+// A CTA takes ROWS_PER_CTA consecutive rows so the table is built once per ~100 KB of traffic.  Bytes 243..255 are
+// not codes, and digits past a population's size must be zero (the host packer writes them so): both are flagged.
+constexpr int EXP5_ROWS_PER_CTA = 8;
 __global__ void __launch_bounds__(256)
 expand5_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int8_t* __restrict__ dst, int k_elems,
-                    int k_stride, long long row0, int n_pops, const int* __restrict__ pop_sizes,
+                    int k_stride, long long row0, long long n_rows, int n_pops, const int* __restrict__ pop_sizes,
                     const int* __restrict__ koff, const int* __restrict__ boff5, int32_t* __restrict__ sx,
                     int32_t* __restrict__ sxx, long long stat_ld, int* flags, int seg_align) {
-  extern __shared__ __align__(16) uint8_t dos[];   // population p at koff[p] + 32 p (32 bytes of slack behind each block)
-  __shared__ uint32_t lut_a[256];                  // digits 0..3, one per byte
-  __shared__ uint32_t lut_b[256];                  // digit 4 | #ones << 8 | #twos << 12 | invalid << 31
-  const long long row = blockIdx.x;
-  const uint8_t* s = src + row * src_stride;
+  __shared__ uint32_t lut[256];          // nibbles (digit << 1) of the five digits | ones << 20 | twos << 24 | invalid << 31
+  __shared__ int item0[P_MAX + 1];       // first work item of each population
+  __shared__ int cnt[2 * P_MAX];         // per population: ones, twos of the current row
   const int tid = threadIdx.x;
   {
-    uint32_t va = 0, vb = 0x80000000u;
+    uint32_t v = 0x80000000u;
     if (tid < 243) {
-      int b = tid, ones = 0, twos = 0, dg[5];
+      int b = tid, ones = 0, twos = 0;
+      v = 0;
 #pragma unroll
-      for (int q = 0; q < 5; q++) { dg[q] = b % 3; b /= 3; ones += dg[q] == 1; twos += dg[q] == 2; }
-      va = (uint32_t)dg[0] | ((uint32_t)dg[1] << 8) | ((uint32_t)dg[2] << 16) | ((uint32_t)dg[3] << 24);
-      vb = (uint32_t)dg[4] | ((uint32_t)ones << 8) | ((uint32_t)twos << 12);
+      for (int q = 0; q < 5; q++) {
+        const int d = b % 3;
+        b /= 3;
+        ones += d == 1;
+        twos += d == 2;
+        v |= (uint32_t)(d << 1) << (4 * q);
+      }
+      v |= ((uint32_t)ones << 20) | ((uint32_t)twos << 24);
     }
-    lut_a[tid] = va;
-    lut_b[tid] = vb;
+    lut[tid] = v;
   }
-  const int smem_bytes = k_elems + 32 * n_pops;
-  for (int j = tid * 16; j < smem_bytes; j += 256 * 16) *reinterpret_cast<uint4*>(dos + j) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    int it = 0;
+    for (int p = 0; p < n_pops; p++) {
+      item0[p] = it;
+      const int kp = (pop_sizes[p] + seg_align - 1) / seg_align * seg_align;
+      it += (kp + 159) / 160;            // items cover the whole padded block (the padding is written as zeros)
+    }
+    item0[n_pops] = it;
+  }
   __syncthreads();
+  const int n_items = item0[n_pops];
   uint32_t bad = 0;
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int p = warp; p < n_pops; p += 8) {
-    const int m = pop_sizes[p];
-    const int nwords = ((m + 4) / 5 + 3) >> 2;
-    const uint32_t* sp = reinterpret_cast<const uint32_t*>(s + boff5[p]);
-    uint32_t* dp = reinterpret_cast<uint32_t*>(dos + koff[p] + 32 * p);
-    int ones = 0, twos = 0;
-    for (int j = lane; j < nwords; j += 32) {
-      const uint32_t w = sp[j];
-      const uint32_t a0 = lut_a[w & 255], a1 = lut_a[(w >> 8) & 255], a2 = lut_a[(w >> 16) & 255], a3 = lut_a[w >> 24];
-      const uint32_t b0 = lut_b[w & 255], b1 = lut_b[(w >> 8) & 255], b2 = lut_b[(w >> 16) & 255], b3 = lut_b[w >> 24];
-      bad |= (b0 | b1 | b2 | b3) & 0x80000000u;
-      ones += ((b0 >> 8) & 7) + ((b1 >> 8) & 7) + ((b2 >> 8) & 7) + ((b3 >> 8) & 7);
-      twos += ((b0 >> 12) & 7) + ((b1 >> 12) & 7) + ((b2 >> 12) & 7) + ((b3 >> 12) & 7);
-      uint32_t* o = dp + 5 * j;              // 20 dosages, one per byte; the slack takes what runs past the block
-      o[0] = a0;
-      o[1] = (b0 & 3u) | (a1 << 8);
-      o[2] = (a1 >> 24) | ((b1 & 3u) << 8) | (a2 << 16);
-      o[3] = (a2 >> 16) | ((b2 & 3u) << 16) | (a3 << 24);
-      o[4] = (a3 >> 8) | ((b3 & 3u) << 24);
-    }
+  const long long r_begin = (long long)blockIdx.x * EXP5_ROWS_PER_CTA;
+  const long long r_end = r_begin + EXP5_ROWS_PER_CTA < n_rows ? r_begin + EXP5_ROWS_PER_CTA : n_rows;
+  for (long long row = r_begin; row < r_end; row++) {
+    if (tid < 2 * n_pops) cnt[tid] = 0;
+    __syncthreads();
+    const uint8_t* s = src + row * src_stride;
+    uint32_t* drow = reinterpret_cast<uint32_t*>(dst + (row0 + row) * (long long)k_stride);
+    for (int it = tid; it < n_items; it += 256) {
+      int p = 0;
+      while (item0[p + 1] <= it) p++;
+      const int j = it - item0[p];
+      const int m = pop_sizes[p];
+      const int nbytes = (m + 4) / 5;                      // code bytes of the block
+      const int nwords = (nbytes + 3) >> 2;
+      const int kp = (m + seg_align - 1) / seg_align * seg_align;
+      const uint32_t* sp = reinterpret_cast<const uint32_t*>(s + boff5[p]) + 8 * j;
+      uint32_t w[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ones += __shfl_xor_sync(0xffffffffu, ones, o);
-      twos += __shfl_xor_sync(0xffffffffu, twos, o);
-    }
-    __syncwarp();
-    // digits past the population's size must be zero (the host packer writes them so)
-    const int kp = (m + seg_align - 1) / seg_align * seg_align;
-    const uint8_t* dpb = dos + koff[p] + 32 * p;
-    for (int c = m + lane; c < nwords * 20; c += 32) bad |= dpb[c];
-    // re-pack: eight dosages -> eight nibbles (E2M1 code = dosage << 1), columns m .. kp stay zero
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst + (row0 + row) * (long long)k_stride) + (koff[p] >> 3);
-    for (int j = lane; j < (kp >> 3); j += 32) {
-      uint2 v = *reinterpret_cast<const uint2*>(dpb + 8 * j);
-      if (8 * j + 8 > m) {                   // the word that straddles the population's end
+      for (int q = 0; q < 8; q++) w[q] = (8 * j + q < nwords) ? __ldg(sp + q) : 0u;
+      // 32 bytes -> 32 x 20 bits of nibbles = 20 output words
+      uint32_t out[20];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          if (8 * j + q >= m) v.x &= ~(0xFFu << (8 * q));
-          if (8 * j + 4 + q >= m) v.y &= ~(0xFFu << (8 * q));
+      for (int q = 0; q < 20; q++) out[q] = 0;
+      int ones = 0, twos = 0;
+#pragma unroll
+      for (int bq = 0; bq < 32; bq++) {
+        const uint32_t e = lut[(w[bq >> 2] >> (8 * (bq & 3))) & 255u];
+        bad |= e & 0x80000000u;
+        ones += (e >> 20) & 7;
+        twos += (e >> 24) & 7;
+        const uint32_t nib = e & 0xFFFFFu;
+        const int bit = 20 * bq;                           // static: the loops are fully unrolled
+        out[bit >> 5] |= nib << (bit & 31);
+        if ((bit & 31) > 12) out[(bit >> 5) + 1] |= nib >> (32 - (bit & 31));
+      }
+      // digits at or past the population's size must be zero
+      const int d0 = 160 * j;
+      if (d0 + 160 > m) {
+#pragma unroll
+        for (int q = 0; q < 20; q++) {
+          const int first = d0 + 8 * q;                    // dosage index of the word's lowest nibble
+          if (first + 8 > m) {
+            const uint32_t keep = first >= m ? 0u : (0xFFFFFFFFu >> (4 * (first + 8 - m)));
+            bad |= out[q] & ~keep;
+            out[q] &= keep;
+          }
         }
       }
-      uint32_t out = 0;
+      uint4* o = reinterpret_cast<uint4*>(drow + (koff[p] >> 3) + 20 * j);
+      const int words_left = (kp >> 3) - 20 * j;           // output words of the padded block from here on (multiple of 4)
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        out |= ((v.x >> (8 * q)) & 3u) << (4 * q + 1);
-        out |= ((v.y >> (8 * q)) & 3u) << (4 * (q + 4) + 1);
+      for (int q = 0; q < 5; q++)
+        if (4 * q < words_left) o[q] = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+      if (ones | twos) {
+        atomicAdd(&cnt[2 * p], ones);
+        atomicAdd(&cnt[2 * p + 1], twos);
       }
-      d[j] = out;
     }
-    if (lane == 0) {
-      sx[(long long)p * stat_ld + row0 + row] = ones + 2 * twos;
-      sxx[(long long)p * stat_ld + row0 + row] = ones + 4 * twos;
+    // tail between the last population block and the row stride
+    {
+      const int k_end = koff[n_pops - 1] + (pop_sizes[n_pops - 1] + seg_align - 1) / seg_align * seg_align;
+      for (int jb = (k_end >> 1) + tid * 4; jb < k_stride; jb += 256 * 4)
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(drow) + jb) = 0u;
     }
+    __syncthreads();
+    if (tid < n_pops) {
+      const int ones = cnt[2 * tid], twos = cnt[2 * tid + 1];
+      sx[(long long)tid * stat_ld + row0 + row] = ones + 2 * twos;
+      sxx[(long long)tid * stat_ld + row0 + row] = ones + 4 * twos;
+    }
+    __syncthreads();
   }
   if (bad) atomicOr(flags, 1);
 }
@@ -328,16 +362,11 @@ int launch_expand5(Ctx* ctx, Panel* panel, const void* dev_src, int64_t src_stri
     ctx->err = "pack5 rows must be 4-byte aligned (use gb_pack5_row_bytes() as the row stride)";
     return GB_ERR_BAD_ARG;
   }
-  const size_t smem = ((size_t)panel->k_elems + 32 * (size_t)panel->n_pops + 15) / 16 * 16;
-  if (smem > 200 * 1024) {
-    ctx->err = "panel row too long for expand5_rows_kernel";
-    return GB_ERR_UNSUPPORTED;
-  }
-  GB_CUDA(cudaFuncSetAttribute(expand5_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  expand5_rows_kernel<<<(unsigned)n_rows, 256, smem, ctx->stream>>>(
-      static_cast<const uint8_t*>(dev_src), src_stride, panel->d_rows, panel->k_elems, panel->k_stride, row0, panel->n_pops,
-      panel->d_pop_sizes, panel->d_koff, panel->d_boff5, panel->d_sx, panel->d_sxx, panel->capacity, panel->d_flags,
-      panel->seg_align);
+  const long long n_ctas = (n_rows + EXP5_ROWS_PER_CTA - 1) / EXP5_ROWS_PER_CTA;
+  expand5_rows_kernel<<<(unsigned)n_ctas, 256, 0, ctx->stream>>>(
+      static_cast<const uint8_t*>(dev_src), src_stride, panel->d_rows, panel->k_elems, panel->k_stride, row0, n_rows,
+      panel->n_pops, panel->d_pop_sizes, panel->d_koff, panel->d_boff5, panel->d_sx, panel->d_sxx, panel->capacity,
+      panel->d_flags, panel->seg_align);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

@@ -182,6 +182,12 @@ GB_API int gb_batch_create(gb_ctx *ctx, gb_panel *panel, int64_t n_windows, cons
                     const int64_t *rows_t, const int64_t *u_off, const int64_t *rows_u,
                     const double *z_t, const double *pop_wgt, const gb_params *params,
                     gb_batch **out);
+/* computeLD() blocks as a resident batch: window w = the n_w x n_w correlation matrix of rows_t[t_off[w] .. t_off[w+1])
+ * (computeLD.cpp:95-116, diagonal forced to `diag`); only stages 0 and 1 of gb_batch_run_stage apply.  For callers that
+ * keep the matrices on the device or time the Gram + mixture epilogue alone (BASELINE config 3); gb_window_ld is the
+ * host-in / host-out form. */
+GB_API int gb_batch_create_ld(gb_ctx *ctx, gb_panel *panel, int64_t n_windows, const int64_t *t_off,
+                       const int64_t *rows_t, const double *pop_wgt, double diag, gb_batch **out);
 GB_API void gb_batch_destroy(gb_batch *batch);
 /* Enqueue every kernel of the batch on the ctx stream (asynchronous). */
 GB_API int gb_batch_run(gb_batch *batch);
@@ -227,6 +233,8 @@ GB_API int64_t gb_pack5_row_bytes(int n_pops, const int *pop_sizes);
 GB_API int gb_pack5_rows_host(int n_pops, const int *pop_sizes, int64_t n_rows, const void *rows,
                        int64_t row_stride, int is_ascii, void *out, int64_t out_stride);
 GB_API int gb_panel_append_pack5_host(gb_panel *panel, int64_t n_rows, const void *rows5, int64_t row_stride);
+/* ... and when the ternary rows already sit in DEVICE memory of the panel's GPU (expansion kernel only). */
+GB_API int gb_panel_append_pack5_device(gb_panel *panel, int64_t n_rows, const void *dev_rows5, int64_t row_stride);
 GB_API int gb_chrom_run_pack5(gb_ctx *ctx, gb_panel *panel, int64_t n_rows, const void *host_rows5,
                        int64_t row_stride, int64_t n_windows, const int64_t *t_off, const int64_t *rows_t,
                        const int64_t *u_off, const int64_t *rows_u, const double *z_t, const double *pop_wgt,
@@ -272,6 +280,13 @@ GB_API int gb_genome_num_chromosomes(const gb_genome *g);
 GB_API int gb_genome_shard_info(const gb_genome *g, int gpu, int64_t *first_window, int64_t *n_windows,
                          int64_t *resident_rows, int64_t *n_batches, int64_t *n_imputed, int *e2m1_resident,
                          double *gram_ops, double *solve_flops);
+/* The panel rows GPU `gpu` keeps resident of chromosome `chrom` (merged [lo, hi) ranges: the measured rows of its windows
+ * with their wings, and the unmeasured rows), so that a feeder only has to read those; and the way to hand them over
+ * piece by piece instead of as one buffer per chromosome (a new piece replaces any piece it overlaps). */
+GB_API int gb_genome_resident_ranges(const gb_genome *g, int gpu, int chrom, int max_ranges, int64_t *lo, int64_t *hi,
+                              int *n_ranges);
+GB_API int gb_genome_set_host_rows(gb_genome *g, int chrom, int64_t row_lo, int64_t n_rows, const void *host_rows5,
+                            int64_t row_stride);
 GB_API int gb_genome_upload(gb_genome *g, int wait);
 GB_API int gb_genome_submit(gb_genome *g, double *const *z_u, double *const *info_u, int *const *window_status);
 GB_API int gb_genome_wait(gb_genome *g, double *gpu_ms, double *upload_ms);
@@ -296,6 +311,13 @@ GB_API int gb_synth_pack5_rows(gb_ctx *ctx, uint64_t seed, int chrom, int64_t n_
                         int out_is_device);
 /* Fill every GPU's resident rows with that generator instead of uploading them (chromosome index = `chrom`). */
 GB_API int gb_genome_fill_synthetic(gb_genome *g, uint64_t seed, int wait);
+
+/* ---- pipe-peak probes (roofline denominators measured on the bench box at bench time) ---- */
+/* MEASURED_PEAKS.json has HBM GB/s and dense bf16 TF/s only.  which: 0 = tcgen05.mma kind::i8 128x128x32 (TOP/s),
+ * 1 = tcgen05.mma kind::mxf4 128x128x64 (TOP/s), 2 = fp64 mma.sync m8n8k4 (TFLOP/s), 3 = device copy (GB/s, read +
+ * write).  Each keeps that one pipe busy on every SM with nothing else going on (no TMA, no epilogue); best of `reps`
+ * event-timed launches. */
+GB_API int gb_probe_peak(gb_ctx *ctx, int which, int reps, double *value);
 
 /* ---- pipelined single windows, host in / host out ---------------------------------------------- */
 /* What a genome loop over dist()/distmix() calls (dist.cpp:63-75 runs one window per call): the

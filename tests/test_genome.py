@@ -73,11 +73,18 @@ def run_genome(chroms, n_gpus=1, n_parts=None, first_part=0, host_rows=None, env
                 os.environ[k] = v
     for i, c in enumerate(chroms):
         kw = {}
-        if host_rows is not None:
+        if host_rows is not None and i != 1:
             kw = dict(rows5_ptr=host_rows[i].ctypes.data, row_stride=host_rows[i].strides[0])
         g.add_chromosome(c["n_rows"], c["t_off"], c["rows_t"], c["u_off"], c["rows_u"], c["z_t"], sites=c["sites"], **kw)
     g.plan(n_parts or n_gpus, first_part)
     if host_rows is not None:
+        # chromosome 1: handed over piece by piece, only the rows the shard keeps resident (what a feeder would read)
+        keep = []
+        for gi in range(n_gpus):
+            for lo, hi in g.resident_ranges(gi, 1):
+                piece = np.ascontiguousarray(host_rows[1][lo:hi])
+                keep.append(piece)
+                g.set_host_rows(1, lo, hi - lo, piece.ctypes.data, piece.strides[0])
         g.upload(wait=False)     # asynchronous: the batches wait for their own rows
     else:
         g.fill_synthetic(SEED)
