@@ -126,6 +126,7 @@ def load_library():
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int),
                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "gb_genome_upload": (C.c_int, [vp, C.c_int]),
+        "gb_genome_download_rows": (C.c_int, [vp, C.c_int, C.c_int, i64, i64, vp, i64]),
         "gb_genome_resident_ranges": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, i64p, i64p, C.POINTER(C.c_int)]),
         "gb_genome_set_host_rows": (C.c_int, [vp, C.c_int, i64, i64, vp, i64]),
         "gb_genome_fill_synthetic": (C.c_int, [vp, C.c_uint64, C.c_int]),
@@ -720,6 +721,11 @@ class Genome:
         n = C.c_int()
         self.check(self.lib.gb_genome_resident_ranges(self.h, gpu, chrom, 64, _ptr(lo), _ptr(hi), C.byref(n)))
         return [(int(lo[i]), int(hi[i])) for i in range(min(n.value, 64))]
+
+    def download_rows(self, gpu: int, chrom: int, row_lo: int, n_rows: int, ptr: int, row_stride: int) -> int:
+        """Resident ternary rows back to host memory; returns the status (8 = this GPU keeps its rows expanded)."""
+        return self.check(self.lib.gb_genome_download_rows(self.h, gpu, chrom, int(row_lo), int(n_rows), C.c_void_p(ptr),
+                                                           int(row_stride)), allow=(GB_ERR_UNSUPPORTED,))
 
     def set_host_rows(self, chrom: int, row_lo: int, n_rows: int, ptr: int, row_stride: int):
         self.check(self.lib.gb_genome_set_host_rows(self.h, chrom, int(row_lo), int(n_rows), C.c_void_p(ptr), int(row_stride)))

@@ -893,6 +893,38 @@ int gb_genome_set_host_rows(gb_genome* g, int chrom, int64_t row_lo, int64_t n_r
   return GB_OK;
 }
 
+// Rows [row_lo, row_lo + n_rows) of chromosome `chrom` back from GPU `gpu`'s resident ternary rows into HOST memory
+// (GB_ERR_UNSUPPORTED when that GPU keeps its rows expanded).  Lets a caller that generated a panel on the device keep
+// a host copy without generating it twice.
+int gb_genome_download_rows(gb_genome* g, int gpu, int chrom, int64_t row_lo, int64_t n_rows, void* host_out, int64_t out_stride) {
+  if (!g || !g->planned || !g->rows_ready || gpu < 0 || gpu >= g->n_gpus || chrom < 0 || chrom >= (int)g->chroms.size() ||
+      n_rows < 0 || !host_out || out_stride < g->row5) {
+    if (g) g->err = "bad download arguments";
+    return GB_ERR_BAD_ARG;
+  }
+  int rc0 = wait_all(g);
+  if (rc0) return rc0;
+  Shard* sh = g->shards[(size_t)gpu];
+  if (sh->e2m1_resident) {
+    g->err = "this GPU keeps its rows in the expanded operand layout";
+    return GB_ERR_UNSUPPORTED;
+  }
+  for (const RowRange& x : sh->resident[(size_t)chrom])
+    if (row_lo >= x.lo && row_lo + n_rows <= x.hi) {
+      cudaSetDevice(sh->ctx->device);
+      cudaStreamSynchronize(sh->copy);
+      cudaError_t e = cudaMemcpy2D(host_out, (size_t)out_stride, sh->d_rows5 + (size_t)(x.res + row_lo - x.lo) * (size_t)g->row5,
+                                   (size_t)g->row5, (size_t)g->row5, (size_t)n_rows, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) {
+        g->err = std::string("device -> host copy of panel rows: ") + cudaGetErrorString(e);
+        return GB_ERR_CUDA;
+      }
+      return GB_OK;
+    }
+  g->err = "the rows are not resident on this GPU";
+  return GB_ERR_BAD_ARG;
+}
+
 int gb_genome_resident_ranges(const gb_genome* g, int gpu, int chrom, int max_ranges, int64_t* lo, int64_t* hi, int* n_ranges) {
   if (!g || !g->planned || gpu < 0 || gpu >= g->n_gpus || chrom < 0 || chrom >= (int)g->chroms.size() || !n_ranges) return GB_ERR_BAD_ARG;
   const std::vector<RowRange>& v = g->shards[(size_t)gpu]->resident[(size_t)chrom];

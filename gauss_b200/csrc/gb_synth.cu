@@ -29,17 +29,25 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64
   return x;
 }
 __device__ __forceinline__ float u01(uint32_t v) { return (float)(v >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {   // murmur3 finaliser: the per-haplotype draw, 2 IMULs
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
 
-// One CTA per row.  Shared tables for the up to 64 sites of the row's LD block: the site key, the copy threshold and
-// per population the allele-frequency threshold (all as 32-bit integers compared against hash bits).
+// One CTA per row.  Shared tables for the up to 64 sites of the row's LD block: a 32-bit site key, the copy threshold and
+// per population the allele-frequency threshold (16-bit fixed point, compared against halves of one 32-bit hash).
 __global__ void __launch_bounds__(256)
 synth_pack5_rows_kernel(uint8_t* __restrict__ dst, long long dst_stride, const int64_t* __restrict__ sites,
                         long long first_site, int n_pops, const int* __restrict__ pop_sizes,
                         const int* __restrict__ boff5, int row_bytes, uint64_t seed, int chrom) {
   extern __shared__ uint32_t sh[];
-  uint64_t* key = reinterpret_cast<uint64_t*>(sh);          // [64] per-site hash key
-  uint32_t* thr_copy = sh + 2 * LD_BLOCK;                   // [64] copy the previous site's allele if bits < thr
-  uint32_t* thr_f = thr_copy + LD_BLOCK;                    // [64][n_pops] allele 1 if bits < thr
+  uint32_t* key = sh;                                       // [64] per-site hash key
+  uint32_t* thr_copy = sh + LD_BLOCK;                       // [64] copy the previous site's allele if (bits & 0xFFFF) < thr
+  uint32_t* thr_f = thr_copy + LD_BLOCK;                    // [64][n_pops] allele 1 if (bits >> 16) < thr
   int* woff = reinterpret_cast<int*>(thr_f + LD_BLOCK * n_pops);   // [n_pops + 1] first 32-bit word of each block
   const long long row = blockIdx.x;
   const long long site = sites ? sites[row] : first_site + row;
@@ -49,10 +57,10 @@ synth_pack5_rows_kernel(uint8_t* __restrict__ dst, long long dst_stride, const i
   const uint64_t base = mix64(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(chrom + 1)));
   for (int k = tid; k <= depth; k += 256) {
     const uint64_t hk = mix64(base + 0xD1B54A32D192ED03ull * (uint64_t)(blk0 + k + 1));
-    key[k] = hk;
+    key[k] = (uint32_t)(hk >> 32);
     const uint64_t a = mix64(hk ^ 0xA5A5A5A5A5A5A5A5ull);
     const float rho = 0.7f + 0.25f * u01((uint32_t)a);
-    thr_copy[k] = k == 0 ? 0u : (uint32_t)(rho * 4294967040.0f);   // the block's first site always draws fresh
+    thr_copy[k] = k == 0 ? 0u : (uint32_t)(rho * 65536.0f);   // the block's first site always draws fresh
   }
   for (int i = tid; i < (depth + 1) * n_pops; i += 256) {
     const int k = i / n_pops, p = i % n_pops;
@@ -64,7 +72,7 @@ synth_pack5_rows_kernel(uint8_t* __restrict__ dst, long long dst_stride, const i
     const float n = (u01((uint32_t)g) + u01((uint32_t)(g >> 32)) + u01((uint32_t)(g >> 16)) + u01((uint32_t)(g >> 40)) - 2.0f) *
                     1.7320508f;
     const float fp = fminf(fmaxf(f + 0.05f * n, 0.005f), 0.995f);
-    thr_f[k * n_pops + p] = (uint32_t)(fp * 4294967040.0f);
+    thr_f[k * n_pops + p] = (uint32_t)(fp * 65536.0f);
   }
   if (tid <= n_pops) woff[tid] = tid < n_pops ? boff5[tid] >> 2 : row_bytes >> 2;
   __syncthreads();
@@ -86,12 +94,13 @@ synth_pack5_rows_kernel(uint8_t* __restrict__ dst, long long dst_stride, const i
         uint32_t dose = 0;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const uint64_t gid = ((uint64_t)p << 40) | ((uint64_t)ind << 1) | (uint64_t)h;
+          const uint32_t gid = ((uint32_t)p * 0x01000193u + (uint32_t)ind) * 2u + (uint32_t)h + 1u;
+          const uint32_t gmul = gid * 0x9E3779B1u;
           int k = depth;
           for (;;) {
-            const uint64_t u = mix64(key[k] + 0x9E3779B97F4A7C15ull * (gid + 1));
-            if ((uint32_t)u >= thr_copy[k]) {               // fresh draw at site k (always at k == 0)
-              dose += (uint32_t)(u >> 32) < thr_f[k * n_pops + p] ? 1u : 0u;
+            const uint32_t u = fmix32(key[k] ^ gmul);
+            if ((u & 0xFFFFu) >= thr_copy[k]) {             // fresh draw at site k (always at k == 0)
+              dose += (u >> 16) < thr_f[k * n_pops + p] ? 1u : 0u;
               break;
             }
             k--;
@@ -113,7 +122,7 @@ int launch_synth_pack5(Ctx* ctx, uint8_t* dst, int64_t dst_stride, int64_t n_row
                        int64_t first_site, int n_pops, const int* d_pop_sizes, const int* d_boff5, int row_bytes,
                        uint64_t seed, int chrom) {
   if (n_rows <= 0) return GB_OK;
-  const size_t smem = sizeof(uint32_t) * (size_t)(3 * LD_BLOCK + LD_BLOCK * n_pops + n_pops + 2);
+  const size_t smem = sizeof(uint32_t) * (size_t)(2 * LD_BLOCK + LD_BLOCK * n_pops + n_pops + 2);
   for (int64_t r0 = 0; r0 < n_rows; r0 += (1ll << 30)) {
     const int64_t n = std::min<int64_t>(n_rows - r0, 1ll << 30);
     synth_pack5_rows_kernel<<<(unsigned)n, 256, smem, ctx->stream>>>(dst + r0 * dst_stride, dst_stride,

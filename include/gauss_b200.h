@@ -287,6 +287,9 @@ GB_API int gb_genome_resident_ranges(const gb_genome *g, int gpu, int chrom, int
                               int *n_ranges);
 GB_API int gb_genome_set_host_rows(gb_genome *g, int chrom, int64_t row_lo, int64_t n_rows, const void *host_rows5,
                             int64_t row_stride);
+/* Resident ternary rows of one GPU back into HOST memory (GB_ERR_UNSUPPORTED when that GPU keeps them expanded). */
+GB_API int gb_genome_download_rows(gb_genome *g, int gpu, int chrom, int64_t row_lo, int64_t n_rows, void *host_out,
+                            int64_t out_stride);
 GB_API int gb_genome_upload(gb_genome *g, int wait);
 GB_API int gb_genome_submit(gb_genome *g, double *const *z_u, double *const *info_u, int *const *window_status);
 GB_API int gb_genome_wait(gb_genome *g, double *gpu_ms, double *upload_ms);

@@ -1,9 +1,9 @@
 #!/usr/bin/env bash
 set -u
 mkdir -p gpurun_out
-echo "== gpu tests"; timeout -s KILL 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-echo "== genome full (new expand5)"; timeout -s KILL 600 python tools/genome_try.py --steps 3 2>&1 | tail -8
-echo "== bench default"; /usr/bin/time -v timeout -s KILL 900 python bench.py --steps 3 --warmup 1 > gpurun_out/bench_r2b.json 2> gpurun_out/bench_r2b.err; tail -c 1500 gpurun_out/bench_r2b.err | grep -v "^\s" | tail -15; grep -E "Elapsed|Maximum resident" gpurun_out/bench_r2b.err
+echo skip tests
+echo skip
+echo "== bench default"; time timeout -s KILL 900 python bench.py --steps 3 --warmup 1 > gpurun_out/bench_r2b.json 2> gpurun_out/bench_r2b.err; tail -c 1500 gpurun_out/bench_r2b.err | grep -v "^\s" | tail -15; 
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/bench_r2b.json").read().strip().split("\n")[-1])
