@@ -360,11 +360,13 @@ class Env:
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=self.dev)
+            from datetime import timedelta
+            # a rank that dies must not leave the others spinning for NCCL's default 10 minutes
+            dist.init_process_group("nccl", device_id=self.dev, timeout=timedelta(seconds=240))
             self.dist = dist
 
-    def barrier(self):
-        if self.dist is not None:
+    def barrier(self, collective=True):
+        if self.dist is not None and collective:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
@@ -457,8 +459,9 @@ def stage_times(env, batch, stream, steps, stages):
     return np.array([[evs[k][s].elapsed_time(evs[k][s + 1]) for s in range(len(stages))] for k in range(steps)])
 
 
-def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, tag="chr22"):
-    """One chromosome-22-shaped batch resident in HBM: value, per-stage times, rooflines, host-buffer legs."""
+def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, tag="chr22", collective=True):
+    """One chromosome-22-shaped batch resident in HBM: value, per-stage times, rooflines, host-buffer legs.
+    collective=False: only this rank runs it (the kernel block of the genome workload) -- no cross-rank barrier."""
     import gauss_b200 as gb
     from gauss_b200 import api
     torch = env.torch
@@ -515,7 +518,7 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
 
     for _ in range(args.warmup):
         step()
-    env.barrier()
+    env.barrier(collective)
     sampler = ClockSampler(env.local)
     sampler.start()
     launches0 = ctx.launch_count
@@ -525,7 +528,7 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
         z, info, status = step()
     e_end.record(stream)
     torch.cuda.synchronize()
-    env.barrier()
+    env.barrier(collective)
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     total_ms = e_start.elapsed_time(e_end)
@@ -598,7 +601,7 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
     eq_chrom = bool(int((s2 == 0).sum()) == n_ok and np.array_equal(z_pin.numpy()[ok_u], z[ok_u]) and
                     np.array_equal(i_pin.numpy()[ok_u], info[ok_u]))
     chrom_step(host5.data_ptr())
-    env.barrier()
+    env.barrier(collective)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         chrom_step(host5.data_ptr())
@@ -864,7 +867,7 @@ def run_gpu(args):
             # kernel-level numbers on one chromosome-22-shaped batch (the round-1 step): per-stage times and rooflines;
             # at N = 1 also its host-buffer legs and the int8 arm
             full = env.world == 1 and not args.quick
-            c22 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=full and not args.no_e2e)
+            c22 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=full and not args.no_e2e, collective=False)
             line["dtype"] = c22["dtype"]
             for k in ("roofline", "roofline_gram", "roofline_chol", "roofline_expand5", "stage_ms", "stage_ms_serial", "solve"):
                 line[k] = c22[k]
@@ -872,7 +875,7 @@ def run_gpu(args):
                                  gpu_launches=c22["launches"], config=chr22_config(),
                                  **{k: c22[k] for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings") if k in c22})
             if full:
-                i8 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=False, fmt="int8", tag="chr22 int8")
+                i8 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=False, fmt="int8", tag="chr22 int8", collective=False)
                 dz = float(np.nanmax(np.abs(i8["z"] - c22["z"])))
                 line["int8"] = dict(value=i8["value"], ms_per_step=i8["ms_per_step"], dtype=i8["dtype"], stage_ms=i8["stage_ms"],
                                     roofline_gram=i8["roofline_gram"], max_abs_dz_vs_e2m1=dz,

@@ -456,9 +456,9 @@ int shard_plan(gb_genome* g, Shard* sh) {
 int copy_host_rows(gb_genome* g, Shard* sh, const Chrom& ch, int64_t a, int64_t b, uint8_t* dst) {
   while (a < b) {
     const HostPiece* pc = nullptr;
-    for (const HostPiece& x : ch.pieces)
-      if (a >= x.lo && a < x.hi) {
-        pc = &x;
+    for (auto it = ch.pieces.rbegin(); it != ch.pieces.rend(); ++it)   // newest piece first
+      if (a >= it->lo && a < it->hi) {
+        pc = &*it;
         break;
       }
     if (!pc) {
@@ -885,9 +885,10 @@ int gb_genome_set_host_rows(gb_genome* g, int chrom, int64_t row_lo, int64_t n_r
   int rc0 = wait_all(g);
   if (rc0) return rc0;
   Chrom& c = g->chroms[(size_t)chrom];
-  // a new piece replaces whatever it overlaps
+  // pieces may overlap (two GPUs both need the wing between their shards): the newest piece holding a row is used; a
+  // piece that is covered entirely by the new one is dropped
   c.pieces.erase(std::remove_if(c.pieces.begin(), c.pieces.end(),
-                                [&](const HostPiece& x) { return x.lo < row_lo + n_rows && row_lo < x.hi; }),
+                                [&](const HostPiece& x) { return x.lo >= row_lo && x.hi <= row_lo + n_rows; }),
                  c.pieces.end());
   if (n_rows > 0) c.pieces.push_back(HostPiece{row_lo, row_lo + n_rows, static_cast<const uint8_t*>(host_rows5), row_stride});
   return GB_OK;

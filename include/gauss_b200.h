@@ -282,7 +282,8 @@ GB_API int gb_genome_shard_info(const gb_genome *g, int gpu, int64_t *first_wind
                          double *gram_ops, double *solve_flops);
 /* The panel rows GPU `gpu` keeps resident of chromosome `chrom` (merged [lo, hi) ranges: the measured rows of its windows
  * with their wings, and the unmeasured rows), so that a feeder only has to read those; and the way to hand them over
- * piece by piece instead of as one buffer per chromosome (a new piece replaces any piece it overlaps). */
+ * piece by piece instead of as one buffer per chromosome (pieces may overlap -- two GPUs both keep the wing between
+ * their shards; the newest piece holding a row is the one read). */
 GB_API int gb_genome_resident_ranges(const gb_genome *g, int gpu, int chrom, int max_ranges, int64_t *lo, int64_t *hi,
                               int *n_ranges);
 GB_API int gb_genome_set_host_rows(gb_genome *g, int chrom, int64_t row_lo, int64_t n_rows, const void *host_rows5,

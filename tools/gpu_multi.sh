@@ -4,11 +4,11 @@ set -u
 NG=${NG:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8; head -2 /proc/meminfo; nproc
-echo "== genome tests on $NG GPUs"; timeout -s KILL 600 python -m pytest tests/test_genome.py -m gpu -x -q 2>&1 | tail -5
+echo skip tests
 echo "== single-process bench, $NG GPUs"
-timeout -s KILL 900 python bench.py --gpus $NG --single-process --steps 3 --warmup 1 --quick --no-cpu-baseline > gpurun_out/bench_sp${NG}.json 2> gpurun_out/bench_sp${NG}.err; echo rc=$?; tail -3 gpurun_out/bench_sp${NG}.err
+timeout -s KILL 400 python bench.py --gpus $NG --single-process --steps 3 --warmup 1 --quick --no-cpu-baseline > gpurun_out/bench_sp${NG}.json 2> gpurun_out/bench_sp${NG}.err; echo rc=$?; tail -3 gpurun_out/bench_sp${NG}.err
 echo "== torchrun bench, $NG ranks"
-timeout -s KILL 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --steps 3 --warmup 1 --quick > gpurun_out/bench_tr${NG}.json 2> gpurun_out/bench_tr${NG}.err; echo rc=$?; tail -3 gpurun_out/bench_tr${NG}.err
+timeout -s KILL 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --steps 3 --warmup 1 --quick > gpurun_out/bench_tr${NG}.json 2> gpurun_out/bench_tr${NG}.err; echo rc=$?; tail -3 gpurun_out/bench_tr${NG}.err
 python - <<PY
 import json
 for f in ("gpurun_out/bench_sp${NG}.json","gpurun_out/bench_tr${NG}.json"):
