@@ -136,6 +136,8 @@ def load_library():
         "gb_genome_launch_count": (i64, [vp]),
         "gb_partition_windows": (C.c_int, [i64, i64p, i64p, i64, C.POINTER(Params), C.c_int, i64p, dblp]),
         "gb_synth_pack5_rows": (C.c_int, [vp, C.c_uint64, C.c_int, i64, i64p, i64, C.c_int, i32p, vp, i64, C.c_int]),
+        "gb_packfile_convert": (C.c_int, [C.c_char_p, C.c_int, i32p, C.c_char_p, C.c_int, C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_char_p, C.c_int]),
         "gb_probe_peak": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
         "gb_run_qcat_strings": (C.c_int, [vp, i64, vp, vp, dblp, vp, C.c_int, vp, dblp, C.c_longlong, C.c_longlong,
                                           C.POINTER(Params), C.c_double, dblp, dblp, dblp, C.POINTER(C.c_int),
@@ -191,6 +193,8 @@ def pack2_rows_host(pop_sizes, rows: np.ndarray, is_ascii: bool | None = None, o
         rows = np.ascontiguousarray(rows)
     if is_ascii is None:
         is_ascii = rows.dtype == np.uint8
+        if is_ascii and rows.size and int(rows.max()) < 32:
+            raise ValueError("uint8 rows holding values below 32 look like numeric dosages, not characters: pass is_ascii explicitly")
     rb = pack5_row_bytes(ps) if _fmt == 5 else pack2_row_bytes(ps)
     if out is None:
         out = np.empty((rows.shape[0], rb), np.uint8)
@@ -347,6 +351,9 @@ class Panel:
         rows = np.ascontiguousarray(rows)
         if is_ascii is None:
             is_ascii = rows.dtype == np.uint8
+            if is_ascii and rows.size and int(rows.max()) < 32:
+                raise ValueError("uint8 rows holding values below 32 look like numeric dosages, not characters: "
+                                 "pass is_ascii explicitly")
         assert rows.ndim == 2 and rows.itemsize == 1
         self.ctx.check(self.ctx.lib.gb_panel_append_host(self.h, rows.shape[0], rows.ctypes.data,
                                                          rows.strides[0], int(bool(is_ascii))))

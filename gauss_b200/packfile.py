@@ -29,17 +29,18 @@ MAGIC = b"GBPACK2\n"
 ALIGN = 4096
 
 
-def read_pop_desc(path: str):
-    """Population description file (gauss.cpp:970-985): one header line, then `pop n_subjects super_pop [...]`."""
+def read_pop_desc(path: str, upper: bool = True):
+    """Population description file (gauss.cpp:970-985): one header line, then `pop n_subjects super_pop [...]`.
+    upper=False keeps the names as written (the reference compares them case-sensitively, gauss.cpp:1040, 1101)."""
     pops, sizes, sups = [], [], []
     with open(path) as f:
         next(f)
         for line in f:
             tok = line.split()
             if len(tok) >= 3:
-                pops.append(tok[0].upper())
+                pops.append(tok[0].upper() if upper else tok[0])
                 sizes.append(int(tok[1]))
-                sups.append(tok[2].upper())
+                sups.append(tok[2].upper() if upper else tok[2])
     return pops, np.array(sizes, np.int32), sups
 
 
@@ -186,7 +187,16 @@ class PackFile:
             names = {k.upper() for k in weights}
             return np.array([p in names for p in self.pops])
         sp = study_pop.upper()
-        return np.array([p == sp or s == sp for p, s in zip(self.pops, self.super_pops)])
+        flags = np.array([p == sp or s == sp for p, s in zip(self.pops, self.super_pops)])
+        if not flags.any():
+            raise ValueError(f"invalid population name '{study_pop}'")   # the reference stops here too (gauss.cpp:1060)
+        return flags
+
+    def weights_for(self, weights: dict) -> np.ndarray:
+        """pop_wgt_vec as init_pop_flag_wgt_vec builds it (gauss.cpp:1093-1117): the weights of the flagged populations in
+        PANEL order -- the order every pop_wgt argument of the C-ABI expects."""
+        wmap = {k.upper(): float(v) for k, v in weights.items()}
+        return np.array([wmap[p] for p in self.pops if p in wmap], np.float64)
 
     def select(self, row_idx, flags, out: np.ndarray | None = None):
         """pack2 rows of the listed SNPs restricted to the flagged populations -> (rows2, flagged sizes).
@@ -239,3 +249,78 @@ def flip_rows(rows2: np.ndarray, sizes, which) -> None:
         sub[:, start:int(boff[k + 1])] = 0               # padding bytes of the block
     sub[:, int(boff[-1]):] = 0
     rows2[which] = sub
+
+
+# ---- native converter + ternary file (gb_packfile_convert, gauss_b200/csrc/gb_packfile.cu) ------------------------------
+MAGIC5 = b"GBPACK5\n"
+
+
+def convert_reference_panel_native(geno_gz: str, pop_desc: str, out_path: str, threads: int = 0) -> dict:
+    """Reference data file (BGZF) -> `.gbpack` with ternary rows, per-population allele frequencies and the BGZF
+    virtual offset of every line, through the library's threaded C++ converter.  -> dict(n_rows, text_bytes, seconds)."""
+    import ctypes as C
+    _, sizes, _ = read_pop_desc(pop_desc)
+    lib = api.load_library()
+    n, tb, sec = C.c_int64(), C.c_double(), C.c_double()
+    err = C.create_string_buffer(512)
+    rc = lib.gb_packfile_convert(geno_gz.encode(), len(sizes), sizes.ctypes.data, out_path.encode(), int(threads),
+                                 C.byref(n), C.byref(tb), C.byref(sec), err, len(err))
+    if rc != api.GB_OK:
+        raise api.GaussB200Error(rc, err.value.decode())
+    return dict(n_rows=n.value, text_bytes=tb.value, seconds=sec.value)
+
+
+class PackFile5:
+    """Memory-mapped ternary `.gbpack` (layout: gb_packfile.cu).  rows[r] is the pack5 row of data line r over ALL
+    populations, af1[r] its per-population allele frequencies, fpos[r] the BGZF virtual offset of the line -- the key
+    the reference's index file refers to a SNP by (gauss.cpp:324-330)."""
+
+    def __init__(self, path: str, pop_desc: str | None = None):
+        with open(path, "rb") as f:
+            head = f.read(72)
+        if head[:8] != MAGIC5:
+            raise ValueError(f"{path} is not a GBPACK5 file")
+        self.path = path
+        ver, n_rows, n_pops, row_bytes, off_sizes, off_rows, off_fpos, off_af1 = np.frombuffer(head[8:], np.uint64)
+        self.n_rows, self.n_pops, self.row_bytes = int(n_rows), int(n_pops), int(row_bytes)
+        self.sizes = np.array(np.memmap(path, np.int32, "r", offset=int(off_sizes), shape=(self.n_pops,)))
+        if self.row_bytes != api.pack5_row_bytes(self.sizes):
+            raise ValueError(f"{path}: row size does not match its population sizes")
+        self.rows = np.memmap(path, np.uint8, "r", offset=int(off_rows), shape=(self.n_rows, self.row_bytes))
+        self.fpos = np.array(np.memmap(path, np.int64, "r", offset=int(off_fpos), shape=(self.n_rows,)))
+        self.af1 = np.memmap(path, np.float64, "r", offset=int(off_af1), shape=(self.n_rows, self.n_pops))
+        self.pops = self.super_pops = None
+        if pop_desc is not None:
+            self.pops, sizes, self.super_pops = read_pop_desc(pop_desc, upper=False)
+            if not np.array_equal(sizes, self.sizes):
+                raise ValueError("population description does not match the packed file")
+        nb = (self.sizes.astype(np.int64) + 4) // 5
+        self._boff = np.concatenate([[0], np.cumsum((nb + 3) // 4 * 4)])
+        self._order = np.argsort(self.fpos, kind="stable")
+
+    def rows_of_fpos(self, fpos) -> np.ndarray:
+        """Row index of every virtual offset (-1 when the file has no line there)."""
+        fpos = np.asarray(fpos, np.int64)
+        srt = self.fpos[self._order]
+        i = np.minimum(np.searchsorted(srt, fpos), max(self.n_rows - 1, 0))
+        hit = (srt[i] == fpos) if self.n_rows else np.zeros(len(fpos), bool)
+        return np.where(hit, self._order[i], -1)
+
+    def select(self, row_idx, flags, out: np.ndarray | None = None):
+        """pack5 rows of the listed SNPs restricted to the flagged populations -> (rows5, flagged sizes).  Population
+        blocks are whole 4-byte units in both layouts, so this is a byte-range gather."""
+        flags = np.asarray(flags, bool)
+        idx = np.asarray(row_idx, np.int64)
+        sizes = self.sizes[flags]
+        rb = api.pack5_row_bytes(sizes)
+        if out is None:
+            out = np.zeros((len(idx), rb), np.uint8)
+        assert out.shape == (len(idx), rb)
+        src = self.rows[idx] if len(idx) else np.empty((0, self.row_bytes), np.uint8)
+        o = 0
+        for k in np.where(flags)[0]:
+            n = int(self._boff[k + 1] - self._boff[k])
+            out[:, o:o + n] = src[:, self._boff[k]:self._boff[k + 1]]
+            o += n
+        out[:, o:] = 0
+        return out, sizes

@@ -316,6 +316,17 @@ GB_API int gb_synth_pack5_rows(gb_ctx *ctx, uint64_t seed, int chrom, int64_t n_
 /* Fill every GPU's resident rows with that generator instead of uploading them (chromosome index = `chrom`). */
 GB_API int gb_genome_fill_synthetic(gb_genome *g, uint64_t seed, int wait);
 
+/* ---- native converter of the reference's panel data file ------------------------------- */
+/* Reads the reference's BGZF data file once (gauss.cpp:572-585: per SNP one text line of n_pops genotype strings over ALL
+ * populations followed by n_pops allele frequencies; blocks as bgzf.c:486-536 reads them), inflating blocks and parsing
+ * lines on n_threads host threads (0 = all), and writes a ".gbpack" file: per SNP a ternary row (gb_pack5_row_bytes
+ * over all populations), its n_pops allele frequencies as doubles (MakeSnpVecMix's filter, gauss.cpp:631-693) and the
+ * BGZF virtual offset of its line (the `fpos` column of the index file, bgzf.h:108) -- layout in gb_packfile.cu;
+ * gauss_b200/packfile.py maps it.  Replaces the per-call bgzf_seek + istringstream parse of ReadGenotype
+ * (gauss.cpp:720-785).  Pure host code.  err (optional) receives a message on failure. */
+GB_API int gb_packfile_convert(const char *geno_path, int n_pops, const int *pop_sizes, const char *out_path,
+                        int n_threads, int64_t *n_rows, double *text_bytes, double *seconds, char *err, int err_cap);
+
 /* ---- pipe-peak probes (roofline denominators measured on the bench box at bench time) ---- */
 /* MEASURED_PEAKS.json has HBM GB/s and dense bf16 TF/s only.  which: 0 = tcgen05.mma kind::i8 128x128x32 (TOP/s),
  * 1 = tcgen05.mma kind::mxf4 128x128x64 (TOP/s), 2 = fp64 mma.sync m8n8k4 (TFLOP/s), 3 = device copy (GB/s, read +

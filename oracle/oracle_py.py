@@ -220,3 +220,59 @@ def _chars(a):
     elif a.dtype != np.uint8:
         raise TypeError("genotypes must be int8 dosages or uint8 ASCII")
     return np.ascontiguousarray(a)
+
+
+# ---- file-level reference path (oracle/ref_files.cpp: the reference's own bgzf.c + gauss.cpp readers) ----------------
+def ref_write_bgzf_panel(data_path, index_path, rsid, chr_, bp, a1, a2, geno, pop_sizes, af):
+    """Index + data file pair written through the reference's bgzf_write (real bgzf_tell offsets in the fpos column).
+    geno: [n, N] uint8 chars over ALL populations; af: [n, P] values printed with 6 decimals.  -> fpos per SNP."""
+    lib = C.CDLL(REF_SO)
+    n = len(bp)
+    geno = np.ascontiguousarray(geno, np.uint8)
+    m = np.ascontiguousarray(pop_sizes, np.int32)
+    af = np.ascontiguousarray(af, np.float64)
+    fpos = np.zeros(n, np.int64)
+
+    def strs(v):
+        arr = (C.c_char_p * n)()
+        arr[:] = [s.encode() for s in v]
+        return arr
+
+    lib.go_write_bgzf_panel.restype = C.c_int
+    rc = lib.go_write_bgzf_panel(data_path.encode(), index_path.encode(), C.c_int64(n), strs(rsid),
+                                 np.ascontiguousarray(chr_, np.int32).ctypes.data_as(C.c_void_p),
+                                 np.ascontiguousarray(bp, np.int64).ctypes.data_as(C.c_void_p), strs(a1), strs(a2),
+                                 geno.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), C.c_int(len(m)),
+                                 af.ctypes.data_as(C.c_void_p), fpos.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"go_write_bgzf_panel failed: {rc}")
+    return fpos
+
+
+def ref_file_distmix(input_file, index_file, data_file, pop_desc_file, chr_, start_bp, end_bp, wing, weights: dict,
+                     af1_cutoff=0.01, cap=200000):
+    """The reference's distmix() body on files (read_ref_desc -> ... -> ReadGenotype -> run_distmix -> output rows)."""
+    lib = C.CDLL(REF_SO)
+    names = list(weights)
+    arr = (C.c_char_p * len(names))()
+    arr[:] = [s.encode() for s in names]
+    vals = np.array([weights[k] for k in names], np.float64)
+    bp = np.zeros(cap, np.int64)
+    af, z, info = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+    typ = np.zeros(cap, np.int32)
+    sbuf = C.create_string_buffer(cap * 48)
+    err = C.create_string_buffer(512)
+    nm, na = C.c_int(0), C.c_int(0)
+    lib.go_file_distmix.restype = C.c_int
+    rc = lib.go_file_distmix(input_file.encode(), index_file.encode(), data_file.encode(), pop_desc_file.encode(),
+                             C.c_int(chr_), C.c_longlong(start_bp), C.c_longlong(end_bp), C.c_longlong(wing), arr,
+                             vals.ctypes.data_as(C.c_void_p), C.c_int(len(names)), C.c_double(af1_cutoff), C.c_int(cap),
+                             bp.ctypes.data_as(C.c_void_p), af.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p),
+                             info.ctypes.data_as(C.c_void_p), typ.ctypes.data_as(C.c_void_p), sbuf, C.c_int(len(sbuf)),
+                             err, C.c_int(len(err)), C.byref(nm), C.byref(na))
+    if rc < 0:
+        return dict(rc=rc, error=err.value.decode(), n_measured=nm.value, n_all=na.value)
+    toks = [ln.split(" ") for ln in sbuf.value.decode().split("\n") if ln]
+    return dict(rc=rc, rsid=[t[0] for t in toks], a1=[t[1] for t in toks], a2=[t[2] for t in toks], bp=bp[:rc].copy(),
+                af1mix=af[:rc].copy(), z=z[:rc].copy(), info=info[:rc].copy(), type=typ[:rc].copy(),
+                n_measured=nm.value, n_all=na.value)

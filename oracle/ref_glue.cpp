@@ -5,7 +5,7 @@
 //   * CalCor / CalWgtCov            src/util.cpp:49-70, 103-124   (extracted verbatim at build time)
 //   * run_dist / run_distmix        src/dist.cpp:129-227, src/distmix.cpp:138-253 (ditto)
 //   * computeLD kernel block        src/computeLD.cpp:95-116      (ditto)
-//   * Arguments::Arguments defaults src/gauss.cpp:18-35           (ditto)
+//   * Arguments::Arguments defaults src/gauss.cpp (compiled unmodified, with bgzf.c: see ref_files.cpp)
 //   * class Snp                     src/snp.{h,cpp}               (compiled unmodified)
 // The extracted fragments are written by oracle/build_ref.sh into oracle/_ref/gen/*.inc
 // (git-ignored; reference sources are never copied into the repository history).
@@ -94,7 +94,7 @@ void LoadProgressBar(int) {}  // util.cpp:449-461 prints a text bar; silent here
 #include "gen/util_49_70.inc"
 #include "gen/util_103_124.inc"
 #include "gen/util_153_169.inc"   // CalCor(std::string&, std::string&)
-#include "gen/gauss_18_35.inc"
+// (Arguments::Arguments, gauss.cpp:18-35, now comes from the reference's own gauss.cpp compiled whole: build_ref.sh)
 void run_dist(std::vector<Snp*>& snp_vec, Arguments& args);
 void run_distmix(std::vector<Snp*>& snp_vec, Arguments& args);
 #include "gen/dist_129_227.inc"
