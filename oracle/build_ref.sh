@@ -51,6 +51,16 @@ gcc -O2 -fPIC -w -I"$SRC" -c "$SRC/bgzf.c" -o "$OUT/bgzf.o"
 g++ $CXXFLAGS -c "$SRC/gauss.cpp" -o "$OUT/gauss.o"
 g++ $CXXFLAGS -c "$HERE/ref_glue.cpp" -o "$OUT/ref_glue.o"
 g++ $CXXFLAGS -c "$HERE/ref_files.cpp" -o "$OUT/ref_files.o"
+printf '#include <RcppEigen.h>\n#include "util.h"\n#include "gen/util_474_507.inc"\n' > "$OUT/gen/util_io.cpp"
+g++ $CXXFLAGS -c "$OUT/gen/util_io.cpp" -o "$OUT/util_io.o"     # BgzfGetLine / FlipGenotypeVec alone, for the patched library
 g++ -shared -o "$OUT/libgauss_ref.so" "$OUT/ref_glue.o" "$OUT/ref_files.o" "$OUT/gauss.o" "$OUT/bgzf.o" "$OUT/snp.o" \
     "$OUT/gauss_oracle_int.o" -lz -lm
 echo "build_ref: wrote $OUT/libgauss_ref.so"
+# the Rcpp-side patch of INTEGRATION.md, compiled over the reference's own Snp / Arguments and linked with the product
+LIBGB="$HERE/../gauss_b200/lib/libgauss_b200.so"
+if [ -f "$LIBGB" ]; then
+  g++ $CXXFLAGS -I"$HERE/../include" -c "$HERE/patch/run_window_patched.cpp" -o "$OUT/run_window_patched.o"
+  g++ -shared -o "$OUT/libgauss_patched.so" "$OUT/run_window_patched.o" "$OUT/gauss.o" "$OUT/bgzf.o" "$OUT/snp.o" "$OUT/util_io.o" \
+      -L"$HERE/../gauss_b200/lib" -lgauss_b200 -Wl,-rpath,'$ORIGIN/../../gauss_b200/lib' -lz -lm
+  echo "build_ref: wrote $OUT/libgauss_patched.so"
+fi

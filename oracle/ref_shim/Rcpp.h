@@ -23,6 +23,11 @@ inline std::ostream& rcout_instance() {
 }
 #define Rcout rcout_instance()
 [[noreturn]] inline void stop(const std::string& msg) { throw std::runtime_error(msg); }
+inline std::string& last_warning() {
+  static std::string w;
+  return w;
+}
+inline void warning(const std::string& msg) { last_warning() = msg; }
 
 // just enough of NumericVector / NumericMatrix for src/computeLD.cpp:95-116
 class NumericVector {
