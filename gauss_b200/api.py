@@ -89,6 +89,8 @@ def load_library():
         "gb_window_ld": (C.c_int, [vp, vp, i64, i64p, dblp, dblp]),
         "gb_window_cor": (C.c_int, [vp, vp, i64, i64p, i64, i64p, dblp, C.POINTER(Params), dblp, dblp]),
         "gb_genes_ld": (C.c_int, [vp, vp, i64, i64p, i64p, dblp, C.c_double, dblp]),
+        "gb_genes_jepeg": (C.c_int, [vp, vp, i64, i64p, i64p, dblp, dblp, dblp, dblp, C.c_double, C.c_double, C.c_double,
+                                     C.c_int, dblp]),
         "gb_zmix_pair_cor": (C.c_int, [vp, vp, i64, i64p, dblp, dblp]),
         "gb_window_qcat": (C.c_int, [vp, vp, i64, i64p, dblp, i64, i64, i64, i64p, dblp, C.POINTER(Params), C.c_double,
                                      C.POINTER(C.c_int), dblp, dblp, dblp, dblp]),
@@ -468,6 +470,19 @@ class Panel:
                                                 _ptr(out)))
         offs = np.concatenate([[0], np.cumsum(sizes * sizes)])
         return [out[offs[g]:offs[g + 1]].reshape(sizes[g], sizes[g]) for g in range(len(sizes))]
+
+    def genes_jepeg(self, g_off, rows, z, info, categ_wgt, pop_wgt=None, lam: float = 0.1, min_abs_eig: float = 1e-5,
+                    categ_cor_cutoff: float = 0.8, denorm_norm_w: int = 3):
+        """gb_genes_jepeg: [n_genes, 16] statistics of jepeg() (pop_wgt None) / jepegmix() for every gene."""
+        go, r = _i64(g_off), _i64(rows)
+        w = None if pop_wgt is None else _f64(pop_wgt)
+        zz, ii, cw = _f64(z), _f64(info), _f64(categ_wgt)
+        assert cw.shape == (len(r), 6) and len(zz) == len(r) == len(ii)
+        out = np.zeros((len(go) - 1, 16))
+        self.ctx.check(self.ctx.lib.gb_genes_jepeg(self.ctx.h, self.h, len(go) - 1, _ptr(go), _ptr(r), _ptr(w), _ptr(zz), _ptr(ii),
+                                                   _ptr(cw), float(lam), float(min_abs_eig), float(categ_cor_cutoff),
+                                                   int(denorm_norm_w), _ptr(out)))
+        return out
 
     def zmix_pair_cor(self, rows, z):
         """gb_zmix_pair_cor: prep_zmix5's pair matrix [n(n-1)/2, 1 + P] (column 0 = z_i z_j)."""

@@ -1174,6 +1174,72 @@ int gb_genes_ld(gb_ctx* ctx, gb_panel* panel, int64_t n_genes, const int64_t* g_
   return rc;
 }
 
+// ---- jepeg() / jepegmix() statistics of every gene in one batch (gene.cpp:288-547, 553-822; jepegmix.cpp:115-139) ------
+// CorG of all genes through the Gram path (as gb_genes_ld), then jepeg_gene_kernel: one thread per gene for the
+// <= 6-category algebra.  out: [n_genes][16] doubles, layout in include/gauss_b200.h.
+int gb_genes_jepeg(gb_ctx* ctx, gb_panel* panel, int64_t n_genes, const int64_t* g_off, const int64_t* rows,
+                   const double* pop_wgt, const double* z, const double* info, const double* categ_wgt, double lambda,
+                   double min_abs_eig, double categ_cor_cutoff, int denorm_norm_w, double* out) {
+  if (!ctx || !panel || n_genes < 0 || !g_off || (!rows && g_off[n_genes] > 0) || !z || !info || !categ_wgt || !out ||
+      denorm_norm_w == 0) {
+    if (ctx) ctx->err = "null or negative argument";
+    return GB_ERR_BAD_ARG;
+  }
+  if (n_genes == 0) return GB_OK;
+  gb_params p;
+  gb_params_default(&p);
+  p.min_num_measured_snp = 0;   // a gene may hold a single SNP
+  gb_batch* b = nullptr;
+  int rc = create_batch_internal(ctx, panel, n_genes, g_off, rows, nullptr, nullptr, nullptr, pop_wgt, &p, true, false, &b,
+                                 false, 1.0 + lambda);
+  if (rc) return rc;
+  const int64_t n_snps = g_off[n_genes];
+  const size_t db = jepeg_gene_desc_bytes();
+  std::vector<uint8_t> h_desc((size_t)n_genes * db);
+  std::vector<char> seen((size_t)n_genes, 0);
+  for (size_t a = 0; a < b->h_wins.size(); a++) {   // h_wins is sorted by size; active[] maps back to the gene
+    const SolveWin& w = b->h_wins[a];
+    const int g = b->active[a];
+    jepeg_gene_desc_fill(h_desc.data() + (size_t)g * db, w.off_tt, g_off[g], w.ld_t, w.n_t);
+    seen[(size_t)g] = 1;
+  }
+  for (int64_t g = 0; g < n_genes; g++)
+    if (!seen[(size_t)g]) jepeg_gene_desc_fill(h_desc.data() + (size_t)g * db, 0, g_off[g], 0, 0);   // empty gene
+  void* d_desc = nullptr;
+  double *d_z = nullptr, *d_info = nullptr, *d_cw = nullptr, *d_out = nullptr;
+  auto done = [&](int code) {
+    for (void* q : {d_desc, (void*)d_z, (void*)d_info, (void*)d_cw, (void*)d_out})
+      if (q) cudaFreeAsync(q, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    gb_batch_destroy(b);
+    return code;
+  };
+  const size_t ns = (size_t)std::max<int64_t>(n_snps, 1);
+  if (cudaMallocAsync(&d_desc, h_desc.size(), ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(reinterpret_cast<void**>(&d_z), sizeof(double) * ns, ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(reinterpret_cast<void**>(&d_info), sizeof(double) * ns, ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(reinterpret_cast<void**>(&d_cw), sizeof(double) * 6 * ns, ctx->stream) != cudaSuccess ||
+      cudaMallocAsync(reinterpret_cast<void**>(&d_out), sizeof(double) * 16 * (size_t)n_genes, ctx->stream) != cudaSuccess) {
+    ctx->err = "cudaMallocAsync(jepeg) failed";
+    cudaGetLastError();
+    return done(GB_ERR_OOM);
+  }
+  cudaMemcpyAsync(d_desc, h_desc.data(), h_desc.size(), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d_z, z, sizeof(double) * (size_t)n_snps, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d_info, info, sizeof(double) * (size_t)n_snps, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d_cw, categ_wgt, sizeof(double) * 6 * (size_t)n_snps, cudaMemcpyHostToDevice, ctx->stream);
+  if ((rc = run_stage(b, 0)) || (rc = run_stage(b, 1))) return done(rc);
+  if ((rc = launch_jepeg_genes(ctx, d_desc, (int)n_genes, b->d_tt, d_z, d_info, d_cw, min_abs_eig, categ_cor_cutoff,
+                               denorm_norm_w, d_out)))
+    return done(rc);
+  if (cudaMemcpyAsync(out, d_out, sizeof(double) * 16 * (size_t)n_genes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = "jepeg results copy failed";
+    return done(GB_ERR_CUDA);
+  }
+  return done(GB_OK);
+}
+
 int gb_window_cor(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* rows_t, int64_t n_u,
                   const int64_t* rows_u, const double* pop_wgt, const gb_params* params, double* B11, double* B21) {
   if (!ctx || !panel || n_t < 1 || n_u < 0) {

@@ -189,4 +189,10 @@ int launch_qcat_finalize(Ctx* ctx, const SolveWin* d_wins, const double* d_ut, c
 int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double* d_src, double* d_dst,
                       double shift, const int* d_skip);
 
+// gb_gene.cu
+int launch_jepeg_genes(Ctx* ctx, const void* d_genes, int n_genes, const double* d_tt, const double* d_z, const double* d_info,
+                       const double* d_cw, double min_abs_eig, double cor_cutoff, int denorm, double* d_out);
+size_t jepeg_gene_desc_bytes();
+void jepeg_gene_desc_fill(void* dst, long long off_tt, long long snp0, int ld, int n);
+
 }  // namespace gb

@@ -148,6 +148,21 @@ GB_API int gb_window_ld(gb_ctx *ctx, gb_panel *panel, int64_t n, const int64_t *
  * pooled CalCor of jepeg(). */
 GB_API int gb_genes_ld(gb_ctx *ctx, gb_panel *panel, int64_t n_genes, const int64_t *g_off, const int64_t *rows,
                 const double *pop_wgt, double diag, double *out);
+/* jepeg() / jepegmix() (BASELINE config 5): the statistics of Gene::CalJepegPval / Gene::CalJepegmixPval (gene.cpp:288-547,
+ * 553-822) for every gene of a run (jepegmix.cpp:115-139) in one call.  Genes as in gb_genes_ld; per SNP (aligned with
+ * rows): z, info (Snp::GetInfo: 1 for a measured SNP) and categ_wgt[6] -- the annotation weight of the SNP in category
+ * PFS, TFB, STR, TAR, CIS, TRN (gene.cpp:28-44), NaN where the SNP has no entry in that category (Snp::categ_map_).
+ * lambda, min_abs_eig, categ_cor_cutoff, denorm_norm_w: Arguments defaults 0.1, 1e-5, 0.8, 3 (gauss.cpp:18-35).
+ * out: 16 doubles per gene --
+ *   [0] chisq  [1] df  [2] jepeg_pval  [3] number of available categories  [4] top category (0..5, -1 = ".")
+ *   [5] top category p-value  [6] index of the top SNP within the gene  [7] reserved
+ *   [8..13] p-value of each category (NaN = not available)  [14] bit mask of removed categories  [15] reserved
+ * with the reference's defaults (chisq -1, df 0, p-values -1) when every category was removed.  pop_wgt == NULL selects
+ * jepeg() (pooled CalCor).  The top SNP's p-value, 2 pnorm(|z|), is left to the caller like every other pnorm5 of the
+ * output stage. */
+GB_API int gb_genes_jepeg(gb_ctx *ctx, gb_panel *panel, int64_t n_genes, const int64_t *g_off, const int64_t *rows,
+                   const double *pop_wgt, const double *z, const double *info, const double *categ_wgt, double lambda,
+                   double min_abs_eig, double categ_cor_cutoff, int denorm_norm_w, double *out);
 /* Parity/debug surface: the correlation blocks the solve consumes.  pop_wgt == NULL selects the
  * pooled Pearson r of dist().  B11 is n_t x n_t symmetric with diagonal 1+lambda; B21 is
  * n_u x n_t row-major. */

@@ -18,6 +18,7 @@ cut_lines() { sed -n "$2,$3p" "$SRC/$1" > "$OUT/gen/$4"; }
 cut_lines util.cpp 49 70 util_49_70.inc            # CalCor(vector<string>, vector<string>)
 cut_lines util.cpp 103 124 util_103_124.inc        # CalWgtCov
 cut_lines util.cpp 153 169 util_153_169.inc        # CalCor(std::string&, std::string&)  (zmix)
+cut_lines util.cpp 284 296 util_284_296.inc        # CnvrtCovToCor
 cut_lines util.cpp 474 507 util_474_507.inc        # FlipGenotypeVec, BgzfGetLine (needed by gauss.cpp's readers)
 cut_lines dist.cpp 129 227 dist_129_227.inc        # run_dist
 cut_lines distmix.cpp 138 253 distmix_138_253.inc  # run_distmix
@@ -36,6 +37,7 @@ grep -q '^void run_qcat(' "$OUT/gen/qcat_134_262.inc"
 grep -q 'Eigen::VectorXd SNP_STD_VEC' "$OUT/gen/gene_569_586.inc"
 grep -q 'CorG(i, i) = 1.0 + lambda_;' "$OUT/gen/gene_305_314.inc"
 grep -q '^void run_qcatmix(' "$OUT/gen/qcatmix_145_286.inc"
+grep -q '^void CnvrtCovToCor(' "$OUT/gen/util_284_296.inc"
 grep -q '^void FlipGenotypeVec(' "$OUT/gen/util_474_507.inc"
 grep -q '^int BgzfGetLine(BGZF\* fp, std::string& line){' "$OUT/gen/util_474_507.inc"
 CXXFLAGS="-O2 -fPIC -ffp-contract=off -w -I$HERE/ref_shim -I$SRC -I$HERE -I$OUT"
@@ -49,11 +51,12 @@ g++ $CXXFLAGS -c "$SRC/snp.cpp" -o "$OUT/snp.o"
 # the reference's I/O half, unmodified: BGZF reader/writer and gauss.cpp (Arguments, Read*, MakeSnpVec*, ReadGenotype, ...)
 gcc -O2 -fPIC -w -I"$SRC" -c "$SRC/bgzf.c" -o "$OUT/bgzf.o"
 g++ $CXXFLAGS -c "$SRC/gauss.cpp" -o "$OUT/gauss.o"
+g++ $CXXFLAGS -c "$SRC/gene.cpp" -o "$OUT/gene.o"               # jepeg / jepegmix per-gene code, unmodified
 g++ $CXXFLAGS -c "$HERE/ref_glue.cpp" -o "$OUT/ref_glue.o"
 g++ $CXXFLAGS -c "$HERE/ref_files.cpp" -o "$OUT/ref_files.o"
 printf '#include <RcppEigen.h>\n#include "util.h"\n#include "gen/util_474_507.inc"\n' > "$OUT/gen/util_io.cpp"
 g++ $CXXFLAGS -c "$OUT/gen/util_io.cpp" -o "$OUT/util_io.o"     # BgzfGetLine / FlipGenotypeVec alone, for the patched library
-g++ -shared -o "$OUT/libgauss_ref.so" "$OUT/ref_glue.o" "$OUT/ref_files.o" "$OUT/gauss.o" "$OUT/bgzf.o" "$OUT/snp.o" \
+g++ -shared -o "$OUT/libgauss_ref.so" "$OUT/ref_glue.o" "$OUT/ref_files.o" "$OUT/gene.o" "$OUT/gauss.o" "$OUT/bgzf.o" "$OUT/snp.o" \
     "$OUT/gauss_oracle_int.o" -lz -lm
 echo "build_ref: wrote $OUT/libgauss_ref.so"
 # the Rcpp-side patch of INTEGRATION.md, compiled over the reference's own Snp / Arguments and linked with the product

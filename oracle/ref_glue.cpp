@@ -89,6 +89,7 @@ double CalVar(const Eigen::Ref<const Eigen::VectorXd>& x) {  // util.cpp:214-219
   return s / (double)(n - 1);
 }
 void LoadProgressBar(int) {}  // util.cpp:449-461 prints a text bar; silent here
+#include "gen/util_284_296.inc"   // CnvrtCovToCor (Eigen-free body, extracted verbatim)
 
 // ---- the reference's own code, extracted at build time -----------------------------------
 #include "gen/util_49_70.inc"
@@ -153,6 +154,54 @@ void go_gene_corg(const char* geno, int64_t n, const int* m, int n_pops, const d
   std::vector<double> wv;
   if (w) wv.assign(w, w + n_pops);
   ref_gene_corg(vec, wv, lambda, w != nullptr, out);
+}
+
+// One gene through the reference's own Gene::RunJepegmix / Gene::RunJepeg (gene.cpp compiled UNMODIFIED: category
+// counting 187-280, CorG, W, CovU = W CorG W^T, collinear / low-variance category removal, MakePosDef + InvMat on the
+// <= 6 x 6 CovX, chi-square and R::pchisq -- gene.cpp:288-547, 553-822).  categ_wgt: [n][6], NaN = the SNP is not
+// annotated in that category.  out: chisq, df, jepeg_pval, top_categ (0..5 or -1), top_categ_pval, top_snp, top_snp_pval.
+#include "gene.h"
+void go_gene_jepeg(const char* geno, int64_t n, const int* m, int n_pops, const double* w, const double* z,
+                   const double* info, const double* categ_wgt, double lambda, double min_abs_eig, double categ_cor_cutoff,
+                   int denorm_norm_w, double* out) {
+  int64_t N = 0;
+  for (int p = 0; p < n_pops; p++) N += m[p];
+  Arguments args;
+  args.lambda = lambda;
+  args.min_abs_eig = min_abs_eig;
+  args.categ_cor_cutoff = categ_cor_cutoff;
+  args.denorm_norm_w = denorm_norm_w;
+  if (w) args.pop_wgt_vec.assign(w, w + n_pops);
+  std::vector<Snp> store((size_t)n);
+  std::vector<Snp*> vec;
+  for (int64_t i = 0; i < n; i++) {
+    Snp& s = store[(size_t)i];
+    auto gv = split_pops(geno + i * N, m, n_pops);
+    s.SetGenotypeVec(gv);
+    s.SetZ(z[i]);
+    s.SetInfo(info[i]);
+    s.SetType(1);
+    s.SetRsid("snp" + std::to_string(i));
+    s.SetGeneid("G");
+    for (int c = 0; c < 6; c++)
+      if (categ_wgt[i * 6 + c] == categ_wgt[i * 6 + c]) s.SetCateg(c, categ_wgt[i * 6 + c]);
+    vec.push_back(&s);
+  }
+  Gene gene(args);
+  if (w) gene.RunJepegmix(vec);
+  else gene.RunJepeg(vec);
+  out[0] = gene.GetChisq();
+  out[1] = gene.GetDf();
+  out[2] = gene.GetJepegPval();
+  static const char* names[6] = {"PFS", "TFB", "STR", "TAR", "CIS", "TRN"};
+  out[3] = -1;
+  for (int c = 0; c < 6; c++)
+    if (gene.GetTopCategName() == names[c]) out[3] = c;
+  out[4] = gene.GetTopCategPval();
+  out[5] = -1;
+  for (int64_t i = 0; i < n; i++)
+    if (gene.GetTopSnpId() == store[(size_t)i].GetRsid()) out[5] = (double)i;
+  out[6] = gene.GetTopSnpPval();
 }
 
 // run_qcat / run_qcatmix: the reference's own bodies around the restated Eigen algorithms above

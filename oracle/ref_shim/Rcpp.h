@@ -9,6 +9,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include "Rmath.h"
 
 namespace Rcpp {
 struct NullStream : std::ostream {
