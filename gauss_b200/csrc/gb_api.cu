@@ -426,6 +426,11 @@ int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
       if ((rc = take(&b->d_info, s.info))) return rc;
     }
   }
+  if (b->clip_mode) {
+    if ((rc = dev_alloc(b, &b->d_eig_G, (size_t)b->tt_elems))) return rc;
+    if ((rc = dev_alloc(b, &b->d_eig_V, (size_t)b->tt_elems))) return rc;
+    if ((rc = dev_alloc(b, &b->d_evals, (size_t)b->n_t_total))) return rc;
+  }
   if (b->n_gather > 0) {
     if ((rc = take(&b->d_scratch, s.scratch))) return rc;
     if ((rc = make_row_tensor_maps(ctx, &b->tmaps_scratch, b->d_scratch, b->n_gather, pn->k_elems, pn->k_stride,
@@ -585,6 +590,12 @@ int run_stage(gb_batch* b, int stage) {
       const int nreal = (int)b->h_wins.size();
       GB_CUDA(cudaMemsetAsync(b->d_status, 0, sizeof(int) * (2 * (size_t)b->n_windows + 2), ctx->stream));
       const int* skip = nullptr;
+      if (b->clip_mode) {
+        // MakePosDef proper (util.cpp:302-318): eigendecomposition, spectrum clipped from below, in place
+        if ((rc = launch_eig_jacobi(ctx, b->d_wins, nreal, b->max_nt, b->d_tt, b->d_eig_G, b->d_eig_V, b->d_evals,
+                                    b->params.min_abs_eig, 1, nullptr)))
+          return rc;
+      }
       if (b->params.check_pd) {
         // certificate that MakePosDef is a no-op: the analytic lower bound on lambda_min(B11) when it
         // applies, else a Cholesky of B11 - min_abs_eig*I (succeeds <=> lambda_min > min_abs_eig)
@@ -1051,7 +1062,7 @@ int gb_batch_fetch(gb_batch* b, double* z_u, double* info_u, int* window_status_
   b->h_status.assign(2 * (size_t)b->n_windows + 3, 0);
   if ((rc = gb::batch_fetch_enqueue(b, z_u, info_u, b->h_status.data()))) return rc;
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return gb::batch_fetch_finish(b, b->h_status.data(), z_u, info_u, window_status_out);
+  return gb::batch_fetch_finish_repair(b, b->h_status.data(), z_u, info_u, window_status_out);
 }
 
 int gb_batch_work(const gb_batch* b, double* gram_ops, double* solve_flops, double* panel_bytes) {
@@ -1742,8 +1753,8 @@ static int chrom_run_packed(gb_ctx* ctx, gb_panel* panel, int host_format, int64
   for (int g = 0; g < n_groups; g++) {
     const int64_t w0 = g_lo[(size_t)g];
     gb_batch* b = batches[(size_t)g];
-    rc = gb::batch_fetch_finish(b, h_status + st_offs[(size_t)g], z_u + u_off[w0], info_u + u_off[w0],
-                      window_status ? window_status + w0 : nullptr);
+    rc = gb::batch_fetch_finish_repair(b, h_status + st_offs[(size_t)g], z_u + u_off[w0], info_u + u_off[w0],
+                                       window_status ? window_status + w0 : nullptr);
     if (rc != GB_OK && worst == GB_OK) worst = rc;
   }
   cleanup();
@@ -1819,6 +1830,44 @@ int gb_window_qcat(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* row
     cudaMemcpyAsync(h_c.data(), d_qc, sizeof(double) * (size_t)n_test, cudaMemcpyDeviceToHost, ctx->stream);
   }
   rc = gb_batch_fetch(b, nullptr, nullptr, nullptr);   // synchronises; window status (breakdown / not certified / format)
+  int n_eig = (int)n_t;
+  if (rc == GB_ERR_NOT_PD) {
+    // CountPC proper (util.cpp:355-388): the certificate could not show that every eigenvalue of B11 lies above
+    // eig_cutoff, so count them.  B11 has been overwritten by its factor: rebuild the blocks, eigendecompose B11 on the
+    // device, then factor / solve / test again with the right number of components.
+    double *d_G = nullptr, *d_V = nullptr, *d_ev = nullptr;
+    const size_t tt = (size_t)std::max<long long>(b->tt_elems, 1);
+    if (cudaMallocAsync(reinterpret_cast<void**>(&d_G), sizeof(double) * tt, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(reinterpret_cast<void**>(&d_V), sizeof(double) * tt, ctx->stream) != cudaSuccess ||
+        cudaMallocAsync(reinterpret_cast<void**>(&d_ev), sizeof(double) * (size_t)std::max<int64_t>(n_t, 1), ctx->stream) != cudaSuccess) {
+      ctx->err = "cudaMallocAsync(qcat eigenvalues) failed";
+      cudaGetLastError();
+      return done2(GB_ERR_OOM);
+    }
+    std::vector<double> ev((size_t)n_t);
+    rc = run_stage(b, 1);
+    if (!rc) rc = launch_qcat_patch(ctx, b->d_wins, b->d_ut, (int)n_u, (int)core_first, (int)n_core, 1.0 + p.lambda);
+    if (!rc) rc = launch_eig_jacobi(ctx, b->d_wins, 1, b->max_nt, b->d_tt, d_G, d_V, d_ev, eig_cutoff, /*clip=*/0, nullptr);
+    if (!rc && cudaMemcpyAsync(ev.data(), d_ev, sizeof(double) * (size_t)n_t, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = GB_ERR_CUDA;
+    if (!rc) rc = run_stage(b, 2);
+    if (!rc) rc = run_stage(b, 3);
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GB_ERR_CUDA;
+    if (!rc) {
+      for (double v : ev) n_eig -= v < eig_cutoff;     // util.cpp:380-386
+      rc = launch_qcat_finalize(ctx, b->d_wins, b->d_ut, b->d_y, (int)n_test, n_eig, d_qt, d_qc);
+    }
+    if (!rc && n_test) {
+      cudaMemcpyAsync(h_t.data(), d_qt, sizeof(double) * (size_t)n_test, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaMemcpyAsync(h_c.data(), d_qc, sizeof(double) * (size_t)n_test, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (!rc) {
+      rc = gb_batch_fetch(b, nullptr, nullptr, nullptr);
+      if (rc == GB_ERR_NOT_PD) rc = GB_OK;             // counted, not certified: that is the answer now
+    }
+    cudaFreeAsync(d_G, ctx->stream);
+    cudaFreeAsync(d_V, ctx->stream);
+    cudaFreeAsync(d_ev, ctx->stream);
+  }
   if (rc == GB_OK) {
     for (int64_t i = 0; i < n_u; i++) {
       t_u[i] = h_t[(size_t)i];
@@ -1828,7 +1877,7 @@ int gb_window_qcat(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* row
       t_m[i] = h_t[(size_t)(n_u + i)];
       chisq_m[i] = h_c[(size_t)(n_u + i)];
     }
-    if (num_eig) *num_eig = (int)n_t;
+    if (num_eig) *num_eig = n_eig;
   }
   return done2(rc);
 }
@@ -1884,7 +1933,7 @@ static int pipe_retire(gb_pipe* pp, gb_pipe::Slot& sl, int* status_out) {
     GB_CUDA(cudaEventSynchronize(sl.done));
     std::memcpy(sl.z_u, sl.h_z, sizeof(double) * (size_t)sl.n_u);
     std::memcpy(sl.info_u, sl.h_info, sizeof(double) * (size_t)sl.n_u);
-    rc = gb::batch_fetch_finish(sl.batch, sl.h_status, sl.z_u, sl.info_u, nullptr);
+    rc = gb::batch_fetch_finish_repair(sl.batch, sl.h_status, sl.z_u, sl.info_u, nullptr);
     batch_free_device(sl.batch);
     delete sl.batch;
     sl.batch = nullptr;
@@ -2170,3 +2219,62 @@ int gb_run_qcat_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const long
   }
   return rc;
 }
+
+namespace gb {
+
+int batch_fetch_finish_repair(gb_batch* b, const int* st, double* z_u, double* info_u, int* window_status_out) {
+  std::vector<int> wst((size_t)b->n_windows, GB_OK);
+  int rc = batch_fetch_finish(b, st, z_u, info_u, wst.data());
+  if (rc) return rc;
+  std::vector<int64_t> bad;
+  for (int64_t w = 0; w < b->n_windows; w++)
+    if (wst[(size_t)w] == GB_ERR_NOT_PD || wst[(size_t)w] == GB_ERR_BREAKDOWN) bad.push_back(w);
+  if (!bad.empty() && !b->clip_mode && !b->ld_mode && !b->counts_mode && !b->d_y) {
+    Ctx* ctx = b->ctx;
+    // sub-batch of the failed windows on the same panel rows; every one of them takes the eigen-clip path
+    std::vector<int64_t> to(1, 0), uo(1, 0), rt, ru;
+    std::vector<double> zt;
+    for (int64_t w : bad) {
+      for (int64_t i = b->t_off[(size_t)w]; i < b->t_off[(size_t)w + 1]; i++) {
+        rt.push_back(b->h_rows_t[(size_t)i]);
+        zt.push_back(b->h_zt.empty() ? 0.0 : b->h_zt[(size_t)i]);
+      }
+      for (int64_t i = b->u_off[(size_t)w]; i < b->u_off[(size_t)w + 1]; i++) ru.push_back(b->h_rows_u[(size_t)i]);
+      to.push_back((int64_t)rt.size());
+      uo.push_back((int64_t)ru.size());
+    }
+    gb_params p = b->params;
+    p.check_pd = 0;
+    gb_batch* r = batch_new(static_cast<gb_ctx*>(ctx), static_cast<gb_panel*>(b->panel), (int64_t)bad.size(),
+                            b->mode == GRAM_MIX ? b->h_wgt.data() : nullptr, &p, false, false, /*defer_flag_check=*/true, 1.0);
+    if (!r) return GB_ERR_OOM;
+    r->clip_mode = true;
+    rc = batch_plan_host(r, to.data(), rt.data(), uo.data(), ru.data(), zt.data(), b->mode == GRAM_MIX ? b->h_wgt.data() : nullptr);
+    if (!rc) rc = batch_plan_device(r, Arena{}, true);
+    for (int stg = 0; stg < 4 && !rc; stg++) rc = run_stage(r, stg);
+    std::vector<double> rz((size_t)uo.back()), ri((size_t)uo.back());
+    std::vector<int> rst(2 * bad.size() + 3, 0), rw(bad.size(), GB_OK);
+    if (!rc) rc = batch_fetch_enqueue(r, rz.data(), ri.data(), rst.data());
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GB_ERR_CUDA;
+    if (!rc) rc = batch_fetch_finish(r, rst.data(), rz.data(), ri.data(), rw.data());
+    if (!rc)
+      for (size_t k = 0; k < bad.size(); k++) {
+        const int64_t w = bad[k], n = b->u_off[(size_t)w + 1] - b->u_off[(size_t)w];
+        if (z_u) std::memcpy(z_u + b->u_off[(size_t)w], rz.data() + uo[k], sizeof(double) * (size_t)n);
+        if (info_u) std::memcpy(info_u + b->u_off[(size_t)w], ri.data() + uo[k], sizeof(double) * (size_t)n);
+        wst[(size_t)w] = rw[k];
+      }
+    cudaStreamSynchronize(ctx->stream);
+    batch_free_device(r);
+    delete r;
+    if (rc) return rc;
+  }
+  int worst = GB_OK;
+  for (int64_t w = 0; w < b->n_windows; w++) {
+    if (window_status_out) window_status_out[w] = wst[(size_t)w];
+    if (wst[(size_t)w] != GB_OK && worst == GB_OK) worst = wst[(size_t)w];
+  }
+  return window_status_out ? GB_OK : worst;
+}
+
+}  // namespace gb

@@ -76,7 +76,8 @@ struct gb_batch {
   std::vector<void*> owned;
   gb::Arena arena;
   size_t arena_used = 0;
-  bool clip_mode = false;             // eigen-clip (MakePosDef) pass enabled for uncertified windows
+  bool clip_mode = false;             // repair batch: every window goes through the eigen-clip (MakePosDef) before the Cholesky
+  double *d_eig_G = nullptr, *d_eig_V = nullptr, *d_evals = nullptr;   // clip_mode workspaces (tt_elems / n_t_total doubles)
 };
 
 namespace gb {
@@ -95,6 +96,11 @@ gb_batch* batch_new(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const doubl
 void batch_free_device(gb_batch* b);
 int batch_fetch_enqueue(gb_batch* b, double* z_u, double* info_u, int* status_staging);
 int batch_fetch_finish(gb_batch* b, const int* st, double* z_u, double* info_u, int* window_status_out);
+// The same, followed by the slow path for windows the certificate could not vouch for (GB_ERR_NOT_PD) or whose
+// factorisation broke down: B11 is rebuilt, eigendecomposed and clipped on the device like the reference's MakePosDef
+// (util.cpp:302-318), factored and solved again; their results replace the first ones and their status becomes GB_OK.
+// Synchronises ctx->stream.  Windows that still break down (NaN correlations) keep GB_ERR_BREAKDOWN and NaN results.
+int batch_fetch_finish_repair(gb_batch* b, const int* st, double* z_u, double* info_u, int* window_status_out);
 int pack5_layout(int n_pops, const int* pop_sizes, std::vector<int>* boff);
 
 // Relative device time of a window (Gram multiply-adds on the tensor cores + the fp64 solve, weighted by the measured

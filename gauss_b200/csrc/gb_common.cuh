@@ -186,6 +186,8 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
 int launch_qcat_patch(Ctx* ctx, const SolveWin* d_wins, double* d_ut, int n_u, int core_first, int n_core, double diag);
 int launch_qcat_finalize(Ctx* ctx, const SolveWin* d_wins, const double* d_ut, const double* d_y, int n_tested,
                          int num_eig, double* d_qt, double* d_qchisq);
+int launch_eig_jacobi(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, double* d_tt, double* d_G, double* d_V,
+                      double* d_evals, double min_abs_eig, int clip, int* d_n_clipped);
 int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double* d_src, double* d_dst,
                       double shift, const int* d_skip);
 

@@ -625,6 +625,19 @@ int shard_run(gb_genome* g, Shard* sh) {
       wst = tmp.data();
     }
     rc = batch_fetch_finish(s.batch, sh->h_status + s.status_off, zs, is, wst);
+    bool repair = false;
+    for (int64_t w = 0; w < s.w1 - s.w0 && !rc; w++) repair |= wst[w] == GB_ERR_NOT_PD || wst[w] == GB_ERR_BREAKDOWN;
+    if (repair) {
+      // uncertified windows take the eigen-clip path (MakePosDef proper).  With ternary residency the working panel has
+      // been reused by later batches meanwhile: expand this batch's rows again first.
+      if (!sh->e2m1_resident)
+        for (const RowRange& x : s.ranges) {
+          const int64_t pos = map_row(sh->resident[(size_t)s.chrom], x.lo);
+          rc = launch_expand5(ctx, sh->panels[s.slot], sh->d_rows5 + (size_t)pos * (size_t)g->row5, g->row5, x.res, x.hi - x.lo);
+          if (rc) break;
+        }
+      if (!rc) rc = batch_fetch_finish_repair(s.batch, sh->h_status + s.status_off, zs, is, wst);
+    }
     if (rc) {
       sh->err = ctx->err;
       return rc;

@@ -612,6 +612,147 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// MakePosDef / CountPC for windows the Cholesky certificate cannot vouch for (util.cpp:302-318, 355-388): a symmetric
+// eigendecomposition of B11 on the device.  Rare path (lambda = 0 with duplicated SNPs, an eigenvalue cut-off above the
+// ridge, negative weights), so it is built for robustness, not speed: cyclic two-sided Jacobi, one CTA per window, the
+// rotations of one round-robin step (n / 2 disjoint pairs) applied as independent 2 x 2 block updates
+//   A'[k][l] = J_k^T A[k][l] J_l,   V'[:, l] = V[:, l] J_l
+// so every element is read and written exactly once per step.  G (n x ld, a full symmetric copy of B11) is
+// diagonalised in place, V accumulates the eigenvectors, B11 itself stays untouched until the clip:
+//   B11 <- B11 + sum_{lambda_i < min_abs_eig} (min_abs_eig - lambda_i) v_i v_i^T      (= V max(Lambda, min) V^T)
+// which is a no-op when nothing lies below the threshold, exactly like the reference's branch.
+__global__ void __launch_bounds__(512)
+eig_jacobi_kernel(const SolveWin* __restrict__ wins, double* tt, double* G_all, double* V_all, double* evals,
+                  double min_abs_eig, int clip, int* n_clipped) {
+  extern __shared__ __align__(16) unsigned char eig_smem[];
+  const SolveWin w = wins[blockIdx.x];
+  const int n = w.n_t, ld = w.ld_t;
+  const int m = (n + 1) & ~1, half = m >> 1;
+  int* pp = reinterpret_cast<int*>(eig_smem);          // [half] pair members of the current step
+  int* qq = pp + half;
+  double* cs = reinterpret_cast<double*>(qq + half + (half & 1));   // [half] cosines, [half] sines
+  double* sn = cs + half;
+  __shared__ double red[512];
+  __shared__ int stop;
+  double* A = tt + w.off_tt;
+  double* G = G_all + w.off_tt;
+  double* V = V_all + w.off_tt;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (long long idx = tid; idx < (long long)n * n; idx += nth) {
+    const int j = (int)(idx / n), i = (int)(idx % n);
+    G[(long long)j * ld + i] = i >= j ? A[(long long)j * ld + i] : A[(long long)i * ld + j];   // lower triangle is the valid one
+    V[(long long)j * ld + i] = i == j ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < 40; sweep++) {
+    double off = 0.0, tot = 0.0;
+    for (long long idx = tid; idx < (long long)n * n; idx += nth) {
+      const int j = (int)(idx / n), i = (int)(idx % n);
+      const double v = G[(long long)j * ld + i];
+      tot += v * v;
+      if (i != j) off += v * v;
+    }
+    red[tid] = off;
+    __syncthreads();
+    for (int o = nth >> 1; o > 0; o >>= 1) {
+      if (tid < o) red[tid] += red[tid + o];
+      __syncthreads();
+    }
+    off = red[0];
+    __syncthreads();
+    red[tid] = tot;
+    __syncthreads();
+    for (int o = nth >> 1; o > 0; o >>= 1) {
+      if (tid < o) red[tid] += red[tid + o];
+      __syncthreads();
+    }
+    tot = red[0];
+    if (tid == 0) stop = !(off > 1e-30 * tot);   // also stops on NaN
+    __syncthreads();
+    if (stop) break;
+    for (int step = 0; step < m - 1; step++) {
+      // round-robin pairing: player 0 stays, the others rotate
+      for (int k = tid; k < half; k += nth) {
+        const int a = k == 0 ? 0 : 1 + (k - 1 + step) % (m - 1);
+        const int bidx = m - 1 - k;
+        const int b = 1 + (bidx - 1 + step) % (m - 1);
+        const int p = min(a, b), q = max(a, b);
+        pp[k] = p;
+        qq[k] = q;
+        double c = 1.0, sgn = 0.0;
+        if (q < n) {
+          const double apq = G[(long long)q * ld + p];
+          if (apq != 0.0) {
+            const double app = G[(long long)p * ld + p], aqq = G[(long long)q * ld + q];
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            sgn = t * c;
+          }
+        }
+        cs[k] = c;
+        sn[k] = sgn;
+      }
+      __syncthreads();
+      for (int blk = tid; blk < half * half; blk += nth) {
+        const int k = blk % half, l = blk / half;            // rows of pair k, columns of pair l
+        const int pk = pp[k], qk = qq[k], pl = pp[l], ql = qq[l];
+        const bool rq = qk < n, cq = ql < n;                 // the dummy player of an odd n
+        const double ck = cs[k], sk = sn[k], cl = cs[l], sl = sn[l];
+        double a00 = G[(long long)pl * ld + pk];
+        double a01 = cq ? G[(long long)ql * ld + pk] : 0.0;
+        double a10 = rq ? G[(long long)pl * ld + qk] : 0.0;
+        double a11 = (rq && cq) ? G[(long long)ql * ld + qk] : 0.0;
+        // columns: (x_p, x_q) <- (c x_p - s x_q, s x_p + c x_q)
+        double b00 = cl * a00 - sl * a01, b01 = sl * a00 + cl * a01;
+        double b10 = cl * a10 - sl * a11, b11 = sl * a10 + cl * a11;
+        // rows, same rotation of pair k
+        a00 = ck * b00 - sk * b10;
+        a10 = sk * b00 + ck * b10;
+        a01 = ck * b01 - sk * b11;
+        a11 = sk * b01 + ck * b11;
+        if (k == l && rq) a01 = a10 = 0.0;                   // the annihilated element, exactly
+        G[(long long)pl * ld + pk] = a00;
+        if (cq) G[(long long)ql * ld + pk] = a01;
+        if (rq) G[(long long)pl * ld + qk] = a10;
+        if (rq && cq) G[(long long)ql * ld + qk] = a11;
+      }
+      for (long long idx = tid; idx < (long long)n * half; idx += nth) {
+        const int l = (int)(idx / n), r = (int)(idx % n);
+        const int pl = pp[l], ql = qq[l];
+        if (ql >= n) continue;
+        const double cl = cs[l], sl = sn[l];
+        const double vp = V[(long long)pl * ld + r], vq = V[(long long)ql * ld + r];
+        V[(long long)pl * ld + r] = cl * vp - sl * vq;
+        V[(long long)ql * ld + r] = sl * vp + cl * vq;
+      }
+      __syncthreads();
+    }
+  }
+  int clipped = 0;
+  for (int i = tid; i < n; i += nth) {
+    const double ev = G[(long long)i * ld + i];
+    evals[w.off_t + i] = ev;
+    clipped += ev < min_abs_eig;
+  }
+  if (clip) {
+    // low-rank correction of the ORIGINAL matrix, eigenvector by eigenvector (usually none or a handful)
+    for (int i = 0; i < n; i++) {
+      const double ev = G[(long long)i * ld + i];
+      if (!(ev < min_abs_eig)) continue;
+      const double d = min_abs_eig - ev;
+      const double* v = V + (long long)i * ld;
+      for (long long idx = tid; idx < (long long)n * n; idx += nth) {
+        const int c = (int)(idx / n), r = (int)(idx % n);
+        if (r >= c) A[(long long)c * ld + r] += d * v[r] * v[c];
+      }
+      __syncthreads();
+    }
+  }
+  if (n_clipped && clipped) atomicAdd(&n_clipped[blockIdx.x], clipped);
+}
+
 // qcat: the tested measured SNPs ride along as extra right-hand-side columns; their correlation row is a row
 // of B11, whose own entry is the forced diagonal 1 + lambda (qcat.cpp:186), not the computed self-correlation.
 __global__ void qcat_patch_kernel(const SolveWin* __restrict__ wins, double* ut, int n_u, int core_first, int n_core,
@@ -732,6 +873,24 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
     GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     trsm_finalize_kernel<128><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
   }
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+// G / V: workspaces laid out like the B11 buffer (tt_elems doubles each); evals per measured SNP (off_t); n_clipped
+// (optional) zero-initialised ints, one per window.
+int launch_eig_jacobi(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, double* d_tt, double* d_G, double* d_V,
+                      double* d_evals, double min_abs_eig, int clip, int* d_n_clipped) {
+  if (n_wins == 0) return GB_OK;
+  const int half = (max_nt + 1) / 2;
+  const size_t smem = sizeof(int) * (size_t)(2 * half + 2) + sizeof(double) * (size_t)(2 * half) + 16;
+  if (smem > 200 * 1024) {
+    ctx->err = "window too large for the eigen-clip path";
+    return GB_ERR_UNSUPPORTED;
+  }
+  GB_CUDA(cudaFuncSetAttribute(eig_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  eig_jacobi_kernel<<<(unsigned)n_wins, 512, smem, ctx->stream>>>(d_wins, d_tt, d_G, d_V, d_evals, min_abs_eig, clip, d_n_clipped);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

@@ -236,30 +236,50 @@ def test_too_few_snps_status_codes(gpu_ctx):
     assert rc == gb.api.GB_ERR_TOO_FEW_MEASURED          # computeLD.cpp:89
 
 
-def test_not_positive_definite_is_reported(gpu_ctx):
-    """lambda = 0 with a duplicated measured SNP makes B11 singular: the reference's MakePosDef would
-    rewrite the matrix, so the window must be flagged instead of silently differing."""
+def test_make_pos_def_clip_on_the_device(gpu_ctx, oracle):
+    """lambda = 0 with a duplicated measured SNP makes B11 singular: the reference's MakePosDef (util.cpp:302-318) clips
+    the spectrum at min_abs_eig and carries on.  The Cholesky certificate cannot vouch for such a window, so it takes
+    the device eigen-clip path and must come back with the reference's numbers, status GB_OK."""
     c = small_case(seed=28, n_snps=120)
     g = c["g"].copy()
     g[5] = g[4]
     panel = make_panel(gpu_ctx, g, c["pop_sizes"])
     p = gb.Params.default()
     p.lambda_ = 0.0
-    BREAKDOWN = 9   # GB_ERR_BREAKDOWN: a non-positive pivot in the factorisation of B11 itself -> no result, NaN
-    z, info, rc = panel.window_distmix(np.arange(0, 40), np.arange(40, 120), np.zeros(40), c["w"], p,
-                                       allow=(gb.api.GB_ERR_NOT_PD, BREAKDOWN))
-    assert rc in (gb.api.GB_ERR_NOT_PD, BREAKDOWN)
-    if rc == BREAKDOWN:
-        assert np.isnan(z).all() and np.isnan(info).all()
-    # a monomorphic SNP has zero variance -> NaN correlations (no guard at distmix.cpp:196)
+    meas, unme = np.arange(0, 40), np.arange(40, 120)
+    zt = np.asarray(c["z"])[:40]
+    t = np.concatenate([np.ones(40, np.int32), np.zeros(80, np.int32)])
+    for w in (c["w"], None):
+        if w is None:
+            z, info, rc = panel.window_dist(meas, unme, zt, p)
+        else:
+            z, info, rc = panel.window_distmix(meas, unme, zt, w, p)
+        assert rc == gb.GB_OK
+        r = oracle.run_window(t, np.arange(120, dtype=np.int64), np.concatenate([zt, np.zeros(80)]), g, c["pop_sizes"], w,
+                              0, 10 ** 12, lam=0.0)
+        assert r["rc"] == 0
+        assert np.abs(z - r["z"][40:]).max() <= TOL and np.abs(info - r["info"][40:]).max() <= TOL
+    # the same window inside a batch with healthy windows: only it is repaired, the others keep their bits
+    t_off, u_off = [0, 40, 70], [0, 80, 130]
+    rows_t = np.concatenate([meas, np.arange(10, 40)])
+    rows_u = np.concatenate([unme, np.arange(60, 110)])
+    zt2 = np.concatenate([zt, zt[10:40]])
+    batch = gb.Batch(panel, t_off, rows_t, u_off, rows_u, zt2, c["w"], p)
+    batch.run()
+    zb, ib, st = batch.fetch()
+    assert (st == 0).all()
+    z1, i1, _ = panel.window_distmix(meas, unme, zt, c["w"], p)
+    z2, i2, _ = panel.window_distmix(np.arange(10, 40), np.arange(60, 110), zt[10:40], c["w"], p)
+    np.testing.assert_array_equal(zb, np.concatenate([z1, z2]))
+    np.testing.assert_array_equal(ib, np.concatenate([i1, i2]))
+    # a monomorphic SNP has zero variance -> NaN correlations (no guard at distmix.cpp:196): nothing to clip, the
+    # factorisation breaks down, the window reports it and every result is NaN (the reference returns NaN too)
+    BREAKDOWN = 9
     g2 = c["g"].copy()
     g2[7] = 0
     panel2 = make_panel(gpu_ctx, g2, c["pop_sizes"])
-    z, info, rc = panel2.window_distmix(np.arange(0, 40), np.arange(40, 120), np.zeros(40), c["w"],
-                                        allow=(gb.api.GB_ERR_NOT_PD, BREAKDOWN))
-    assert rc in (gb.api.GB_ERR_NOT_PD, BREAKDOWN)
-    if rc == BREAKDOWN:
-        assert np.isnan(z).all() and np.isnan(info).all()
+    z, info, rc = panel2.window_distmix(meas, unme, np.zeros(40), c["w"], allow=(BREAKDOWN,))
+    assert rc == BREAKDOWN and np.isnan(z).all() and np.isnan(info).all()
 
 
 def test_batch_equals_single_windows_and_placement_invariance(gpu_ctx, oracle):

@@ -129,9 +129,15 @@ def test_qcat_edge_cases(gpu_ctx, oracle):
     # nothing measured in the prediction window
     none_m = panel.window_qcat(meas, z[meas], headwing, 0, unme, None)
     np.testing.assert_array_equal(none_m["t_u"], full["t_u"])
-    # a cut-off above the ridge cannot be certified: no eigen-count path on the GPU, reported instead of guessed
-    r = panel.window_qcat(meas, z[meas], headwing, n_core, unme, None, eig_cutoff=0.5, allow=(api.GB_ERR_NOT_PD,))
-    assert r["rc"] == api.GB_ERR_NOT_PD
+    # a cut-off above the ridge cannot be certified by a factorisation: the device eigendecomposition counts the
+    # components like CountPC (util.cpp:355-388) and the tests use num_eig - 3 degrees of freedom
+    r = panel.window_qcat(meas, z[meas], headwing, n_core, unme, None, eig_cutoff=0.5)
+    ref = oracle.run_qcat(t, bp, z, g, c["pop_sizes"], None, c["start_bp"], c["end_bp"], eig_cutoff=0.5)
+    assert r["rc"] == 0 and ref["rc"] == 0
+    assert r["num_eig"] == int(ref["m"][unme[0]]) < len(meas)
+    assert np.abs(r["t_u"] - ref["t"][unme]).max() <= 1e-8 and np.abs(r["chisq_u"] - ref["chisq"][unme]).max() <= 1e-8
+    core_m = meas[headwing:headwing + n_core]
+    assert np.abs(r["t_m"] - ref["t"][core_m]).max() <= 1e-8
     with pytest.raises(gb.GaussB200Error):
         panel.window_qcat(meas, z[meas], len(meas) - 2, 5, unme, None)     # core range runs past the measured list
 
