@@ -732,7 +732,8 @@ class Genome:
         self.check(self.lib.gb_genome_shard_info(self.h, gpu, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e),
                                                  C.byref(f), C.byref(g), C.byref(hh)))
         return dict(first_window=a.value, n_windows=b.value, resident_rows=c.value, n_batches=d.value,
-                    n_imputed=e.value, e2m1_resident=bool(f.value), gram_ops=g.value, solve_flops=hh.value)
+                    n_imputed=e.value, e2m1_resident=f.value == 100, expanded_pct=f.value, gram_ops=g.value,
+                    solve_flops=hh.value)
 
     def upload(self, wait: bool = True):
         self.check(self.lib.gb_genome_upload(self.h, int(bool(wait))))

@@ -108,6 +108,7 @@ struct Segment {
   size_t status_off = 0;
   cudaEvent_t landed = nullptr;           // the rows this segment touches are resident
   int slot = 0;                           // which compute stream / working panel / arena
+  bool expanded = false;                  // its rows stay resident in the E2M1 operand layout (no expansion per run)
 };
 
 struct Shard {
@@ -115,12 +116,17 @@ struct Shard {
   int part = 0;                           // partition index this shard computes
   gb_ctx* ctx = nullptr;
   std::vector<Segment> segs;
-  std::vector<std::vector<RowRange>> resident;   // per chromosome: merged row ranges kept in HBM
-  int64_t resident_rows = 0;
-  bool e2m1_resident = false;
-  uint8_t* d_rows5 = nullptr;             // ternary residency: [resident_rows][row5]
-  int64_t* d_sites = nullptr;             // synthetic fill: site index per resident row
-  gb_panel* panels[2] = {nullptr, nullptr};   // working panels (ternary residency) or panels[0] = the resident panel
+  // Residency is decided per batch: as many batches as HBM allows keep their rows EXPANDED (E2M1 operand rows, 16.7 KB
+  // per SNP of the 33KG shape, read by TMA directly); the others keep them as ternary rows (6.5 KB) and expand them into
+  // a working panel right before they run.  A whole genome on one GPU is ~70 % / 30 %; from two GPUs on all is expanded.
+  std::vector<std::vector<RowRange>> resident;     // per chromosome: every row range this shard needs (what a feeder supplies)
+  std::vector<std::vector<RowRange>> res_e, res_t; // ... split by form: expanded (res = row in `big`) / ternary (res = row in d_rows5)
+  int64_t resident_rows = 0, rows_e = 0, rows_t = 0;
+  bool e2m1_resident = false;             // every batch is expanded
+  uint8_t* d_rows5 = nullptr;             // ternary residency: [rows_t][row5]
+  int64_t* d_sites = nullptr;             // synthetic fill: site index per needed row (indexed like `resident`)
+  gb_panel* big = nullptr;                // expanded residency: [rows_e] operand rows
+  gb_panel* panels[2] = {nullptr, nullptr};   // working panels of the ternary batches
   Arena arenas[2];
   cudaStream_t cs[2] = {nullptr, nullptr}, sides[2] = {nullptr, nullptr}, copy = nullptr;
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_tmp = nullptr;
@@ -241,6 +247,8 @@ int shard_free(gb_genome* g, Shard* sh) {
   }
   sh->segs.clear();
   cudaStreamSynchronize(sh->ctx->stream);
+  if (sh->big) gb_panel_destroy(sh->big);
+  sh->big = nullptr;
   for (int i = 0; i < 2; i++) {
     if (sh->panels[i]) gb_panel_destroy(sh->panels[i]);
     if (sh->arenas[i].base) cudaFree(sh->arenas[i].base);
@@ -311,25 +319,29 @@ int shard_plan(gb_genome* g, Shard* sh) {
       sh->segs.push_back(std::move(sg));
     }
   }
-  // 2. residency: union of the segments' ranges per chromosome
-  sh->resident_rows = 0;
+  // 2. every row range this shard needs, per chromosome (what a feeder has to supply)
+  auto merge_ranges = [&](bool want_e, bool want_t, std::vector<std::vector<RowRange>>& out, int64_t& total) {
+    out.assign(g->chroms.size(), {});
+    total = 0;
+    for (size_t c = 0; c < g->chroms.size(); c++) {
+      std::vector<RowRange> all;
+      for (const Segment& s : sh->segs)
+        if (s.chrom == (int)c && ((s.expanded && want_e) || (!s.expanded && want_t))) all.insert(all.end(), s.ranges.begin(), s.ranges.end());
+      std::sort(all.begin(), all.end(), [](const RowRange& a, const RowRange& b) { return a.lo < b.lo; });
+      std::vector<RowRange>& m = out[c];
+      for (const RowRange& x : all) {
+        if (!m.empty() && x.lo <= m.back().hi) m.back().hi = std::max(m.back().hi, x.hi);
+        else m.push_back(x);
+      }
+      for (RowRange& x : m) {
+        x.res = total;
+        x.issued = x.lo;
+        total += x.hi - x.lo;
+      }
+    }
+  };
+  merge_ranges(true, true, sh->resident, sh->resident_rows);
   int64_t max_seg_rows = 1;
-  for (size_t c = 0; c < g->chroms.size(); c++) {
-    std::vector<RowRange> all;
-    for (const Segment& s : sh->segs)
-      if (s.chrom == (int)c) all.insert(all.end(), s.ranges.begin(), s.ranges.end());
-    std::sort(all.begin(), all.end(), [](const RowRange& a, const RowRange& b) { return a.lo < b.lo; });
-    std::vector<RowRange>& m = sh->resident[c];
-    for (const RowRange& x : all) {
-      if (!m.empty() && x.lo <= m.back().hi) m.back().hi = std::max(m.back().hi, x.hi);
-      else m.push_back(x);
-    }
-    for (RowRange& x : m) {
-      x.res = sh->resident_rows;
-      x.issued = x.lo;
-      sh->resident_rows += x.hi - x.lo;
-    }
-  }
   for (Segment& s : sh->segs) {
     int64_t n = 0;
     for (const RowRange& x : s.ranges) n += x.hi - x.lo;
@@ -349,43 +361,69 @@ int shard_plan(gb_genome* g, Shard* sh) {
   SH_CUDA(cudaEventCreate(&sh->ev_start));
   SH_CUDA(cudaEventCreate(&sh->ev_end));
   SH_CUDA(cudaEventCreateWithFlags(&sh->ev_tmp, cudaEventDisableTiming));
-  // 4. host planning of every batch against a panel description (the panels are created below, once the residency
-  //    mode is known; planning only needs n_rows / layout, which are the same for every panel of this genome)
   const int n_slots = g->n_streams;
-  // decide residency
+  // 4. residency per batch.  Workspace need of a batch from its window sizes (what batch_arena_bytes will report):
+  size_t arena_est = 0;
+  for (const Segment& s : sh->segs) {
+    const Chrom& ch = g->chroms[(size_t)s.chrom];
+    double tt = 0, ut = 0, dinv = 0, ntt = 0, nut = 0;
+    for (int64_t w = s.w0; w < s.w1; w++) {
+      const double nt = (double)(ch.t_off[(size_t)w + 1] - ch.t_off[(size_t)w]), nu = (double)(ch.u_off[(size_t)w + 1] - ch.u_off[(size_t)w]);
+      tt += nt * (nt + 8);
+      ut += nt * (nu + 8);
+      dinv += (nt / 64 + 1) * 4096;
+      ntt += nt;
+      nut += nu;
+    }
+    const double bytes = 8 * (2 * tt + ut + 2 * dinv + 2 * nut) + 12 * nut + 12.0 * g->n_pops * (ntt + nut) + (1 << 20);
+    arena_est = std::max(arena_est, (size_t)bytes);
+  }
   size_t free_b = 0, total_b = 0;
   SH_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  // E2M1 row stride: population blocks on 128-column boundaries, two dosages per byte
-  int64_t k_elems = 0;
+  int64_t k_elems = 0;   // E2M1 row: population blocks on 128-column boundaries, two dosages per byte
   for (int p = 0; p < g->n_pops; p++) k_elems += (g->pop_sizes[(size_t)p] + K_BLOCK - 1) / K_BLOCK * K_BLOCK;
-  const int64_t k_stride = k_elems / 2;
-  const double e2m1_bytes = (double)sh->resident_rows * (double)(k_stride + 8 * g->n_pops);
-  const double pack5_bytes = (double)sh->resident_rows * g->row5 + 2.0 * (double)max_seg_rows * (double)(k_stride + 8 * g->n_pops);
-  if (g->resident_mode == 2) sh->e2m1_resident = true;
-  else if (g->resident_mode == 1) sh->e2m1_resident = false;
-  else sh->e2m1_resident = e2m1_bytes + 24e9 < (double)free_b * 0.92;
-  (void)pack5_bytes;
-  // panels
-  if (sh->e2m1_resident) {
-    int rc = gb_panel_create_fmt(sh->ctx, g->n_pops, g->pop_sizes.data(), std::max<int64_t>(sh->resident_rows, 1),
-                                 GB_PANEL_E2M1, &sh->panels[0]);
+  const double row_e = (double)(k_elems / 2 + 8 * g->n_pops), row_t = (double)g->row5;
+  {
+    // start with everything ternary (+ the two working panels), then keep batches expanded while the budget lasts
+    const double base = (double)sh->resident_rows * row_t + (double)n_slots * (double)max_seg_rows * row_e;
+    double extra_budget = (double)free_b * 0.93 - (double)n_slots * (double)arena_est * 1.05 - 4e9 - base;
+    if (const char* e = getenv("GB_GENOME_EXPANDED_GB")) extra_budget = atof(e) * 1e9;   // tuning / tests: cap on the extra bytes
+    const bool force_t = g->resident_mode == 1, force_e = g->resident_mode == 2;
+    double used = 0.0;
+    for (Segment& s : sh->segs) {
+      const double extra = (double)s.n_rows * (row_e - row_t);
+      s.expanded = force_e || (!force_t && used + extra <= extra_budget);
+      if (s.expanded) used += extra;
+    }
+  }
+  merge_ranges(true, false, sh->res_e, sh->rows_e);
+  merge_ranges(false, true, sh->res_t, sh->rows_t);
+  sh->e2m1_resident = sh->rows_t == 0;
+  if (sh->rows_e > 0) {
+    int rc = gb_panel_create_fmt(sh->ctx, g->n_pops, g->pop_sizes.data(), sh->rows_e, GB_PANEL_E2M1, &sh->big);
     if (rc) {
       sh->err = "resident E2M1 panel: " + ctx->err;
       return rc;
     }
-    sh->panels[0]->n_rows = sh->resident_rows;
-    sh->chunk_rows = std::min<int64_t>(std::max<int64_t>(sh->resident_rows, 1), 65536);
+    sh->big->n_rows = sh->rows_e;
+    sh->chunk_rows = std::min<int64_t>(sh->rows_e, 65536);
     for (int i = 0; i < 2; i++) SH_CUDA(cudaMalloc(reinterpret_cast<void**>(&sh->d_chunk[i]), (size_t)sh->chunk_rows * (size_t)g->row5));
-  } else {
-    for (int i = 0; i < n_slots; i++) {
-      int rc = gb_panel_create_fmt(sh->ctx, g->n_pops, g->pop_sizes.data(), max_seg_rows, GB_PANEL_E2M1, &sh->panels[i]);
+  }
+  {
+    // the working panels double as the holder of the population tables the synthetic generator needs
+    int64_t max_t_rows = 1;
+    for (const Segment& s : sh->segs)
+      if (!s.expanded) max_t_rows = std::max(max_t_rows, s.n_rows);
+    const int n_work = sh->rows_t > 0 ? n_slots : 1;
+    for (int i = 0; i < n_work; i++) {
+      int rc = gb_panel_create_fmt(sh->ctx, g->n_pops, g->pop_sizes.data(), sh->rows_t > 0 ? max_t_rows : 1, GB_PANEL_E2M1, &sh->panels[i]);
       if (rc) {
         sh->err = "working panel: " + ctx->err;
         return rc;
       }
-      sh->panels[i]->n_rows = max_seg_rows;
+      sh->panels[i]->n_rows = sh->panels[i]->capacity;
     }
-    SH_CUDA(cudaMalloc(reinterpret_cast<void**>(&sh->d_rows5), (size_t)std::max<int64_t>(sh->resident_rows, 1) * (size_t)g->row5));
+    if (sh->rows_t > 0) SH_CUDA(cudaMalloc(reinterpret_cast<void**>(&sh->d_rows5), (size_t)sh->rows_t * (size_t)g->row5));
   }
   // 5. batches: phase 1 for all (sizes), arenas, phase 2
   size_t arena_need = 0;
@@ -395,10 +433,10 @@ int shard_plan(gb_genome* g, Shard* sh) {
     Segment& s = sh->segs[si];
     const Chrom& ch = g->chroms[(size_t)s.chrom];
     s.slot = (int)(si % (size_t)n_slots);
-    gb_panel* panel = sh->e2m1_resident ? sh->panels[0] : sh->panels[s.slot];
-    // position of the segment's rows: in the working panel (ternary residency) or in the resident panel
-    if (sh->e2m1_resident) {
-      for (RowRange& x : s.ranges) x.res = map_row(sh->resident[(size_t)s.chrom], x.lo);
+    gb_panel* panel = s.expanded ? sh->big : sh->panels[s.slot];
+    // position of the segment's rows: in the resident expanded panel, or in its working panel
+    if (s.expanded) {
+      for (RowRange& x : s.ranges) x.res = map_row(sh->res_e[(size_t)s.chrom], x.lo);
     } else {
       int64_t off = 0;
       for (RowRange& x : s.ranges) {
@@ -491,33 +529,37 @@ int shard_rows_for_segment(gb_genome* g, Shard* sh, Segment& s, bool synthetic) 
   ctx->stream = sh->copy;
   int rc = GB_OK;
   static thread_local int chunk_flip = 0;
+  std::vector<RowRange>& have = s.expanded ? sh->res_e[(size_t)s.chrom] : sh->res_t[(size_t)s.chrom];
   for (const RowRange& need : s.ranges) {
-    for (RowRange& res : sh->resident[(size_t)s.chrom]) {
+    for (RowRange& res : have) {
       if (need.lo < res.lo || need.lo >= res.hi) continue;
       const int64_t a = res.issued, b = std::max(res.issued, need.hi);
       if (b <= a) break;
-      const int64_t pos = res.res + (a - res.lo);      // position in the resident buffer / panel
-      if (!sh->e2m1_resident) {
+      const int64_t pos = res.res + (a - res.lo);      // position in the ternary buffer / the expanded panel
+      // site index of the rows (synthetic fill): d_sites is laid out like `resident`
+      const int64_t spos = ch.sites.empty() ? 0 : map_row(sh->resident[(size_t)s.chrom], a);
+      if (!s.expanded) {
         uint8_t* dst = sh->d_rows5 + (size_t)pos * (size_t)g->row5;
         if (synthetic) {
-          rc = launch_synth_pack5(ctx, dst, g->row5, b - a, ch.sites.empty() ? nullptr : sh->d_sites + pos, a, g->n_pops,
+          rc = launch_synth_pack5(ctx, dst, g->row5, b - a, ch.sites.empty() ? nullptr : sh->d_sites + spos, a, g->n_pops,
                                   sh->panels[0]->d_pop_sizes, sh->panels[0]->d_boff5, g->row5, g->synth_seed, s.chrom);
         } else {
           rc = copy_host_rows(g, sh, ch, a, b, dst);
         }
       } else {
+        // ternary rows pass through a staging chunk and are expanded into the resident panel once
         for (int64_t r0 = a; r0 < b && !rc; r0 += sh->chunk_rows) {
           const int64_t n = std::min(sh->chunk_rows, b - r0);
           uint8_t* stg = sh->d_chunk[chunk_flip & 1];
           chunk_flip++;
           // (same stream: the expansion that last read this staging chunk is ordered before the copy that refills it)
           if (synthetic) {
-            rc = launch_synth_pack5(ctx, stg, g->row5, n, ch.sites.empty() ? nullptr : sh->d_sites + res.res + (r0 - res.lo), r0,
+            rc = launch_synth_pack5(ctx, stg, g->row5, n, ch.sites.empty() ? nullptr : sh->d_sites + spos + (r0 - a), r0,
                                     g->n_pops, sh->panels[0]->d_pop_sizes, sh->panels[0]->d_boff5, g->row5, g->synth_seed, s.chrom);
           } else {
             rc = copy_host_rows(g, sh, ch, r0, r0 + n, stg);
           }
-          if (!rc) rc = launch_expand5(ctx, sh->panels[0], stg, g->row5, res.res + (r0 - res.lo), n);
+          if (!rc) rc = launch_expand5(ctx, sh->big, stg, g->row5, pos + (r0 - a), n);
         }
       }
       res.issued = b;
@@ -537,9 +579,10 @@ int shard_rows_for_segment(gb_genome* g, Shard* sh, Segment& s, bool synthetic) 
 int shard_rows(gb_genome* g, Shard* sh, bool synthetic) {
   Ctx* ctx = sh->ctx;
   SH_CUDA(cudaSetDevice(ctx->device));
-  for (auto& v : sh->resident)
-    for (RowRange& x : v) x.issued = x.lo;
-  if (sh->e2m1_resident) gb_panel_clear(sh->panels[0]), sh->panels[0]->n_rows = sh->resident_rows;
+  for (auto* set : {&sh->res_e, &sh->res_t})
+    for (auto& v : *set)
+      for (RowRange& x : v) x.issued = x.lo;
+  if (sh->big) gb_panel_clear(sh->big), sh->big->n_rows = sh->rows_e;
   SH_CUDA(cudaStreamSynchronize(ctx->stream));
   if (synthetic) {
     // site index of every resident row (rows of a chromosome are not in bp order: measured block | unmeasured block)
@@ -580,10 +623,10 @@ int shard_run(gb_genome* g, Shard* sh) {
     SH_CUDA(cudaStreamWaitEvent(cs, s.landed, 0));   // the rows this batch touches are resident (a completed event costs nothing)
     ctx->stream = cs;
     ctx->side_stream = sh->sides[s.slot];
-    if (!sh->e2m1_resident) {
+    if (!s.expanded) {
       gb_panel* panel = sh->panels[s.slot];
       for (const RowRange& x : s.ranges) {
-        const int64_t pos = map_row(sh->resident[(size_t)s.chrom], x.lo);
+        const int64_t pos = map_row(sh->res_t[(size_t)s.chrom], x.lo);
         rc = launch_expand5(ctx, panel, sh->d_rows5 + (size_t)pos * (size_t)g->row5, g->row5, x.res, x.hi - x.lo);
         if (rc) break;
       }
@@ -630,9 +673,9 @@ int shard_run(gb_genome* g, Shard* sh) {
     if (repair) {
       // uncertified windows take the eigen-clip path (MakePosDef proper).  With ternary residency the working panel has
       // been reused by later batches meanwhile: expand this batch's rows again first.
-      if (!sh->e2m1_resident)
+      if (!s.expanded)
         for (const RowRange& x : s.ranges) {
-          const int64_t pos = map_row(sh->resident[(size_t)s.chrom], x.lo);
+          const int64_t pos = map_row(sh->res_t[(size_t)s.chrom], x.lo);
           rc = launch_expand5(ctx, sh->panels[s.slot], sh->d_rows5 + (size_t)pos * (size_t)g->row5, g->row5, x.res, x.hi - x.lo);
           if (rc) break;
         }
@@ -856,7 +899,11 @@ int gb_genome_shard_info(const gb_genome* g, int gpu, int64_t* first_window, int
   if (resident_rows) *resident_rows = sh->resident_rows;
   if (n_batches) *n_batches = (int64_t)sh->segs.size();
   if (n_imputed) *n_imputed = sh->n_imputed;
-  if (e2m1_resident) *e2m1_resident = sh->e2m1_resident ? 1 : 0;
+  if (e2m1_resident) {   // per cent of this GPU's panel rows kept in the expanded operand layout (100 = no expansion at run time)
+    const int64_t tot = sh->rows_e + sh->rows_t;
+    *e2m1_resident = tot ? (int)((100 * sh->rows_e + tot / 2) / tot) : 100;
+    if (sh->rows_t > 0 && *e2m1_resident == 100) *e2m1_resident = 99;
+  }
   if (gram_ops) *gram_ops = sh->gram_ops;
   if (solve_flops) *solve_flops = sh->solve_flops;
   return GB_OK;
@@ -919,11 +966,7 @@ int gb_genome_download_rows(gb_genome* g, int gpu, int chrom, int64_t row_lo, in
   int rc0 = wait_all(g);
   if (rc0) return rc0;
   Shard* sh = g->shards[(size_t)gpu];
-  if (sh->e2m1_resident) {
-    g->err = "this GPU keeps its rows in the expanded operand layout";
-    return GB_ERR_UNSUPPORTED;
-  }
-  for (const RowRange& x : sh->resident[(size_t)chrom])
+  for (const RowRange& x : sh->res_t[(size_t)chrom])
     if (row_lo >= x.lo && row_lo + n_rows <= x.hi) {
       cudaSetDevice(sh->ctx->device);
       cudaStreamSynchronize(sh->copy);
@@ -935,8 +978,8 @@ int gb_genome_download_rows(gb_genome* g, int gpu, int chrom, int64_t row_lo, in
       }
       return GB_OK;
     }
-  g->err = "the rows are not resident on this GPU";
-  return GB_ERR_BAD_ARG;
+  g->err = "the rows are not resident in ternary form on this GPU (expanded operand rows cannot be read back)";
+  return GB_ERR_UNSUPPORTED;
 }
 
 int gb_genome_resident_ranges(const gb_genome* g, int gpu, int chrom, int max_ranges, int64_t* lo, int64_t* hi, int* n_ranges) {

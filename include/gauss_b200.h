@@ -291,7 +291,8 @@ GB_API int gb_genome_add_chromosome(gb_genome *g, int64_t n_rows, const void *ho
                              const int64_t *rows_u, const double *z_t, const int64_t *sites);
 GB_API int gb_genome_plan(gb_genome *g, int n_parts, int first_part);
 GB_API int gb_genome_num_chromosomes(const gb_genome *g);
-/* What GPU `gpu` of this genome was given (any pointer may be NULL). */
+/* What GPU `gpu` of this genome was given (any pointer may be NULL).  e2m1_resident: per cent of its panel rows kept
+ * resident in the expanded operand layout (100: no expansion at run time; a whole 33KG genome on one GPU: ~70). */
 GB_API int gb_genome_shard_info(const gb_genome *g, int gpu, int64_t *first_window, int64_t *n_windows,
                          int64_t *resident_rows, int64_t *n_batches, int64_t *n_imputed, int *e2m1_resident,
                          double *gram_ops, double *solve_flops);

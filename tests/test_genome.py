@@ -150,8 +150,14 @@ def test_genome_equals_oracle_and_is_placement_independent(gpu_ctx, oracle):
     z4, i4, *_ = run_genome(chroms, env={"GB_GENOME_RESIDENT": "pack5", "GB_GENOME_STREAMS": "1", "GB_GENOME_BATCH_WINDOWS": "3"})
     z5, i5, _, _, inf5, _ = run_genome(chroms, env={"GB_GENOME_RESIDENT": "e2m1"})
     assert inf5[0]["e2m1_resident"]
+    # hybrid residency (what a whole genome on one GPU gets): a budget that keeps only some batches expanded, with
+    # generated rows and with uploaded rows
+    hyb = {"GB_GENOME_EXPANDED_GB": "0.0008", "GB_GENOME_BATCH_WINDOWS": "2"}
+    z6, i6, _, _, inf6, _ = run_genome(chroms, env=hyb)
+    assert 0 < inf6[0]["expanded_pct"] < 100
+    z7, i7, *_ = run_genome(chroms, host_rows=host, env=hyb)
     for ci in range(len(chroms)):
-        for other_z, other_i in ((z2, i2), (z3, i3), (z4, i4), (z5, i5)):
+        for other_z, other_i in ((z2, i2), (z3, i3), (z4, i4), (z5, i5), (z6, i6), (z7, i7)):
             assert np.array_equal(z1[ci], other_z[ci], equal_nan=True)
             assert np.array_equal(i1[ci], other_i[ci], equal_nan=True)
 
