@@ -447,6 +447,43 @@ def chr22_batch_inputs(sizes):
                 rows_u=np.concatenate(rows_u), z_t=np.concatenate(z_t))
 
 
+def converter_rate(sizes, g):
+    """gb_packfile_convert on a BGZF file in the reference's data format (gauss.cpp:572-585), written here with zlib
+    the way bgzf.c:280-330 frames its blocks: GB/s of panel text through inflate + parse + ternary pack on host threads."""
+    import struct
+    import zlib
+    from gauss_b200 import packfile
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    chars = (g + 48).astype(np.uint8)
+    lines = []
+    for row in chars:
+        strs = [row[offs[k]:offs[k + 1]].tobytes() for k in range(len(sizes))]
+        afs = [b"%.6f" % (float(g_.mean()) / 2) for g_ in (row[offs[k]:offs[k + 1]].astype(np.float64) - 48 for k in range(len(sizes)))]
+        lines.append(b" ".join(strs + afs) + b"\n")
+    data = b"".join(lines)
+    tmp = tempfile.mkdtemp()
+    geno, desc, outp = os.path.join(tmp, "p_geno.gz"), os.path.join(tmp, "desc.txt"), os.path.join(tmp, "p.gbpack")
+    with open(desc, "w") as f:
+        f.write("pop n sup\n" + "".join(f"P{k} {int(m)} S\n" for k, m in enumerate(sizes)))
+    with open(geno, "wb") as f:
+        for i in list(range(0, len(data), 0xff00)) + [None]:
+            c = b"" if i is None else data[i:i + 0xff00]
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            payload = co.compress(c) + co.flush()
+            f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(payload) + 8 - 1))
+            f.write(payload + struct.pack("<II", zlib.crc32(c), len(c)))
+    info = packfile.convert_reference_panel_native(geno, desc, outp)
+    pf = packfile.PackFile5(outp)
+    ok = bool(np.array_equal(np.asarray(pf.rows), __import__("gauss_b200").api.pack5_rows_host(sizes, g, is_ascii=False)))
+    for pth in (geno, desc, outp):
+        os.unlink(pth)
+    os.rmdir(tmp)
+    return dict(rows=int(info["n_rows"]), text_gb=info["text_bytes"] / 1e9, seconds=info["seconds"], threads=os.cpu_count(),
+                text_gbs=info["text_bytes"] / info["seconds"] / 1e9, compressed_mb=None, rows_equal_host_packer=ok,
+                note="gb_packfile_convert: BGZF inflate + line parse + ternary pack, block-parallel on host threads; "
+                     "the reference re-inflates and re-parses this text on every call (ReadGenotype, gauss.cpp:720-785)")
+
+
 def stage_times(env, batch, stream, steps, stages):
     torch = env.torch
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(steps)]
@@ -629,6 +666,29 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
     # per-window calls on pinned int8 host rows (the seam run_distmix has today)
     host8 = torch.empty((n_all, N), dtype=torch.int8, pin_memory=True)
     host8.numpy()[:] = g8
+    # K0 on the device (chars / int8 rows -> packed operand rows + per-population sums), and the native converter of the
+    # reference's BGZF text panel (host threads) -- the "packed-panel stream" of the north star
+    out["pack"] = {}
+    try:
+        d8 = host8.to(env.dev)
+        pk_panel = gb.Panel(ctx, sizes, n_all, "e2m1")
+        pms = []
+        for _ in range(3):
+            pk_panel.clear()
+            ev0.record(stream)
+            pk_panel.append_device_ptr(d8.data_ptr(), n_all, N, is_ascii=False)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            pms.append(ev0.elapsed_time(ev1))
+        pbytes = n_all * (N + k_stride + 8 * len(sizes))
+        out["pack"]["pack_rows_kernel"] = dict(ms=min(pms), gbs=pbytes / (min(pms) / 1e3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"],
+                                               frac=pbytes / (min(pms) / 1e3) / 1e9 / pk["hbm_gbs"],
+                                               note="one byte per dosage in, E2M1 nibbles + sum x / sum x^2 out (read + write bytes)")
+        pk_panel.close()
+        del d8
+        out["pack"]["converter"] = converter_rate(sizes, g8[:1500])
+    except Exception as e:  # noqa: BLE001
+        out["pack"]["error"] = f"{type(e).__name__}: {e}"
     max_rows = int(max(len(x["measured"]) + len(x["unmeasured"]) for x in windows))
     pipe = gb.Pipe(ctx, sizes, max_rows, depth=3)
     res_z = [np.zeros(len(x["unmeasured"])) for x in windows]
@@ -873,7 +933,7 @@ def run_gpu(args):
                 line[k] = c22[k]
             line["chr22"] = dict(value=c22["value"], ms_per_step=c22["ms_per_step"], imputed_per_step=c22["n_imputed"],
                                  gpu_launches=c22["launches"], config=chr22_config(),
-                                 **{k: c22[k] for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings") if k in c22})
+                                 **{k: c22[k] for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings", "pack") if k in c22})
             if full:
                 i8 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=False, fmt="int8", tag="chr22 int8", collective=False)
                 dz = float(np.nanmax(np.abs(i8["z"] - c22["z"])))
@@ -886,8 +946,8 @@ def run_gpu(args):
         n_all, = env.reduce([c22["n_imputed"]], "SUM")
         line.update(value=n_all / (tot_ms / 1e3), ms_per_step=tot_ms, scaling="weak", dtype=c22["dtype"], config=chr22_config(),
                     gpu_launches=c22["launches"], clocks=c22["clocks"], imputed_per_step=c22["n_imputed"], host_affinity=env.numa)
-        for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings", "roofline", "roofline_gram", "roofline_chol", "roofline_expand5",
-                  "stage_ms", "stage_ms_serial", "solve"):
+        for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings", "pack", "roofline", "roofline_gram", "roofline_chol",
+                  "roofline_expand5", "stage_ms", "stage_ms_serial", "solve"):
             if k in c22:
                 line[k] = c22[k]
     elif workload in ("ld5000", "dist1kg"):

@@ -16,6 +16,8 @@
 
 using namespace gb;
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "gb_batch.cuh"
 
 extern "C" void gb_pipe_destroy(gb_pipe* pp);
@@ -546,8 +548,6 @@ gb_batch* batch_new(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const doubl
   if (params) b->params = *params;
   else gb_params_default(&b->params);
   b->n_windows = n_windows;
-  b->cm = ctx->gram_cm;
-  b->cn = ctx->gram_cn;
   b->defer_flag_check = defer_flag_check;
   return b;
 }
@@ -561,7 +561,18 @@ int check_device(Ctx* ctx) {
   return GB_OK;
 }
 
+int run_stage_impl(gb_batch* b, int stage);
+
+// NVTX range per stage: shows up in nsys / ncu timelines, costs nothing without a profiler attached
 int run_stage(gb_batch* b, int stage) {
+  static const char* const names[] = {"gb:row_stats", "gb:gram", "gb:cholesky", "gb:solve"};
+  nvtxRangePushA(stage >= 0 && stage < 4 ? names[stage] : stage == 10 ? "gb:gram_mma" : "gb:gram_finish");
+  const int rc = run_stage_impl(b, stage);
+  nvtxRangePop();
+  return rc;
+}
+
+int run_stage_impl(gb_batch* b, int stage) {
   Ctx* ctx = b->ctx;
   Panel* pn = b->panel;
   int rc = check_device(ctx);
@@ -578,11 +589,11 @@ int run_stage(gb_batch* b, int stage) {
                              b->d_pool_u, nullptr, b->d_st_sx_u, b->d_st_mean_u);
     }
     case 1:
-      if ((rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn, 0)))
+      if ((rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, 0)))
         return rc;
       return b->gp.raw_out ? launch_gram_finalize(ctx, b->gp, (int)b->h_tiles.size()) : GB_OK;
     case 10:  // profiling: the tensor-core kernel alone
-      return launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, b->cm, b->cn, 0);
+      return launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, 0);
     case 11:  // profiling: the finish pass alone (a no-op for panels whose finish is fused)
       return b->gp.raw_out ? launch_gram_finalize(ctx, b->gp, (int)b->h_tiles.size()) : GB_OK;
     case 2: {
@@ -721,18 +732,6 @@ int gb_ctx_create(int device, gb_ctx** out) {
   if (const char* e = getenv("GB_SEG_ORDER")) ctx->seg_order = atoi(e);   // tuning knob: 0 panel order, 1 descending, 2 alternating
   if (const char* e = getenv("GB_CHOL_SMS")) ctx->chol_sms = atoi(e);   // tuning knob; 0 = no overlap
   if (const char* e = getenv("GB_GRAM_KIND")) ctx->e2m1_mxf4 = strcmp(e, "f8f6f4") != 0;
-  if (const char* e = getenv("GB_GRAM_CLUSTER")) {  // tuning knob: "CMxCN", e.g. 2x2
-    int cm = 0, cn = 0;
-    if (sscanf(e, "%dx%d", &cm, &cn) == 2 && gram_cluster_supported(cm, cn)) {
-      ctx->gram_cm = cm;
-      ctx->gram_cn = cn;
-    } else {
-      g_create_err = std::string("GB_GRAM_CLUSTER=") + e + " is not a supported cluster shape";
-      cudaStreamDestroy(ctx->own_stream);
-      delete ctx;
-      return GB_ERR_BAD_ARG;
-    }
-  }
   {  // keep freed blocks cached in the device's default pool instead of returning them to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -998,7 +997,7 @@ static int run_gram_range(gb_batch* b, int first, int count, int max_ctas, int* 
   gp.tile_counter = tile_counter;
   int rc = GB_OK;
   if (with_kernel)
-    rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, gp, b->cm, b->cn, max_ctas);
+    rc = launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, gp, max_ctas);
   if (rc || !with_finish) return rc;
   return gp.raw_out ? launch_gram_finalize(ctx, gp, count) : GB_OK;
 }
@@ -2152,8 +2151,6 @@ int gb_run_window_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const lo
   return rc;
 }
 
-}  // extern "C"
-
 // ---- host-side mirror of run_qcat / run_qcatmix (qcat.cpp:134-262, qcatmix.cpp:145-286) -----------------
 int gb_run_qcat_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const long long* bp, const double* z,
                         const char* const* pop_strings, int n_pops, const int* pop_sizes, const double* pop_wgt,
@@ -2219,6 +2216,8 @@ int gb_run_qcat_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const long
   }
   return rc;
 }
+
+}  // extern "C"
 
 namespace gb {
 

@@ -68,7 +68,6 @@ struct gb_batch {
   int8_t* d_scratch = nullptr;
   gb::RowMaps tmaps_scratch;
   int fkind = 0;                      // tensor-core kind of this batch (GramParams::fkind)
-  int cm = 1, cn = 1;                 // Gram cluster shape this batch was planned for
   bool defer_flag_check = false;      // pipelined path: the panel is still being packed at plan time
   std::vector<int> h_status;          // fetch staging: [2*n_windows + 2 status words | panel flags]
   gb::GramParams gp{};

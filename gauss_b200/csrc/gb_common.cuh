@@ -44,7 +44,7 @@ struct GramTile {      // one 128 x 128 output tile
 };
 
 struct GramParams {
-  const GramTile* tiles;  // cm*cn descriptors per cluster tile, in cluster-rank order (r*cn + c)
+  const GramTile* tiles;  // one descriptor per 128 x 128 output tile
   int n_tiles;            // number of tiles
   int* tile_counter;      // nullptr: tiles dealt round-robin; else a zeroed device counter several launches draw tile ids from
   int mode;
@@ -93,18 +93,12 @@ struct Ctx {
   int64_t launches = 0;
   // lazily grown device scratch shared by the single-window entry points
   void* fn_encode_tiled = nullptr;  // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
-  // Thread-block cluster shape of the Gram kernel (A tiles x B tiles).  Measured on B200:
-  // an SM takes in about one 128-byte TMA row every ~3.5 clocks whoever requested it, so multicast
-  // does not raise the feed rate and only couples the CTAs; 1 x 1 is the fastest shape.
-  int gram_cm = 1, gram_cn = 1;
-  int gram_clusters = 0;            // clusters of the last Gram launch (diagnostics)
   int panel_format = GB_PANEL_E2M1; // format gb_panel_create uses (GB_PANEL_FORMAT=int8|e2m1 overrides)
   int e2m1_mxf4 = 1;                // E2M1 panels: 1 = kind::mxf4 (packed nibbles, K = 64), 0 = kind::f8f6f4 (GB_GRAM_KIND)
 };
 
 // TMA descriptors of one row-major packed-row matrix {k_elems, n_rows} with boxes of 128 K columns x
-// {128, 64, 32, 16} rows: a CM x CN cluster fetches A tiles in 128/CN-row and B tiles in
-// 128/CM-row slices.
+// {128, 64, 32, 16} rows (the kernels use the 128-row box).
 enum MapFormat : int { MAP_INT8 = 0, MAP_E2M1_EXPAND = 1, MAP_E2M1_PACKED = 2 };
 struct RowMaps {
   static constexpr int N = 4;
@@ -157,12 +151,10 @@ int launch_row_prep(Ctx* ctx, const Panel* panel, const int32_t* d_rows, int64_t
 // gb_gram.cu
 int make_row_tensor_maps(Ctx* ctx, RowMaps* out, const void* base, int64_t n_rows, int64_t k_elems,
                          int64_t k_stride_bytes, int format);
-bool gram_cluster_supported(int cm, int cn);
 int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors);
 int launch_zmix_pairs(Ctx* ctx, const Panel* panel, const int32_t* d_counts, int n, const int32_t* d_rows,
                       const double* d_z, double* d_out);
-int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn,
-                int max_ctas);
+int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int max_ctas);
 
 // gb_solve.cu
 struct SolveWin {        // per-window solve descriptor

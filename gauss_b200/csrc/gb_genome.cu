@@ -26,6 +26,8 @@
 #include <string>
 #include <thread>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "gb_batch.cuh"
 
 using namespace gb;
@@ -170,6 +172,7 @@ struct gb_genome {
   int64_t batch_windows = 48;
   int n_streams = 2;
   int resident_mode = 0;       // 0 auto, 1 pack5, 2 e2m1
+  double expanded_gb = -1.0;   // >= 0: cap on the bytes spent on keeping batches expanded (GB_GENOME_EXPANDED_GB)
   uint64_t synth_seed = 0;
   // run arguments
   double* const* out_z = nullptr;
@@ -387,7 +390,7 @@ int shard_plan(gb_genome* g, Shard* sh) {
     // start with everything ternary (+ the two working panels), then keep batches expanded while the budget lasts
     const double base = (double)sh->resident_rows * row_t + (double)n_slots * (double)max_seg_rows * row_e;
     double extra_budget = (double)free_b * 0.93 - (double)n_slots * (double)arena_est * 1.05 - 4e9 - base;
-    if (const char* e = getenv("GB_GENOME_EXPANDED_GB")) extra_budget = atof(e) * 1e9;   // tuning / tests: cap on the extra bytes
+    if (g->expanded_gb >= 0.0) extra_budget = g->expanded_gb * 1e9;   // GB_GENOME_EXPANDED_GB (tuning / tests): cap on the extra bytes
     const bool force_t = g->resident_mode == 1, force_e = g->resident_mode == 2;
     double used = 0.0;
     for (Segment& s : sh->segs) {
@@ -706,13 +709,21 @@ void shard_thread(gb_genome* g, Shard* sh) {
     int rc = GB_OK;
     sh->err.clear();
     switch (cmd) {
-      case CMD_PLAN: rc = shard_plan(g, sh); break;
+      case CMD_PLAN:
+        nvtxRangePushA("gb:genome_plan");
+        rc = shard_plan(g, sh);
+        nvtxRangePop();
+        break;
       case CMD_UPLOAD: {
         rc = shard_rows(g, sh, false);
         break;
       }
       case CMD_FILL: rc = shard_rows(g, sh, true); break;
-      case CMD_RUN: rc = shard_run(g, sh); break;
+      case CMD_RUN:
+        nvtxRangePushA("gb:genome_run");
+        rc = shard_run(g, sh);
+        nvtxRangePop();
+        break;
       default: break;
     }
     {
@@ -777,6 +788,7 @@ int gb_genome_create(int n_gpus, const int* devices, int n_pops, const int* pop_
   }
   if (const char* e = getenv("GB_GENOME_BATCH_WINDOWS")) g->batch_windows = std::max(1, atoi(e));
   if (const char* e = getenv("GB_GENOME_STREAMS")) g->n_streams = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("GB_GENOME_EXPANDED_GB")) g->expanded_gb = atof(e);
   if (const char* e = getenv("GB_GENOME_RESIDENT")) g->resident_mode = !strcmp(e, "pack5") ? 1 : !strcmp(e, "e2m1") ? 2 : 0;
   for (int i = 0; i < n_gpus; i++) {
     Shard* sh = new Shard();

@@ -365,8 +365,7 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
       if (ct < 0) break;
       const GramTile t = prm.tiles[ct];
       if (t.a_valid <= 0 || t.b_valid <= 0) {
-        // padding slot of a ragged cluster tile: the MMAs ran (peers need this CTA's slices and
-        // barrier traffic) but nothing is stored; just hand the accumulators back
+        // empty descriptor: the MMAs ran, nothing is stored; just hand the accumulators back
         for (int s = 0; s < n_seg; s++) {
           ptx::mbar_wait(&tfull_bar[acc_buf], acc_phase);
           __syncwarp();
@@ -778,15 +777,10 @@ int launch_gram_t(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const 
   kern<<<(unsigned)n_ctas, THREADS, SMEM_ALLOC, ctx->stream>>>(panel.m[0], scratch.m[0], panel.m[0], scratch.m[0], prm);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
-  ctx->gram_clusters = n_ctas;
   return GB_OK;
 }
 
 }  // namespace
-
-// Round 1 built and measured CM x CN thread-block clusters with TMA multicast (2x1 ... 4x2, 8x1); all were
-// slower than independent CTAs and the code is gone: only 1 x 1 is accepted.
-bool gram_cluster_supported(int cm, int cn) { return cm == 1 && cn == 1; }
 
 int launch_zmix_pairs(Ctx* ctx, const Panel* panel, const int32_t* d_counts, int n, const int32_t* d_rows,
                       const double* d_z, double* d_out) {
@@ -813,13 +807,8 @@ int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors) {
   return GB_OK;
 }
 
-int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int cm, int cn,
-                int max_ctas) {
+int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const GramParams& prm, int max_ctas) {
   if (prm.n_tiles <= 0) return GB_OK;
-  if (cm != 1 || cn != 1) {
-    ctx->err = "unsupported Gram cluster shape";
-    return GB_ERR_UNSUPPORTED;
-  }
   if (prm.n_seg > P_MAX) {
     ctx->err = "too many population segments for the Gram kernel";
     return GB_ERR_UNSUPPORTED;

@@ -42,6 +42,7 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = is_ascii ? 48 : 0;
   bool bad = false, big = false;
+  const bool aligned_src = (reinterpret_cast<uintptr_t>(src) & 3) == 0;   // else the first word of the buffer may not be touched
   // source offset of population p = sum of sizes before it
   int src_off = 0;
   int next_p = 0;
@@ -53,10 +54,24 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
     int sum = 0, sq = 0;
     for (int j = lane * 8; j < kp; j += 256) {
       uint32_t lo = 0, hi = 0;
+      // eight source bytes: two funnel-shifted words out of three ALIGNED 32-bit loads (population offsets are not
+      // aligned), byte loads only where the block ends or the buffer itself is unaligned
+      uint32_t raw_lo = 0, raw_hi = 0;
+      // the three words cover [a & ~3, a & ~3 + 12): inside the row's population block, and not before the buffer
+      const bool fast = j + 12 <= m && (aligned_src || row * src_stride + src_off + j >= 4);
+      if (fast) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(sp + j);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3) * 8;
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+        raw_lo = __funnelshift_r(w0, w1, sh);
+        raw_hi = __funnelshift_r(w1, w2, sh);
+      }
 #pragma unroll
       for (int b = 0; b < 8; b++) {
         int v = 0;
-        if (j + b < m) v = (int)(signed char)((int)sp[j + b] - sub);
+        if (fast) v = (int)(signed char)((int)(((b < 4 ? raw_lo : raw_hi) >> (8 * (b & 3))) & 0xffu) - sub);
+        else if (j + b < m) v = (int)(signed char)((int)sp[j + b] - sub);
         sum += v;
         sq += v * v;
         big |= (unsigned)v > 2u;

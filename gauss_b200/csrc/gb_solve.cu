@@ -866,13 +866,17 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
     return GB_ERR_UNSUPPORTED;
   }
   const dim3 grid((unsigned)((max_nu + ub - 1) / ub), (unsigned)n_wins);
-  if (narrow) {
-    GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trsm_finalize_kernel<64><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
-  } else {
-    GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trsm_finalize_kernel<128><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
+  // the opt-in shared-memory limit is a per-device function attribute: raise it only when a launch needs more than
+  // any earlier one did
+  static size_t attr_smem[64][2] = {};
+  size_t& have = attr_smem[ctx->device & 63][narrow ? 1 : 0];
+  if (smem > have) {
+    if (narrow) GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
   }
+  if (narrow) trsm_finalize_kernel<64><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
+  else trsm_finalize_kernel<128><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

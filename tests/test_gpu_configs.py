@@ -82,6 +82,32 @@ def test_cfg2_full_size_33kg_window(gpu_ctx, oracle):
     assert (info > 0).all() and (info <= 1.0 + 1e-12).all()
 
 
+def test_cfg2_mean_size_window_against_the_oracle_end_to_end(gpu_ctx, oracle):
+    """configs[1] once at the MEAN window size of chr22 (n_t = 742 measured) through the whole oracle -- the restated
+    run_distmix with its eigendecomposition and full-pivot LU inverse -- at the full 32,147 individuals; 160 of the
+    window's unmeasured SNPs keep the oracle's O(n_t n_u N) loop to ~20 s."""
+    _, sizes, w = synth.flagged_33kg_pgc2()
+    d = np.load(SITES)
+    bp_m = np.unique(d["bp"].astype(np.int64))
+    _, _, windows = synth.chr22_windows(bp_m)
+    nts = np.array([len(x["measured"]) for x in windows])
+    win = windows[int(np.argmin(np.abs(nts - 742)))]
+    n_t, n_u = len(win["measured"]), 160
+    assert 700 <= n_t <= 790
+    g = synth.make_genotypes(n_t + n_u, sizes, seed=43)
+    rng = np.random.default_rng(43)
+    z_t = rng.standard_normal(n_t) * 1.34
+    panel = gb.Panel(gpu_ctx, sizes, len(g))
+    panel.append_host(g, is_ascii=False)
+    z, info, rc = panel.window_distmix(np.arange(n_t), np.arange(n_t, n_t + n_u), z_t, w)
+    assert rc == gb.GB_OK
+    t = np.concatenate([np.ones(n_t, np.int32), np.zeros(n_u, np.int32)])
+    r = oracle.run_window(t, np.arange(n_t + n_u, dtype=np.int64), np.concatenate([z_t, np.zeros(n_u)]), g, sizes, w, 0, 10 ** 12)
+    assert r["rc"] == 0 and r["n_t"] == n_t
+    assert np.abs(z - r["z"][n_t:]).max() <= TOL and np.abs(info - r["info"][n_t:]).max() <= TOL
+    assert np.abs(z - r["z"][n_t:]).max() <= 1e-8 and np.abs(info - r["info"][n_t:]).max() <= 1e-9
+
+
 def test_cfg3_compute_ld_5000_snp_block(gpu_ctx, oracle):
     """configs[2]: computeLD() on a dense 5,000-SNP block, ancestry-mixed, 33KG-shaped panel."""
     _, sizes, w = synth.flagged_33kg_pgc2()

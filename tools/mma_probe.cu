@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "gb_ptx.cuh"
+#include "probe_ptx.cuh"
 
 using namespace gb;
 

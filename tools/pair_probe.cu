@@ -7,7 +7,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
-#include "gb_ptx.cuh"
+#include "probe_ptx.cuh"
 
 using namespace gb;
 
