@@ -45,8 +45,9 @@ enum gb_status {
   /* "Not enough number of SNPs loaded - DIST[MIX] not performed": dist.cpp:146-151, distmix.cpp:154-160 */
   GB_ERR_TOO_FEW_MEASURED = 5,
   GB_ERR_TOO_FEW_UNMEASURED = 6,
-  /* B11 is not certified to satisfy lambda_min >= min_abs_eig, i.e. the reference's MakePosDef
-   * (util.cpp:302-318) would have modified it; no eigen-clip path exists on the device. */
+  /* B11 is not certified to satisfy lambda_min >= min_abs_eig, i.e. the reference's MakePosDef (util.cpp:302-318) may
+   * have modified it.  The imputation entry points (window / batch / chromosome / pipe / genome) do not return this any
+   * more: such windows are eigendecomposed and clipped on the device like MakePosDef and come back GB_OK. */
   GB_ERR_NOT_PD = 7,
   GB_ERR_UNSUPPORTED = 8,
   /* The Cholesky factorisation of B11 itself met a non-positive pivot (lambda = 0 with duplicated SNPs, negative
@@ -66,8 +67,8 @@ typedef struct gb_params {
   double min_abs_eig;         /* 1e-5  MakePosDef threshold (dist.cpp:181) */
   int min_num_measured_snp;   /* 10    window rejected if n_t <= this */
   int min_num_unmeasured_snp; /* 10    window rejected if n_u <= this */
-  int check_pd;               /* 1: certify lambda_min(B11) > min_abs_eig with a shifted Cholesky
-                                 (GB_ERR_NOT_PD otherwise); 0: only detect factorisation breakdown */
+  int check_pd;               /* 1: certify lambda_min(B11) > min_abs_eig (analytic bound, else a shifted Cholesky) and send
+                                 uncertified windows through the eigen-clip path; 0: only detect factorisation breakdown */
   int reserved;
 } gb_params;
 
@@ -95,8 +96,9 @@ GB_API int gb_panel_create(gb_ctx *ctx, int n_pops, const int *pop_sizes, int64_
  * exact integer counts; they differ in bytes per dosage.
  *   GB_PANEL_INT8  one signed byte per dosage (kind::i8, int32 accumulate): exact for ANY byte the
  *                  reference's (c - '0') arithmetic can produce.
- *   GB_PANEL_E2M1  one 4-bit E2M1 float per dosage (kind::f8f6f4, fp32 accumulate): half the HBM
- *                  footprint and twice the dosages per TMA row; exact for dosages in {0, 1, 2, 3, 4, 6}
+ *   GB_PANEL_E2M1  one 4-bit E2M1 float per dosage (tcgen05.mma kind::mxf4 with unit block scales, fp32
+ *                  accumulate; the DEFAULT): half the HBM footprint and twice the dosages per TMA row; exact for
+ *                  dosages in {0, 1, 2, 3, 4, 6}
  *                  (every product and every per-population sum is an integer below 2^24).  A row holding any other value makes the next
  *                  batch/window call fail with GB_ERR_UNSUPPORTED -- repack as GB_PANEL_INT8.
  * gb_panel_create uses GB_PANEL_E2M1 (real panels hold only '0','1','2') unless the environment
@@ -110,8 +112,9 @@ GB_API int gb_panel_clear(gb_panel *panel); /* forget all rows, keep the allocat
 GB_API int64_t gb_panel_num_rows(const gb_panel *panel);
 GB_API int64_t gb_panel_num_samples(const gb_panel *panel);
 /* Append SNP rows given as the reference stores them: n_rows * n_pops C strings, string
- * (r, p) holding pop_sizes[p] chars '0'/'1'/'2' (any 7-bit char c packs as c - '0', like the
- * reference's arithmetic).  HOST memory. */
+ * (r, p) holding EXACTLY pop_sizes[p] chars '0'/'1'/'2' (any 7-bit char c packs as c - '0', like the
+ * reference's arithmetic) and a terminating NUL -- std::string::c_str() of Snp::genotype_vec_; a shorter or longer
+ * string is GB_ERR_BAD_ARG (the reference's CalCor walks x[i].length() characters, util.cpp:55).  HOST memory. */
 GB_API int gb_panel_append_strings(gb_panel *panel, int64_t n_rows, const char *const *pop_strings);
 /* Same rows as one flat HOST buffer: row r at rows + r*row_stride, populations concatenated
  * (sum(pop_sizes) bytes).  is_ascii != 0: bytes are chars; 0: bytes are int8 dosages. */
