@@ -572,9 +572,11 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
     z, info = z.copy(), info.copy()
     n_ok = int((status == 0).sum())
     # ---- the same K steps stage by stage (serialised, every kernel on all SMs)
-    STAGES = [0, 10, 11, 2, 3]   # row statistics | Gram tensor-core kernel | Gram finish pass | Cholesky | solve
+    # row statistics | Gram tensor-core kernel | Gram finish pass | Cholesky | explicit L^-1 (int8-split solve only) | solve
+    STAGES = [0, 10, 11, 20, 21, 3]
     st = stage_times(env, batch, stream, args.steps, STAGES)
-    gram_ms, fin_ms, chol_ms, trsm_ms = (float(st[:, i].mean()) for i in (1, 2, 3, 4))
+    gram_ms, fin_ms, chol_ms, trtri_ms, trsm_ms = (float(st[:, i].mean()) for i in (1, 2, 3, 4, 5))
+    ozaki = os.environ.get("GB_SOLVE", "ozaki") != "fp64"
     nts = np.array([len(x["measured"]) for x in windows], float)
     nus = np.array([len(x["unmeasured"]) for x in windows], float)
     okw = (nts > 10) & (nus > 10)
@@ -587,7 +589,8 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
         value=n_imputed * args.steps / (total_ms / 1e3), ms_per_step=total_ms / args.steps, launches=int(launches), clocks=clocks,
         n_imputed=n_imputed, windows_ok=n_ok, panel_gen_s=gen_s, work=work, z=z, info=info, status=status,
         stage_ms_serial=float(st.sum(1).mean()),
-        stage_ms=dict(row_stats=float(st[:, 0].mean()), gram=gram_ms, gram_finish=fin_ms, cholesky=chol_ms, solve=trsm_ms),
+        stage_ms=dict(row_stats=float(st[:, 0].mean()), gram=gram_ms, gram_finish=fin_ms, cholesky=chol_ms, linv=trtri_ms, solve=trsm_ms),
+        solver="int8-split GEMM on tcgen05 (kind::i8, 7 x 7-bit digits, 28 digit pairs) behind an explicit L^-1" if ozaki else "fp64 DMMA triangular solve",
         roofline=dict(bound="tensor", kernel="trsm_finalize_kernel", achieved=trsm_flops / (trsm_ms / 1e3) / 1e12, peak=fp64_peak,
                       unit="TFLOP/s", frac=trsm_flops / (trsm_ms / 1e3) / 1e12 / fp64_peak,
                       traffic=NCU["trsm"].get("dram_bytes"), ms=trsm_ms, share_of_step=trsm_ms / float(st.sum(1).mean()),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgauss_b200.so")
-SOURCES = ["gb_api.cu", "gb_gram.cu", "gb_pack.cu", "gb_solve.cu", "gb_genome.cu", "gb_synth.cu", "gb_probe.cu", "gb_packfile.cu", "gb_gene.cu"]
+SOURCES = ["gb_api.cu", "gb_gram.cu", "gb_pack.cu", "gb_solve.cu", "gb_genome.cu", "gb_synth.cu", "gb_probe.cu", "gb_packfile.cu", "gb_gene.cu", "gb_ozaki.cu"]
 HEADERS = ["gb_common.cuh", "gb_ptx.cuh", "gb_batch.cuh", os.path.join("..", "..", "include", "gauss_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

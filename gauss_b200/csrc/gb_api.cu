@@ -319,6 +319,33 @@ int batch_plan_host(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, co
     b->max_nt = std::max(b->max_nt, sw.n_t);
     b->max_nu = std::max(b->max_nu, sw.n_u);
   }
+  b->ozaki = ctx->solve_ozaki && !b->ld_mode && !b->counts_mode && !b->h_wins.empty() && b->max_nt <= 2048;
+  if (b->ozaki) {
+    b->oz_kpad = (b->max_nt + 127) / 128 * 128;
+    b->h_oz_wins.resize(b->h_wins.size() * ozaki_win_bytes());
+    ozaki_plan(b->h_wins.data(), (int)b->h_wins.size(), b->oz_kpad, b->h_oz_wins.data(), &b->h_oz_tiles, &b->oz_a_rows, &b->oz_b_rows);
+    b->oz_n_tiles = (int)(b->h_oz_tiles.size() / ozaki_tile_bytes());
+    // B21 tiles learn where their rows sit in the digit planes (a tile belongs to the window whose B21 block it writes)
+    for (GramTile& t : b->h_tiles) {
+      if (!t.a_is_u) continue;
+      for (size_t i = 0; i < b->h_wins.size(); i++)
+        if (b->h_wins[i].off_ut == t.out_off && b->h_wins[i].ld_u == t.ld_out) {
+          long long a_row0;
+          int ra;
+          ozaki_tile_rows(b->h_oz_wins.data(), (int)i, &a_row0, &ra);
+          t.oz_ra = ra;
+          t.oz_row0 = a_row0 + t.i0;
+          break;
+        }
+    }
+    b->h_wins_x = b->h_wins;
+    for (SolveWin& sw : b->h_wins_x) {   // X = L^-1 is laid out like B11 (n_t x ld_t, here row-major); outputs go to scratch
+      sw.n_u = sw.n_t;
+      sw.ld_u = sw.ld_t;
+      sw.off_ut = sw.off_tt;
+      sw.off_u = sw.off_t;
+    }
+  }
   return GB_OK;
 }
 
@@ -326,7 +353,7 @@ int batch_plan_host(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, co
 // the allocation itself so the two cannot drift apart.
 namespace {
 struct TransientSizes {
-  size_t sd_u, pool_u, st_sx_t, st_mean_t, st_sx_u, st_mean_u, counts, tt, ut, dinv, zu, info, scratch, clip;
+  size_t sd_u, pool_u, st_sx_t, st_mean_t, st_sx_u, st_mean_u, counts, tt, ut, dinv, zu, info, scratch, clip, oz_x, oz_pa, oz_pb;
 };
 TransientSizes transient_sizes(const gb_batch* b) {
   const Panel* pn = b->panel;
@@ -353,6 +380,11 @@ TransientSizes transient_sizes(const gb_batch* b) {
     }
   }
   s.scratch = (size_t)b->n_gather * (size_t)pn->k_stride;
+  if (b->ozaki) {
+    s.oz_x = sizeof(double) * (size_t)b->tt_elems;
+    s.oz_pa = (size_t)b->oz_a_rows * (size_t)b->oz_kpad;
+    s.oz_pb = (size_t)b->oz_b_rows * (size_t)b->oz_kpad;
+  }
   return s;
 }
 }  // namespace
@@ -360,7 +392,7 @@ TransientSizes transient_sizes(const gb_batch* b) {
 size_t batch_arena_bytes(const gb_batch* b) {
   const TransientSizes s = transient_sizes(b);
   const size_t all[] = {s.sd_u, s.pool_u, s.st_sx_t, s.st_mean_t, s.st_sx_u, s.st_mean_u, s.counts,
-                        s.tt, s.ut, s.dinv, s.zu, s.info, s.scratch};
+                        s.tt, s.ut, s.dinv, s.zu, s.info, s.scratch, s.oz_x, s.oz_pa, s.oz_pb};
   size_t total = 0;
   for (size_t v : all) total += align256(v ? v : 1);
   return total + 4096;
@@ -428,6 +460,21 @@ int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
       if ((rc = take(&b->d_info, s.info))) return rc;
     }
   }
+  if (b->ozaki) {
+    if ((rc = dev_upload(b, &b->d_wins_x, b->h_wins_x))) return rc;
+    uint8_t* tmp = nullptr;
+    if ((rc = dev_upload(b, &tmp, b->h_oz_wins))) return rc;
+    b->d_oz_wins = tmp;
+    if ((rc = dev_upload(b, &tmp, b->h_oz_tiles))) return rc;
+    b->d_oz_tiles = tmp;
+    if ((rc = dev_alloc(b, &b->d_oz_y, (size_t)b->n_t_total))) return rc;
+    if ((rc = dev_alloc(b, &b->d_oz_scr, 2 * (size_t)b->n_t_total))) return rc;
+    if ((rc = dev_alloc(b, &b->d_oz_amax, b->h_wins.size()))) return rc;
+    if ((rc = dev_alloc(b, &b->d_oz_ex, b->h_wins.size()))) return rc;
+    if ((rc = take(&b->d_x, s.oz_x))) return rc;
+    if ((rc = take(&b->d_oz_pa, s.oz_pa))) return rc;
+    if ((rc = take(&b->d_oz_pb, s.oz_pb))) return rc;
+  }
   if (b->clip_mode) {
     if ((rc = dev_alloc(b, &b->d_eig_G, (size_t)b->tt_elems))) return rc;
     if ((rc = dev_alloc(b, &b->d_eig_V, (size_t)b->tt_elems))) return rc;
@@ -458,6 +505,8 @@ int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
   gp.out_ut = b->d_ut;
   gp.out_counts = b->d_counts;
   gp.counts_seg_stride = b->counts_elems;
+  gp.oz_pa = (b->ozaki && gp.raw_out) ? b->d_oz_pa : nullptr;   // the finish pass writes B21's digit planes itself
+  gp.oz_kpad = b->oz_kpad;
   if (!sync) return GB_OK;
   // the same sync makes the pack kernels' representability flag readable
   int h_flags = 0;
@@ -566,7 +615,7 @@ int run_stage_impl(gb_batch* b, int stage);
 // NVTX range per stage: shows up in nsys / ncu timelines, costs nothing without a profiler attached
 int run_stage(gb_batch* b, int stage) {
   static const char* const names[] = {"gb:row_stats", "gb:gram", "gb:cholesky", "gb:solve"};
-  nvtxRangePushA(stage >= 0 && stage < 4 ? names[stage] : stage == 10 ? "gb:gram_mma" : "gb:gram_finish");
+  nvtxRangePushA(stage >= 0 && stage < 4 ? names[stage] : stage == 10 ? "gb:gram_mma" : stage == 11 ? "gb:gram_finish" : stage == 20 ? "gb:cholesky_only" : "gb:trtri");
   const int rc = run_stage_impl(b, stage);
   nvtxRangePop();
   return rc;
@@ -596,7 +645,8 @@ int run_stage_impl(gb_batch* b, int stage) {
       return launch_gram(ctx, b->fkind == 7 ? pn->tmaps_packed : pn->tmaps, b->tmaps_scratch, b->gp, 0);
     case 11:  // profiling: the finish pass alone (a no-op for panels whose finish is fused)
       return b->gp.raw_out ? launch_gram_finalize(ctx, b->gp, (int)b->h_tiles.size()) : GB_OK;
-    case 2: {
+    case 2:
+    case 20: {
       if (b->ld_mode || b->counts_mode) return GB_OK;
       const int nreal = (int)b->h_wins.size();
       GB_CUDA(cudaMemsetAsync(b->d_status, 0, sizeof(int) * (2 * (size_t)b->n_windows + 2), ctx->stream));
@@ -618,10 +668,29 @@ int run_stage_impl(gb_batch* b, int stage) {
           return rc;
         skip = b->d_skip;
       }
-      return launch_cholesky(ctx, b->d_wins, b->n_chol_wins, b->max_nt, b->d_tt, b->d_dinv, b->d_status, skip);
+      if ((rc = launch_cholesky(ctx, b->d_wins, b->n_chol_wins, b->max_nt, b->d_tt, b->d_dinv, b->d_status, skip))) return rc;
+      if (stage == 20) return GB_OK;   // profiling: the factorisation alone
+    }
+    // fall through
+    case 21: {
+      if (b->ld_mode || b->counts_mode) return GB_OK;
+      if (b->ozaki && !b->d_y) {
+        // int8-split solve: X = L^-1 by the blocked trsm kernel on identity columns (zero blocks skipped; it also leaves
+        // y = L^-1 z_t).  It needs L only, so it rides with the factorisation (beside the B21 Gram tiles in gb_batch_run)
+        const int nw = (int)b->h_wins.size();
+        if ((rc = launch_ozaki_prepare_identity(ctx, b->d_wins_x, nw, b->d_x))) return rc;
+        return launch_trsm_finalize(ctx, b->d_wins_x, nw, b->max_nt, b->max_nt, b->d_tt, b->d_dinv, b->d_x, b->d_zt,
+                                    b->d_oz_scr, b->d_oz_scr + b->n_t_total, b->d_oz_y, /*tri=*/1);
+      }
+      return GB_OK;
     }
     case 3:
       if (b->ld_mode || b->counts_mode) return GB_OK;
+      if (b->ozaki && !b->d_y)
+        // W^T = B21 X^T as an exact digit-split GEMM on tcgen05 (gb_ozaki.cu); X and y come from stage 2
+        return launch_ozaki_solve(ctx, b->d_wins, b->d_oz_wins, b->h_oz_wins.data(), (int)b->h_wins.size(), b->d_oz_tiles,
+                                  b->oz_n_tiles, b->oz_kpad, b->d_x, b->d_ut, b->gp.oz_pa == nullptr, b->d_oz_pa, b->oz_a_rows,
+                                  b->d_oz_pb, b->oz_b_rows, b->d_oz_amax, b->d_oz_ex, b->d_oz_y, b->d_zu, b->d_info);
       return launch_trsm_finalize(ctx, b->d_wins, (int)b->h_wins.size(), b->max_nt, b->max_nu, b->d_tt, b->d_dinv,
                                   b->d_ut, b->d_zt, b->d_zu, b->d_info, b->d_y);
     default:
@@ -732,6 +801,7 @@ int gb_ctx_create(int device, gb_ctx** out) {
   if (const char* e = getenv("GB_SEG_ORDER")) ctx->seg_order = atoi(e);   // tuning knob: 0 panel order, 1 descending, 2 alternating
   if (const char* e = getenv("GB_CHOL_SMS")) ctx->chol_sms = atoi(e);   // tuning knob; 0 = no overlap
   if (const char* e = getenv("GB_GRAM_KIND")) ctx->e2m1_mxf4 = strcmp(e, "f8f6f4") != 0;
+  if (const char* e = getenv("GB_SOLVE")) ctx->solve_ozaki = strcmp(e, "fp64") != 0;   // "fp64": the DMMA triangular solve
   {  // keep freed blocks cached in the device's default pool instead of returning them to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -1264,7 +1334,10 @@ int gb_window_cor(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* rows
   const int64_t t_off[2] = {0, n_t}, u_off[2] = {0, n_u};
   std::vector<double> zt((size_t)n_t, 0.0);
   gb_batch* b = nullptr;
+  const int keep_solver = ctx->solve_ozaki;   // this surface returns B21 as doubles: not the digit planes of the int8-split solve
+  ctx->solve_ozaki = 0;
   int rc = gb_batch_create(ctx, panel, 1, t_off, rows_t, u_off, rows_u, zt.data(), pop_wgt, &p, &b);
+  ctx->solve_ozaki = keep_solver;
   if (rc) return rc;
   rc = run_stage(b, 0);
   if (!rc) rc = run_stage(b, 1);
@@ -1796,8 +1869,12 @@ int gb_window_qcat(gb_ctx* ctx, gb_panel* panel, int64_t n_t, const int64_t* row
   const int64_t t_off[2] = {0, n_t}, u_off[2] = {0, n_test};
   double dummy = 0.0;
   gb_batch* b = nullptr;
+  // qcat correlates y with every column of W: it keeps the fp64 triangular solve, which stores W
+  const int keep_solver = ctx->solve_ozaki;
+  ctx->solve_ozaki = 0;
   int rc = create_batch_internal(ctx, panel, 1, t_off, rows_t, u_off, ru.data(), z_t ? z_t : &dummy, pop_wgt, &p, false,
                                  false, &b);
+  ctx->solve_ozaki = keep_solver;
   if (rc) return rc;
   auto done = [&](int code) {
     cudaStreamSynchronize(ctx->stream);

@@ -71,6 +71,18 @@ struct gb_batch {
   bool defer_flag_check = false;      // pipelined path: the panel is still being packed at plan time
   std::vector<int> h_status;          // fetch staging: [2*n_windows + 2 status words | panel flags]
   gb::GramParams gp{};
+  // int8-split solve (ctx->solve_ozaki at plan time)
+  bool ozaki = false;
+  int oz_kpad = 0, oz_n_tiles = 0;
+  long long oz_a_rows = 0, oz_b_rows = 0;
+  std::vector<uint8_t> h_oz_wins, h_oz_tiles;
+  std::vector<gb::SolveWin> h_wins_x;       // the windows as the trtri-by-trsm sees them (n_u = n_t, X in place of W)
+  gb::SolveWin* d_wins_x = nullptr;
+  void *d_oz_wins = nullptr, *d_oz_tiles = nullptr;
+  double *d_x = nullptr, *d_oz_y = nullptr, *d_oz_scr = nullptr;
+  int8_t *d_oz_pa = nullptr, *d_oz_pb = nullptr;
+  unsigned long long* d_oz_amax = nullptr;
+  int* d_oz_ex = nullptr;
   // memory: `owned` pointers are freed with the batch; buffers carved from `arena` (when set) are not
   std::vector<void*> owned;
   gb::Arena arena;

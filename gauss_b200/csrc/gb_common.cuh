@@ -41,6 +41,10 @@ struct GramTile {      // one 128 x 128 output tile
   int i0, j0;          // local coordinates of the tile inside the window's output matrix
   int ld_out;          // leading dimension of the output matrix (doubles / int32)
   long long out_off;   // element offset of the window's output matrix in the output buffer
+  // int8-split solve (B21 tiles only): the finish pass writes the digit planes of B21 instead of its doubles
+  int oz_ra;           // rows per digit plane of the window (0: not an int8-split batch)
+  int oz_pad;
+  long long oz_row0;   // row of digit plane 0 that holds the tile's first A row
 };
 
 struct GramParams {
@@ -75,6 +79,8 @@ struct GramParams {
   double* out_ut;        // B21^T buffers ([n_t][ld_u], u contiguous)
   int32_t* out_counts;   // GRAM_COUNTS: [n_seg][n_a][n_b]
   long long counts_seg_stride;
+  int8_t* oz_pa;         // int8-split solve: digit planes of B21 ([plane][u][k], k contiguous), written by the finish pass
+  int oz_kpad;           // bytes per plane row
 };
 
 // ------------------------------------------------------------------ context / panel
@@ -95,6 +101,7 @@ struct Ctx {
   void* fn_encode_tiled = nullptr;  // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int panel_format = GB_PANEL_E2M1; // format gb_panel_create uses (GB_PANEL_FORMAT=int8|e2m1 overrides)
   int e2m1_mxf4 = 1;                // E2M1 panels: 1 = kind::mxf4 (packed nibbles, K = 64), 0 = kind::f8f6f4 (GB_GRAM_KIND)
+  int solve_ozaki = 1;              // 1: the solve's n_t^2 n_u term runs as an int8-split GEMM on tcgen05 (GB_SOLVE=fp64 opts out)
 };
 
 // TMA descriptors of one row-major packed-row matrix {k_elems, n_rows} with boxes of 128 K columns x
@@ -174,7 +181,7 @@ int launch_pd_bound(Ctx* ctx, const SolveWin* d_wins, int n_real, const double* 
                     double gneg, double min_abs_eig, int* d_skip);
 int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,
                          const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info,
-                         double* d_y_out);
+                         double* d_y_out, int tri = 0);
 int launch_qcat_patch(Ctx* ctx, const SolveWin* d_wins, double* d_ut, int n_u, int core_first, int n_core, double diag);
 int launch_qcat_finalize(Ctx* ctx, const SolveWin* d_wins, const double* d_ut, const double* d_y, int n_tested,
                          int num_eig, double* d_qt, double* d_qchisq);
@@ -182,6 +189,19 @@ int launch_eig_jacobi(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, 
                       double* d_evals, double min_abs_eig, int clip, int* d_n_clipped);
 int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double* d_src, double* d_dst,
                       double shift, const int* d_skip);
+
+// gb_ozaki.cu: the solve's n_t^2 n_u term as an exact int8-split GEMM on tcgen05 (kind::i8)
+constexpr int OZ_NDIG = 7;   // signed 7-bit digit planes per operand
+size_t ozaki_win_bytes();
+size_t ozaki_tile_bytes();
+void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, void* ow_out, std::vector<uint8_t>* tiles_out, long long* a_rows,
+                long long* b_rows);
+int launch_ozaki_prepare_identity(Ctx* ctx, const SolveWin* d_wins, int n_wins, double* d_x);
+int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const void* h_ow, int n_wins, const void* d_tiles,
+                       int n_tiles, int kpad, const double* d_x, const double* d_ut, int slice_b21, int8_t* d_planes_a,
+                       long long a_rows, int8_t* d_planes_b, long long b_rows, unsigned long long* d_amax, int* d_ex,
+                       const double* d_y, double* d_zu, double* d_info);
+void ozaki_tile_rows(const void* h_ow, int win, long long* a_row0, int* ra);
 
 // gb_gene.cu
 int launch_jepeg_genes(Ctx* ctx, const void* d_genes, int n_genes, const double* d_tt, const double* d_z, const double* d_info,

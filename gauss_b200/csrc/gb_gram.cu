@@ -626,6 +626,7 @@ gram_finalize_kernel(const __grid_constant__ GramParams prm) {
   const long long gi = t.i0 + r;
   const bool diag_tile = (!t.a_is_u) && (t.i0 == t.j0);
   const double ai = aiS[r], sd_r = sdA[r];
+  const bool oz = prm.oz_pa != nullptr && t.a_is_u && t.oz_ra > 0;
 #pragma unroll 1
   for (int ch = 0; ch < EPI_COLS / 8; ch++) {
     double x[8];
@@ -647,6 +648,32 @@ gram_finalize_kernel(const __grid_constant__ GramParams prm) {
         x[2 * k2] = fma(g, h2.x, x[2 * k2]);
         x[2 * k2 + 1] = fma(g, h2.y, x[2 * k2 + 1]);
       }
+    }
+    if (oz) {
+      // int8-split solve: this B21 tile leaves as the 7 signed 7-bit digit planes of its correlations (|r| <= 1: scale
+      // 2^0, 49-bit fixed point), 8 consecutive k of row u per 64-bit store and plane; the doubles are not stored
+      uint32_t lo[OZ_NDIG], hi[OZ_NDIG];
+#pragma unroll
+      for (int p = 0; p < OZ_NDIG; p++) lo[p] = hi[p] = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int c = c0 + ch * 8 + k;
+        const double cor = ok[k] ? __ddiv_rn(fma(-ai, bjS[c], x[k]), __dmul_rn(sd_r, sdB[c])) : 0.0;
+        long long q = __double2ll_rn(ldexp(cor, 7 * OZ_NDIG - 2));
+#pragma unroll
+        for (int p = 0; p < OZ_NDIG; p++) {
+          const long long dd = ((q + 64) & 127) - 64;
+          q = (q - dd) >> 7;
+          const uint32_t byte = (uint32_t)(uint8_t)(int8_t)dd << (8 * (k & 3));
+          if (k < 4) lo[p] |= byte;
+          else hi[p] |= byte;
+        }
+      }
+      int8_t* prow = prm.oz_pa + (t.oz_row0 + r) * (long long)prm.oz_kpad + t.j0 + c0 + ch * 8;
+#pragma unroll
+      for (int p = 0; p < OZ_NDIG; p++)
+        *reinterpret_cast<uint2*>(prow + (long long)p * t.oz_ra * prm.oz_kpad) = make_uint2(lo[p], hi[p]);
+      continue;
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {

@@ -1,0 +1,482 @@
+// gb_ozaki.cu -- the solve's n_t^2 n_u term on the int8 tensor cores (tcgen05.mma kind::i8), exact-integer split.
+//
+// fp64 is the weak pipe of this chip (36.9 TFLOP/s measured against 4,518 int8 TOP/s), and the triangular solve
+// W = L^-1 B21^T is the longest kernel of a step.  This path replaces it by a GEMM without the trsm's sequential
+// dependency and moves the GEMM to the tensor cores:
+//   X  = L^-1                 (explicit: the blocked trsm kernel on identity columns, zero blocks skipped; + n_t^3 / 3)
+//   W^T = B21 X^T             (n_u x n_t, only ||W_col||^2 and W_col . y are needed: W is never stored)
+// Both operands are split into NDIG = 7 signed 7-bit digits of a 49-bit fixed-point value (x = 2^e sum_s d_s 2^(7s - 47),
+// d_s in [-64, 63]); every digit-pair product sum_k dB_s[u, k] dX_t[r, k] is an exact int32 (|.| <= 64^2 K); pairs of
+// equal weight s + t share one TMEM accumulator; the NG = 7 heaviest weight groups (s + t >= 6: 28 pairs) are recombined
+// in fp64 (2^(7 (s + t) - 94 + e_X) each).  Quantisation (2^-47 of the scale per entry) and the dropped groups (< 2^-47
+// per product term) leave |dW| ~ 1e-12: the 1e-6 bar with six orders to spare, and inside what the fp64 path achieved
+// against the LU oracle.  L^-1 is lower triangular, so the K range of the 128-row tile J of X ends at 128 (J + 1).
+//
+// Kernel = the Gram kernel's skeleton: warp 0 TMA producer (128-byte-swizzled [128 rows x 128 B] boxes, 6 stages),
+// warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue; work item = (window, 128 unmeasured SNPs), inner loop
+// over the X row tiles J, so info_u and z_u accumulate in two registers per thread and are written once.
+#include <algorithm>
+#include <cstring>
+
+#include "gb_batch.cuh"
+#include "gb_ptx.cuh"
+
+namespace gb {
+
+namespace {
+
+constexpr int NDIG = OZ_NDIG;       // signed 7-bit digits per operand (7: a 49-bit fixed-point value)
+constexpr int GMIN = 6;             // lightest digit-weight group kept (s + t >= GMIN)
+constexpr int NG = 2 * (NDIG - 1) - GMIN + 1;   // 7 groups: s + t = 12 .. 6, 28 digit pairs
+constexpr int QBITS = 7 * NDIG - 2; // value = 2^e sum_s d_s 2^(7 s - QBITS), |value| 2^-e < 1
+constexpr int OZ_STAGES = 6;
+constexpr int OZ_TILE = 128;
+constexpr int OZ_STAGE_OPERAND = OZ_TILE * 128;      // 16 KiB
+constexpr int OZ_STAGE_BYTES = 2 * OZ_STAGE_OPERAND;
+constexpr int OZ_ACC_BUFS = 4;
+constexpr int OZ_TMEM_COLS = OZ_ACC_BUFS * OZ_TILE;
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_EPI_THREADS = OZ_EPI_WARPS * 32;
+constexpr int OZ_THREADS = 128 + OZ_EPI_THREADS;
+constexpr int OZ_OFF_BARS = 0;
+constexpr int OZ_N_BARS = 2 * OZ_STAGES + 2 * OZ_ACC_BUFS;
+constexpr int OZ_OFF_TMEM_PTR = OZ_OFF_BARS + OZ_N_BARS * 8;
+constexpr int OZ_OFF_RED = 256;                              // double [2][128] cross-half reduction
+constexpr int OZ_OFF_STAGES = 4096;
+constexpr int OZ_Y_MAX = 2048;                               // measured SNPs per window the smem copy of y holds
+constexpr int OZ_OFF_Y = OZ_OFF_STAGES + OZ_STAGES * OZ_STAGE_BYTES;
+constexpr int OZ_SMEM = OZ_OFF_Y + OZ_Y_MAX * 8;
+constexpr int OZ_SMEM_ALLOC = OZ_SMEM + 1024;
+static_assert(OZ_SMEM_ALLOC <= 232448, "shared memory budget exceeded");
+static_assert(OZ_OFF_RED + 2 * 128 * 8 <= OZ_OFF_STAGES, "header overlaps the stages");
+
+struct OzWin {
+  int n_t, n_u;
+  int nbt, nbu;            // 128-row tiles of X rows / of unmeasured rows
+  long long a_row0;        // first row of the window's B21 digit planes in the A tensor map (plane p: + p * ra)
+  long long b_row0;        // ... of its X digit planes in the B tensor map (plane p: + p * rb)
+  int ra, rb;              // rows per plane
+  long long off_t, off_u;  // into y / into z_u, info_u
+};
+struct OzTile {
+  int win, ut;
+};
+
+__device__ __forceinline__ double oz_int_to_double(int v) {
+  return __dsub_rn(__hiloint2double(0x43300000, v ^ 0x80000000), 4503601774854144.0);  // 2^52 + 2^31
+}
+__device__ __forceinline__ void oz_epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory"); }
+
+// digit pairs of group gi (weight g' = 2 (NDIG - 1) - gi): s from max(0, g' - (NDIG - 1)) to min(NDIG - 1, g')
+__device__ __forceinline__ void oz_group_range(int gi, int& gw, int& s_lo, int& s_hi) {
+  gw = 2 * (NDIG - 1) - gi;
+  s_lo = gw - (NDIG - 1) > 0 ? gw - (NDIG - 1) : 0;
+  s_hi = gw < NDIG - 1 ? gw : NDIG - 1;
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const OzWin* __restrict__ wins, const OzTile* __restrict__ tiles, int n_tiles,
+                   const int* __restrict__ ex, const double* __restrict__ y, double* __restrict__ zu,
+                   double* __restrict__ info) {
+  extern __shared__ uint8_t oz_smem_raw[];
+  uint8_t* smem = oz_smem_raw + ((1024u - (ptx::smem_u32(oz_smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OZ_OFF_BARS);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + OZ_STAGES;
+  uint64_t* tfull_bar = bars + 2 * OZ_STAGES;
+  uint64_t* tempty_bar = bars + 2 * OZ_STAGES + OZ_ACC_BUFS;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OZ_OFF_TMEM_PTR);
+  double* red = reinterpret_cast<double*>(smem + OZ_OFF_RED);
+  double* ys = reinterpret_cast<double*>(smem + OZ_OFF_Y);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_b);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < OZ_STAGES; s++) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < OZ_ACC_BUFS; b++) {
+      ptx::mbar_init(&tfull_bar[b], 1);
+      ptx::mbar_init(&tempty_bar[b], OZ_EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, OZ_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    ptx::setmaxnreg_dec<56>();
+    if (warp == 0) {
+      // ===================================================================== TMA producer
+      if (ptx::elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
+          const OzTile t = tiles[ct];
+          const OzWin w = wins[t.win];
+          const int a_row = (int)(w.a_row0 + (long long)t.ut * OZ_TILE);
+          for (int J = 0; J < w.nbt; J++) {
+            const int b_row = (int)(w.b_row0 + (long long)J * OZ_TILE);
+            for (int gi = 0; gi < NG; gi++) {
+              int gw, s_lo, s_hi;
+              oz_group_range(gi, gw, s_lo, s_hi);
+              for (int s = s_lo; s <= s_hi; s++) {
+                const int ra = a_row + s * w.ra, rb = b_row + (gw - s) * w.rb;
+                for (int kb = 0; kb <= J; kb++) {
+                  ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                  uint8_t* sa = smem + OZ_OFF_STAGES + stage * OZ_STAGE_BYTES;
+                  ptx::mbar_arrive_expect_tx(&full_bar[stage], OZ_STAGE_BYTES);
+                  ptx::tma_load_2d(sa, &tm_a, &full_bar[stage], kb * 128, ra);
+                  ptx::tma_load_2d(sa + OZ_STAGE_OPERAND, &tm_b, &full_bar[stage], kb * 128, rb);
+                  if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+                }
+              }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================================================================== MMA issuer
+      if (ptx::elect_one()) {
+        const uint32_t idesc = ptx::make_idesc_i8(OZ_TILE, OZ_TILE);
+        const uint64_t desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + OZ_OFF_STAGES));
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
+          const OzWin w = wins[tiles[ct].win];
+          for (int J = 0; J < w.nbt; J++) {
+            for (int gi = 0; gi < NG; gi++) {
+              int gw, s_lo, s_hi;
+              oz_group_range(gi, gw, s_lo, s_hi);
+              ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+              ptx::tc_fence_after();
+              const uint32_t d_tmem = tmem_base + acc * OZ_TILE;
+              uint32_t accumulate = 0;
+              const int n_blocks = (s_hi - s_lo + 1) * (J + 1);
+              for (int b = 0; b < n_blocks; b++) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                const uint64_t da = desc0 + (uint64_t)(stage * (OZ_STAGE_BYTES >> 4));
+                const uint64_t db = da + (OZ_STAGE_OPERAND >> 4);
+                ptx::mma_i8_ss(d_tmem, da, db, idesc, accumulate);
+                ptx::mma_i8_ss(d_tmem, da + 2, db + 2, idesc, 1);
+                ptx::mma_i8_ss(d_tmem, da + 4, db + 4, idesc, 1);
+                ptx::mma_i8_ss(d_tmem, da + 6, db + 6, idesc, 1);
+                accumulate = 1;
+                ptx::mma_commit(&empty_bar[stage]);
+                if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+              }
+              ptx::mma_commit(&tfull_bar[acc]);
+              if (++acc == OZ_ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    ptx::setmaxnreg_inc<224>();
+    // ===================================================================== epilogue warps
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;          // row of the tile = unmeasured SNP
+    const int half = ew >> 2;                // which 64 columns (X rows) this thread owns
+    const int c0 = half * 64;
+    const int etid = threadIdx.x - 128;
+    int acc_buf = 0;
+    uint32_t acc_phase = 0;
+    for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
+      const OzTile t = tiles[ct];
+      const OzWin w = wins[t.win];
+      const int e_x = ex[t.win];
+      oz_epi_bar_sync();   // the previous tile's readers of ys / red are done
+      for (int i = etid; i < w.nbt * OZ_TILE; i += OZ_EPI_THREADS) ys[i] = i < w.n_t ? y[w.off_t + i] : 0.0;
+      oz_epi_bar_sync();
+      double p_info = 0.0, p_z = 0.0;
+      for (int J = 0; J < w.nbt; J++) {
+        double a[64];
+#pragma unroll
+        for (int e = 0; e < 64; e++) a[e] = 0.0;
+        for (int gi = 0; gi < NG; gi++) {
+          const int gw = 2 * (NDIG - 1) - gi;
+          const double sc = __hiloint2double((1023 + 7 * gw - 2 * QBITS + e_x) << 20, 0);   // 2^(7 g' - 2 QBITS + e_X)
+          ptx::mbar_wait(&tfull_bar[acc_buf], acc_phase);
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + acc_buf * OZ_TILE + ((uint32_t)(quad * 32) << 16) + c0;
+          uint32_t vbuf[2][16];
+          ptx::tmem_ld_32x32b_x16(taddr, vbuf[0]);
+#pragma unroll
+          for (int ch = 0; ch < 4; ch++) {
+            uint32_t (&v)[16] = vbuf[ch & 1];
+            ptx::tmem_ld_wait();
+            if (ch < 3) {
+              ptx::tmem_ld_32x32b_x16(taddr + (ch + 1) * 16, vbuf[(ch + 1) & 1]);
+            } else {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc_buf]);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e++) a[ch * 16 + e] = fma(sc, oz_int_to_double((int)v[e]), a[ch * 16 + e]);
+          }
+          if (++acc_buf == OZ_ACC_BUFS) { acc_buf = 0; acc_phase ^= 1; }
+        }
+        const double* yj = ys + J * OZ_TILE + c0;
+#pragma unroll
+        for (int e = 0; e < 64; e++) {
+          p_info = fma(a[e], a[e], p_info);
+          p_z = fma(a[e], yj[e], p_z);
+        }
+      }
+      // the two column halves of a row, in a fixed order
+      if (half == 1) {
+        red[r] = p_info;
+        red[128 + r] = p_z;
+      }
+      oz_epi_bar_sync();
+      if (half == 0) {
+        const int u = t.ut * OZ_TILE + r;
+        if (u < w.n_u) {
+          const double s_info = p_info + red[r], s_z = p_z + red[128 + r];
+          const double inf = fabs(s_info);             // info = |b21 B11^-1 b12|      (dist.cpp:198)
+          zu[w.off_u + u] = s_z / sqrt(inf);           // z / sqrt(info)               (dist.cpp:200)
+          info[w.off_u + u] = inf;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, OZ_TMEM_COLS);
+  }
+}
+
+// ---- operand preparation -------------------------------------------------------------------------------------------
+// max |v| of a window's matrix (as the bits of a non-negative double, which order like unsigned integers)
+__global__ void __launch_bounds__(256)
+oz_absmax_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ X, unsigned long long* amax) {
+  const SolveWin w = wins[blockIdx.y];
+  const long long total = (long long)w.n_t * w.ld_t;
+  double m = 0.0;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int r = (int)(i / w.ld_t), c = (int)(i % w.ld_t);
+    if (c <= r && c < w.n_t) m = fmax(m, fabs(X[w.off_tt + i]));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(&amax[blockIdx.y], (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void oz_exponent_kernel(const unsigned long long* __restrict__ amax, int n, int* ex) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = __longlong_as_double((long long)amax[i]);
+  int e = 0;
+  if (m > 0.0 && m < 1e300) frexp(m, &e);    // m = f 2^e, f in [0.5, 1)  ->  |v| 2^-e < 1
+  ex[i] = e;
+}
+
+__device__ __forceinline__ void oz_digits(double v, int e, int8_t (&d)[NDIG]) {
+  long long q = __double2ll_rn(ldexp(v, QBITS - e));
+#pragma unroll
+  for (int p = 0; p < NDIG; p++) {
+    const long long dd = ((q + 64) & 127) - 64;
+    d[p] = (int8_t)dd;
+    q = (q - dd) >> 7;
+  }
+}
+
+// X = L^-1 (row-major n_t x ld_t, lower triangular) -> digit planes: one CTA per (row, window), k contiguous
+__global__ void __launch_bounds__(256)
+oz_slice_x_kernel(const SolveWin* __restrict__ wins, const OzWin* __restrict__ ow, const double* __restrict__ X,
+                  const int* __restrict__ ex, int8_t* __restrict__ planes, int kpad) {
+  const SolveWin w = wins[blockIdx.y];
+  const OzWin o = ow[blockIdx.y];
+  const int r = blockIdx.x;
+  if (r >= o.rb) return;
+  const int e = ex[blockIdx.y];
+  const double* row = X + w.off_tt + (long long)r * w.ld_t;
+  for (int k = threadIdx.x; k < kpad; k += 256) {
+    int8_t d[NDIG];
+    const double v = (r < w.n_t && k <= r) ? row[k] : 0.0;
+    oz_digits(v, e, d);
+#pragma unroll
+    for (int p = 0; p < NDIG; p++) planes[(o.b_row0 + (long long)p * o.rb + r) * kpad + k] = d[p];
+  }
+}
+
+// B21^T (row-major n_t x ld_u: k rows, u contiguous) -> digit planes with k contiguous per unmeasured SNP u (transpose
+// through shared memory: a CTA takes 32 u x 128 k)
+__global__ void __launch_bounds__(256)
+oz_slice_b_kernel(const SolveWin* __restrict__ wins, const OzWin* __restrict__ ow, const double* __restrict__ ut,
+                  int8_t* __restrict__ planes, int kpad) {
+  __shared__ double tile[128][33];
+  const SolveWin w = wins[blockIdx.z];
+  const OzWin o = ow[blockIdx.z];
+  const int u0 = blockIdx.x * 32, k0 = blockIdx.y * 128;
+  if (u0 >= o.ra || k0 >= kpad) return;
+  const double* B = ut + w.off_ut;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int kk = wid; kk < 128; kk += 8) {
+    const int k = k0 + kk, u = u0 + lane;
+    tile[kk][lane] = (k < w.n_t && u < w.n_u) ? B[(long long)k * w.ld_u + u] : 0.0;
+  }
+  __syncthreads();
+  // warp -> one u at a time, lane -> 4 consecutive k: a warp writes 128 contiguous bytes per plane
+  for (int uu = wid; uu < 32; uu += 8) {
+    int8_t d[4][NDIG];
+#pragma unroll
+    for (int q = 0; q < 4; q++) oz_digits(tile[4 * lane + q][uu], 0, d[q]);
+#pragma unroll
+    for (int p = 0; p < NDIG; p++) {
+      const uint32_t word = (uint32_t)(uint8_t)d[0][p] | ((uint32_t)(uint8_t)d[1][p] << 8) | ((uint32_t)(uint8_t)d[2][p] << 16) |
+                            ((uint32_t)(uint8_t)d[3][p] << 24);
+      *reinterpret_cast<uint32_t*>(planes + (o.a_row0 + (long long)p * o.ra + u0 + uu) * kpad + k0 + 4 * lane) = word;
+    }
+  }
+}
+
+// X := identity (the right-hand side of the trtri-by-trsm), row-major n_t x ld_t
+__global__ void oz_identity_kernel(const SolveWin* __restrict__ wins, double* X) {
+  const SolveWin w = wins[blockIdx.y];
+  const long long total = (long long)w.n_t * w.ld_t;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x)
+    X[w.off_tt + i] = (i / w.ld_t) == (i % w.ld_t) ? 1.0 : 0.0;
+}
+
+}  // namespace
+
+int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_rows, int64_t k_elems,
+                        int64_t k_stride_bytes, int format, int box_rows);
+
+size_t ozaki_win_bytes() { return sizeof(OzWin); }
+size_t ozaki_tile_bytes() { return sizeof(OzTile); }
+
+// Host-side plan of the int8-split solve for a batch: fills the window / tile descriptors (in the order of `wins`,
+// heaviest first) and returns the plane sizes.  kpad = K bytes per plane row (multiple of 128, >= the largest n_t).
+void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, void* ow_out, std::vector<uint8_t>* tiles_out, long long* a_rows,
+                long long* b_rows) {
+  OzWin* ow = static_cast<OzWin*>(ow_out);
+  long long ar = 0, br = 0;
+  std::vector<OzTile> tiles;
+  for (int i = 0; i < n_wins; i++) {
+    OzWin o{};
+    o.n_t = wins[i].n_t;
+    o.n_u = wins[i].n_u;
+    o.nbt = (o.n_t + OZ_TILE - 1) / OZ_TILE;
+    o.nbu = (o.n_u + OZ_TILE - 1) / OZ_TILE;
+    o.ra = o.nbu * OZ_TILE;
+    o.rb = o.nbt * OZ_TILE;
+    o.a_row0 = ar;
+    o.b_row0 = br;
+    o.off_t = wins[i].off_t;
+    o.off_u = wins[i].off_u;
+    ar += (long long)NDIG * o.ra;
+    br += (long long)NDIG * o.rb;
+    ow[i] = o;
+    for (int ut = 0; ut < o.nbu; ut++) tiles.push_back(OzTile{i, ut});
+  }
+  (void)kpad;
+  tiles_out->resize(tiles.size() * sizeof(OzTile));
+  if (!tiles.empty()) std::memcpy(tiles_out->data(), tiles.data(), tiles_out->size());
+  *a_rows = ar;
+  *b_rows = br;
+}
+
+// Device side of the solve: X = L^-1 by the caller (trsm on identity), then slicing + the GEMM.
+int launch_ozaki_prepare_identity(Ctx* ctx, const SolveWin* d_wins, int n_wins, double* d_x) {
+  if (n_wins == 0) return GB_OK;
+  oz_identity_kernel<<<dim3(64, (unsigned)n_wins), 256, 0, ctx->stream>>>(d_wins, d_x);
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return GB_OK;
+}
+
+void ozaki_tile_rows(const void* h_ow, int win, long long* a_row0, int* ra) {
+  const OzWin& o = static_cast<const OzWin*>(h_ow)[win];
+  *a_row0 = o.a_row0;
+  *ra = o.ra;
+}
+
+// slice_b21 != 0: B21 is in d_ut as doubles (int8 panels: the Gram kernel finishes its tiles itself) and is sliced here;
+// otherwise the finish pass of the Gram stage has already written the digit planes.
+int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const void* h_ow, int n_wins, const void* d_tiles,
+                       int n_tiles, int kpad, const double* d_x, const double* d_ut, int slice_b21, int8_t* d_planes_a,
+                       long long a_rows, int8_t* d_planes_b, long long b_rows, unsigned long long* d_amax, int* d_ex,
+                       const double* d_y, double* d_zu, double* d_info) {
+  if (n_wins == 0 || n_tiles == 0) return GB_OK;
+  const OzWin* how = static_cast<const OzWin*>(h_ow);
+  int max_ra = 0, max_rb = 0, max_nt = 0;
+  for (int i = 0; i < n_wins; i++) {
+    max_ra = std::max(max_ra, how[i].ra);
+    max_rb = std::max(max_rb, how[i].rb);
+    max_nt = std::max(max_nt, how[i].n_t);
+  }
+  if (max_rb > OZ_Y_MAX) {
+    ctx->err = "window has too many measured SNPs for the int8-split solve";
+    return GB_ERR_UNSUPPORTED;
+  }
+  const bool trace = getenv("GB_OZ_TRACE") != nullptr;   // diagnostics: event-timed pieces, printed per call
+  cudaEvent_t ev[6];
+  int n_ev = 0;
+  auto mark = [&]() {
+    if (!trace) return;
+    cudaEventCreate(&ev[n_ev]);
+    cudaEventRecord(ev[n_ev++], ctx->stream);
+  };
+  mark();
+  GB_CUDA(cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long) * (size_t)n_wins, ctx->stream));
+  oz_absmax_kernel<<<dim3(32, (unsigned)n_wins), 256, 0, ctx->stream>>>(d_wins, d_x, d_amax);
+  oz_exponent_kernel<<<(unsigned)((n_wins + 127) / 128), 128, 0, ctx->stream>>>(d_amax, n_wins, d_ex);
+  mark();
+  oz_slice_x_kernel<<<dim3((unsigned)max_rb, (unsigned)n_wins), 256, 0, ctx->stream>>>(d_wins, static_cast<const OzWin*>(d_ow), d_x,
+                                                                                    d_ex, d_planes_b, kpad);
+  mark();
+  if (slice_b21)
+    oz_slice_b_kernel<<<dim3((unsigned)(max_ra / 32), (unsigned)(kpad / 128), (unsigned)n_wins), 256, 0, ctx->stream>>>(
+        d_wins, static_cast<const OzWin*>(d_ow), d_ut, d_planes_a, kpad);
+  mark();
+  GB_CUDA(cudaGetLastError());
+  ctx->launches += 4;
+  CUtensorMap tm_a, tm_b;
+  int rc;
+  if ((rc = make_row_tensor_map(ctx, &tm_a, d_planes_a, a_rows, kpad, kpad, MAP_INT8, OZ_TILE))) return rc;
+  if ((rc = make_row_tensor_map(ctx, &tm_b, d_planes_b, b_rows, kpad, kpad, MAP_INT8, OZ_TILE))) return rc;
+  static bool attr_set_dev[64] = {};
+  if (!attr_set_dev[ctx->device & 63]) {
+    GB_CUDA(cudaFuncSetAttribute(ozaki_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_ALLOC));
+    attr_set_dev[ctx->device & 63] = true;
+  }
+  const int n_ctas = std::min(n_tiles, ctx->sm_count);
+  ozaki_solve_kernel<<<(unsigned)n_ctas, OZ_THREADS, OZ_SMEM_ALLOC, ctx->stream>>>(
+      tm_a, tm_b, static_cast<const OzWin*>(d_ow), static_cast<const OzTile*>(d_tiles), n_tiles, d_ex, d_y, d_zu, d_info);
+  mark();
+  GB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  if (trace) {
+    cudaStreamSynchronize(ctx->stream);
+    static const char* const nm[] = {"absmax", "slice_x", "slice_b21", "gemm"};
+    fprintf(stderr, "[oz trace]");
+    for (int i = 0; i + 1 < n_ev; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      fprintf(stderr, " %s %.3f ms |", nm[i], ms);
+    }
+    fprintf(stderr, " tiles %d kpad %d\n", n_tiles, kpad);
+    for (int i = 0; i < n_ev; i++) cudaEventDestroy(ev[i]);
+  }
+  return GB_OK;
+}
+
+}  // namespace gb

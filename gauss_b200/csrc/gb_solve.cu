@@ -410,7 +410,7 @@ template <int UB_>
 __global__ void __launch_bounds__(256, 2)
 trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt,
                      const double* __restrict__ dinv, double* ut, const double* __restrict__ zt,
-                     double* zu, double* info, double* y_out) {
+                     double* zu, double* info, double* y_out, int tri) {
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t, nu = w.n_u;
   constexpr int NTW = UB_ / 32;      // 8-column MMA tiles per warp
@@ -445,7 +445,10 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   for (int nt = 0; nt < NTW; nt++) p_info[nt][0] = p_info[nt][1] = p_z[nt][0] = p_z[nt][1] = 0.0;
   const int cvalid = ldu - u0;               // columns that exist in the row (ldu is a multiple of 8)
 
-  for (int ib = 0; ib < nb; ib++) {
+  // tri: the right-hand side is the identity (explicit L^-1 for the int8-split solve): block rows above this CTA's
+  // first column hold zeros and stay zero, and the block columns of W left of it contribute nothing
+  const int ib0 = tri ? u0 / NB : 0;
+  for (int ib = ib0; ib < nb; ib++) {
     const int i0 = ib * NB;
     double C[4][NTW][2];
 #pragma unroll
@@ -484,8 +487,10 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
     };
     double acc_y = 0.0;  // thread (row yr_, quarter yq): sum over k = yq mod 4 of L(i0 + yr_, k) y_k
     __syncthreads();  // previous row block finished with the aliased buffers (Ts / Ds)
-    if (nchunk > 0) issue(0, 0);
-    for (int ch = 0; ch < nchunk; ch++) {
+    // (the y column of a tri launch is exact only in the CTA of column block 0, the one that writes y_out)
+    const int ch0 = ib0 * (NB / KC);
+    if (nchunk > ch0) issue(ch0, ch0 & 1);
+    for (int ch = ch0; ch < nchunk; ch++) {
       const int buf = ch & 1;
       if (ch + 1 < nchunk) {
         issue(ch + 1, buf ^ 1);
@@ -851,7 +856,7 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
 
 int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,
                          const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info,
-                         double* d_y_out) {
+                         double* d_y_out, int tri) {
   if (n_wins == 0 || max_nu == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
   // 128 columns per CTA when the launch has waves to spare, 64 when it is about one wave (a single window, the
@@ -875,8 +880,8 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
     else GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     have = smem;
   }
-  if (narrow) trsm_finalize_kernel<64><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
-  else trsm_finalize_kernel<128><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out);
+  if (narrow) trsm_finalize_kernel<64><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out, tri);
+  else trsm_finalize_kernel<128><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out, tri);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

@@ -215,8 +215,9 @@ GB_API int gb_batch_fetch(gb_batch *batch, double *z_u, double *info_u, int *win
 GB_API int gb_batch_work(const gb_batch *batch, double *gram_ops, double *solve_flops,
                   double *panel_bytes);
 /* Enqueue only one stage (profiling / roofline timing): 0 = row statistics, 1 = Gram + finish pass,
- * 2 = Cholesky, 3 = triangular solve + finalise; 10 / 11 = the two halves of stage 1 (tensor-core
- * kernel / finish pass). */
+ * 2 = Cholesky (+ the explicit L^-1 of the int8-split solve), 3 = solve + finalise (int8-split GEMM on tcgen05, or the
+ * fp64 triangular solve with GB_SOLVE=fp64); 10 / 11 = the two halves of stage 1 (tensor-core kernel / finish pass),
+ * 20 / 21 = the two halves of stage 2 (factorisation / L^-1). */
 GB_API int gb_batch_run_stage(gb_batch *batch, int stage);
 
 /* ---- 2-bit host rows ("pack2") and the chromosome driver ---------------------------------------- */
