@@ -475,6 +475,18 @@ int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
     if ((rc = take(&b->d_oz_pa, s.oz_pa))) return rc;
     if ((rc = take(&b->d_oz_pb, s.oz_pb))) return rc;
   }
+  if (const char* e = getenv("GB_POISON")) {
+    // diagnostics: fill chosen transient buffers with a byte pattern before anything writes them ("mask:byte"), to
+    // expose reads of memory the batch never initialised
+    unsigned mask = 0, byte = 0x55;
+    sscanf(e, "%u:%u", &mask, &byte);
+    const struct { void* p; size_t n; } bufs[] = {
+        {b->d_x, s.oz_x}, {b->d_oz_pa, s.oz_pa}, {b->d_oz_pb, s.oz_pb}, {b->d_oz_y, sizeof(double) * (size_t)b->n_t_total},
+        {b->d_oz_scr, 2 * sizeof(double) * (size_t)b->n_t_total}, {b->d_ut, s.ut}, {b->d_tt, s.tt}, {b->d_dinv, s.dinv},
+        {b->d_zu, s.zu}, {b->d_info, s.info}, {b->d_scratch, 0}};
+    for (int i = 0; i < 10; i++)
+      if ((mask >> i & 1) && bufs[i].p && bufs[i].n) cudaMemsetAsync(bufs[i].p, (int)byte, bufs[i].n, ctx->stream);
+  }
   if (b->clip_mode) {
     if ((rc = dev_alloc(b, &b->d_eig_G, (size_t)b->tt_elems))) return rc;
     if ((rc = dev_alloc(b, &b->d_eig_V, (size_t)b->tt_elems))) return rc;

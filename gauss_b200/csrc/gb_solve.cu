@@ -397,9 +397,10 @@ constexpr int LSS = NB + 4;   // row stride of staged L / inv(L_ii)   [k][row]
 constexpr int tr_smem_bytes(int ub) { return 2 * (KC * LSS + KC * (ub + 4)) * 8; }   // 102,400 for 128 columns
 static_assert(2 * KC >= NB, "aliased tiles must fit the chunk buffers");
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+// 16-byte asynchronous copy of which only the first `n_valid` doubles (0, 1 or 2) are read; the rest is zero-filled
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int n_valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  const int sz = valid ? 16 : 0;
+  const int sz = n_valid >= 2 ? 16 : n_valid == 1 ? 8 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -474,14 +475,16 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
       for (int it = 0; it < (KC * NB / 2) / 256; it++) {
         const int idx = tid + it * 256;
         const int kk = idx >> 5, r2 = (idx & 31) * 2;
-        cp_async16(ls + kk * LSS + r2, L + (long long)(kbase + kk) * ld + i0 + r2, i0 + r2 < n);
+        // row n of an odd-sized window is padding nothing ever wrote: it must read as zero, not as stale memory (a NaN
+        // there would reach the valid rows through 0 * NaN in the inv(L_ii) product)
+        cp_async16(ls + kk * LSS + r2, L + (long long)(kbase + kk) * ld + i0 + r2, n - (i0 + r2));
       }
       // W chunk: KC rows x 128 columns, 64 pieces per row
 #pragma unroll
       for (int it = 0; it < (KC * UB_ / 2) / 256; it++) {
         const int idx = tid + it * 256;
         const int kk = idx / (UB_ / 2), c2 = (idx % (UB_ / 2)) * 2;
-        cp_async16(ws + kk * WSS + c2, W + (long long)(kbase + kk) * ldu + u0 + c2, c2 < cvalid);
+        cp_async16(ws + kk * WSS + c2, W + (long long)(kbase + kk) * ldu + u0 + c2, c2 < cvalid ? 2 : 0);
       }
       cp_async_commit();
     };

@@ -403,6 +403,34 @@ def test_pipe_matches_single_window_calls(gpu_ctx, oracle):
     assert np.abs(z - r["z"][len(rt):]).max() <= TIGHT
 
 
+@pytest.mark.parametrize("solver", ["int8", "fp64"])
+def test_results_do_not_depend_on_uninitialised_memory(solver, monkeypatch):
+    """GB_POISON fills every transient buffer of a batch with 0xFF bytes (NaNs as doubles, -1 digits) before any
+    kernel writes it.  Padding that is read but never written -- row n_t of an odd-sized B11, the columns between
+    n_u and its multiple of 8 -- must not reach a result: stream-ordered allocations hand back memory full of
+    whatever the previous batch left there."""
+    c = small_case(seed=33, n_snps=900, pop_sizes=(61, 103, 40, 25, 2, 330, 97), measured_frac=0.3, core=(0, 900))
+    g, t = c["g"].astype(np.int8), c["type"]
+    monkeypatch.setenv("GB_SOLVE", solver)
+    ctx = gb.Context(0)
+    try:
+        panel = make_panel(ctx, g, c["pop_sizes"])
+        for lo, hi in [(0, 300), (150, 520), (0, 900)]:
+            idx = np.arange(lo, hi)
+            rt, ru = idx[t[lo:hi] == 1], idx[t[lo:hi] == 0]
+            monkeypatch.delenv("GB_POISON", raising=False)
+            z0, i0, _ = panel.window_distmix(rt, ru, c["z"][rt], c["w"])
+            for byte in (0xFF, 0x7F):
+                monkeypatch.setenv("GB_POISON", "1023:%d" % byte)
+                z1, i1, _ = panel.window_distmix(rt, ru, c["z"][rt], c["w"])
+                np.testing.assert_array_equal(z1, z0)
+                np.testing.assert_array_equal(i1, i0)
+                z2, i2, _ = panel.window_dist(rt, ru, c["z"][rt])
+                assert np.isfinite(z2).all() and np.isfinite(i2).all()
+    finally:
+        ctx.close()
+
+
 def test_overlapped_batch_run_equals_staged_run(gpu_ctx):
     """gb_batch_run puts the factorisation on a side stream beside the B21 Gram tiles once a batch has at least one
     B21 tile per SM; the results must be the bits of the stage-by-stage run, run after run."""
