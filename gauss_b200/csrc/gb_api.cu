@@ -319,7 +319,9 @@ int batch_plan_host(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, co
     b->max_nt = std::max(b->max_nt, sw.n_t);
     b->max_nu = std::max(b->max_nu, sw.n_u);
   }
-  b->ozaki = ctx->solve_ozaki && !b->ld_mode && !b->counts_mode && !b->h_wins.empty() && b->max_nt <= 2048;
+  // (mixture weights that are negative or sum well beyond 1 can push |cor| past what the B21 digit planes carry: fp64 then)
+  b->ozaki = ctx->solve_ozaki && !b->ld_mode && !b->counts_mode && !b->h_wins.empty() && b->max_nt <= 2048 &&
+             (b->mode != GRAM_MIX || b->gneg <= 0.25);
   if (b->ozaki) {
     b->oz_kpad = (b->max_nt + 127) / 128 * 128;
     b->h_oz_wins.resize(b->h_wins.size() * ozaki_win_bytes());
@@ -471,6 +473,7 @@ int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
     if ((rc = dev_alloc(b, &b->d_oz_scr, 2 * (size_t)b->n_t_total))) return rc;
     if ((rc = dev_alloc(b, &b->d_oz_amax, b->h_wins.size()))) return rc;
     if ((rc = dev_alloc(b, &b->d_oz_ex, b->h_wins.size()))) return rc;
+    if ((rc = dev_alloc(b, &b->d_oz_nan, (size_t)std::max<int64_t>(b->n_u_total, 1)))) return rc;
     if ((rc = take(&b->d_x, s.oz_x))) return rc;
     if ((rc = take(&b->d_oz_pa, s.oz_pa))) return rc;
     if ((rc = take(&b->d_oz_pb, s.oz_pb))) return rc;
@@ -519,6 +522,7 @@ int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
   gp.counts_seg_stride = b->counts_elems;
   gp.oz_pa = (b->ozaki && gp.raw_out) ? b->d_oz_pa : nullptr;   // the finish pass writes B21's digit planes itself
   gp.oz_kpad = b->oz_kpad;
+  gp.oz_nan = b->d_oz_nan;
   if (!sync) return GB_OK;
   // the same sync makes the pack kernels' representability flag readable
   int h_flags = 0;
@@ -640,6 +644,7 @@ int run_stage_impl(gb_batch* b, int stage) {
   if (rc) return rc;
   switch (stage) {
     case 0: {
+      if (b->ozaki) GB_CUDA(cudaMemsetAsync(b->d_oz_nan, 0, (size_t)std::max<int64_t>(b->n_u_total, 1), ctx->stream));
       if (b->n_gather > 0)
         if ((rc = launch_gather_rows(ctx, pn, b->d_gather, b->n_gather, b->d_scratch))) return rc;
       if (b->counts_mode) return GB_OK;
@@ -702,7 +707,7 @@ int run_stage_impl(gb_batch* b, int stage) {
         // W^T = B21 X^T as an exact digit-split GEMM on tcgen05 (gb_ozaki.cu); X and y come from stage 2
         return launch_ozaki_solve(ctx, b->d_wins, b->d_oz_wins, b->h_oz_wins.data(), (int)b->h_wins.size(), b->d_oz_tiles,
                                   b->oz_n_tiles, b->oz_kpad, b->d_x, b->d_ut, b->gp.oz_pa == nullptr, b->d_oz_pa, b->oz_a_rows,
-                                  b->d_oz_pb, b->oz_b_rows, b->d_oz_amax, b->d_oz_ex, b->d_oz_y, b->d_zu, b->d_info);
+                                  b->d_oz_pb, b->oz_b_rows, b->d_oz_amax, b->d_oz_ex, b->d_oz_y, b->d_oz_nan, b->d_zu, b->d_info);
       return launch_trsm_finalize(ctx, b->d_wins, (int)b->h_wins.size(), b->max_nt, b->max_nu, b->d_tt, b->d_dinv,
                                   b->d_ut, b->d_zt, b->d_zu, b->d_info, b->d_y);
     default:

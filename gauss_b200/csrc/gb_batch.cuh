@@ -81,6 +81,7 @@ struct gb_batch {
   void *d_oz_wins = nullptr, *d_oz_tiles = nullptr;
   double *d_x = nullptr, *d_oz_y = nullptr, *d_oz_scr = nullptr;
   int8_t *d_oz_pa = nullptr, *d_oz_pb = nullptr;
+  uint8_t* d_oz_nan = nullptr;       // [n_u_total] rows of B21 the digit planes cannot represent (-> NaN results, as the doubles give)
   unsigned long long* d_oz_amax = nullptr;
   int* d_oz_ex = nullptr;
   // memory: `owned` pointers are freed with the batch; buffers carved from `arena` (when set) are not

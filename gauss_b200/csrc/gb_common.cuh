@@ -81,6 +81,7 @@ struct GramParams {
   long long counts_seg_stride;
   int8_t* oz_pa;         // int8-split solve: digit planes of B21 ([plane][u][k], k contiguous), written by the finish pass
   int oz_kpad;           // bytes per plane row
+  uint8_t* oz_nan;       // [n_u_total] set when a row of B21 holds a value the digits cannot carry (NaN: a monomorphic SNP)
 };
 
 // ------------------------------------------------------------------ context / panel
@@ -200,7 +201,7 @@ int launch_ozaki_prepare_identity(Ctx* ctx, const SolveWin* d_wins, int n_wins, 
 int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const void* h_ow, int n_wins, const void* d_tiles,
                        int n_tiles, int kpad, const double* d_x, const double* d_ut, int slice_b21, int8_t* d_planes_a,
                        long long a_rows, int8_t* d_planes_b, long long b_rows, unsigned long long* d_amax, int* d_ex,
-                       const double* d_y, double* d_zu, double* d_info);
+                       const double* d_y, uint8_t* d_nan, double* d_zu, double* d_info);
 void ozaki_tile_rows(const void* h_ow, int win, long long* a_row0, int* ra);
 
 // gb_gene.cu

@@ -580,6 +580,105 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
   }
 }
 
+// ---- int8-split solve: a B21 tile leaves the finish pass as digit planes ---------------------------------------------
+// The solve multiplies B21 by L^-T on the int8 tensor cores (gb_ozaki.cu), so this pass writes the OZ_NDIG signed 7-bit
+// digit planes of a tile's correlations instead of its doubles:
+//   q = rint(cor 2^47),  q = sum_p d_p 128^p,  d_p in [-64, 63]     (|cor| < 1.97; 49-bit fixed point)
+// Digits without a carry chain: q' = q + BIAS with BIAS = sum_p 64 128^p has the unsigned base-128 digits d_p + 64, and
+// the signed 7-bit field p of q' ^ BIAS is d_p itself.  q comes out of the mantissa of cor 2^47 + 1.5 2^52 (one FMA, no
+// 64-bit conversion).  The correlation is formed as cov (1/sd_i 1/sd_j): a couple of ulps from the reference's division,
+// three orders of magnitude below the 2^-47 the digits resolve.  A value the digits cannot carry (NaN: a monomorphic
+// unmeasured SNP has sd = 0) marks its row in oz_nan; the solve returns NaN for it, as the doubles would.
+// Thread (row r = unmeasured SNP, half h) takes 8 consecutive k per step; the planes want k contiguous per row, so 32
+// columns at a time go through shared memory ([plane][row][32 B]) and leave as whole 32-byte sectors.
+constexpr int OZ_STG_ROW = 40;   // bytes per staged row: 32 + 8 of padding (8-byte accesses, bank-conflict-free per half-warp)
+constexpr size_t OZ_STAGE_BYTES = (size_t)OZ_NDIG * TILE * OZ_STG_ROW;
+
+__device__ __forceinline__ int oz_bfe_s32(uint32_t v, int pos) {
+  int d;
+  asm("bfe.s32 %0, %1, %2, 7;" : "=r"(d) : "r"(v), "r"(pos));
+  return d;
+}
+__device__ __forceinline__ uint32_t oz_pack4(int b0, int b1, int b2, int b3) {
+  return __byte_perm(__byte_perm((uint32_t)b0, (uint32_t)b1, 0x0040), __byte_perm((uint32_t)b2, (uint32_t)b3, 0x0040), 0x5410);
+}
+
+__device__ __forceinline__ void finalize_oz_tile(const GramParams& prm, const GramTile& t, const double* gA, const double* hB,
+                                                 const double* aiS, const double* bjS, const double* isdA, const double* isdB,
+                                                 uint8_t* stage) {
+  constexpr unsigned long long BIAS = 0x0001020408102040ull;             // sum_{p<7} 64 * 128^p
+  constexpr unsigned long long MAGIC_BITS = 0x4338000000000000ull;       // bits of 1.5 * 2^52
+  const int tid = threadIdx.x;
+  const int r = tid & 127, h = tid >> 7;
+  const bool live = r < t.a_valid;
+  const int n_seg = prm.n_seg;
+  const double* out = prm.out_ut + t.out_off;
+  const long long gi = t.i0 + r;
+  const double ai = aiS[r], isd_r = isdA[r];
+  bool row_bad = false;
+#pragma unroll 1
+  for (int it = 0; it < TILE / 32; it++) {
+#pragma unroll 1
+    for (int sub = 0; sub < 2; sub++) {
+      const int cb = it * 32 + sub * 16 + h * 8;    // this thread's 8 columns (measured SNPs k)
+      double x[8];
+      bool ok[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        ok[k] = live && cb + k < t.b_valid;
+        x[k] = ok[k] ? out[(long long)(t.j0 + cb + k) * t.ld_out + gi] : 0.0;
+      }
+#pragma unroll 3
+      for (int p = 0; p < n_seg; p++) {   // + kappa_p s^p_i s^p_j
+        const double g = gA[p * TILE + r];
+        const double2* hv = reinterpret_cast<const double2*>(hB + p * TILE + cb);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) {
+          const double2 h2 = hv[k2];
+          x[2 * k2] = fma(g, h2.x, x[2 * k2]);
+          x[2 * k2 + 1] = fma(g, h2.y, x[2 * k2 + 1]);
+        }
+      }
+      uint32_t w0[8], w1[8];   // digits 0..3 at bits 0, 7, 14, 21 of w0; digits 4..6 at bits 0, 7, 14 of w1
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        double cor = ok[k] ? fma(-ai, bjS[cb + k], x[k]) * (isd_r * isdB[cb + k]) : 0.0;
+        if (!(fabs(cor) <= 1.97)) {
+          row_bad = true;
+          cor = 0.0;
+        }
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(fma(cor, 140737488355328.0, 6755399441055744.0));
+        const unsigned long long q = (bits + (BIAS - MAGIC_BITS)) ^ BIAS;
+        const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
+        w0[k] = lo;
+        w1[k] = __funnelshift_r(lo, hi, 28);
+      }
+      uint8_t* srow = stage + (size_t)r * OZ_STG_ROW + sub * 16 + h * 8;
+#pragma unroll
+      for (int p = 0; p < OZ_NDIG; p++) {
+        const int pos = 7 * (p < 4 ? p : p - 4);
+        int b[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) b[k] = oz_bfe_s32(p < 4 ? w0[k] : w1[k], pos);
+        *reinterpret_cast<uint2*>(srow + (size_t)p * TILE * OZ_STG_ROW) =
+            make_uint2(oz_pack4(b[0], b[1], b[2], b[3]), oz_pack4(b[4], b[5], b[6], b[7]));
+      }
+    }
+    __syncthreads();
+    // 7 planes x 128 rows x 32 bytes: four lanes per row, a warp stores eight whole sectors per instruction
+#pragma unroll 2
+    for (int idx = tid; idx < OZ_NDIG * TILE * 4; idx += 256) {
+      const int q4 = idx & 3, row = (idx >> 2) & (TILE - 1), p = idx >> 9;
+      if (row < t.a_valid) {
+        const uint2 v = *reinterpret_cast<const uint2*>(stage + ((size_t)p * TILE + row) * OZ_STG_ROW + q4 * 8);
+        *reinterpret_cast<uint2*>(prm.oz_pa + ((t.oz_row0 + row) + (long long)p * t.oz_ra) * prm.oz_kpad + t.j0 + it * 32 + q4 * 8) = v;
+      }
+    }
+    __syncthreads();
+  }
+  if (row_bad && prm.oz_nan) prm.oz_nan[t.a_list0 + r] = 1;
+}
+
 // Finish pass of the regrouped fold (E2M1 panels, mixture mode).  One CTA per 128 x 128 tile of
 // the same tile list; reads the raw sum_p (coef_p m_p) S^p_ij the Gram kernel stored and writes
 //   cor_ij = (raw + sum_p kappa_p s^p_i s^p_j - a_i b_j) / (sd_i sd_j),   a_i = sum_p w_p s^p_i / m_p,
@@ -599,6 +698,7 @@ gram_finalize_kernel(const __grid_constant__ GramParams prm) {
   double* sdA = bjS + TILE;
   double* sdB = sdA + TILE;
   const int tid = threadIdx.x;
+  const bool oz = prm.oz_pa != nullptr && t.a_is_u && t.oz_ra > 0;
   {
     const int side = tid >> 7, idx = tid & 127;
     const int valid = side ? t.b_valid : t.a_valid;
@@ -616,9 +716,14 @@ gram_finalize_kernel(const __grid_constant__ GramParams prm) {
       wsum = __dadd_rn(wsum, __dmul_rn(prm.wgt[p], st_mean[p * ld + li]));   // wsum_mi  (util.cpp:120-121)
     }
     (side ? bjS : aiS)[idx] = wsum;
-    (side ? sdB : sdA)[idx] = from_u ? prm.sd_u[li] : prm.sd_t[li];
+    const double sd = from_u ? prm.sd_u[li] : prm.sd_t[li];
+    (side ? sdB : sdA)[idx] = oz ? 1.0 / sd : sd;   // the digit planes take cov * (1/sd_i * 1/sd_j): see finalize_oz_tile
   }
   __syncthreads();
+  if (oz) {
+    finalize_oz_tile(prm, t, gA, hB, aiS, bjS, sdA, sdB, reinterpret_cast<uint8_t*>(sdB + TILE));
+    return;
+  }
   const int r = tid & 127;
   const int c0 = (tid >> 7) * EPI_COLS;
   if (r >= t.a_valid) return;
@@ -626,7 +731,6 @@ gram_finalize_kernel(const __grid_constant__ GramParams prm) {
   const long long gi = t.i0 + r;
   const bool diag_tile = (!t.a_is_u) && (t.i0 == t.j0);
   const double ai = aiS[r], sd_r = sdA[r];
-  const bool oz = prm.oz_pa != nullptr && t.a_is_u && t.oz_ra > 0;
 #pragma unroll 1
   for (int ch = 0; ch < EPI_COLS / 8; ch++) {
     double x[8];
@@ -648,32 +752,6 @@ gram_finalize_kernel(const __grid_constant__ GramParams prm) {
         x[2 * k2] = fma(g, h2.x, x[2 * k2]);
         x[2 * k2 + 1] = fma(g, h2.y, x[2 * k2 + 1]);
       }
-    }
-    if (oz) {
-      // int8-split solve: this B21 tile leaves as the 7 signed 7-bit digit planes of its correlations (|r| <= 1: scale
-      // 2^0, 49-bit fixed point), 8 consecutive k of row u per 64-bit store and plane; the doubles are not stored
-      uint32_t lo[OZ_NDIG], hi[OZ_NDIG];
-#pragma unroll
-      for (int p = 0; p < OZ_NDIG; p++) lo[p] = hi[p] = 0u;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int c = c0 + ch * 8 + k;
-        const double cor = ok[k] ? __ddiv_rn(fma(-ai, bjS[c], x[k]), __dmul_rn(sd_r, sdB[c])) : 0.0;
-        long long q = __double2ll_rn(ldexp(cor, 7 * OZ_NDIG - 2));
-#pragma unroll
-        for (int p = 0; p < OZ_NDIG; p++) {
-          const long long dd = ((q + 64) & 127) - 64;
-          q = (q - dd) >> 7;
-          const uint32_t byte = (uint32_t)(uint8_t)(int8_t)dd << (8 * (k & 3));
-          if (k < 4) lo[p] |= byte;
-          else hi[p] |= byte;
-        }
-      }
-      int8_t* prow = prm.oz_pa + (t.oz_row0 + r) * (long long)prm.oz_kpad + t.j0 + c0 + ch * 8;
-#pragma unroll
-      for (int p = 0; p < OZ_NDIG; p++)
-        *reinterpret_cast<uint2*>(prow + (long long)p * t.oz_ra * prm.oz_kpad) = make_uint2(lo[p], hi[p]);
-      continue;
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -821,11 +899,11 @@ int launch_zmix_pairs(Ctx* ctx, const Panel* panel, const int32_t* d_counts, int
 
 int launch_gram_finalize(Ctx* ctx, const GramParams& prm, int n_descriptors) {
   if (n_descriptors <= 0) return GB_OK;
-  const size_t smem = sizeof(double) * (size_t)(2 * prm.n_seg * TILE + 4 * TILE);
+  const size_t smem = sizeof(double) * (size_t)(2 * prm.n_seg * TILE + 4 * TILE) + (prm.oz_pa ? OZ_STAGE_BYTES : 0);
   static bool attr_set_dev[64] = {};
   if (!attr_set_dev[ctx->device & 63]) {
     GB_CUDA(cudaFuncSetAttribute(gram_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(sizeof(double) * (2 * P_MAX * TILE + 4 * TILE))));
+                                 (int)(sizeof(double) * (2 * P_MAX * TILE + 4 * TILE) + OZ_STAGE_BYTES)));
     attr_set_dev[ctx->device & 63] = true;
   }
   gram_finalize_kernel<<<(unsigned)n_descriptors, 256, smem, ctx->stream>>>(prm);

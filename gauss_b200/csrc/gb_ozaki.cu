@@ -77,8 +77,8 @@ __device__ __forceinline__ void oz_group_range(int gi, int& gw, int& s_lo, int& 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const OzWin* __restrict__ wins, const OzTile* __restrict__ tiles, int n_tiles,
-                   const int* __restrict__ ex, const double* __restrict__ y, double* __restrict__ zu,
-                   double* __restrict__ info) {
+                   const int* __restrict__ ex, const double* __restrict__ y, const uint8_t* __restrict__ nanflag,
+                   double* __restrict__ zu, double* __restrict__ info) {
   extern __shared__ uint8_t oz_smem_raw[];
   uint8_t* smem = oz_smem_raw + ((1024u - (ptx::smem_u32(oz_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OZ_OFF_BARS);
@@ -248,7 +248,8 @@ ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int u = t.ut * OZ_TILE + r;
         if (u < w.n_u) {
           const double s_info = p_info + red[r], s_z = p_z + red[128 + r];
-          const double inf = fabs(s_info);             // info = |b21 B11^-1 b12|      (dist.cpp:198)
+          // a row of B21 the digit planes could not carry (NaN: sd = 0) gives NaN, as its doubles would
+          const double inf = nanflag[w.off_u + u] ? __longlong_as_double(0x7ff8000000000000ll) : fabs(s_info);   // info = |b21 B11^-1 b12|  (dist.cpp:198)
           zu[w.off_u + u] = s_z / sqrt(inf);           // z / sqrt(info)               (dist.cpp:200)
           info[w.off_u + u] = inf;
         }
@@ -320,7 +321,7 @@ oz_slice_x_kernel(const SolveWin* __restrict__ wins, const OzWin* __restrict__ o
 // through shared memory: a CTA takes 32 u x 128 k)
 __global__ void __launch_bounds__(256)
 oz_slice_b_kernel(const SolveWin* __restrict__ wins, const OzWin* __restrict__ ow, const double* __restrict__ ut,
-                  int8_t* __restrict__ planes, int kpad) {
+                  int8_t* __restrict__ planes, int kpad, uint8_t* __restrict__ nanflag) {
   __shared__ double tile[128][33];
   const SolveWin w = wins[blockIdx.z];
   const OzWin o = ow[blockIdx.z];
@@ -336,8 +337,17 @@ oz_slice_b_kernel(const SolveWin* __restrict__ wins, const OzWin* __restrict__ o
   // warp -> one u at a time, lane -> 4 consecutive k: a warp writes 128 contiguous bytes per plane
   for (int uu = wid; uu < 32; uu += 8) {
     int8_t d[4][NDIG];
+    bool bad = false;
 #pragma unroll
-    for (int q = 0; q < 4; q++) oz_digits(tile[4 * lane + q][uu], 0, d[q]);
+    for (int q = 0; q < 4; q++) {
+      double v = tile[4 * lane + q][uu];
+      if (!(fabs(v) <= 1.97)) {   // NaN (sd = 0) or beyond what 7 digits at scale 2^0 carry
+        bad = true;
+        v = 0.0;
+      }
+      oz_digits(v, 0, d[q]);
+    }
+    if (bad) nanflag[w.off_u + u0 + uu] = 1;
 #pragma unroll
     for (int p = 0; p < NDIG; p++) {
       const uint32_t word = (uint32_t)(uint8_t)d[0][p] | ((uint32_t)(uint8_t)d[1][p] << 8) | ((uint32_t)(uint8_t)d[2][p] << 16) |
@@ -414,7 +424,7 @@ void ozaki_tile_rows(const void* h_ow, int win, long long* a_row0, int* ra) {
 int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const void* h_ow, int n_wins, const void* d_tiles,
                        int n_tiles, int kpad, const double* d_x, const double* d_ut, int slice_b21, int8_t* d_planes_a,
                        long long a_rows, int8_t* d_planes_b, long long b_rows, unsigned long long* d_amax, int* d_ex,
-                       const double* d_y, double* d_zu, double* d_info) {
+                       const double* d_y, uint8_t* d_nan, double* d_zu, double* d_info) {
   if (n_wins == 0 || n_tiles == 0) return GB_OK;
   const OzWin* how = static_cast<const OzWin*>(h_ow);
   int max_ra = 0, max_rb = 0, max_nt = 0;
@@ -445,7 +455,7 @@ int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const
   mark();
   if (slice_b21)
     oz_slice_b_kernel<<<dim3((unsigned)(max_ra / 32), (unsigned)(kpad / 128), (unsigned)n_wins), 256, 0, ctx->stream>>>(
-        d_wins, static_cast<const OzWin*>(d_ow), d_ut, d_planes_a, kpad);
+        d_wins, static_cast<const OzWin*>(d_ow), d_ut, d_planes_a, kpad, d_nan);
   mark();
   GB_CUDA(cudaGetLastError());
   ctx->launches += 4;
@@ -460,7 +470,7 @@ int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const
   }
   const int n_ctas = std::min(n_tiles, ctx->sm_count);
   ozaki_solve_kernel<<<(unsigned)n_ctas, OZ_THREADS, OZ_SMEM_ALLOC, ctx->stream>>>(
-      tm_a, tm_b, static_cast<const OzWin*>(d_ow), static_cast<const OzTile*>(d_tiles), n_tiles, d_ex, d_y, d_zu, d_info);
+      tm_a, tm_b, static_cast<const OzWin*>(d_ow), static_cast<const OzTile*>(d_tiles), n_tiles, d_ex, d_y, d_nan, d_zu, d_info);
   mark();
   GB_CUDA(cudaGetLastError());
   ctx->launches++;

@@ -431,6 +431,43 @@ def test_results_do_not_depend_on_uninitialised_memory(solver, monkeypatch):
         ctx.close()
 
 
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_monomorphic_unmeasured_snp_gives_nan_under_both_solvers(oracle, monkeypatch, fmt):
+    """An unmeasured SNP without variation has sd = 0: its correlations are 0/0, and the reference's z and info
+    for it are NaN (dist.cpp:196-200).  The int8-split solve carries B21 as integer digit planes, which have no NaN:
+    the finish pass flags the row instead and the solve returns NaN for it -- and only for it."""
+    c = small_case(seed=41, n_snps=420, pop_sizes=(61, 103, 40, 25, 2, 330, 97), measured_frac=0.3, core=(0, 420))
+    g, t = c["g"].astype(np.int8).copy(), c["type"]
+    idx = np.arange(420)
+    rt, ru = idx[t == 1], idx[t == 0]
+    g[ru[5]] = 0
+    g[ru[140]] = 2
+    res = {}
+    for solver in ("int8", "fp64"):
+        monkeypatch.setenv("GB_SOLVE", solver)
+        ctx = gb.Context(0)
+        try:
+            panel = make_panel(ctx, g, c["pop_sizes"], fmt=fmt)
+            res[solver, "mix"] = panel.window_distmix(rt, ru, c["z"][rt], c["w"])[:2]
+            res[solver, "pooled"] = panel.window_dist(rt, ru, c["z"][rt])[:2]
+        finally:
+            ctx.close()
+    r = oracle.run_window(t, c["bp"], c["z"], g, c["pop_sizes"], c["w"], 0, 10**15)
+    for mode in ("mix", "pooled"):
+        for solver in ("int8", "fp64"):
+            z, info = res[solver, mode]
+            bad = np.isnan(z)
+            assert bad.sum() == 2 and bad[5] and bad[140]
+            assert np.array_equal(np.isnan(info), bad)
+        good = ~np.isnan(res["fp64", mode][0])
+        assert np.abs(res["int8", mode][0][good] - res["fp64", mode][0][good]).max() <= TIGHT
+        assert np.abs(res["int8", mode][1][good] - res["fp64", mode][1][good]).max() <= TIGHT
+    zo = r["z"][t == 0]
+    assert np.isnan(zo[5]) and np.isnan(zo[140])
+    good = ~np.isnan(zo)
+    assert np.abs(res["int8", "mix"][0][good] - zo[good]).max() <= TIGHT
+
+
 def test_overlapped_batch_run_equals_staged_run(gpu_ctx):
     """gb_batch_run puts the factorisation on a side stream beside the B21 Gram tiles once a batch has at least one
     B21 tile per SM; the results must be the bits of the stage-by-stage run, run after run."""
