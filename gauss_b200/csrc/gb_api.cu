@@ -325,7 +325,7 @@ int batch_plan_host(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, co
   if (b->ozaki) {
     b->oz_kpad = (b->max_nt + 127) / 128 * 128;
     b->h_oz_wins.resize(b->h_wins.size() * ozaki_win_bytes());
-    ozaki_plan(b->h_wins.data(), (int)b->h_wins.size(), b->oz_kpad, b->h_oz_wins.data(), &b->h_oz_tiles, &b->oz_a_rows, &b->oz_b_rows);
+    ozaki_plan(b->h_wins.data(), (int)b->h_wins.size(), b->oz_kpad, ctx->sm_count, b->h_oz_wins.data(), &b->h_oz_tiles, &b->oz_a_rows, &b->oz_b_rows);
     b->oz_n_tiles = (int)(b->h_oz_tiles.size() / ozaki_tile_bytes());
     // B21 tiles learn where their rows sit in the digit planes (a tile belongs to the window whose B21 block it writes)
     for (GramTile& t : b->h_tiles) {
@@ -696,8 +696,9 @@ int run_stage_impl(gb_batch* b, int stage) {
         // y = L^-1 z_t).  It needs L only, so it rides with the factorisation (beside the B21 Gram tiles in gb_batch_run)
         const int nw = (int)b->h_wins.size();
         if ((rc = launch_ozaki_prepare_identity(ctx, b->d_wins_x, nw, b->d_x))) return rc;
+        GB_CUDA(cudaMemsetAsync(b->d_oz_amax, 0, sizeof(unsigned long long) * (size_t)nw, ctx->stream));
         return launch_trsm_finalize(ctx, b->d_wins_x, nw, b->max_nt, b->max_nt, b->d_tt, b->d_dinv, b->d_x, b->d_zt,
-                                    b->d_oz_scr, b->d_oz_scr + b->n_t_total, b->d_oz_y, /*tri=*/1);
+                                    b->d_oz_scr, b->d_oz_scr + b->n_t_total, b->d_oz_y, /*tri=*/1, b->d_oz_amax);
       }
       return GB_OK;
     }

@@ -182,7 +182,7 @@ int launch_pd_bound(Ctx* ctx, const SolveWin* d_wins, int n_real, const double* 
                     double gneg, double min_abs_eig, int* d_skip);
 int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,
                          const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info,
-                         double* d_y_out, int tri = 0);
+                         double* d_y_out, int tri = 0, unsigned long long* d_amax = nullptr);
 int launch_qcat_patch(Ctx* ctx, const SolveWin* d_wins, double* d_ut, int n_u, int core_first, int n_core, double diag);
 int launch_qcat_finalize(Ctx* ctx, const SolveWin* d_wins, const double* d_ut, const double* d_y, int n_tested,
                          int num_eig, double* d_qt, double* d_qchisq);
@@ -195,7 +195,7 @@ int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double
 constexpr int OZ_NDIG = 7;   // signed 7-bit digit planes per operand
 size_t ozaki_win_bytes();
 size_t ozaki_tile_bytes();
-void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, void* ow_out, std::vector<uint8_t>* tiles_out, long long* a_rows,
+void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, int n_ctas, void* ow_out, std::vector<uint8_t>* tiles_out, long long* a_rows,
                 long long* b_rows);
 int launch_ozaki_prepare_identity(Ctx* ctx, const SolveWin* d_wins, int n_wins, double* d_x);
 int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const void* h_ow, int n_wins, const void* d_tiles,

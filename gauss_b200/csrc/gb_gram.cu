@@ -589,9 +589,10 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
 // 64-bit conversion).  The correlation is formed as cov (1/sd_i 1/sd_j): a couple of ulps from the reference's division,
 // three orders of magnitude below the 2^-47 the digits resolve.  A value the digits cannot carry (NaN: a monomorphic
 // unmeasured SNP has sd = 0) marks its row in oz_nan; the solve returns NaN for it, as the doubles would.
-// Thread (row r = unmeasured SNP, half h) takes 8 consecutive k per step; the planes want k contiguous per row, so 32
-// columns at a time go through shared memory ([plane][row][32 B]) and leave as whole 32-byte sectors.
-constexpr int OZ_STG_ROW = 40;   // bytes per staged row: 32 + 8 of padding (8-byte accesses, bank-conflict-free per half-warp)
+// A thread takes 4 rows (unmeasured SNPs) x 8 consecutive k per pass; the planes want k contiguous per row, so 64
+// columns at a time go through shared memory ([plane][row][64 B]) and leave as whole 32-byte sectors.
+constexpr int OZ_PASS_COLS = 64;  // columns per trip through the staging buffer
+constexpr int OZ_STG_ROW = OZ_PASS_COLS + 8;   // bytes per staged row: 8 of padding (8-byte accesses, bank-conflict-free per half-warp)
 constexpr size_t OZ_STAGE_BYTES = (size_t)OZ_NDIG * TILE * OZ_STG_ROW;
 
 __device__ __forceinline__ int oz_bfe_s32(uint32_t v, int pos) {
@@ -609,42 +610,56 @@ __device__ __forceinline__ void finalize_oz_tile(const GramParams& prm, const Gr
   constexpr unsigned long long BIAS = 0x0001020408102040ull;             // sum_{p<7} 64 * 128^p
   constexpr unsigned long long MAGIC_BITS = 0x4338000000000000ull;       // bits of 1.5 * 2^52
   const int tid = threadIdx.x;
-  const int r = tid & 127, h = tid >> 7;
-  const bool live = r < t.a_valid;
+  const int lane = tid & 31, cg = tid >> 5;     // rows lane + 32 j (j < 4); column group cg: 8 consecutive k per pass
   const int n_seg = prm.n_seg;
-  const double* out = prm.out_ut + t.out_off;
-  const long long gi = t.i0 + r;
-  const double ai = aiS[r], isd_r = isdA[r];
-  bool row_bad = false;
+  const double* out = prm.out_ut + t.out_off + t.i0;
+  unsigned row_bad = 0;
 #pragma unroll 1
-  for (int it = 0; it < TILE / 32; it++) {
+  for (int pass = 0; pass < TILE / OZ_PASS_COLS; pass++) {
+    const int cb = pass * OZ_PASS_COLS + cg * 8;    // this thread's 8 columns (measured SNPs k)
+    // 4 rows x 8 columns per thread: the rank-P loop below reads 4 + 4 shared-memory vectors per 32 DFMAs (one row per
+    // thread took 5 per 8, and the shared-memory pipe, not fp64 or HBM, set this pass's time)
+    double x[4][8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const bool col_ok = cb + k < t.b_valid;
+      const double* col = out + (long long)(t.j0 + cb + k) * t.ld_out;
+#pragma unroll
+      for (int j = 0; j < 4; j++) x[j][k] = (col_ok && lane + 32 * j < t.a_valid) ? col[lane + 32 * j] : 0.0;
+    }
 #pragma unroll 1
-    for (int sub = 0; sub < 2; sub++) {
-      const int cb = it * 32 + sub * 16 + h * 8;    // this thread's 8 columns (measured SNPs k)
-      double x[8];
-      bool ok[8];
+    for (int p = 0; p < n_seg; p++) {   // + kappa_p s^p_i s^p_j
+      double g[4];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        ok[k] = live && cb + k < t.b_valid;
-        x[k] = ok[k] ? out[(long long)(t.j0 + cb + k) * t.ld_out + gi] : 0.0;
-      }
-#pragma unroll 3
-      for (int p = 0; p < n_seg; p++) {   // + kappa_p s^p_i s^p_j
-        const double g = gA[p * TILE + r];
-        const double2* hv = reinterpret_cast<const double2*>(hB + p * TILE + cb);
+      for (int j = 0; j < 4; j++) g[j] = gA[p * TILE + lane + 32 * j];
+      const double2* hv = reinterpret_cast<const double2*>(hB + p * TILE + cb);
 #pragma unroll
-        for (int k2 = 0; k2 < 4; k2++) {
-          const double2 h2 = hv[k2];
-          x[2 * k2] = fma(g, h2.x, x[2 * k2]);
-          x[2 * k2 + 1] = fma(g, h2.y, x[2 * k2 + 1]);
+      for (int k2 = 0; k2 < 4; k2++) {
+        const double2 h2 = hv[k2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          x[j][2 * k2] = fma(g[j], h2.x, x[j][2 * k2]);
+          x[j][2 * k2 + 1] = fma(g[j], h2.y, x[j][2 * k2 + 1]);
         }
       }
+    }
+    double bj[8], isd_c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      bj[k] = bjS[cb + k];
+      isd_c[k] = isdB[cb + k];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = lane + 32 * j;
+      const double ai = aiS[r], isd_r = isdA[r];
       uint32_t w0[8], w1[8];   // digits 0..3 at bits 0, 7, 14, 21 of w0; digits 4..6 at bits 0, 7, 14 of w1
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        double cor = ok[k] ? fma(-ai, bjS[cb + k], x[k]) * (isd_r * isdB[cb + k]) : 0.0;
+        const bool ok = r < t.a_valid && cb + k < t.b_valid;
+        double cor = ok ? fma(-ai, bj[k], x[j][k]) * (isd_r * isd_c[k]) : 0.0;
         if (!(fabs(cor) <= 1.97)) {
-          row_bad = true;
+          row_bad |= 1u << j;
           cor = 0.0;
         }
         const unsigned long long bits = (unsigned long long)__double_as_longlong(fma(cor, 140737488355328.0, 6755399441055744.0));
@@ -653,7 +668,7 @@ __device__ __forceinline__ void finalize_oz_tile(const GramParams& prm, const Gr
         w0[k] = lo;
         w1[k] = __funnelshift_r(lo, hi, 28);
       }
-      uint8_t* srow = stage + (size_t)r * OZ_STG_ROW + sub * 16 + h * 8;
+      uint8_t* srow = stage + (size_t)r * OZ_STG_ROW + cg * 8;
 #pragma unroll
       for (int p = 0; p < OZ_NDIG; p++) {
         const int pos = 7 * (p < 4 ? p : p - 4);
@@ -665,18 +680,23 @@ __device__ __forceinline__ void finalize_oz_tile(const GramParams& prm, const Gr
       }
     }
     __syncthreads();
-    // 7 planes x 128 rows x 32 bytes: four lanes per row, a warp stores eight whole sectors per instruction
+    // 7 planes x 128 rows x 64 bytes: eight lanes per row, a warp stores eight whole sectors per instruction
 #pragma unroll 2
-    for (int idx = tid; idx < OZ_NDIG * TILE * 4; idx += 256) {
-      const int q4 = idx & 3, row = (idx >> 2) & (TILE - 1), p = idx >> 9;
+    for (int idx = tid; idx < OZ_NDIG * TILE * (OZ_PASS_COLS / 8); idx += 256) {
+      const int q8 = idx & 7, row = (idx >> 3) & (TILE - 1), p = idx >> 10;
       if (row < t.a_valid) {
-        const uint2 v = *reinterpret_cast<const uint2*>(stage + ((size_t)p * TILE + row) * OZ_STG_ROW + q4 * 8);
-        *reinterpret_cast<uint2*>(prm.oz_pa + ((t.oz_row0 + row) + (long long)p * t.oz_ra) * prm.oz_kpad + t.j0 + it * 32 + q4 * 8) = v;
+        const uint2 v = *reinterpret_cast<const uint2*>(stage + ((size_t)p * TILE + row) * OZ_STG_ROW + q8 * 8);
+        *reinterpret_cast<uint2*>(prm.oz_pa + ((t.oz_row0 + row) + (long long)p * t.oz_ra) * prm.oz_kpad + t.j0 +
+                                  pass * OZ_PASS_COLS + q8 * 8) = v;
       }
     }
     __syncthreads();
   }
-  if (row_bad && prm.oz_nan) prm.oz_nan[t.a_list0 + r] = 1;
+  if (row_bad && prm.oz_nan) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (row_bad >> j & 1) prm.oz_nan[t.a_list0 + lane + 32 * j] = 1;
+  }
 }
 
 // Finish pass of the regrouped fold (E2M1 panels, mixture mode).  One CTA per 128 x 128 tile of
@@ -685,7 +705,7 @@ __device__ __forceinline__ void finalize_oz_tile(const GramParams& prm, const Gr
 // in place (diagonal forced, symmetric mirror for computeLD).  A separate, fully occupied kernel
 // instead of a tail on the 8 epilogue warps of the tensor-core kernel: there it serialised with
 // the next tile's MMAs (3 TMEM buffers ahead at most) and cost 27 % of the kernel.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gram_finalize_kernel(const __grid_constant__ GramParams prm) {
   const GramTile t = prm.tiles[blockIdx.x];
   if (t.a_valid <= 0 || t.b_valid <= 0) return;

@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <queue>
+
 #include "gb_batch.cuh"
 #include "gb_ptx.cuh"
 
@@ -48,6 +50,7 @@ constexpr int OZ_OFF_Y = OZ_OFF_STAGES + OZ_STAGES * OZ_STAGE_BYTES;
 constexpr int OZ_SMEM = OZ_OFF_Y + OZ_Y_MAX * 8;
 constexpr int OZ_SMEM_ALLOC = OZ_SMEM + 1024;
 static_assert(OZ_SMEM_ALLOC <= 232448, "shared memory budget exceeded");
+static_assert(NDIG == 7, "oz_digits and the finish pass extract exactly seven 7-bit fields");
 static_assert(OZ_OFF_RED + 2 * 128 * 8 <= OZ_OFF_STAGES, "header overlaps the stages");
 
 struct OzWin {
@@ -124,6 +127,7 @@ ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         uint32_t phase = 0;
         for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
           const OzTile t = tiles[ct];
+          if (t.win < 0) continue;   // unused slot of the longest-first deal
           const OzWin w = wins[t.win];
           const int a_row = (int)(w.a_row0 + (long long)t.ut * OZ_TILE);
           for (int J = 0; J < w.nbt; J++) {
@@ -154,6 +158,7 @@ ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
+          if (tiles[ct].win < 0) continue;
           const OzWin w = wins[tiles[ct].win];
           for (int J = 0; J < w.nbt; J++) {
             for (int gi = 0; gi < NG; gi++) {
@@ -197,6 +202,7 @@ ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     uint32_t acc_phase = 0;
     for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
       const OzTile t = tiles[ct];
+      if (t.win < 0) continue;
       const OzWin w = wins[t.win];
       const int e_x = ex[t.win];
       oz_epi_bar_sync();   // the previous tile's readers of ys / red are done
@@ -265,20 +271,6 @@ ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 }
 
 // ---- operand preparation -------------------------------------------------------------------------------------------
-// max |v| of a window's matrix (as the bits of a non-negative double, which order like unsigned integers)
-__global__ void __launch_bounds__(256)
-oz_absmax_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ X, unsigned long long* amax) {
-  const SolveWin w = wins[blockIdx.y];
-  const long long total = (long long)w.n_t * w.ld_t;
-  double m = 0.0;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int r = (int)(i / w.ld_t), c = (int)(i % w.ld_t);
-    if (c <= r && c < w.n_t) m = fmax(m, fabs(X[w.off_tt + i]));
-  }
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(&amax[blockIdx.y], (unsigned long long)__double_as_longlong(m));
-}
-
 __global__ void oz_exponent_kernel(const unsigned long long* __restrict__ amax, int n, int* ex) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -288,13 +280,17 @@ __global__ void oz_exponent_kernel(const unsigned long long* __restrict__ amax, 
   ex[i] = e;
 }
 
+// q = rint(v 2^(QBITS - e)) = sum_p d_p 128^p, d_p in [-64, 63]: with BIAS = sum_p 64 128^p the unsigned base-128 digits of
+// q + BIAS are d_p + 64, so the signed 7-bit field p of (q + BIAS) ^ BIAS is d_p -- no carry chain (|v| 2^-e < 1)
 __device__ __forceinline__ void oz_digits(double v, int e, int8_t (&d)[NDIG]) {
-  long long q = __double2ll_rn(ldexp(v, QBITS - e));
+  constexpr unsigned long long BIAS = 0x0001020408102040ull;
+  const unsigned long long q = ((unsigned long long)__double2ll_rn(ldexp(v, QBITS - e)) + BIAS) ^ BIAS;
+  const uint32_t lo = (uint32_t)q, w1 = __funnelshift_r((uint32_t)q, (uint32_t)(q >> 32), 28);
 #pragma unroll
   for (int p = 0; p < NDIG; p++) {
-    const long long dd = ((q + 64) & 127) - 64;
-    d[p] = (int8_t)dd;
-    q = (q - dd) >> 7;
+    int f;
+    asm("bfe.s32 %0, %1, %2, 7;" : "=r"(f) : "r"(p < 4 ? lo : w1), "r"(7 * (p < 4 ? p : p - 4)));
+    d[p] = (int8_t)f;
   }
 }
 
@@ -308,12 +304,18 @@ oz_slice_x_kernel(const SolveWin* __restrict__ wins, const OzWin* __restrict__ o
   if (r >= o.rb) return;
   const int e = ex[blockIdx.y];
   const double* row = X + w.off_tt + (long long)r * w.ld_t;
-  for (int k = threadIdx.x; k < kpad; k += 256) {
-    int8_t d[NDIG];
-    const double v = (r < w.n_t && k <= r) ? row[k] : 0.0;
-    oz_digits(v, e, d);
+  for (int k4 = 4 * threadIdx.x; k4 < kpad; k4 += 4 * 256) {   // 4 consecutive k per thread: one 32-bit store per plane
+    int8_t d[4][NDIG];
 #pragma unroll
-    for (int p = 0; p < NDIG; p++) planes[(o.b_row0 + (long long)p * o.rb + r) * kpad + k] = d[p];
+    for (int q = 0; q < 4; q++) {
+      const int k = k4 + q;
+      oz_digits((r < w.n_t && k <= r) ? row[k] : 0.0, e, d[q]);
+    }
+#pragma unroll
+    for (int p = 0; p < NDIG; p++)
+      *reinterpret_cast<uint32_t*>(planes + (o.b_row0 + (long long)p * o.rb + r) * kpad + k4) =
+          (uint32_t)(uint8_t)d[0][p] | ((uint32_t)(uint8_t)d[1][p] << 8) | ((uint32_t)(uint8_t)d[2][p] << 16) |
+          ((uint32_t)(uint8_t)d[3][p] << 24);
   }
 }
 
@@ -375,8 +377,8 @@ size_t ozaki_tile_bytes() { return sizeof(OzTile); }
 
 // Host-side plan of the int8-split solve for a batch: fills the window / tile descriptors (in the order of `wins`,
 // heaviest first) and returns the plane sizes.  kpad = K bytes per plane row (multiple of 128, >= the largest n_t).
-void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, void* ow_out, std::vector<uint8_t>* tiles_out, long long* a_rows,
-                long long* b_rows) {
+void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, int n_ctas, void* ow_out, std::vector<uint8_t>* tiles_out,
+                long long* a_rows, long long* b_rows) {
   OzWin* ow = static_cast<OzWin*>(ow_out);
   long long ar = 0, br = 0;
   std::vector<OzTile> tiles;
@@ -398,8 +400,27 @@ void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, void* ow_out, std::v
     for (int ut = 0; ut < o.nbu; ut++) tiles.push_back(OzTile{i, ut});
   }
   (void)kpad;
-  tiles_out->resize(tiles.size() * sizeof(OzTile));
-  if (!tiles.empty()) std::memcpy(tiles_out->data(), tiles.data(), tiles_out->size());
+  // A tile of a window with nbt column blocks costs nbt (nbt + 1) / 2 K-block sweeps, known here: deal the tiles to the
+  // persistent CTAs longest-processing-time-first (the windows come heaviest first) instead of round-robin.  CTA c runs
+  // slots c, c + n_ctas, ...; unused slots hold win = -1.
+  n_ctas = std::max(1, std::min<int>(n_ctas, (int)tiles.size()));
+  std::vector<std::vector<OzTile>> per_cta((size_t)n_ctas);
+  std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>, std::greater<>> load;
+  for (int c = 0; c < n_ctas; c++) load.push({0, c});
+  std::stable_sort(tiles.begin(), tiles.end(), [&](const OzTile& a, const OzTile& c) { return ow[a.win].nbt > ow[c.win].nbt; });
+  size_t rounds = 0;
+  for (const OzTile& t : tiles) {
+    auto [l, c] = load.top();
+    load.pop();
+    per_cta[(size_t)c].push_back(t);
+    rounds = std::max(rounds, per_cta[(size_t)c].size());
+    load.push({l + (long long)ow[t.win].nbt * (ow[t.win].nbt + 1) / 2, c});
+  }
+  std::vector<OzTile> slots(rounds * (size_t)n_ctas, OzTile{-1, 0});
+  for (int c = 0; c < n_ctas; c++)
+    for (size_t r = 0; r < per_cta[(size_t)c].size(); r++) slots[r * (size_t)n_ctas + (size_t)c] = per_cta[(size_t)c][r];
+  tiles_out->resize(slots.size() * sizeof(OzTile));
+  if (!slots.empty()) std::memcpy(tiles_out->data(), slots.data(), tiles_out->size());
   *a_rows = ar;
   *b_rows = br;
 }
@@ -446,8 +467,7 @@ int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const
     cudaEventRecord(ev[n_ev++], ctx->stream);
   };
   mark();
-  GB_CUDA(cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long) * (size_t)n_wins, ctx->stream));
-  oz_absmax_kernel<<<dim3(32, (unsigned)n_wins), 256, 0, ctx->stream>>>(d_wins, d_x, d_amax);
+  // d_amax: max |L^-1| per window, left by the triangular solve that formed X
   oz_exponent_kernel<<<(unsigned)((n_wins + 127) / 128), 128, 0, ctx->stream>>>(d_amax, n_wins, d_ex);
   mark();
   oz_slice_x_kernel<<<dim3((unsigned)max_rb, (unsigned)n_wins), 256, 0, ctx->stream>>>(d_wins, static_cast<const OzWin*>(d_ow), d_x,
@@ -458,7 +478,7 @@ int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const
         d_wins, static_cast<const OzWin*>(d_ow), d_ut, d_planes_a, kpad, d_nan);
   mark();
   GB_CUDA(cudaGetLastError());
-  ctx->launches += 4;
+  ctx->launches += 3;
   CUtensorMap tm_a, tm_b;
   int rc;
   if ((rc = make_row_tensor_map(ctx, &tm_a, d_planes_a, a_rows, kpad, kpad, MAP_INT8, OZ_TILE))) return rc;
@@ -468,7 +488,7 @@ int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const
     GB_CUDA(cudaFuncSetAttribute(ozaki_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_ALLOC));
     attr_set_dev[ctx->device & 63] = true;
   }
-  const int n_ctas = std::min(n_tiles, ctx->sm_count);
+  const int n_ctas = std::min(n_tiles, ctx->sm_count);   // ozaki_plan dealt the slots to this many CTAs
   ozaki_solve_kernel<<<(unsigned)n_ctas, OZ_THREADS, OZ_SMEM_ALLOC, ctx->stream>>>(
       tm_a, tm_b, static_cast<const OzWin*>(d_ow), static_cast<const OzTile*>(d_tiles), n_tiles, d_ex, d_y, d_nan, d_zu, d_info);
   mark();
@@ -476,7 +496,7 @@ int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const
   ctx->launches++;
   if (trace) {
     cudaStreamSynchronize(ctx->stream);
-    static const char* const nm[] = {"absmax", "slice_x", "slice_b21", "gemm"};
+    static const char* const nm[] = {"exponent", "slice_x", "slice_b21", "gemm"};
     fprintf(stderr, "[oz trace]");
     for (int i = 0; i + 1 < n_ev; i++) {
       float ms = 0;

@@ -411,7 +411,7 @@ template <int UB_>
 __global__ void __launch_bounds__(256, 2)
 trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt,
                      const double* __restrict__ dinv, double* ut, const double* __restrict__ zt,
-                     double* zu, double* info, double* y_out, int tri) {
+                     double* zu, double* info, double* y_out, int tri, unsigned long long* amax_out) {
   const SolveWin w = wins[blockIdx.y];
   const int n = w.n_t, nu = w.n_u;
   constexpr int NTW = UB_ / 32;      // 8-column MMA tiles per warp
@@ -449,6 +449,7 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
   // tri: the right-hand side is the identity (explicit L^-1 for the int8-split solve): block rows above this CTA's
   // first column hold zeros and stay zero, and the block columns of W left of it contribute nothing
   const int ib0 = tri ? u0 / NB : 0;
+  double vmax = 0.0;   // tri: max |L^-1| of this CTA's columns (the int8-split solve scales its digit planes by it)
   for (int ib = ib0; ib < nb; ib++) {
     const int i0 = ib * NB;
     double C[4][NTW][2];
@@ -580,6 +581,7 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const double v = C[mt][nt][e];
+          if (c + e < cvalid) vmax = fmax(vmax, fabs(v));
           p_info[nt][e] = fma(v, v, p_info[nt][e]);
           p_z[nt][e] = fma(yr, v, p_z[nt][e]);
         }
@@ -609,6 +611,10 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
       }
   }
   __syncthreads();
+  if (amax_out) {   // bits of a non-negative double order like unsigned integers
+    for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.0) atomicMax(&amax_out[blockIdx.y], (unsigned long long)__double_as_longlong(vmax));
+  }
   if (y_out && blockIdx.x == 0)   // qcat: y = L^-1 Z1 is an output too (every CTA carries the same column)
     for (int i = tid; i < n; i += 256) y_out[w.off_t + i] = ys[i];
   if (tid < UB_ && u0 + tid < nu) {
@@ -859,7 +865,7 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
 
 int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,
                          const double* d_dinv, double* d_ut, const double* d_zt, double* d_zu, double* d_info,
-                         double* d_y_out, int tri) {
+                         double* d_y_out, int tri, unsigned long long* d_amax) {
   if (n_wins == 0 || max_nu == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
   // 128 columns per CTA when the launch has waves to spare, 64 when it is about one wave (a single window, the
@@ -883,8 +889,8 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
     else GB_CUDA(cudaFuncSetAttribute(trsm_finalize_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     have = smem;
   }
-  if (narrow) trsm_finalize_kernel<64><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out, tri);
-  else trsm_finalize_kernel<128><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out, tri);
+  if (narrow) trsm_finalize_kernel<64><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out, tri, d_amax);
+  else trsm_finalize_kernel<128><<<grid, 256, smem, ctx->stream>>>(d_wins, d_tt, d_dinv, d_ut, d_zt, d_zu, d_info, d_y_out, tri, d_amax);
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
   return GB_OK;

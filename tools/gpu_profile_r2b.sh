@@ -1,0 +1,14 @@
+#!/usr/bin/env bash
+# round-2 profile pass with the int8-split solver: plain run must exit 0 first, then the launch list, then one --set full capture
+set -u
+mkdir -p gpurun_out
+TAG=${TAG:-r02b}
+ARGS="--workload chr22 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
+timeout -s KILL 200 python bench.py $ARGS > gpurun_out/plain_${TAG}.json 2> gpurun_out/plain_${TAG}.err || { echo "plain run failed"; tail -5 gpurun_out/plain_${TAG}.err; exit 1; }
+echo "plain ok"; tail -c 600 gpurun_out/plain_${TAG}.json
+K='regex:gram_seg|gram_fin|chol_|trsm_|row_prep|pack_rows|expand5|pd_bound|copy_shift|gather_rows|synth_pack5|probe|ozaki|oz_'
+timeout -s KILL 500 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 700 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py $ARGS > gpurun_out/ncu_launch_${TAG}.log 2>&1
+echo "launch list rc=$?"
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k 'regex:gram_seg|gram_finalize|trsm_finalize|ozaki_solve|oz_slice_x|oz_absmax' -s 6 -c 14 -o gpurun_out/prof_${TAG} -f python bench.py $ARGS > gpurun_out/ncu_full_${TAG}.log 2>&1
+echo "full rc=$?"
+ls -la gpurun_out/prof_${TAG}.ncu-rep
