@@ -192,7 +192,9 @@ int launch_copy_shift(Ctx* ctx, const SolveWin* d_wins, int n_wins, const double
                       double shift, const int* d_skip);
 
 // gb_ozaki.cu: the solve's n_t^2 n_u term as an exact int8-split GEMM on tcgen05 (kind::i8)
-constexpr int OZ_NDIG = 7;   // signed 7-bit digit planes per operand
+constexpr int OZ_NDIG = 6;    // signed 8-bit digit planes per operand
+constexpr int OZ_QBITS = 8 * OZ_NDIG - 2;   // fixed-point bits below the scale: v = 2^e q 2^-46, |q| < 2^46 (1.95 2^46 for B21)
+constexpr unsigned long long OZ_BIAS = 0x0000808080808080ull;   // sum_p 128 * 256^p: q + BIAS has the unsigned digits d_p + 128
 size_t ozaki_win_bytes();
 size_t ozaki_tile_bytes();
 void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, int n_ctas, void* ow_out, std::vector<uint8_t>* tiles_out, long long* a_rows,

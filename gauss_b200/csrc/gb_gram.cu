@@ -581,33 +581,24 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
 }
 
 // ---- int8-split solve: a B21 tile leaves the finish pass as digit planes ---------------------------------------------
-// The solve multiplies B21 by L^-T on the int8 tensor cores (gb_ozaki.cu), so this pass writes the OZ_NDIG signed 7-bit
-// digit planes of a tile's correlations instead of its doubles:
-//   q = rint(cor 2^47),  q = sum_p d_p 128^p,  d_p in [-64, 63]     (|cor| < 1.97; 49-bit fixed point)
-// Digits without a carry chain: q' = q + BIAS with BIAS = sum_p 64 128^p has the unsigned base-128 digits d_p + 64, and
-// the signed 7-bit field p of q' ^ BIAS is d_p itself.  q comes out of the mantissa of cor 2^47 + 1.5 2^52 (one FMA, no
-// 64-bit conversion).  The correlation is formed as cov (1/sd_i 1/sd_j): a couple of ulps from the reference's division,
-// three orders of magnitude below the 2^-47 the digits resolve.  A value the digits cannot carry (NaN: a monomorphic
-// unmeasured SNP has sd = 0) marks its row in oz_nan; the solve returns NaN for it, as the doubles would.
+// The solve multiplies B21 by L^-T on the int8 tensor cores (gb_ozaki.cu), so this pass writes the OZ_NDIG = 6 signed
+// 8-bit digit planes of a tile's correlations instead of its doubles:
+//   q = rint(cor 2^46),  q = sum_p d_p 256^p,  d_p in [-128, 127]     (|cor| <= 1.95; 48-bit fixed point)
+// Digits without a carry chain: q + BIAS with BIAS = sum_p 128 256^p has the unsigned base-256 digits d_p + 128, so
+// the six low bytes of (q + BIAS) ^ BIAS are the digits.  q comes out of the mantissa of cor 2^46 + 1.5 2^52 (one FMA,
+// no 64-bit conversion); the planes of 4 consecutive k are a 4 x 4 byte transpose (PRMT).  The correlation is formed as
+// cov (1/sd_i 1/sd_j): a couple of ulps from the reference's division, three orders of magnitude below the 2^-46 the
+// digits resolve.  A value the digits cannot carry (NaN: a monomorphic unmeasured SNP has sd = 0) marks its row in
+// oz_nan; the solve returns NaN for it, as the doubles would.
 // A thread takes 4 rows (unmeasured SNPs) x 8 consecutive k per pass; the planes want k contiguous per row, so 64
 // columns at a time go through shared memory ([plane][row][64 B]) and leave as whole 32-byte sectors.
 constexpr int OZ_PASS_COLS = 64;  // columns per trip through the staging buffer
 constexpr int OZ_STG_ROW = OZ_PASS_COLS + 8;   // bytes per staged row: 8 of padding (8-byte accesses, bank-conflict-free per half-warp)
 constexpr size_t OZ_STAGE_BYTES = (size_t)OZ_NDIG * TILE * OZ_STG_ROW;
 
-__device__ __forceinline__ int oz_bfe_s32(uint32_t v, int pos) {
-  int d;
-  asm("bfe.s32 %0, %1, %2, 7;" : "=r"(d) : "r"(v), "r"(pos));
-  return d;
-}
-__device__ __forceinline__ uint32_t oz_pack4(int b0, int b1, int b2, int b3) {
-  return __byte_perm(__byte_perm((uint32_t)b0, (uint32_t)b1, 0x0040), __byte_perm((uint32_t)b2, (uint32_t)b3, 0x0040), 0x5410);
-}
-
 __device__ __forceinline__ void finalize_oz_tile(const GramParams& prm, const GramTile& t, const double* gA, const double* hB,
                                                  const double* aiS, const double* bjS, const double* isdA, const double* isdB,
                                                  uint8_t* stage) {
-  constexpr unsigned long long BIAS = 0x0001020408102040ull;             // sum_{p<7} 64 * 128^p
   constexpr unsigned long long MAGIC_BITS = 0x4338000000000000ull;       // bits of 1.5 * 2^52
   const int tid = threadIdx.x;
   const int lane = tid & 31, cg = tid >> 5;     // rows lane + 32 j (j < 4); column group cg: 8 consecutive k per pass
@@ -653,34 +644,40 @@ __device__ __forceinline__ void finalize_oz_tile(const GramParams& prm, const Gr
     for (int j = 0; j < 4; j++) {
       const int r = lane + 32 * j;
       const double ai = aiS[r], isd_r = isdA[r];
-      uint32_t w0[8], w1[8];   // digits 0..3 at bits 0, 7, 14, 21 of w0; digits 4..6 at bits 0, 7, 14 of w1
+      uint32_t lo[8], hi[8];   // bytes of lo: digits 0..3; low bytes of hi: digits 4, 5
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const bool ok = r < t.a_valid && cb + k < t.b_valid;
         double cor = ok ? fma(-ai, bj[k], x[j][k]) * (isd_r * isd_c[k]) : 0.0;
-        if (!(fabs(cor) <= 1.97)) {
+        if (!(fabs(cor) <= 1.95)) {
           row_bad |= 1u << j;
           cor = 0.0;
         }
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(fma(cor, 140737488355328.0, 6755399441055744.0));
-        const unsigned long long q = (bits + (BIAS - MAGIC_BITS)) ^ BIAS;
-        const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
-        w0[k] = lo;
-        w1[k] = __funnelshift_r(lo, hi, 28);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(fma(cor, 70368744177664.0, 6755399441055744.0));
+        const unsigned long long q = (bits + (OZ_BIAS - MAGIC_BITS)) ^ OZ_BIAS;
+        lo[k] = (uint32_t)q;
+        hi[k] = (uint32_t)(q >> 32);
       }
       uint8_t* srow = stage + (size_t)r * OZ_STG_ROW + cg * 8;
+      uint32_t pl[OZ_NDIG][2];
 #pragma unroll
-      for (int p = 0; p < OZ_NDIG; p++) {
-        const int pos = 7 * (p < 4 ? p : p - 4);
-        int b[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) b[k] = oz_bfe_s32(p < 4 ? w0[k] : w1[k], pos);
-        *reinterpret_cast<uint2*>(srow + (size_t)p * TILE * OZ_STG_ROW) =
-            make_uint2(oz_pack4(b[0], b[1], b[2], b[3]), oz_pack4(b[4], b[5], b[6], b[7]));
+      for (int hf = 0; hf < 2; hf++) {   // 4 x 4 byte transposes: plane p of k = 4 hf .. 4 hf + 3
+        const uint32_t a = __byte_perm(lo[4 * hf], lo[4 * hf + 1], 0x5140), b = __byte_perm(lo[4 * hf + 2], lo[4 * hf + 3], 0x5140);
+        const uint32_t c = __byte_perm(lo[4 * hf], lo[4 * hf + 1], 0x7362), d = __byte_perm(lo[4 * hf + 2], lo[4 * hf + 3], 0x7362);
+        const uint32_t e = __byte_perm(hi[4 * hf], hi[4 * hf + 1], 0x5140), f = __byte_perm(hi[4 * hf + 2], hi[4 * hf + 3], 0x5140);
+        pl[0][hf] = __byte_perm(a, b, 0x5410);
+        pl[1][hf] = __byte_perm(a, b, 0x7632);
+        pl[2][hf] = __byte_perm(c, d, 0x5410);
+        pl[3][hf] = __byte_perm(c, d, 0x7632);
+        pl[4][hf] = __byte_perm(e, f, 0x5410);
+        pl[5][hf] = __byte_perm(e, f, 0x7632);
       }
+#pragma unroll
+      for (int p = 0; p < OZ_NDIG; p++)
+        *reinterpret_cast<uint2*>(srow + (size_t)p * TILE * OZ_STG_ROW) = make_uint2(pl[p][0], pl[p][1]);
     }
     __syncthreads();
-    // 7 planes x 128 rows x 64 bytes: eight lanes per row, a warp stores eight whole sectors per instruction
+    // 6 planes x 128 rows x 64 bytes: eight lanes per row, a warp stores eight whole sectors per instruction
 #pragma unroll 2
     for (int idx = tid; idx < OZ_NDIG * TILE * (OZ_PASS_COLS / 8); idx += 256) {
       const int q8 = idx & 7, row = (idx >> 3) & (TILE - 1), p = idx >> 10;

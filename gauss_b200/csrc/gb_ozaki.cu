@@ -5,12 +5,16 @@
 // dependency and moves the GEMM to the tensor cores:
 //   X  = L^-1                 (explicit: the blocked trsm kernel on identity columns, zero blocks skipped; + n_t^3 / 3)
 //   W^T = B21 X^T             (n_u x n_t, only ||W_col||^2 and W_col . y are needed: W is never stored)
-// Both operands are split into NDIG = 7 signed 7-bit digits of a 49-bit fixed-point value (x = 2^e sum_s d_s 2^(7s - 47),
-// d_s in [-64, 63]); every digit-pair product sum_k dB_s[u, k] dX_t[r, k] is an exact int32 (|.| <= 64^2 K); pairs of
-// equal weight s + t share one TMEM accumulator; the NG = 7 heaviest weight groups (s + t >= 6: 28 pairs) are recombined
-// in fp64 (2^(7 (s + t) - 94 + e_X) each).  Quantisation (2^-47 of the scale per entry) and the dropped groups (< 2^-47
-// per product term) leave |dW| ~ 1e-12: the 1e-6 bar with six orders to spare, and inside what the fp64 path achieved
-// against the LU oracle.  L^-1 is lower triangular, so the K range of the 128-row tile J of X ends at 128 (J + 1).
+// Both operands are split into NDIG = 6 signed 8-bit digits of a 48-bit fixed-point value (x = 2^e sum_s d_s 2^(8s - 46),
+// d_s in [-128, 127]); every digit-pair product sum_k dB_s[u, k] dX_t[r, k] is an exact int32 (|.| <= 128^2 K per pair,
+// 6 pairs and K <= 2048 at most: 2^27.6); pairs of equal weight s + t share one TMEM accumulator; the NG = 7 heaviest
+// weight groups (s + t >= 4: 26 of the 36 pairs) are recombined in fp64 (2^(8 (s + t) - 92 + e_X) each).  Quantisation
+// (2^-46 of the scale per entry) and the dropped groups (< 2^-52 of a product term) leave |dz| ~ 2e-12 on a 750-SNP
+// window (simulated against extended precision): the 1e-6 bar with five orders to spare and tighter than the fp64 path's
+// own distance to the LU oracle.  (Seven 7-bit digits with 28 pairs, the first version, measured 4.6e-11 and cost a
+// plane and two pairs more; s + t >= 5, 21 pairs, gives 7.5e-11.)  Balanced base-256 digits need no carry chain: with
+// BIAS = sum_p 128 256^p the bytes of (q + BIAS) ^ 0x80..80 ARE the digits.  L^-1 is lower triangular, so the K range of
+// the 128-row tile J of X ends at 128 (J + 1).
 //
 // Kernel = the Gram kernel's skeleton: warp 0 TMA producer (128-byte-swizzled [128 rows x 128 B] boxes, 6 stages),
 // warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue; work item = (window, 128 unmeasured SNPs), inner loop
@@ -27,10 +31,11 @@ namespace gb {
 
 namespace {
 
-constexpr int NDIG = OZ_NDIG;       // signed 7-bit digits per operand (7: a 49-bit fixed-point value)
-constexpr int GMIN = 6;             // lightest digit-weight group kept (s + t >= GMIN)
-constexpr int NG = 2 * (NDIG - 1) - GMIN + 1;   // 7 groups: s + t = 12 .. 6, 28 digit pairs
-constexpr int QBITS = 7 * NDIG - 2; // value = 2^e sum_s d_s 2^(7 s - QBITS), |value| 2^-e < 1
+constexpr int NDIG = OZ_NDIG;       // signed 8-bit digits per operand (6: a 48-bit fixed-point value)
+constexpr int DBITS = 8;
+constexpr int GMIN = 4;             // lightest digit-weight group kept (s + t >= GMIN)
+constexpr int NG = 2 * (NDIG - 1) - GMIN + 1;   // 7 groups: s + t = 10 .. 4, 26 digit pairs
+constexpr int QBITS = OZ_QBITS;     // value = 2^e sum_s d_s 2^(8 s - QBITS), |value| 2^-e < 1
 constexpr int OZ_STAGES = 6;
 constexpr int OZ_TILE = 128;
 constexpr int OZ_STAGE_OPERAND = OZ_TILE * 128;      // 16 KiB
@@ -50,7 +55,7 @@ constexpr int OZ_OFF_Y = OZ_OFF_STAGES + OZ_STAGES * OZ_STAGE_BYTES;
 constexpr int OZ_SMEM = OZ_OFF_Y + OZ_Y_MAX * 8;
 constexpr int OZ_SMEM_ALLOC = OZ_SMEM + 1024;
 static_assert(OZ_SMEM_ALLOC <= 232448, "shared memory budget exceeded");
-static_assert(NDIG == 7, "oz_digits and the finish pass extract exactly seven 7-bit fields");
+static_assert(NDIG == 6 && QBITS == 46, "oz_digits and the finish pass read the digits as the six low bytes of a 64-bit word");
 static_assert(OZ_OFF_RED + 2 * 128 * 8 <= OZ_OFF_STAGES, "header overlaps the stages");
 
 struct OzWin {
@@ -215,7 +220,7 @@ ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         for (int e = 0; e < 64; e++) a[e] = 0.0;
         for (int gi = 0; gi < NG; gi++) {
           const int gw = 2 * (NDIG - 1) - gi;
-          const double sc = __hiloint2double((1023 + 7 * gw - 2 * QBITS + e_x) << 20, 0);   // 2^(7 g' - 2 QBITS + e_X)
+          const double sc = __hiloint2double((1023 + DBITS * gw - 2 * QBITS + e_x) << 20, 0);   // 2^(8 g' - 2 QBITS + e_X)
           ptx::mbar_wait(&tfull_bar[acc_buf], acc_phase);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + acc_buf * OZ_TILE + ((uint32_t)(quad * 32) << 16) + c0;
@@ -280,18 +285,12 @@ __global__ void oz_exponent_kernel(const unsigned long long* __restrict__ amax, 
   ex[i] = e;
 }
 
-// q = rint(v 2^(QBITS - e)) = sum_p d_p 128^p, d_p in [-64, 63]: with BIAS = sum_p 64 128^p the unsigned base-128 digits of
-// q + BIAS are d_p + 64, so the signed 7-bit field p of (q + BIAS) ^ BIAS is d_p -- no carry chain (|v| 2^-e < 1)
+// q = rint(v 2^(QBITS - e)) = sum_p d_p 256^p, d_p in [-128, 127]: q + BIAS has the unsigned base-256 digits d_p + 128,
+// so the bytes of (q + BIAS) ^ BIAS are the signed digits themselves -- no carry chain (|v| 2^-e < 1)
 __device__ __forceinline__ void oz_digits(double v, int e, int8_t (&d)[NDIG]) {
-  constexpr unsigned long long BIAS = 0x0001020408102040ull;
-  const unsigned long long q = ((unsigned long long)__double2ll_rn(ldexp(v, QBITS - e)) + BIAS) ^ BIAS;
-  const uint32_t lo = (uint32_t)q, w1 = __funnelshift_r((uint32_t)q, (uint32_t)(q >> 32), 28);
+  const unsigned long long q = ((unsigned long long)__double2ll_rn(ldexp(v, QBITS - e)) + OZ_BIAS) ^ OZ_BIAS;
 #pragma unroll
-  for (int p = 0; p < NDIG; p++) {
-    int f;
-    asm("bfe.s32 %0, %1, %2, 7;" : "=r"(f) : "r"(p < 4 ? lo : w1), "r"(7 * (p < 4 ? p : p - 4)));
-    d[p] = (int8_t)f;
-  }
+  for (int p = 0; p < NDIG; p++) d[p] = (int8_t)(uint8_t)(q >> (8 * p));
 }
 
 // X = L^-1 (row-major n_t x ld_t, lower triangular) -> digit planes: one CTA per (row, window), k contiguous
@@ -343,7 +342,7 @@ oz_slice_b_kernel(const SolveWin* __restrict__ wins, const OzWin* __restrict__ o
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       double v = tile[4 * lane + q][uu];
-      if (!(fabs(v) <= 1.97)) {   // NaN (sd = 0) or beyond what 7 digits at scale 2^0 carry
+      if (!(fabs(v) <= 1.95)) {   // NaN (sd = 0) or beyond what the digits carry at scale 2^0
         bad = true;
         v = 0.0;
       }
