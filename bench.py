@@ -17,8 +17,10 @@ Workloads (`--workload`):
             around everything the step enqueues incl. the D2H of z / info), max over ranks
   e2e       the same job from pinned HOST rows (ternary packed panel): host -> device upload of every GPU's rows inside
             the timed region, batches starting as their rows land, results written to host arrays; wall clock
-  roofline  the longest kernel of the step (trsm_finalize_kernel) against the fp64 tensor-core rate measured on this box
-            at bench time (gb_probe_peak); roofline_gram / roofline_chol / roofline_expand5 beside it
+  roofline  the longest kernel of the step (gram_seg_kernel, tensor-bound) against the tensor-pipe rate of its instruction
+            kind measured on this box at bench time (gb_probe_peak); roofline_solve (the int8-split solve GEMM against the
+            kind::i8 probe), roofline_linv / roofline_chol (fp64 probe), roofline_finish / roofline_expand5 (HBM) beside it.
+            GB_SOLVE=fp64 brings back the DMMA triangular solve, which is then the longest kernel and the `roofline`
   cpu_baseline / --impl reference   the reference's own CPU code (oracle/_ref) on a bounded sample, see cpu_model()
 """
 from __future__ import annotations
@@ -585,18 +587,14 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
     mhz = clocks.get("sm_max_mhz") or 1965.0
     fp64_peak = probes.get("fp64") or 148 * 128 * mhz * 1e6 / 1e12
     fp64_src = "gb_probe_peak fp64 (mma.sync m8n8k4, measured on this box now)" if probes.get("fp64") else "148 SM x 128 flop x SM clock"
+    serial_ms = float(st.sum(1).mean())
     out.update(
         value=n_imputed * args.steps / (total_ms / 1e3), ms_per_step=total_ms / args.steps, launches=int(launches), clocks=clocks,
         n_imputed=n_imputed, windows_ok=n_ok, panel_gen_s=gen_s, work=work, z=z, info=info, status=status,
-        stage_ms_serial=float(st.sum(1).mean()),
+        stage_ms_serial=serial_ms,
         stage_ms=dict(row_stats=float(st[:, 0].mean()), gram=gram_ms, gram_finish=fin_ms, cholesky=chol_ms, linv=trtri_ms, solve=trsm_ms),
-        solver="int8-split GEMM on tcgen05 (kind::i8, 7 x 7-bit digits, 28 digit pairs) behind an explicit L^-1" if ozaki else "fp64 DMMA triangular solve",
-        roofline=dict(bound="tensor", kernel="trsm_finalize_kernel", achieved=trsm_flops / (trsm_ms / 1e3) / 1e12, peak=fp64_peak,
-                      unit="TFLOP/s", frac=trsm_flops / (trsm_ms / 1e3) / 1e12 / fp64_peak,
-                      traffic=NCU["trsm"].get("dram_bytes"), ms=trsm_ms, share_of_step=trsm_ms / float(st.sum(1).mean()),
-                      note=(f"longest kernel of the step ({tag} batch, event-timed alone); algorithmic flops sum(n_t^2 n_u + n_t^2 + "
-                            f"4 n_t n_u) = {trsm_flops:.4g} per launch (no Cholesky term); pipe = fp64 tensor core (DMMA m8n8k4); peak = "
-                            f"{fp64_src}; traffic = dram bytes per launch from {NCU['trsm'].get('file')} vs {8 * float((nts * nts + nts * nus)[okw].sum()) / 1e9:.2f} GB algorithmic")),
+        solver=("int8-split GEMM on tcgen05 (kind::i8, six signed 8-bit digit planes per operand, the 26 digit pairs of weight >= 2^-64) "
+                "behind an explicit L^-1") if ozaki else "fp64 DMMA triangular solve",
         roofline_chol=dict(bound="tensor", kernel="chol_diag/panel/update chain", achieved=chol_flops / (chol_ms / 1e3) / 1e12,
                            peak=fp64_peak, unit="TFLOP/s", frac=chol_flops / (chol_ms / 1e3) / 1e12 / fp64_peak, ms=chol_ms,
                            note=f"sum n_t^3 / 3 = {chol_flops:.4g} flops over the whole factorisation chain (latency-bound dependent launches)"),
@@ -607,15 +605,59 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
     ach = work["gram_ops"] / (gram_ms / 1e3) / 1e12
     rg = dict(bound="tensor", kernel="gram_seg_kernel<%s>" % ("kind::mxf4" if is_fp4 else "kind::i8"), achieved=ach,
               peak=gram_peak or rate * pk["bf16_tflops"], unit="TOP/s",
-              frac=ach / (gram_peak or rate * pk["bf16_tflops"]), ms=gram_ms,
+              frac=ach / (gram_peak or rate * pk["bf16_tflops"]), ms=gram_ms, share_of_step=gram_ms / serial_ms,
               frac_vs_bf16_burst_x=ach / (rate * pk["bf16_tflops"]), frac_vs_bf16_sustained_x=ach / (rate * pk["bf16_tflops_sustained"]),
               frac_vs_int8_spec_4500=ach / 4500.0, ncu_tensor_pipe_pct=NCU["gram"].get("tensor_pipe_pct"), ncu_file=NCU["gram"].get("file"),
               traffic=NCU["gram"].get("dram_bytes"),
               note=(f"algorithmic ops 2 N (n_u n_t + n_t (n_t + 1) / 2) summed over windows = {work['gram_ops']:.4g} per launch; peak = "
                     f"{'tensor-pipe probe of this instruction kind measured on this box now (gb_probe_peak)' if gram_peak else str(rate) + ' x burst bf16 of MEASURED_PEAKS.json (probe failed)'}; "
-                    f"frac_vs_bf16_*_x = against {rate:g} x the bf16 figures of {pk['source']}"))
+                    f"frac_vs_bf16_*_x = against {rate:g} x the bf16 figures of {pk['source']}; traffic = dram bytes per launch "
+                    f"({NCU['gram'].get('file')}) vs {work['panel_bytes'] / (2 if is_fp4 else 1) / 1e9:.2f} GB of operand rows"))
     out["roofline_gram"] = rg
-    out["solve"] = dict(flops_per_step=work["solve_flops"], tflops=work["solve_flops"] / ((chol_ms + trsm_ms) / 1e3) / 1e12)
+    if ozaki:
+        # the solve as it runs now: explicit L^-1 (stage 21) + digit-plane GEMM (stage 3); the GEMM's own work is the 26 digit-pair
+        # products over the triangular K range of L^-1
+        n_pairs = 26
+        gemm_ops = float(2 * n_pairs * (nus * nts * (nts + 1) / 2)[okw].sum())
+        i8_peak = probes.get("i8") or 2.0 * pk["bf16_tflops"]
+        out["roofline_solve"] = dict(
+            bound="tensor", kernel="ozaki_solve_kernel (+ oz_slice_x_kernel)", achieved=gemm_ops / (trsm_ms / 1e3) / 1e12, peak=i8_peak,
+            unit="TOP/s", frac=gemm_ops / (trsm_ms / 1e3) / 1e12 / i8_peak, ms=trsm_ms, share_of_step=trsm_ms / serial_ms,
+            fp64_equivalent_tflops=trsm_flops / (trsm_ms / 1e3) / 1e12, fp64_probe_tflops=fp64_peak,
+            ncu_tensor_pipe_pct=NCU.get("ozaki", {}).get("tensor_pipe_pct"), traffic=NCU.get("ozaki", {}).get("dram_bytes"),
+            ncu_file=NCU.get("ozaki", {}).get("file"),
+            note=(f"int8 ops of the GEMM itself: 2 x {n_pairs} digit pairs x sum n_u n_t (n_t + 1) / 2 = {gemm_ops:.4g} per launch against the "
+                  f"kind::i8 pipe probe of this box; the stage time also holds the slicing of L^-1 into digit planes.  "
+                  f"fp64_equivalent_tflops = the solve's algorithmic fp64 flops ({trsm_flops:.4g}, what the DMMA triangular solve spent "
+                  f"at 0.67 of the fp64 probe) over the same time: the reason this path exists"))
+        linv_flops = chol_flops   # n_t^3 / 3 per window: the triangular solve against the identity with the zero blocks skipped
+        out["roofline_linv"] = dict(bound="tensor", kernel="trsm_finalize_kernel<64> (tri: L^-1, y = L^-1 z)", achieved=linv_flops / (trtri_ms / 1e3) / 1e12,
+                                    peak=fp64_peak, unit="TFLOP/s", frac=linv_flops / (trtri_ms / 1e3) / 1e12 / fp64_peak, ms=trtri_ms,
+                                    note=f"sum n_t^3 / 3 = {linv_flops:.4g} flops; a sequential block chain per 64-column CTA: latency-bound, "
+                                         "runs beside the B21 Gram tiles with the factorisation")
+        b21 = float((nts * nus)[okw].sum())
+        b11 = float((nts * (nts + 1) / 2)[okw].sum())
+        fin_bytes = b21 * (8 + 6) + b11 * 16
+        if is_fp4:
+          out["roofline_finish"] = dict(bound="hbm", kernel="gram_finalize_kernel", achieved=fin_bytes / (fin_ms / 1e3) / 1e9, peak=pk["hbm_gbs"],
+                                        unit="GB/s", frac=fin_bytes / (fin_ms / 1e3) / 1e9 / pk["hbm_gbs"], ms=fin_ms,
+                                        traffic=NCU.get("finish", {}).get("dram_bytes"), ncu_file=NCU.get("finish", {}).get("file"),
+                                        note=f"B21: 8 B read + 6 digit-plane bytes written per entry ({b21:.4g} entries), B11: 8 + 8 B per lower-triangle "
+                                             f"entry ({b11:.4g}); 21 DFMA + the digit split per entry keep it issue-bound, not HBM-bound (ncu: "
+                                             f"{NCU.get('finish', {}).get('issue_active_pct')} % issue slots, {NCU.get('finish', {}).get('dram_pct')} % DRAM)")
+        out["roofline"] = dict(rg)
+        out["roofline"]["note"] = "longest kernel of the step (event-timed alone on all SMs); " + rg["note"]
+        out["solve"] = dict(flops_per_step=work["solve_flops"], ms=chol_ms + trtri_ms + trsm_ms,
+                            tflops=work["solve_flops"] / ((chol_ms + trtri_ms + trsm_ms) / 1e3) / 1e12,
+                            note="Cholesky + explicit L^-1 + int8-split GEMM; algorithmic fp64 flops of the reference's formulation over their time")
+    else:
+        out["roofline"] = dict(bound="tensor", kernel="trsm_finalize_kernel", achieved=trsm_flops / (trsm_ms / 1e3) / 1e12, peak=fp64_peak,
+                               unit="TFLOP/s", frac=trsm_flops / (trsm_ms / 1e3) / 1e12 / fp64_peak,
+                               traffic=NCU["trsm"].get("dram_bytes"), ms=trsm_ms, share_of_step=trsm_ms / serial_ms,
+                               note=(f"longest kernel of the step ({tag} batch, event-timed alone); algorithmic flops sum(n_t^2 n_u + n_t^2 + "
+                                     f"4 n_t n_u) = {trsm_flops:.4g} per launch (no Cholesky term); pipe = fp64 tensor core (DMMA m8n8k4); peak = "
+                                     f"{fp64_src}; traffic = dram bytes per launch from {NCU['trsm'].get('file')} vs {8 * float((nts * nts + nts * nus)[okw].sum()) / 1e9:.2f} GB algorithmic"))
+        out["solve"] = dict(flops_per_step=work["solve_flops"], ms=chol_ms + trsm_ms, tflops=work["solve_flops"] / ((chol_ms + trsm_ms) / 1e3) / 1e12)
     out["dtype"] = ("e2m1 x e2m1 -> f32 (exact integer counts, tcgen05 kind::mxf4)" if is_fp4 else "int8 x int8 -> int32 (tcgen05 kind::i8)") + " + f64 fold/solve"
     if not with_e2e:
         batch.close()
@@ -932,7 +974,8 @@ def run_gpu(args):
             full = env.world == 1 and not args.quick
             c22 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=full and not args.no_e2e, collective=False)
             line["dtype"] = c22["dtype"]
-            for k in ("roofline", "roofline_gram", "roofline_chol", "roofline_expand5", "stage_ms", "stage_ms_serial", "solve"):
+            for k in ("roofline", "roofline_gram", "roofline_solve", "roofline_linv", "roofline_finish", "roofline_chol", "roofline_expand5",
+                      "stage_ms", "stage_ms_serial", "solve", "solver"):
                 line[k] = c22[k]
             line["chr22"] = dict(value=c22["value"], ms_per_step=c22["ms_per_step"], imputed_per_step=c22["n_imputed"],
                                  gpu_launches=c22["launches"], config=chr22_config(),
@@ -949,8 +992,8 @@ def run_gpu(args):
         n_all, = env.reduce([c22["n_imputed"]], "SUM")
         line.update(value=n_all / (tot_ms / 1e3), ms_per_step=tot_ms, scaling="weak", dtype=c22["dtype"], config=chr22_config(),
                     gpu_launches=c22["launches"], clocks=c22["clocks"], imputed_per_step=c22["n_imputed"], host_affinity=env.numa)
-        for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings", "pack", "roofline", "roofline_gram", "roofline_chol",
-                  "roofline_expand5", "stage_ms", "stage_ms_serial", "solve"):
+        for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings", "pack", "roofline", "roofline_gram", "roofline_solve", "roofline_linv",
+                  "roofline_finish", "roofline_chol", "roofline_expand5", "stage_ms", "stage_ms_serial", "solve", "solver"):
             if k in c22:
                 line[k] = c22[k]
     elif workload in ("ld5000", "dist1kg"):

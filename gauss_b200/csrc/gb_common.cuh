@@ -57,6 +57,7 @@ struct GramParams {
   int raw_out;           // 1: store the raw weighted Gram sum; gram_finalize_kernel finishes it (E2M1, mixture)
   int mirror;            // 1: also store the transposed entry (full symmetric matrix, computeLD)
   int wide_fold;         // int8 mixture fold: 1 = m*sumxy - sumx*sumy may not fit int32, form it exactly in fp64
+  int feed_test;         // diagnostics only (GB_GRAM_FEEDTEST): 1 = every tile loads rows 0.. (an L2-hot, fully shared feed), results meaningless
   long long* dbg;        // diagnostics only (GB_GRAM_TRACE): per-CTA stall counters, 8 per CTA; nullptr in production
   Seg seg[P_MAX];
   double coef[P_MAX];    // w_p * (m_p / (m_p - 1))          (util.cpp:117-118)

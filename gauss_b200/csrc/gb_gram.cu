@@ -37,7 +37,7 @@ namespace {
 
 constexpr int TILE = 128;
 constexpr int STAGES_FUSED = 4;   // smem pipeline depth when the row-statistics tables share shared memory
-constexpr int STAGES_RAW = 6;     // ... and when they do not (E2M1 panels: finish pass in gram_finalize_kernel)
+constexpr int STAGES_RAW = 7;     // ... and when they do not (E2M1 panels: finish pass in gram_finalize_kernel)
 constexpr int MAX_STAGES = STAGES_RAW;
 constexpr int STAGE_OPERAND_BYTES = TILE * K_BLOCK;  // 16 KiB
 constexpr int STAGE_BYTES = 2 * STAGE_OPERAND_BYTES; // A + B
@@ -225,7 +225,9 @@ gram_seg_kernel(const __grid_constant__ CUtensorMap tm_a_panel,
         tile_id[seq & (TILE_RING - 1)] = ct;
         ptx::mbar_arrive(&tile_bar[seq & (TILE_RING - 1)]);   // release: the id is visible to whoever sees the phase flip
         if (ct < 0) break;
-        const int2 rows = *reinterpret_cast<const int2*>(&prm.tiles[ct].a_row0);   // a_row0, b_row0
+        int2 rows = *reinterpret_cast<const int2*>(&prm.tiles[ct].a_row0);   // a_row0, b_row0
+        if (prm.feed_test == 1) rows = make_int2(0, 128);
+        if (prm.feed_test == 2) rows = make_int2((int)blockIdx.x * 256, (int)blockIdx.x * 256 + 128);
         const int2 srcs = *reinterpret_cast<const int2*>(&prm.tiles[ct].a_src);    // a_src, b_src
         const CUtensorMap* map_a = srcs.x ? &tm_a_scratch : &tm_a_panel;
         const CUtensorMap* map_b = srcs.y ? &tm_b_scratch : &tm_b_panel;
@@ -940,6 +942,7 @@ int launch_gram(Ctx* ctx, const RowMaps& panel, const RowMaps& scratch, const Gr
     // reference's).  Largest population first: its long MMA chain covers the epilogue's store phase of the
     // previous tile; then big and small ones alternate so the epilogue catches up behind every long chain.
     GramParams q = prm;
+    if (const char* e = getenv("GB_GRAM_FEEDTEST")) q.feed_test = atoi(e);   // diagnostics: timing only
     int idx[P_MAX];
     for (int i = 0; i < prm.n_seg; i++) idx[i] = i;
     std::sort(idx, idx + prm.n_seg, [&](int a, int b) { return prm.seg[a].natoms > prm.seg[b].natoms; });
