@@ -325,7 +325,7 @@ int batch_plan_host(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, co
   if (b->ozaki) {
     b->oz_kpad = (b->max_nt + 127) / 128 * 128;
     b->h_oz_wins.resize(b->h_wins.size() * ozaki_win_bytes());
-    ozaki_plan(b->h_wins.data(), (int)b->h_wins.size(), b->oz_kpad, ctx->sm_count, b->h_oz_wins.data(), &b->h_oz_tiles, &b->oz_a_rows, &b->oz_b_rows);
+    ozaki_plan(b->h_wins.data(), (int)b->h_wins.size(), b->oz_kpad, ctx->heavy_sms > 0 ? ctx->heavy_sms : ctx->sm_count, b->h_oz_wins.data(), &b->h_oz_tiles, &b->oz_a_rows, &b->oz_b_rows);
     b->oz_n_tiles = (int)(b->h_oz_tiles.size() / ozaki_tile_bytes());
     // B21 tiles learn where their rows sit in the digit planes (a tile belongs to the window whose B21 block it writes)
     for (GramTile& t : b->h_tiles) {
@@ -612,6 +612,7 @@ gb_batch* batch_new(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const doubl
   b->counts_mode = counts_mode;
   if (params) b->params = *params;
   else gb_params_default(&b->params);
+  if (getenv("GB_NO_CERT")) b->params.check_pd = 0;   // diagnostics (timing only): no certificate windows in the factorisation launches
   b->n_windows = n_windows;
   b->defer_flag_check = defer_flag_check;
   return b;
@@ -1135,6 +1136,23 @@ int gb_batch_run(gb_batch* b) {
   if ((rc = run_gram_range(b, n_tt, n_all - n_tt, 0, nullptr, false, true))) return rc;
   return run_stage(b, 3);
 }
+
+}  // extern "C"
+
+namespace gb {
+int batch_run_front(gb_batch* b, int max_ctas) {
+  int rc = run_stage(b, 0);
+  if (rc || b->counts_mode) return rc;
+  return run_gram_range(b, 0, b->n_tiles_tt, max_ctas);
+}
+int batch_run_chain(gb_batch* b) { return run_stage(b, 2); }
+int batch_run_b21(gb_batch* b, int max_ctas) {
+  return run_gram_range(b, b->n_tiles_tt, (int)b->h_tiles.size() - b->n_tiles_tt, max_ctas);
+}
+int batch_run_solve(gb_batch* b) { return run_stage(b, 3); }
+}  // namespace gb
+
+extern "C" {
 
 int gb_batch_run_stage(gb_batch* b, int stage) {
   if (!b) return GB_ERR_BAD_ARG;

@@ -107,6 +107,11 @@ gb_batch* batch_new(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const doubl
                     bool ld_mode, bool counts_mode, bool defer_flag_check, double ld_diag);
 void batch_free_device(gb_batch* b);
 int batch_fetch_enqueue(gb_batch* b, double* z_u, double* info_u, int* status_staging);
+// The pieces of gb_batch_run for a caller that pipelines batches itself (gb_genome.cu): all on ctx->stream as set by the caller.
+int batch_run_front(gb_batch* b, int max_ctas);   // row statistics + the B11 Gram tiles (finished)
+int batch_run_chain(gb_batch* b);                 // factorisation (+ explicit L^-1 for the int8-split solve): needs B11 only
+int batch_run_b21(gb_batch* b, int max_ctas);     // the B21 Gram tiles (finished)
+int batch_run_solve(gb_batch* b);                 // needs all of the above
 int batch_fetch_finish(gb_batch* b, const int* st, double* z_u, double* info_u, int* window_status_out);
 // The same, followed by the slow path for windows the certificate could not vouch for (GB_ERR_NOT_PD) or whose
 // factorisation broke down: B11 is rebuilt, eigendecomposed and clipped on the device like the reference's MakePosDef

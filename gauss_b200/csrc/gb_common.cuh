@@ -103,6 +103,8 @@ struct Ctx {
   void* fn_encode_tiled = nullptr;  // cuTensorMapEncodeTiled via cudaGetDriverEntryPoint
   int panel_format = GB_PANEL_E2M1; // format gb_panel_create uses (GB_PANEL_FORMAT=int8|e2m1 overrides)
   int e2m1_mxf4 = 1;                // E2M1 panels: 1 = kind::mxf4 (packed nibbles, K = 64), 0 = kind::f8f6f4 (GB_GRAM_KIND)
+  int heavy_sms = 0;                // > 0: CTAs the persistent kernels of the int8-split solve may use (the genome driver keeps the
+                                    // rest of the SMs for the factorisation chain of the next batch); 0 = sm_count
   int solve_ozaki = 1;              // 1: the solve's n_t^2 n_u term runs as an int8-split GEMM on tcgen05 (GB_SOLVE=fp64 opts out)
 };
 

@@ -131,6 +131,7 @@ struct Shard {
   gb_panel* panels[2] = {nullptr, nullptr};   // working panels of the ternary batches
   Arena arenas[2];
   cudaStream_t cs[2] = {nullptr, nullptr}, sides[2] = {nullptr, nullptr}, copy = nullptr;
+  cudaEvent_t ev_lane[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};   // pipelined run: B11 done / chain done, per arena slot
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_tmp = nullptr;
   double* h_z = nullptr;                  // pinned staging [n_u of the shard]
   double* h_info = nullptr;
@@ -171,6 +172,8 @@ struct gb_genome {
   int n_parts = 1, first_part = 0;
   int64_t batch_windows = 48;
   int n_streams = 2;
+  int chain_sms = 32;          // > 0: batches are software-pipelined over one heavy lane and one factorisation lane that keeps this
+                               // many SMs (GB_GENOME_CHAIN_SMS; 0: every batch forks its own factorisation, two batches alternate)
   int resident_mode = 0;       // 0 auto, 1 pack5, 2 e2m1
   double expanded_gb = -1.0;   // >= 0: cap on the bytes spent on keeping batches expanded (GB_GENOME_EXPANDED_GB)
   uint64_t synth_seed = 0;
@@ -276,7 +279,7 @@ int shard_free(gb_genome* g, Shard* sh) {
   }
   if (sh->copy) cudaStreamDestroy(sh->copy);
   sh->copy = nullptr;
-  for (cudaEvent_t* e : {&sh->ev_start, &sh->ev_end, &sh->ev_tmp})
+  for (cudaEvent_t* e : {&sh->ev_start, &sh->ev_end, &sh->ev_tmp, &sh->ev_lane[0], &sh->ev_lane[1], &sh->ev_chain[0], &sh->ev_chain[1]})
     if (*e) {
       cudaEventDestroy(*e);
       *e = nullptr;
@@ -356,14 +359,21 @@ int shard_plan(gb_genome* g, Shard* sh) {
     return GB_ERR_UNSUPPORTED;
   }
   // 3. streams, events
+  int prio_lo = 0, prio_hi = 0;
+  SH_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (int i = 0; i < 2; i++) {
     SH_CUDA(cudaStreamCreateWithFlags(&sh->cs[i], cudaStreamNonBlocking));
-    SH_CUDA(cudaStreamCreateWithFlags(&sh->sides[i], cudaStreamNonBlocking));
+    // the factorisation lanes: many small dependent launches, scheduled ahead of the heavy lane's CTAs wherever an SM frees up
+    SH_CUDA(cudaStreamCreateWithPriority(&sh->sides[i], cudaStreamNonBlocking, prio_hi));
   }
   SH_CUDA(cudaStreamCreateWithFlags(&sh->copy, cudaStreamNonBlocking));
   SH_CUDA(cudaEventCreate(&sh->ev_start));
   SH_CUDA(cudaEventCreate(&sh->ev_end));
   SH_CUDA(cudaEventCreateWithFlags(&sh->ev_tmp, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    SH_CUDA(cudaEventCreateWithFlags(&sh->ev_lane[i], cudaEventDisableTiming));
+    SH_CUDA(cudaEventCreateWithFlags(&sh->ev_chain[i], cudaEventDisableTiming));
+  }
   const int n_slots = g->n_streams;
   // 4. residency per batch.  Workspace need of a batch from its window sizes (what batch_arena_bytes will report):
   size_t arena_est = 0;
@@ -621,6 +631,59 @@ int shard_run(gb_genome* g, Shard* sh) {
   SH_CUDA(cudaEventRecord(ev_t0, sh->cs[0]));
   for (int i = 1; i < n_slots; i++) SH_CUDA(cudaStreamWaitEvent(sh->cs[i], ev_t0, 0));
   int rc = GB_OK;
+  if (ctx->heavy_sms > 0 && n_slots == 2) {
+    // Software pipeline over two lanes.  The heavy lane (one stream: the Gram kernels, their finish passes, the solve GEMM;
+    // its persistent kernels take heavy_sms CTAs, one per SM) runs   P_0 Q_0 | P_1 S_0 Q_1 | P_2 S_1 Q_2 | ...
+    // (P = row statistics + B11 tiles, Q = B21 tiles, S = solve) and the factorisation lane (the other stream, high
+    // priority, on the SMs the heavy lane leaves) runs the Cholesky + L^-1 chain of batch i between P_i and S_i: a
+    // latency-bound chain of ~60 small launches gets a whole heavy period to finish instead of stalling its own batch.
+    // Batches alternate between the two arenas; stream order on the heavy lane (S_{i-1} before P_{i+1}) keeps them apart.
+    cudaStream_t H = sh->cs[0], Cs = sh->sides[0];
+    const int heavy = ctx->heavy_sms;
+    // diagnostics (timing only, results meaningless): which lane sets the period?
+    const char* skip_env = getenv("GB_GENOME_SKIP");
+    const bool skip_chain = skip_env && !strcmp(skip_env, "chain"), skip_heavy = skip_env && !strcmp(skip_env, "heavy");
+    Segment* prev = nullptr;
+    for (Segment& s : sh->segs) {
+      SH_CUDA(cudaStreamWaitEvent(H, s.landed, 0));
+      ctx->stream = H;
+      if (!s.expanded) {
+        gb_panel* panel = sh->panels[s.slot];
+        for (const RowRange& x : s.ranges) {
+          const int64_t pos = map_row(sh->res_t[(size_t)s.chrom], x.lo);
+          rc = launch_expand5(ctx, panel, sh->d_rows5 + (size_t)pos * (size_t)g->row5, g->row5, x.res, x.hi - x.lo);
+          if (rc) break;
+        }
+      }
+      if (!rc) rc = batch_run_front(s.batch, heavy);
+      if (rc) break;
+      SH_CUDA(cudaEventRecord(sh->ev_lane[s.slot], H));
+      SH_CUDA(cudaStreamWaitEvent(Cs, sh->ev_lane[s.slot], 0));
+      ctx->stream = Cs;
+      if (!skip_chain) rc = batch_run_chain(s.batch);
+      ctx->stream = H;
+      if (rc) break;
+      SH_CUDA(cudaEventRecord(sh->ev_chain[s.slot], Cs));
+      if (prev) {
+        SH_CUDA(cudaStreamWaitEvent(H, sh->ev_chain[prev->slot], 0));
+        if (!skip_heavy) rc = batch_run_solve(prev->batch);
+        if (!rc) rc = batch_fetch_enqueue(prev->batch, sh->h_z + prev->stage_off, sh->h_info + prev->stage_off, sh->h_status + prev->status_off);
+        if (rc) break;
+      }
+      if (!skip_heavy) rc = batch_run_b21(s.batch, heavy);
+      if (rc) break;
+      prev = &s;
+    }
+    if (!rc && prev) {
+      SH_CUDA(cudaStreamWaitEvent(H, sh->ev_chain[prev->slot], 0));
+      rc = batch_run_solve(prev->batch);
+      if (!rc) rc = batch_fetch_enqueue(prev->batch, sh->h_z + prev->stage_off, sh->h_info + prev->stage_off, sh->h_status + prev->status_off);
+    }
+    if (!rc) {   // the timing join below looks at cs[0] only; the factorisation lane has been joined by the last solve
+      SH_CUDA(cudaEventRecord(sh->ev_tmp, Cs));
+      SH_CUDA(cudaStreamWaitEvent(H, sh->ev_tmp, 0));
+    }
+  } else
   for (Segment& s : sh->segs) {
     cudaStream_t cs = sh->cs[s.slot];
     SH_CUDA(cudaStreamWaitEvent(cs, s.landed, 0));   // the rows this batch touches are resident (a completed event costs nothing)
@@ -788,6 +851,8 @@ int gb_genome_create(int n_gpus, const int* devices, int n_pops, const int* pop_
   }
   if (const char* e = getenv("GB_GENOME_BATCH_WINDOWS")) g->batch_windows = std::max(1, atoi(e));
   if (const char* e = getenv("GB_GENOME_STREAMS")) g->n_streams = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("GB_GENOME_CHAIN_SMS")) g->chain_sms = std::max(0, atoi(e));
+  if (g->n_streams < 2) g->chain_sms = 0;
   if (const char* e = getenv("GB_GENOME_EXPANDED_GB")) g->expanded_gb = atof(e);
   if (const char* e = getenv("GB_GENOME_RESIDENT")) g->resident_mode = !strcmp(e, "pack5") ? 1 : !strcmp(e, "e2m1") ? 2 : 0;
   for (int i = 0; i < n_gpus; i++) {
@@ -796,6 +861,7 @@ int gb_genome_create(int n_gpus, const int* devices, int n_pops, const int* pop_
     g->shards.push_back(sh);
     g->devices.push_back(devices ? devices[i] : i);
     int rc = gb_ctx_create(g->devices.back(), &sh->ctx);
+    if (!rc && g->chain_sms > 0 && sh->ctx->sm_count > 2 * g->chain_sms) sh->ctx->heavy_sms = sh->ctx->sm_count - g->chain_sms;
     if (rc) {
       g->err = gb_last_error(nullptr);
       for (Shard* s : g->shards) {

@@ -11,7 +11,7 @@
 // weight groups (s + t >= 4: 26 of the 36 pairs) are recombined in fp64 (2^(8 (s + t) - 92 + e_X) each).  Quantisation
 // (2^-46 of the scale per entry) and the dropped groups (< 2^-52 of a product term) leave |dz| ~ 2e-12 on a 750-SNP
 // window (simulated against extended precision): the 1e-6 bar with five orders to spare and tighter than the fp64 path's
-// own distance to the LU oracle.  (Seven 7-bit digits with 28 pairs, the first version, measured 4.6e-11 and cost a
+// own distance to the LU-based CPU restatement.  (Seven 7-bit digits with 28 pairs, the first version, measured 4.6e-11 and cost a
 // plane and two pairs more; s + t >= 5, 21 pairs, gives 7.5e-11.)  Balanced base-256 digits need no carry chain: with
 // BIAS = sum_p 128 256^p the bytes of (q + BIAS) ^ 0x80..80 ARE the digits.  L^-1 is lower triangular, so the K range of
 // the 128-row tile J of X ends at 128 (J + 1).
@@ -487,7 +487,7 @@ int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const
     GB_CUDA(cudaFuncSetAttribute(ozaki_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_ALLOC));
     attr_set_dev[ctx->device & 63] = true;
   }
-  const int n_ctas = std::min(n_tiles, ctx->sm_count);   // ozaki_plan dealt the slots to this many CTAs
+  const int n_ctas = std::min(n_tiles, ctx->heavy_sms > 0 ? ctx->heavy_sms : ctx->sm_count);   // ozaki_plan dealt the slots to this many CTAs
   ozaki_solve_kernel<<<(unsigned)n_ctas, OZ_THREADS, OZ_SMEM_ALLOC, ctx->stream>>>(
       tm_a, tm_b, static_cast<const OzWin*>(d_ow), static_cast<const OzTile*>(d_tiles), n_tiles, d_ex, d_y, d_nan, d_zu, d_info);
   mark();

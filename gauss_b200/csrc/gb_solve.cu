@@ -872,6 +872,7 @@ int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_n
   // chromosome driver's quarter batches): the longest CTA then sets the kernel's duration, and it is half as long
   const long long ctas128 = (long long)((max_nu + UB - 1) / UB) * n_wins;
   bool narrow = ctas128 < 3LL * ctx->sm_count;     // 2 CTAs per SM: below 1.5 waves
+  if (tri) narrow = true;   // L^-1 runs in the latency-bound factorisation lane: shorter CTAs, and the zero-block skipping is finer
   if (const char* e = getenv("GB_TRSM_NARROW")) narrow = atoi(e) != 0;   // tuning knob
   const int ub = narrow ? 64 : UB;
   const size_t smem = tr_smem_bytes(ub) + sizeof(double) * (size_t)(nb_max * NB + 5 * NB);
