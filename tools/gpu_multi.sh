@@ -4,7 +4,7 @@ set -u
 NG=${NG:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8; head -2 /proc/meminfo; nproc
-echo skip tests
+echo "== multi-GPU tests"; timeout -s KILL 600 python -m pytest tests/test_genome.py -m gpu -x -q 2>&1 | tail -3
 echo "== single-process bench, $NG GPUs"
 timeout -s KILL 400 python bench.py --gpus $NG --single-process --steps 3 --warmup 1 --quick --no-cpu-baseline > gpurun_out/bench_sp${NG}.json 2> gpurun_out/bench_sp${NG}.err; echo rc=$?; tail -3 gpurun_out/bench_sp${NG}.err
 echo "== torchrun bench, $NG ranks"
