@@ -156,8 +156,17 @@ def test_genome_equals_oracle_and_is_placement_independent(gpu_ctx, oracle):
     z6, i6, _, _, inf6, _ = run_genome(chroms, env=hyb)
     assert 0 < inf6[0]["expanded_pct"] < 100
     z7, i7, *_ = run_genome(chroms, host_rows=host, env=hyb)
+    # (e) both schedules: the two-lane software pipeline (default) against per-batch forks on two alternating streams,
+    # and the fp64 triangular solve within its distance of the int8-split one
+    z8, i8, *_ = run_genome(chroms, env={"GB_GENOME_CHAIN_SMS": "0", "GB_GENOME_BATCH_WINDOWS": "2"})
+    z9, i9, *_ = run_genome(chroms, env={"GB_GENOME_CHAIN_SMS": "48", "GB_GENOME_BATCH_WINDOWS": "2"})
+    zf, jf, *_ = run_genome(chroms, env={"GB_SOLVE": "fp64"})
     for ci in range(len(chroms)):
-        for other_z, other_i in ((z2, i2), (z3, i3), (z4, i4), (z5, i5), (z6, i6), (z7, i7)):
+        ok = ~np.isnan(z1[ci])
+        assert np.array_equal(np.isnan(zf[ci]), ~ok)
+        assert np.abs(zf[ci][ok] - z1[ci][ok]).max() <= 1e-10 and np.abs(jf[ci][ok] - i1[ci][ok]).max() <= 1e-10
+    for ci in range(len(chroms)):
+        for other_z, other_i in ((z2, i2), (z3, i3), (z4, i4), (z5, i5), (z6, i6), (z7, i7), (z8, i8), (z9, i9)):
             assert np.array_equal(z1[ci], other_z[ci], equal_nan=True)
             assert np.array_equal(i1[ci], other_i[ci], equal_nan=True)
 
