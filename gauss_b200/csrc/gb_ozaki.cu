@@ -275,6 +275,279 @@ ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   }
 }
 
+// ---- version 2: the A planes of a K block stay in shared memory across the digit pairs ----------------------------
+// Version 1 above streams a fresh [A plane | X plane] pair of tiles (32 KB) for every 128 x 128 x 128 MMA block, and the
+// L2 -> SM path, not the tensor pipe, sets its time (imma pipe 70 %, L2 79 %).  Here a work unit is (window, 128 unmeasured
+// SNPs, 64 rows of X): for one K block the six A-plane tiles (16 KB each) and the six X-plane tiles (64 rows: 8 KB each)
+// feed all 26 digit pairs -- 144 KB for 13 MMA-block equivalents instead of 416 KB -- because the seven weight groups
+// now accumulate at the same time: seven 64-column TMEM accumulators (+ one spare of the 512 columns).
+//   producer: two FIFO rings (8 A slots, 8 X slots); order per K block  A0 X5 A1..A5 X4..X0
+//   MMA     : bursts t = 5..0 over the X planes, inner s (A planes) ascending; A_s is released after its last burst
+//             (s = 0 after t = 4, ... s = 4, 5 after t = 0: the order they were loaded in), X_t after its burst
+//   groups  : weight 10 - gi; in the last K block gi = 0, 1, 2, 3, 4, 6, 5 complete in that order, and the next unit
+//             first needs gi = 5, 4, 3, 2, 1, 0, 6: it takes the spare and then the slots in their order of completion,
+//             so the epilogue drains an accumulator while the MMAs of the next unit already run in another
+// MEASURED (chr22 batch, same results bit for bit): 1.23 ms against 1.07 ms for version 1 -- a loss, kept as the record
+// (GB_OZ_KERNEL=2).  With N = 64 a tcgen05.mma reads 128 A rows from shared memory for half the work: 6 KB per 32-clock
+// instruction is 192 B/clk against the ~128 B/clk shared memory delivers, so the pipe is paced by operand READS at ~48 clk
+// per instruction (1.5x), and one thread has to issue an MMA every 32 clocks (the first version of the loop, with modulo
+// slot arithmetic, ran 1.65 ms).  The seven groups cannot be live at N = 128 (896 of 512 TMEM columns).
+constexpr int V2_NX = 64;                 // X rows per unit = MMA N
+constexpr int V2_A_SLOTS = 8, V2_A_BYTES = OZ_TILE * 128;    // powers of two: the issuing thread's slot arithmetic is masks
+constexpr int V2_B_SLOTS = 8, V2_B_BYTES = V2_NX * 128;
+constexpr int V2_ACC = 8;                 // 64-column accumulators
+constexpr int V2_OFF_AFULL = 0, V2_OFF_AEMPTY = V2_OFF_AFULL + 8 * V2_A_SLOTS, V2_OFF_BFULL = V2_OFF_AEMPTY + 8 * V2_A_SLOTS;
+constexpr int V2_OFF_BEMPTY = V2_OFF_BFULL + 8 * V2_B_SLOTS, V2_OFF_TFULL = V2_OFF_BEMPTY + 8 * V2_B_SLOTS;
+constexpr int V2_OFF_TEMPTY = V2_OFF_TFULL + 8 * V2_ACC, V2_OFF_TMEM_PTR = V2_OFF_TEMPTY + 8 * V2_ACC;
+constexpr int V2_OFF_RED = 512;           // double [2][128]
+constexpr int V2_OFF_Y = V2_OFF_RED + 2 * 128 * 8;   // double [2][64]
+constexpr int V2_OFF_A = 4096;
+constexpr int V2_OFF_B = V2_OFF_A + V2_A_SLOTS * V2_A_BYTES;
+constexpr int V2_SMEM_ALLOC = V2_OFF_B + V2_B_SLOTS * V2_B_BYTES + 1024;
+static_assert(V2_OFF_TMEM_PTR + 8 <= V2_OFF_RED && V2_OFF_Y + 2 * 64 * 8 <= V2_OFF_A, "v2 header layout");
+static_assert(V2_SMEM_ALLOC <= 232448, "shared memory budget exceeded");
+static_assert(NDIG == 6 && GMIN == 4, "the burst schedule below is written for six planes and s + t >= 4");
+
+// accumulator slots of the seven groups, 4 bits each (bits 28..31: the spare)
+__device__ __forceinline__ uint32_t v2_rotate(uint32_t m) {
+  auto get = [&](int i) { return (m >> (4 * i)) & 15u; };
+  // need order gi = 5, 4, 3, 2, 1, 0, 6  <-  spare, old[0], old[1], old[2], old[3], old[4], old[6]; new spare = old[5]
+  return (get(4) << 0) | (get(3) << 4) | (get(2) << 8) | (get(1) << 12) | (get(0) << 16) | (get(7) << 20) | (get(6) << 24) |
+         (get(5) << 28);
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_solve_kernel_v2(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                      const OzWin* __restrict__ wins, const OzTile* __restrict__ tiles, int n_tiles,
+                      const int* __restrict__ ex, const double* __restrict__ y, const uint8_t* __restrict__ nanflag,
+                      double* __restrict__ zu, double* __restrict__ info) {
+  extern __shared__ uint8_t oz_smem_raw[];
+  uint8_t* smem = oz_smem_raw + ((1024u - (ptx::smem_u32(oz_smem_raw) & 1023u)) & 1023u);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + V2_OFF_AFULL);
+  uint64_t* a_empty = reinterpret_cast<uint64_t*>(smem + V2_OFF_AEMPTY);
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + V2_OFF_BFULL);
+  uint64_t* b_empty = reinterpret_cast<uint64_t*>(smem + V2_OFF_BEMPTY);
+  uint64_t* tfull = reinterpret_cast<uint64_t*>(smem + V2_OFF_TFULL);
+  uint64_t* tempty = reinterpret_cast<uint64_t*>(smem + V2_OFF_TEMPTY);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + V2_OFF_TMEM_PTR);
+  double* red = reinterpret_cast<double*>(smem + V2_OFF_RED);
+  double* ys = reinterpret_cast<double*>(smem + V2_OFF_Y);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_b);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int i = 0; i < V2_A_SLOTS; i++) {
+      ptx::mbar_init(&a_full[i], 1);
+      ptx::mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < V2_B_SLOTS; i++) {
+      ptx::mbar_init(&b_full[i], 1);
+      ptx::mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < V2_ACC; i++) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], OZ_EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t SLOTS0 = 0x76543210u;   // group gi -> slot gi, spare 7
+
+  if (warp < 4) {   // (no setmaxnreg here: 384 threads x 168 registers fit, and the unrolled issue loop wants more than 56)
+    if (warp == 0) {
+      // ===================================================================== TMA producer
+      if (ptx::elect_one()) {
+        uint32_t a_cnt = 0, b_cnt = 0;
+        for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
+          const OzTile t = tiles[ct];
+          if (t.win < 0) continue;
+          const OzWin w = wins[t.win];
+          const int a_row = (int)(w.a_row0 + (long long)t.ut * OZ_TILE);
+          const int nbh = (w.n_t + V2_NX - 1) / V2_NX;
+          for (int jh = 0; jh < nbh; jh++) {
+            const int b_row = (int)(w.b_row0 + (long long)jh * V2_NX);
+            const int n_kb = jh / 2 + 1;
+            for (int kb = 0; kb < n_kb; kb++) {
+              auto load_a = [&](int s) {
+                const uint32_t slot = a_cnt & (V2_A_SLOTS - 1), par = (a_cnt / V2_A_SLOTS) & 1u;
+                ptx::mbar_wait(&a_empty[slot], par ^ 1);
+                ptx::mbar_arrive_expect_tx(&a_full[slot], V2_A_BYTES);
+                ptx::tma_load_2d(smem + V2_OFF_A + slot * V2_A_BYTES, &tm_a, &a_full[slot], kb * 128, a_row + s * w.ra);
+                a_cnt++;
+              };
+              auto load_b = [&](int tt) {
+                const uint32_t slot = b_cnt & (V2_B_SLOTS - 1), par = (b_cnt / V2_B_SLOTS) & 1u;
+                ptx::mbar_wait(&b_empty[slot], par ^ 1);
+                ptx::mbar_arrive_expect_tx(&b_full[slot], V2_B_BYTES);
+                ptx::tma_load_2d(smem + V2_OFF_B + slot * V2_B_BYTES, &tm_b, &b_full[slot], kb * 128, b_row + tt * w.rb);
+                b_cnt++;
+              };
+              load_a(0);
+              load_b(5);
+              for (int s = 1; s < NDIG; s++) load_a(s);
+              for (int tt = 4; tt >= 0; tt--) load_b(tt);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================================================================== MMA issuer
+      if (ptx::elect_one()) {
+        const uint32_t idesc = ptx::make_idesc_i8(OZ_TILE, V2_NX);
+        const uint64_t desc_a0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + V2_OFF_A));
+        const uint64_t desc_b0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + V2_OFF_B));
+        uint32_t a_cnt = 0, b_cnt = 0, slots = SLOTS0, acc_par = 0;   // acc_par bit = parity of the slot's CURRENT use
+        bool first = true;
+        for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
+          if (tiles[ct].win < 0) continue;
+          const OzWin w = wins[tiles[ct].win];
+          const int nbh = (w.n_t + V2_NX - 1) / V2_NX;
+          for (int jh = 0; jh < nbh; jh++) {
+            if (!first) slots = v2_rotate(slots);
+            first = false;
+            const int n_kb = jh / 2 + 1;
+            uint32_t started = 0;
+            for (int kb = 0; kb < n_kb; kb++) {
+              const bool last_kb = kb == n_kb - 1;
+              // the 26 pairs, fully unrolled: group, release and completion points are compile-time constants, the
+              // single issuing thread is left with masks and shifts (its instruction stream paces the small N = 64 MMAs)
+#pragma unroll
+              for (int tt = NDIG - 1; tt >= 0; tt--) {
+                const uint32_t bslot = b_cnt & (V2_B_SLOTS - 1), bpar = (b_cnt / V2_B_SLOTS) & 1u;
+                ptx::mbar_wait(&b_full[bslot], bpar);
+                ptx::tc_fence_after();
+                const uint64_t db = desc_b0 + (uint64_t)(bslot * (V2_B_BYTES >> 4));
+#pragma unroll
+                for (int s = (GMIN - tt > 0 ? GMIN - tt : 0); s < NDIG; s++) {
+                  const uint32_t ai = a_cnt + (uint32_t)s, aslot = ai & (V2_A_SLOTS - 1), apar = (ai / V2_A_SLOTS) & 1u;
+                  if (tt == NDIG - 1) {   // first use of this plane's tile in this K block
+                    ptx::mbar_wait(&a_full[aslot], apar);
+                    ptx::tc_fence_after();
+                  }
+                  const int gi = 2 * (NDIG - 1) - (s + tt);
+                  const uint32_t slot = (slots >> (4 * gi)) & 15u;
+                  const uint32_t acc = (started >> gi) & 1u;
+                  if (!acc) {             // first MMA of the group in this unit: the slot's previous owner must be drained
+                    ptx::mbar_wait(&tempty[slot], ((acc_par >> slot) & 1u) ^ 1u);
+                    ptx::tc_fence_after();
+                    started |= 1u << gi;
+                  }
+                  const uint32_t d_tmem = tmem_base + slot * V2_NX;
+                  const uint64_t da = desc_a0 + (uint64_t)(aslot * (V2_A_BYTES >> 4));
+                  ptx::mma_i8_ss(d_tmem, da, db, idesc, acc);
+                  ptx::mma_i8_ss(d_tmem, da + 2, db + 2, idesc, 1);
+                  ptx::mma_i8_ss(d_tmem, da + 4, db + 4, idesc, 1);
+                  ptx::mma_i8_ss(d_tmem, da + 6, db + 6, idesc, 1);
+                  if (tt == (GMIN - s > 0 ? GMIN - s : 0)) ptx::mma_commit(&a_empty[aslot]);   // last burst that uses plane s
+                  if (last_kb && tt == (s + tt - (NDIG - 1) > 0 ? s + tt - (NDIG - 1) : 0)) {    // the group's last pair
+                    ptx::mma_commit(&tfull[slot]);
+                    acc_par ^= 1u << slot;
+                  }
+                }
+                ptx::mma_commit(&b_empty[bslot]);
+                b_cnt++;
+              }
+              a_cnt += NDIG;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;          // row of the tile = unmeasured SNP
+    const int half = ew >> 2;                // which 32 of the unit's 64 X rows this thread owns
+    const int etid = threadIdx.x - 128;
+    uint32_t slots = SLOTS0, full_par = 0;
+    bool first = true;
+    int unit = 0;
+    for (int ct = blockIdx.x; ct < n_tiles; ct += gridDim.x) {
+      const OzTile t = tiles[ct];
+      if (t.win < 0) continue;
+      const OzWin w = wins[t.win];
+      const int e_x = ex[t.win];
+      const int nbh = (w.n_t + V2_NX - 1) / V2_NX;
+      double p_info = 0.0, p_z = 0.0;
+      for (int jh = 0; jh < nbh; jh++, unit++) {
+        if (!first) slots = v2_rotate(slots);
+        first = false;
+        double* yb = ys + (unit & 1) * V2_NX;
+        if (etid < V2_NX) {
+          const int k = jh * V2_NX + etid;
+          yb[etid] = k < w.n_t ? y[w.off_t + k] : 0.0;
+        }
+        oz_epi_bar_sync();   // (the readers of this buffer two units ago passed the previous unit's barrier)
+        double a[32];
+#pragma unroll
+        for (int e = 0; e < 32; e++) a[e] = 0.0;
+#pragma unroll 1
+        for (int idx = 0; idx < NG; idx++) {
+          const int gi = idx == 5 ? 6 : idx == 6 ? 5 : idx;       // order of completion
+          const int gw = 2 * (NDIG - 1) - gi;
+          const double sc = __hiloint2double((1023 + DBITS * gw - 2 * QBITS + e_x) << 20, 0);   // 2^(8 g' - 2 QBITS + e_X)
+          const uint32_t slot = (slots >> (4 * gi)) & 15u;
+          ptx::mbar_wait(&tfull[slot], (full_par >> slot) & 1u);
+          full_par ^= 1u << slot;
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + slot * V2_NX + ((uint32_t)(quad * 32) << 16) + half * 32;
+          uint32_t v0[16], v1[16];
+          ptx::tmem_ld_32x32b_x16(taddr, v0);
+          ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[slot]);
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            a[e] = fma(sc, oz_int_to_double((int)v0[e]), a[e]);
+            a[16 + e] = fma(sc, oz_int_to_double((int)v1[e]), a[16 + e]);
+          }
+        }
+        const double* yj = yb + half * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          p_info = fma(a[e], a[e], p_info);
+          p_z = fma(a[e], yj[e], p_z);
+        }
+      }
+      // the two halves of a row, in a fixed order
+      oz_epi_bar_sync();   // the previous tile's readers of red are done
+      if (half == 1) {
+        red[r] = p_info;
+        red[128 + r] = p_z;
+      }
+      oz_epi_bar_sync();
+      if (half == 0) {
+        const int u = t.ut * OZ_TILE + r;
+        if (u < w.n_u) {
+          const double s_info = p_info + red[r], s_z = p_z + red[128 + r];
+          const double inf = nanflag[w.off_u + u] ? __longlong_as_double(0x7ff8000000000000ll) : fabs(s_info);   // info = |b21 B11^-1 b12|  (dist.cpp:198)
+          zu[w.off_u + u] = s_z / sqrt(inf);           // z / sqrt(info)               (dist.cpp:200)
+          info[w.off_u + u] = inf;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---- operand preparation -------------------------------------------------------------------------------------------
 __global__ void oz_exponent_kernel(const unsigned long long* __restrict__ amax, int n, int* ex) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,6 +644,12 @@ __global__ void oz_identity_kernel(const SolveWin* __restrict__ wins, double* X)
 int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_rows, int64_t k_elems,
                         int64_t k_stride_bytes, int format, int box_rows);
 
+// GB_OZ_KERNEL=2 selects the all-groups-live kernel (measured slower: see its header); default = the streaming kernel
+static bool oz_use_v2() {
+  static const bool v2 = [] { const char* e = getenv("GB_OZ_KERNEL"); return e && atoi(e) == 2; }();
+  return v2;
+}
+
 size_t ozaki_win_bytes() { return sizeof(OzWin); }
 size_t ozaki_tile_bytes() { return sizeof(OzTile); }
 
@@ -413,7 +692,12 @@ void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, int n_ctas, void* ow
     load.pop();
     per_cta[(size_t)c].push_back(t);
     rounds = std::max(rounds, per_cta[(size_t)c].size());
-    load.push({l + (long long)ow[t.win].nbt * (ow[t.win].nbt + 1) / 2, c});
+    long long cost = (long long)ow[t.win].nbt * (ow[t.win].nbt + 1) / 2;
+    if (oz_use_v2()) {   // 64-row blocks of X, block jh sweeps jh / 2 + 1 K blocks
+      cost = 0;
+      for (long long jh = 0; jh < (ow[t.win].n_t + 63) / 64; jh++) cost += jh / 2 + 1;
+    }
+    load.push({l + cost, c});
   }
   std::vector<OzTile> slots(rounds * (size_t)n_ctas, OzTile{-1, 0});
   for (int c = 0; c < n_ctas; c++)
@@ -478,18 +762,24 @@ int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const
   mark();
   GB_CUDA(cudaGetLastError());
   ctx->launches += 3;
+  const bool v1 = !oz_use_v2();
   CUtensorMap tm_a, tm_b;
   int rc;
   if ((rc = make_row_tensor_map(ctx, &tm_a, d_planes_a, a_rows, kpad, kpad, MAP_INT8, OZ_TILE))) return rc;
-  if ((rc = make_row_tensor_map(ctx, &tm_b, d_planes_b, b_rows, kpad, kpad, MAP_INT8, OZ_TILE))) return rc;
+  if ((rc = make_row_tensor_map(ctx, &tm_b, d_planes_b, b_rows, kpad, kpad, MAP_INT8, v1 ? OZ_TILE : V2_NX))) return rc;
   static bool attr_set_dev[64] = {};
   if (!attr_set_dev[ctx->device & 63]) {
     GB_CUDA(cudaFuncSetAttribute(ozaki_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_ALLOC));
+    GB_CUDA(cudaFuncSetAttribute(ozaki_solve_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_ALLOC));
     attr_set_dev[ctx->device & 63] = true;
   }
   const int n_ctas = std::min(n_tiles, ctx->heavy_sms > 0 ? ctx->heavy_sms : ctx->sm_count);   // ozaki_plan dealt the slots to this many CTAs
-  ozaki_solve_kernel<<<(unsigned)n_ctas, OZ_THREADS, OZ_SMEM_ALLOC, ctx->stream>>>(
-      tm_a, tm_b, static_cast<const OzWin*>(d_ow), static_cast<const OzTile*>(d_tiles), n_tiles, d_ex, d_y, d_nan, d_zu, d_info);
+  if (v1)
+    ozaki_solve_kernel<<<(unsigned)n_ctas, OZ_THREADS, OZ_SMEM_ALLOC, ctx->stream>>>(
+        tm_a, tm_b, static_cast<const OzWin*>(d_ow), static_cast<const OzTile*>(d_tiles), n_tiles, d_ex, d_y, d_nan, d_zu, d_info);
+  else
+    ozaki_solve_kernel_v2<<<(unsigned)n_ctas, OZ_THREADS, V2_SMEM_ALLOC, ctx->stream>>>(
+        tm_a, tm_b, static_cast<const OzWin*>(d_ow), static_cast<const OzTile*>(d_tiles), n_tiles, d_ex, d_y, d_nan, d_zu, d_info);
   mark();
   GB_CUDA(cudaGetLastError());
   ctx->launches++;
