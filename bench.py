@@ -574,10 +574,14 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
     z, info = z.copy(), info.copy()
     n_ok = int((status == 0).sum())
     # ---- the same K steps stage by stage (serialised, every kernel on all SMs)
-    # row statistics | Gram tensor-core kernel | Gram finish pass | Cholesky | explicit L^-1 (int8-split solve only) | solve
-    STAGES = [0, 10, 11, 20, 21, 3]
+    # row statistics | Gram tensor-core kernel | Gram finish pass | factorisation chain (Cholesky with the rows of L^-1
+    # growing beside its steps on an auxiliary stream: int8-split solve only) | solve
+    STAGES = [0, 10, 11, 2, 3]
     st = stage_times(env, batch, stream, args.steps, STAGES)
-    gram_ms, fin_ms, chol_ms, trtri_ms, trsm_ms = (float(st[:, i].mean()) for i in (1, 2, 3, 4, 5))
+    gram_ms, fin_ms, chain_ms, trsm_ms = (float(st[:, i].mean()) for i in (1, 2, 3, 4))
+    # ... and the two halves of the chain alone, one after the other (what each costs without the overlap)
+    st2 = stage_times(env, batch, stream, args.steps, [20, 21])
+    chol_ms, trtri_ms = float(st2[:, 0].mean()), float(st2[:, 1].mean())
     ozaki = os.environ.get("GB_SOLVE", "ozaki") != "fp64"
     nts = np.array([len(x["measured"]) for x in windows], float)
     nus = np.array([len(x["unmeasured"]) for x in windows], float)
@@ -592,7 +596,10 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
         value=n_imputed * args.steps / (total_ms / 1e3), ms_per_step=total_ms / args.steps, launches=int(launches), clocks=clocks,
         n_imputed=n_imputed, windows_ok=n_ok, panel_gen_s=gen_s, work=work, z=z, info=info, status=status,
         stage_ms_serial=serial_ms,
-        stage_ms=dict(row_stats=float(st[:, 0].mean()), gram=gram_ms, gram_finish=fin_ms, cholesky=chol_ms, linv=trtri_ms, solve=trsm_ms),
+        stage_ms=dict(row_stats=float(st[:, 0].mean()), gram=gram_ms, gram_finish=fin_ms, factorisation_chain=chain_ms, solve=trsm_ms),
+        stage_ms_alone=dict(cholesky=chol_ms, linv=trtri_ms,
+                            note="the chain's halves run one after the other: in the step the rows of L^-1 are formed on an auxiliary stream "
+                                 "while the factorisation takes its next steps, so factorisation_chain < cholesky + linv"),
         solver=("int8-split GEMM on tcgen05 (kind::i8, six signed 8-bit digit planes per operand, the 26 digit pairs of weight >= 2^-64) "
                 "behind an explicit L^-1") if ozaki else "fp64 DMMA triangular solve",
         roofline_chol=dict(bound="tensor", kernel="chol_diag/panel/update chain", achieved=chol_flops / (chol_ms / 1e3) / 1e12,
@@ -631,10 +638,13 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
                   f"fp64_equivalent_tflops = the solve's algorithmic fp64 flops ({trsm_flops:.4g}, what the DMMA triangular solve spent "
                   f"at 0.67 of the fp64 probe) over the same time: the reason this path exists"))
         linv_flops = chol_flops   # n_t^3 / 3 per window: the triangular solve against the identity with the zero blocks skipped
-        out["roofline_linv"] = dict(bound="tensor", kernel="trsm_finalize_kernel<64> (tri: L^-1, y = L^-1 z)", achieved=linv_flops / (trtri_ms / 1e3) / 1e12,
+        out["roofline_linv"] = dict(bound="tensor", kernel="linv_row_kernel (X = L^-1 row block by row block, y = L^-1 z)",
+                                    achieved=linv_flops / (trtri_ms / 1e3) / 1e12,
                                     peak=fp64_peak, unit="TFLOP/s", frac=linv_flops / (trtri_ms / 1e3) / 1e12 / fp64_peak, ms=trtri_ms,
-                                    note=f"sum n_t^3 / 3 = {linv_flops:.4g} flops; a sequential block chain per 64-column CTA: latency-bound, "
-                                         "runs beside the B21 Gram tiles with the factorisation")
+                                    ms_added_to_the_chain=chain_ms - chol_ms,
+                                    note=f"sum n_t^3 / 3 = {linv_flops:.4g} flops; timed alone (one launch per 64-row block, each waiting for the "
+                                         "previous: latency-bound); inside the step the launches ride beside the factorisation's own "
+                                         "steps and add ms_added_to_the_chain")
         b21 = float((nts * nus)[okw].sum())
         b11 = float((nts * (nts + 1) / 2)[okw].sum())
         fin_bytes = b21 * (8 + 6) + b11 * 16
@@ -647,9 +657,9 @@ def bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e, fmt=None, ta
                                              f"{NCU.get('finish', {}).get('issue_active_pct')} % issue slots, {NCU.get('finish', {}).get('dram_pct')} % DRAM)")
         out["roofline"] = dict(rg)
         out["roofline"]["note"] = "longest kernel of the step (event-timed alone on all SMs); " + rg["note"]
-        out["solve"] = dict(flops_per_step=work["solve_flops"], ms=chol_ms + trtri_ms + trsm_ms,
-                            tflops=work["solve_flops"] / ((chol_ms + trtri_ms + trsm_ms) / 1e3) / 1e12,
-                            note="Cholesky + explicit L^-1 + int8-split GEMM; algorithmic fp64 flops of the reference's formulation over their time")
+        out["solve"] = dict(flops_per_step=work["solve_flops"], ms=chain_ms + trsm_ms,
+                            tflops=work["solve_flops"] / ((chain_ms + trsm_ms) / 1e3) / 1e12,
+                            note="factorisation chain (Cholesky + explicit L^-1) + int8-split GEMM; algorithmic fp64 flops of the reference's formulation over their time")
     else:
         out["roofline"] = dict(bound="tensor", kernel="trsm_finalize_kernel", achieved=trsm_flops / (trsm_ms / 1e3) / 1e12, peak=fp64_peak,
                                unit="TFLOP/s", frac=trsm_flops / (trsm_ms / 1e3) / 1e12 / fp64_peak,
@@ -975,7 +985,7 @@ def run_gpu(args):
             c22 = bench_chr22(env, args, ctx, stream, sizes, w, probes, with_e2e=full and not args.no_e2e, collective=False)
             line["dtype"] = c22["dtype"]
             for k in ("roofline", "roofline_gram", "roofline_solve", "roofline_linv", "roofline_finish", "roofline_chol", "roofline_expand5",
-                      "stage_ms", "stage_ms_serial", "solve", "solver"):
+                      "stage_ms", "stage_ms_alone", "stage_ms_serial", "solve", "solver"):
                 line[k] = c22[k]
             line["chr22"] = dict(value=c22["value"], ms_per_step=c22["ms_per_step"], imputed_per_step=c22["n_imputed"],
                                  gpu_launches=c22["launches"], config=chr22_config(),
@@ -993,7 +1003,7 @@ def run_gpu(args):
         line.update(value=n_all / (tot_ms / 1e3), ms_per_step=tot_ms, scaling="weak", dtype=c22["dtype"], config=chr22_config(),
                     gpu_launches=c22["launches"], clocks=c22["clocks"], imputed_per_step=c22["n_imputed"], host_affinity=env.numa)
         for k in ("e2e", "e2e_cold", "e2e_per_window", "e2e_strings", "pack", "roofline", "roofline_gram", "roofline_solve", "roofline_linv",
-                  "roofline_finish", "roofline_chol", "roofline_expand5", "stage_ms", "stage_ms_serial", "solve", "solver"):
+                  "roofline_finish", "roofline_chol", "roofline_expand5", "stage_ms", "stage_ms_alone", "stage_ms_serial", "solve", "solver"):
             if k in c22:
                 line[k] = c22[k]
     elif workload in ("ld5000", "dist1kg"):

@@ -686,22 +686,22 @@ int run_stage_impl(gb_batch* b, int stage) {
           return rc;
         skip = b->d_skip;
       }
-      if ((rc = launch_cholesky(ctx, b->d_wins, b->n_chol_wins, b->max_nt, b->d_tt, b->d_dinv, b->d_status, skip))) return rc;
-      if (stage == 20) return GB_OK;   // profiling: the factorisation alone
-    }
-    // fall through
-    case 21: {
-      if (b->ld_mode || b->counts_mode) return GB_OK;
-      if (b->ozaki && !b->d_y) {
-        // int8-split solve: X = L^-1 by the blocked trsm kernel on identity columns (zero blocks skipped; it also leaves
-        // y = L^-1 z_t).  It needs L only, so it rides with the factorisation (beside the B21 Gram tiles in gb_batch_run)
-        const int nw = (int)b->h_wins.size();
-        if ((rc = launch_ozaki_prepare_identity(ctx, b->d_wins_x, nw, b->d_x))) return rc;
-        GB_CUDA(cudaMemsetAsync(b->d_oz_amax, 0, sizeof(unsigned long long) * (size_t)nw, ctx->stream));
-        return launch_trsm_finalize(ctx, b->d_wins_x, nw, b->max_nt, b->max_nt, b->d_tt, b->d_dinv, b->d_x, b->d_zt,
-                                    b->d_oz_scr, b->d_oz_scr + b->n_t_total, b->d_oz_y, /*tri=*/1, b->d_oz_amax);
-      }
+      // int8-split solve: X = L^-1 and y = L^-1 z_t grow row block by row block on an auxiliary stream while the
+      // factorisation takes its own steps (linv_row_kernel); stage 20 (profiling) factors only, stage 21 inverts only
+      const bool with_linv = stage == 2 && b->ozaki && !b->d_y;
+      LinvArgs la{b->d_wins, nreal, b->d_tt, b->d_dinv, b->d_x, b->d_zt, b->d_oz_y, b->d_oz_amax};
+      if (with_linv) GB_CUDA(cudaMemsetAsync(b->d_oz_amax, 0, sizeof(unsigned long long) * (size_t)nreal, ctx->stream));
+      if ((rc = launch_cholesky(ctx, b->d_wins, b->n_chol_wins, b->max_nt, b->d_tt, b->d_dinv, b->d_status, skip,
+                                with_linv ? &la : nullptr)))
+        return rc;
       return GB_OK;
+    }
+    case 21: {   // profiling: the explicit inverse alone, after stage 20
+      if (b->ld_mode || b->counts_mode || !(b->ozaki && !b->d_y)) return GB_OK;
+      const int nw = (int)b->h_wins.size();
+      LinvArgs la{b->d_wins, nw, b->d_tt, b->d_dinv, b->d_x, b->d_zt, b->d_oz_y, b->d_oz_amax};
+      GB_CUDA(cudaMemsetAsync(b->d_oz_amax, 0, sizeof(unsigned long long) * (size_t)nw, ctx->stream));
+      return launch_linv_rows(ctx, la, b->max_nt);
     }
     case 3:
       if (b->ld_mode || b->counts_mode) return GB_OK;
@@ -838,6 +838,8 @@ void gb_ctx_destroy(gb_ctx* ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
   for (int i = 0; i < 2; i++) {
     if (ctx->chrom_streams[i]) cudaStreamDestroy(ctx->chrom_streams[i]);
     if (ctx->chrom_sides[i]) cudaStreamDestroy(ctx->chrom_sides[i]);

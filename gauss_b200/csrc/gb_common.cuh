@@ -92,6 +92,8 @@ struct Ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t side_stream = nullptr;   // lazily created: the factorisation beside the B21 Gram tiles (gb_batch_run)
+  cudaStream_t aux_stream = nullptr;    // lazily created: the rows of L^-1 beside the factorisation's own steps (launch_cholesky)
+  cudaEvent_t ev_aux = nullptr;
   int seg_order = 2;                    // processing order of the populations in the regrouped Gram fold (GB_SEG_ORDER)
   int chol_sms = 64;                    // SMs the B21 Gram launch leaves to it (GB_CHOL_SMS; 0 = run the stages one after another)
   cudaStream_t chrom_sides[2] = {nullptr, nullptr};     // ... and the side stream each of them forks its factorisation onto
@@ -179,8 +181,20 @@ struct SolveWin {        // per-window solve descriptor
   int flags;             // bit 0: publish inv(L_kk) (real factorisation; clear for the PD-certificate copy)
   int pad;
 };
+// X = L^-1 row block by row block (int8-split solve): buffers of the REAL windows (no certificate copies)
+struct LinvArgs {
+  const SolveWin* d_wins;
+  int n_real;
+  const double* d_tt;
+  const double* d_dinv;
+  double* d_x;
+  const double* d_zt;
+  double* d_y;
+  unsigned long long* d_amax;
+};
 int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, double* d_tt, double* d_dinv,
-                    int* d_status, const int* d_skip);
+                    int* d_status, const int* d_skip, const LinvArgs* linv = nullptr);
+int launch_linv_rows(Ctx* ctx, const LinvArgs& a, int max_nt);
 int launch_pd_bound(Ctx* ctx, const SolveWin* d_wins, int n_real, const double* d_rq_t, double lambda,
                     double gneg, double min_abs_eig, int* d_skip);
 int launch_trsm_finalize(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, int max_nu, const double* d_tt,

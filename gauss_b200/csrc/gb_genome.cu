@@ -128,10 +128,10 @@ struct Shard {
   uint8_t* d_rows5 = nullptr;             // ternary residency: [rows_t][row5]
   int64_t* d_sites = nullptr;             // synthetic fill: site index per needed row (indexed like `resident`)
   gb_panel* big = nullptr;                // expanded residency: [rows_e] operand rows
-  gb_panel* panels[2] = {nullptr, nullptr};   // working panels of the ternary batches
-  Arena arenas[2];
+  gb_panel* panels[4] = {nullptr, nullptr, nullptr, nullptr};   // working panels of the ternary batches
+  Arena arenas[4];
   cudaStream_t cs[2] = {nullptr, nullptr}, sides[2] = {nullptr, nullptr}, copy = nullptr;
-  cudaEvent_t ev_lane[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};   // pipelined run: B11 done / chain done, per arena slot
+  cudaEvent_t ev_lane[4] = {nullptr, nullptr, nullptr, nullptr}, ev_chain[4] = {nullptr, nullptr, nullptr, nullptr};   // pipelined run: B11 done / chain done, per arena slot
   cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_tmp = nullptr;
   double* h_z = nullptr;                  // pinned staging [n_u of the shard]
   double* h_info = nullptr;
@@ -172,6 +172,7 @@ struct gb_genome {
   int n_parts = 1, first_part = 0;
   int64_t batch_windows = 48;
   int n_streams = 2;
+  int lane_depth = 1;          // pipelined run: the solve of a batch is issued this many batches behind its front (GB_GENOME_LANE_DEPTH, 1..3)
   int chain_sms = 32;          // > 0: batches are software-pipelined over one heavy lane and one factorisation lane that keeps this
                                // many SMs (GB_GENOME_CHAIN_SMS; 0: every batch forks its own factorisation, two batches alternate)
   int resident_mode = 0;       // 0 auto, 1 pack5, 2 e2m1
@@ -255,12 +256,14 @@ int shard_free(gb_genome* g, Shard* sh) {
   cudaStreamSynchronize(sh->ctx->stream);
   if (sh->big) gb_panel_destroy(sh->big);
   sh->big = nullptr;
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 4; i++) {
     if (sh->panels[i]) gb_panel_destroy(sh->panels[i]);
     if (sh->arenas[i].base) cudaFree(sh->arenas[i].base);
-    if (sh->d_chunk[i]) cudaFree(sh->d_chunk[i]);
     sh->panels[i] = nullptr;
     sh->arenas[i] = Arena{};
+  }
+  for (int i = 0; i < 2; i++) {
+    if (sh->d_chunk[i]) cudaFree(sh->d_chunk[i]);
     sh->d_chunk[i] = nullptr;
   }
   if (sh->d_rows5) cudaFree(sh->d_rows5);
@@ -279,7 +282,8 @@ int shard_free(gb_genome* g, Shard* sh) {
   }
   if (sh->copy) cudaStreamDestroy(sh->copy);
   sh->copy = nullptr;
-  for (cudaEvent_t* e : {&sh->ev_start, &sh->ev_end, &sh->ev_tmp, &sh->ev_lane[0], &sh->ev_lane[1], &sh->ev_chain[0], &sh->ev_chain[1]})
+  for (cudaEvent_t* e : {&sh->ev_start, &sh->ev_end, &sh->ev_tmp, &sh->ev_lane[0], &sh->ev_lane[1], &sh->ev_lane[2], &sh->ev_lane[3],
+                         &sh->ev_chain[0], &sh->ev_chain[1], &sh->ev_chain[2], &sh->ev_chain[3]})
     if (*e) {
       cudaEventDestroy(*e);
       *e = nullptr;
@@ -288,6 +292,11 @@ int shard_free(gb_genome* g, Shard* sh) {
 }
 
 // ---- plan: segments, residency, working panels, arenas, batches (runs on the shard's own thread) --------------------
+// arenas / working panels a shard rotates its batches over: D + 1 in the pipelined run, else one per compute stream
+static int slots_of(const gb_genome* g, const Shard* sh) {
+  return (sh->ctx->heavy_sms > 0 && g->n_streams == 2) ? g->lane_depth + 1 : g->n_streams;
+}
+
 int shard_plan(gb_genome* g, Shard* sh) {
   Ctx* ctx = sh->ctx;
   SH_CUDA(cudaSetDevice(ctx->device));
@@ -370,11 +379,11 @@ int shard_plan(gb_genome* g, Shard* sh) {
   SH_CUDA(cudaEventCreate(&sh->ev_start));
   SH_CUDA(cudaEventCreate(&sh->ev_end));
   SH_CUDA(cudaEventCreateWithFlags(&sh->ev_tmp, cudaEventDisableTiming));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 4; i++) {
     SH_CUDA(cudaEventCreateWithFlags(&sh->ev_lane[i], cudaEventDisableTiming));
     SH_CUDA(cudaEventCreateWithFlags(&sh->ev_chain[i], cudaEventDisableTiming));
   }
-  const int n_slots = g->n_streams;
+  const int n_slots = slots_of(g, sh);
   // 4. residency per batch.  Workspace need of a batch from its window sizes (what batch_arena_bytes will report):
   size_t arena_est = 0;
   for (const Segment& s : sh->segs) {
@@ -623,28 +632,37 @@ int shard_rows(gb_genome* g, Shard* sh, bool synthetic) {
 int shard_run(gb_genome* g, Shard* sh) {
   Ctx* ctx = sh->ctx;
   SH_CUDA(cudaSetDevice(ctx->device));
-  const int n_slots = g->n_streams;
+  const int n_slots = slots_of(g, sh);
   cudaStream_t main_stream = ctx->stream, main_side = ctx->side_stream;
   cudaEvent_t ev_t0, ev_t1;
   SH_CUDA(cudaEventCreate(&ev_t0));
   SH_CUDA(cudaEventCreate(&ev_t1));
   SH_CUDA(cudaEventRecord(ev_t0, sh->cs[0]));
-  for (int i = 1; i < n_slots; i++) SH_CUDA(cudaStreamWaitEvent(sh->cs[i], ev_t0, 0));
+  for (int i = 1; i < 2; i++) SH_CUDA(cudaStreamWaitEvent(sh->cs[i], ev_t0, 0));
   int rc = GB_OK;
-  if (ctx->heavy_sms > 0 && n_slots == 2) {
+  if (ctx->heavy_sms > 0 && g->n_streams == 2) {
     // Software pipeline over two lanes.  The heavy lane (one stream: the Gram kernels, their finish passes, the solve GEMM;
-    // its persistent kernels take heavy_sms CTAs, one per SM) runs   P_0 Q_0 | P_1 S_0 Q_1 | P_2 S_1 Q_2 | ...
-    // (P = row statistics + B11 tiles, Q = B21 tiles, S = solve) and the factorisation lane (the other stream, high
-    // priority, on the SMs the heavy lane leaves) runs the Cholesky + L^-1 chain of batch i between P_i and S_i: a
-    // latency-bound chain of ~60 small launches gets a whole heavy period to finish instead of stalling its own batch.
-    // Batches alternate between the two arenas; stream order on the heavy lane (S_{i-1} before P_{i+1}) keeps them apart.
+    // its persistent kernels take heavy_sms CTAs, one per SM) runs, with a lag of D = lane_depth batches,
+    //   P_0 Q_0 | P_1 Q_1 | P_2 S_0 Q_2 | P_3 S_1 Q_3 | ...        (P = row statistics + B11 tiles, Q = B21 tiles, S = solve)
+    // and the factorisation lane (the other stream, high priority, on the SMs the heavy lane leaves) runs the Cholesky +
+    // L^-1 chain of batch i between P_i and S_i: ~100 small dependent launches whose latency is set by the largest window
+    // of the batch get D heavy periods to finish (with D = 1 the solve waited ~1 ms per batch for them).
+    // Batches rotate over D + 1 arenas; stream order on the heavy lane (S_{i-D} before P_{i+1}) keeps them apart.
     cudaStream_t H = sh->cs[0], Cs = sh->sides[0];
     const int heavy = ctx->heavy_sms;
+    const size_t lag = (size_t)(n_slots - 1);
     // diagnostics (timing only, results meaningless): which lane sets the period?
     const char* skip_env = getenv("GB_GENOME_SKIP");
     const bool skip_chain = skip_env && !strcmp(skip_env, "chain"), skip_heavy = skip_env && !strcmp(skip_env, "heavy");
-    Segment* prev = nullptr;
-    for (Segment& s : sh->segs) {
+    auto solve_of = [&](Segment& p) -> int {
+      SH_CUDA(cudaStreamWaitEvent(H, sh->ev_chain[p.slot], 0));
+      int r = skip_heavy ? GB_OK : batch_run_solve(p.batch);
+      if (!r) r = batch_fetch_enqueue(p.batch, sh->h_z + p.stage_off, sh->h_info + p.stage_off, sh->h_status + p.status_off);
+      return r;
+    };
+    size_t next_solve = 0;
+    for (size_t si = 0; si < sh->segs.size() && !rc; si++) {
+      Segment& s = sh->segs[si];
       SH_CUDA(cudaStreamWaitEvent(H, s.landed, 0));
       ctx->stream = H;
       if (!s.expanded) {
@@ -664,21 +682,14 @@ int shard_run(gb_genome* g, Shard* sh) {
       ctx->stream = H;
       if (rc) break;
       SH_CUDA(cudaEventRecord(sh->ev_chain[s.slot], Cs));
-      if (prev) {
-        SH_CUDA(cudaStreamWaitEvent(H, sh->ev_chain[prev->slot], 0));
-        if (!skip_heavy) rc = batch_run_solve(prev->batch);
-        if (!rc) rc = batch_fetch_enqueue(prev->batch, sh->h_z + prev->stage_off, sh->h_info + prev->stage_off, sh->h_status + prev->status_off);
+      if (si >= lag) {
+        rc = solve_of(sh->segs[next_solve++]);
         if (rc) break;
       }
       if (!skip_heavy) rc = batch_run_b21(s.batch, heavy);
-      if (rc) break;
-      prev = &s;
     }
-    if (!rc && prev) {
-      SH_CUDA(cudaStreamWaitEvent(H, sh->ev_chain[prev->slot], 0));
-      rc = batch_run_solve(prev->batch);
-      if (!rc) rc = batch_fetch_enqueue(prev->batch, sh->h_z + prev->stage_off, sh->h_info + prev->stage_off, sh->h_status + prev->status_off);
-    }
+    ctx->stream = H;
+    while (!rc && next_solve < sh->segs.size()) rc = solve_of(sh->segs[next_solve++]);
     if (!rc) {   // the timing join below looks at cs[0] only; the factorisation lane has been joined by the last solve
       SH_CUDA(cudaEventRecord(sh->ev_tmp, Cs));
       SH_CUDA(cudaStreamWaitEvent(H, sh->ev_tmp, 0));
@@ -705,12 +716,12 @@ int shard_run(gb_genome* g, Shard* sh) {
   ctx->side_stream = main_side;
   if (rc) {
     sh->err = ctx->err;
-    for (int i = 0; i < n_slots; i++) cudaStreamSynchronize(sh->cs[i]);
+    for (int i = 0; i < 2; i++) cudaStreamSynchronize(sh->cs[i]);
     cudaEventDestroy(ev_t0);
     cudaEventDestroy(ev_t1);
     return rc;
   }
-  for (int i = 1; i < n_slots; i++) {
+  for (int i = 1; i < 2; i++) {
     SH_CUDA(cudaEventRecord(sh->ev_tmp, sh->cs[i]));
     SH_CUDA(cudaStreamWaitEvent(sh->cs[0], sh->ev_tmp, 0));
   }
@@ -853,6 +864,7 @@ int gb_genome_create(int n_gpus, const int* devices, int n_pops, const int* pop_
   if (const char* e = getenv("GB_GENOME_STREAMS")) g->n_streams = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("GB_GENOME_CHAIN_SMS")) g->chain_sms = std::max(0, atoi(e));
   if (g->n_streams < 2) g->chain_sms = 0;
+  if (const char* e = getenv("GB_GENOME_LANE_DEPTH")) g->lane_depth = std::min(3, std::max(1, atoi(e)));
   if (const char* e = getenv("GB_GENOME_EXPANDED_GB")) g->expanded_gb = atof(e);
   if (const char* e = getenv("GB_GENOME_RESIDENT")) g->resident_mode = !strcmp(e, "pack5") ? 1 : !strcmp(e, "e2m1") ? 2 : 0;
   for (int i = 0; i < n_gpus; i++) {

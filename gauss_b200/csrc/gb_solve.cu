@@ -627,6 +627,120 @@ trsm_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row block j of X = L^-1 (the right operand of the int8-split solve), launched right after diagonal block j has been
+// factored, on a stream of its own, so that the explicit inverse grows in the shadow of the factorisation's own steps:
+//   X_jj = inv(L_jj)  (published by the factorisation as dinv),
+//   X_ji = -inv(L_jj) sum_{k=i}^{j-1} L_jk X_ki   (i < j),         y_j = inv(L_jj) (z_j - sum_{k<j} L_jk y_k).
+// Row j of L is final once step j - 1 has run; rows < j of X come from the earlier launches of this kernel.  One CTA
+// per 64 x 64 tile: grid (j + 1, windows); CTA i < j forms X_ji, CTA j copies X_jj and solves the y block.  X is
+// row-major n_t x ld_t like B11's buffer; blocks above the diagonal are never written (nothing reads them).  Compared
+// with the block-sequential triangular solve on identity columns (one long CTA per 64 columns) this is nb^2 / 2 short
+// uniform CTAs per window: a quarter of the SM-time, and no latency of its own.
+__global__ void __launch_bounds__(256)
+linv_row_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt, const double* __restrict__ dinv, double* xmat,
+                const double* __restrict__ zt, double* y, unsigned long long* amax, int j) {
+  const SolveWin w = wins[blockIdx.y];
+  const int n = w.n_t;
+  const int i = blockIdx.x;
+  if (j >= win_nb(n) || i > j) return;
+  const double* L = tt + w.off_tt;
+  double* X = xmat + w.off_tt;
+  const int ld = w.ld_t;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j0 = j * NB, i0 = i * NB;
+  const double* D = dinv + w.off_dinv + (long long)j * NB * NB;   // D[c * NB + r] = inv(L_jj)(r, c), zero above the diagonal
+  extern __shared__ __align__(16) double sm[];
+  double vmax = 0.0;
+  if (i == j) {
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      const int c = idx >> 6, r = idx & 63;     // consecutive threads: consecutive r (dinv) ...
+      sm[r * TS + c] = D[idx];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      const int r = idx >> 6, c = idx & 63;     // ... consecutive c (X is row-major)
+      if (j0 + r < n && j0 + c < n) {
+        const double v = sm[r * TS + c];
+        X[(long long)(j0 + r) * ld + j0 + c] = v;
+        vmax = fmax(vmax, fabs(v));
+      }
+    }
+    // y_j: 4 threads per row gather sum_{col < j0} L(j0 + r, col) y_col, then the 64 x 64 triangular product
+    double* part = sm + NB * TS;     // [4][64]
+    double* rhs = part + 4 * NB;     // [64]
+    {
+      const int r = tid & 63, q = tid >> 6;
+      double acc = 0.0;
+      if (j0 + r < n)
+        for (int col = q; col < j0; col += 4) acc = fma(L[(long long)col * ld + j0 + r], y[w.off_t + col], acc);
+      part[q * NB + r] = acc;
+    }
+    __syncthreads();
+    if (tid < NB)
+      rhs[tid] = (j0 + tid < n) ? zt[w.off_t + j0 + tid] - ((part[tid] + part[NB + tid]) + (part[2 * NB + tid] + part[3 * NB + tid])) : 0.0;
+    __syncthreads();
+    if (tid < NB && j0 + tid < n) {
+      double v = 0.0;
+      for (int q = 0; q <= tid; q++) v = fma(sm[tid * TS + q], rhs[q], v);
+      y[w.off_t + j0 + tid] = v;
+    }
+  } else {
+    double* Ls = sm;             // Ls[kk * TS + r] = L(j0 + r, k0 + kk)
+    double* Xs = sm + NB * TS;   // Xs[kk * TS + c] = X(k0 + kk, i0 + c)
+    double C[4][2][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) C[mt][nt][0] = C[mt][nt][1] = 0.0;
+    for (int k = i; k < j; k++) {
+      const int k0 = k * NB;
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int kk = idx >> 6, r = idx & 63;
+        Ls[kk * TS + r] = (j0 + r < n) ? L[(long long)(k0 + kk) * ld + j0 + r] : 0.0;
+        // X_ii is lower triangular and its upper part was never written: read it as the zeros it stands for
+        Xs[kk * TS + r] = (k > i || r <= kk) ? X[(long long)(k0 + kk) * ld + i0 + r] : 0.0;
+      }
+      __syncthreads();
+      tile64_dmma(Ls, Xs, C, NB, 1.0, lane, warp);
+      __syncthreads();
+    }
+    // X_ji = -inv(L_jj) C
+    const int gid = lane >> 2, tig = lane & 3;
+    double* Cs = Xs;   // Cs[q * TS + c] = C(q, c)
+    double* Ds = Ls;   // Ds[q * TS + r] = inv(L_jj)(r, q)
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+          Cs[(32 * (warp >> 2) + 8 * mt + gid) * TS + 16 * (warp & 3) + 8 * nt + 2 * tig + e] = C[mt][nt][e];
+    for (int idx = tid; idx < NB * NB; idx += 256) Ds[(idx >> 6) * TS + (idx & 63)] = D[idx];
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) C[mt][nt][0] = C[mt][nt][1] = 0.0;
+    tile64_dmma(Ds, Cs, C, NB, -1.0, lane, warp);
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+      const int r = j0 + 32 * (warp >> 2) + 8 * mt + gid;
+      if (r >= n) continue;
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        const int c = i0 + 16 * (warp & 3) + 8 * nt + 2 * tig;
+        *reinterpret_cast<double2*>(&X[(long long)r * ld + c]) = make_double2(C[mt][nt][0], C[mt][nt][1]);
+        vmax = fmax(vmax, fmax(fabs(C[mt][nt][0]), fabs(C[mt][nt][1])));
+      }
+    }
+  }
+  if (amax) {   // bits of a non-negative double order like unsigned integers
+    for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && vmax > 0.0) atomicMax(&amax[blockIdx.y], (unsigned long long)__double_as_longlong(vmax));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // MakePosDef / CountPC for windows the Cholesky certificate cannot vouch for (util.cpp:302-318, 355-388): a symmetric
 // eigendecomposition of B11 on the device.  Rare path (lambda = 0 with duplicated SNPs, an eigenvalue cut-off above the
 // ridge, negative weights), so it is built for robustness, not speed: cyclic two-sided Jacobi, one CTA per window, the
@@ -810,10 +924,54 @@ qcat_finalize_kernel(const SolveWin* __restrict__ wins, const double* __restrict
 
 }  // namespace
 
+static int linv_attr(Ctx* ctx) {
+  static bool set_dev[64] = {};
+  if (!set_dev[ctx->device & 63]) {
+    GB_CUDA(cudaFuncSetAttribute(linv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * NB * TS)));
+    set_dev[ctx->device & 63] = true;
+  }
+  return GB_OK;
+}
+
+// Rows [j_lo, j_hi) of X = L^-1 (and of y) on `stream`, one launch per row block.
+static int launch_linv_rows_on(Ctx* ctx, cudaStream_t stream, const LinvArgs& a, int j_lo, int j_hi) {
+  int rc = linv_attr(ctx);
+  if (rc) return rc;
+  for (int j = j_lo; j < j_hi; j++) {
+    linv_row_kernel<<<dim3((unsigned)(j + 1), (unsigned)a.n_real), 256, sizeof(double) * 2 * NB * TS, stream>>>(
+        a.d_wins, a.d_tt, a.d_dinv, a.d_x, a.d_zt, a.d_y, a.d_amax, j);
+    ctx->launches++;
+  }
+  GB_CUDA(cudaGetLastError());
+  return GB_OK;
+}
+
+int launch_linv_rows(Ctx* ctx, const LinvArgs& a, int max_nt) {
+  if (a.n_real == 0) return GB_OK;
+  return launch_linv_rows_on(ctx, ctx->stream, a, 0, (max_nt + NB - 1) / NB);
+}
+
 int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, double* d_tt, double* d_dinv,
-                    int* d_status, const int* d_skip) {
+                    int* d_status, const int* d_skip, const LinvArgs* linv) {
   if (n_wins == 0) return GB_OK;
   const int nb_max = (max_nt + NB - 1) / NB;
+  // the explicit inverse of the int8-split solve: row block j on an auxiliary stream as soon as diagonal block j exists
+  if (linv && linv->n_real > 0) {
+    if (!ctx->aux_stream) {
+      int lo = 0, hi = 0;
+      GB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      GB_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+      GB_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
+    }
+  } else {
+    linv = nullptr;
+  }
+  auto linv_row_after = [&](int j) -> int {   // diagonal block j has just been enqueued on ctx->stream
+    if (!linv) return GB_OK;
+    GB_CUDA(cudaEventRecord(ctx->ev_aux, ctx->stream));
+    GB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux, 0));
+    return launch_linv_rows_on(ctx, ctx->aux_stream, *linv, j, j + 1);
+  };
   const size_t smem_panel = sizeof(double) * 2 * NB * TS;
   const size_t smem_diag = sizeof(double) * (2 * NB * MP + 3 * 16 * 17 + 32);
   const size_t smem_update = std::max(sizeof(double) * 2 * NB * TS, smem_diag);   // the update CTA of tile (k+1, k+1) also factors it
@@ -839,6 +997,8 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
   chol_diag_kernel<<<n_wins, 256, smem_diag, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status, d_skip, 0);
   ctx->launches++;
   mark();
+  int rc_l = linv_row_after(0);
+  if (rc_l) return rc_l;
   for (int k = 0; k + 1 < nb_max; k++) {
     const int tb = nb_max - k - 1;
     chol_panel_kernel<<<dim3(tb, n_wins), 256, smem_panel, ctx->stream>>>(d_wins, d_tt, d_dinv, d_skip, k);
@@ -847,6 +1007,11 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
                                                                                          d_skip, k);
     mark();
     ctx->launches += 2;
+    if ((rc_l = linv_row_after(k + 1))) return rc_l;   // the update launch has factored diagonal block k + 1
+  }
+  if (linv) {   // join: whatever follows on ctx->stream needs all of X and y
+    GB_CUDA(cudaEventRecord(ctx->ev_aux, ctx->aux_stream));
+    GB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));
   }
   if (trace) {
     cudaStreamSynchronize(ctx->stream);
