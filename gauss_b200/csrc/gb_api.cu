@@ -1070,7 +1070,10 @@ int gb_batch_create_ld(gb_ctx* ctx, gb_panel* panel, int64_t n_windows, const in
 void gb_batch_destroy(gb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
+  // a run that failed half-way may have left work on the forked streams: nothing may touch the buffers freed below
   cudaStreamSynchronize(b->ctx->stream);
+  if (b->ctx->side_stream) cudaStreamSynchronize(b->ctx->side_stream);
+  if (b->ctx->aux_stream) cudaStreamSynchronize(b->ctx->aux_stream);
   batch_free_device(b);
   delete b;
 }
