@@ -692,15 +692,29 @@ linv_row_kernel(const SolveWin* __restrict__ wins, const double* __restrict__ tt
     for (int mt = 0; mt < 4; mt++)
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) C[mt][nt][0] = C[mt][nt][1] = 0.0;
-    for (int k = i; k < j; k++) {
+    // the tiles of step k + 1 travel in registers while step k is multiplied (the launch is a chain of dependent
+    // launches: its loads' latency is all it has to hide)
+    double pl[16], px[16];
+    auto fetch = [&](int k) {
       const int k0 = k * NB;
-      for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int kk = idx >> 6, r = idx & 63;
-        Ls[kk * TS + r] = (j0 + r < n) ? L[(long long)(k0 + kk) * ld + j0 + r] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        const int idx = tid + 256 * q, kk = idx >> 6, r = idx & 63;
+        pl[q] = (j0 + r < n) ? L[(long long)(k0 + kk) * ld + j0 + r] : 0.0;
         // X_ii is lower triangular and its upper part was never written: read it as the zeros it stands for
-        Xs[kk * TS + r] = (k > i || r <= kk) ? X[(long long)(k0 + kk) * ld + i0 + r] : 0.0;
+        px[q] = (k > i || r <= kk) ? X[(long long)(k0 + kk) * ld + i0 + r] : 0.0;
+      }
+    };
+    fetch(i);
+    for (int k = i; k < j; k++) {
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        const int idx = tid + 256 * q, kk = idx >> 6, r = idx & 63;
+        Ls[kk * TS + r] = pl[q];
+        Xs[kk * TS + r] = px[q];
       }
       __syncthreads();
+      if (k + 1 < j) fetch(k + 1);
       tile64_dmma(Ls, Xs, C, NB, 1.0, lane, warp);
       __syncthreads();
     }
