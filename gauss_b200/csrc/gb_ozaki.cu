@@ -287,7 +287,7 @@ ozaki_solve_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 //   groups  : weight 10 - gi; in the last K block gi = 0, 1, 2, 3, 4, 6, 5 complete in that order, and the next unit
 //             first needs gi = 5, 4, 3, 2, 1, 0, 6: it takes the spare and then the slots in their order of completion,
 //             so the epilogue drains an accumulator while the MMAs of the next unit already run in another
-// MEASURED (chr22 batch, same results bit for bit): 1.23 ms against 1.07 ms for version 1 -- a loss, kept as the record
+// MEASURED (chr22 batch, results equal to fp64 rounding): 1.23 ms against 1.07 ms for version 1 -- a loss, kept as the record
 // (GB_OZ_KERNEL=2).  With N = 64 a tcgen05.mma reads 128 A rows from shared memory for half the work: 6 KB per 32-clock
 // instruction is 192 B/clk against the ~128 B/clk shared memory delivers, so the pipe is paced by operand READS at ~48 clk
 // per instruction (1.5x), and one thread has to issue an MMA every 32 clocks (the first version of the loop, with modulo
@@ -645,9 +645,9 @@ int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_
                         int64_t k_stride_bytes, int format, int box_rows);
 
 // GB_OZ_KERNEL=2 selects the all-groups-live kernel (measured slower: see its header); default = the streaming kernel
-static bool oz_use_v2() {
-  static const bool v2 = [] { const char* e = getenv("GB_OZ_KERNEL"); return e && atoi(e) == 2; }();
-  return v2;
+static bool oz_use_v2() {   // read per call (plan and launch of a batch must see the same value)
+  const char* e = getenv("GB_OZ_KERNEL");
+  return e && atoi(e) == 2;
 }
 
 size_t ozaki_win_bytes() { return sizeof(OzWin); }

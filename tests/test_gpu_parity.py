@@ -468,6 +468,24 @@ def test_monomorphic_unmeasured_snp_gives_nan_under_both_solvers(oracle, monkeyp
     assert np.abs(res["int8", "mix"][0][good] - zo[good]).max() <= TIGHT
 
 
+def test_solve_gemm_variants_agree(gpu_ctx, monkeypatch):
+    """GB_OZ_KERNEL=2 selects the all-groups-live variant of the digit-plane GEMM (kept as a measured alternative): the
+    same exact integer products, recombined in fp64 in another order -- equal to rounding."""
+    c = small_case(seed=47, n_snps=900, pop_sizes=(61, 103, 40, 25, 2, 330, 97), measured_frac=0.35, core=(0, 900))
+    g, t = c["g"].astype(np.int8), c["type"]
+    panel = make_panel(gpu_ctx, g, c["pop_sizes"])
+    for lo, hi in [(0, 300), (120, 900), (0, 900)]:
+        idx = np.arange(lo, hi)
+        rt, ru = idx[t[lo:hi] == 1], idx[t[lo:hi] == 0]
+        monkeypatch.delenv("GB_OZ_KERNEL", raising=False)
+        z1, i1, _ = panel.window_distmix(rt, ru, c["z"][rt], c["w"])
+        monkeypatch.setenv("GB_OZ_KERNEL", "2")
+        z2, i2, _ = panel.window_distmix(rt, ru, c["z"][rt], c["w"])
+        monkeypatch.delenv("GB_OZ_KERNEL", raising=False)
+        assert np.abs(z2 - z1).max() <= 1e-12 and np.abs(i2 - i1).max() <= 1e-12
+        assert not np.array_equal(z2, np.zeros_like(z2))
+
+
 def test_overlapped_batch_run_equals_staged_run(gpu_ctx):
     """gb_batch_run puts the factorisation on a side stream beside the B21 Gram tiles once a batch has at least one
     B21 tile per SM; the results must be the bits of the stage-by-stage run, run after run."""
