@@ -486,6 +486,29 @@ def test_solve_gemm_variants_agree(gpu_ctx, monkeypatch):
         assert not np.array_equal(z2, np.zeros_like(z2))
 
 
+def test_windows_beyond_the_digit_plane_limit_take_the_fp64_solve(monkeypatch):
+    """More than 2,048 measured SNPs in a window: the int8-split solve's accumulator bound (6 pairs x 128^2 x K) and its
+    shared-memory copy of y end there, so the batch is solved by the fp64 triangular solve -- same numbers as with
+    GB_SOLVE=fp64, bit for bit."""
+    c = small_case(seed=53, n_snps=2500, pop_sizes=(300, 330), measured_frac=0.86, core=(0, 2500))
+    g, t = c["g"].astype(np.int8), c["type"]
+    idx = np.arange(2500)
+    rt, ru = idx[t == 1], idx[t == 0]
+    assert len(rt) > 2048 and len(ru) > 10
+    res = {}
+    for solver in ("int8", "fp64"):
+        monkeypatch.setenv("GB_SOLVE", solver)
+        ctx = gb.Context(0)
+        try:
+            panel = make_panel(ctx, g, c["pop_sizes"])
+            res[solver] = panel.window_distmix(rt, ru, c["z"][rt], c["w"])[:2]
+        finally:
+            ctx.close()
+    assert np.isfinite(res["int8"][0]).all() and np.isfinite(res["int8"][1]).all()
+    np.testing.assert_array_equal(res["int8"][0], res["fp64"][0])
+    np.testing.assert_array_equal(res["int8"][1], res["fp64"][1])
+
+
 def test_overlapped_batch_run_equals_staged_run(gpu_ctx):
     """gb_batch_run puts the factorisation on a side stream beside the B21 Gram tiles once a batch has at least one
     B21 tile per SM; the results must be the bits of the stage-by-stage run, run after run."""
