@@ -26,9 +26,13 @@ __device__ __forceinline__ uint32_t e2m1_code(int v) {
   }
 }
 
-// One CTA per SNP row; warp w packs populations w, w+8, ...  Each lane moves 8 consecutive
-// dosages per step: byte loads (source population offsets are unaligned) and one 64-bit (int8) or
-// 32-bit (E2M1 nibbles, low nibble = lower K index) store.
+// One CTA per SNP row.  The row is cut into items of 512 consecutive dosages of one population (a warp-step: 16 dosages
+// per lane); the 8 warps take items round-robin, so a 6,360-individual population and an 86-individual one no longer
+// decide which warp finishes last (populations used to be dealt whole).  Per lane: sixteen source bytes out of five
+// ALIGNED 32-bit loads (population offsets are not aligned), byte loads only where a block ends or the buffer itself is
+// unaligned; when all sixteen are dosages 0 / 1 / 2 -- every real panel -- the work is word-wide: SIMD byte subtract,
+// DP4A for sum x and sum x^2, and for E2M1 a bit compress of bytes to nibbles (code = dosage << 1); anything else
+// takes the per-byte path.  One 128-bit (int8) or 64-bit (E2M1 nibbles, low nibble = lower K index) store per lane.
 template <int FORMAT>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_ascii,
@@ -36,56 +40,99 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
                  const int* __restrict__ pop_sizes, const int* __restrict__ koff,
                  int32_t* __restrict__ sx, int32_t* __restrict__ sxx, long long stat_ld, int* flags,
                  int seg_align) {
+  __shared__ int s_sum[P_MAX], s_sq[P_MAX], s_soff[P_MAX + 1], s_item0[P_MAX + 1];
   const long long row = blockIdx.x;
   const uint8_t* s = src + row * src_stride;
   int8_t* d = dst + (row0 + row) * (long long)k_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < P_MAX) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    int so = 0, it = 0;
+    for (int p = 0; p < n_pops; p++) {
+      s_soff[p] = so;
+      s_item0[p] = it;
+      so += pop_sizes[p];
+      it += ((pop_sizes[p] + seg_align - 1) / seg_align * seg_align + 511) >> 9;
+    }
+    s_soff[n_pops] = so;
+    s_item0[n_pops] = it;
+  }
+  __syncthreads();
+  const uint32_t sub4 = is_ascii ? 0x30303030u : 0u;
   const int sub = is_ascii ? 48 : 0;
   bool bad = false, big = false;
   const bool aligned_src = (reinterpret_cast<uintptr_t>(src) & 3) == 0;   // else the first word of the buffer may not be touched
-  // source offset of population p = sum of sizes before it
-  int src_off = 0;
-  int next_p = 0;
-  for (int p = warp; p < n_pops; p += 8) {
-    for (; next_p < p; next_p++) src_off += pop_sizes[next_p];
+  const int n_items = s_item0[n_pops];
+  int p = 0;
+  for (int it = warp; it < n_items; it += 8) {
+    while (it >= s_item0[p + 1]) p++;
     const int m = pop_sizes[p];
-    const int kp = (m + seg_align - 1) / seg_align * seg_align;
+    const int kp = (m + seg_align - 1) / seg_align * seg_align;   // a multiple of 32: 16-dosage lanes never straddle it
+    const int src_off = s_soff[p];
     const uint8_t* sp = s + src_off;
+    const int j = ((it - s_item0[p]) << 9) + lane * 16;
     int sum = 0, sq = 0;
-    for (int j = lane * 8; j < kp; j += 256) {
-      uint32_t lo = 0, hi = 0;
-      // eight source bytes: two funnel-shifted words out of three ALIGNED 32-bit loads (population offsets are not
-      // aligned), byte loads only where the block ends or the buffer itself is unaligned
-      uint32_t raw_lo = 0, raw_hi = 0;
-      // the three words cover [a & ~3, a & ~3 + 12): inside the row's population block, and not before the buffer
-      const bool fast = j + 12 <= m && (aligned_src || row * src_stride + src_off + j >= 4);
+    if (j < kp) {
+      uint32_t raw[4] = {0u, 0u, 0u, 0u};
+      // the five words cover [a & ~3, a & ~3 + 20): inside the row's population block, and not before the buffer
+      const bool fast = j + 20 <= m && (aligned_src || row * src_stride + src_off + j >= 4);
       if (fast) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(sp + j);
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
         const uint32_t sh = (uint32_t)(a & 3) * 8;
-        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-        raw_lo = __funnelshift_r(w0, w1, sh);
-        raw_hi = __funnelshift_r(w1, w2, sh);
-      }
+        uint32_t w[5];
 #pragma unroll
-      for (int b = 0; b < 8; b++) {
-        int v = 0;
-        if (fast) v = (int)(signed char)((int)(((b < 4 ? raw_lo : raw_hi) >> (8 * (b & 3))) & 0xffu) - sub);
-        else if (j + b < m) v = (int)(signed char)((int)sp[j + b] - sub);
-        sum += v;
-        sq += v * v;
-        big |= (unsigned)v > 2u;
+        for (int q = 0; q < 5; q++) w[q] = __ldg(wp + q);
+#pragma unroll
+        for (int q = 0; q < 4; q++) raw[q] = __vsub4(__funnelshift_r(w[q], w[q + 1], sh), sub4);
+      }
+      const uint32_t any = raw[0] | raw[1] | raw[2] | raw[3];
+      const uint32_t three = ((raw[0] & (raw[0] >> 1)) | (raw[1] & (raw[1] >> 1)) | (raw[2] & (raw[2] >> 1)) | (raw[3] & (raw[3] >> 1))) &
+                             0x01010101u;   // a byte with bits 0 and 1 set
+      uint32_t out[4] = {0u, 0u, 0u, 0u};   // int8: the 16 bytes; E2M1: out[0], out[1] = 16 nibbles
+      if (fast && (any & 0xFCFCFCFCu) == 0u && three == 0u) {
+        // all sixteen are 0 / 1 / 2
+        uint32_t su = 0u, sq_u = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          su = __dp4a(raw[q], 0x01010101u, su);
+          sq_u = __dp4a(raw[q], raw[q], sq_u);
+        }
+        sum = (int)su;
+        sq = (int)sq_u;
         if (FORMAT == GB_PANEL_E2M1) {
-          const uint32_t c = e2m1_code(v);
-          bad |= c == 0xFFu;
-          lo |= (c & 0xFu) << (4 * b);
+          uint32_t c4[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const uint32_t t = (raw[q] | (raw[q] >> 4)) & 0x00FF00FFu;
+            c4[q] = (t | (t >> 8)) & 0x0000FFFFu;
+          }
+          out[0] = (c4[0] | (c4[1] << 16)) << 1;   // E2M1 code of dosage 0 / 1 / 2 = dosage << 1
+          out[1] = (c4[2] | (c4[3] << 16)) << 1;
         } else {
-          if (b < 4) lo |= (uint32_t)(v & 0xff) << (8 * b);
-          else hi |= (uint32_t)(v & 0xff) << (8 * (b - 4));
+#pragma unroll
+          for (int q = 0; q < 4; q++) out[q] = raw[q];
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+          int v = 0;
+          if (fast) v = (int)(signed char)(raw[b >> 2] >> (8 * (b & 3)));
+          else if (j + b < m) v = (int)(signed char)((int)sp[j + b] - sub);
+          sum += v;
+          sq += v * v;
+          big |= (unsigned)v > 2u;
+          if (FORMAT == GB_PANEL_E2M1) {
+            const uint32_t c = e2m1_code(v);
+            bad |= c == 0xFFu;
+            out[b >> 3] |= (c & 0xFu) << (4 * (b & 7));
+          } else {
+            out[b >> 2] |= (uint32_t)(v & 0xff) << (8 * (b & 3));
+          }
         }
       }
-      if (FORMAT == GB_PANEL_E2M1) *reinterpret_cast<uint32_t*>(d + ((koff[p] + j) >> 1)) = lo;
-      else *reinterpret_cast<uint2*>(d + koff[p] + j) = make_uint2(lo, hi);
+      if (FORMAT == GB_PANEL_E2M1) *reinterpret_cast<uint2*>(d + ((koff[p] + j) >> 1)) = make_uint2(out[0], out[1]);
+      else *reinterpret_cast<uint4*>(d + koff[p] + j) = make_uint4(out[0], out[1], out[2], out[3]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -93,9 +140,14 @@ pack_rows_kernel(const uint8_t* __restrict__ src, long long src_stride, int is_a
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
     if (lane == 0) {
-      sx[(long long)p * stat_ld + row0 + row] = sum;
-      sxx[(long long)p * stat_ld + row0 + row] = sq;
+      atomicAdd(&s_sum[p], sum);
+      atomicAdd(&s_sq[p], sq);
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_pops) {
+    sx[(long long)threadIdx.x * stat_ld + row0 + row] = s_sum[threadIdx.x];
+    sxx[(long long)threadIdx.x * stat_ld + row0 + row] = s_sq[threadIdx.x];
   }
   if (bad) atomicOr(flags, 1);
   if (big) atomicOr(flags, 2);   // a byte outside {0, 1, 2}: the int8 fold may not assume |d| <= 4 m^2
