@@ -835,11 +835,18 @@ int gb_ctx_create(int device, gb_ctx** out) {
 void gb_ctx_destroy(gb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->win_panel) {
+    gb_panel_destroy(static_cast<gb_panel*>(ctx->win_panel));
+    ctx->win_panel = nullptr;
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  for (cudaEvent_t e : ctx->ev_stage)
+    if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; i++) {
     if (ctx->chrom_streams[i]) cudaStreamDestroy(ctx->chrom_streams[i]);
     if (ctx->chrom_sides[i]) cudaStreamDestroy(ctx->chrom_sides[i]);
@@ -1012,36 +1019,86 @@ int gb_panel_append_strings(gb_panel* p, int64_t n_rows, const char* const* pop_
   Ctx* ctx = p->ctx;
   int rc = check_device(ctx);
   if (rc) return rc;
-  // concatenate the per-population strings of each SNP into one pinned staging row
+  // The per-population strings of each SNP are concatenated into pinned staging rows, copied and packed.  This is the
+  // drop-in seam (a window of run_distmix arrives as ~4,400 SNPs x 21 strings, 140 MB), so it is built for rate: the
+  // staging buffer lives in the context (pinning 140 MB per call cost more than everything else), host threads gather
+  // disjoint row ranges, and the rows go in chunks so that the copy + pack of one chunk runs while the next is gathered.
   const size_t N = (size_t)p->n_samples;
-  char* stage = nullptr;
-  GB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&stage), (size_t)n_rows * N));
-  for (int64_t r = 0; r < n_rows; r++) {
-    char* dst = stage + (size_t)r * N;
-    for (int k = 0; k < p->n_pops; k++) {
-      const char* s = pop_strings[r * p->n_pops + k];
-      if (!s) {
-        cudaFreeHost(stage);
-        ctx->err = "null genotype string";
-        return GB_ERR_BAD_ARG;
-      }
-      // the string must hold exactly the population's individuals: a shorter one would be over-read here, and the
-      // reference's CalCor walks x[i].length() characters (util.cpp:55), so a longer one cannot be reproduced by
-      // truncating it
-      const size_t m = (size_t)p->pop_sizes[(size_t)k];
-      if (strnlen(s, m + 1) != m) {
-        cudaFreeHost(stage);
-        ctx->err = "genotype string of SNP " + std::to_string(r) + ", population " + std::to_string(k) + " does not hold " +
-                   std::to_string(m) + " characters";
-        return GB_ERR_BAD_ARG;
-      }
-      std::memcpy(dst, s, m);
-      dst += p->pop_sizes[(size_t)k];
-    }
+  const int n_pops = p->n_pops;
+  constexpr int64_t CHUNK = 1024;                 // rows per chunk; two chunk buffers
+  const size_t need = (size_t)std::min<int64_t>(n_rows, 2 * CHUNK) * N;
+  if (ctx->h_stage_cap < need) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_cap = 0;
+    GB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stage), need));
+    ctx->h_stage_cap = need;
   }
-  rc = gb_panel_append_host(p, n_rows, stage, (int64_t)N, 1);
-  cudaStreamSynchronize(ctx->stream);
-  cudaFreeHost(stage);
+  if (!ctx->ev_stage[0]) {
+    GB_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage[0], cudaEventDisableTiming));
+    GB_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage[1], cudaEventDisableTiming));
+  }
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  std::atomic<long long> bad_row{-1};
+  std::atomic<int> bad_pop{-1}, bad_kind{0};   // kind 1: null string, 2: wrong length
+  auto gather = [&](char* stage, int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1 && bad_row.load(std::memory_order_relaxed) < 0; r++) {
+      char* dst = stage + (size_t)(r - r0) * N;
+      for (int k = 0; k < n_pops; k++) {
+        const char* s = pop_strings[r * n_pops + k];
+        // the string must hold exactly the population's individuals: a shorter one would be over-read here, and the
+        // reference's CalCor walks x[i].length() characters (util.cpp:55), so a longer one cannot be reproduced by
+        // truncating it
+        const size_t m = (size_t)p->pop_sizes[(size_t)k];
+        const int kind = !s ? 1 : (strnlen(s, m + 1) != m ? 2 : 0);
+        if (kind) {
+          long long expect = -1;
+          if (bad_row.compare_exchange_strong(expect, (long long)r)) {
+            bad_pop = k;
+            bad_kind = kind;
+          }
+          return;
+        }
+        std::memcpy(dst, s, m);
+        dst += m;
+      }
+    }
+  };
+  int n_chunk = 0;
+  for (int64_t c0 = 0; c0 < n_rows && !rc; c0 += CHUNK, n_chunk++) {
+    const int64_t c1 = std::min(n_rows, c0 + CHUNK);
+    const int buf = n_chunk & 1;
+    char* stage = ctx->h_stage + (size_t)buf * (size_t)CHUNK * N;
+    if (n_chunk >= 2) GB_CUDA(cudaEventSynchronize(ctx->ev_stage[buf]));   // the copy that last read this buffer is done
+    const int n_thr = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), std::max<int64_t>(1, (c1 - c0) / 64));
+    if (n_thr <= 1) {
+      gather(stage, c0, c1);
+    } else {
+      std::vector<std::thread> th;
+      const int64_t per = (c1 - c0 + n_thr - 1) / n_thr;
+      for (int t = 0; t < n_thr; t++) {
+        const int64_t a = c0 + t * per, b = std::min(c1, a + per);
+        if (a < b) th.emplace_back([&, a, b, stage, c0] { gather(stage + (size_t)(a - c0) * N, a, b); });
+      }
+      for (auto& t : th) t.join();
+    }
+    if (bad_row.load() >= 0) break;
+    rc = gb_panel_append_host(p, c1 - c0, stage, (int64_t)N, 1);
+    if (!rc) GB_CUDA(cudaEventRecord(ctx->ev_stage[buf], ctx->stream));
+  }
+  cudaStreamSynchronize(ctx->stream);   // the staging buffers are free for the next call; the panel rows are packed
+  if (bad_row.load() >= 0) {
+    // rows of earlier chunks were appended: take them back so that a failed call leaves the panel as it found it
+    p->n_rows -= std::min<int64_t>(p->n_rows, (int64_t)n_chunk * CHUNK);
+    const int k = bad_pop.load();
+    if (bad_kind.load() == 1) {
+      ctx->err = "null genotype string";
+    } else {
+      ctx->err = "genotype string of SNP " + std::to_string(bad_row.load()) + ", population " + std::to_string(k) + " does not hold " +
+                 std::to_string(p->pop_sizes[(size_t)k]) + " characters";
+    }
+    return GB_ERR_BAD_ARG;
+  }
   return rc;
 }
 
@@ -2213,6 +2270,28 @@ int gb_pipe_wait(gb_pipe* pp, int64_t ticket, int* window_status) {
 }
 
 // ---- host-side mirror of run_dist / run_distmix ---------------------------------------------------
+// The context's working panel for the per-window string entry points: reused while the population layout and the
+// format stay the same, regrown (x 1.25) when a window needs more rows.  Freed with the context.
+static int window_panel(gb_ctx* ctx, int n_pops, const int* pop_sizes, int64_t rows, int format, gb_panel** out) {
+  gb_panel* w = static_cast<gb_panel*>(ctx->win_panel);
+  if (w) {
+    bool same = w->format == format && w->n_pops == n_pops && w->capacity >= rows;
+    for (int k = 0; same && k < n_pops; k++) same = w->pop_sizes[(size_t)k] == pop_sizes[k];
+    if (same) {
+      gb_panel_clear(w);
+      *out = w;
+      return GB_OK;
+    }
+    ctx->win_panel = nullptr;
+    gb_panel_destroy(w);
+  }
+  int rc = gb_panel_create_fmt(ctx, n_pops, pop_sizes, rows + rows / 4, format, &w);
+  if (rc) return rc;
+  ctx->win_panel = w;
+  *out = w;
+  return GB_OK;
+}
+
 int gb_run_window_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const long long* bp, double* z,
                           double* info, const char* const* pop_strings, int n_pops, const int* pop_sizes,
                           const double* pop_wgt, long long start_bp, long long end_bp, const gb_params* params,
@@ -2246,11 +2325,22 @@ int gb_run_window_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const lo
   // Genotype strings of a real panel hold only '0','1','2' -> 4-bit operands.  The reference's
   // (c - '0') arithmetic accepts any byte; strings with other characters are repacked as int8,
   // which reproduces it for every 7-bit char.
+  const bool trace = getenv("GB_STRINGS_TRACE") != nullptr;   // diagnostics: wall-clock phases of a call on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
   for (int format = ctx->panel_format;; format = GB_PANEL_INT8) {
-    rc = gb_panel_create_fmt(ctx, n_pops, pop_sizes, nt + nu, format, &panel);
+    // the working panel is kept in the context between calls (a genome is ~2,900 calls of the same shape): creating
+    // and destroying 70 MB of device rows, statistics and tensor maps per window cost as much as the window itself
+    auto t0 = now();
+    rc = window_panel(ctx, n_pops, pop_sizes, nt + nu, format, &panel);
     if (rc) return rc;
+    const double t_panel = ms_since(t0);
+    t0 = now();
     rc = gb_panel_append_strings(panel, nt + nu, strs.data());
+    const double t_append = ms_since(t0);
+    double t_impute = 0.0;
     if (!rc) {
+      t0 = now();
       std::vector<int64_t> rt((size_t)nt), ru((size_t)nu);
       std::vector<double> zt((size_t)nt), zu((size_t)nu), iu((size_t)nu);
       for (int64_t i = 0; i < nt; i++) rt[(size_t)i] = i, zt[(size_t)i] = z[meas[(size_t)i]];
@@ -2261,8 +2351,11 @@ int gb_run_window_strings(gb_ctx* ctx, int64_t n_snps, const int* type, const lo
           z[unme[(size_t)i]] = zu[(size_t)i];
           info[unme[(size_t)i]] = iu[(size_t)i];
         }
+      t_impute = ms_since(t0);
     }
-    gb_panel_destroy(panel);
+    if (trace)
+      fprintf(stderr, "[strings trace] n_t %lld n_u %lld | panel %.2f ms | gather + copy + pack %.2f ms | plan + run + fetch %.2f ms\n",
+              (long long)nt, (long long)nu, t_panel, t_append, t_impute);
     panel = nullptr;
     if (rc != GB_ERR_UNSUPPORTED || format == GB_PANEL_INT8) break;
   }

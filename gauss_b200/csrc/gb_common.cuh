@@ -94,6 +94,10 @@ struct Ctx {
   cudaStream_t side_stream = nullptr;   // lazily created: the factorisation beside the B21 Gram tiles (gb_batch_run)
   cudaStream_t aux_stream = nullptr;    // lazily created: the rows of L^-1 beside the factorisation's own steps (launch_cholesky)
   cudaEvent_t ev_aux = nullptr;
+  char* h_stage = nullptr;              // lazily grown pinned staging of gb_panel_append_strings (two chunks of rows)
+  size_t h_stage_cap = 0;
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  void* win_panel = nullptr;            // working panel of the per-window string entry points (a gb_panel, kept between calls)
   int seg_order = 2;                    // processing order of the populations in the regrouped Gram fold (GB_SEG_ORDER)
   int chol_sms = 64;                    // SMs the B21 Gram launch leaves to it (GB_CHOL_SMS; 0 = run the stages one after another)
   cudaStream_t chrom_sides[2] = {nullptr, nullptr};     // ... and the side stream each of them forks its factorisation onto
