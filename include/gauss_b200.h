@@ -378,7 +378,9 @@ GB_API int gb_pipe_wait(gb_pipe *pipe, int64_t ticket, int *window_status);
  * info and, per SNP, n_pops genotype strings (may be NULL for type 2).  Splits measured /
  * unmeasured exactly as dist.cpp:132-141, enforces the thresholds (dist.cpp:146), packs the
  * strings, runs the window on the GPU and writes z/info of the imputed SNPs back in place
- * (SetZ/SetInfo, dist.cpp:200-202).  pop_wgt == NULL -> run_dist. */
+ * (SetZ/SetInfo, dist.cpp:200-202).  pop_wgt == NULL -> run_dist.
+ * The context keeps a pinned staging buffer and a working panel between calls (a genome is ~2,900 calls of one
+ * shape) and gathers the strings on a few host threads; like every call on a gb_ctx it is not re-entrant. */
 GB_API int gb_run_window_strings(gb_ctx *ctx, int64_t n_snps, const int *type, const long long *bp,
                           double *z, double *info, const char *const *pop_strings, int n_pops,
                           const int *pop_sizes, const double *pop_wgt, long long start_bp,
