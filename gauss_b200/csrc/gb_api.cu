@@ -1639,23 +1639,20 @@ int gb_pack5_rows_host(int n_pops, const int* pop_sizes, int64_t n_rows, const v
       for (int p = 0; p < n_pops; p++) {
         const int m = pop_sizes[p];
         uint8_t* d = dst + boff[(size_t)p];
-        const int full = m / 5;
-        unsigned over = 0;   // branch-free: the flag is looked at once per block, the loop stays a straight byte pipeline
-        for (int o = 0; o < full; o++) {
-          const uint8_t* q = src + 5 * o;
-          const unsigned a = (uint8_t)(q[0] - sub), b = (uint8_t)(q[1] - sub), c = (uint8_t)(q[2] - sub),
-                         e = (uint8_t)(q[3] - sub), f = (uint8_t)(q[4] - sub);
-          over |= (a > 2u) | (b > 2u) | (c > 2u) | (e > 2u) | (f > 2u);
-          d[o] = (uint8_t)(a + 3u * b + 9u * c + 27u * e + 81u * f);
+        int j = 0;
+        for (; j + 5 <= m; j += 5) {
+          const unsigned a = (uint8_t)(src[j] - sub), b = (uint8_t)(src[j + 1] - sub), c = (uint8_t)(src[j + 2] - sub),
+                         e = (uint8_t)(src[j + 3] - sub), f = (uint8_t)(src[j + 4] - sub);
+          if (a > 2u || b > 2u || c > 2u || e > 2u || f > 2u) bad.store(1, std::memory_order_relaxed);
+          d[j / 5] = (uint8_t)(a + 3u * b + 9u * c + 27u * e + 81u * f);
         }
         unsigned v = 0, mul = 1;
-        for (int k = 5 * full; k < m; k++, mul *= 3) {
+        for (int k = j; k < m; k++, mul *= 3) {
           const unsigned a = (uint8_t)(src[k] - sub);
-          over |= a > 2u;
+          if (a > 2u) bad.store(1, std::memory_order_relaxed);
           v += mul * (a % 3u);
         }
-        if (5 * full < m) d[full] = (uint8_t)v;
-        if (over) bad.store(1, std::memory_order_relaxed);
+        if (j < m) d[j / 5] = (uint8_t)v;
         src += m;
       }
     }
