@@ -1078,7 +1078,12 @@ int gb_panel_append_strings(gb_panel* p, int64_t n_rows, const char* const* pop_
       const int64_t per = (c1 - c0 + n_thr - 1) / n_thr;
       for (int t = 0; t < n_thr; t++) {
         const int64_t a = c0 + t * per, b = std::min(c1, a + per);
-        if (a < b) th.emplace_back([&, a, b, stage, c0] { gather(stage + (size_t)(a - c0) * N, a, b); });
+        if (a >= b) continue;
+        try {
+          th.emplace_back([&, a, b, stage, c0] { gather(stage + (size_t)(a - c0) * N, a, b); });
+        } catch (...) {   // no thread to be had: this range is gathered here (nothing may be thrown across the C-ABI)
+          gather(stage + (size_t)(a - c0) * N, a, b);
+        }
       }
       for (auto& t : th) t.join();
     }
@@ -1609,7 +1614,13 @@ int gb_pack2_rows_host(int n_pops, const int* pop_sizes, int64_t n_rows, const v
     work(0, n_rows);
   } else {
     std::vector<std::thread> th;
-    for (int t = 0; t < nth; t++) th.emplace_back(work, n_rows * t / nth, n_rows * (t + 1) / nth);
+    for (int t = 0; t < nth; t++) {
+      try {
+        th.emplace_back(work, n_rows * t / nth, n_rows * (t + 1) / nth);
+      } catch (...) {   // no thread to be had: this range runs here (nothing may be thrown across the C-ABI)
+        work(n_rows * t / nth, n_rows * (t + 1) / nth);
+      }
+    }
     for (auto& t : th) t.join();
   }
   return bad.load() ? GB_ERR_UNSUPPORTED : GB_OK;
@@ -1663,7 +1674,13 @@ int gb_pack5_rows_host(int n_pops, const int* pop_sizes, int64_t n_rows, const v
     work(0, n_rows);
   } else {
     std::vector<std::thread> th;
-    for (int t = 0; t < nth; t++) th.emplace_back(work, n_rows * t / nth, n_rows * (t + 1) / nth);
+    for (int t = 0; t < nth; t++) {
+      try {
+        th.emplace_back(work, n_rows * t / nth, n_rows * (t + 1) / nth);
+      } catch (...) {   // no thread to be had: this range runs here (nothing may be thrown across the C-ABI)
+        work(n_rows * t / nth, n_rows * (t + 1) / nth);
+      }
+    }
     for (auto& t : th) t.join();
   }
   return bad.load() ? GB_ERR_UNSUPPORTED : GB_OK;

@@ -884,7 +884,12 @@ int gb_genome_create(int n_gpus, const int* devices, int n_pops, const int* pop_
       return rc;
     }
   }
-  for (Shard* sh : g->shards) sh->th = std::thread(shard_thread, g, sh);
+  try {
+    for (Shard* sh : g->shards) sh->th = std::thread(shard_thread, g, sh);
+  } catch (...) {   // nothing may be thrown across the C-ABI
+    gb_genome_destroy(g);   // stops and joins the threads that did start
+    return GB_ERR_OOM;
+  }
   *out = g;
   return GB_OK;
 }

@@ -105,14 +105,21 @@ void parallel_for(int n_threads, int64_t n, F&& fn) {
   }
   std::atomic<int64_t> next{0};
   std::vector<std::thread> th;
-  for (int t = 0; t < n_threads; t++)
-    th.emplace_back([&] {
-      for (;;) {
-        const int64_t i = next.fetch_add(1);
-        if (i >= n) return;
-        fn(i);
-      }
-    });
+  auto drain = [&] {
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= n) return;
+      fn(i);
+    }
+  };
+  for (int t = 0; t < n_threads; t++) {
+    try {
+      th.emplace_back(drain);
+    } catch (...) {   // no thread to be had: fewer workers (nothing may be thrown across the C-ABI)
+      break;
+    }
+  }
+  if (th.empty()) drain();
   for (auto& t : th) t.join();
 }
 
