@@ -269,7 +269,10 @@ chol_panel_kernel(const SolveWin* __restrict__ wins, double* tt, const double* _
   }
 }
 
-// trailing update of step k: A_ij -= L_ik L_jk^T for k < j <= i
+// trailing update of step k: A_ij -= L_ik L_jk^T for k < j <= i.  One CTA per block ROW i: L_ik stays in shared memory
+// for the whole strip j = k+1 .. i, and the next tile's L_jk and A_ij travel in registers while the current product
+// runs (a CTA per tile spent its 9 us on three exposed loads for half a microsecond of tensor work, and a step of the
+// largest window launched 171 of them).
 __global__ void __launch_bounds__(256)
 chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, double* dinv, int* status,
                    const int* __restrict__ skip, int k) {
@@ -278,17 +281,14 @@ chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, double* dinv, 
   const int n = w.n_t;
   const int nb = win_nb(n);
   const int tb = nb - k - 1;
-  if (tb <= 0) return;
-  const int t = blockIdx.x;
-  if (t >= tb * (tb + 1) / 2) return;
-  int ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-  while ((ii + 1) * (ii + 2) / 2 <= t) ii++;
-  while (ii * (ii + 1) / 2 > t) ii--;
-  const int jj = t - ii * (ii + 1) / 2;
-  const int i0 = (k + 1 + ii) * NB, j0 = (k + 1 + jj) * NB, k0 = k * NB;
+  const int ii = blockIdx.x;
+  if (tb <= 0 || ii >= tb) return;
+  const int i0 = (k + 1 + ii) * NB, k0 = k * NB;
   double* A = tt + w.off_tt;
   const int ld = w.ld_t;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
 
   extern __shared__ __align__(16) double sm[];
   double* Ls = sm;            // Ls[kk*TS + r] = L(i0+r, k0+kk)
@@ -296,39 +296,64 @@ chol_update_kernel(const SolveWin* __restrict__ wins, double* tt, double* dinv, 
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int kk = idx >> 6, r = idx & 63;
     Ls[kk * TS + r] = (i0 + r < n) ? A[(long long)(k0 + kk) * ld + i0 + r] : 0.0;
-    Rs[kk * TS + r] = (j0 + r < n) ? A[(long long)(k0 + kk) * ld + j0 + r] : 0.0;
   }
-  __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  const int gid = lane >> 2, tig = lane & 3;
-  double C[4][2][2];
+  double pr[16];          // the next tile's L_jk, element idx = tid + 256 q
+  double Cn[4][2][2];     // ... and its A_ij fragment
+  auto fetch = [&](int jj) {
+    const int j0 = (k + 1 + jj) * NB;
 #pragma unroll
-  for (int mt = 0; mt < 4; mt++) {
-    const int r = i0 + 32 * (warp >> 2) + 8 * mt + gid;
+    for (int q = 0; q < 16; q++) {
+      const int idx = tid + 256 * q, kk = idx >> 6, r = idx & 63;
+      pr[q] = (j0 + r < n) ? A[(long long)(k0 + kk) * ld + j0 + r] : 0.0;
+    }
 #pragma unroll
-    for (int nt = 0; nt < 2; nt++)
+    for (int mt = 0; mt < 4; mt++) {
+      const int r = i0 + 32 * (warp >> 2) + 8 * mt + gid;
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int c = j0 + 16 * (warp & 3) + 8 * nt + 2 * tig + e;
-        C[mt][nt][e] = (r < n && c < n && r >= c) ? A[(long long)c * ld + r] : 0.0;
+      for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = j0 + 16 * (warp & 3) + 8 * nt + 2 * tig + e;
+          Cn[mt][nt][e] = (r < n && c < n && r >= c) ? A[(long long)c * ld + r] : 0.0;
+        }
+    }
+  };
+  fetch(0);
+  for (int jj = 0; jj <= ii; jj++) {
+    const int j0 = (k + 1 + jj) * NB;
+    __syncthreads();   // the previous product has read Rs (first trip: orders nothing that matters)
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int idx = tid + 256 * q;
+      Rs[(idx >> 6) * TS + (idx & 63)] = pr[q];
+    }
+    double C[4][2][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        C[mt][nt][0] = Cn[mt][nt][0];
+        C[mt][nt][1] = Cn[mt][nt][1];
       }
+    __syncthreads();   // Ls (first trip) and Rs are complete
+    if (jj < ii) fetch(jj + 1);
+    tile64_dmma(Ls, Rs, C, NB, -1.0, lane, warp);   // C -= L_ik L_jk^T
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+      const int r = i0 + 32 * (warp >> 2) + 8 * mt + gid;
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = j0 + 16 * (warp & 3) + 8 * nt + 2 * tig + e;
+          if (r < n && c < n && r >= c) A[(long long)c * ld + r] = C[mt][nt][e];
+        }
+    }
   }
-  tile64_dmma(Ls, Rs, C, NB, -1.0, lane, warp);   // C -= L_ik L_jk^T
-#pragma unroll
-  for (int mt = 0; mt < 4; mt++) {
-    const int r = i0 + 32 * (warp >> 2) + 8 * mt + gid;
-#pragma unroll
-    for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int c = j0 + 16 * (warp & 3) + 8 * nt + 2 * tig + e;
-        if (r < n && c < n && r >= c) A[(long long)c * ld + r] = C[mt][nt][e];
-      }
-  }
-  // Look-ahead: the CTA that has just finished the next diagonal tile (k+1, k+1) factors and inverts it right away,
-  // while the other CTAs of this launch are still updating the rest of the trailing matrix.  The 64 x 64
+  // Look-ahead: the CTA of block row k + 1 has just finished the next diagonal tile (k+1, k+1): it factors and inverts it
+  // right away, while the other CTAs of this launch are still updating the rest of the trailing matrix.  The 64 x 64
   // factorisation is the sequential part of a block step; as a separate launch it sat on the critical path.
-  if (t == 0) {
+  if (ii == 0) {
     __syncthreads();   // the tile is complete in global memory (visible to this CTA) and the operand buffers are free
     chol_diag_body(w, blockIdx.y, tt, dinv, status, k + 1, sm);
   }
@@ -1017,7 +1042,7 @@ int launch_cholesky(Ctx* ctx, const SolveWin* d_wins, int n_wins, int max_nt, do
     const int tb = nb_max - k - 1;
     chol_panel_kernel<<<dim3(tb, n_wins), 256, smem_panel, ctx->stream>>>(d_wins, d_tt, d_dinv, d_skip, k);
     mark();
-    chol_update_kernel<<<dim3(tb * (tb + 1) / 2, n_wins), 256, smem_update, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status,
+    chol_update_kernel<<<dim3(tb, n_wins), 256, smem_update, ctx->stream>>>(d_wins, d_tt, d_dinv, d_status,
                                                                                          d_skip, k);
     mark();
     ctx->launches += 2;
