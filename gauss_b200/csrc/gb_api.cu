@@ -340,13 +340,6 @@ int batch_plan_host(gb_batch* b, const int64_t* t_off, const int64_t* rows_t, co
           break;
         }
     }
-    b->h_wins_x = b->h_wins;
-    for (SolveWin& sw : b->h_wins_x) {   // X = L^-1 is laid out like B11 (n_t x ld_t, here row-major); outputs go to scratch
-      sw.n_u = sw.n_t;
-      sw.ld_u = sw.ld_t;
-      sw.off_ut = sw.off_tt;
-      sw.off_u = sw.off_t;
-    }
   }
   return GB_OK;
 }
@@ -463,14 +456,12 @@ int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
     }
   }
   if (b->ozaki) {
-    if ((rc = dev_upload(b, &b->d_wins_x, b->h_wins_x))) return rc;
     uint8_t* tmp = nullptr;
     if ((rc = dev_upload(b, &tmp, b->h_oz_wins))) return rc;
     b->d_oz_wins = tmp;
     if ((rc = dev_upload(b, &tmp, b->h_oz_tiles))) return rc;
     b->d_oz_tiles = tmp;
     if ((rc = dev_alloc(b, &b->d_oz_y, (size_t)b->n_t_total))) return rc;
-    if ((rc = dev_alloc(b, &b->d_oz_scr, 2 * (size_t)b->n_t_total))) return rc;
     if ((rc = dev_alloc(b, &b->d_oz_amax, b->h_wins.size()))) return rc;
     if ((rc = dev_alloc(b, &b->d_oz_ex, b->h_wins.size()))) return rc;
     if ((rc = dev_alloc(b, &b->d_oz_nan, (size_t)std::max<int64_t>(b->n_u_total, 1)))) return rc;
@@ -485,7 +476,7 @@ int batch_plan_device(gb_batch* b, Arena arena, bool sync) {
     sscanf(e, "%u:%u", &mask, &byte);
     const struct { void* p; size_t n; } bufs[] = {
         {b->d_x, s.oz_x}, {b->d_oz_pa, s.oz_pa}, {b->d_oz_pb, s.oz_pb}, {b->d_oz_y, sizeof(double) * (size_t)b->n_t_total},
-        {b->d_oz_scr, 2 * sizeof(double) * (size_t)b->n_t_total}, {b->d_ut, s.ut}, {b->d_tt, s.tt}, {b->d_dinv, s.dinv},
+        {nullptr, 0}, {b->d_ut, s.ut}, {b->d_tt, s.tt}, {b->d_dinv, s.dinv},
         {b->d_zu, s.zu}, {b->d_info, s.info}, {b->d_scratch, 0}};
     for (int i = 0; i < 10; i++)
       if ((mask >> i & 1) && bufs[i].p && bufs[i].n) cudaMemsetAsync(bufs[i].p, (int)byte, bufs[i].n, ctx->stream);

@@ -76,10 +76,8 @@ struct gb_batch {
   int oz_kpad = 0, oz_n_tiles = 0;
   long long oz_a_rows = 0, oz_b_rows = 0;
   std::vector<uint8_t> h_oz_wins, h_oz_tiles;
-  std::vector<gb::SolveWin> h_wins_x;       // the windows as the trtri-by-trsm sees them (n_u = n_t, X in place of W)
-  gb::SolveWin* d_wins_x = nullptr;
   void *d_oz_wins = nullptr, *d_oz_tiles = nullptr;
-  double *d_x = nullptr, *d_oz_y = nullptr, *d_oz_scr = nullptr;
+  double *d_x = nullptr, *d_oz_y = nullptr;
   int8_t *d_oz_pa = nullptr, *d_oz_pb = nullptr;
   uint8_t* d_oz_nan = nullptr;       // [n_u_total] rows of B21 the digit planes cannot represent (-> NaN results, as the doubles give)
   unsigned long long* d_oz_amax = nullptr;

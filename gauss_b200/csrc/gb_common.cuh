@@ -220,7 +220,6 @@ size_t ozaki_win_bytes();
 size_t ozaki_tile_bytes();
 void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, int n_ctas, void* ow_out, std::vector<uint8_t>* tiles_out, long long* a_rows,
                 long long* b_rows);
-int launch_ozaki_prepare_identity(Ctx* ctx, const SolveWin* d_wins, int n_wins, double* d_x);
 int launch_ozaki_solve(Ctx* ctx, const SolveWin* d_wins, const void* d_ow, const void* h_ow, int n_wins, const void* d_tiles,
                        int n_tiles, int kpad, const double* d_x, const double* d_ut, int slice_b21, int8_t* d_planes_a,
                        long long a_rows, int8_t* d_planes_b, long long b_rows, unsigned long long* d_amax, int* d_ex,

@@ -631,14 +631,6 @@ oz_slice_b_kernel(const SolveWin* __restrict__ wins, const OzWin* __restrict__ o
   }
 }
 
-// X := identity (the right-hand side of the trtri-by-trsm), row-major n_t x ld_t
-__global__ void oz_identity_kernel(const SolveWin* __restrict__ wins, double* X) {
-  const SolveWin w = wins[blockIdx.y];
-  const long long total = (long long)w.n_t * w.ld_t;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x)
-    X[w.off_tt + i] = (i / w.ld_t) == (i % w.ld_t) ? 1.0 : 0.0;
-}
-
 }  // namespace
 
 int make_row_tensor_map(Ctx* ctx, CUtensorMap* out, const void* base, int64_t n_rows, int64_t k_elems,
@@ -708,15 +700,7 @@ void ozaki_plan(const SolveWin* wins, int n_wins, int kpad, int n_ctas, void* ow
   *b_rows = br;
 }
 
-// Device side of the solve: X = L^-1 by the caller (trsm on identity), then slicing + the GEMM.
-int launch_ozaki_prepare_identity(Ctx* ctx, const SolveWin* d_wins, int n_wins, double* d_x) {
-  if (n_wins == 0) return GB_OK;
-  oz_identity_kernel<<<dim3(64, (unsigned)n_wins), 256, 0, ctx->stream>>>(d_wins, d_x);
-  GB_CUDA(cudaGetLastError());
-  ctx->launches++;
-  return GB_OK;
-}
-
+// Device side of the solve: X = L^-1 and y come from the factorisation stage (linv_row_kernel); slicing + the GEMM here.
 void ozaki_tile_rows(const void* h_ow, int win, long long* a_row0, int* ra) {
   const OzWin& o = static_cast<const OzWin*>(h_ow)[win];
   *a_row0 = o.a_row0;
